@@ -1,0 +1,118 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Builds the reference's own src/whisper.cpp (textually included from /root/reference at
+// compile time, nothing is copied into this repository) into oracle/_ref/libwhisper_ref.so and
+// adds a few `wref_*` taps so the parity tests can read the reference's intermediates:
+//
+//   mel spectrogram            whisper_state::mel            (src/whisper.cpp:414-420, 3178-3272)
+//   conv stem output           whisper_state::embd_conv      (src/whisper.cpp:1982-2042)
+//   encoder output             whisper_state::embd_enc       (src/whisper.cpp:2044-2275)
+//   cross / self KV caches     whisper_state::kv_cross/self  (src/whisper.cpp:2278-2354, 2567-2599)
+//   logits filter + sampler    whisper_process_logits / whisper_sample_token (src/whisper.cpp:6196-6543)
+//   block (de)quantisers       ggml_quantize_chunk / type traits (ggml/src/ggml-quants.c)
+//
+// The whisper.h API of the reference is exported unchanged by the same library.
+
+#ifndef REF_WHISPER_CPP
+#error "REF_WHISPER_CPP must point at <reference>/src/whisper.cpp"
+#endif
+
+#include REF_WHISPER_CPP
+
+#include <cstdint>
+#include <cstring>
+
+extern "C" {
+
+#define WREF_API __attribute__((visibility("default")))
+
+// ---- mel -------------------------------------------------------------------------------------
+WREF_API int wref_mel_n_len(struct whisper_state * st)     { return st->mel.n_len; }
+WREF_API int wref_mel_n_len_org(struct whisper_state * st) { return st->mel.n_len_org; }
+WREF_API int wref_mel_n_mel(struct whisper_state * st)     { return st->mel.n_mel; }
+WREF_API int wref_mel_copy(struct whisper_state * st, float * out, int64_t cap) {
+    const int64_t n = (int64_t) st->mel.data.size();
+    if (n > cap) return -1;
+    memcpy(out, st->mel.data.data(), n*sizeof(float));
+    return 0;
+}
+
+WREF_API struct whisper_state * wref_ctx_state(struct whisper_context * ctx) { return ctx->state; }
+
+// ---- tensors living in the per-graph compute buffers -------------------------------------------
+static int64_t tensor_copy_f32(struct ggml_tensor * t, float * out, int64_t cap) {
+    if (!t) return -1;
+    const int64_t n = ggml_nelements(t);
+    if (!out) return n;
+    if (n > cap || t->type != GGML_TYPE_F32) return -2;
+    ggml_backend_tensor_get(t, out, 0, n*sizeof(float));
+    return n;
+}
+
+// embd_conv: ne = [n_ctx, n_state] (time fastest)           src/whisper.cpp:2012-2024
+WREF_API int64_t wref_embd_conv(struct whisper_state * st, float * out, int64_t cap) { return tensor_copy_f32(st->embd_conv, out, cap); }
+// embd_enc : ne = [n_state, n_ctx] (feature fastest)        src/whisper.cpp:2245-2259
+WREF_API int64_t wref_embd_enc (struct whisper_state * st, float * out, int64_t cap) { return tensor_copy_f32(st->embd_enc,  out, cap); }
+
+// raw F16 KV caches; returns number of f16 elements
+static int64_t kv_copy(struct ggml_tensor * t, uint16_t * out, int64_t cap) {
+    const int64_t n = ggml_nelements(t);
+    if (!out) return n;
+    if (n > cap || t->type != GGML_TYPE_F16) return -2;
+    ggml_backend_tensor_get(t, out, 0, n*sizeof(uint16_t));
+    return n;
+}
+WREF_API int64_t wref_kv_cross_k(struct whisper_state * st, uint16_t * out, int64_t cap) { return kv_copy(st->kv_cross.k, out, cap); }
+WREF_API int64_t wref_kv_cross_v(struct whisper_state * st, uint16_t * out, int64_t cap) { return kv_copy(st->kv_cross.v, out, cap); }
+WREF_API int64_t wref_kv_self_k (struct whisper_state * st, uint16_t * out, int64_t cap) { return kv_copy(st->kv_self.k,  out, cap); }
+WREF_API int64_t wref_kv_self_v (struct whisper_state * st, uint16_t * out, int64_t cap) { return kv_copy(st->kv_self.v,  out, cap); }
+WREF_API int     wref_kv_self_size(struct whisper_state * st) { return (int) st->kv_self.size; }
+
+// ---- logits filter + greedy sampler on injected logits ----------------------------------------
+// history: token ids already in decoder.sequence.tokens; has_ts/seek_delta as whisper_decoder fields.
+// logits_in: raw [n_vocab] logits (as state.logits row).  Outputs are the three per-decoder arrays
+// after whisper_process_logits, and the greedy whisper_sample_token result.
+WREF_API int wref_process_logits(
+        struct whisper_context * ctx, struct whisper_state * st, const struct whisper_full_params * params,
+        const whisper_token * history, int n_history, int has_ts, int seek_delta, float temperature,
+        const float * logits_in, float * logits_out, float * logprobs_out, float * probs_out,
+        whisper_token_data * sampled) {
+    const int n_vocab = ctx->vocab.n_vocab;
+    auto & dec = st->decoders[0];
+    dec.sequence.tokens.clear();
+    for (int i = 0; i < n_history; ++i) {
+        whisper_token_data td = { history[i], 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, -1, 0.0f };
+        dec.sequence.tokens.push_back(td);
+    }
+    dec.has_ts     = has_ts != 0;
+    dec.seek_delta = seek_delta;
+    dec.i_batch    = 0;
+    dec.grammar    = {};
+    st->logits.assign(logits_in, logits_in + n_vocab);
+    whisper_process_logits(*ctx, *st, dec, *params, temperature);
+    if (logits_out)   memcpy(logits_out,   dec.logits.data(),   n_vocab*sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), n_vocab*sizeof(float));
+    if (probs_out)    memcpy(probs_out,    dec.probs.data(),    n_vocab*sizeof(float));
+    if (sampled)      *sampled = whisper_sample_token(*ctx, dec, true);
+    return 0;
+}
+
+// ---- block quantisers (ggml/src/ggml-quants.c) ------------------------------------------------
+WREF_API int64_t wref_row_size(int type, int64_t n_per_row) { return (int64_t) ggml_row_size((ggml_type) type, n_per_row); }
+WREF_API int64_t wref_quantize(int type, const float * src, void * dst, int64_t nrows, int64_t n_per_row) {
+    return (int64_t) ggml_quantize_chunk((ggml_type) type, src, dst, 0, nrows, n_per_row, nullptr);
+}
+WREF_API int wref_dequantize(int type, const void * src, float * dst, int64_t n) {
+    const auto * tr = ggml_get_type_traits((ggml_type) type);
+    if (!tr || !tr->to_float) return -1;
+    tr->to_float(src, dst, n);
+    return 0;
+}
+// GELU exactly as the CPU backend evaluates it (F16 table, ggml/src/ggml-cpu/vec.h:988-1001)
+WREF_API float wref_fp16_round(float x) { return ggml_fp16_to_fp32(ggml_fp32_to_fp16(x)); }
+
+WREF_API int wref_sizeof_full_params(void)    { return (int) sizeof(struct whisper_full_params); }
+WREF_API int wref_sizeof_context_params(void) { return (int) sizeof(struct whisper_context_params); }
+WREF_API int wref_sizeof_token_data(void)     { return (int) sizeof(whisper_token_data); }
+
+} // extern "C"

@@ -1,0 +1,44 @@
+// wb_common.h -- error reporting, launch accounting and small RAII helpers shared by the engine sources.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace wb {
+
+// thread-local last-error text (exposed through wb200_last_error)
+void set_error(const char * fmt, ...) __attribute__((format(printf, 1, 2)));
+const char * last_error();
+
+// every kernel launch issued by this library bumps this counter (bench.py reports it as gpu_launches)
+void     count_launch(uint64_t n = 1);
+uint64_t launch_count();
+
+// logging through the whisper_log_set callback (default: stderr)
+enum LogLevel { LOG_DEBUG = 1, LOG_INFO = 2, LOG_WARN = 3, LOG_ERROR = 4 };
+void logf(int level, const char * fmt, ...) __attribute__((format(printf, 2, 3)));
+
+#define WB_CUDA_OK(expr) \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ::wb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); return false; } } while (0)
+#define WB_CUDA_OKV(expr, rv) \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ::wb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); return rv; } } while (0)
+
+template <typename T> struct DevBuf {
+    T * p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete; DevBuf & operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    bool alloc(size_t count, bool zero = false) {
+        release();
+        if (count == 0) return true;
+        if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) { p = nullptr; set_error("cudaMalloc(%zu bytes) failed", count * sizeof(T)); return false; }
+        n = count;
+        if (zero && cudaMemset(p, 0, count * sizeof(T)) != cudaSuccess) { set_error("cudaMemset failed"); return false; }
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+} // namespace wb

@@ -1,0 +1,367 @@
+// wb_gemm.cu -- the tcgen05 GEMM used by every dense contraction of the encode path
+// (conv stem, encoder QKV/O/MLP, cross K/V, attention scores and PV in the unfused path, decoder prompt).
+//
+// One CTA computes a 128 (weight rows, TMEM lanes) x BN (activation rows, TMEM columns) tile:
+//   warp 0      : TMA producer   -- B tile (and A tile for f16 weights) into a STAGES-deep smem ring
+//   warp 1      : MMA issuer     -- one thread issues 4 x tcgen05.mma (K=16) per 64-wide k-block, commits to mbarriers
+//   warps 2..9  : quant decoders -- (quantised A only) each thread turns one 32-value block into 32 halves and
+//                                   stores them into the 128B-swizzled K-major operand tile;
+//                                   after the main loop the same warps run the epilogue (TMEM -> regs -> global)
+// Layout facts relied on (guides: blackwell_cuda_programming.md "UMMA", B300_MICROARCH.md "tcgen05"):
+//   * K-major SW128 tile: row r at byte r*128, 16-byte chunk c stored at chunk (c ^ (r & 7)); 8-row groups 1024 B apart
+//   * a warp may only tcgen05.ld the TMEM lane quarter (warp_id % 4)
+#include "wb_gemm.cuh"
+#include "wb_ptx.cuh"
+#include "wb_common.h"
+
+namespace wb {
+
+static constexpr int GEMM_THREADS  = 320;
+static constexpr int A_TILE_BYTES  = 128 * 64 * 2;
+
+template <int BN> struct GemmCfg {
+    static constexpr int B_TILE_BYTES = BN * 64 * 2;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int SMEM   = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmKParams {
+    int M, N, K, taps, nkb_per_tap, nb0;
+    int a_batched;
+    // quantised A
+    const void * a_base; const uint8_t * a_qs; const uint32_t * a_qh; const __half * a_d;
+    GemmEpilogue ep;
+};
+
+__device__ __forceinline__ float gelu_ref_f16(float x) {
+    // ggml CPU: table lookup on the f16-rounded input, table entries are f16(gelu(f32(x16)))  (vec.h:988-1001, ggml-cpu.c:3847)
+    if (x <= -10.0f) return 0.0f;
+    if (x >=  10.0f) return x;
+    const float xh = __half2float(__float2half_rn(x));
+    const float g  = 0.5f*xh*(1.0f + tanhf(0.79788456080286535587989211986876f*xh*(1.0f + 0.044715f*xh*xh)));
+    return __half2float(__float2half_rn(g));
+}
+
+struct RawBlk { uint4 q0, q1; uint32_t qh; __half d; };
+
+template <int WT>
+__device__ __forceinline__ void raw_load(const GemmKParams & p, int m, int k, RawBlk & r, bool valid) {
+    if (!valid) { r.q0 = r.q1 = make_uint4(0, 0, 0, 0); r.qh = 0; r.d = __float2half(0.0f); return; }
+    const int64_t nblk = (int64_t) p.K >> 5;
+    const int64_t bi   = (int64_t) m * nblk + (k >> 5);
+    if (WT == WT_Q4_0 || WT == WT_Q5_0) {
+        r.q0 = __ldg(reinterpret_cast<const uint4 *>(p.a_qs) + bi);
+        if (WT == WT_Q5_0) r.qh = __ldg(p.a_qh + bi);
+        r.d = p.a_d[bi];
+    } else if (WT == WT_Q8_0) {
+        r.q0 = __ldg(reinterpret_cast<const uint4 *>(p.a_qs) + 2*bi);
+        r.q1 = __ldg(reinterpret_cast<const uint4 *>(p.a_qs) + 2*bi + 1);
+        r.d = p.a_d[bi];
+    }
+}
+
+template <int BN, int WT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr bool QUANT = (WT != WT_F16);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t * sA = smem;
+    uint8_t * sB = smem + STAGES * A_TILE_BYTES;
+    uint64_t * bars      = reinterpret_cast<uint64_t *>(sB + STAGES * Cfg::B_TILE_BYTES);
+    uint64_t * full_bar  = bars;
+    uint64_t * empty_bar = bars + STAGES;
+    uint64_t * accum_bar = bars + 2*STAGES;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2*STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128;
+    const int n0 = blockIdx.y * BN;
+    const int b0 = blockIdx.z % p.nb0;
+    const int b1 = blockIdx.z / p.nb0;
+    const int nkb = p.taps * p.nkb_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmB);
+        if (!QUANT) tma_prefetch_desc(&tmA);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], QUANT ? 1 + 8 : 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int tap = kb / p.nkb_per_tap;
+                const int k0  = (kb - tap * p.nkb_per_tap) * 64;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const uint32_t tx = Cfg::B_TILE_BYTES + (QUANT ? 0 : A_TILE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], tx);
+                const int z2 = p.taps > 1 ? tap : b0;
+                const int z3 = p.taps > 1 ? (int) blockIdx.z : b1;
+                tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, z2, z3);
+                if (!QUANT) {
+                    const int az2 = p.taps > 1 ? tap : (p.a_batched ? b0 : 0);
+                    const int az3 = p.a_batched ? (p.taps > 1 ? (int) blockIdx.z : b1) : 0;
+                    tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, m0, az2, az3);
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, BN);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_TILE_BYTES));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * Cfg::B_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // +32 bytes per K=16 step inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_f16_ss(tmem_base, adesc + 2*k, bdesc + 2*k, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ------------------------------------------------------------------ warps 2..9
+        const int pt = threadIdx.x - 64;           // 0..255
+        if (QUANT) {
+            const int row  = pt >> 1;
+            const int half = pt & 1;
+            const int m    = m0 + row;
+            const bool mval = m < p.M;
+            uint8_t * dst_row = sA + row * 128;
+            const int sw = row & 7;
+            int s = 0; uint32_t ph = 0;
+            if (WT == WT_Q4_K || WT == WT_Q5_K) {
+                constexpr int BLK = (WT == WT_Q4_K) ? 144 : 176;
+                const uint8_t * rowp = reinterpret_cast<const uint8_t *>(p.a_base) + (int64_t) m * (p.K >> 8) * BLK;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int k = kb * 64 + half * 32;
+                    uint4 o[4];
+                    if (mval && k < p.K) {
+                        dequant_kq_sub<WT == WT_Q5_K>(rowp + (int64_t) (k >> 8) * BLK, (k & 255) >> 5, o);
+                    } else {
+                        o[0] = o[1] = o[2] = o[3] = make_uint4(0, 0, 0, 0);
+                    }
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t * d = dst_row + s * A_TILE_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4 *>(d + (((half * 4 + c) ^ sw) << 4)) = o[c];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            } else {
+                RawBlk r0, r1, r2;
+                raw_load<WT>(p, m, half * 32,      r0, mval && (half * 32      < p.K) && 0 < nkb);
+                raw_load<WT>(p, m, 64 + half * 32, r1, mval && (64 + half * 32 < p.K) && 1 < nkb);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int k2 = (kb + 2) * 64 + half * 32;
+                    raw_load<WT>(p, m, k2, r2, mval && (kb + 2 < nkb) && (k2 < p.K));
+                    uint4 o[4];
+                    if (WT == WT_Q4_0)      dequant_q4_0(r0.q0, r0.d, o);
+                    else if (WT == WT_Q5_0) dequant_q5_0(r0.q0, r0.qh, r0.d, o);
+                    else                    dequant_q8_0(r0.q0, r0.q1, r0.d, o);
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t * d = dst_row + s * A_TILE_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4 *>(d + (((half * 4 + c) ^ sw) << 4)) = o[c];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    r0 = r1; r1 = r2;
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------ epilogue
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q    = warp & 3;                 // TMEM lane quarter this warp may read
+        const int hsel = (warp - 2) >> 2;          // which half of the columns
+        const int m    = m0 + q * 32 + lane;
+        const bool mval = m < p.M;
+        const GemmEpilogue & e = p.ep;
+        const float bias = (mval && e.bias_m)  ? e.bias_m[m]  : 0.0f;
+        const float scl  = ((mval && e.scale_m) ? e.scale_m[m] : 1.0f) * e.alpha;
+        const int64_t ooff = (int64_t) b0 * e.out_b0 + (int64_t) b1 * e.out_b1;
+        const int64_t roff = (int64_t) b0 * e.res_b0 + (int64_t) b1 * e.res_b1;
+        constexpr int CH = BN / 2 / 32;            // 32-column chunks per warp
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+            const int col = hsel * (BN / 2) + c * 32;
+            if (n0 + col >= p.N) break;            // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) col, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = (__uint_as_float(v[j]) + bias) * scl;
+                if (e.act == 1) x = gelu_ref_f16(x);
+                f[j] = x;
+            }
+            if (e.res) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + col + j;
+                    if (mval && n < p.N) f[j] += e.res[roff + (int64_t) n * e.ldr + m];
+                }
+            }
+            if (!e.out_mmajor) {
+                if (e.out_f16) {
+                    __half * o = reinterpret_cast<__half *>(e.out) + ooff;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + col + j;
+                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = __float2half_rn(f[j]);
+                    }
+                } else {
+                    float * o = reinterpret_cast<float *>(e.out) + ooff;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + col + j;
+                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = f[j];
+                    }
+                }
+            } else if (mval) {
+                const int nb = n0 + col;
+                const bool full = (nb + 32 <= p.N);
+                if (e.out_f16) {
+                    __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __half2 h0 = __floats2half2_rn(f[j], f[j+1]),   h1 = __floats2half2_rn(f[j+2], f[j+3]);
+                            __half2 h2 = __floats2half2_rn(f[j+4], f[j+5]), h3 = __floats2half2_rn(f[j+6], f[j+7]);
+                            uint4 u = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
+                                                 *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+                            *reinterpret_cast<uint4 *>(o + j) = u;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
+                    }
+                } else {
+                    float * o = reinterpret_cast<float *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
+                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j+1], f[j+2], f[j+3]);
+                    } else {
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = f[j];
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<BN>(tmem_base);
+}
+
+// =============================================================================================== host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void * p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+bool make_tmap_f16(CUtensorMap * out, const void * base, uint64_t k, uint64_t rows, uint64_t z2, uint64_t z3,
+                   uint64_t stride_rows, uint64_t stride_z2, uint64_t stride_z3, uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t dims[4]    = { k, rows, z2 ? z2 : 1, z3 ? z3 : 1 };
+    cuuint64_t strides[3] = { stride_rows * 2, (stride_z2 ? stride_z2 : stride_rows * rows) * 2,
+                              (stride_z3 ? stride_z3 : stride_rows * rows * (z2 ? z2 : 1)) * 2 };
+    cuuint32_t box[4]     = { 64, box_rows, 1, 1 };
+    cuuint32_t estr[4]    = { 1, 1, 1, 1 };
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
+        set_error("make_tmap_f16: base/strides must be 16-byte aligned (base=%p strides=%llu,%llu,%llu)", base,
+                  (unsigned long long) strides[0], (unsigned long long) strides[1], (unsigned long long) strides[2]);
+        return false;
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int) r); return false; }
+    return true;
+}
+
+template <int BN, int WT>
+static cudaError_t launch_t(const GemmDesc & g, const GemmKParams & kp, cudaStream_t st) {
+    auto kern = gemm_kernel<BN, WT>;
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((g.M + 127) / 128, (g.N + BN - 1) / BN, g.nb0 * g.nb1);
+    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(kp, g.tmA, g.tmB);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int WT>
+static cudaError_t launch_bn(const GemmDesc & g, const GemmKParams & kp, cudaStream_t st) {
+    switch (g.BN) {
+        case 64:  return launch_t<64,  WT>(g, kp, st);
+        case 128: return launch_t<128, WT>(g, kp, st);
+        case 256: return launch_t<256, WT>(g, kp, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
+    GemmKParams kp;
+    kp.M = g.M; kp.N = g.N; kp.K = g.K; kp.taps = g.taps; kp.nkb_per_tap = (g.K + 63) / 64; kp.nb0 = g.nb0;
+    kp.a_batched = g.a_batched;
+    kp.a_base = g.A.base; kp.a_qs = g.A.qs; kp.a_qh = g.A.qh; kp.a_d = g.A.d;
+    kp.ep = g.ep;
+    switch (g.A.type) {
+        case WT_F16:  return launch_bn<WT_F16>(g, kp, st);
+        case WT_Q4_0: return launch_bn<WT_Q4_0>(g, kp, st);
+        case WT_Q5_0: return launch_bn<WT_Q5_0>(g, kp, st);
+        case WT_Q8_0: return launch_bn<WT_Q8_0>(g, kp, st);
+        case WT_Q4_K: return launch_bn<WT_Q4_K>(g, kp, st);
+        case WT_Q5_K: return launch_bn<WT_Q5_K>(g, kp, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace wb

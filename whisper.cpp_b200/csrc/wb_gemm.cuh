@@ -1,0 +1,55 @@
+// wb_gemm.cuh -- host-side description of one tcgen05 GEMM launch.
+//
+//   C[m][n] = sum_{tap} sum_{k} A[m][tap][k] * B[n][tap][k]            (both operands K-major, f16 in smem)
+//
+// "A" is the weight side: 128 rows per CTA land on the 128 TMEM lanes.  It is either an f16 matrix fetched by TMA
+// or a quantised matrix (planar Q4_0/Q5_0/Q8_0, verbatim Q4_K/Q5_K) whose 32-value blocks are decoded to f16 by
+// the producer warps straight into the 128-byte-swizzled operand tile.
+// "B" is the activation side (tokens / time steps / queries): BN rows per CTA fetched by TMA.
+// This replaces ggml_mul_mat (ggml/src/ggml-cpu/ggml-cpu.c:1254-1452) + the separate add/scale/gelu/cpy nodes the
+// reference graphs attach to it (src/whisper.cpp:2119-2123, 2225-2239, 2309-2346, 2012-2020).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "wb_quant.cuh"
+
+namespace wb {
+
+struct GemmEpilogue {
+    const float * bias_m  = nullptr;  // [M] added first
+    const float * scale_m = nullptr;  // [M] multiplies (acc + bias)
+    float alpha = 1.0f;               // scalar factor applied with scale_m
+    int   act   = 0;                  // 1: GELU with the reference's f16-table semantics (ggml-cpu/vec.h:988-1001)
+    const float * res = nullptr;      // residual, f32, indexed res[n*ldr + m] (+ batch strides), added last
+    int64_t ldr = 0;
+    void *  out = nullptr;            // f32 or f16
+    int     out_f16 = 0;
+    int     out_mmajor = 0;           // 0: out[n*ldo + m]   1: out[m*ldo + n]
+    int64_t ldo = 0;
+    int64_t out_b0 = 0, out_b1 = 0;   // element strides of the two batch indices
+    int64_t res_b0 = 0, res_b1 = 0;
+    int     n_row_off = 0;            // written row index = n + n_row_off (used to leave a padding row in front)
+};
+
+struct GemmDesc {
+    int M = 0, N = 0, K = 0;          // K per tap
+    int taps = 1;                     // 3 for the conv stem (tap is TMA dim 2 of both operands)
+    int BN = 128;                     // 64 / 128 / 256
+    int nb0 = 1, nb1 = 1;             // batch extents (blockIdx.z = b1*nb0 + b0); with taps==1 b0 is TMA dim 2, b1 dim 3
+    QMat A;                           // weight side; type WT_F16 => tmA used
+    int  a_batched = 0;               // f16 A only: 1 = A tensor map also takes the batch coordinates (attention)
+    CUtensorMap tmA;                  // valid when A.type == WT_F16
+    CUtensorMap tmB;
+    GemmEpilogue ep;
+};
+
+// 4-D tensor map over f16 data: dims {k, rows, z2, z3}; strides in ELEMENTS for dims 1..3; box = {64, box_rows, 1, 1};
+// 128-byte swizzle.  Returns false (and sets wb error text) on failure.
+bool make_tmap_f16(CUtensorMap * out, const void * base, uint64_t k, uint64_t rows, uint64_t z2, uint64_t z3,
+                   uint64_t stride_rows, uint64_t stride_z2, uint64_t stride_z3, uint32_t box_rows);
+
+// enqueue on `stream`; returns cudaError
+cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t stream);
+
+} // namespace wb
