@@ -1,0 +1,188 @@
+"""oracle/ref_numpy.py -- TEST INFRASTRUCTURE ONLY.  NumPy restatement of the reference arithmetic on the hot path.
+
+Nothing under whisper.cpp_b200/ imports this module; only tests/, bench.py's cpu_baseline leg and
+__graft_entry__.smoke() do, and only as a checker.
+
+Pinning: every function here is checked in tests/test_oracle_cpu.py against the UNMODIFIED reference built from
+/root/reference (oracle/_ref/libwhisper_ref.so): block decoders against ggml's own `to_float` traits, the Q8_0
+activation quantiser + integer dot against ggml_quantize_chunk output, log-mel against `whisper_pcm_to_mel`, the
+logits filter against `whisper_process_logits`.  The reference ships no numeric golden vectors for this path
+(SURVEY.md section 8c), so the compiled reference is the pin.
+
+Citations are file:line in ggml-org/whisper.cpp @ 233fe1fc.
+"""
+import numpy as np
+
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K = 0, 1, 2, 6, 8, 12, 13
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# block formats  (ggml/src/ggml-common.h:194-356, ggml/src/ggml-quants.c:459-567, 880-887, 1529-1551, 1731-1756)
+# ----------------------------------------------------------------------------------------------------------------------
+def _f16(b):
+    return np.frombuffer(np.ascontiguousarray(b).tobytes(), dtype=np.float16).astype(np.float32)
+
+
+def dequantize(wtype, raw, rows, k):
+    """file bytes -> float32 [rows][k]; exact f32 arithmetic as dequantize_row_*"""
+    raw = np.frombuffer(raw, dtype=np.uint8)
+    if wtype == F16:
+        return np.frombuffer(raw.tobytes(), dtype=np.float16).astype(np.float32).reshape(rows, k)
+    if wtype == F32:
+        return np.frombuffer(raw.tobytes(), dtype=np.float32).reshape(rows, k).copy()
+    if wtype in (Q4_0, Q5_0, Q8_0):
+        bs = {Q4_0: 18, Q5_0: 22, Q8_0: 34}[wtype]
+        blk = raw.reshape(-1, bs)
+        d = _f16(blk[:, 0:2]).reshape(-1, 1)
+        if wtype == Q8_0:
+            q = blk[:, 2:34].view(np.int8).astype(np.float32)
+            return (q * d).reshape(rows, k)
+        if wtype == Q4_0:
+            qs = blk[:, 2:18]
+            lo = (qs & 0xF).astype(np.int32) - 8
+            hi = (qs >> 4).astype(np.int32) - 8
+            return (np.concatenate([lo, hi], axis=1).astype(np.float32) * d).reshape(rows, k)
+        qh = blk[:, 2:6].copy().view(np.uint32).reshape(-1, 1)
+        qs = blk[:, 6:22]
+        bits = (qh >> np.arange(32, dtype=np.uint32)[None, :]) & 1
+        lo = ((qs & 0xF).astype(np.int32) | (bits[:, :16].astype(np.int32) << 4)) - 16
+        hi = ((qs >> 4).astype(np.int32) | (bits[:, 16:].astype(np.int32) << 4)) - 16
+        return (np.concatenate([lo, hi], axis=1).astype(np.float32) * d).reshape(rows, k)
+    if wtype in (Q4_K, Q5_K):
+        bs = 144 if wtype == Q4_K else 176
+        blk = raw.reshape(-1, bs)
+        d = _f16(blk[:, 0:2]); dmin = _f16(blk[:, 2:4])
+        sc8 = blk[:, 4:16].astype(np.int32)
+        sc = np.empty((blk.shape[0], 8), np.int32); mn = np.empty_like(sc)
+        for j in range(8):                                   # get_scale_min_k4
+            if j < 4:
+                sc[:, j] = sc8[:, j] & 63; mn[:, j] = sc8[:, j + 4] & 63
+            else:
+                sc[:, j] = (sc8[:, j + 4] & 0xF) | ((sc8[:, j - 4] >> 6) << 4)
+                mn[:, j] = (sc8[:, j + 4] >> 4) | ((sc8[:, j] >> 6) << 4)
+        qoff = 16 + (32 if wtype == Q5_K else 0)
+        qs = blk[:, qoff:qoff + 128].astype(np.int32)
+        out = np.empty((blk.shape[0], 256), np.float32)
+        for j in range(8):
+            q = (qs[:, 32 * (j // 2):32 * (j // 2) + 32] >> (4 * (j & 1))) & 0xF
+            if wtype == Q5_K:
+                q = q | (((blk[:, 16:48].astype(np.int32) >> j) & 1) << 4)
+            d1 = (d * sc[:, j].astype(np.float32)).astype(np.float32)[:, None]
+            m1 = (dmin * mn[:, j].astype(np.float32)).astype(np.float32)[:, None]
+            out[:, 32 * j:32 * j + 32] = d1 * q.astype(np.float32) - m1
+        return out.reshape(rows, k)
+    raise ValueError(wtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU mul_mat on quantised weights: activations -> Q8_0, integer dot per block
+# (ggml-cpu/ggml-cpu.c:1181-1357; quantize_row_q8_0 AVX2 form ggml-cpu/arch/x86/quants.c; vec_dot ggml-cpu/quants.c:365-406)
+# ----------------------------------------------------------------------------------------------------------------------
+def quantize_q8_0(x):
+    x = np.asarray(x, np.float32).reshape(-1, 32)
+    amax = np.abs(x).max(axis=1, keepdims=True)
+    d = (amax / np.float32(127.0)).astype(np.float32)
+    idv = np.where(amax != 0, np.float32(127.0) / np.where(amax != 0, amax, 1), 0).astype(np.float32)
+    q = np.rint(x * idv).astype(np.int32)                     # _MM_ROUND_NEAREST = ties to even
+    return q, d.astype(np.float16).astype(np.float32)
+
+
+def _block_ints(wtype, raw):
+    raw = np.frombuffer(raw, dtype=np.uint8)
+    bs = {Q4_0: 18, Q5_0: 22, Q8_0: 34}[wtype]
+    blk = raw.reshape(-1, bs)
+    d = _f16(blk[:, 0:2])
+    if wtype == Q8_0:
+        return blk[:, 2:34].view(np.int8).astype(np.int32), d
+    if wtype == Q4_0:
+        qs = blk[:, 2:18]
+        return np.concatenate([(qs & 0xF).astype(np.int32) - 8, (qs >> 4).astype(np.int32) - 8], axis=1), d
+    qh = blk[:, 2:6].copy().view(np.uint32).reshape(-1, 1)
+    qs = blk[:, 6:22]
+    bits = ((qh >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.int32)
+    lo = ((qs & 0xF).astype(np.int32) | (bits[:, :16] << 4)) - 16
+    hi = ((qs >> 4).astype(np.int32) | (bits[:, 16:] << 4)) - 16
+    return np.concatenate([lo, hi], axis=1), d
+
+
+def mul_mat_q(wtype, raw, rows, k, x):
+    """y[t][n] as ggml's CPU mul_mat computes it for Q4_0/Q5_0/Q8_0 weights (f32 sum over blocks in block order)."""
+    x = np.asarray(x, np.float32).reshape(-1, k)
+    wi, wd = _block_ints(wtype, raw)
+    wi = wi.reshape(rows, k // 32, 32); wd = wd.reshape(rows, k // 32)
+    out = np.empty((x.shape[0], rows), np.float32)
+    for t in range(x.shape[0]):
+        xq, xd = quantize_q8_0(x[t])
+        sumi = np.einsum("nbk,bk->nb", wi, xq.reshape(k // 32, 32)).astype(np.float32)
+        out[t] = (sumi * (wd * xd.reshape(1, -1))).astype(np.float32).sum(axis=1, dtype=np.float32)
+    return out
+
+
+def mul_mat_f16(raw, rows, k, x):
+    """F16 weights: activations rounded to f16, f32 accumulation (ggml-cpu.c vec_dot_f16)"""
+    w = np.frombuffer(raw, dtype=np.float16).astype(np.float32).reshape(rows, k)
+    xh = np.asarray(x, np.float32).reshape(-1, k).astype(np.float16).astype(np.float32)
+    return (xh.astype(np.float64) @ w.astype(np.float64).T).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# element-wise pieces
+# ----------------------------------------------------------------------------------------------------------------------
+def gelu(x):
+    """ggml_vec_gelu_f32 with GGML_GELU_FP16 (ggml-cpu/vec.h:46, 963-1001): f16 table lookup"""
+    x = np.asarray(x, np.float32)
+    xh = x.astype(np.float16).astype(np.float32)
+    g = np.float32(0.5) * xh * (np.float32(1.0) + np.tanh(np.float32(0.79788456080286535587989211986876) * xh *
+                                                         (np.float32(1.0) + np.float32(0.044715) * xh * xh)))
+    g = g.astype(np.float16).astype(np.float32)
+    return np.where(x <= -10, np.float32(0), np.where(x >= 10, x, g)).astype(np.float32)
+
+
+def layernorm(x, w, b, eps=1e-5):
+    """ggml_compute_forward_norm_f32 (ggml-cpu/ops.cpp:3698-3765) followed by mul + add (whisper.cpp:2108-2115)"""
+    x = np.asarray(x, np.float32)
+    mean = x.mean(axis=-1, keepdims=True, dtype=np.float32)
+    y = x - mean
+    var = (y * y).mean(axis=-1, keepdims=True, dtype=np.float32)
+    return (y * (np.float32(1.0) / np.sqrt(var + np.float32(eps)))) * w + b
+
+
+def attention(q, k, v, scale, n_zero_keys=0):
+    """one head: softmax(scale * q k^T) v with `n_zero_keys` extra all-zero, UNMASKED keys (whisper.cpp:2148-2165)
+    q is rounded to f16 like the CPU flash-attn path (ggml-cpu/ops.cpp:8590); f64 accumulation here."""
+    qh = np.asarray(q, np.float32).astype(np.float16).astype(np.float64)
+    s = (qh @ np.asarray(k, np.float64).T) * scale
+    if n_zero_keys:
+        s = np.concatenate([s, np.zeros((s.shape[0], n_zero_keys))], axis=1)
+        v = np.concatenate([np.asarray(v, np.float64), np.zeros((n_zero_keys, v.shape[1]))], axis=0)
+    m = s.max(axis=1, keepdims=True)
+    p = np.exp(s - m)
+    return ((p @ np.asarray(v, np.float64)) / p.sum(axis=1, keepdims=True)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# log-mel spectrogram (src/whisper.cpp:3005-3272) in float64 -- "exact" version used to bound both implementations
+# ----------------------------------------------------------------------------------------------------------------------
+def log_mel(pcm, filters):
+    pcm = np.asarray(pcm, np.float64)
+    n = pcm.shape[0]
+    n_mel = filters.shape[0]
+    padded = np.zeros(n + 480000 + 400)
+    padded[200:200 + n] = pcm
+    n_reflect = min(200, max(0, n - 1))
+    if n_reflect:
+        padded[200 - n_reflect:200] = pcm[1:1 + n_reflect][::-1]
+    n_len = (padded.shape[0] - 400) // 160
+    n_eff = n + 200
+    n_comp = min(n_eff // 160 + 1, n_len)
+    hann = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(400) / 400))
+    mel = np.full((n_mel, n_len), -10.0)
+    idx = np.arange(400)[None, :] + 160 * np.arange(n_comp)[:, None]
+    frames = padded[idx]
+    valid = idx < n_eff
+    frames = np.where(valid, frames, 0.0) * hann[None, :]
+    spec = np.abs(np.fft.rfft(frames, axis=1)) ** 2
+    mel[:, :n_comp] = np.log10(np.maximum(filters.astype(np.float64) @ spec.T, 1e-10))
+    mmax = mel.max() - 8.0
+    mel = np.maximum(mel, mmax)
+    return ((mel + 4.0) / 4.0).astype(np.float32)

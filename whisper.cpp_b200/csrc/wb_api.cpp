@@ -1,0 +1,530 @@
+// wb_api.cpp -- the whisper.h C ABI (include/whisper_b200.h) except whisper_full* (wb_full.cpp):
+// context / state lifecycle, low-level mel/encode/decode entry points, tokenizer, language table, getters, timings.
+// Behavioural reference: src/whisper.cpp:3284-3332 (tokenizer), 3386-3557 (state), 3618-4323 (API bodies).
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <regex>
+#include <thread>
+#include "wb_state.h"
+#include "wb_kernels.cuh"
+
+using namespace wb;
+
+namespace wb {
+extern const char * const g_lang_codes[100];
+extern const char * const g_lang_names[100];
+void set_log_sink(void (*cb)(int, const char *, void *), void * ud);
+
+int64_t time_us() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------------- KV bookkeeping
+bool KvCells::find_slot(const int * pos, const int * seq, uint32_t n_tokens) {       // whisper.cpp:1019-1068
+    if (n_tokens > size) { set_error("kv: n_tokens=%u > n_ctx=%u", n_tokens, size); return false; }
+    uint32_t tested = 0;
+    for (;;) {
+        if (head + n_tokens > size) { tested += size - head; head = 0; continue; }
+        bool ok = true;
+        for (uint32_t i = 0; i < n_tokens; ++i) {
+            if (cells[head + i].pos >= 0) { ok = false; head += i + 1; tested += i + 1; break; }
+        }
+        if (ok) break;
+        if (tested >= size) return false;
+    }
+    for (uint32_t i = 0; i < n_tokens; ++i) { cells[head + i].pos = pos[i]; cells[head + i].seqs |= 1u << seq[i]; }
+    return true;
+}
+int KvCells::cell_max() const {                                                      // whisper.cpp:1071-1079
+    for (uint32_t i = size - 1; i > 0; --i) if (cells[i].pos >= 0 && cells[i].seqs) return (int) i + 1;
+    return 1;
+}
+void KvCells::seq_rm(int seq, int p0, int p1) {                                      // whisper.cpp:1091-1119
+    uint32_t new_head = size;
+    if (p0 < 0) p0 = 0;
+    if (p1 < 0) p1 = INT32_MAX;
+    for (uint32_t i = 0; i < size; ++i) {
+        Cell & c = cells[i];
+        if (c.pos >= p0 && c.pos < p1) {
+            if (seq < 0) c.seqs = 0;
+            else if (c.seqs & (1u << seq)) c.seqs &= ~(1u << seq);
+            else continue;
+            if (!c.seqs) { c.pos = -1; if (new_head == size) new_head = i; }
+        }
+    }
+    if (new_head != size) head = new_head;
+}
+void KvCells::seq_cp(int src, int dst, int p0, int p1) {                             // whisper.cpp:1121-1137
+    if (p0 < 0) p0 = 0;
+    if (p1 < 0) p1 = INT32_MAX;
+    head = 0;
+    for (auto & c : cells) if ((c.seqs & (1u << src)) && c.pos >= p0 && c.pos < p1) c.seqs |= 1u << dst;
+}
+
+// ---------------------------------------------------------------------------------------------------- engine glue
+bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset) {
+    const int64_t t0 = time_us();
+    const int n_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
+    if (st.eng.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.eng.n_mel, ctx.model.hp.n_mels); return false; }
+    const int seek = mel_offset;
+    if (!st.eng.encode(&seek, 1, n_ctx)) return false;
+    st.t_encode_us += time_us() - t0;
+    st.n_encode++;
+    return true;
+}
+
+bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens, const int * pos, const int * seq,
+                  const int8_t * want, int n_tokens) {
+    const int64_t t0 = time_us();
+    const int n_vocab = ctx.model.hp.n_vocab;
+    KvCells & kv = st.kv;
+    if (!kv.find_slot(pos, seq, (uint32_t) n_tokens)) { set_error("decode: no KV slot for %d tokens", n_tokens); return false; }
+    kv.n = (uint32_t) std::min<int>((int) kv.size, std::max(1, kv.cell_max()));      // padding 1 on this path (whisper.cpp:2884-2885)
+    const int n_kv = (int) kv.n;
+    std::vector<DecToken> rows(n_tokens);
+    std::vector<int> cells(n_tokens), nkv(n_tokens), idx((size_t) n_tokens * n_kv);
+    for (int j = 0; j < n_tokens; ++j) {
+        rows[j] = { tokens[j], pos[j], seq[j], st.slot, want[j] != 0 };
+        cells[j] = (int) kv.head + j;
+        int c = 0;
+        for (int i = 0; i < n_kv; ++i) {                                              // KQ_mask rule, whisper.cpp:2928-2938
+            const KvCells::Cell & cell = kv.cells[i];
+            if ((cell.seqs & (1u << seq[j])) && cell.pos <= pos[j]) idx[(size_t) j * n_kv + c++] = i;
+        }
+        nkv[j] = c;
+    }
+    st.logits.resize((size_t) n_tokens * n_vocab);
+    if (!st.eng.decode(rows.data(), n_tokens, cells.data(), idx.data(), n_kv, nkv.data(), st.logits.data())) return false;
+    const int64_t dt = time_us() - t0;
+    if (n_tokens == 1)      { st.t_decode_us += dt; st.n_decode++; }                  // whisper.cpp:2974-2983
+    else if (n_tokens < 16) { st.t_batchd_us += dt; st.n_batchd += n_tokens; }
+    else                    { st.t_prompt_us += dt; st.n_prompt += n_tokens; }
+    return true;
+}
+
+static std::vector<whisper_token> tokenize(const Vocab & vocab, const std::string & text) {   // whisper.cpp:3284-3332
+    std::vector<std::string> words;
+    {
+        std::string str = text;
+        static const std::regex re(R"('s|'t|'re|'ve|'m|'ll|'d| ?[[:alpha:]]+| ?[[:digit:]]+| ?[^\s[:alpha:][:digit:]]+|\s+(?!\S)|\s+)");
+        std::smatch mt;
+        while (std::regex_search(str, mt, re)) {
+            for (auto x : mt) words.push_back(x);
+            str = mt.suffix();
+        }
+    }
+    std::vector<whisper_token> out;
+    for (const auto & word : words) {
+        if (word.empty()) continue;
+        int i = 0; const int n = (int) word.size();
+        while (i < n) {
+            int j = n; bool found = false;
+            while (j > i) {
+                auto it = vocab.token_to_id.find(word.substr(i, j - i));
+                if (it != vocab.token_to_id.end()) { out.push_back(it->second); i = j; found = true; break; }
+                --j;
+            }
+            if (!found) { logf(LOG_ERROR, "unknown token\n"); ++i; }
+        }
+    }
+    return out;
+}
+
+} // namespace wb
+
+// =====================================================================================================================
+extern "C" {
+
+WB_EXPORT const char * whisper_version(void) { return "1.9.3-b200"; }
+
+WB_EXPORT struct whisper_context_params whisper_context_default_params(void) {       // whisper.cpp:3618-3634
+    struct whisper_context_params p;
+    memset(&p, 0, sizeof(p));
+    p.use_gpu = true; p.flash_attn = true; p.gpu_device = 0;
+    p.dtw_token_timestamps = false; p.dtw_aheads_preset = WHISPER_AHEADS_NONE; p.dtw_n_top = -1;
+    p.dtw_aheads.n_heads = 0; p.dtw_aheads.heads = nullptr; p.dtw_mem_size = 1024 * 1024 * 128;
+    return p;
+}
+WB_EXPORT struct whisper_context_params * whisper_context_default_params_by_ref(void) {
+    auto * p = new whisper_context_params(); *p = whisper_context_default_params(); return p;
+}
+WB_EXPORT void whisper_free_context_params(struct whisper_context_params * p) { delete p; }
+WB_EXPORT void whisper_free_params(struct whisper_full_params * p) { delete p; }
+
+// ---------------------------------------------------------------------------------------------------- init / free
+WB_EXPORT struct whisper_context * whisper_init_with_params_no_state(struct whisper_model_loader * loader, struct whisper_context_params params) {
+    if (!loader) return nullptr;
+    whisper_context * ctx = nullptr;
+    bool ok = false;
+    try {
+        if (!params.use_gpu) {
+            set_error("this engine runs on a B200 only: whisper_context_params.use_gpu=false is not supported (no CPU fallback)");
+        } else {
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+                set_error("no CUDA device available: libwhisper_b200 has no CPU fallback");
+            } else if (params.gpu_device < 0 || params.gpu_device >= ndev) {
+                set_error("gpu_device %d out of range (%d devices)", params.gpu_device, ndev);
+            } else {
+                if (params.flash_attn && params.dtw_token_timestamps) {
+                    logf(LOG_WARN, "%s: dtw_token_timestamps is not supported with flash_attn - disabling\n", __func__);
+                    params.dtw_token_timestamps = false;
+                }
+                ctx = new whisper_context();
+                ctx->params = params;
+                ctx->t_start_us = time_us();
+                ok = model_load(loader, ctx->model, ctx->vocab, params.gpu_device);
+                ctx->t_load_us = ctx->model.t_load_us;
+            }
+        }
+    } catch (const std::exception & e) {
+        set_error("exception during model load: %s", e.what());
+    } catch (...) {
+        set_error("unknown exception during model load");
+    }
+    loader->close(loader->context);                                                  // always, whisper.cpp:3750,3756
+    if (!ok) { logf(LOG_ERROR, "%s: failed to load model\n", __func__); delete ctx; return nullptr; }
+    return ctx;
+}
+
+WB_EXPORT struct whisper_context * whisper_init_from_file_with_params_no_state(const char * path_model, struct whisper_context_params params) {
+    if (!path_model) return nullptr;
+    logf(LOG_INFO, "%s: loading model from '%s'\n", __func__, path_model);
+    std::ifstream fin(path_model, std::ios::binary);
+    if (!fin) { set_error("failed to open '%s'", path_model); return nullptr; }
+    whisper_model_loader loader = {};
+    loader.context = &fin;
+    loader.read  = [](void * c, void * out, size_t n) -> size_t { auto * f = (std::ifstream *) c; f->read((char *) out, (std::streamsize) n); return (size_t) f->gcount(); };
+    loader.eof   = [](void * c) -> bool { return ((std::ifstream *) c)->eof(); };
+    loader.close = [](void * c) { ((std::ifstream *) c)->close(); };
+    whisper_context * ctx = whisper_init_with_params_no_state(&loader, params);
+    if (ctx) ctx->path_model = path_model;
+    return ctx;
+}
+
+WB_EXPORT struct whisper_context * whisper_init_from_buffer_with_params_no_state(void * buffer, size_t buffer_size, struct whisper_context_params params) {
+    struct Buf { const uint8_t * p; size_t size, off; } b = { (const uint8_t *) buffer, buffer_size, 0 };
+    logf(LOG_INFO, "%s: loading model from buffer\n", __func__);
+    whisper_model_loader loader = {};
+    loader.context = &b;
+    loader.read  = [](void * c, void * out, size_t n) -> size_t { auto * q = (Buf *) c; size_t k = std::min(n, q->size - q->off); memcpy(out, q->p + q->off, k); q->off += k; return k; };
+    loader.eof   = [](void * c) -> bool { auto * q = (Buf *) c; return q->off >= q->size; };
+    loader.close = [](void *) {};
+    return whisper_init_with_params_no_state(&loader, params);
+}
+
+WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx) {  // whisper.cpp:3386-3557
+    if (!ctx) return nullptr;
+    whisper_state * st = nullptr;
+    try {
+        st = new whisper_state();
+        int cap = 1;
+        if (const char * e = getenv("WB200_STATE_WINDOWS")) cap = std::max(1, atoi(e));
+        if (!st->eng.init(&ctx->model, cap)) { delete st; return nullptr; }
+        st->kv.reset((uint32_t) st->eng.n_cells);
+        st->kv_self_n_dec = 1;
+        st->decoders[0].rng = std::mt19937(0);
+    } catch (...) { set_error("whisper_init_state: allocation failed"); delete st; return nullptr; }
+    return st;
+}
+
+#define WB_INIT_WITH_STATE(call) \
+    whisper_context * ctx = call; if (!ctx) return nullptr; \
+    ctx->state = whisper_init_state(ctx); if (!ctx->state) { whisper_free(ctx); return nullptr; } return ctx;
+
+WB_EXPORT void whisper_free_state(struct whisper_state * st) { delete st; }
+WB_EXPORT void whisper_free(struct whisper_context * ctx) { if (ctx) { whisper_free_state(ctx->state); delete ctx; } }
+
+WB_EXPORT struct whisper_context * whisper_init_from_file_with_params(const char * path, struct whisper_context_params p)            { WB_INIT_WITH_STATE(whisper_init_from_file_with_params_no_state(path, p)) }
+WB_EXPORT struct whisper_context * whisper_init_from_buffer_with_params(void * b, size_t n, struct whisper_context_params p)           { WB_INIT_WITH_STATE(whisper_init_from_buffer_with_params_no_state(b, n, p)) }
+WB_EXPORT struct whisper_context * whisper_init_with_params(struct whisper_model_loader * l, struct whisper_context_params p)          { WB_INIT_WITH_STATE(whisper_init_with_params_no_state(l, p)) }
+WB_EXPORT struct whisper_context * whisper_init_from_file(const char * path)                      { return whisper_init_from_file_with_params(path, whisper_context_default_params()); }
+WB_EXPORT struct whisper_context * whisper_init_from_buffer(void * b, size_t n)                   { return whisper_init_from_buffer_with_params(b, n, whisper_context_default_params()); }
+WB_EXPORT struct whisper_context * whisper_init(struct whisper_model_loader * l)                  { return whisper_init_with_params(l, whisper_context_default_params()); }
+WB_EXPORT struct whisper_context * whisper_init_from_file_no_state(const char * path)             { return whisper_init_from_file_with_params_no_state(path, whisper_context_default_params()); }
+WB_EXPORT struct whisper_context * whisper_init_from_buffer_no_state(void * b, size_t n)          { return whisper_init_from_buffer_with_params_no_state(b, n, whisper_context_default_params()); }
+WB_EXPORT struct whisper_context * whisper_init_no_state(struct whisper_model_loader * l)         { return whisper_init_with_params_no_state(l, whisper_context_default_params()); }
+
+WB_EXPORT int whisper_ctx_init_openvino_encoder_with_state(struct whisper_context *, struct whisper_state *, const char *, const char *, const char *) { return 1; }
+WB_EXPORT int whisper_ctx_init_openvino_encoder(struct whisper_context *, const char *, const char *, const char *) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------- low-level pipeline
+WB_EXPORT int whisper_pcm_to_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * samples, int n_samples, int) {
+    if (!ctx || !st || (n_samples > 0 && !samples) || n_samples < 0) return -1;
+    const int64_t t0 = time_us();
+    if (!st->eng.pcm_to_mel(samples, n_samples)) { logf(LOG_ERROR, "%s: failed to compute mel spectrogram\n", __func__); return -1; }
+    st->t_mel_us += time_us() - t0;
+    return 0;
+}
+WB_EXPORT int whisper_pcm_to_mel(struct whisper_context * ctx, const float * samples, int n_samples, int n_threads) {
+    return ctx ? whisper_pcm_to_mel_with_state(ctx, ctx->state, samples, n_samples, n_threads) : -1;
+}
+WB_EXPORT int whisper_set_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * data, int n_len, int n_mel) {
+    if (!ctx || !st) return -1;
+    if (n_mel != ctx->model.n_filt_mel) { logf(LOG_ERROR, "%s: invalid number of mel bands: %d (expected %d)\n", __func__, n_mel, ctx->model.n_filt_mel); return -1; }
+    return st->eng.set_mel(data, n_len, n_mel) ? 0 : -1;
+}
+WB_EXPORT int whisper_set_mel(struct whisper_context * ctx, const float * data, int n_len, int n_mel) {
+    return ctx ? whisper_set_mel_with_state(ctx, ctx->state, data, n_len, n_mel) : -1;
+}
+WB_EXPORT int whisper_encode_with_state(struct whisper_context * ctx, struct whisper_state * st, int offset, int) {
+    if (!ctx || !st) return -1;
+    if (!encode_window(*ctx, *st, offset)) { logf(LOG_ERROR, "%s: failed to eval\n", __func__); return -1; }
+    return 0;
+}
+WB_EXPORT int whisper_encode(struct whisper_context * ctx, int offset, int n_threads) { return ctx ? whisper_encode_with_state(ctx, ctx->state, offset, n_threads) : -1; }
+
+WB_EXPORT int whisper_decode_with_state(struct whisper_context * ctx, struct whisper_state * st, const whisper_token * tokens, int n_tokens, int n_past, int) {
+    if (!ctx || !st || !tokens || n_tokens <= 0) return 1;
+    std::vector<int> pos(n_tokens), seq(n_tokens, 0); std::vector<int8_t> want(n_tokens, 0);
+    for (int i = 0; i < n_tokens; ++i) pos[i] = n_past + i;
+    want[n_tokens - 1] = 1;                                                          // whisper_batch_prep_legacy, whisper.cpp:511-523
+    st->kv.seq_rm(0, n_past, -1);
+    if (!decode_batch(*ctx, *st, tokens, pos.data(), seq.data(), want.data(), n_tokens)) { logf(LOG_ERROR, "%s: failed to eval\n", __func__); return 1; }
+    return 0;
+}
+WB_EXPORT int whisper_decode(struct whisper_context * ctx, const whisper_token * tokens, int n_tokens, int n_past, int n_threads) {
+    if (!ctx || !ctx->state) { logf(LOG_ERROR, "%s: ERROR state was not loaded.\n", __func__); return -1; }
+    return whisper_decode_with_state(ctx, ctx->state, tokens, n_tokens, n_past, n_threads);
+}
+WB_EXPORT float * whisper_get_logits(struct whisper_context * ctx) { return ctx->state->logits.data(); }
+WB_EXPORT float * whisper_get_logits_from_state(struct whisper_state * st) { return st->logits.data(); }
+
+// ---------------------------------------------------------------------------------------------------- tokenizer / languages
+WB_EXPORT int whisper_tokenize(struct whisper_context * ctx, const char * text, whisper_token * tokens, int n_max_tokens) {
+    const auto res = tokenize(ctx->vocab, text);
+    if (n_max_tokens < (int) res.size()) { logf(LOG_ERROR, "%s: too many resulting tokens: %d (max %d)\n", __func__, (int) res.size(), n_max_tokens); return -(int) res.size(); }
+    for (size_t i = 0; i < res.size(); ++i) tokens[i] = res[i];
+    return (int) res.size();
+}
+WB_EXPORT int whisper_token_count(struct whisper_context * ctx, const char * text) { return -whisper_tokenize(ctx, text, nullptr, 0); }
+WB_EXPORT int whisper_lang_max_id(void) { return 99; }
+WB_EXPORT int whisper_lang_id(const char * lang) {
+    if (lang) {
+        for (int i = 0; i < 100; ++i) if (!strcmp(lang, g_lang_codes[i])) return i;
+        for (int i = 0; i < 100; ++i) if (!strcmp(lang, g_lang_names[i])) return i;
+    }
+    logf(LOG_ERROR, "%s: unknown language '%s'\n", __func__, lang ? lang : "(null)");
+    return -1;
+}
+WB_EXPORT const char * whisper_lang_str(int id)      { if (id >= 0 && id < 100) return g_lang_codes[id]; logf(LOG_ERROR, "%s: unknown language id %d\n", __func__, id); return nullptr; }
+WB_EXPORT const char * whisper_lang_str_full(int id) { if (id >= 0 && id < 100) return g_lang_names[id]; logf(LOG_ERROR, "%s: unknown language id %d\n", __func__, id); return nullptr; }
+
+WB_EXPORT int whisper_lang_auto_detect_with_state(struct whisper_context * ctx, struct whisper_state * st, int offset_ms, int n_threads, float * lang_probs) {
+    const int seek = offset_ms / 10;                                                 // whisper.cpp:4047-4120
+    if (seek < 0) { logf(LOG_ERROR, "%s: offset %dms is before the start of the audio\n", __func__, offset_ms); return -1; }
+    if (seek >= st->eng.n_len_org) { logf(LOG_ERROR, "%s: offset %dms is past the end of the audio (%dms)\n", __func__, offset_ms, st->eng.n_len_org * 10); return -2; }
+    if (whisper_encode_with_state(ctx, st, seek, n_threads) != 0) return -6;
+    const whisper_token sot = ctx->vocab.token_sot;
+    if (whisper_decode_with_state(ctx, st, &sot, 1, 0, n_threads) != 0) return -7;
+    std::vector<std::pair<double, int>> li;
+    for (int id = 0; id < 100; ++id) {
+        const int tok = sot + 1 + id;
+        if (tok >= ctx->vocab.n_vocab) continue;
+        li.emplace_back(st->logits[tok], id);
+    }
+    if (li.empty()) return -7;
+    std::sort(li.begin(), li.end(), [](const std::pair<double, int> & a, const std::pair<double, int> & b) { return a.first > b.first; });
+    const double mx = li[0].first; double sum = 0.0;
+    for (auto & kv : li) { kv.first = exp(kv.first - mx); sum += kv.first; }
+    for (auto & kv : li) kv.first /= sum;
+    if (lang_probs) for (auto & kv : li) lang_probs[kv.second] = (float) kv.first;
+    return li[0].second;
+}
+WB_EXPORT int whisper_lang_auto_detect(struct whisper_context * ctx, int offset_ms, int n_threads, float * lang_probs) {
+    return whisper_lang_auto_detect_with_state(ctx, ctx->state, offset_ms, n_threads, lang_probs);
+}
+
+// ---------------------------------------------------------------------------------------------------- getters
+WB_EXPORT int whisper_n_len(struct whisper_context * ctx)              { return ctx->state->eng.n_len_org; }
+WB_EXPORT int whisper_n_len_from_state(struct whisper_state * st)      { return st->eng.n_len_org; }
+WB_EXPORT int whisper_n_vocab(struct whisper_context * ctx)            { return ctx->vocab.n_vocab; }
+WB_EXPORT int whisper_n_text_ctx(struct whisper_context * ctx)         { return ctx->model.hp.n_text_ctx; }
+WB_EXPORT int whisper_n_audio_ctx(struct whisper_context * ctx)        { return ctx->model.hp.n_audio_ctx; }
+WB_EXPORT int whisper_is_multilingual(struct whisper_context * ctx)    { return ctx->vocab.is_multilingual() ? 1 : 0; }
+WB_EXPORT int whisper_model_n_vocab(struct whisper_context * ctx)       { return ctx->model.hp.n_vocab; }
+WB_EXPORT int whisper_model_n_audio_ctx(struct whisper_context * ctx)   { return ctx->model.hp.n_audio_ctx; }
+WB_EXPORT int whisper_model_n_audio_state(struct whisper_context * ctx) { return ctx->model.hp.n_audio_state; }
+WB_EXPORT int whisper_model_n_audio_head(struct whisper_context * ctx)  { return ctx->model.hp.n_audio_head; }
+WB_EXPORT int whisper_model_n_audio_layer(struct whisper_context * ctx) { return ctx->model.hp.n_audio_layer; }
+WB_EXPORT int whisper_model_n_text_ctx(struct whisper_context * ctx)    { return ctx->model.hp.n_text_ctx; }
+WB_EXPORT int whisper_model_n_text_state(struct whisper_context * ctx)  { return ctx->model.hp.n_text_state; }
+WB_EXPORT int whisper_model_n_text_head(struct whisper_context * ctx)   { return ctx->model.hp.n_text_head; }
+WB_EXPORT int whisper_model_n_text_layer(struct whisper_context * ctx)  { return ctx->model.hp.n_text_layer; }
+WB_EXPORT int whisper_model_n_mels(struct whisper_context * ctx)        { return ctx->model.hp.n_mels; }
+WB_EXPORT int whisper_model_ftype(struct whisper_context * ctx)         { return ctx->model.hp.ftype; }
+WB_EXPORT int whisper_model_type(struct whisper_context * ctx)          { return ctx->model.mtype; }
+WB_EXPORT const char * whisper_model_type_readable(struct whisper_context * ctx) {
+    static const char * const names[] = { "unknown", "tiny", "base", "small", "medium", "large" };
+    const int t = ctx->model.mtype; return names[t >= 0 && t <= 5 ? t : 0];
+}
+WB_EXPORT const char * whisper_token_to_str(struct whisper_context * ctx, whisper_token token) {
+    auto it = ctx->vocab.id_to_token.find(token);
+    return it == ctx->vocab.id_to_token.end() ? "" : it->second.c_str();
+}
+WB_EXPORT whisper_token whisper_token_eot (struct whisper_context * ctx) { return ctx->vocab.token_eot; }
+WB_EXPORT whisper_token whisper_token_sot (struct whisper_context * ctx) { return ctx->vocab.token_sot; }
+WB_EXPORT whisper_token whisper_token_solm(struct whisper_context * ctx) { return ctx->vocab.token_solm; }
+WB_EXPORT whisper_token whisper_token_prev(struct whisper_context * ctx) { return ctx->vocab.token_prev; }
+WB_EXPORT whisper_token whisper_token_nosp(struct whisper_context * ctx) { return ctx->vocab.token_nosp; }
+WB_EXPORT whisper_token whisper_token_not (struct whisper_context * ctx) { return ctx->vocab.token_not; }
+WB_EXPORT whisper_token whisper_token_beg (struct whisper_context * ctx) { return ctx->vocab.token_beg; }
+WB_EXPORT whisper_token whisper_token_lang(struct whisper_context * ctx, int lang_id) { return ctx->vocab.token_sot + 1 + lang_id; }
+WB_EXPORT whisper_token whisper_token_translate (struct whisper_context * ctx) { return ctx->vocab.token_translate; }
+WB_EXPORT whisper_token whisper_token_transcribe(struct whisper_context * ctx) { return ctx->vocab.token_transcribe; }
+
+// ---------------------------------------------------------------------------------------------------- timings / diagnostics
+WB_EXPORT struct whisper_timings * whisper_get_timings(struct whisper_context * ctx) {
+    if (!ctx || !ctx->state) return nullptr;
+    const whisper_state & s = *ctx->state;
+    auto * t = new whisper_timings();
+    t->sample_ms = 1e-3f * s.t_sample_us / std::max(1, s.n_sample);
+    t->encode_ms = 1e-3f * s.t_encode_us / std::max(1, s.n_encode);
+    t->decode_ms = 1e-3f * s.t_decode_us / std::max(1, s.n_decode);
+    t->batchd_ms = 1e-3f * s.t_batchd_us / std::max(1, s.n_batchd);
+    t->prompt_ms = 1e-3f * s.t_prompt_us / std::max(1, s.n_prompt);
+    return t;
+}
+WB_EXPORT void whisper_print_timings(struct whisper_context * ctx) {
+    const int64_t t_end = time_us();
+    logf(LOG_INFO, "\n");
+    logf(LOG_INFO, "%s:     load time = %8.2f ms\n", __func__, ctx->t_load_us / 1000.0f);
+    if (ctx->state) {
+        const whisper_state & s = *ctx->state;
+        const int ns = std::max(1, s.n_sample), ne = std::max(1, s.n_encode), nd = std::max(1, s.n_decode), nb = std::max(1, s.n_batchd), np = std::max(1, s.n_prompt);
+        logf(LOG_INFO, "%s:     fallbacks = %3d p / %3d h\n", __func__, s.n_fail_p, s.n_fail_h);
+        logf(LOG_INFO, "%s:      mel time = %8.2f ms\n", __func__, s.t_mel_us / 1000.0f);
+        logf(LOG_INFO, "%s:   sample time = %8.2f ms / %5d runs ( %8.2f ms per run)\n", __func__, 1e-3f * s.t_sample_us, ns, 1e-3f * s.t_sample_us / ns);
+        logf(LOG_INFO, "%s:   encode time = %8.2f ms / %5d runs ( %8.2f ms per run)\n", __func__, 1e-3f * s.t_encode_us, ne, 1e-3f * s.t_encode_us / ne);
+        logf(LOG_INFO, "%s:   decode time = %8.2f ms / %5d runs ( %8.2f ms per run)\n", __func__, 1e-3f * s.t_decode_us, nd, 1e-3f * s.t_decode_us / nd);
+        logf(LOG_INFO, "%s:   batchd time = %8.2f ms / %5d runs ( %8.2f ms per run)\n", __func__, 1e-3f * s.t_batchd_us, nb, 1e-3f * s.t_batchd_us / nb);
+        logf(LOG_INFO, "%s:   prompt time = %8.2f ms / %5d runs ( %8.2f ms per run)\n", __func__, 1e-3f * s.t_prompt_us, np, 1e-3f * s.t_prompt_us / np);
+    }
+    logf(LOG_INFO, "%s:    total time = %8.2f ms\n", __func__, (t_end - ctx->t_start_us) / 1000.0f);
+}
+WB_EXPORT void whisper_reset_timings(struct whisper_context * ctx) {
+    ctx->t_start_us = time_us();
+    if (ctx->state) {
+        whisper_state & s = *ctx->state;
+        s.t_mel_us = s.t_sample_us = s.t_encode_us = s.t_decode_us = s.t_batchd_us = s.t_prompt_us = 0;
+        s.n_sample = s.n_encode = s.n_decode = s.n_batchd = s.n_prompt = 0;
+    }
+}
+WB_EXPORT const char * whisper_print_system_info(void) {
+    static std::string s;
+    s = "WHISPER_B200 : CUDA = 1 | ARCH = sm_100a | TCGEN05 = 1 | TMA = 1 | CPU_FALLBACK = 0 | ";
+    int ndev = 0; if (cudaGetDeviceCount(&ndev) == cudaSuccess) s += "DEVICES = " + std::to_string(ndev) + " | ";
+    return s.c_str();
+}
+WB_EXPORT void whisper_log_set(ggml_log_callback cb, void * user_data) {
+    set_log_sink(reinterpret_cast<void (*)(int, const char *, void *)>(cb), user_data);
+}
+WB_EXPORT int          whisper_bench_memcpy(int)           { logf(LOG_WARN, "whisper_bench_memcpy: ggml CPU micro-benchmark not available in this engine\n"); return 0; }
+WB_EXPORT const char * whisper_bench_memcpy_str(int)       { return "not supported by libwhisper_b200 (ggml CPU micro-benchmark)\n"; }
+WB_EXPORT int          whisper_bench_ggml_mul_mat(int)     { logf(LOG_WARN, "whisper_bench_ggml_mul_mat: ggml CPU micro-benchmark not available in this engine\n"); return 0; }
+WB_EXPORT const char * whisper_bench_ggml_mul_mat_str(int) { return "not supported by libwhisper_b200 (ggml CPU micro-benchmark)\n"; }
+
+// ---------------------------------------------------------------------------------------------------- results
+#define SEG(st, i) ((st)->result_all[(size_t) (i)])
+WB_EXPORT int whisper_full_n_segments_from_state(struct whisper_state * st) { return (int) st->result_all.size(); }
+WB_EXPORT int whisper_full_n_segments(struct whisper_context * ctx)         { return (int) ctx->state->result_all.size(); }
+WB_EXPORT int whisper_full_lang_id_from_state(struct whisper_state * st)    { return st->lang_id; }
+WB_EXPORT int whisper_full_lang_id(struct whisper_context * ctx)            { return ctx->state->lang_id; }
+WB_EXPORT int64_t whisper_full_get_segment_t0_from_state(struct whisper_state * st, int i) { return SEG(st, i).t0; }
+WB_EXPORT int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).t0; }
+WB_EXPORT int64_t whisper_full_get_segment_t1_from_state(struct whisper_state * st, int i) { return SEG(st, i).t1; }
+WB_EXPORT int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).t1; }
+WB_EXPORT bool whisper_full_get_segment_speaker_turn_next_from_state(struct whisper_state * st, int i) { return SEG(st, i).speaker_turn_next; }
+WB_EXPORT bool whisper_full_get_segment_speaker_turn_next(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).speaker_turn_next; }
+WB_EXPORT const char * whisper_full_get_segment_text_from_state(struct whisper_state * st, int i) { return SEG(st, i).text.c_str(); }
+WB_EXPORT const char * whisper_full_get_segment_text(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).text.c_str(); }
+WB_EXPORT float whisper_full_get_segment_no_speech_prob_from_state(struct whisper_state * st, int i) { return SEG(st, i).no_speech_prob; }
+WB_EXPORT float whisper_full_get_segment_no_speech_prob(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).no_speech_prob; }
+WB_EXPORT int whisper_full_n_tokens_from_state(struct whisper_state * st, int i) { return (int) SEG(st, i).tokens.size(); }
+WB_EXPORT int whisper_full_n_tokens(struct whisper_context * ctx, int i)         { return (int) SEG(ctx->state, i).tokens.size(); }
+WB_EXPORT const char * whisper_full_get_token_text_from_state(struct whisper_context * ctx, struct whisper_state * st, int i, int t) { return whisper_token_to_str(ctx, SEG(st, i).tokens[t].id); }
+WB_EXPORT const char * whisper_full_get_token_text(struct whisper_context * ctx, int i, int t) { return whisper_token_to_str(ctx, SEG(ctx->state, i).tokens[t].id); }
+WB_EXPORT whisper_token whisper_full_get_token_id_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].id; }
+WB_EXPORT whisper_token whisper_full_get_token_id(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].id; }
+WB_EXPORT whisper_token_data whisper_full_get_token_data_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t]; }
+WB_EXPORT whisper_token_data whisper_full_get_token_data(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t]; }
+WB_EXPORT int64_t whisper_full_get_token_t0_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].t0; }
+WB_EXPORT int64_t whisper_full_get_token_t0(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].t0; }
+WB_EXPORT int64_t whisper_full_get_token_t1_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].t1; }
+WB_EXPORT int64_t whisper_full_get_token_t1(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].t1; }
+WB_EXPORT float whisper_full_get_token_p_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].p; }
+WB_EXPORT float whisper_full_get_token_p(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].p; }
+
+WB_EXPORT int     whisper_full_n_vad_segments(struct whisper_context *)                       { return 0; }
+WB_EXPORT int     whisper_full_n_vad_segments_from_state(struct whisper_state *)              { return 0; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t0(struct whisper_context *, int)              { return 0; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t0_from_state(struct whisper_state *, int)     { return 0; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t1(struct whisper_context *, int)              { return 0; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t1_from_state(struct whisper_state *, int)     { return 0; }
+
+// ---------------------------------------------------------------------------------------------------- VAD (out of scope)
+WB_EXPORT struct whisper_vad_params whisper_vad_default_params(void) {               // whisper.cpp VAD defaults
+    whisper_vad_params p; p.threshold = 0.5f; p.min_speech_duration_ms = 250; p.min_silence_duration_ms = 100;
+    p.max_speech_duration_s = 3.4028235e38f; p.speech_pad_ms = 30; p.samples_overlap = 0.1f; return p;
+}
+WB_EXPORT struct whisper_vad_context_params whisper_vad_default_context_params(void) { whisper_vad_context_params p; p.n_threads = 4; p.use_gpu = false; p.gpu_device = 0; return p; }
+static void vad_unsupported(const char * fn) { logf(LOG_ERROR, "%s: Silero VAD is not part of libwhisper_b200 (SURVEY.md section 2: out of scope)\n", fn); }
+WB_EXPORT struct whisper_vad_context * whisper_vad_init_from_file_with_params(const char *, struct whisper_vad_context_params) { vad_unsupported(__func__); return nullptr; }
+WB_EXPORT struct whisper_vad_context * whisper_vad_init_with_params(struct whisper_model_loader * l, struct whisper_vad_context_params) { if (l && l->close) l->close(l->context); vad_unsupported(__func__); return nullptr; }
+WB_EXPORT bool    whisper_vad_detect_speech(struct whisper_vad_context *, const float *, int)          { return false; }
+WB_EXPORT bool    whisper_vad_detect_speech_no_reset(struct whisper_vad_context *, const float *, int) { return false; }
+WB_EXPORT void    whisper_vad_reset_state(struct whisper_vad_context *) {}
+WB_EXPORT int     whisper_vad_n_probs(struct whisper_vad_context *) { return 0; }
+WB_EXPORT float * whisper_vad_probs(struct whisper_vad_context *)   { return nullptr; }
+WB_EXPORT struct whisper_vad_segments * whisper_vad_segments_from_probs(struct whisper_vad_context *, struct whisper_vad_params) { return nullptr; }
+WB_EXPORT struct whisper_vad_segments * whisper_vad_segments_from_samples(struct whisper_vad_context *, struct whisper_vad_params, const float *, int) { return nullptr; }
+WB_EXPORT int   whisper_vad_segments_n_segments(struct whisper_vad_segments *)         { return 0; }
+WB_EXPORT float whisper_vad_segments_get_segment_t0(struct whisper_vad_segments *, int) { return 0.0f; }
+WB_EXPORT float whisper_vad_segments_get_segment_t1(struct whisper_vad_segments *, int) { return 0.0f; }
+WB_EXPORT void  whisper_vad_free_segments(struct whisper_vad_segments *) {}
+WB_EXPORT void  whisper_vad_free(struct whisper_vad_context *) {}
+
+// ---------------------------------------------------------------------------------------------------- engine extensions
+WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float * out, int64_t cap) {
+    if (!st) return -1;
+    Engine & E = st->eng;
+    const HParams & hp = E.m->hp;
+    if (cudaSetDevice(E.m->device) != cudaSuccess) return -1;
+    const int T = E.enc_n_ctx > 0 ? E.enc_n_ctx : hp.n_audio_ctx, d = hp.n_audio_state, Lt = hp.n_text_layer;
+    if (which == 0) {
+        const int64_t n = (int64_t) E.n_mel * E.n_len;
+        if (!out) return n;
+        if (n > cap) return -2;
+        return cudaMemcpy(out, E.mel.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? n : -3;
+    }
+    if (which == 1 || which == 2) {
+        const int64_t n = (int64_t) T * d;
+        if (!out) return n;
+        if (n > cap) return -2;
+        const float * src = which == 1 ? E.conv32.p : E.enc32.p;
+        if (!src) { set_error("wb200_read_tensor: set WB200_DEBUG_TAPS=1 before creating the state"); return -4; }
+        return cudaMemcpy(out, src, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? n : -3;
+    }
+    if (which == 3 || which == 4) {
+        const int64_t n = (int64_t) Lt * E.Tp_max * d;
+        if (!out) return n;
+        if (n > cap) return -2;
+        std::vector<__half> tmp((size_t) n);
+        const __half * src = E.kv_cross.p + (size_t) st->slot * 2 * n + (which == 4 ? n : 0);
+        if (cudaMemcpy(tmp.data(), src, (size_t) n * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+        for (int64_t i = 0; i < n; ++i) out[i] = __half2float(tmp[(size_t) i]);
+        return n;
+    }
+    return -5;
+}
+WB_EXPORT int wb200_last_encode_ms(struct whisper_state * st, float * out4) {
+    if (!st || !out4) return -1;
+    for (int i = 0; i < 4; ++i) out4[i] = st->eng.last_ms[i];
+    return 0;
+}
+WB_EXPORT const char * wb200_last_error(void) { return wb::last_error(); }
+WB_EXPORT uint64_t wb200_launch_count(void)   { return wb::launch_count(); }
+
+} // extern "C"

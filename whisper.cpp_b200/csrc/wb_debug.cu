@@ -50,4 +50,99 @@ int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const fl
     return 0;
 }
 
+
+
+// log-mel of a PCM buffer; mel_out [n_mel][n_len]; returns n_len (<0 on error)
+__attribute__((visibility("default")))
+int wb200_dbg_mel(const float * pcm, int n_samples, const float * filters, int n_mel, float * mel_out, int64_t cap) {
+    const int n_len = (n_samples + 480000) / 160;
+    if ((int64_t) n_mel * n_len > cap) return -1;
+    DevBuf<float> dp, df, dm, dg;
+    if (!dp.alloc(n_samples > 0 ? n_samples : 1) || !df.alloc((size_t) n_mel * 201) || !dm.alloc((size_t) n_mel * n_len) || !dg.alloc(4)) return -2;
+    WB_CUDA_OKV(cudaMemcpy(dp.p, pcm, (size_t) n_samples * 4, cudaMemcpyHostToDevice), -3);
+    WB_CUDA_OKV(cudaMemcpy(df.p, filters, (size_t) n_mel * 201 * 4, cudaMemcpyHostToDevice), -3);
+    mel_spectrogram(dp.p, n_samples, df.p, n_mel, dm.p, n_len, dg.p, 0);
+    WB_CUDA_OKV(cudaDeviceSynchronize(), -4);
+    WB_CUDA_OKV(cudaMemcpy(mel_out, dm.p, (size_t) n_mel * n_len * 4, cudaMemcpyDeviceToHost), -3);
+    return n_len;
+}
+
+__attribute__((visibility("default")))
+int wb200_dbg_layernorm(const float * x, const float * w, const float * b, float eps, int rows, int d, float * out32, uint16_t * out16) {
+    DevBuf<float> dx, dw, db, do32; DevBuf<__half> do16;
+    if (!dx.alloc((size_t) rows * d) || !dw.alloc(d) || !db.alloc(d) || !do32.alloc((size_t) rows * d) || !do16.alloc((size_t) rows * d)) return -1;
+    cudaMemcpy(dx.p, x, (size_t) rows * d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dw.p, w, (size_t) d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db.p, b, (size_t) d * 4, cudaMemcpyHostToDevice);
+    layernorm(dx.p, dw.p, db.p, eps, rows, d, do16.p, do32.p, 0);
+    WB_CUDA_OKV(cudaDeviceSynchronize(), -4);
+    cudaMemcpy(out32, do32.p, (size_t) rows * d * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out16, do16.p, (size_t) rows * d * 2, cudaMemcpyDeviceToHost);
+    return 0;
+}
+
+// y[t][n] via the decode GEMV; weights in FILE layout.  flags bit0 gelu, bit1 fused LayerNorm (ln_w, ln_b given)
+__attribute__((visibility("default")))
+int wb200_dbg_gemv(int wtype, int N, int K, int n_tok, const void * w_file, const float * x, const float * bias,
+                   const float * scale, const float * res, const float * ln_w, const float * ln_b, float * out, int flags) {
+    cudaStream_t st = 0;
+    const size_t wbytes = (size_t) ((double) N * K * wt_bpw(wtype) + 0.5);
+    DevBuf<uint8_t> wraw, planar; DevBuf<float> dx, dbias, dscale, dres, dlw, dlb, dout;
+    if (!wraw.alloc(wbytes) || !dx.alloc((size_t) n_tok * K) || !dout.alloc((size_t) n_tok * N)) return -1;
+    cudaMemcpy(wraw.p, w_file, wbytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(dx.p, x, (size_t) n_tok * K * 4, cudaMemcpyHostToDevice);
+    GemvArgs a;
+    if (wtype == WT_F16 || wt_is_kquant(wtype)) { a.W.type = wtype; a.W.N = N; a.W.K = K; a.W.base = wraw.p; }
+    else if (wt_is_block32(wtype)) { if (!planar.alloc(wbytes + 64)) return -1; if (!repack_block32(wtype, wraw.p, planar.p, N, K, &a.W, st)) return -4; }
+    else return -5;
+    if (bias)  { dbias.alloc(N);  cudaMemcpy(dbias.p, bias, (size_t) N * 4, cudaMemcpyHostToDevice); a.bias = dbias.p; }
+    if (scale) { dscale.alloc(N); cudaMemcpy(dscale.p, scale, (size_t) N * 4, cudaMemcpyHostToDevice); a.scale = dscale.p; }
+    if (res)   { dres.alloc((size_t) n_tok * N); cudaMemcpy(dres.p, res, (size_t) n_tok * N * 4, cudaMemcpyHostToDevice); a.res = dres.p; }
+    if (flags & 2) { dlw.alloc(K); dlb.alloc(K); cudaMemcpy(dlw.p, ln_w, (size_t) K * 4, cudaMemcpyHostToDevice); cudaMemcpy(dlb.p, ln_b, (size_t) K * 4, cudaMemcpyHostToDevice); a.ln_w = dlw.p; a.ln_b = dlb.p; }
+    a.x = dx.p; a.n_tok = n_tok; a.act = (flags & 1) ? 1 : 0; a.out = dout.p;
+    gemv(a, st);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("gemv: %s", cudaGetErrorString(e)); return -7; }
+    cudaMemcpy(out, dout.p, (size_t) n_tok * N * 4, cudaMemcpyDeviceToHost);
+    return 0;
+}
+
+// decode attention kernels.  kc/vc given as f16 bit patterns [n_cells][d]
+__attribute__((visibility("default")))
+int wb200_dbg_attn_self(const float * q, const uint16_t * kc, const uint16_t * vc, const int * idx, int ld_idx, const int * n_kv,
+                        int n_tok, int n_head, int n_cells, float * out) {
+    const int d = n_head * 64;
+    DevBuf<float> dq, dout; DevBuf<__half> dk, dv; DevBuf<int> di, dn;
+    dq.alloc((size_t) n_tok * d); dout.alloc((size_t) n_tok * d); dk.alloc((size_t) n_cells * d); dv.alloc((size_t) n_cells * d);
+    di.alloc((size_t) n_tok * ld_idx); dn.alloc(n_tok);
+    cudaMemcpy(dq.p, q, (size_t) n_tok * d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dk.p, kc, (size_t) n_cells * d * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dv.p, vc, (size_t) n_cells * d * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(di.p, idx, (size_t) n_tok * ld_idx * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dn.p, n_kv, (size_t) n_tok * 4, cudaMemcpyHostToDevice);
+    attn_self_decode(dq.p, d, dk.p, dv.p, di.p, ld_idx, dn.p, n_tok, n_head, d, dout.p, d, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("attn_self: %s", cudaGetErrorString(e)); return -7; }
+    cudaMemcpy(out, dout.p, (size_t) n_tok * d * 4, cudaMemcpyDeviceToHost);
+    return 0;
+}
+__attribute__((visibility("default")))
+int wb200_dbg_attn_cross(const float * q, const uint16_t * kc, const uint16_t * vc, int n_keys, int n_tok, int n_head, float scale, float * out) {
+    const int d = n_head * 64;
+    DevBuf<float> dq, dout, dpart; DevBuf<__half> dk, dv; DevBuf<int> dslot, dcnt;
+    dq.alloc((size_t) n_tok * d); dout.alloc((size_t) n_tok * d); dk.alloc((size_t) n_tok * n_keys * d); dv.alloc((size_t) n_tok * n_keys * d);
+    dpart.alloc((size_t) n_tok * n_head * 8 * 66); dslot.alloc(n_tok); dcnt.alloc((size_t) n_tok * n_head, true);
+    std::vector<int> slots(n_tok); for (int i = 0; i < n_tok; ++i) slots[i] = i;
+    cudaMemcpy(dslot.p, slots.data(), (size_t) n_tok * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dq.p, q, (size_t) n_tok * d * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dk.p, kc, (size_t) n_tok * n_keys * d * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dv.p, vc, (size_t) n_tok * n_keys * d * 2, cudaMemcpyHostToDevice);
+    for (int rep = 0; rep < 2; ++rep)   // twice: the second run checks that the arrival counters were reset
+        attn_cross_decode(dq.p, d, dk.p, dv.p, dslot.p, (int64_t) n_keys * d, n_keys, n_tok, n_head, d, scale, dpart.p, dcnt.p, dout.p, d, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("attn_cross: %s", cudaGetErrorString(e)); return -7; }
+    cudaMemcpy(out, dout.p, (size_t) n_tok * d * 4, cudaMemcpyDeviceToHost);
+    return 0;
+}
+
 } // extern "C"

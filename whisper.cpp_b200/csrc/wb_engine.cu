@@ -1,0 +1,285 @@
+// wb_engine.cu -- see wb_engine.h.  Graph structure follows whisper_build_graph_conv / _encoder / _cross / _decoder
+// (src/whisper.cpp:1982-2042, 2044-2275, 2278-2354, 2466-2844); every `ggml_mul_mat (+add/scale/gelu/cpy)` group of the
+// reference is one tcgen05 GEMM launch (encode) or one fused GEMV launch (decode step) here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "wb_engine.h"
+#include "wb_kernels.cuh"
+
+namespace wb {
+
+static inline int pad256(int n) { return (n + 255) / 256 * 256; }
+
+struct EncLayerPlan { GemmDesc qk, v, s, pv, o, fc1, fc2; };
+struct EncPlan {
+    int n_ctx = 0, n_win = 0;
+    GemmDesc conv1, conv2, conv2_tap, cross;
+    std::vector<EncLayerPlan> layers;
+};
+
+Engine::~Engine() {
+    if (m) cudaSetDevice(m->device);
+    delete plan;
+    if (hints) cudaFreeHost(hints);
+    if (hlogits) cudaFreeHost(hlogits);
+    for (auto & e : ev) if (e) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+}
+
+bool Engine::init(const Model * model, int cap_windows) {
+    m = model; cap_win = std::max(1, cap_windows);
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto & e : ev) WB_CUDA_OK(cudaEventCreate(&e));
+    const HParams & hp = m->hp;
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = hp.n_audio_ctx, Tp = pad256(T), M = hp.n_mels, Lt = hp.n_text_layer, V = hp.n_vocab;
+    const size_t B = cap_win;
+    Tp_max = Tp;
+    debug_taps = getenv("WB200_DEBUG_TAPS") != nullptr;
+    if (!gmax.alloc(4)) return false;
+    if (!mel_win.alloc(B * (2*T + 2) * M, true) || !h1.alloc(B * (2*T + 2) * d, true) || !x.alloc(B * T * d) || !xn.alloc(B * T * d) ||
+        !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || !S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp) ||
+        !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d) || !kv_cross.alloc(B * 2 * Lt * Tp * d, true)) return false;
+    if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
+    // decoder workspaces (8 rows per pass)
+    if (!dx.alloc(8 * d) || !dqkv.alloc(8 * 3 * d) || !dattn.alloc(8 * d) || !dq2.alloc(8 * d) || !dh.alloc(8 * 4 * d) ||
+        !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 8 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
+    if (!set_cells(pad256(hp.n_text_ctx))) return false;
+    WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) 8 * V * sizeof(float)));
+    return true;
+}
+
+bool Engine::set_cells(int n) {
+    const HParams & hp = m->hp;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    n_cells = n;
+    const size_t e = (size_t) hp.n_text_layer * n * hp.n_text_state;
+    if (!kv_k.alloc(e, true) || !kv_v.alloc(e, true)) return false;
+    ld_idx = n;
+    const size_t nints = 5 * 8 + (size_t) 8 * ld_idx;
+    if (!dints.alloc(nints)) return false;
+    if (hints) cudaFreeHost(hints);
+    hints = nullptr;
+    WB_CUDA_OK(cudaMallocHost(&hints, nints * sizeof(int)));
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------- audio front-end
+bool Engine::pcm_to_mel(const float * samples, int n_samples) {
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    n_mel = m->n_filt_mel;
+    n_len = (n_samples + 480000) / 160;                       // whisper.cpp:3202-3218
+    n_len_org = 1 + (n_samples + 200 - 400) / 160;            // whisper.cpp:3220
+    if (!pcm.alloc(std::max(n_samples, 1)) || !mel.alloc((size_t) n_mel * n_len)) return false;
+    WB_CUDA_OK(cudaEventRecord(ev[0], st));
+    if (n_samples > 0) WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st));
+    mel_spectrogram(pcm.p, n_samples, m->filters, n_mel, mel.p, n_len, gmax.p, st);
+    WB_CUDA_OK(cudaEventRecord(ev[1], st));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&last_ms[0], ev[0], ev[1]);
+    return true;
+}
+bool Engine::set_mel(const float * data, int n_len_, int n_mel_) {
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    n_len = n_len_; n_len_org = n_len_; n_mel = n_mel_;
+    if (!mel.alloc((size_t) std::max(1, n_mel * n_len))) return false;
+    if (data) WB_CUDA_OK(cudaMemcpyAsync(mel.p, data, (size_t) n_mel * n_len * 4, cudaMemcpyHostToDevice, st));
+    else      WB_CUDA_OK(cudaMemsetAsync(mel.p, 0, (size_t) n_mel * n_len * 4, st));   // whisper-bench passes NULL, 0 (bench.cpp:69)
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    return true;
+}
+bool Engine::read_mel(std::vector<float> & out) {
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    out.resize((size_t) n_mel * n_len);
+    if (!out.empty()) WB_CUDA_OK(cudaMemcpy(out.data(), mel.p, out.size() * 4, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------- encoder plan
+static bool build_plan(Engine & E, int n_ctx, int n_win) {
+    const Model & m = *E.m; const HParams & hp = m.hp;
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = n_ctx, Tp = pad256(T), M = hp.n_mels, Lt = hp.n_text_layer, La = hp.n_audio_layer;
+    const int NT = n_win * T;
+    delete E.plan; E.plan = new EncPlan(); EncPlan & P = *E.plan;
+    P.n_ctx = n_ctx; P.n_win = n_win;
+    const int64_t win_rows = 2 * hp.n_audio_ctx + 2;            // allocation stride of mel_win / h1 (full-size windows)
+    QMat f16A; f16A.type = WT_F16;
+
+    { // conv1: [d x 2T] = sum_tap W1[tap] (d x M) * melT[t + tap] (whisper.cpp:2012-2015; ggml_conv_1d = im2col(F16) + mul_mat)
+        GemmDesc & g = P.conv1; g.M = d; g.N = 2*T; g.K = M; g.taps = 3; g.BN = 256; g.nb0 = n_win; g.A = f16A; g.A.base = m.conv1_w;
+        g.a_zsel[0] = 3; g.a_zsel[1] = 0; g.b_zsel[0] = 3; g.b_zsel[1] = 1;
+        if (!make_tmap_f16(&g.tmA, m.conv1_w, M, d, 3, 1, M, (uint64_t) d * M, 0, 128)) return false;
+        if (!make_tmap_f16(&g.tmB, E.mel_win.p, M, 2*T, 3, n_win, M, M, win_rows * M, 256)) return false;
+        g.ep.bias_m = m.conv1_b; g.ep.act = 1; g.ep.out = E.h1.p; g.ep.out_f16 = 1; g.ep.ldo = d; g.ep.n_row_off = 1; g.ep.out_b0 = win_rows * d;
+    }
+    { // conv2 (stride 2) + GELU + positional embedding (whisper.cpp:2017-2020, 2094-2095)
+        GemmDesc & g = P.conv2; g.M = d; g.N = T; g.K = d; g.taps = 3; g.BN = 256; g.nb0 = n_win; g.A = f16A; g.A.base = m.conv2_w;
+        g.a_zsel[0] = 3; g.a_zsel[1] = 0; g.b_zsel[0] = 3; g.b_zsel[1] = 1;
+        if (!make_tmap_f16(&g.tmA, m.conv2_w, d, d, 3, 1, d, (uint64_t) d * d, 0, 128)) return false;
+        if (!make_tmap_f16(&g.tmB, E.h1.p, d, T, 3, n_win, 2*d, d, win_rows * d, 256)) return false;
+        g.ep.bias_m = m.conv2_b; g.ep.act = 1; g.ep.res = m.e_pe; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; g.ep.out_b0 = (int64_t) T * d;
+        P.conv2_tap = g; P.conv2_tap.ep.res = nullptr; P.conv2_tap.ep.out = E.conv32.p;
+    }
+    CUtensorMap tm_xn, tm_xn_win, tm_attn, tm_hfc, tm_q, tm_k, tm_p, tm_vt, tm_enc;
+    if (!make_tmap_f16(&tm_xn, E.xn.p, d, NT, 1, 1, d, 0, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_xn_win, E.xn.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_attn, E.attn.p, d, NT, 1, 1, d, 0, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_q, E.qk.p,     64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 256)) return false;
+    if (!make_tmap_f16(&tm_k, E.qk.p + d, 64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 128)) return false;
+    if (!make_tmap_f16(&tm_p, E.P.p, Tp, T, H, n_win, Tp, (uint64_t) T * Tp, (uint64_t) H * T * Tp, 128)) return false;
+    if (!make_tmap_f16(&tm_vt, E.vt.p, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) d * Tp, 64)) return false;
+    if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, 256)) return false;
+
+    P.layers.resize(La);
+    for (int l = 0; l < La; ++l) {
+        const EncLayerW & L = m.enc[l]; EncLayerPlan & lp = P.layers[l];
+        { GemmDesc & g = lp.qk; g.M = 2*d; g.N = NT; g.K = d; g.BN = 256; g.A = L.qk; g.tmB = tm_xn;        // whisper.cpp:2119-2130
+          if (L.qk.type == WT_F16 && !make_tmap_f16(&g.tmA, L.qk.base, d, 2*d, 1, 1, d, 0, 0, 128)) return false;
+          g.ep.bias_m = L.qk_bias; g.ep.out = E.qk.p; g.ep.out_f16 = 1; g.ep.ldo = 2*d; }
+        { GemmDesc & g = lp.v; g.M = d; g.N = T; g.K = d; g.BN = 256; g.nb0 = n_win; g.A = L.v; g.tmB = tm_xn_win; g.b_zsel[0] = 1; g.b_zsel[1] = 0;  // 2134-2138
+          if (L.v.type == WT_F16 && !make_tmap_f16(&g.tmA, L.v.base, d, d, 1, 1, d, 0, 0, 128)) return false;
+          g.ep.bias_m = L.v_bias; g.ep.out = E.vt.p; g.ep.out_f16 = 1; g.ep.out_mmajor = 1; g.ep.ldo = Tp; g.ep.out_b0 = (int64_t) d * Tp; }
+        { GemmDesc & g = lp.s; g.M = Tp; g.N = T; g.K = 64; g.BN = 256; g.nb0 = H; g.nb1 = n_win; g.A = f16A; g.A.base = E.qk.p + d;     // K.Q^T, 1536 padded keys
+          g.tmA = tm_k; g.tmB = tm_q; g.a_zsel[0] = 1; g.a_zsel[1] = 2;
+          g.ep.alpha = 1.0f / sqrtf(64.0f); g.ep.out = E.S.p; g.ep.ldo = Tp; g.ep.out_b0 = (int64_t) T * Tp; g.ep.out_b1 = (int64_t) H * T * Tp; }
+        { GemmDesc & g = lp.pv; g.M = T; g.N = 64; g.K = Tp; g.BN = 64; g.nb0 = H; g.nb1 = n_win; g.A = f16A; g.A.base = E.P.p;
+          g.tmA = tm_p; g.tmB = tm_vt; g.a_zsel[0] = 1; g.a_zsel[1] = 2;
+          g.ep.out = E.attn.p; g.ep.out_f16 = 1; g.ep.out_mmajor = 1; g.ep.ldo = d; g.ep.out_b0 = 64; g.ep.out_b1 = (int64_t) T * d; }
+        { GemmDesc & g = lp.o; g.M = d; g.N = NT; g.K = d; g.BN = 256; g.A = L.o; g.tmB = tm_attn;           // 2200-2208
+          if (L.o.type == WT_F16 && !make_tmap_f16(&g.tmA, L.o.base, d, d, 1, 1, d, 0, 0, 128)) return false;
+          g.ep.bias_m = L.o_bias; g.ep.res = E.x.p; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; }
+        { GemmDesc & g = lp.fc1; g.M = 4*d; g.N = NT; g.K = d; g.BN = 256; g.A = L.fc1; g.tmB = tm_xn;       // 2225-2232
+          if (L.fc1.type == WT_F16 && !make_tmap_f16(&g.tmA, L.fc1.base, d, 4*d, 1, 1, d, 0, 0, 128)) return false;
+          g.ep.bias_m = L.fc1_bias; g.ep.act = 1; g.ep.out = E.hfc.p; g.ep.out_f16 = 1; g.ep.ldo = 4*d; }
+        { GemmDesc & g = lp.fc2; g.M = d; g.N = NT; g.K = 4*d; g.BN = 256; g.A = L.fc2; g.tmB = tm_hfc;      // 2235-2242
+          if (L.fc2.type == WT_F16 && !make_tmap_f16(&g.tmA, L.fc2.base, 4*d, d, 1, 1, 4*d, 0, 0, 128)) return false;
+          g.ep.bias_m = L.fc2_bias; g.ep.res = E.x.p; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; }
+    }
+    { // cross K/V of every text layer in one launch (whisper.cpp:2306-2347)
+        GemmDesc & g = P.cross; g.M = d; g.N = T; g.K = d; g.BN = 256; g.nb0 = 2 * Lt; g.nb1 = n_win; g.A = m.cross_kv; g.a_rows_per_b0 = d;
+        g.tmB = tm_enc; g.b_zsel[0] = 2; g.b_zsel[1] = 0;
+        if (m.cross_kv.type == WT_F16) {
+            if (!make_tmap_f16(&g.tmA, m.cross_kv.base, d, (uint64_t) 2 * Lt * d, 1, 1, d, 0, 0, 128)) return false;
+        }
+        g.ep.bias_m = m.cross_bias; g.ep.scale_m = m.cross_scale; g.ep.out = E.kv_cross.p; g.ep.out_f16 = 1; g.ep.ldo = d;
+        g.ep.out_b0 = (int64_t) E.Tp_max * d; g.ep.out_b1 = (int64_t) 2 * Lt * E.Tp_max * d;
+    }
+    return true;
+}
+
+#define WB_GEMM(desc) do { cudaError_t e_ = gemm_launch(desc, st); if (e_ != cudaSuccess) { set_error("%s:%d gemm_launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return false; } } while (0)
+
+bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
+    const HParams & hp = m->hp;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    if (n_win < 1 || n_win > cap_win) { set_error("encode: n_win=%d exceeds the state's capacity %d", n_win, cap_win); return false; }
+    if (n_ctx <= 0 || n_ctx > hp.n_audio_ctx) { set_error("encode: bad n_ctx %d", n_ctx); return false; }
+    if (!plan || plan->n_ctx != n_ctx || plan->n_win != n_win) {
+        if (plan && plan->n_ctx != n_ctx) {   // different padding: make sure padded key rows are zero again
+            WB_CUDA_OK(cudaMemsetAsync(kv_cross.p, 0, kv_cross.bytes(), st));
+            WB_CUDA_OK(cudaMemsetAsync(vt.p, 0, vt.bytes(), st));
+            WB_CUDA_OK(cudaMemsetAsync(h1.p, 0, h1.bytes(), st));
+        }
+        if (!build_plan(*this, n_ctx, n_win)) return false;
+    }
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = n_ctx, Tp = pad256(T), M = hp.n_mels;
+    const int NT = n_win * T;
+    const int64_t win_rows = 2 * hp.n_audio_ctx + 2;
+    EncPlan & PL = *plan;
+
+    WB_CUDA_OK(cudaEventRecord(ev[1], st));
+    for (int w = 0; w < n_win; ++w)
+        mel_window_f16(mel.p, n_len, n_mel, seeks[w], 2*T, mel_win.p + (size_t) w * win_rows * M, st);
+    WB_GEMM(PL.conv1);
+    if (debug_taps) WB_GEMM(PL.conv2_tap);
+    WB_GEMM(PL.conv2);
+    WB_CUDA_OK(cudaEventRecord(ev[2], st));
+    for (size_t l = 0; l < PL.layers.size(); ++l) {
+        const EncLayerW & L = m->enc[l]; EncLayerPlan & lp = PL.layers[l];
+        layernorm(x.p, L.ln0.w, L.ln0.b, hp.eps, NT, d, xn.p, nullptr, st);
+        WB_GEMM(lp.qk);
+        WB_GEMM(lp.v);
+        WB_GEMM(lp.s);
+        softmax_rows_f16(S.p, P.p, (int64_t) n_win * H * T, Tp, st);
+        WB_GEMM(lp.pv);
+        WB_GEMM(lp.o);
+        layernorm(x.p, L.ln1.w, L.ln1.b, hp.eps, NT, d, xn.p, nullptr, st);
+        WB_GEMM(lp.fc1);
+        WB_GEMM(lp.fc2);
+    }
+    layernorm(x.p, m->e_ln.w, m->e_ln.b, hp.eps, NT, d, enc16.p, debug_taps ? enc32.p : nullptr, st);
+    WB_CUDA_OK(cudaEventRecord(ev[3], st));
+    WB_GEMM(PL.cross);
+    WB_CUDA_OK(cudaEventRecord(ev[4], st));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&last_ms[1], ev[1], ev[2]);
+    cudaEventElapsedTime(&last_ms[2], ev[2], ev[3]);
+    cudaEventElapsedTime(&last_ms[3], ev[3], ev[4]);
+    enc_n_ctx = n_ctx; enc_n_win = n_win;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------- decoder
+bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * logits_out) {
+    const HParams & hp = m->hp;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, V = hp.n_vocab;
+    const int Tp = Tp_max;                                         // kv_cross layout stride
+    const int n_keys = pad256(enc_n_ctx > 0 ? enc_n_ctx : hp.n_audio_ctx);
+    const float kq_scale = powf(64.0f, -0.25f);                    // whisper.cpp:2514
+    if (ld > ld_idx) { set_error("decode: idx row length %d exceeds pool %d", ld, ld_idx); return false; }
+
+    for (int r0 = 0; r0 < n_rows; r0 += 8) {
+        const int n = std::min(8, n_rows - r0);
+        int * h_tok = hints, * h_pos = hints + 8, * h_cell = hints + 16, * h_slot = hints + 24, * h_nkv = hints + 32, * h_idx = hints + 40;
+        bool any_logits = false; int max_kv = 0;
+        for (int j = 0; j < n; ++j) {
+            const DecToken & t = rows[r0 + j];
+            if (t.token < 0 || t.token >= V || t.pos < 0 || t.pos >= hp.n_text_ctx || t.slot < 0 || t.slot >= cap_win) {
+                set_error("decode: bad token/pos/slot (%d, %d, %d)", t.token, t.pos, t.slot); return false;
+            }
+            h_tok[j] = t.token; h_pos[j] = t.pos; h_cell[j] = cells[r0 + j]; h_slot[j] = t.slot; h_nkv[j] = n_kv[r0 + j];
+            max_kv = std::max(max_kv, n_kv[r0 + j]);
+            memcpy(h_idx + (size_t) j * ld_idx, kv_idx + (size_t) (r0 + j) * ld, (size_t) n_kv[r0 + j] * sizeof(int));
+            any_logits |= t.want_logits;
+        }
+        const size_t nint = 40 + (size_t) (n - 1) * ld_idx + max_kv;
+        WB_CUDA_OK(cudaMemcpyAsync(dints.p, hints, nint * sizeof(int), cudaMemcpyHostToDevice, st));
+        const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_idx = dints.p + 40;
+
+        dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
+        for (int l = 0; l < Lt; ++l) {
+            const DecLayerW & L = m->dec[l];
+            __half * kc = kv_k.p + (size_t) l * n_cells * d;
+            __half * vc = kv_v.p + (size_t) l * n_cells * d;
+            { GemvArgs a; a.W = L.qkv; a.x = dx.p; a.n_tok = n; a.ln_w = L.ln0.w; a.ln_b = L.ln0.b; a.eps = hp.eps;      // whisper.cpp:2536-2599
+              a.bias = L.qkv_bias; a.scale = L.qkv_scale; a.out = dqkv.p; a.k_cache = kc; a.v_cache = vc; a.cells = d_cell; a.kv_d = d;
+              gemv(a, st); }
+            attn_self_decode(dqkv.p, 3*d, kc, vc, d_idx, ld_idx, d_nkv, n, H, d, dattn.p, d, st);                            // 2603-2625
+            { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }    // 2647-2659
+            { GemvArgs a; a.W = L.cq; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnc.w; a.ln_b = L.lnc.b; a.eps = hp.eps;        // 2661-2681
+              a.bias = L.cq_bias; a.out = dq2.p; gemv(a, st); }
+            attn_cross_decode(dq2.p, d, kv_cross.p + (size_t) l * Tp * d, kv_cross.p + (size_t) (Lt + l) * Tp * d, d_slot,
+                              (int64_t) 2 * Lt * Tp * d, n_keys, n, H, d, kq_scale, xpart.p, xcnt.p, dattn.p, d, st);       // 2688-2705
+            { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }  // 2754-2766
+            { GemvArgs a; a.W = L.fc1; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnm.w; a.ln_b = L.lnm.b; a.eps = hp.eps;       // 2770-2794
+              a.bias = L.fc1_bias; a.act = 1; a.out = dh.p; gemv(a, st); }
+            { GemvArgs a; a.W = L.fc2; a.x = dh.p; a.n_tok = n; a.bias = L.fc2_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }   // 2797-2806
+        }
+        if (any_logits) {
+            GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
+            gemv(a, st);
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits)
+                WB_CUDA_OK(cudaMemcpyAsync(hlogits + (size_t) j * V, dlogits.p + (size_t) j * V, (size_t) V * 4, cudaMemcpyDeviceToHost, st));
+        }
+        WB_CUDA_OK(cudaStreamSynchronize(st));
+        if (any_logits && logits_out)
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits)
+                memcpy(logits_out + (size_t) (r0 + j) * V, hlogits + (size_t) j * V, (size_t) V * 4);
+    }
+    return true;
+}
+
+} // namespace wb

@@ -27,7 +27,7 @@ template <int BN> struct GemmCfg {
 
 struct GemmKParams {
     int M, N, K, taps, nkb_per_tap, nb0;
-    int a_batched;
+    int a_zsel0, a_zsel1, b_zsel0, b_zsel1, a_rows_per_b0;
     // quantised A
     const void * a_base; const uint8_t * a_qs; const uint32_t * a_qh; const __half * a_d;
     GemmEpilogue ep;
@@ -84,6 +84,7 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
     const int b0 = blockIdx.z % p.nb0;
     const int b1 = blockIdx.z / p.nb0;
     const int nkb = p.taps * p.nkb_per_tap;
+    const int mg0 = m0 + b0 * p.a_rows_per_b0;     // first global A row of this tile (stacked weight matrices)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmB);
@@ -113,14 +114,10 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 const uint32_t tx = Cfg::B_TILE_BYTES + (QUANT ? 0 : A_TILE_BYTES);
                 mbar_arrive_expect_tx(&full_bar[s], tx);
-                const int z2 = p.taps > 1 ? tap : b0;
-                const int z3 = p.taps > 1 ? (int) blockIdx.z : b1;
-                tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, z2, z3);
-                if (!QUANT) {
-                    const int az2 = p.taps > 1 ? tap : (p.a_batched ? b0 : 0);
-                    const int az3 = p.a_batched ? (p.taps > 1 ? (int) blockIdx.z : b1) : 0;
-                    tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, m0, az2, az3);
-                }
+                const int sel[4] = { 0, b0, b1, tap };
+                tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, sel[p.b_zsel0], sel[p.b_zsel1]);
+                if (!QUANT)
+                    tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, mg0, sel[p.a_zsel0], sel[p.a_zsel1]);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -150,8 +147,8 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
         if (QUANT) {
             const int row  = pt >> 1;
             const int half = pt & 1;
-            const int m    = m0 + row;
-            const bool mval = m < p.M;
+            const int m    = mg0 + row;              // global row in the (stacked) weight matrix
+            const bool mval = (m0 + row) < p.M;
             uint8_t * dst_row = sA + row * 128;
             const int sw = row & 7;
             int s = 0; uint32_t ph = 0;
@@ -209,8 +206,9 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
         const int m    = m0 + q * 32 + lane;
         const bool mval = m < p.M;
         const GemmEpilogue & e = p.ep;
-        const float bias = (mval && e.bias_m)  ? e.bias_m[m]  : 0.0f;
-        const float scl  = ((mval && e.scale_m) ? e.scale_m[m] : 1.0f) * e.alpha;
+        const int mg = m + b0 * p.a_rows_per_b0;   // bias / scale follow the stacked-matrix row
+        const float bias = (mval && e.bias_m)  ? e.bias_m[mg]  : 0.0f;
+        const float scl  = ((mval && e.scale_m) ? e.scale_m[mg] : 1.0f) * e.alpha;
         const int64_t ooff = (int64_t) b0 * e.out_b0 + (int64_t) b1 * e.out_b1;
         const int64_t roff = (int64_t) b0 * e.res_b0 + (int64_t) b1 * e.res_b1;
         constexpr int CH = BN / 2 / 32;            // 32-column chunks per warp
@@ -350,7 +348,8 @@ static cudaError_t launch_bn(const GemmDesc & g, const GemmKParams & kp, cudaStr
 cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
     GemmKParams kp;
     kp.M = g.M; kp.N = g.N; kp.K = g.K; kp.taps = g.taps; kp.nkb_per_tap = (g.K + 63) / 64; kp.nb0 = g.nb0;
-    kp.a_batched = g.a_batched;
+    kp.a_zsel0 = g.a_zsel[0]; kp.a_zsel1 = g.a_zsel[1]; kp.b_zsel0 = g.b_zsel[0]; kp.b_zsel1 = g.b_zsel[1];
+    kp.a_rows_per_b0 = g.a_rows_per_b0;
     kp.a_base = g.A.base; kp.a_qs = g.A.qs; kp.a_qh = g.A.qh; kp.a_d = g.A.d;
     kp.ep = g.ep;
     switch (g.A.type) {

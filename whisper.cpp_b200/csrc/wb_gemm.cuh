@@ -36,9 +36,12 @@ struct GemmDesc {
     int M = 0, N = 0, K = 0;          // K per tap
     int taps = 1;                     // 3 for the conv stem (tap is TMA dim 2 of both operands)
     int BN = 128;                     // 64 / 128 / 256
-    int nb0 = 1, nb1 = 1;             // batch extents (blockIdx.z = b1*nb0 + b0); with taps==1 b0 is TMA dim 2, b1 dim 3
+    int nb0 = 1, nb1 = 1;             // batch extents (blockIdx.z = b1*nb0 + b0)
+    // what feeds TMA coordinates z2 / z3 of each operand: 0 = zero, 1 = b0, 2 = b1, 3 = tap
+    int a_zsel[2] = { 0, 0 };
+    int b_zsel[2] = { 1, 2 };
+    int a_rows_per_b0 = 0;            // A row offset = b0 * a_rows_per_b0 (stacked weights: one launch, many matrices)
     QMat A;                           // weight side; type WT_F16 => tmA used
-    int  a_batched = 0;               // f16 A only: 1 = A tensor map also takes the batch coordinates (attention)
     CUtensorMap tmA;                  // valid when A.type == WT_F16
     CUtensorMap tmB;
     GemmEpilogue ep;

@@ -1,18 +1,74 @@
-// wb_kernels.cu -- bandwidth-bound kernels of the encode/decode path.
+// wb_kernels.cu -- the bandwidth-bound kernels of the encode/decode path (everything that is not a tcgen05 GEMM).
+// Each kernel cites the reference lines whose arithmetic it reproduces.
+#include <cmath>
+#include <mutex>
+#include <vector>
 #include "wb_kernels.cuh"
 #include "wb_common.h"
 
 namespace wb {
 
+// =====================================================================================================================
+//  small utilities
+// =====================================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum / max for blockDim.x <= 1024 (scratch: 32 floats of shared memory)
+__device__ __forceinline__ float block_sum(float v, float * scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? scratch[lane] : 0.0f;
+    return warp_sum(r);
+}
+__device__ __forceinline__ float block_max(float v, float * scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = (lane < nw) ? scratch[lane] : -INFINITY;
+    return warp_max(r);
+}
+__device__ __forceinline__ float gelu_ref_f16(float x) {   // ggml-cpu/vec.h:988-1001 (f16 table semantics)
+    if (x <= -10.0f) return 0.0f;
+    if (x >=  10.0f) return x;
+    const float xh = __half2float(__float2half_rn(x));
+    const float g  = 0.5f*xh*(1.0f + tanhf(0.79788456080286535587989211986876f*xh*(1.0f + 0.044715f*xh*xh)));
+    return __half2float(__float2half_rn(g));
+}
+
+// =====================================================================================================================
+//  conversions / re-layout
+// =====================================================================================================================
 __global__ void k_f32_to_f16(const float * __restrict__ s, __half * __restrict__ d, int64_t n) {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (; i < n; i += stride) d[i] = __float2half_rn(s[i]);
 }
+__global__ void k_f16_to_f32(const __half * __restrict__ s, float * __restrict__ d, int64_t n) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) d[i] = __half2float(s[i]);
+}
+static inline int grid_for(int64_t n, int tpb) { int64_t b = (n + tpb - 1) / tpb; return (int) (b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16); }
 void f32_to_f16(const float * src, __half * dst, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
-    const int blocks = (int) ((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-    k_f32_to_f16<<<blocks, 256, 0, st>>>(src, dst, n); count_launch();
+    k_f32_to_f16<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n); count_launch();
+}
+void f16_to_f32(const __half * src, float * dst, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_f16_to_f32<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n); count_launch();
 }
 
 // one thread per 32-block: gather the unaligned file block with byte loads, scatter to the planar arrays
@@ -21,25 +77,19 @@ __global__ void k_repack32(const uint8_t * __restrict__ src, uint8_t * __restric
                            __half * __restrict__ d, int64_t nblk) {
     constexpr int BS = (WT == WT_Q4_0) ? 18 : (WT == WT_Q5_0 ? 22 : 34);
     constexpr int QS = (WT == WT_Q8_0) ? 32 : 16;
-    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk) return;
     const uint8_t * b = src + i * BS;
-    uint16_t dh = (uint16_t) b[0] | ((uint16_t) b[1] << 8);
-    d[i] = __ushort_as_half(dh);
+    d[i] = __ushort_as_half((unsigned short) ((uint16_t) b[0] | ((uint16_t) b[1] << 8)));
     int off = 2;
     if (WT == WT_Q5_0) { qh[i] = (uint32_t) b[2] | ((uint32_t) b[3] << 8) | ((uint32_t) b[4] << 16) | ((uint32_t) b[5] << 24); off = 6; }
     for (int j = 0; j < QS; ++j) qs[i * QS + j] = b[off + j];
 }
-
-bool repack_block32(int wtype, const uint8_t * src, uint8_t * dst, int N, int K, QMat * out, cudaStream_t st) {
-    const int64_t nblk = (int64_t) N * (K / 32);
-    const int QS = wt_qs_bytes(wtype);
-    uint8_t * qs = dst;                                   // 16-byte aligned (cudaMalloc base)
-    uint8_t * p  = dst + nblk * QS;
-    uint32_t * qh = nullptr;
-    if (wtype == WT_Q5_0) { qh = reinterpret_cast<uint32_t *>(p); p += nblk * 4; }
-    __half * d = reinterpret_cast<__half *>(p);
+bool repack_block32_into(int wtype, const uint8_t * src, const QMat & dst, int rows, int K, cudaStream_t st) {
+    const int64_t nblk = (int64_t) rows * (K / 32);
+    if (nblk == 0) return true;
     const int blocks = (int) ((nblk + 255) / 256);
+    uint8_t * qs = const_cast<uint8_t *>(dst.qs); uint32_t * qh = const_cast<uint32_t *>(dst.qh); __half * d = const_cast<__half *>(dst.d);
     switch (wtype) {
         case WT_Q4_0: k_repack32<WT_Q4_0><<<blocks, 256, 0, st>>>(src, qs, qh, d, nblk); break;
         case WT_Q5_0: k_repack32<WT_Q5_0><<<blocks, 256, 0, st>>>(src, qs, qh, d, nblk); break;
@@ -47,8 +97,629 @@ bool repack_block32(int wtype, const uint8_t * src, uint8_t * dst, int N, int K,
         default: set_error("repack_block32: bad type %d", wtype); return false;
     }
     count_launch();
-    out->type = wtype; out->N = N; out->K = K; out->base = nullptr; out->qs = qs; out->qh = qh; out->d = d;
     return cudaGetLastError() == cudaSuccess;
+}
+bool repack_block32(int wtype, const uint8_t * src, uint8_t * dst, int N, int K, QMat * out, cudaStream_t st) {
+    const int64_t nblk = (int64_t) N * (K / 32);
+    out->type = wtype; out->N = N; out->K = K; out->base = nullptr;
+    out->qs = dst;
+    uint8_t * p = dst + nblk * wt_qs_bytes(wtype);
+    out->qh = nullptr;
+    if (wtype == WT_Q5_0) { out->qh = reinterpret_cast<uint32_t *>(p); p += nblk * 4; }
+    out->d = reinterpret_cast<__half *>(p);
+    return repack_block32_into(wtype, src, *out, N, K, st);
+}
+
+// =====================================================================================================================
+//  log-mel spectrogram  (src/whisper.cpp:3005-3272)
+// =====================================================================================================================
+// Hann window and the 400-entry sin/cos table are evaluated on the HOST with the reference's own expressions
+// (whisper.cpp:3023-3039) so they are bit-identical to the tables the CPU path uses; [0,400)=hann [400,800)=cos [800,1200)=sin
+__constant__ float c_mel_tab[1200];
+
+static void mel_tables_upload() {
+    static std::mutex mu; static bool done[64] = { false };
+    int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && done[dev]) return;
+    std::vector<float> t(1200);
+    for (int i = 0; i < 400; ++i) {
+        t[i] = (float) (0.5 * (1.0 - cosf((float) ((2.0 * M_PI * i) / 400))));
+        const double theta = (2 * M_PI * i) / 400;
+        t[400 + i] = cosf((float) theta);
+        t[800 + i] = sinf((float) theta);
+    }
+    cudaMemcpyToSymbol(c_mel_tab, t.data(), 1200 * sizeof(float));
+    if (dev < 64) done[dev] = true;
+}
+
+__device__ __forceinline__ int float_order_key(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float float_from_key(int k)  { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+__global__ void k_mel_init(int * gmax_key) { *gmax_key = float_order_key(-1e20f); }
+
+// one block per frame
+__global__ void __launch_bounds__(256)
+k_mel_frames(const float * __restrict__ pcm, int N, const float * __restrict__ filt, int n_mel,
+             float * __restrict__ mel, int n_len, int * __restrict__ gmax_key) {
+    __shared__ float x[400];
+    __shared__ float P[204];
+    __shared__ float red[32];
+    const int i   = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n_eff  = N + 200;                               // samples handed to the worker: n_samples + stage_2_pad
+    const int n_comp = min(n_eff / 160 + 1, n_len);           // frames that are really transformed (whisper.cpp:3125)
+    if (i >= n_comp) {                                        // whisper.cpp:3168-3174
+        for (int j = tid; j < n_mel; j += blockDim.x) mel[(int64_t) j * n_len + i] = -10.0f;
+        if (tid == 0) atomicMax(gmax_key, float_order_key(-10.0f));
+        return;
+    }
+    const int offset   = i * 160;
+    const int n_reflect = min(200, max(0, N - 1));
+    const int lim = min(400, n_eff - offset);
+    for (int j = tid; j < 400; j += blockDim.x) {
+        float s = 0.0f;
+        if (j < lim) {
+            const int idx = offset + j;                       // index into the padded signal
+            if (idx < 200) { const int r = idx - (200 - n_reflect); s = (r >= 0) ? pcm[n_reflect - r] : 0.0f; }
+            else if (idx < 200 + N) s = pcm[idx - 200];
+            s = c_mel_tab[j] * s;
+        }
+        x[j] = s;
+    }
+    __syncthreads();
+    if (tid < 201) {                                          // direct 400-point DFT bin `tid`
+        float re = 0.0f, im = 0.0f;
+        int idx = 0;
+        for (int n = 0; n < 400; ++n) {
+            const float v = x[n];
+            re += v * c_mel_tab[400 + idx];
+            im -= v * c_mel_tab[800 + idx];
+            idx += tid; if (idx >= 400) idx -= 400;
+        }
+        P[tid] = re * re + im * im;
+    }
+    __syncthreads();
+    float lmax = -1e20f;
+    for (int j = tid; j < n_mel; j += blockDim.x) {
+        const float * f = filt + (int64_t) j * 201;
+        double sum = 0.0;
+        int k = 0;
+        for (; k < 201 - 3; k += 4) {                         // same grouping as whisper.cpp:3152-3158 (float inside, double outside)
+            const float part = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[k], f[k]), __fmul_rn(P[k+1], f[k+1])), __fmul_rn(P[k+2], f[k+2])), __fmul_rn(P[k+3], f[k+3]));
+            sum += part;
+        }
+        for (; k < 201; ++k) sum += __fmul_rn(P[k], f[k]);
+        sum = log10(fmax(sum, 1e-10));
+        const float v = (float) sum;
+        mel[(int64_t) j * n_len + i] = v;
+        lmax = fmaxf(lmax, v);
+    }
+    lmax = block_max(lmax, red);
+    if (tid == 0) atomicMax(gmax_key, float_order_key(lmax));
+}
+
+__global__ void k_mel_norm(float * __restrict__ mel, int64_t n, const int * __restrict__ gmax_key) {
+    const double mmax = (double) float_from_key(*gmax_key) - 8.0;     // whisper.cpp:3240-3256
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float v = mel[i];
+        if ((double) v < mmax) v = (float) mmax;
+        mel[i] = (float) (((double) v + 4.0) / 4.0);
+    }
+}
+
+void mel_spectrogram(const float * pcm, int n_samples, const float * filters, int n_mel, float * mel, int n_len,
+                     float * gmax_scratch, cudaStream_t st) {
+    mel_tables_upload();
+    int * key = reinterpret_cast<int *>(gmax_scratch);
+    k_mel_init<<<1, 1, 0, st>>>(key);
+    k_mel_frames<<<n_len, 256, 0, st>>>(pcm, n_samples, filters, n_mel, mel, n_len, key);
+    const int64_t n = (int64_t) n_mel * n_len;
+    k_mel_norm<<<grid_for(n, 256), 256, 0, st>>>(mel, n, key);
+    count_launch(3);
+}
+
+__global__ void k_mel_window(const float * __restrict__ mel, int n_len, int n_mel, int seek, int n_frames, __half * __restrict__ out) {
+    // out[r][j], r in [0, n_frames+2): tile transpose through shared memory (mel is mel-major, out is time-major)
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int dj = threadIdx.y; dj < 32; dj += blockDim.y) {
+        const int j = j0 + dj, t = t0 + threadIdx.x;
+        float v = 0.0f;
+        if (j < n_mel && t < n_frames && seek + t < n_len && seek + t >= 0) v = mel[(int64_t) j * n_len + seek + t];
+        tile[dj][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int dt = threadIdx.y; dt < 32; dt += blockDim.y) {
+        const int t = t0 + dt, j = j0 + threadIdx.x;
+        if (t < n_frames && j < n_mel) out[(int64_t) (t + 1) * n_mel + j] = __float2half_rn(tile[threadIdx.x][dt]);
+    }
+}
+__global__ void k_zero_rows2(__half * out, int n_mel, int n_frames) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_mel) { out[j] = __float2half(0.0f); out[(int64_t) (n_frames + 1) * n_mel + j] = __float2half(0.0f); }
+}
+void mel_window_f16(const float * mel, int n_len, int n_mel, int seek, int n_frames, __half * out, cudaStream_t st) {
+    dim3 grid((n_frames + 31) / 32, (n_mel + 31) / 32), block(32, 8);
+    k_mel_window<<<grid, block, 0, st>>>(mel, n_len, n_mel, seek, n_frames, out);
+    k_zero_rows2<<<(n_mel + 127) / 128, 128, 0, st>>>(out, n_mel, n_frames);
+    count_launch(2);
+}
+
+// =====================================================================================================================
+//  LayerNorm: two-pass statistics, then (x-mean)*rstd*w + b   (ggml-cpu/ops.cpp:3698-3765; whisper.cpp:2108-2115)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+k_layernorm(const float * __restrict__ x, const float * __restrict__ w, const float * __restrict__ b, float eps,
+            int rows, int d, __half * __restrict__ o16, float * __restrict__ o32) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float * xr = x + (int64_t) warp * d;
+    float s = 0.0f;
+    for (int i = lane; i < d; i += 32) s += xr[i];
+    const float mean = warp_sum(s) / d;
+    float v = 0.0f;
+    for (int i = lane; i < d; i += 32) { const float t = xr[i] - mean; v += t * t; }
+    const float var = warp_sum(v) / d;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    for (int i = lane; i < d; i += 32) {
+        const float y = __fadd_rn(__fmul_rn(__fmul_rn(xr[i] - mean, rstd), w[i]), b[i]);
+        if (o16) o16[(int64_t) warp * d + i] = __float2half_rn(y);
+        if (o32) o32[(int64_t) warp * d + i] = y;
+    }
+}
+void layernorm(const float * x, const float * w, const float * b, float eps, int rows, int d, __half * o16, float * o32, cudaStream_t st) {
+    if (rows <= 0) return;
+    const int blocks = (rows * 32 + 255) / 256;
+    k_layernorm<<<blocks, 256, 0, st>>>(x, w, b, eps, rows, d, o16, o32); count_launch();
+}
+
+// =====================================================================================================================
+//  row softmax for the unfused attention path (scores are already scaled)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+k_softmax_rows(const float * __restrict__ s, __half * __restrict__ p, int64_t rows, int cols) {
+    const int64_t row = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float * sr = s + row * cols;
+    float m = -INFINITY;
+    for (int i = lane; i < cols; i += 32) m = fmaxf(m, sr[i]);
+    m = warp_max(m);
+    float sum = 0.0f;
+    for (int i = lane; i < cols; i += 32) sum += expf(sr[i] - m);
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int i = lane; i < cols; i += 32) p[row * cols + i] = __float2half_rn(expf(sr[i] - m) * inv);
+}
+void softmax_rows_f16(const float * s, __half * p, int64_t rows, int cols, cudaStream_t st) {
+    if (rows <= 0) return;
+    const int64_t blocks = (rows * 32 + 255) / 256;
+    k_softmax_rows<<<(unsigned) blocks, 256, 0, st>>>(s, p, rows, cols); count_launch();
+}
+
+// =====================================================================================================================
+//  decoder: token + position embedding (get_rows on the quantised table is an exact f32 dequantisation,
+//  ggml-cpu/ops.cpp:4850 -> ggml-quants.c dequantize_row_*)
+// =====================================================================================================================
+__device__ __forceinline__ float dequant_elem(const QMat & W, int64_t row, int e) {
+    const int K = W.K;
+    switch (W.type) {
+        case WT_F16: return __half2float(reinterpret_cast<const __half *>(W.base)[row * K + e]);
+        case WT_Q4_0: { const int64_t b = row * (K >> 5) + (e >> 5); const int i = e & 31;
+                        const uint8_t q = W.qs[b * 16 + (i & 15)]; const int v = (i < 16 ? (q & 0xF) : (q >> 4)) - 8;
+                        return (float) v * __half2float(W.d[b]); }
+        case WT_Q5_0: { const int64_t b = row * (K >> 5) + (e >> 5); const int i = e & 31;
+                        const uint8_t q = W.qs[b * 16 + (i & 15)]; const uint32_t h = (W.qh[b] >> i) & 1u;
+                        const int v = (int) ((i < 16 ? (q & 0xF) : (q >> 4)) | (h << 4)) - 16;
+                        return (float) v * __half2float(W.d[b]); }
+        case WT_Q8_0: { const int64_t b = row * (K >> 5) + (e >> 5);
+                        return (float) reinterpret_cast<const int8_t *>(W.qs)[b * 32 + (e & 31)] * __half2float(W.d[b]); }
+        case WT_Q4_K: case WT_Q5_K: {
+            const int BLK = W.type == WT_Q4_K ? 144 : 176;
+            const uint8_t * blk = reinterpret_cast<const uint8_t *>(W.base) + (row * (K >> 8) + (e >> 8)) * BLK;
+            const int j = (e & 255) >> 5, l = e & 31;
+            int sc, mn; kq_scale_min(j, blk + 4, sc, mn);
+            const float d = __half2float(*reinterpret_cast<const __half *>(blk)), dmin = __half2float(*reinterpret_cast<const __half *>(blk + 2));
+            const uint8_t * qs = blk + 16 + (W.type == WT_Q5_K ? 32 : 0) + 32 * (j >> 1);
+            int q = (qs[l] >> (4 * (j & 1))) & 0xF;
+            if (W.type == WT_Q5_K) q |= ((blk[16 + l] >> j) & 1) << 4;
+            return d * sc * q - dmin * mn;
+        }
+    }
+    return 0.0f;
+}
+__global__ void k_dec_embed(const QMat te, const float * __restrict__ pe, const int * __restrict__ tok, const int * __restrict__ pos,
+                            int d, float * __restrict__ x) {
+    const int t = blockIdx.x;
+    const int token = tok[t], p = pos[t];
+    for (int e = threadIdx.x; e < d; e += blockDim.x)
+        x[(int64_t) t * d + e] = dequant_elem(te, token, e) + pe[(int64_t) p * d + e];
+}
+void dec_embed(const QMat & te, const float * pe, const int * tokens, const int * pos, int n_tok, int d, float * x, cudaStream_t st) {
+    k_dec_embed<<<n_tok, 256, 0, st>>>(te, pe, tokens, pos, d, x); count_launch();
+}
+
+// =====================================================================================================================
+//  GEMV for the decode step: y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n]
+//
+//  Reference arithmetic (ggml-cpu/ggml-cpu.c:1181-1357): activations are quantised per 32 values to Q8_0
+//  (quantize_row_q8_0, AVX2 form ggml-cpu/arch/x86/quants.c: d = amax/127 stored as f16, q = rint(x*127/amax)) or per 256
+//  values to Q8_K for K-quants (ggml-quants.c:2768-2805); the dot product is integer inside a block and
+//  sum_b (d_w*d_x) * sumi outside (ggml-cpu/quants.c:365-406, 696-769).  This kernel does the same with __dp4a, so it
+//  differs from the reference only in f32 summation order.  F16 weights: x rounded to f16, products accumulated in f32.
+//  LayerNorm of x (when requested) is fused in front: every CTA recomputes it from the f32 residual stream.
+// =====================================================================================================================
+struct GemvK {
+    QMat W; const float * x; int n_tok;
+    const float * ln_w, * ln_b; float eps;
+    const float * bias, * scale; int act; const float * res; float * out;
+    __half * k_cache, * v_cache; const int * cells; int kv_d;
+};
+
+template <int WT> struct GemvSmem;
+
+// shared-memory carve-up (dynamic): per token  xq int8[K] | xd float[K/32] (block32) / xd float[K/256] + bs int[K/32] (K-quant)
+// or half[K] for F16.  scratch float[K] for the LayerNorm/quantise prologue (shared by all tokens).
+template <int WT>
+__device__ __forceinline__ size_t gemv_tok_bytes(int K) {
+    if (WT == WT_F16) return (size_t) K * 2;
+    if (WT == WT_Q4_K || WT == WT_Q5_K) return (size_t) K + (size_t) (K / 256) * 4 + (size_t) (K / 32) * 4;
+    return (size_t) K + (size_t) (K / 32) * 4;
+}
+
+template <int WT, int NT>
+__global__ void __launch_bounds__(256)
+k_gemv(const GemvK a) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int K = a.W.K, N = a.W.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float * scratch = reinterpret_cast<float *>(sm);                     // [K]
+    __shared__ float red[32];
+    uint8_t * tokbase = sm + (size_t) K * 4;
+    const size_t tb = (gemv_tok_bytes<WT>(K) + 15) & ~size_t(15);
+
+    // ---------------------------------------------------------------- prologue: (LN) + activation quantisation
+    for (int t = 0; t < a.n_tok; ++t) {
+        const float * xr = a.x + (int64_t) t * K;
+        if (a.ln_w) {
+            float s = 0.0f;
+            for (int i = tid; i < K; i += 256) s += xr[i];
+            const float mean = block_sum(s, red) / K;
+            float v = 0.0f;
+            for (int i = tid; i < K; i += 256) { const float d0 = xr[i] - mean; v += d0 * d0; }
+            const float rstd = 1.0f / sqrtf(block_sum(v, red) / K + a.eps);
+            for (int i = tid; i < K; i += 256)
+                scratch[i] = __fadd_rn(__fmul_rn(__fmul_rn(xr[i] - mean, rstd), a.ln_w[i]), a.ln_b[i]);
+        } else {
+            for (int i = tid; i < K; i += 256) scratch[i] = xr[i];
+        }
+        __syncthreads();
+        uint8_t * tp = tokbase + t * tb;
+        if (WT == WT_F16) {
+            __half * xh = reinterpret_cast<__half *>(tp);
+            for (int i = tid; i < K; i += 256) xh[i] = __float2half_rn(scratch[i]);
+        } else if (WT == WT_Q4_K || WT == WT_Q5_K) {
+            // quantize_row_q8_K (ggml-quants.c:2768-2805): per 256: iscale = -127/max (signed max-magnitude), q = min(127, nearest(iscale*x)), d = 1/iscale
+            int8_t * xq = reinterpret_cast<int8_t *>(tp);
+            float * xd = reinterpret_cast<float *>(tp + K);
+            int *   bs = reinterpret_cast<int *>(tp + K + (K / 256) * 4);
+            for (int sb = warp; sb < K / 256; sb += 8) {
+                float v[8]; float amax = 0.0f, mx = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = scratch[sb * 256 + j * 32 + lane]; const float av = fabsf(v[j]); if (av > amax) { amax = av; mx = v[j]; } }
+                // warp arg-max of |v| (first occurrence in element order wins in the reference; ties are measure-zero)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float oa = __shfl_xor_sync(0xffffffffu, amax, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
+                    if (oa > amax) { amax = oa; mx = om; }
+                }
+                if (amax == 0.0f) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xq[sb * 256 + j * 32 + lane] = 0;
+                    if (lane == 0) xd[sb] = 0.0f;
+                    if (lane < 8) bs[sb * 8 + lane] = 0;
+                    continue;
+                }
+                const float iscale = -127.0f / mx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    int q = __float2int_rn(iscale * v[j]); q = min(127, q);
+                    xq[sb * 256 + j * 32 + lane] = (int8_t) q;
+                    int ssum = q;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                    if (lane == 0) bs[sb * 8 + j] = ssum;
+                }
+                if (lane == 0) xd[sb] = 1.0f / iscale;
+            }
+        } else {
+            int8_t * xq = reinterpret_cast<int8_t *>(tp);
+            float * xd = reinterpret_cast<float *>(tp + K);
+            for (int b = warp; b < K / 32; b += 8) {
+                const float v = scratch[b * 32 + lane];
+                const float amax = warp_max(fabsf(v));
+                const float d  = amax / 127.0f;
+                const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+                xq[b * 32 + lane] = (int8_t) __float2int_rn(v * id);
+                if (lane == 0) xd[b] = __half2float(__float2half_rn(d));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------------------------------------------------------- rows: one warp per output row
+    const int nwarps_total = gridDim.x * 8;
+    for (int row = blockIdx.x * 8 + warp; row < N; row += nwarps_total) {
+        float acc[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = 0.0f;
+
+        if (WT == WT_F16) {
+            const uint4 * wr = reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(a.W.base) + (int64_t) row * K);
+            for (int c = lane; c < K / 8; c += 32) {
+                const uint4 w8 = __ldg(wr + c);
+                const __half2 * wh = reinterpret_cast<const __half2 *>(&w8);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (t < a.n_tok) {
+                        const uint4 x8 = *reinterpret_cast<const uint4 *>(tokbase + t * tb + (size_t) c * 16);
+                        const __half2 * xh = reinterpret_cast<const __half2 *>(&x8);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 wf = __half22float2(wh[e]), xf = __half22float2(xh[e]);
+                            acc[t] = fmaf(wf.x, xf.x, acc[t]); acc[t] = fmaf(wf.y, xf.y, acc[t]);
+                        }
+                    }
+                }
+            }
+        } else if (WT == WT_Q4_K || WT == WT_Q5_K) {
+            constexpr int BLK = (WT == WT_Q4_K) ? 144 : 176;
+            const uint8_t * rowp = reinterpret_cast<const uint8_t *>(a.W.base) + (int64_t) row * (K >> 8) * BLK;
+            for (int c = lane; c < K / 8; c += 32) {           // chunk of 8 weights: super-block c/32, sub-block (c%32)/4, quarter c%4
+                const int sb = c >> 5, j = (c & 31) >> 2, qd = c & 3;
+                const uint8_t * blk = rowp + (int64_t) sb * BLK;
+                const __half2 dm = *reinterpret_cast<const __half2 *>(blk);
+                int sc, mn; kq_scale_min(j, blk + 4, sc, mn);
+                const uint8_t * qs = blk + 16 + (WT == WT_Q5_K ? 32 : 0) + 32 * (j >> 1) + 8 * qd;
+                uint32_t w0 = (*reinterpret_cast<const uint32_t *>(qs)     >> (4 * (j & 1))) & 0x0F0F0F0Fu;
+                uint32_t w1 = (*reinterpret_cast<const uint32_t *>(qs + 4) >> (4 * (j & 1))) & 0x0F0F0F0Fu;
+                if (WT == WT_Q5_K) {
+                    const uint8_t * qh = blk + 16 + 8 * qd;
+                    w0 |= ((*reinterpret_cast<const uint32_t *>(qh)     >> j) & 0x01010101u) << 4;
+                    w1 |= ((*reinterpret_cast<const uint32_t *>(qh + 4) >> j) & 0x01010101u) << 4;
+                }
+                const float dl = __low2float(dm) * (float) sc, ml = __high2float(dm) * (float) mn;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (t < a.n_tok) {
+                        const uint8_t * tp = tokbase + t * tb;
+                        const int * xq = reinterpret_cast<const int *>(tp) + (sb * 256 + j * 32 + qd * 8) / 4;
+                        const float d8 = reinterpret_cast<const float *>(tp + K)[sb];
+                        const int xa = xq[0], xb = xq[1];
+                        const int sumi = __dp4a((int) w0, xa, __dp4a((int) w1, xb, 0));
+                        const int sumx = __dp4a(0x01010101, xa, __dp4a(0x01010101, xb, 0));
+                        acc[t] += d8 * (dl * (float) sumi - ml * (float) sumx);
+                    }
+                }
+            }
+        } else {
+            const int64_t rb = (int64_t) row * (K >> 5);
+            for (int c = lane; c < K / 8; c += 32) {           // chunk = quarter block
+                const int b = c >> 2, qd = c & 3;
+                const float dw = __half2float(a.W.d[rb + b]);
+                int vl, vh;
+                if (WT == WT_Q8_0) {
+                    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(a.W.qs + (rb + b) * 32) + qd);
+                    vl = (int) w.x; vh = (int) w.y;
+                } else {
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(a.W.qs + (rb + b) * 16) + qd);
+                    uint32_t lo = w & 0x0F0F0F0Fu, hi = (w >> 4) & 0x0F0F0F0Fu;
+                    if (WT == WT_Q5_0) {
+                        const uint32_t qh = __ldg(a.W.qh + rb + b);
+                        lo |= spread4_to_bit4(qh >> (4 * qd));
+                        hi |= spread4_to_bit4(qh >> (16 + 4 * qd));
+                        vl = (int) __vsub4(lo, 0x10101010u); vh = (int) __vsub4(hi, 0x10101010u);
+                    } else {
+                        vl = (int) __vsub4(lo, 0x08080808u); vh = (int) __vsub4(hi, 0x08080808u);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    if (t < a.n_tok) {
+                        const uint8_t * tp = tokbase + t * tb;
+                        const int * xq = reinterpret_cast<const int *>(tp);
+                        const float dx = reinterpret_cast<const float *>(tp + K)[b];
+                        int xa, xb;
+                        if (WT == WT_Q8_0) { xa = xq[b * 8 + 2 * qd]; xb = xq[b * 8 + 2 * qd + 1]; }
+                        else               { xa = xq[b * 8 + qd];     xb = xq[b * 8 + 4 + qd]; }
+                        const int sumi = __dp4a(vl, xa, __dp4a(vh, xb, 0));
+                        acc[t] = fmaf(dw * dx, (float) sumi, acc[t]);
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = warp_sum(acc[t]);
+        if (lane == 0) {
+            const float bias = a.bias ? a.bias[row] : 0.0f;
+            const float scl  = a.scale ? a.scale[row] : 1.0f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (t < a.n_tok) {
+                    float v = (acc[t] + bias) * scl;
+                    if (a.act == 1) v = gelu_ref_f16(v);
+                    if (a.res) v += a.res[(int64_t) t * N + row];
+                    if (a.out) a.out[(int64_t) t * N + row] = v;
+                    if (a.k_cache && row >= a.kv_d) {
+                        const int64_t cell = a.cells[t];
+                        if (row < 2 * a.kv_d) a.k_cache[cell * a.kv_d + (row - a.kv_d)] = __float2half_rn(v);
+                        else                  a.v_cache[cell * a.kv_d + (row - 2 * a.kv_d)] = __float2half_rn(v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int WT, int NT>
+static void gemv_launch(const GemvK & k, cudaStream_t st) {
+    const int K = k.W.K, N = k.W.N;
+    size_t tokb;
+    if (WT == WT_F16) tokb = (size_t) K * 2;
+    else if (WT == WT_Q4_K || WT == WT_Q5_K) tokb = (size_t) K + (size_t) (K / 256) * 4 + (size_t) (K / 32) * 4;
+    else tokb = (size_t) K + (size_t) (K / 32) * 4;
+    tokb = (tokb + 15) & ~size_t(15);
+    const size_t smem = (size_t) K * 4 + tokb * k.n_tok;
+    auto kern = k_gemv<WT, NT>;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); smem_set = smem; }
+    int grid = (N + 7) / 8;                  // one row per warp per pass
+    const int cap = 148 * 4;                 // keep the per-CTA prologue amortised over several rows
+    if (grid > cap) grid = cap;
+    kern<<<grid, 256, smem, st>>>(k); count_launch();
+}
+template <int WT>
+static void gemv_nt(const GemvK & k, cudaStream_t st) {
+    if (k.n_tok <= 1)      gemv_launch<WT, 1>(k, st);
+    else if (k.n_tok <= 2) gemv_launch<WT, 2>(k, st);
+    else if (k.n_tok <= 4) gemv_launch<WT, 4>(k, st);
+    else                   gemv_launch<WT, 8>(k, st);
+}
+void gemv(const GemvArgs & a, cudaStream_t st) {
+    GemvK k; k.W = a.W; k.x = a.x; k.n_tok = a.n_tok; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.eps = a.eps;
+    k.bias = a.bias; k.scale = a.scale; k.act = a.act; k.res = a.res; k.out = a.out;
+    k.k_cache = a.k_cache; k.v_cache = a.v_cache; k.cells = a.cells; k.kv_d = a.kv_d;
+    switch (a.W.type) {
+        case WT_F16:  gemv_nt<WT_F16>(k, st);  break;
+        case WT_Q4_0: gemv_nt<WT_Q4_0>(k, st); break;
+        case WT_Q5_0: gemv_nt<WT_Q5_0>(k, st); break;
+        case WT_Q8_0: gemv_nt<WT_Q8_0>(k, st); break;
+        case WT_Q4_K: gemv_nt<WT_Q4_K>(k, st); break;
+        case WT_Q5_K: gemv_nt<WT_Q5_K>(k, st); break;
+        default: set_error("gemv: unsupported weight type %d", a.W.type);
+    }
+}
+
+// =====================================================================================================================
+//  decode-step attention (ggml_flash_attn_ext on CPU: ggml-cpu/ops.cpp:8479-8715): Q is rounded to f16, K/V are f16,
+//  scores and the running sums are f32 here (the CPU accumulates V in f16; f32 is strictly closer to exact).
+// =====================================================================================================================
+__device__ __forceinline__ float dot64_f16(const __half * __restrict__ k, const float * __restrict__ q) {
+    float s = 0.0f;
+    const uint4 * k4 = reinterpret_cast<const uint4 *>(k);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = k4[c];
+        const __half2 * h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); s = fmaf(f.x, q[c*8 + 2*e], s); s = fmaf(f.y, q[c*8 + 2*e + 1], s); }
+    }
+    return s;
+}
+
+// grid (n_head, n_tok), block 128
+__global__ void __launch_bounds__(128)
+k_attn_self(const float * __restrict__ q, int ldq, const __half * __restrict__ kc, const __half * __restrict__ vc,
+            const int * __restrict__ idx, int ld_idx, const int * __restrict__ n_kv, int d, float * __restrict__ out, int ldo) {
+    extern __shared__ float sh[];            // qh[64] | sc[max n_kv] | part[2][64]
+    __shared__ float red[32];
+    const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const int nk = n_kv[t];
+    float * qh = sh; float * sc = sh + 64; float * part = sc + ((ld_idx + 3) & ~3);
+    if (tid < 64) qh[tid] = __half2float(__float2half_rn(q[(int64_t) t * ldq + h * 64 + tid]));
+    __syncthreads();
+    const int * cells = idx + (int64_t) t * ld_idx;
+    float m = -INFINITY;
+    for (int i = tid; i < nk; i += 128) {
+        const float s = dot64_f16(kc + (int64_t) cells[i] * d + h * 64, qh);
+        sc[i] = s; m = fmaxf(m, s);
+    }
+    m = block_max(m, red);
+    float l = 0.0f;
+    for (int i = tid; i < nk; i += 128) { const float p = expf(sc[i] - m); sc[i] = p; l += p; }
+    l = block_sum(l, red);
+    const int f = tid & 63, g = tid >> 6;
+    float acc = 0.0f;
+    for (int i = g; i < nk; i += 2) acc = fmaf(sc[i], __half2float(vc[(int64_t) cells[i] * d + h * 64 + f]), acc);
+    part[g * 64 + f] = acc;
+    __syncthreads();
+    if (tid < 64) out[(int64_t) t * ldo + h * 64 + tid] = (l > 0.0f) ? (part[tid] + part[64 + tid]) / l : 0.0f;
+}
+void attn_self_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * idx, int ld_idx,
+                      const int * n_kv, int n_tok, int n_head, int d, float * out, int ldo, cudaStream_t st) {
+    const size_t smem = (64 + ((ld_idx + 3) & ~3) + 128) * sizeof(float);
+    k_attn_self<<<dim3(n_head, n_tok), 128, smem, st>>>(q, ldq, kc, vc, idx, ld_idx, n_kv, d, out, ldo); count_launch();
+}
+
+// grid (n_head, NSPLIT, n_tok), block 128.  Split-KV with an in-kernel combine by the last CTA of each (token, head).
+static constexpr int XSPLIT = 8;
+__global__ void __launch_bounds__(128)
+k_attn_cross(const float * __restrict__ q, int ldq, const __half * __restrict__ kc, const __half * __restrict__ vc,
+             const int * __restrict__ slot, int64_t slot_stride, int n_keys, int d, float scale,
+             float * __restrict__ partial, int * __restrict__ counters, float * __restrict__ out, int ldo) {
+    __shared__ float qh[64];
+    __shared__ float sc[256];
+    __shared__ float part[128];
+    __shared__ float red[32];
+    __shared__ int   is_last;
+    const int h = blockIdx.x, sp = blockIdx.y, t = blockIdx.z, tid = threadIdx.x, n_head = gridDim.x;
+    const int per = (n_keys + XSPLIT - 1) / XSPLIT;          // <= 256
+    const int k0 = sp * per, k1 = min(n_keys, k0 + per);
+    const __half * kb = kc + (int64_t) slot[t] * slot_stride;
+    const __half * vb = vc + (int64_t) slot[t] * slot_stride;
+    if (tid < 64) qh[tid] = __half2float(__float2half_rn(q[(int64_t) t * ldq + h * 64 + tid]));
+    __syncthreads();
+    float m = -INFINITY;
+    for (int i = k0 + tid; i < k1; i += 128) {
+        const float s = dot64_f16(kb + (int64_t) i * d + h * 64, qh) * scale;
+        sc[i - k0] = s; m = fmaxf(m, s);
+    }
+    m = block_max(m, red);
+    float l = 0.0f;
+    for (int i = k0 + tid; i < k1; i += 128) { const float p = expf(sc[i - k0] - m); sc[i - k0] = p; l += p; }
+    l = block_sum(l, red);
+    const int f = tid & 63, g = tid >> 6;
+    float acc = 0.0f;
+    for (int i = k0 + g; i < k1; i += 2) acc = fmaf(sc[i - k0], __half2float(vb[(int64_t) i * d + h * 64 + f]), acc);
+    part[g * 64 + f] = acc;
+    __syncthreads();
+    float * pp = partial + (((int64_t) t * n_head + h) * XSPLIT + sp) * 66;
+    if (tid < 64) pp[2 + tid] = part[tid] + part[64 + tid];
+    if (tid == 0) { pp[0] = m; pp[1] = l; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(&counters[t * n_head + h], 1);
+        is_last = (prev == XSPLIT - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float * p0 = partial + ((int64_t) t * n_head + h) * XSPLIT * 66;
+    float M = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < XSPLIT; ++s) M = fmaxf(M, p0[s * 66]);
+    if (tid < 64) {
+        float L = 0.0f, o = 0.0f;
+#pragma unroll
+        for (int s = 0; s < XSPLIT; ++s) {
+            const float w = expf(p0[s * 66] - M);
+            L = fmaf(p0[s * 66 + 1], w, L);
+            o = fmaf(p0[s * 66 + 2 + tid], w, o);
+        }
+        out[(int64_t) t * ldo + h * 64 + tid] = o / L;
+    }
+    if (tid == 0) counters[t * n_head + h] = 0;
+}
+void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * slot, int64_t slot_stride,
+                       int n_keys, int n_tok, int n_head, int d, float scale, float * partial, int * counters,
+                       float * out, int ldo, cudaStream_t st) {
+    k_attn_cross<<<dim3(n_head, XSPLIT, n_tok), 128, 0, st>>>(q, ldq, kc, vc, slot, slot_stride, n_keys, d, scale, partial, counters, out, ldo);
+    count_launch();
 }
 
 } // namespace wb

@@ -7,9 +7,59 @@
 
 namespace wb {
 
+// ---- conversions / weight re-layout -------------------------------------------------------------------------------
 void f32_to_f16(const float * src, __half * dst, int64_t n, cudaStream_t st);
-
-// file-layout 32-blocks (18/22/34 B) -> planar arrays inside `dst` (same total bytes, 64 B slack); fills `out`
+void f16_to_f32(const __half * src, float * dst, int64_t n, cudaStream_t st);
+// file-layout 32-blocks (18/22/34 B each, [rows][K/32]) -> planar arrays of `dst` (already offset to the first row)
+bool repack_block32_into(int wtype, const uint8_t * file_blocks_dev, const QMat & dst, int rows, int K, cudaStream_t st);
+// convenience for tests: carve the planar arrays out of one buffer
 bool repack_block32(int wtype, const uint8_t * file_blocks_dev, uint8_t * dst, int N, int K, QMat * out, cudaStream_t st);
+
+// ---- log-mel (src/whisper.cpp:3005-3272) ---------------------------------------------------------------------------
+// pcm: n_samples f32 on device.  mel: [n_mel][n_len] f32 with n_len = (n_samples + 480000)/160.  gmax: 1 float scratch.
+void mel_spectrogram(const float * pcm, int n_samples, const float * filters, int n_mel, float * mel, int n_len,
+                     float * gmax_scratch, cudaStream_t st);
+// window of 2*n_ctx frames starting at `seek` -> time-major f16 [2*n_ctx + 2][n_mel], rows 0 and 2*n_ctx+1 zero
+// (src/whisper.cpp:2389-2411: frames past n_len are zero)
+void mel_window_f16(const float * mel, int n_len, int n_mel, int seek, int n_frames, __half * out, cudaStream_t st);
+
+// ---- LayerNorm (ggml-cpu/ops.cpp:3698-3765 two-pass + mul/add, src/whisper.cpp:2108-2115) ---------------------------
+// out16 and/or out32 may be null
+void layernorm(const float * x, const float * w, const float * b, float eps, int rows, int d,
+               __half * out16, float * out32, cudaStream_t st);
+
+// ---- unfused attention helper: softmax over rows of f32 scores -> f16 probabilities --------------------------------
+void softmax_rows_f16(const float * s, __half * p, int64_t rows, int cols, cudaStream_t st);
+
+// ---- decoder step (src/whisper.cpp:2466-2844) -----------------------------------------------------------------------
+// x[t][:] = dequant(d_te[token[t]]) + d_pe[pos[t]]   (get_rows + add, whisper.cpp:2523-2526)
+void dec_embed(const QMat & te, const float * pe, const int * tokens, const int * pos, int n_tok, int d, float * x, cudaStream_t st);
+
+struct GemvArgs {
+    QMat W;                       // [N][K]
+    const float * x = nullptr;    // [n_tok][K] f32 (ldx = K)
+    int n_tok = 1;                // 1..8
+    const float * ln_w = nullptr; // optional fused LayerNorm of x before the contraction
+    const float * ln_b = nullptr;
+    float eps = 1e-5f;
+    const float * bias = nullptr;   // [N]
+    const float * scale = nullptr;  // [N] multiplies (acc + bias)
+    int act = 0;                    // 1: GELU (reference f16-table semantics)
+    const float * res = nullptr;    // [n_tok][N] added last (may alias out)
+    float * out = nullptr;          // [n_tok][N] f32 (nullable when only the KV store is wanted)
+    // optional KV append (decoder self-attention): rows [kv_d, 2kv_d) -> k_cache, [2kv_d, 3kv_d) -> v_cache, rounded to f16
+    __half * k_cache = nullptr; __half * v_cache = nullptr; const int * cells = nullptr; int kv_d = 0;
+};
+void gemv(const GemvArgs & a, cudaStream_t st);
+
+// self-attention for n_tok query tokens over a paged KV cache.  q: [n_tok][d] f32 (already scaled),
+// k/v cache: [n_cells][d] f16 for this layer.  idx[t*ld_idx + i], i < n_kv[t] lists the cells token t may attend to.
+void attn_self_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * idx, int ld_idx,
+                      const int * n_kv, int n_tok, int n_head, int d, float * out, int ldo, cudaStream_t st);
+// cross-attention over the 1536 padded keys (zero rows included, whisper.cpp:2689-2703). kc/vc: per-token base pointers
+// are kc + slot[t]*slot_stride.  partial: scratch [n_tok][n_head][NSPLIT][66] f32, counters: [n_tok][n_head] ints (zeroed).
+void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * slot, int64_t slot_stride,
+                       int n_keys, int n_tok, int n_head, int d, float scale, float * partial, int * counters,
+                       float * out, int ldo, cudaStream_t st);
 
 } // namespace wb
