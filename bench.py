@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- xRT (audio seconds / wall seconds) + encode ms of the Whisper hot path on B200.
+
+Workload (BASELINE.json configs[3] scaled to one GPU): large-v3 Q5_0, synthetic weights (no checkpoints offline),
+8 independent 30 s chunks per GPU, greedy decode (best_of=1, no temperature fallback), timestamps on.  A "step" is
+one pass over the rank's 8 chunks.  Multi-GPU = independent chunks per rank, no collective on the data path
+(weak scaling); torch.distributed is used only for the barrier and the max-over-ranks time.
+
+  value  : xRT with the PCM already resident in HBM (wb200_pcm_upload before the timed region)
+  e2e    : xRT through whisper_full_with_state with HOST PCM buffers (H2D of the samples, D2H of the logits inside)
+  roofline / cpu_baseline : see DESIGN.md section 6
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, unmodified whisper.cpp) on a bounded
+sample of the same workload (1 chunk per step) with all host threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_pkg  # noqa: E402
+
+CHUNKS_PER_GPU = 8
+CHUNK_SECONDS = 30.0
+MODEL_CFG = "large-v3"
+WORKLOAD = "large-v3 Q5_0 (synthetic weights), %d x 30 s chunks per GPU, greedy best_of=1, no fallback, timestamps on" % CHUNKS_PER_GPU
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j.get("hbm_gbs", 6650.0)), float(j.get("bf16_tflops_sustained", 1400.0)), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank, n_chunks):
+    synth = load_pkg().synth
+    return [synth.synth_audio(seed=1000 * rank + i, seconds=CHUNK_SECONDS) for i in range(n_chunks)]
+
+
+def ensure_model(path, wtype_name="q5_0"):
+    synth = load_pkg().synth
+    if not os.path.exists(path):
+        tmp = path + ".tmp.%d" % os.getpid()
+        synth.write_model(tmp, MODEL_CFG, synth.Q5_0, seed=0, fast_pool=True)
+        os.replace(tmp, path)
+    return path
+
+
+def full_params(L, n_threads):
+    p = L.whisper_full_default_params(0)
+    p.print_progress = False
+    p.greedy.best_of = 1
+    p.temperature_inc = 0.0
+    p.n_threads = n_threads
+    return p
+
+
+def count_tokens(L, state):
+    n = 0
+    for i in range(L.whisper_full_n_segments_from_state(state)):
+        n += L.whisper_full_n_tokens_from_state(state, i)
+    return n
+
+
+def run_reference(args, rank, world):
+    """reference arm: unmodified whisper.cpp CPU path (oracle/_ref) on 1 chunk per step, all host threads"""
+    if rank != 0:
+        return
+    pkg = load_pkg()
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
+    R = pkg.bind_whisper_api(C.CDLL(ref_path))
+    model = ensure_model(os.path.join(tempfile.gettempdir(), "wb200-%s-q5_0.bin" % MODEL_CFG))
+    cp = R.whisper_context_default_params(); cp.use_gpu = False
+    ctx = R.whisper_init_from_file_with_params(model.encode(), cp)
+    assert ctx
+    cores = os.cpu_count() or 1
+    pcm = make_inputs(0, 1)[0]
+    p = full_params(R, cores)
+    times = []
+    enc_ms = []
+    for it in range(args.warmup + args.steps):
+        R.whisper_reset_timings(ctx)
+        t0 = time.perf_counter()
+        rc = R.whisper_full(ctx, p, pcm.ctypes.data_as(C.c_void_p), len(pcm))
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        tm = R.whisper_get_timings(ctx)
+        if it >= args.warmup:
+            times.append(dt); enc_ms.append(tm.contents[1])
+    total = sum(times)
+    xrt = CHUNK_SECONDS * len(times) / total
+    out = {"impl": "reference", "metric": "xRT (audio-s/wall-s)", "value": xrt, "unit": "x real time", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "int8xint8->i32 block dot (Q5_0 x Q8_0), f32 accumulate", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "sample": "1 chunk (30 s) per step"},
+           "encode_ms": float(np.mean(enc_ms)),
+           "cpu_baseline": {"value": xrt, "unit": "x real time", "cores": cores, "kind": "reference", "sample": "1 x 30 s chunk per step, whisper_full greedy, n_threads=%d" % cores},
+           "e2e": {"value": xrt, "unit": "x real time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=CHUNKS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = load_pkg()
+    model = os.path.join(tempfile.gettempdir(), "wb200-%s-q5_0.bin" % MODEL_CFG)
+    if local == 0:
+        ensure_model(model)
+    if world > 1:
+        dist.barrier()
+
+    eng = pkg.WhisperB200(model, gpu_device=local)
+    L = eng.L
+    vp = C.c_void_p
+    L.whisper_full_with_state.argtypes = [vp, vp, pkg.FullParams, vp, C.c_int]
+    L.wb200_pcm_upload.argtypes = [vp, vp, C.c_int]
+    L.wb200_traffic.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.wb200_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.wb200_last_encode_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    n_chunks = args.chunks
+    pcms = make_inputs(rank, n_chunks)
+    pinned = [torch.from_numpy(p).pin_memory() for p in pcms]          # e2e copies start from pinned host memory
+    states = [L.whisper_init_state(eng.ctx) for _ in range(n_chunks)]
+    assert all(states), L.wb200_last_error()
+    p = full_params(L, 4)
+    n_streams = int(os.environ.get("WB200_BATCH_STREAMS", "4"))
+
+    def run_pass(resident):
+        """one step: every chunk of this rank through whisper_full_with_state, n_streams states in flight"""
+        nxt = [0]; lock = threading.Lock(); rcs = []
+
+        def work():
+            while True:
+                with lock:
+                    i = nxt[0]; nxt[0] += 1
+                if i >= n_chunks:
+                    return
+                ptr = None if resident else C.c_void_p(pinned[i].data_ptr())
+                rcs.append(L.whisper_full_with_state(eng.ctx, states[i], p, ptr, len(pcms[i])))
+
+        th = [threading.Thread(target=work) for _ in range(min(n_streams, n_chunks))]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert all(r == 0 for r in rcs), (rcs, L.wb200_last_error())
+
+    def timed(resident, steps, warmup):
+        for _ in range(warmup):
+            run_pass(resident)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        h0, d0 = C.c_uint64(), C.c_uint64(); L.wb200_traffic(C.byref(h0), C.byref(d0))
+        n0 = eng.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run_pass(resident)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h1, d1 = C.c_uint64(), C.c_uint64(); L.wb200_traffic(C.byref(h1), C.byref(d1))
+        launches = eng.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, launches, (h1.value - h0.value) / steps, (d1.value - d0.value) / steps
+
+    # ---- device-resident inputs ("value")
+    for i in range(n_chunks):
+        assert L.wb200_pcm_upload(states[i], C.c_void_p(pinned[i].data_ptr()), len(pcms[i])) == 0
+    sampler = ClockSampler(local); sampler.start()
+    dt_res, launches, _, _ = timed(True, args.steps, args.warmup)
+    clocks = sampler.stop()
+    audio_s = CHUNK_SECONDS * n_chunks * args.steps * world
+    value = audio_s / dt_res
+    tokens = sum(count_tokens(L, s) for s in states)
+    enc = (C.c_float * 4)()
+    L.wb200_last_encode_ms(states[0], enc)
+
+    # ---- host buffers through the C ABI ("e2e")
+    dt_e2e, _, h2d, d2h = timed(False, args.steps, 1)
+    e2e = audio_s / dt_e2e
+
+    out = {"metric": "xRT (audio-s/wall-s)", "value": value, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f16 tcgen05 (encode) / int8 dp4a block dot (decode), f32 accumulate", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "streams_per_gpu": n_streams, "l2": "inputs and weights (1.06 GB/GPU + 0.65 GB/state) exceed the 126 MB L2"},
+           "encode_ms": float(enc[1] + enc[2] + enc[3]), "encode_ms_parts": {"mel": float(enc[0]), "conv": float(enc[1]), "encoder": float(enc[2]), "cross": float(enc[3])},
+           "decoded_tokens_per_step": tokens, "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel class: separate pass of ONE chunk with per-launch CUDA events (library side,
+        # on the launching stream); not inside the timed region so the event overhead does not perturb `value`
+        L.wb200_profile_enable(1)
+        assert L.whisper_full_with_state(eng.ctx, states[0], p, None, len(pcms[0])) == 0
+        ms = (C.c_double * 4)(); ln = (C.c_uint64 * 4)(); by = (C.c_double * 4)(); fl = (C.c_double * 4)()
+        L.wb200_profile_collect(ms, ln, by, fl)
+        L.wb200_profile_enable(0)
+        hbm, tf, how = measured_peaks()
+        names = ["tcgen05_gemm", "gemv_q5_0", "decode_attention", "other"]
+        classes = {names[i]: {"ms": ms[i], "launches": int(ln[i]), "GBps": (by[i] / 1e9) / (ms[i] / 1e3) if ms[i] > 0 else 0.0,
+                              "TFLOPs": (fl[i] / 1e12) / (ms[i] / 1e3) if ms[i] > 0 else 0.0} for i in range(4)}
+        dom = max(range(3), key=lambda i: ms[i])
+        if dom == 0:
+            roof = {"kernel": names[0], "bound": "tensor", "achieved": classes[names[0]]["TFLOPs"], "peak": tf, "unit": "TFLOP/s", "frac": classes[names[0]]["TFLOPs"] / tf, "traffic": None, "peak_source": how + " (sustained bf16)"}
+        else:
+            roof = {"kernel": names[dom], "bound": "hbm", "achieved": classes[names[dom]]["GBps"], "peak": hbm, "unit": "GB/s", "frac": classes[names[dom]]["GBps"] / hbm, "traffic": None, "peak_source": how}
+        out["roofline"] = roof
+        out["kernel_classes"] = classes
+        if not args.no_cpu_baseline:
+            try:
+                ref_path = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
+                R = pkg.bind_whisper_api(C.CDLL(ref_path))
+                cp = R.whisper_context_default_params(); cp.use_gpu = False
+                rctx = R.whisper_init_from_file_with_params(model.encode(), cp)
+                cores = os.cpu_count() or 1
+                rp = full_params(R, cores)
+                t0 = time.perf_counter()
+                assert R.whisper_full(rctx, rp, pcms[0].ctypes.data_as(vp), len(pcms[0])) == 0
+                dt = time.perf_counter() - t0
+                tm = R.whisper_get_timings(rctx)
+                out["cpu_baseline"] = {"value": CHUNK_SECONDS / dt, "unit": "x real time", "cores": cores, "kind": "reference",
+                                       "sample": "1 x 30 s chunk of the same workload, unmodified whisper.cpp CPU (AVX2 build), n_threads=%d" % cores,
+                                       "encode_ms": float(tm.contents[1]), "decode_ms_per_token": float(tm.contents[2])}
+                R.whisper_free(rctx)
+            except Exception as e:  # noqa: BLE001
+                out["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(out), flush=True)
+    for s in states:
+        L.whisper_free_state(s)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -417,6 +417,18 @@ WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * state, int which, flo
 WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                                const float * const * samples, const int * n_samples, int n_chunks,
                                struct whisper_state ** states_out);
+/* the default state owned by a context created with a *_with_params (non-_no_state) call; NULL otherwise */
+WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx);
+/* stage PCM in HBM ahead of time: a following whisper_full_with_state(ctx, state, params, NULL, n_samples) (or
+ * whisper_pcm_to_mel_with_state with samples == NULL) then starts from the device-resident samples (bench.py `value`) */
+WB_EXPORT int wb200_pcm_upload(struct whisper_state * state, const float * samples, int n_samples);
+/* per-kernel-class CUDA-event timing (classes: 0 tcgen05 GEMM, 1 decode GEMV, 2 decode attention, 3 other).
+ * enable(1) clears the accumulators; collect() synchronises the device and fills four arrays of 4 entries:
+ * summed duration [ms], launches, algorithmic bytes, algorithmic flops. */
+WB_EXPORT void wb200_profile_enable(int on);
+WB_EXPORT void wb200_profile_collect(double * ms4, uint64_t * launches4, double * bytes4, double * flops4);
+/* bytes this library has copied host->device / device->host since load */
+WB_EXPORT void wb200_traffic(uint64_t * h2d, uint64_t * d2h);
 /* last CUDA error text for this thread ("" when none) */
 WB_EXPORT const char * wb200_last_error(void);
 /* number of CUDA kernels this library has launched since load (bench.py's gpu_launches) */

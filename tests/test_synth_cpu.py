@@ -1,0 +1,44 @@
+"""CPU tests of the synthetic-model tooling (whisper.cpp_b200/synth.py): the NumPy block quantisers are bit-identical
+to ggml's reference quantisers, the mel filterbank equals the one shipped inside the reference's own model files, and
+the files it writes load in the UNMODIFIED reference (loader/format parity, src/whisper.cpp:1485-1962)."""
+import importlib.util
+import os
+import ctypes as C
+import numpy as np
+import pytest
+
+from wbtest import ROOT, DATA_DIR, Q4_0, Q5_0, Q8_0, F16, ref_quantize, bind_whisper_api, parse_model_header
+
+spec = importlib.util.spec_from_file_location("wb_synth", os.path.join(ROOT, "whisper.cpp_b200", "synth.py"))
+synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+
+
+@pytest.mark.parametrize("wtype", [Q4_0, Q5_0, Q8_0])
+def test_numpy_quantisers_bit_exact_vs_ggml(ref, wtype):
+    rng = np.random.default_rng(wtype)
+    w = (rng.standard_normal((64, 1280)) * 0.02).astype(np.float32)
+    w[0, :32] = 0.0
+    w[1, 5] = 0.5
+    assert synth.quantize(wtype, w) == ref_quantize(ref, wtype, w)
+
+
+@pytest.mark.parametrize("stub,n_mels", [("for-tests-ggml-tiny.en.bin", 80)])
+def test_mel_filterbank_matches_reference_model_files(stub, n_mels):
+    _, filt = parse_model_header(os.path.join(DATA_DIR, stub))
+    mine = synth.mel_filters(n_mels)
+    assert mine.shape == filt.shape
+    assert np.abs(mine - filt).max() < 1e-6
+
+
+@pytest.mark.parametrize("wtype", [F16, Q5_0])
+def test_written_model_loads_in_reference(ref, tmp_path, wtype):
+    bind_whisper_api(ref)
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", wtype, seed=1, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    cp = ref.whisper_context_default_params(); cp.use_gpu = False
+    ctx = ref.whisper_init_from_file_with_params(path.encode(), cp)
+    assert ctx
+    assert ref.whisper_model_n_audio_layer(ctx) == 2 and ref.whisper_model_n_text_state(ctx) == 384
+    assert ref.whisper_model_ftype(ctx) == synth.FTYPE_OF[wtype]
+    assert ref.whisper_token_to_str(ctx, 220) == b" "
+    ref.whisper_free(ctx)

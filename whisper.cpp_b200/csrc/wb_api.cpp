@@ -252,7 +252,7 @@ WB_EXPORT int whisper_ctx_init_openvino_encoder(struct whisper_context *, const 
 
 // ---------------------------------------------------------------------------------------------------- low-level pipeline
 WB_EXPORT int whisper_pcm_to_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * samples, int n_samples, int) {
-    if (!ctx || !st || (n_samples > 0 && !samples) || n_samples < 0) return -1;
+    if (!ctx || !st || n_samples < 0) return -1;     // samples == NULL is legal after wb200_pcm_upload (device-resident input)
     const int64_t t0 = time_us();
     if (!st->eng.pcm_to_mel(samples, n_samples)) { logf(LOG_ERROR, "%s: failed to compute mel spectrogram\n", __func__); return -1; }
     st->t_mel_us += time_us() - t0;
@@ -524,6 +524,14 @@ WB_EXPORT int wb200_last_encode_ms(struct whisper_state * st, float * out4) {
     for (int i = 0; i < 4; ++i) out4[i] = st->eng.last_ms[i];
     return 0;
 }
+WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx) { return ctx ? ctx->state : nullptr; }
+WB_EXPORT int wb200_pcm_upload(struct whisper_state * st, const float * samples, int n_samples) {
+    if (!st || !samples || n_samples <= 0) return -1;
+    return st->eng.pcm_upload(samples, n_samples) ? 0 : -1;
+}
+WB_EXPORT void wb200_profile_enable(int on) { wb::prof_enable(on != 0); }
+WB_EXPORT void wb200_profile_collect(double * ms4, uint64_t * launches4, double * bytes4, double * flops4) { wb::prof_collect(ms4, launches4, bytes4, flops4); }
+WB_EXPORT void wb200_traffic(uint64_t * h2d, uint64_t * d2h) { if (h2d) *h2d = wb::h2d_bytes(); if (d2h) *d2h = wb::d2h_bytes(); }
 WB_EXPORT const char * wb200_last_error(void) { return wb::last_error(); }
 WB_EXPORT uint64_t wb200_launch_count(void)   { return wb::launch_count(); }
 

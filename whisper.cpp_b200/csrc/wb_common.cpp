@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace wb {
 
@@ -19,6 +20,49 @@ const char * last_error() { return g_err; }
 
 void     count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 uint64_t launch_count()           { return g_launches.load(std::memory_order_relaxed); }
+
+static std::atomic<uint64_t> g_h2d{0}, g_d2h{0};
+void count_h2d(uint64_t n) { g_h2d.fetch_add(n, std::memory_order_relaxed); }
+void count_d2h(uint64_t n) { g_d2h.fetch_add(n, std::memory_order_relaxed); }
+uint64_t h2d_bytes() { return g_h2d.load(); }
+uint64_t d2h_bytes() { return g_d2h.load(); }
+
+// ---- profiling -------------------------------------------------------------------------------------------------------
+struct ProfEntry { int cls; cudaEvent_t e0, e1; double bytes, flops; };
+static std::atomic<bool> g_prof{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof_entries;
+void prof_enable(bool on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto & e : g_prof_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    g_prof_entries.clear();
+    g_prof.store(on);
+}
+bool prof_enabled() { return g_prof.load(std::memory_order_relaxed); }
+ProfScope::ProfScope(int cls, cudaStream_t stream, double bytes, double flops) : st(stream) {
+    if (!prof_enabled()) return;
+    ProfEntry e; e.cls = cls; e.bytes = bytes; e.flops = flops;
+    if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess) return;
+    cudaEventRecord(e.e0, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    idx = (int) g_prof_entries.size();
+    g_prof_entries.push_back(e);
+}
+ProfScope::~ProfScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (idx < (int) g_prof_entries.size()) cudaEventRecord(g_prof_entries[idx].e1, st);
+}
+void prof_collect(double * ms, uint64_t * launches, double * bytes, double * flops) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int c = 0; c < PC_COUNT; ++c) { ms[c] = 0; launches[c] = 0; bytes[c] = 0; flops[c] = 0; }
+    for (auto & e : g_prof_entries) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, e.e0, e.e1) != cudaSuccess) continue;
+        ms[e.cls] += t; launches[e.cls]++; bytes[e.cls] += e.bytes; flops[e.cls] += e.flops;
+    }
+}
 
 // log sink: installed by whisper_log_set (wb_api.cpp); signature mirrors ggml_log_callback
 typedef void (*log_cb_t)(int level, const char * text, void * user);

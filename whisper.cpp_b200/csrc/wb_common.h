@@ -15,6 +15,25 @@ const char * last_error();
 void     count_launch(uint64_t n = 1);
 uint64_t launch_count();
 
+// ---- optional per-kernel-class timing (CUDA events on the launching stream); off by default.  bench.py uses it for
+// the roofline entry: algorithmic bytes / flops are supplied by the launcher, durations come from event pairs.
+enum ProfClass { PC_GEMM = 0, PC_GEMV = 1, PC_ATTN = 2, PC_OTHER = 3, PC_COUNT = 4 };
+void prof_enable(bool on);
+bool prof_enabled();
+struct ProfScope {
+    int idx = -1; cudaStream_t st;
+    ProfScope(int cls, cudaStream_t stream, double bytes, double flops);
+    ~ProfScope();
+};
+// sums since the last prof_enable(true); synchronises the device.  arrays of PC_COUNT
+void prof_collect(double * ms, uint64_t * launches, double * bytes, double * flops);
+
+// host<->device traffic issued by the library (bytes), for bench.py's e2e accounting
+void     count_h2d(uint64_t n);
+void     count_d2h(uint64_t n);
+uint64_t h2d_bytes();
+uint64_t d2h_bytes();
+
 // logging through the whisper_log_set callback (default: stderr)
 enum LogLevel { LOG_DEBUG = 1, LOG_INFO = 2, LOG_WARN = 3, LOG_ERROR = 4 };
 void logf(int level, const char * fmt, ...) __attribute__((format(printf, 2, 3)));

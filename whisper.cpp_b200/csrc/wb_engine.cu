@@ -66,14 +66,25 @@ bool Engine::set_cells(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------------- audio front-end
+bool Engine::pcm_upload(const float * samples, int n_samples) {
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    if ((size_t) n_samples > pcm.n && !pcm.alloc(std::max(n_samples, 1))) return false;
+    if (n_samples > 0) { WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st)); count_h2d((uint64_t) n_samples * 4); }
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    pcm_resident = n_samples;
+    return true;
+}
 bool Engine::pcm_to_mel(const float * samples, int n_samples) {
     WB_CUDA_OK(cudaSetDevice(m->device));
+    if (!samples && n_samples > 0 && pcm_resident != n_samples) { set_error("pcm_to_mel: no host samples and no resident PCM of %d samples", n_samples); return false; }
     n_mel = m->n_filt_mel;
     n_len = (n_samples + 480000) / 160;                       // whisper.cpp:3202-3218
     n_len_org = 1 + (n_samples + 200 - 400) / 160;            // whisper.cpp:3220
-    if (!pcm.alloc(std::max(n_samples, 1)) || !mel.alloc((size_t) n_mel * n_len)) return false;
+    if (samples) pcm_resident = 0;
+    if ((size_t) std::max(n_samples, 1) > pcm.n && !pcm.alloc(std::max(n_samples, 1))) return false;
+    if ((size_t) n_mel * n_len > mel.n && !mel.alloc((size_t) n_mel * n_len)) return false;
     WB_CUDA_OK(cudaEventRecord(ev[0], st));
-    if (n_samples > 0) WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st));
+    if (n_samples > 0 && samples) { WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st)); count_h2d((uint64_t) n_samples * 4); }
     mel_spectrogram(pcm.p, n_samples, m->filters, n_mel, mel.p, n_len, gmax.p, st);
     WB_CUDA_OK(cudaEventRecord(ev[1], st));
     WB_CUDA_OK(cudaStreamSynchronize(st));
@@ -83,7 +94,7 @@ bool Engine::pcm_to_mel(const float * samples, int n_samples) {
 bool Engine::set_mel(const float * data, int n_len_, int n_mel_) {
     WB_CUDA_OK(cudaSetDevice(m->device));
     n_len = n_len_; n_len_org = n_len_; n_mel = n_mel_;
-    if (!mel.alloc((size_t) std::max(1, n_mel * n_len))) return false;
+    if ((size_t) std::max(1, n_mel * n_len) > mel.n && !mel.alloc((size_t) std::max(1, n_mel * n_len))) return false;
     if (data) WB_CUDA_OK(cudaMemcpyAsync(mel.p, data, (size_t) n_mel * n_len * 4, cudaMemcpyHostToDevice, st));
     else      WB_CUDA_OK(cudaMemsetAsync(mel.p, 0, (size_t) n_mel * n_len * 4, st));   // whisper-bench passes NULL, 0 (bench.cpp:69)
     WB_CUDA_OK(cudaStreamSynchronize(st));
@@ -247,6 +258,7 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         }
         const size_t nint = 40 + (size_t) (n - 1) * ld_idx + max_kv;
         WB_CUDA_OK(cudaMemcpyAsync(dints.p, hints, nint * sizeof(int), cudaMemcpyHostToDevice, st));
+        count_h2d(nint * sizeof(int));
         const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_idx = dints.p + 40;
 
         dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
@@ -271,8 +283,10 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         if (any_logits) {
             GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
             gemv(a, st);
-            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits)
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) {
                 WB_CUDA_OK(cudaMemcpyAsync(hlogits + (size_t) j * V, dlogits.p + (size_t) j * V, (size_t) V * 4, cudaMemcpyDeviceToHost, st));
+                count_d2h((uint64_t) V * 4);
+            }
         }
         WB_CUDA_OK(cudaStreamSynchronize(st));
         if (any_logits && logits_out)

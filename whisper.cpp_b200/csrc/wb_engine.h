@@ -28,6 +28,7 @@ struct Engine {
     // ---- audio front-end
     DevBuf<float> pcm, mel, gmax;
     int n_len = 0, n_len_org = 0, n_mel = 0;
+    int pcm_resident = 0;            // samples already in `pcm` (wb200_pcm_upload); pcm_to_mel(nullptr, n) then skips the H2D copy
 
     // ---- encoder workspaces
     int Tp_max = 0;
@@ -54,6 +55,7 @@ struct Engine {
     bool set_cells(int n);           // (re)allocate the self-KV pool; contents are lost
 
     // PCM (host) -> mel on device.  Returns false on CUDA error.
+    bool pcm_upload(const float * samples, int n_samples);
     bool pcm_to_mel(const float * samples, int n_samples);
     bool set_mel(const float * data, int n_len, int n_mel);
     bool read_mel(std::vector<float> & out);

@@ -1,0 +1,684 @@
+// wb_full.cpp -- whisper_full / whisper_full_with_state / whisper_full_parallel and the host-side decoding policy:
+// logits filtering, greedy / temperature / beam sampling, timestamp-driven window advance, fallback ladder, segment
+// emission.  Semantics follow src/whisper.cpp:5947-6053 (defaults), 6156-6667 (filters, samplers, scoring),
+// 6831-7788 (seek loop) and 7813-7941 (parallel); the device work goes through wb::encode_window / wb::decode_batch.
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <regex>
+#include <thread>
+#include "wb_state.h"
+
+using namespace wb;
+
+namespace {
+
+const char * const k_non_speech[] = {   // src/whisper.cpp:6149-6154
+    "\"", "#", "(", ")", "*", "+", "/", ":", ";", "<", "=", ">", "@", "[", "\\", "]", "^",
+    "_", "`", "{", "|", "}", "~", "「", "」", "『", "』", "<<", ">>", "<<<", ">>>", "--",
+    "---", "-(", "-[", "('", "(\"", "((", "))", "(((", ")))", "[[", "]]", "{{", "}}", "♪♪",
+    "♪♪♪", "♩", "♪", "♫", "♬", "♭", "♮", "♯" };
+
+// log-softmax over the finite entries (src/whisper.cpp:6156-6176)
+void compute_logprobs(const std::vector<float> & logits, int n, std::vector<float> & logprobs) {
+    const float mx = *std::max_element(logits.begin(), logits.begin() + n);
+    float lse = 0.0f;
+    for (int i = 0; i < n; ++i) if (logits[i] > -INFINITY) lse += expf(logits[i] - mx);
+    lse = logf(lse) + mx;
+    for (int i = 0; i < n; ++i) logprobs[i] = logits[i] > -INFINITY ? logits[i] - lse : -INFINITY;
+}
+void compute_probs(const std::vector<float> & logits, int n, const std::vector<float> & logprobs, std::vector<float> & probs) {
+    for (int i = 0; i < n; ++i) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
+}
+
+// src/whisper.cpp:6196-6471 without the grammar branch (grammar sampling is out of scope)
+void process_logits(whisper_context & ctx, whisper_state & st, Decoder & dec, const whisper_full_params & params, float temperature) {
+    const Vocab & vocab = ctx.vocab;
+    const auto & cur = dec.sequence.tokens;
+    const bool is_initial = cur.empty();
+    const int n = vocab.n_vocab;
+    auto & probs = dec.probs; auto & logits = dec.logits; auto & logprobs = dec.logprobs;
+    logits.resize(n); probs.resize(n); logprobs.resize(n);
+    memcpy(logits.data(), st.logits.data() + (size_t) dec.i_batch * n, (size_t) n * sizeof(float));
+    if (temperature > 0.0f) for (int i = 0; i < n; ++i) logits[i] /= temperature;
+
+    auto suppress = [&](int id) { if (id >= 0 && id < n) logits[id] = -INFINITY; };
+    if (params.suppress_blank && is_initial) {
+        suppress(vocab.token_eot);
+        auto it = vocab.token_to_id.find(" ");
+        if (it != vocab.token_to_id.end()) suppress(it->second);
+    }
+    suppress(vocab.token_not);
+    if (params.no_timestamps) for (int i = vocab.token_beg; i < n; ++i) logits[i] = -INFINITY;
+    if (!params.no_timestamps && !params.single_segment && params.max_tokens > 0 && (int) cur.size() >= params.max_tokens)
+        for (int i = 0; i < vocab.token_eot; ++i) logits[i] = -INFINITY;
+    suppress(vocab.token_sot); suppress(vocab.token_nosp);
+    if (!params.tdrz_enable) suppress(vocab.token_solm);
+    suppress(vocab.token_translate); suppress(vocab.token_transcribe); suppress(vocab.token_prev);
+    for (int i = 0; i < 100; ++i) suppress(vocab.token_sot + 1 + i);       // one per entry of the language table
+    suppress(vocab.token_prev);
+
+    if (params.logits_filter_callback)
+        params.logits_filter_callback(&ctx, &st, cur.data(), (int) cur.size(), logits.data(), params.logits_filter_callback_user_data);
+
+    if (params.suppress_regex) {
+        std::regex re(params.suppress_regex);
+        for (const auto & kv : vocab.token_to_id) if (std::regex_match(kv.first, re)) suppress(kv.second);
+    }
+    if (params.suppress_nst) {
+        for (const char * t : k_non_speech) {
+            const std::string a = t, b = std::string(" ") + t;
+            auto it = vocab.token_to_id.find(a); if (it != vocab.token_to_id.end()) suppress(it->second);
+            it = vocab.token_to_id.find(b);      if (it != vocab.token_to_id.end()) suppress(it->second);
+        }
+        auto it = vocab.token_to_id.find(" -"); if (it != vocab.token_to_id.end()) suppress(it->second);
+        it = vocab.token_to_id.find(" '");      if (it != vocab.token_to_id.end()) suppress(it->second);
+    }
+    { // timestamps come in pairs, except right before EOT
+        const bool last_ts = !cur.empty() && cur.back().id >= vocab.token_beg;
+        const bool penult_ts = cur.size() < 2 || cur[cur.size() - 2].id >= vocab.token_beg;
+        if (last_ts) {
+            if (penult_ts) for (int i = vocab.token_beg; i < n; ++i) logits[i] = -INFINITY;
+            else           for (int i = 0; i < vocab.token_eot; ++i) logits[i] = -INFINITY;
+        }
+    }
+    if (is_initial && params.max_initial_ts > 0.0f) {
+        const float precision = float(WB_CHUNK_SIZE) / ctx.model.hp.n_audio_ctx;
+        const int tid0 = (int) std::round(params.max_initial_ts / precision);
+        for (int i = vocab.token_beg + tid0 + 1; i < n; ++i) logits[i] = -INFINITY;
+    }
+    if (dec.has_ts) {
+        const int tid0 = dec.seek_delta / 2;
+        for (int i = vocab.token_beg; i < vocab.token_beg + tid0 && i < n; ++i) logits[i] = -INFINITY;
+    }
+    compute_logprobs(logits, n, logprobs);
+    { // if the timestamp mass beats every text token, force a timestamp
+        float ts_logprob = -INFINITY;
+        {
+            float lse = 0.0f;
+            const float mx = *std::max_element(logprobs.begin() + vocab.token_beg, logprobs.begin() + n);
+            for (int i = vocab.token_beg; i < n; ++i) if (logprobs[i] > -INFINITY) lse += expf(logprobs[i] - mx);
+            if (lse > 0.0f) ts_logprob = logf(lse) + mx;
+        }
+        const float max_text = *std::max_element(logprobs.begin(), logprobs.begin() + vocab.token_beg);
+        if (ts_logprob > max_text) for (int i = 0; i < vocab.token_beg; ++i) { logits[i] = -INFINITY; logprobs[i] = -INFINITY; }
+    }
+    compute_probs(logits, n, logprobs, probs);
+}
+
+whisper_token_data blank_token() { whisper_token_data t; memset(&t, 0, sizeof(t)); t.t0 = t.t1 = t.t_dtw = -1; return t; }
+
+void timestamp_stats(const Vocab & vocab, const std::vector<float> & probs, whisper_token & tid, float & pt, float & ptsum) {
+    double sum_ts = 0.0, max_ts = 0.0;
+    for (int i = vocab.token_beg; i < vocab.n_vocab; ++i) {
+        if (probs[i] == -INFINITY) continue;
+        sum_ts += probs[i];
+        if (max_ts < probs[i]) { max_ts = probs[i]; tid = i; }
+    }
+    pt = (float) (max_ts / (sum_ts + 1e-10)); ptsum = (float) sum_ts;
+}
+
+// src/whisper.cpp:6486-6543
+whisper_token_data sample_token(whisper_context & ctx, Decoder & dec, bool best) {
+    const Vocab & vocab = ctx.vocab;
+    whisper_token_data r = blank_token();
+    timestamp_stats(vocab, dec.probs, r.tid, r.pt, r.ptsum);
+    if (best) {
+        for (int i = 0; i < vocab.n_vocab; ++i) if (r.p < dec.probs[i]) { r.id = i; r.p = dec.probs[i]; r.plog = dec.logprobs[i]; }
+    } else {
+        std::discrete_distribution<> dist(dec.probs.begin(), dec.probs.end());
+        r.id = dist(dec.rng); r.p = dec.probs[r.id]; r.plog = dec.logprobs[r.id];
+    }
+    if (r.id >= vocab.token_beg) { r.tid = r.id; r.pt = r.p; }
+    return r;
+}
+
+// src/whisper.cpp:6545-6618: k draws from the categorical distribution (the partial sort of the reference has no effect on the result)
+std::vector<whisper_token_data> sample_token_topk(whisper_context & ctx, Decoder & dec, int k) {
+    const Vocab & vocab = ctx.vocab;
+    whisper_token tid = vocab.token_beg; float pt = 0.0f, ptsum = 0.0f;
+    timestamp_stats(vocab, dec.probs, tid, pt, ptsum);
+    std::discrete_distribution<> dist(dec.probs.begin(), dec.probs.end());
+    std::vector<whisper_token_data> out; out.reserve(k);
+    for (int i = 0; i < k; ++i) {
+        const int id = dist(dec.rng);
+        whisper_token_data t = blank_token();
+        t.id = id; t.tid = tid; t.p = dec.probs[id]; t.plog = dec.logprobs[id]; t.pt = pt; t.ptsum = ptsum;
+        if (t.id >= vocab.token_beg) { t.tid = t.id; t.pt = t.p; }
+        out.push_back(t);
+    }
+    return out;
+}
+
+// src/whisper.cpp:6621-6667
+void sequence_score(const whisper_full_params & params, Sequence & s) {
+    if (s.result_len == 0) return;
+    double r = 0.0;
+    for (int i = 0; i < s.result_len; ++i) r += s.tokens[i].plog;
+    s.sum_logprobs = r; s.avg_logprobs = r / s.result_len;
+    double penalty = s.result_len;
+    if (params.length_penalty > 0.0f) penalty = pow((5.0 + penalty) / 6.0, params.length_penalty);
+    s.score = r / penalty;
+    std::map<whisper_token, int> counts; int cnt = 0;
+    for (int i = std::max(0, s.result_len - 32); i < s.result_len; ++i) { counts[s.tokens[i].id]++; cnt++; }
+    double ent = 0.0;
+    for (const auto & kv : counts) { const double p = kv.second / (double) cnt; ent -= p * log(p); }
+    s.entropy = ent;
+}
+
+bool tokens_equal(const Sequence & a, const Sequence & b) {
+    if (a.tokens.size() != b.tokens.size()) return false;
+    for (int i = (int) a.tokens.size() - 1; i >= 0; --i) if (a.tokens[i].id != b.tokens[i].id) return false;
+    return true;
+}
+
+std::string to_timestamp(int64_t t, bool comma = false) {
+    int64_t msec = t * 10;
+    const int64_t hr = msec / 3600000; msec -= hr * 3600000;
+    const int64_t mn = msec / 60000;   msec -= mn * 60000;
+    const int64_t sec = msec / 1000;   msec -= sec * 1000;
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%02d:%02d:%02d%s%03d", (int) hr, (int) mn, (int) sec, comma ? "," : ".", (int) msec);
+    return buf;
+}
+
+template <typename F> void run_parallel(int n_threads, F && fn) {
+    if (n_threads <= 1) { fn(); return; }
+    std::vector<std::thread> th(n_threads - 1);
+    for (auto & t : th) t = std::thread(fn);
+    fn();
+    for (auto & t : th) t.join();
+}
+
+} // namespace
+
+extern "C" {
+
+WB_EXPORT struct whisper_full_params whisper_full_default_params(enum whisper_sampling_strategy strategy) {   // whisper.cpp:5947-6053
+    struct whisper_full_params p;
+    memset(&p, 0, sizeof(p));
+    p.strategy = strategy;
+    p.n_threads = std::min(4, (int) std::thread::hardware_concurrency());
+    p.n_max_text_ctx = 16384;
+    p.no_context = true; p.print_progress = true; p.print_timestamps = true;
+    p.thold_pt = 0.01f; p.thold_ptsum = 0.01f;
+    p.language = "en";
+    p.suppress_blank = true;
+    p.temperature = 0.0f; p.max_initial_ts = 1.0f; p.length_penalty = -1.0f;
+    p.temperature_inc = 0.2f; p.entropy_thold = 2.4f; p.logprob_thold = -1.0f; p.no_speech_thold = 0.6f;
+    p.greedy.best_of = -1; p.beam_search.beam_size = -1; p.beam_search.patience = -1.0f;
+    p.grammar_penalty = 100.0f;
+    p.vad_params = whisper_vad_default_params();
+    if (strategy == WHISPER_SAMPLING_GREEDY) p.greedy.best_of = 5;
+    else if (strategy == WHISPER_SAMPLING_BEAM_SEARCH) { p.beam_search.beam_size = 5; p.beam_search.patience = -1.0f; }
+    return p;
+}
+WB_EXPORT struct whisper_full_params * whisper_full_default_params_by_ref(enum whisper_sampling_strategy strategy) {
+    auto * p = new whisper_full_params(); *p = whisper_full_default_params(strategy); return p;
+}
+
+WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisper_state * state, struct whisper_full_params params,
+                                      const float * samples, int n_samples) {
+    if (!ctx || !state) return -1;
+    auto & result_all = state->result_all;
+    result_all.clear();
+    const Vocab & vocab = ctx->vocab;
+
+    if (n_samples > 0) {
+        if (whisper_pcm_to_mel_with_state(ctx, state, samples, n_samples, params.n_threads) != 0) {
+            logf(LOG_ERROR, "%s: failed to compute log mel spectrogram\n", __func__);
+            return -2;
+        }
+    }
+    if (params.language == nullptr || strlen(params.language) == 0 || strcmp(params.language, "auto") == 0 || params.detect_language) {
+        std::vector<float> probs(whisper_lang_max_id() + 1, 0.0f);
+        const int lang_id = whisper_lang_auto_detect_with_state(ctx, state, 0, params.n_threads, probs.data());
+        if (lang_id < 0) { logf(LOG_ERROR, "%s: failed to auto-detect language\n", __func__); return -3; }
+        state->lang_id = lang_id;
+        params.language = whisper_lang_str(lang_id);
+        logf(LOG_INFO, "%s: auto-detected language: %s (p = %f)\n", __func__, params.language, probs[lang_id]);
+        if (params.detect_language) return 0;
+    }
+    if (params.token_timestamps) {
+        static std::atomic<bool> warned{false};
+        if (!warned.exchange(true)) logf(LOG_WARN, "%s: token_timestamps (experimental) is not implemented by this engine; token t0/t1 stay -1\n", __func__);
+    }
+    if (params.grammar_rules && params.n_grammar_rules > 0) {
+        static std::atomic<bool> warned{false};
+        if (!warned.exchange(true)) logf(LOG_WARN, "%s: grammar-constrained sampling is out of scope for this engine; grammar ignored\n", __func__);
+    }
+
+    const int seek_start = params.offset_ms / 10;
+    const int seek_end = params.duration_ms == 0 ? whisper_n_len_from_state(state) : seek_start + params.duration_ms / 10;
+    const int delta_min = 10;
+    if (seek_end < seek_start + delta_min) {
+        logf(LOG_WARN, "%s: input is too short - %d ms < 100 ms. consider padding the input audio with silence\n", __func__, (seek_end - seek_start) * 10);
+        return 0;
+    }
+
+    std::vector<float> temperatures;
+    if (params.temperature_inc > 0.0f) for (float t = params.temperature; t < 1.0f + 1e-6f; t += params.temperature_inc) temperatures.push_back(t);
+    else temperatures.push_back(params.temperature);
+
+    int n_decoders = 1;
+    if (params.strategy == WHISPER_SAMPLING_GREEDY) n_decoders = params.greedy.best_of;
+    else if (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) n_decoders = std::max(params.greedy.best_of, params.beam_search.beam_size);
+    n_decoders = std::max(1, n_decoders);
+    if (n_decoders > MAX_DECODERS) { logf(LOG_ERROR, "%s: too many decoders requested (%d), max = %d\n", __func__, n_decoders, MAX_DECODERS); return -4; }
+    for (int j = 1; j < n_decoders; ++j) state->decoders[j].rng = std::mt19937(j);
+
+    auto & past0 = state->prompt_past0; auto & past1 = state->prompt_past1;
+    if (params.no_context) { past0.clear(); past1.clear(); }
+    const int n_text_ctx = ctx->model.hp.n_text_ctx;
+    const int max_prompt_ctx = std::min(params.n_max_text_ctx, n_text_ctx / 2);
+
+    std::vector<whisper_token> init_prompt_tokens;
+    if (!params.prompt_tokens && params.initial_prompt) {
+        init_prompt_tokens.resize(1024);
+        int need = whisper_tokenize(ctx, params.initial_prompt, init_prompt_tokens.data(), (int) init_prompt_tokens.size());
+        if (need < 0) { init_prompt_tokens.resize(-need); need = whisper_tokenize(ctx, params.initial_prompt, init_prompt_tokens.data(), (int) init_prompt_tokens.size()); }
+        init_prompt_tokens.resize(std::max(0, need));
+        params.prompt_tokens = init_prompt_tokens.data(); params.prompt_n_tokens = (int) init_prompt_tokens.size();
+    }
+    if (params.prompt_tokens && params.prompt_n_tokens > 0) {
+        if (params.carry_initial_prompt) {
+            if (past0.empty()) {
+                const int max_tokens = std::max(1, max_prompt_ctx - 1);
+                if (params.prompt_n_tokens > max_tokens)
+                    logf(LOG_WARN, "%s: initial prompt is too long (%d tokens), will use only the last %d tokens\n", __func__, params.prompt_n_tokens, max_tokens);
+                const int nt = std::min(params.prompt_n_tokens, max_tokens);
+                past0.assign(params.prompt_tokens + (params.prompt_n_tokens - nt), params.prompt_tokens + params.prompt_n_tokens);
+            }
+        } else {
+            for (int i = 0; i < params.prompt_n_tokens; ++i) past1.push_back(params.prompt_tokens[i]);
+            std::rotate(past1.begin(), past1.end() - params.prompt_n_tokens, past1.end());
+        }
+    }
+
+    if (params.audio_ctx > ctx->model.hp.n_audio_ctx) {
+        logf(LOG_ERROR, "%s: audio_ctx is larger than the maximum allowed (%d > %d)\n", __func__, params.audio_ctx, ctx->model.hp.n_audio_ctx);
+        return -5;
+    }
+    state->exp_n_audio_ctx = params.audio_ctx;
+
+    std::vector<whisper_token> prompt_init = { vocab.token_sot };
+    if (vocab.is_multilingual()) {
+        const int lang_id = whisper_lang_id(params.language);
+        state->lang_id = lang_id;
+        prompt_init.push_back(vocab.token_sot + 1 + lang_id);
+        prompt_init.push_back(params.translate ? vocab.token_translate : vocab.token_transcribe);
+    }
+    {
+        const bool is_distil = ctx->model.hp.n_text_layer == 2 && ctx->model.hp.n_vocab != 51866;
+        if (is_distil && !params.no_timestamps) {
+            logf(LOG_WARN, "%s: using first release distilled models - forcing no_timestamps\n", __func__);
+            params.no_timestamps = true;
+        }
+    }
+    if (params.no_timestamps) prompt_init.push_back(vocab.token_not);
+
+    int seek = seek_start;
+    std::vector<whisper_token> prompt; prompt.reserve(n_text_ctx);
+
+    struct BeamCand { int decoder_idx; int seek_delta; bool has_ts; Sequence sequence; };
+    std::vector<std::vector<BeamCand>> bc_per_dec(n_decoders);
+    std::vector<BeamCand> cands;
+    std::vector<int> b_tok, b_pos, b_seq; std::vector<int8_t> b_want;
+
+    while (true) {
+        if (params.progress_callback)
+            params.progress_callback(ctx, state, (100 * (seek - seek_start)) / (seek_end - seek_start), params.progress_callback_user_data);
+        if (seek + delta_min >= seek_end) break;
+        if (params.encoder_begin_callback && !params.encoder_begin_callback(ctx, state, params.encoder_begin_callback_user_data)) {
+            logf(LOG_ERROR, "%s: encoder_begin_callback returned false - aborting\n", __func__);
+            break;
+        }
+        if (!encode_window(*ctx, *state, seek)) { logf(LOG_ERROR, "%s: failed to encode\n", __func__); return -6; }
+        if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) { logf(LOG_ERROR, "%s: failed to encode\n", __func__); return -6; }
+
+        if (seek > seek_start && seek + 500 >= seek_end) { past0.clear(); past1.clear(); }
+
+        int best_decoder_id = 0;
+        for (int it = 0; it < (int) temperatures.size(); ++it) {
+            const float t_cur = temperatures[it];
+            int n_cur = 1;
+            if (params.strategy == WHISPER_SAMPLING_GREEDY) { if (t_cur > 0.0f) n_cur = params.greedy.best_of; }
+            else if (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) n_cur = t_cur > 0.0f ? params.greedy.best_of : params.beam_search.beam_size;
+            n_cur = std::max(1, n_cur);
+
+            for (int j = 0; j < n_cur; ++j) {
+                Decoder & d = state->decoders[j];
+                d.sequence.tokens.clear(); d.sequence.result_len = 0; d.sequence.sum_logprobs_all = 0.0;
+                d.sequence.sum_logprobs = -INFINITY; d.sequence.avg_logprobs = -INFINITY; d.sequence.entropy = 0.0; d.sequence.score = -INFINITY;
+                d.seek_delta = 100 * WB_CHUNK_SIZE;
+                d.failed = d.completed = d.has_ts = false;
+            }
+
+            { // prompt + KV cache for this attempt (whisper.cpp:7126-7221)
+                prompt.clear();
+                if (params.n_max_text_ctx > 0 && t_cur < 0.5f) {
+                    const bool take0 = params.carry_initial_prompt && !past0.empty();
+                    const bool take1 = !past1.empty();
+                    if (max_prompt_ctx > 0 && (take0 || take1)) {
+                        prompt.push_back(vocab.token_prev);
+                        int n0 = 0;
+                        if (take0) { n0 = (int) past0.size(); prompt.insert(prompt.end(), past0.end() - n0, past0.end()); }
+                        const int n1 = std::min<int>(max_prompt_ctx - n0 - 1, (int) past1.size());
+                        prompt.insert(prompt.end(), past1.end() - n1, past1.end());
+                    }
+                }
+                prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
+
+                if (state->kv_self_n_dec < n_cur) {
+                    const int factor = n_cur > 1 ? n_cur + 2 : 1;
+                    const int cells = ((n_text_ctx + 255) / 256 * 256) * factor;
+                    if (!state->eng.set_cells(cells)) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
+                    state->kv.reset((uint32_t) cells);
+                    state->kv_self_n_dec = n_cur;
+                }
+                state->kv.clear();
+
+                const int np = (int) prompt.size();
+                b_tok.assign(prompt.begin(), prompt.end()); b_pos.resize(np); b_seq.assign(np, 0); b_want.assign(np, 0);
+                for (int i = 0; i < np; ++i) b_pos[i] = i;
+                b_want[np - 1] = 1;
+                if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), np)) { logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -8; }
+                if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -8;
+
+                { // no_speech probability from the unfiltered logits of the last prompt token (whisper.cpp:7190-7200)
+                    const int n = vocab.n_vocab;
+                    std::vector<float> raw(state->logits.begin() + (size_t) (np - 1) * n, state->logits.begin() + (size_t) np * n);
+                    std::vector<float> lp(n), pr(n);
+                    compute_logprobs(raw, n, lp); compute_probs(raw, n, lp, pr);
+                    state->no_speech_prob = pr[vocab.token_nosp];
+                }
+                {
+                    const int64_t ts = time_us();
+                    state->decoders[0].i_batch = np - 1;
+                    process_logits(*ctx, *state, state->decoders[0], params, t_cur);
+                    for (int j = 1; j < n_cur; ++j) {
+                        Decoder & d = state->decoders[j];
+                        state->kv.seq_cp(0, j, -1, -1);
+                        d.probs = state->decoders[0].probs; d.logits = state->decoders[0].logits; d.logprobs = state->decoders[0].logprobs;
+                    }
+                    state->t_sample_us += time_us() - ts;
+                }
+            }
+
+            for (int i = 0, n_max = n_text_ctx / 2 - 4; i < n_max; ++i) {
+                const int64_t ts0 = time_us();
+                if (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) for (auto & bc : bc_per_dec) bc.clear();
+
+                { // sampling
+                    std::atomic<int> j_cur(0);
+                    auto work = [&]() {
+                        for (;;) {
+                            const int j = j_cur.fetch_add(1);
+                            if (j >= n_cur) break;
+                            Decoder & d = state->decoders[j];
+                            if (d.completed || d.failed) continue;
+                            if (params.strategy == WHISPER_SAMPLING_GREEDY) {
+                                d.sequence.tokens.push_back(sample_token(*ctx, d, t_cur < 1e-6f));
+                                d.sequence.sum_logprobs_all += d.sequence.tokens.back().plog;
+                            } else {
+                                const auto toks = sample_token_topk(*ctx, d, params.beam_search.beam_size);
+                                for (const auto & tk : toks) {
+                                    bc_per_dec[j].push_back({ j, d.seek_delta, d.has_ts, d.sequence });
+                                    bc_per_dec[j].back().sequence.tokens.push_back(tk);
+                                    bc_per_dec[j].back().sequence.sum_logprobs_all += tk.plog;
+                                }
+                            }
+                        }
+                    };
+                    run_parallel(std::min(params.n_threads, n_cur), work);
+                }
+                cands.clear();
+                for (const auto & bc : bc_per_dec) { cands.insert(cands.end(), bc.begin(), bc.end()); if (!bc.empty()) state->n_sample += 1; }
+
+                if (params.strategy == WHISPER_SAMPLING_BEAM_SEARCH) {                 // whisper.cpp:7305-7357
+                    std::sort(cands.begin(), cands.end(), [](const BeamCand & a, const BeamCand & b) {
+                        if (a.sequence.sum_logprobs_all != b.sequence.sum_logprobs_all) return a.sequence.sum_logprobs_all > b.sequence.sum_logprobs_all;
+                        return a.decoder_idx < b.decoder_idx;
+                    });
+                    uint32_t cur_c = 0;
+                    for (int j = 0; j < n_cur; ++j) {
+                        Decoder & d = state->decoders[j];
+                        if (d.completed || d.failed) continue;
+                        if (cur_c >= cands.size()) cur_c = 0;
+                        BeamCand & c = cands[cur_c++];
+                        while (cands.size() > cur_c && tokens_equal(cands[cur_c].sequence, c.sequence) && i > 0) ++cur_c;
+                        d.seek_delta = c.seek_delta; d.has_ts = c.has_ts; d.sequence = c.sequence;
+                        state->kv.seq_cp(c.decoder_idx, MAX_DECODERS + j, -1, -1);
+                    }
+                    for (int j = 0; j < n_cur; ++j) {
+                        Decoder & d = state->decoders[j];
+                        if (d.completed || d.failed) continue;
+                        state->kv.seq_rm(j, -1, -1);
+                        state->kv.seq_cp(MAX_DECODERS + j, j, -1, -1);
+                        state->kv.seq_rm(MAX_DECODERS + j, -1, -1);
+                    }
+                }
+
+                for (int j = 0; j < n_cur; ++j) {                                     // whisper.cpp:7363-7445
+                    Decoder & d = state->decoders[j];
+                    if (d.completed || d.failed) continue;
+                    int & result_len = d.sequence.result_len;
+                    {
+                        const whisper_token_data & tk = d.sequence.tokens.back();
+                        if (tk.id > vocab.token_beg) {
+                            const int sd_new = 2 * (tk.id - vocab.token_beg);
+                            if (d.has_ts && d.seek_delta > sd_new && result_len < i) { d.failed = true; continue; }
+                            d.seek_delta = sd_new; result_len = i + 1; d.has_ts = true;
+                        }
+                        if (tk.id == vocab.token_eot || (params.max_tokens > 0 && i >= params.max_tokens) ||
+                            (d.has_ts && seek + d.seek_delta + delta_min >= seek_end)) {
+                            if (result_len == 0 && !params.no_timestamps) {
+                                if (seek + d.seek_delta + delta_min >= seek_end) result_len = i + 1;
+                                else { d.failed = true; continue; }
+                            }
+                            if (params.single_segment || params.no_timestamps) { result_len = i + 1; d.seek_delta = 100 * WB_CHUNK_SIZE; }
+                            d.completed = true;
+                            continue;
+                        }
+                        if (ctx->model.n_loaded == 0) { d.seek_delta = 100 * WB_CHUNK_SIZE; d.completed = true; continue; }   // weight-less test stubs
+                    }
+                    if (i == n_max - 1 && (result_len == 0 || d.seek_delta < 100 * WB_CHUNK_SIZE / 2)) { d.failed = true; continue; }
+                }
+                {
+                    bool all_done = true;
+                    for (int j = 0; j < n_cur; ++j) { const Decoder & d = state->decoders[j]; if (!(d.completed || d.failed)) all_done = false; }
+                    if (all_done) break;
+                }
+                state->t_sample_us += time_us() - ts0;
+
+                { // next-token logits for every live decoder (whisper.cpp:7469-7546)
+                    b_tok.clear(); b_pos.clear(); b_seq.clear(); b_want.clear();
+                    const int n_past = (int) prompt.size() + i;
+                    for (int j = 0; j < n_cur; ++j) {
+                        Decoder & d = state->decoders[j];
+                        if (d.failed || d.completed) continue;
+                        d.i_batch = (int) b_tok.size();
+                        b_tok.push_back(d.sequence.tokens.back().id); b_pos.push_back(n_past); b_seq.push_back(j); b_want.push_back(1);
+                    }
+                    if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), (int) b_tok.size())) {
+                        logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -9;
+                    }
+                    if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -9;
+                    const int64_t ts1 = time_us();
+                    std::atomic<int> j_cur(0);
+                    auto work = [&]() {
+                        for (;;) {
+                            const int j = j_cur.fetch_add(1);
+                            if (j >= n_cur) break;
+                            Decoder & d = state->decoders[j];
+                            if (d.failed || d.completed) continue;
+                            process_logits(*ctx, *state, d, params, t_cur);
+                        }
+                    };
+                    run_parallel(std::min(params.n_threads, n_cur), work);
+                    state->t_sample_us += time_us() - ts1;
+                }
+            }
+
+            { // rank the sequences (whisper.cpp:7549-7583)
+                double best_score = -INFINITY;
+                for (int j = 0; j < n_cur; ++j) {
+                    Decoder & d = state->decoders[j];
+                    if (d.failed) continue;
+                    d.sequence.tokens.resize(d.sequence.result_len);
+                    sequence_score(params, d.sequence);
+                    if (d.sequence.result_len > 32 && d.sequence.entropy < params.entropy_thold) { d.failed = true; state->n_fail_h++; continue; }
+                    if (best_score < d.sequence.score) { best_score = d.sequence.score; best_decoder_id = j; }
+                }
+            }
+            bool success = true;
+            if (it != (int) temperatures.size() - 1) {
+                const Decoder & d = state->decoders[best_decoder_id];
+                if (d.failed || (d.sequence.avg_logprobs < params.logprob_thold && state->no_speech_prob < params.no_speech_thold)) { success = false; state->n_fail_p++; }
+            }
+            if (success) break;
+        }
+
+        { // emit segments (whisper.cpp:7612-7784)
+            const Decoder & best = state->decoders[best_decoder_id];
+            int seek_delta = best.seek_delta;
+            const int result_len = best.sequence.result_len;
+            const auto & cur = best.sequence.tokens;
+            const bool is_no_speech = state->no_speech_prob > params.no_speech_thold && best.sequence.avg_logprobs < params.logprob_thold;
+
+            past1.clear();
+            if (!params.carry_initial_prompt && !prompt.empty() && prompt.front() == vocab.token_prev)
+                past1.insert(past1.end(), prompt.begin() + 1, prompt.end() - prompt_init.size());
+            if (!is_no_speech) for (int i = 0; i < result_len; ++i) past1.push_back(cur[i].id);
+
+            if (!cur.empty() && ctx->model.n_loaded > 0 && !is_no_speech) {
+                int i0 = 0;
+                int64_t t0 = seek + 2 * (cur.front().tid - vocab.token_beg);
+                std::string text; bool speaker_turn_next = false;
+                auto push_segment = [&](int64_t a, int64_t b, int from, int to_incl) {
+                    if (params.print_realtime) {
+                        if (params.print_timestamps) printf("[%s --> %s]  %s\n", to_timestamp(a).c_str(), to_timestamp(b).c_str(), text.c_str());
+                        else printf("%s", text.c_str());
+                        fflush(stdout);
+                    }
+                    Segment sg; sg.t0 = a; sg.t1 = b; sg.text = text; sg.no_speech_prob = state->no_speech_prob; sg.speaker_turn_next = speaker_turn_next;
+                    for (int j = from; j <= to_incl; ++j) sg.tokens.push_back(cur[j]);
+                    result_all.push_back(std::move(sg));
+                    if (params.new_segment_callback) params.new_segment_callback(ctx, state, 1, params.new_segment_callback_user_data);
+                };
+                for (int i = 0; i < (int) cur.size(); ++i) {
+                    if (params.print_special || cur[i].id < vocab.token_eot) text += whisper_token_to_str(ctx, cur[i].id);
+                    if (params.tdrz_enable && cur[i].id == vocab.token_solm) speaker_turn_next = true;
+                    if (cur[i].id > vocab.token_beg && !params.single_segment) {
+                        const int64_t t1 = seek + 2 * (cur[i].tid - vocab.token_beg);
+                        if (!text.empty()) push_segment(t0, t1, i0, i);
+                        text.clear();
+                        t0 = t1;
+                        while (i + 1 < (int) cur.size() && cur[i + 1].id > vocab.token_beg) {
+                            ++i;
+                            if (params.print_special) text += whisper_token_to_str(ctx, cur[i].id);
+                            t0 = seek + 2 * (cur[i].tid - vocab.token_beg);
+                        }
+                        i0 = i + 1;
+                        speaker_turn_next = false;
+                    }
+                }
+                if (!text.empty()) push_segment(t0, seek + seek_delta, i0, (int) cur.size() - 1);
+            }
+
+            const bool max_tokens_ts_ending = params.max_tokens > 0 && !params.single_segment && cur.size() > (size_t) params.max_tokens;
+            const bool single_ts_ending = cur.size() > 1 && !max_tokens_ts_ending &&
+                cur[cur.size() - 2].id < vocab.token_beg && cur[cur.size() - 1].id > vocab.token_beg;
+            if (single_ts_ending) seek_delta = std::min(seek_end - seek, WB_CHUNK_SIZE * 100);
+            seek += seek_delta;
+        }
+    }
+    return 0;
+}
+
+WB_EXPORT int whisper_full(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples) {
+    if (!ctx || !ctx->state) return -1;
+    if (params.vad) { logf(LOG_ERROR, "%s: VAD is not part of libwhisper_b200 (whisper_full returns -1 as for a failed VAD)\n", __func__); return -1; }
+    return whisper_full_with_state(ctx, ctx->state, params, samples, n_samples);
+}
+
+WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples, int n_processors) {
+    if (n_processors <= 1) return whisper_full(ctx, params, samples, n_samples);          // whisper.cpp:7813-7941
+    if (!ctx || !ctx->state) return -1;
+    if (params.vad) { logf(LOG_ERROR, "%s: VAD is not part of libwhisper_b200\n", __func__); return -1; }
+    int ret = 0;
+    std::vector<whisper_state *> states;
+    const int offset_samples = (WB_SAMPLE_RATE * params.offset_ms) / 1000;
+    const int per = (n_samples - offset_samples) / n_processors;
+    std::vector<std::thread> workers(n_processors - 1);
+    std::vector<int> rets(n_processors - 1, 0);
+    for (int i = 0; i < n_processors - 1; ++i) {
+        states.push_back(whisper_init_state(ctx));
+        if (!states.back()) { for (int k = 0; k < i; ++k) { workers[k].join(); whisper_free_state(states[k]); } return -7; }
+        const int start = offset_samples + (i + 1) * per;
+        const int n_cur = (i == n_processors - 2) ? n_samples - start : per;
+        whisper_full_params pc = params;
+        pc.offset_ms = 0; pc.print_progress = false; pc.print_realtime = false;
+        pc.new_segment_callback = nullptr; pc.new_segment_callback_user_data = nullptr;
+        pc.progress_callback = nullptr; pc.progress_callback_user_data = nullptr;
+        whisper_state * s = states[i]; int * r = &rets[i];
+        workers[i] = std::thread([ctx, s, pc, samples, start, n_cur, r]() { *r = whisper_full_with_state(ctx, s, pc, samples + start, n_cur); });
+    }
+    {
+        whisper_full_params pc = params; pc.print_realtime = false;
+        ret = whisper_full_with_state(ctx, ctx->state, pc, samples, offset_samples + per);
+    }
+    for (auto & w : workers) w.join();
+    const int64_t offset_t = (int64_t) (params.offset_ms / 10.0);
+    whisper_state * main = ctx->state;
+    for (int i = 0; i < n_processors - 1; ++i) {
+        for (auto & r : states[i]->result_all) {
+            const int64_t shift = 100 * ((int64_t) (i + 1) * per) / WB_SAMPLE_RATE + offset_t;
+            r.t0 += shift; r.t1 += shift;
+            if (!main->result_all.empty()) r.t0 = std::max(r.t0, main->result_all.back().t1);
+            main->result_all.push_back(std::move(r));
+            if (params.new_segment_callback) params.new_segment_callback(ctx, main, 1, params.new_segment_callback_user_data);
+        }
+        main->t_mel_us += states[i]->t_mel_us; main->t_sample_us += states[i]->t_sample_us; main->t_encode_us += states[i]->t_encode_us;
+        main->t_decode_us += states[i]->t_decode_us; main->t_batchd_us += states[i]->t_batchd_us; main->t_prompt_us += states[i]->t_prompt_us;
+        main->n_sample += states[i]->n_sample; main->n_encode += states[i]->n_encode; main->n_decode += states[i]->n_decode;
+        main->n_batchd += states[i]->n_batchd; main->n_prompt += states[i]->n_prompt;
+        if (rets[i] != 0 && ret == 0) ret = rets[i];
+        whisper_free_state(states[i]);
+    }
+    main->t_mel_us /= n_processors; main->t_sample_us /= n_processors; main->t_encode_us /= n_processors; main->t_decode_us /= n_processors;
+    logf(LOG_WARN, "\n%s: the audio has been split into %d chunks at the following times:\n", __func__, n_processors);
+    for (int i = 0; i < n_processors - 1; ++i)
+        logf(LOG_WARN, "%s: split %d - %s\n", __func__, i + 1, to_timestamp(100 * ((int64_t) (i + 1) * per) / WB_SAMPLE_RATE + offset_t).c_str());
+    logf(LOG_WARN, "%s: the transcription quality may be degraded near these boundaries\n", __func__);
+    return ret;
+}
+
+// Independent PCM buffers on one device: n_streams states work concurrently (each on its own CUDA stream); chunk i's
+// segments are left in states_out[i] (caller frees with whisper_free_state).  Chunk semantics = whisper_full_with_state.
+WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
+                               const int * n_samples, int n_chunks, struct whisper_state ** states_out) {
+    if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
+    int n_streams = 4;
+    if (const char * e = getenv("WB200_BATCH_STREAMS")) n_streams = std::max(1, atoi(e));
+    n_streams = std::min(n_streams, n_chunks);
+    for (int i = 0; i < n_chunks; ++i) { states_out[i] = whisper_init_state(ctx); if (!states_out[i]) return -7; }
+    std::atomic<int> next(0); std::atomic<int> rc(0);
+    whisper_full_params pc = params;
+    pc.print_progress = false; pc.print_realtime = false;
+    auto work = [&]() {
+        for (;;) {
+            const int i = next.fetch_add(1);
+            if (i >= n_chunks) break;
+            const int r = whisper_full_with_state(ctx, states_out[i], pc, samples[i], n_samples[i]);
+            if (r != 0) rc.store(r);
+        }
+    };
+    run_parallel(n_streams, work);
+    return rc.load();
+}
+
+} // extern "C"

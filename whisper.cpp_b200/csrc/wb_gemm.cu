@@ -346,6 +346,9 @@ static cudaError_t launch_bn(const GemmDesc & g, const GemmKParams & kp, cudaStr
 }
 
 cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
+    const double nb = (double) g.nb0 * g.nb1;
+    ProfScope prof(PC_GEMM, st, nb * ((double) g.M * g.K * g.taps * wt_bpw(g.A.type) + (double) g.N * g.K * g.taps * 2 + (double) g.M * g.N * (g.ep.out_f16 ? 2 : 4)),
+                   nb * 2.0 * g.M * g.N * g.K * g.taps);
     GemmKParams kp;
     kp.M = g.M; kp.N = g.N; kp.K = g.K; kp.taps = g.taps; kp.nkb_per_tap = (g.K + 63) / 64; kp.nb0 = g.nb0;
     kp.a_zsel0 = g.a_zsel[0]; kp.a_zsel1 = g.a_zsel[1]; kp.b_zsel0 = g.b_zsel[0]; kp.b_zsel1 = g.b_zsel[1];

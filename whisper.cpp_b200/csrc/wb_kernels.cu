@@ -590,6 +590,8 @@ static void gemv_nt(const GemvK & k, cudaStream_t st) {
     else                   gemv_launch<WT, 8>(k, st);
 }
 void gemv(const GemvArgs & a, cudaStream_t st) {
+    // algorithmic bytes: the weight matrix once + activations in / results out
+    ProfScope prof(PC_GEMV, st, (double) a.W.N * a.W.K * wt_bpw(a.W.type) + (double) a.n_tok * (a.W.K + a.W.N) * 4, 2.0 * a.W.N * a.W.K * a.n_tok);
     GemvK k; k.W = a.W; k.x = a.x; k.n_tok = a.n_tok; k.ln_w = a.ln_w; k.ln_b = a.ln_b; k.eps = a.eps;
     k.bias = a.bias; k.scale = a.scale; k.act = a.act; k.res = a.res; k.out = a.out;
     k.k_cache = a.k_cache; k.v_cache = a.v_cache; k.cells = a.cells; k.kv_d = a.kv_d;
@@ -651,6 +653,7 @@ k_attn_self(const float * __restrict__ q, int ldq, const __half * __restrict__ k
 }
 void attn_self_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * idx, int ld_idx,
                       const int * n_kv, int n_tok, int n_head, int d, float * out, int ldo, cudaStream_t st) {
+    ProfScope prof(PC_ATTN, st, 0.0, 0.0);
     const size_t smem = (64 + ((ld_idx + 3) & ~3) + 128) * sizeof(float);
     k_attn_self<<<dim3(n_head, n_tok), 128, smem, st>>>(q, ldq, kc, vc, idx, ld_idx, n_kv, d, out, ldo); count_launch();
 }
@@ -718,6 +721,7 @@ k_attn_cross(const float * __restrict__ q, int ldq, const __half * __restrict__ 
 void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * slot, int64_t slot_stride,
                        int n_keys, int n_tok, int n_head, int d, float scale, float * partial, int * counters,
                        float * out, int ldo, cudaStream_t st) {
+    ProfScope prof(PC_ATTN, st, (double) n_tok * 2.0 * n_keys * d * 2, 4.0 * n_tok * n_keys * d);
     k_attn_cross<<<dim3(n_head, XSPLIT, n_tok), 128, 0, st>>>(q, ldq, kc, vc, slot, slot_stride, n_keys, d, scale, partial, counters, out, ldo);
     count_launch();
 }

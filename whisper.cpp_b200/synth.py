@@ -1,0 +1,247 @@
+"""Synthetic Whisper model files in the legacy "ggml" container (no network => no real checkpoints here).
+
+Writes exactly the byte layout `models/convert-pt-to-ggml.py:268-339` produces and `whisper_model_load`
+(src/whisper.cpp:1485-1962) reads: magic, 11 x i32 hparams, mel filters, vocabulary, then the tensor records with
+reversed dims and no padding.  2-D weights are quantised like `whisper-quantize` does it
+(examples/quantize/quantize.cpp:160-168, examples/common-ggml.cpp:141): every 2-D tensor except the conv biases and
+the two positional embeddings; conv kernels stay F16, 1-D tensors F32; ftype in the header becomes 2000 + ftype.
+
+The block quantisers restate ggml's reference quantisers (ggml/src/ggml-quants.c: quantize_row_q4_0_ref :113-147,
+quantize_row_q5_0_ref :187-229, quantize_row_q8_0_ref :276-299); tests/test_synth_cpu.py checks them
+bit-for-bit against the compiled reference.  Host-side tooling only: no dependency on oracle/.
+"""
+import struct
+import zlib
+
+import numpy as np
+
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K = 0, 1, 2, 6, 8, 12, 13
+FTYPE_OF = {F32: 0, F16: 1, Q4_0: 2, Q8_0: 7, Q5_0: 8, Q4_K: 12, Q5_K: 13}
+
+CONFIGS = {
+    # name: n_vocab, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels
+    "tiny.en":        (51864, 1500, 384, 6, 4, 448, 384, 6, 4, 80),
+    "base.en":        (51864, 1500, 512, 8, 6, 448, 512, 8, 6, 80),
+    "large-v3":       (51866, 1500, 1280, 20, 32, 448, 1280, 20, 32, 128),
+    "large-v3-turbo": (51866, 1500, 1280, 20, 32, 448, 1280, 20, 4, 128),
+    # reduced shapes for parity tests the CPU reference finishes in seconds
+    "test-2l.en":     (51864, 1500, 384, 6, 2, 448, 384, 6, 2, 80),
+    "test-2l-512.en": (51864, 1500, 512, 8, 2, 448, 512, 8, 2, 80),
+    "test-2l-multi":  (51866, 1500, 256, 4, 2, 448, 256, 4, 2, 128),
+}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def mel_filters(n_mels, n_fft=400, sr=16000):
+    """Slaney-style mel filterbank (what OpenAI's mel_filters.npz holds; librosa.filters.mel defaults)."""
+    def hz_to_mel(f):
+        f = np.asarray(f, np.float64)
+        mels = f / (200.0 / 3)
+        min_log_hz, min_log_mel, logstep = 1000.0, 1000.0 / (200.0 / 3), np.log(6.4) / 27.0
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, mels)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, np.float64)
+        f = m * (200.0 / 3)
+        min_log_hz, min_log_mel, logstep = 1000.0, 1000.0 / (200.0 / 3), np.log(6.4) / 27.0
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f)
+
+    fftfreqs = np.linspace(0, sr / 2, n_fft // 2 + 1)
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(0.0), hz_to_mel(sr / 2), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    w = np.zeros((n_mels, n_fft // 2 + 1))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0, np.minimum(lower, upper))
+    w *= (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return w.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def quantize(wtype, w):
+    """float32 [rows][k] -> file bytes"""
+    w = np.ascontiguousarray(w, np.float32)
+    if wtype == F32:
+        return w.tobytes()
+    if wtype == F16:
+        return w.astype(np.float16).tobytes()
+    x = w.reshape(-1, 32)
+    nb = x.shape[0]
+    if wtype == Q8_0:
+        amax = np.abs(x).max(axis=1)
+        d = (amax / np.float32(127.0)).astype(np.float32)
+        idv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), 0).astype(np.float32)
+        q = np.round(x * idv[:, None])  # roundf: half away from zero == np.round only for non-ties; fix ties below
+        t = x * idv[:, None]
+        q = np.where(np.abs(t - np.trunc(t)) == 0.5, np.trunc(t) + np.sign(t), np.rint(t)).astype(np.int8)
+        out = np.empty((nb, 34), np.uint8)
+        out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q.view(np.uint8)
+        return out.tobytes()
+    # signed value of maximum magnitude (first occurrence, as the scalar loop finds it)
+    idx = np.abs(x).argmax(axis=1)
+    mx = x[np.arange(nb), idx]
+    if wtype == Q4_0:
+        d = (mx / np.float32(-8.0)).astype(np.float32)
+        idv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), 0).astype(np.float32)
+        t = (x * idv[:, None]).astype(np.float32) + np.float32(8.5)
+        q = np.minimum(15, t.astype(np.int8).astype(np.int32)).astype(np.uint8)
+        out = np.empty((nb, 18), np.uint8)
+        out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q[:, :16] | (q[:, 16:] << 4)
+        return out.tobytes()
+    if wtype == Q5_0:
+        d = (mx / np.float32(-16.0)).astype(np.float32)
+        idv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), 0).astype(np.float32)
+        t = (x * idv[:, None]).astype(np.float32) + np.float32(16.5)
+        q = np.minimum(31, t.astype(np.int8).astype(np.int32)).astype(np.uint32)
+        out = np.empty((nb, 22), np.uint8)
+        out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+        hi = (q >> 4) & 1
+        qh = (hi << np.arange(32, dtype=np.uint32)[None, :]).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+        out[:, 2:6] = qh.view(np.uint8).reshape(nb, 4)
+        out[:, 6:] = ((q[:, :16] & 0xF) | ((q[:, 16:] & 0xF) << 4)).astype(np.uint8)
+        return out.tobytes()
+    raise ValueError(f"synth.quantize: type {wtype} needs an external quantiser (pass quantizer=...)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def tensor_list(cfg):
+    """(name, shape as torch would have it, kind) in the order whisper_model_load creates them; kind: 'mat','vec','conv','pos','cbias'"""
+    n_vocab, n_actx, d, n_ah, La, n_tctx, dt, n_th, Lt, n_mels = cfg
+    out = [("encoder.positional_embedding", (n_actx, d), "pos"),
+           ("encoder.conv1.weight", (d, n_mels, 3), "conv"), ("encoder.conv1.bias", (d, 1), "cbias"),
+           ("encoder.conv2.weight", (d, d, 3), "conv"), ("encoder.conv2.bias", (d, 1), "cbias"),
+           ("encoder.ln_post.weight", (d,), "lnw"), ("encoder.ln_post.bias", (d,), "vec")]
+    for i in range(La):
+        p = f"encoder.blocks.{i}."
+        out += [(p + "mlp_ln.weight", (d,), "lnw"), (p + "mlp_ln.bias", (d,), "vec"),
+                (p + "mlp.0.weight", (4 * d, d), "mat"), (p + "mlp.0.bias", (4 * d,), "vec"),
+                (p + "mlp.2.weight", (d, 4 * d), "mat"), (p + "mlp.2.bias", (d,), "vec"),
+                (p + "attn_ln.weight", (d,), "lnw"), (p + "attn_ln.bias", (d,), "vec"),
+                (p + "attn.query.weight", (d, d), "mat"), (p + "attn.query.bias", (d,), "vec"),
+                (p + "attn.key.weight", (d, d), "mat"),
+                (p + "attn.value.weight", (d, d), "mat"), (p + "attn.value.bias", (d,), "vec"),
+                (p + "attn.out.weight", (d, d), "mat"), (p + "attn.out.bias", (d,), "vec")]
+    out += [("decoder.positional_embedding", (n_tctx, dt), "pos"),
+            ("decoder.token_embedding.weight", (n_vocab, dt), "mat"),
+            ("decoder.ln.weight", (dt,), "lnw"), ("decoder.ln.bias", (dt,), "vec")]
+    for i in range(Lt):
+        p = f"decoder.blocks.{i}."
+        out += [(p + "mlp_ln.weight", (dt,), "lnw"), (p + "mlp_ln.bias", (dt,), "vec"),
+                (p + "mlp.0.weight", (4 * dt, dt), "mat"), (p + "mlp.0.bias", (4 * dt,), "vec"),
+                (p + "mlp.2.weight", (dt, 4 * dt), "mat"), (p + "mlp.2.bias", (dt,), "vec"),
+                (p + "attn_ln.weight", (dt,), "lnw"), (p + "attn_ln.bias", (dt,), "vec"),
+                (p + "attn.query.weight", (dt, dt), "mat"), (p + "attn.query.bias", (dt,), "vec"),
+                (p + "attn.key.weight", (dt, dt), "mat"),
+                (p + "attn.value.weight", (dt, dt), "mat"), (p + "attn.value.bias", (dt,), "vec"),
+                (p + "attn.out.weight", (dt, dt), "mat"), (p + "attn.out.bias", (dt,), "vec"),
+                (p + "cross_attn_ln.weight", (dt,), "lnw"), (p + "cross_attn_ln.bias", (dt,), "vec"),
+                (p + "cross_attn.query.weight", (dt, dt), "mat"), (p + "cross_attn.query.bias", (dt,), "vec"),
+                (p + "cross_attn.key.weight", (dt, dt), "mat"),
+                (p + "cross_attn.value.weight", (dt, dt), "mat"), (p + "cross_attn.value.bias", (dt,), "vec"),
+                (p + "cross_attn.out.weight", (dt, dt), "mat"), (p + "cross_attn.out.bias", (dt,), "vec")]
+    return out
+
+
+def read_vocab_blob(stub_path):
+    """raw bytes of the vocabulary section (i32 count + (u32 len, bytes)*) of an existing legacy model file"""
+    with open(stub_path, "rb") as f:
+        data = f.read()
+    off = 4 + 44
+    n_mel, n_fft = struct.unpack_from("<2i", data, off)
+    off += 8 + n_mel * n_fft * 4
+    start = off
+    n, = struct.unpack_from("<i", data, off)
+    off += 4
+    for _ in range(n):
+        ln, = struct.unpack_from("<I", data, off)
+        off += 4 + ln
+    return data[start:off]
+
+
+def synthetic_vocab_blob(n):
+    """n distinct printable tokens; token 220 is " " (needed by suppress_blank, src/whisper.cpp:6238)"""
+    parts = [struct.pack("<i", n)]
+    for i in range(n):
+        s = b" " if i == 220 else (b" w%d" % i if i % 3 else b"w%d" % i)
+        parts.append(struct.pack("<I", len(s)) + s)
+    return b"".join(parts)
+
+
+def write_model(path, config="test-2l.en", wtype=F16, seed=0, sigma=0.02, vocab_from=None, quantizer=None, fast_pool=False):
+    """Write a synthetic model.  Weights: matrices/embeddings N(0, sigma^2), LN weight 1+N(0,.02^2), biases N(0,.02^2),
+    per-tensor seed = crc32(name) ^ seed.  fast_pool=True draws matrix blocks from one pre-quantised
+    pool of 2^22 values (for the multi-GB benchmark models; same marginal distribution, seconds instead of minutes)."""
+    cfg = CONFIGS[config] if isinstance(config, str) else tuple(config)
+    n_vocab, n_actx, d, n_ah, La, n_tctx, dt, n_th, Lt, n_mels = cfg
+    q = quantizer or quantize
+    ftype = FTYPE_OF[wtype] + (2000 if wtype not in (F32, F16) else 0)
+    blk = {Q4_0: (32, 18), Q5_0: (32, 22), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176)}.get(wtype)
+    pool = None
+    if fast_pool:
+        prng = np.random.default_rng(seed ^ 0x5EED)
+        pool_w = (prng.standard_normal(1 << 22) * sigma).astype(np.float32)
+        if blk:
+            pool = np.frombuffer(q(wtype, pool_w.reshape(-1, blk[0])), dtype=np.uint8).reshape(-1, blk[1])
+        elif wtype == F16:
+            pool = pool_w.astype(np.float16).reshape(-1, 32)
+        else:
+            pool = pool_w.reshape(-1, 32)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", 0x67676d6c))
+        f.write(struct.pack("<11i", n_vocab, n_actx, d, n_ah, La, n_tctx, dt, n_th, Lt, n_mels, ftype))
+        filt = mel_filters(n_mels)
+        f.write(struct.pack("<2i", n_mels, 201))
+        f.write(filt.tobytes())
+        if vocab_from:
+            f.write(read_vocab_blob(vocab_from))
+        else:
+            f.write(synthetic_vocab_blob(n_vocab - (1 if n_vocab >= 51865 else 0) * 0))
+        for name, shape, kind in tensor_list(cfg):
+            rng = np.random.default_rng((zlib.crc32(name.encode()) ^ seed) & 0xFFFFFFFF)
+            n_el = int(np.prod(shape))
+            if kind == "mat":
+                ttype = wtype
+                if pool is not None:
+                    per = pool.shape[1] if not blk else blk[0]
+                    nblk = n_el // (blk[0] if blk else 32)
+                    idx = rng.integers(0, pool.shape[0], size=nblk)
+                    data = pool[idx].tobytes()
+                else:
+                    data = q(wtype, (rng.standard_normal(shape) * sigma).astype(np.float32))
+            elif kind == "conv":
+                ttype = F16 if wtype != F32 else F32
+                w = (rng.standard_normal(shape) * sigma * 2).astype(np.float32)
+                data = w.astype(np.float16).tobytes() if ttype == F16 else w.tobytes()
+            elif kind == "pos":
+                ttype = F32
+                data = (rng.standard_normal(shape) * sigma).astype(np.float32).tobytes()
+            elif kind == "lnw":
+                ttype = F32
+                data = (1.0 + rng.standard_normal(shape) * 0.02).astype(np.float32).tobytes()
+            else:
+                ttype = F32
+                data = (rng.standard_normal(shape) * 0.02).astype(np.float32).tobytes()
+            nb = name.encode()
+            f.write(struct.pack("<3i", len(shape), len(nb), ttype))
+            for dim in reversed(shape):
+                f.write(struct.pack("<i", dim))
+            f.write(nb)
+            f.write(data)
+    return path
+
+
+def synth_audio(seed=1234, seconds=30.0, sr=16000):
+    """sum of 8 sinusoids 80-3800 Hz with random phases x slow AM + N(0, 0.01^2), peak 0.5"""
+    rng = np.random.default_rng(seed)
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    x = np.zeros(n)
+    for f0 in rng.uniform(80, 3800, size=8):
+        x += np.sin(2 * np.pi * f0 * t + rng.uniform(0, 2 * np.pi)) * (0.5 + 0.5 * np.sin(2 * np.pi * rng.uniform(0.1, 2.0) * t + rng.uniform(0, 6.28)))
+    x += rng.standard_normal(n) * 0.01
+    x *= 0.5 / np.abs(x).max()
+    return x.astype(np.float32)
