@@ -79,6 +79,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_LOG_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
+_quiet = _LOG_CB(lambda level, text, ud: None)
+
+
+def silence(lib):
+    """route the library's INFO chatter away from stdout/stderr (whisper_log_set, whisper.h:763)"""
+    if os.environ.get("WB200_VERBOSE"):
+        return
+    lib.whisper_log_set.argtypes = [_LOG_CB, C.c_void_p]
+    lib.whisper_log_set(_quiet, None)
+
+
 def make_inputs(rank, n_chunks):
     synth = load_pkg().synth
     return [synth.synth_audio(seed=1000 * rank + i, seconds=CHUNK_SECONDS) for i in range(n_chunks)]
@@ -116,6 +128,7 @@ def run_reference(args, rank, world):
     pkg = load_pkg()
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
     R = pkg.bind_whisper_api(C.CDLL(ref_path))
+    silence(R)
     model = ensure_model(os.path.join(tempfile.gettempdir(), "wb200-%s-q5_0.bin" % MODEL_CFG))
     cp = R.whisper_context_default_params(); cp.use_gpu = False
     ctx = R.whisper_init_from_file_with_params(model.encode(), cp)
@@ -172,6 +185,7 @@ def main():
     if world > 1:
         dist.barrier()
 
+    silence(pkg.bind_whisper_api(C.CDLL(pkg.LIB_PATH)))
     eng = pkg.WhisperB200(model, gpu_device=local)
     L = eng.L
     vp = C.c_void_p
@@ -273,6 +287,7 @@ def main():
             try:
                 ref_path = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
                 R = pkg.bind_whisper_api(C.CDLL(ref_path))
+                silence(R)
                 cp = R.whisper_context_default_params(); cp.use_gpu = False
                 rctx = R.whisper_init_from_file_with_params(model.encode(), cp)
                 cores = os.cpu_count() or 1

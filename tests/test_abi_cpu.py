@@ -1,0 +1,83 @@
+"""CPU tests of the drop-in boundary: libwhisper_b200.so loads without a GPU, exports every symbol include/whisper_b200.h
+declares (and exactly the whisper_* set the reference library exports), its by-value structs have the reference's sizes,
+pure-host entry points behave like the reference, and the product path fails LOUDLY when no CUDA device exists."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from wbtest import ROOT, LIB_PATH, REF_PATH, DATA_DIR, bind_whisper_api, ContextParams, FullParams, TokenData, load_lib
+
+
+def _exported(path):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return {l.split()[-1] for l in out.splitlines() if " T " in l}
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "whisper_b200.h")).read()
+    declared = set(re.findall(r"WB_EXPORT[^;(]*?\b(whisper_\w+|wb200_\w+)\s*\(", hdr))
+    assert len(declared) > 130
+    missing = declared - _exported(LIB_PATH)
+    assert not missing, missing
+
+
+def test_same_whisper_symbols_as_reference():
+    if not os.path.exists(REF_PATH):
+        pytest.skip("reference library not built")
+    mine = {s for s in _exported(LIB_PATH) if s.startswith("whisper_")}
+    theirs = {s for s in _exported(REF_PATH) if s.startswith("whisper_")}
+    assert mine == theirs
+
+
+def test_struct_sizes_match_reference(ref):
+    assert C.sizeof(FullParams) == ref.wref_sizeof_full_params() == 304
+    assert C.sizeof(ContextParams) == ref.wref_sizeof_context_params() == 48
+    assert C.sizeof(TokenData) == ref.wref_sizeof_token_data() == 56
+
+
+def test_default_params_equal_reference(ref):
+    L = bind_whisper_api(load_lib()); R = bind_whisper_api(ref)
+    for strategy in (0, 1):
+        a = L.whisper_full_default_params(strategy); b = R.whisper_full_default_params(strategy)
+        for name, _ in FullParams._fields_:
+            va, vb = getattr(a, name), getattr(b, name)
+            if name == "n_threads":
+                continue
+            if name == "prompt_tokens":
+                assert not va and not vb      # NULL pointers on both sides
+                continue
+            if name in ("greedy", "beam_search", "vad_params"):
+                for sub, _ in type(va)._fields_:
+                    assert getattr(va, sub) == getattr(vb, sub), (name, sub)
+            else:
+                assert va == vb, name
+    a = L.whisper_context_default_params(); b = R.whisper_context_default_params()
+    for name in ("use_gpu", "flash_attn", "gpu_device", "dtw_token_timestamps", "dtw_aheads_preset", "dtw_n_top", "dtw_mem_size"):
+        assert getattr(a, name) == getattr(b, name), name
+
+
+def test_language_table_equals_reference(ref):
+    L = bind_whisper_api(load_lib()); R = bind_whisper_api(ref)
+    assert L.whisper_lang_max_id() == R.whisper_lang_max_id() == 99
+    for i in range(100):
+        assert L.whisper_lang_str(i) == R.whisper_lang_str(i)
+        assert L.whisper_lang_str_full(i) == R.whisper_lang_str_full(i)
+        assert L.whisper_lang_id(R.whisper_lang_str(i)) == i
+        assert L.whisper_lang_id(R.whisper_lang_str_full(i)) == i
+    assert L.whisper_lang_id(b"klingon") == -1
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = bind_whisper_api(load_lib())
+    cp = L.whisper_context_default_params()
+    ctx = L.whisper_init_from_file_with_params(os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin").encode(), cp)
+    assert not ctx
+    assert b"no CUDA device" in L.wb200_last_error() or b"CPU fallback" in L.wb200_last_error()
+    cp.use_gpu = False
+    assert not L.whisper_init_from_file_with_params(os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin").encode(), cp)
