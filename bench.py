@@ -197,31 +197,26 @@ def main():
     n_chunks = args.chunks
     pcms = make_inputs(rank, n_chunks)
     pinned = [torch.from_numpy(p).pin_memory() for p in pcms]          # e2e copies start from pinned host memory
-    states = [L.whisper_init_state(eng.ctx) for _ in range(n_chunks)]
-    assert all(states), L.wb200_last_error()
+    resident = [t.cuda(local, non_blocking=False) for t in pinned]     # `value`: PCM already in HBM
+    L.wb200_full_batch_ex.argtypes = [vp, pkg.FullParams, C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(vp), C.c_int]
     p = full_params(L, 4)
-    n_streams = int(os.environ.get("WB200_BATCH_STREAMS", "4"))
+    n_arr = (C.c_int * n_chunks)(*[len(x) for x in pcms])
+    host_ptrs = (vp * n_chunks)(*[t.data_ptr() for t in pinned])
+    dev_ptrs = (vp * n_chunks)(*[t.data_ptr() for t in resident])
+    last = {"tokens": 0, "enc": None}
 
-    def run_pass(resident):
-        """one step: every chunk of this rank through whisper_full_with_state, n_streams states in flight"""
-        nxt = [0]; lock = threading.Lock(); rcs = []
+    def run_pass(on_device):
+        """one step: all chunks of this rank through the lock-step batch driver (whisper_full_with_state semantics per chunk)"""
+        outs = (vp * n_chunks)()
+        rc = L.wb200_full_batch_ex(eng.ctx, p, dev_ptrs if on_device else host_ptrs, n_arr, n_chunks, outs, 1 if on_device else 0)
+        assert rc == 0, (rc, L.wb200_last_error())
+        last["tokens"] = sum(count_tokens(L, outs[i]) for i in range(n_chunks))
+        for i in range(n_chunks):
+            L.whisper_free_state(outs[i])
 
-        def work():
-            while True:
-                with lock:
-                    i = nxt[0]; nxt[0] += 1
-                if i >= n_chunks:
-                    return
-                ptr = None if resident else C.c_void_p(pinned[i].data_ptr())
-                rcs.append(L.whisper_full_with_state(eng.ctx, states[i], p, ptr, len(pcms[i])))
-
-        th = [threading.Thread(target=work) for _ in range(min(n_streams, n_chunks))]
-        [t.start() for t in th]; [t.join() for t in th]
-        assert all(r == 0 for r in rcs), (rcs, L.wb200_last_error())
-
-    def timed(resident, steps, warmup):
+    def timed(on_device, steps, warmup):
         for _ in range(warmup):
-            run_pass(resident)
+            run_pass(on_device)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -229,7 +224,7 @@ def main():
         n0 = eng.launch_count()
         t0 = time.perf_counter()
         for _ in range(steps):
-            run_pass(resident)
+            run_pass(on_device)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         h1, d1 = C.c_uint64(), C.c_uint64(); L.wb200_traffic(C.byref(h1), C.byref(d1))
@@ -241,25 +236,33 @@ def main():
         return dt, launches, (h1.value - h0.value) / steps, (d1.value - d0.value) / steps
 
     # ---- device-resident inputs ("value")
-    for i in range(n_chunks):
-        assert L.wb200_pcm_upload(states[i], C.c_void_p(pinned[i].data_ptr()), len(pcms[i])) == 0
     sampler = ClockSampler(local); sampler.start()
     dt_res, launches, _, _ = timed(True, args.steps, args.warmup)
     clocks = sampler.stop()
     audio_s = CHUNK_SECONDS * n_chunks * args.steps * world
     value = audio_s / dt_res
-    tokens = sum(count_tokens(L, s) for s in states)
-    enc = (C.c_float * 4)()
-    L.wb200_last_encode_ms(states[0], enc)
+    tokens = last["tokens"]
 
     # ---- host buffers through the C ABI ("e2e")
     dt_e2e, _, h2d, d2h = timed(False, args.steps, 1)
     e2e = audio_s / dt_e2e
 
+    # ---- encode ms of ONE 30 s window (whisper-bench "Enc." semantics: conv + encoder + cross, bench.cpp:63-150) on the default state
+    st0 = L.wb200_ctx_state(eng.ctx)
+    L.whisper_pcm_to_mel.argtypes = [vp, vp, C.c_int, C.c_int]
+    assert L.whisper_pcm_to_mel(eng.ctx, vp(pinned[0].data_ptr()), len(pcms[0]), 1) == 0
+    enc = (C.c_float * 4)()
+    enc_runs = []
+    for _ in range(5):
+        assert L.whisper_encode(eng.ctx, 0, 1) == 0
+        L.wb200_last_encode_ms(st0, enc)
+        enc_runs.append([float(enc[i]) for i in range(4)])
+    enc = enc_runs[-1]
+
     out = {"metric": "xRT (audio-s/wall-s)", "value": value, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f16 tcgen05 (encode) / int8 dp4a block dot (decode), f32 accumulate", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "streams_per_gpu": n_streams, "l2": "inputs and weights (1.06 GB/GPU + 0.65 GB/state) exceed the 126 MB L2"},
+           "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "decode": "lock-step batch of up to 8 sequences per GPU", "l2": "weights (1.08 GB) + KV (0.3 GB/sequence) streamed every step exceed the 126 MB L2"},
            "encode_ms": float(enc[1] + enc[2] + enc[3]), "encode_ms_parts": {"mel": float(enc[0]), "conv": float(enc[1]), "encoder": float(enc[2]), "cross": float(enc[3])},
            "decoded_tokens_per_step": tokens, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
@@ -268,7 +271,7 @@ def main():
         # ---- roofline of the dominant kernel class: separate pass of ONE chunk with per-launch CUDA events (library side,
         # on the launching stream); not inside the timed region so the event overhead does not perturb `value`
         L.wb200_profile_enable(1)
-        assert L.whisper_full_with_state(eng.ctx, states[0], p, None, len(pcms[0])) == 0
+        run_pass(True)
         ms = (C.c_double * 4)(); ln = (C.c_uint64 * 4)(); by = (C.c_double * 4)(); fl = (C.c_double * 4)()
         L.wb200_profile_collect(ms, ln, by, fl)
         L.wb200_profile_enable(0)
@@ -303,8 +306,6 @@ def main():
             except Exception as e:  # noqa: BLE001
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out), flush=True)
-    for s in states:
-        L.whisper_free_state(s)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

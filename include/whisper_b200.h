@@ -412,11 +412,16 @@ WB_EXPORT void  whisper_vad_free         (struct whisper_vad_context * ctx);
  * which: 0 = mel [n_mel][n_len] f32, 1 = conv-stem output [n_ctx][n_state] f32 (token-major),
  *        2 = encoder output [n_ctx][n_state] f32, 3/4 = cross K/V [n_text_layer][1536][n_state] as f32 */
 WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * state, int which, float * out, int64_t cap);
-/* run `n_chunks` independent PCM buffers through whisper_full_with_state semantics on ONE
- * device, `n_streams` states in flight; the segments of chunk i land in states[i].  Returns 0 ok. */
+/* run `n_chunks` independent PCM buffers through whisper_full_with_state semantics on ONE device in LOCK-STEP:
+ * up to 8 member states share one engine, so every encoder pass / decode step serves all live chunks at once
+ * (weights are read once per step).  Chunk i's segments land in the result-only state states_out[i] (free with
+ * whisper_free_state).  _ex flags bit 0: samples[i] are DEVICE pointers (PCM already in HBM).  Returns 0 ok. */
 WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,
                                const float * const * samples, const int * n_samples, int n_chunks,
                                struct whisper_state ** states_out);
+WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params,
+                                  const float * const * samples, const int * n_samples, int n_chunks,
+                                  struct whisper_state ** states_out, int flags);
 /* the default state owned by a context created with a *_with_params (non-_no_state) call; NULL otherwise */
 WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx);
 /* stage PCM in HBM ahead of time: a following whisper_full_with_state(ctx, state, params, NULL, n_samples) (or

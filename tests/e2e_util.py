@@ -11,6 +11,8 @@ synth = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(synth)
 
 vp = C.c_void_p
+_LOG_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, vp)
+_quiet = _LOG_CB(lambda level, text, ud: None)
 
 
 def _p(a):
@@ -23,6 +25,9 @@ class Side:
     def __init__(self, L, model_path, is_ref):
         self.L = bind_whisper_api(L)
         self.is_ref = is_ref
+        if not os.environ.get("WB200_VERBOSE"):
+            L.whisper_log_set.argtypes = [_LOG_CB, vp]
+            L.whisper_log_set(_quiet, None)
         cp = L.whisper_context_default_params()
         cp.use_gpu = not is_ref
         self.ctx = L.whisper_init_from_file_with_params(model_path.encode(), cp)

@@ -138,3 +138,36 @@ def test_loader_fixtures_and_errors(lib):
     assert not L.whisper_init_from_file_with_params(b"/nonexistent/model.bin", cp)
     bad = os.path.join(DATA_DIR, "jfk.wav")
     assert not L.whisper_init_from_file_with_params(bad.encode(), cp)       # bad magic
+
+
+def test_lockstep_batch_equals_one_by_one(lib, ref, tmp_path):
+    """wb200_full_batch (lock-step batched encode/decode of independent chunks) must give, chunk by chunk, exactly the
+    tokens whisper_full gives for that chunk alone: batching only changes how many sequences share a weight read."""
+    import ctypes as C
+    from wbtest import FullParams
+    path = _build(tmp_path, ref, "test-2l.en", Q5_0, seed=5)
+    A = Side(lib, path, False)
+    try:
+        L = A.L
+        vp = C.c_void_p
+        chunks = [synth.synth_audio(seed=20 + i, seconds=s) for i, s in enumerate((30.0, 12.0, 47.0, 30.0, 3.0))]
+        fp = L.whisper_full_default_params(0); fp.print_progress = False; fp.temperature_inc = 0.0; fp.greedy.best_of = 1
+        L.wb200_full_batch.argtypes = [vp, FullParams, C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        n = len(chunks)
+        ptrs = (vp * n)(*[c.ctypes.data for c in chunks]); lens = (C.c_int * n)(*[len(c) for c in chunks]); outs = (vp * n)()
+        assert L.wb200_full_batch(A.ctx, fp, ptrs, lens, n, outs) == 0, L.wb200_last_error()
+        batched = []
+        for i in range(n):
+            st = outs[i]
+            batched.append([[L.whisper_full_get_token_id_from_state(st, s, j) for j in range(L.whisper_full_n_tokens_from_state(st, s))]
+                            for s in range(L.whisper_full_n_segments_from_state(st))])
+            L.whisper_free_state(st)
+        single = []
+        for c in chunks:
+            assert L.whisper_full(A.ctx, fp, c.ctypes.data_as(vp), len(c)) == 0
+            single.append([[L.whisper_full_get_token_id(A.ctx, s, j) for j in range(L.whisper_full_n_tokens(A.ctx, s))]
+                           for s in range(L.whisper_full_n_segments(A.ctx))])
+        assert batched == single
+        assert sum(len(t) for c in batched for t in c) > 0
+    finally:
+        A.free()

@@ -17,6 +17,8 @@ extern const char * const g_lang_codes[100];
 extern const char * const g_lang_names[100];
 void set_log_sink(void (*cb)(int, const char *, void *), void * ud);
 
+bool & tls_pcm_is_device() { static thread_local bool f = false; return f; }
+
 int64_t time_us() {
     return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -64,44 +66,172 @@ void KvCells::seq_cp(int src, int dst, int p0, int p1) {                        
 }
 
 // ---------------------------------------------------------------------------------------------------- engine glue
+namespace {
+// host-side preparation of one decode request: KV slot search + attention index lists (whisper.cpp:2876-2948)
+struct PreparedDecode {
+    std::vector<DecToken> rows; std::vector<int> cells, nkv, idx; int ld = 0;
+};
+bool prepare_decode(whisper_state & st, const int * tokens, const int * pos, const int * seq, const int8_t * want, int n_tokens, PreparedDecode & P) {
+    KvCells & kv = st.kv;
+    if (!kv.find_slot(pos, seq, (uint32_t) n_tokens)) { set_error("decode: no KV slot for %d tokens", n_tokens); return false; }
+    kv.n = (uint32_t) std::min<int>((int) kv.size, std::max(1, kv.cell_max()));      // padding 1 on this path (whisper.cpp:2884-2885)
+    const int n_kv = (int) kv.n;
+    P.ld = n_kv;
+    P.rows.resize(n_tokens); P.cells.resize(n_tokens); P.nkv.resize(n_tokens); P.idx.assign((size_t) n_tokens * n_kv, 0);
+    for (int j = 0; j < n_tokens; ++j) {
+        P.rows[j] = { tokens[j], pos[j], seq[j], st.slot, want[j] != 0 };
+        P.cells[j] = st.cell_off + (int) kv.head + j;
+        int c = 0;
+        for (int i = 0; i < n_kv; ++i) {                                              // KQ_mask rule, whisper.cpp:2928-2938
+            const KvCells::Cell & cell = kv.cells[i];
+            if ((cell.seqs & (1u << seq[j])) && cell.pos <= pos[j]) P.idx[(size_t) j * n_kv + c++] = st.cell_off + i;
+        }
+        P.nkv[j] = c;
+    }
+    return true;
+}
+void account_decode(whisper_state & st, int n_tokens, int64_t dt) {                    // whisper.cpp:2974-2983
+    if (n_tokens == 1)      { st.t_decode_us += dt; st.n_decode++; }
+    else if (n_tokens < 16) { st.t_batchd_us += dt; st.n_batchd += n_tokens; }
+    else                    { st.t_prompt_us += dt; st.n_prompt += n_tokens; }
+}
+} // namespace
+
 bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset) {
     const int64_t t0 = time_us();
     const int n_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
-    if (st.eng.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.eng.n_mel, ctx.model.hp.n_mels); return false; }
-    const int seek = mel_offset;
-    if (!st.eng.encode(&seek, 1, n_ctx)) return false;
-    st.t_encode_us += time_us() - t0;
+    if (st.fe.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.fe.n_mel, ctx.model.hp.n_mels); return false; }
+    if (st.group) {
+        Group::Req r; r.kind = 0; r.ctx = &ctx; r.st = &st; r.seek = mel_offset; r.n_ctx = n_ctx;
+        if (!st.group->submit(r)) return false;
+        st.t_encode_us += r.dt_us;
+    } else {
+        const EncSrc src = { st.fe.mel.p, st.fe.n_len, st.fe.n_mel, mel_offset, st.slot };
+        if (!st.eng->encode(&src, 1, n_ctx)) return false;
+        st.t_encode_us += time_us() - t0;
+    }
     st.n_encode++;
     return true;
 }
 
 bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens, const int * pos, const int * seq,
-                  const int8_t * want, int n_tokens) {
+                  const int8_t * want, int n_tokens, const SampReq * samp) {
     const int64_t t0 = time_us();
     const int n_vocab = ctx.model.hp.n_vocab;
-    KvCells & kv = st.kv;
-    if (!kv.find_slot(pos, seq, (uint32_t) n_tokens)) { set_error("decode: no KV slot for %d tokens", n_tokens); return false; }
-    kv.n = (uint32_t) std::min<int>((int) kv.size, std::max(1, kv.cell_max()));      // padding 1 on this path (whisper.cpp:2884-2885)
-    const int n_kv = (int) kv.n;
-    std::vector<DecToken> rows(n_tokens);
-    std::vector<int> cells(n_tokens), nkv(n_tokens), idx((size_t) n_tokens * n_kv);
-    for (int j = 0; j < n_tokens; ++j) {
-        rows[j] = { tokens[j], pos[j], seq[j], st.slot, want[j] != 0 };
-        cells[j] = (int) kv.head + j;
-        int c = 0;
-        for (int i = 0; i < n_kv; ++i) {                                              // KQ_mask rule, whisper.cpp:2928-2938
-            const KvCells::Cell & cell = kv.cells[i];
-            if ((cell.seqs & (1u << seq[j])) && cell.pos <= pos[j]) idx[(size_t) j * n_kv + c++] = i;
-        }
-        nkv[j] = c;
+    if (st.group) {
+        Group::Req r; r.kind = 1; r.ctx = &ctx; r.st = &st; r.tokens = tokens; r.pos = pos; r.seq = seq; r.want = want; r.n = n_tokens; r.samp = samp;
+        if (!st.group->submit(r)) return false;
+        account_decode(st, n_tokens, r.dt_us);
+        return true;
     }
-    st.logits.resize((size_t) n_tokens * n_vocab);
-    if (!st.eng.decode(rows.data(), n_tokens, cells.data(), idx.data(), n_kv, nkv.data(), st.logits.data())) return false;
-    const int64_t dt = time_us() - t0;
-    if (n_tokens == 1)      { st.t_decode_us += dt; st.n_decode++; }                  // whisper.cpp:2974-2983
-    else if (n_tokens < 16) { st.t_batchd_us += dt; st.n_batchd += n_tokens; }
-    else                    { st.t_prompt_us += dt; st.n_prompt += n_tokens; }
+    PreparedDecode P;
+    if (!prepare_decode(st, tokens, pos, seq, want, n_tokens, P)) return false;
+    if (samp) {
+        if (!st.eng->set_samp_mask(samp->mask_key, *samp->mask_bits)) return false;
+        st.samp_out.assign(n_tokens, SampOut());
+        if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), nullptr, &samp->cfg, samp->rowinfo, st.samp_out.data())) return false;
+    } else {
+        st.samp_out.clear();
+        st.logits.resize((size_t) n_tokens * n_vocab);
+        std::vector<float *> outs(n_tokens);
+        for (int j = 0; j < n_tokens; ++j) outs[j] = st.logits.data() + (size_t) j * n_vocab;
+        if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), outs.data())) return false;
+    }
+    account_decode(st, n_tokens, time_us() - t0);
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------- batch group
+bool Group::submit(Req & r) {
+    std::unique_lock<std::mutex> lk(mu);
+    pending.push_back(&r);
+    if ((int) pending.size() >= n_active) {
+        std::vector<Req *> batch; batch.swap(pending);
+        lk.unlock();
+        run(batch);
+        lk.lock();
+        for (Req * q : batch) q->done = true;
+        cv.notify_all();
+    } else {
+        cv.wait(lk, [&] { return r.done; });
+    }
+    return r.ok;
+}
+void Group::leave() {
+    std::unique_lock<std::mutex> lk(mu);
+    n_active--;
+    if (!pending.empty() && (int) pending.size() >= n_active) {
+        std::vector<Req *> batch; batch.swap(pending);
+        lk.unlock();
+        run(batch);
+        lk.lock();
+        for (Req * q : batch) q->done = true;
+        cv.notify_all();
+    }
+}
+void Group::run(std::vector<Req *> & batch) {
+    // encode requests first (they only touch the encoder workspaces and the members' cross-KV slots)
+    std::vector<Req *> enc, dec;
+    for (Req * q : batch) (q->kind == 0 ? enc : dec).push_back(q);
+    if (!enc.empty()) {
+        const int64_t t0 = time_us();
+        bool same_ctx = true;
+        for (Req * q : enc) same_ctx &= (q->n_ctx == enc[0]->n_ctx);
+        bool ok = true;
+        if (same_ctx) {
+            std::vector<EncSrc> srcs;
+            for (Req * q : enc) srcs.push_back({ q->st->fe.mel.p, q->st->fe.n_len, q->st->fe.n_mel, q->seek, q->st->slot });
+            ok = eng.encode(srcs.data(), (int) srcs.size(), enc[0]->n_ctx);
+        } else {
+            for (Req * q : enc) { const EncSrc s = { q->st->fe.mel.p, q->st->fe.n_len, q->st->fe.n_mel, q->seek, q->st->slot }; ok &= eng.encode(&s, 1, q->n_ctx); }
+        }
+        const int64_t dt = (time_us() - t0) / (int64_t) enc.size();
+        for (Req * q : enc) { q->ok = ok; q->dt_us = dt; }
+    }
+    if (!dec.empty()) {
+        const int64_t t0 = time_us();
+        const int n_vocab = eng.m->hp.n_vocab;
+        std::vector<PreparedDecode> preps(dec.size());
+        bool ok = true; int total = 0, ld = 1;
+        for (size_t i = 0; i < dec.size(); ++i) {
+            Req * q = dec[i];
+            ok &= prepare_decode(*q->st, q->tokens, q->pos, q->seq, q->want, q->n, preps[i]);
+            total += q->n; ld = std::max(ld, preps[i].ld);
+        }
+        bool all_samp = true;
+        for (Req * q : dec) all_samp &= (q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key &&
+                                         memcmp(&q->samp->cfg, &dec[0]->samp->cfg, sizeof(SampCfg)) == 0);
+        if (ok && all_samp) ok = eng.set_samp_mask(dec[0]->samp->mask_key, *dec[0]->samp->mask_bits);
+        if (ok) {
+            std::vector<DecToken> rows; std::vector<int> cells, nkv, idx((size_t) total * ld, 0); std::vector<float *> outs;
+            std::vector<int> rowinfo; std::vector<SampOut> souts((size_t) total); std::vector<std::pair<Req *, int>> origin;
+            rows.reserve(total);
+            // interleave: row k of every request first, so that single-token steps of all members share one pass of <= 8 rows
+            // and multi-token prompts advance in lock-step (causal order inside each member is preserved)
+            int maxn = 0; for (Req * q : dec) maxn = std::max(maxn, q->n);
+            for (Req * q : dec) { if (all_samp) q->st->samp_out.assign(q->n, SampOut()); else { q->st->samp_out.clear(); q->st->logits.resize((size_t) q->n * n_vocab); } }
+            for (int k = 0; k < maxn; ++k) {
+                for (size_t i = 0; i < dec.size(); ++i) {
+                    Req * q = dec[i]; if (k >= q->n) continue;
+                    const PreparedDecode & P = preps[i];
+                    const size_t r = rows.size();
+                    rows.push_back(P.rows[k]); cells.push_back(P.cells[k]); nkv.push_back(P.nkv[k]);
+                    memcpy(idx.data() + r * ld, P.idx.data() + (size_t) k * P.ld, (size_t) P.nkv[k] * sizeof(int));
+                    outs.push_back(all_samp ? nullptr : q->st->logits.data() + (size_t) k * n_vocab);
+                    if (all_samp) { rowinfo.push_back(q->samp->rowinfo[2*k]); rowinfo.push_back(q->samp->rowinfo[2*k + 1]); }
+                    origin.emplace_back(q, k);
+                }
+            }
+            if (all_samp) {
+                ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), nullptr, &dec[0]->samp->cfg, rowinfo.data(), souts.data());
+                for (int r = 0; r < total; ++r) origin[r].first->st->samp_out[origin[r].second] = souts[r];
+            } else {
+                ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), outs.data());
+            }
+        }
+        const int64_t dt = (time_us() - t0) / (int64_t) dec.size();
+        for (Req * q : dec) { q->ok = ok; q->dt_us = dt; }
+    }
 }
 
 static std::vector<whisper_token> tokenize(const Vocab & vocab, const std::string & text) {   // whisper.cpp:3284-3332
@@ -220,10 +350,10 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
     whisper_state * st = nullptr;
     try {
         st = new whisper_state();
-        int cap = 1;
-        if (const char * e = getenv("WB200_STATE_WINDOWS")) cap = std::max(1, atoi(e));
-        if (!st->eng.init(&ctx->model, cap)) { delete st; return nullptr; }
-        st->kv.reset((uint32_t) st->eng.n_cells);
+        st->own_eng.reset(new Engine());
+        st->eng = st->own_eng.get();
+        if (!st->fe.init(&ctx->model) || !st->eng->init(&ctx->model, 1)) { delete st; return nullptr; }
+        st->kv.reset((uint32_t) st->eng->n_cells);
         st->kv_self_n_dec = 1;
         st->decoders[0].rng = std::mt19937(0);
     } catch (...) { set_error("whisper_init_state: allocation failed"); delete st; return nullptr; }
@@ -236,6 +366,9 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
 
 WB_EXPORT void whisper_free_state(struct whisper_state * st) { delete st; }
 WB_EXPORT void whisper_free(struct whisper_context * ctx) { if (ctx) { whisper_free_state(ctx->state); delete ctx; } }
+} // extern "C"
+whisper_context::~whisper_context() {}
+extern "C" {
 
 WB_EXPORT struct whisper_context * whisper_init_from_file_with_params(const char * path, struct whisper_context_params p)            { WB_INIT_WITH_STATE(whisper_init_from_file_with_params_no_state(path, p)) }
 WB_EXPORT struct whisper_context * whisper_init_from_buffer_with_params(void * b, size_t n, struct whisper_context_params p)           { WB_INIT_WITH_STATE(whisper_init_from_buffer_with_params_no_state(b, n, p)) }
@@ -254,7 +387,7 @@ WB_EXPORT int whisper_ctx_init_openvino_encoder(struct whisper_context *, const 
 WB_EXPORT int whisper_pcm_to_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * samples, int n_samples, int) {
     if (!ctx || !st || n_samples < 0) return -1;     // samples == NULL is legal after wb200_pcm_upload (device-resident input)
     const int64_t t0 = time_us();
-    if (!st->eng.pcm_to_mel(samples, n_samples)) { logf(LOG_ERROR, "%s: failed to compute mel spectrogram\n", __func__); return -1; }
+    if (!st->fe.pcm_to_mel(samples, n_samples, wb::tls_pcm_is_device())) { logf(LOG_ERROR, "%s: failed to compute mel spectrogram\n", __func__); return -1; }
     st->t_mel_us += time_us() - t0;
     return 0;
 }
@@ -264,7 +397,7 @@ WB_EXPORT int whisper_pcm_to_mel(struct whisper_context * ctx, const float * sam
 WB_EXPORT int whisper_set_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * data, int n_len, int n_mel) {
     if (!ctx || !st) return -1;
     if (n_mel != ctx->model.n_filt_mel) { logf(LOG_ERROR, "%s: invalid number of mel bands: %d (expected %d)\n", __func__, n_mel, ctx->model.n_filt_mel); return -1; }
-    return st->eng.set_mel(data, n_len, n_mel) ? 0 : -1;
+    return st->fe.set_mel(data, n_len, n_mel) ? 0 : -1;
 }
 WB_EXPORT int whisper_set_mel(struct whisper_context * ctx, const float * data, int n_len, int n_mel) {
     return ctx ? whisper_set_mel_with_state(ctx, ctx->state, data, n_len, n_mel) : -1;
@@ -315,7 +448,7 @@ WB_EXPORT const char * whisper_lang_str_full(int id) { if (id >= 0 && id < 100) 
 WB_EXPORT int whisper_lang_auto_detect_with_state(struct whisper_context * ctx, struct whisper_state * st, int offset_ms, int n_threads, float * lang_probs) {
     const int seek = offset_ms / 10;                                                 // whisper.cpp:4047-4120
     if (seek < 0) { logf(LOG_ERROR, "%s: offset %dms is before the start of the audio\n", __func__, offset_ms); return -1; }
-    if (seek >= st->eng.n_len_org) { logf(LOG_ERROR, "%s: offset %dms is past the end of the audio (%dms)\n", __func__, offset_ms, st->eng.n_len_org * 10); return -2; }
+    if (seek >= st->fe.n_len_org) { logf(LOG_ERROR, "%s: offset %dms is past the end of the audio (%dms)\n", __func__, offset_ms, st->fe.n_len_org * 10); return -2; }
     if (whisper_encode_with_state(ctx, st, seek, n_threads) != 0) return -6;
     const whisper_token sot = ctx->vocab.token_sot;
     if (whisper_decode_with_state(ctx, st, &sot, 1, 0, n_threads) != 0) return -7;
@@ -338,8 +471,8 @@ WB_EXPORT int whisper_lang_auto_detect(struct whisper_context * ctx, int offset_
 }
 
 // ---------------------------------------------------------------------------------------------------- getters
-WB_EXPORT int whisper_n_len(struct whisper_context * ctx)              { return ctx->state->eng.n_len_org; }
-WB_EXPORT int whisper_n_len_from_state(struct whisper_state * st)      { return st->eng.n_len_org; }
+WB_EXPORT int whisper_n_len(struct whisper_context * ctx)              { return ctx->state->fe.n_len_org; }
+WB_EXPORT int whisper_n_len_from_state(struct whisper_state * st)      { return st->fe.n_len_org; }
 WB_EXPORT int whisper_n_vocab(struct whisper_context * ctx)            { return ctx->vocab.n_vocab; }
 WB_EXPORT int whisper_n_text_ctx(struct whisper_context * ctx)         { return ctx->model.hp.n_text_ctx; }
 WB_EXPORT int whisper_n_audio_ctx(struct whisper_context * ctx)        { return ctx->model.hp.n_audio_ctx; }
@@ -489,15 +622,16 @@ WB_EXPORT void  whisper_vad_free(struct whisper_vad_context *) {}
 // ---------------------------------------------------------------------------------------------------- engine extensions
 WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float * out, int64_t cap) {
     if (!st) return -1;
-    Engine & E = st->eng;
+    if (!st->eng) return -1;
+    Engine & E = *st->eng;
     const HParams & hp = E.m->hp;
     if (cudaSetDevice(E.m->device) != cudaSuccess) return -1;
     const int T = E.enc_n_ctx > 0 ? E.enc_n_ctx : hp.n_audio_ctx, d = hp.n_audio_state, Lt = hp.n_text_layer;
     if (which == 0) {
-        const int64_t n = (int64_t) E.n_mel * E.n_len;
+        const int64_t n = (int64_t) st->fe.n_mel * st->fe.n_len;
         if (!out) return n;
         if (n > cap) return -2;
-        return cudaMemcpy(out, E.mel.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? n : -3;
+        return cudaMemcpy(out, st->fe.mel.p, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess ? n : -3;
     }
     if (which == 1 || which == 2) {
         const int64_t n = (int64_t) T * d;
@@ -520,14 +654,15 @@ WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float 
     return -5;
 }
 WB_EXPORT int wb200_last_encode_ms(struct whisper_state * st, float * out4) {
-    if (!st || !out4) return -1;
-    for (int i = 0; i < 4; ++i) out4[i] = st->eng.last_ms[i];
+    if (!st || !out4 || !st->eng) return -1;
+    for (int i = 0; i < 4; ++i) out4[i] = st->eng->last_ms[i];
+    out4[0] = st->fe.last_mel_ms;
     return 0;
 }
 WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx) { return ctx ? ctx->state : nullptr; }
 WB_EXPORT int wb200_pcm_upload(struct whisper_state * st, const float * samples, int n_samples) {
     if (!st || !samples || n_samples <= 0) return -1;
-    return st->eng.pcm_upload(samples, n_samples) ? 0 : -1;
+    return st->fe.pcm_upload(samples, n_samples) ? 0 : -1;
 }
 WB_EXPORT void wb200_profile_enable(int on) { wb::prof_enable(on != 0); }
 WB_EXPORT void wb200_profile_collect(double * ms4, uint64_t * launches4, double * bytes4, double * flops4) { wb::prof_collect(ms4, launches4, bytes4, flops4); }

@@ -18,11 +18,18 @@ struct EncPlan {
     std::vector<EncLayerPlan> layers;
 };
 
+void Engine::drop_graphs() {
+    for (auto & kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+}
+
 Engine::~Engine() {
     if (m) cudaSetDevice(m->device);
+    drop_graphs();
     delete plan;
     if (hints) cudaFreeHost(hints);
     if (hlogits) cudaFreeHost(hlogits);
+    if (hsamp) cudaFreeHost(hsamp);
     for (auto & e : ev) if (e) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
 }
@@ -37,9 +44,10 @@ bool Engine::init(const Model * model, int cap_windows) {
     const size_t B = cap_win;
     Tp_max = Tp;
     debug_taps = getenv("WB200_DEBUG_TAPS") != nullptr;
-    if (!gmax.alloc(4)) return false;
+    use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
+    fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
     if (!mel_win.alloc(B * (2*T + 2) * M, true) || !h1.alloc(B * (2*T + 2) * d, true) || !x.alloc(B * T * d) || !xn.alloc(B * T * d) ||
-        !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || !S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp) ||
+        !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || (!fused_attn && (!S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp))) ||
         !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d) || !kv_cross.alloc(B * 2 * Lt * Tp * d, true)) return false;
     if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
     // decoder workspaces (8 rows per pass)
@@ -47,17 +55,20 @@ bool Engine::init(const Model * model, int cap_windows) {
         !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 8 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
     WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) 8 * V * sizeof(float)));
+    WB_CUDA_OK(cudaMallocHost(&hsamp, 8 * sizeof(SampOut)));
+    if (!dsamp.alloc(8) || !samp_mask.alloc((size_t) (V + 31) / 32, true)) return false;
     return true;
 }
 
 bool Engine::set_cells(int n) {
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
+    drop_graphs();
     n_cells = n;
     const size_t e = (size_t) hp.n_text_layer * n * hp.n_text_state;
     if (!kv_k.alloc(e, true) || !kv_v.alloc(e, true)) return false;
-    ld_idx = n;
-    const size_t nints = 5 * 8 + (size_t) 8 * ld_idx;
+    ld_idx = pad256(hp.n_text_ctx);          // a query attends to at most n_text_ctx positions
+    const size_t nints = 56 + (size_t) 8 * ld_idx;
     if (!dints.alloc(nints)) return false;
     if (hints) cudaFreeHost(hints);
     hints = nullptr;
@@ -66,7 +77,20 @@ bool Engine::set_cells(int n) {
 }
 
 // ---------------------------------------------------------------------------------------------------- audio front-end
-bool Engine::pcm_upload(const float * samples, int n_samples) {
+FrontEnd::~FrontEnd() {
+    if (m) cudaSetDevice(m->device);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+}
+bool FrontEnd::init(const Model * model) {
+    m = model;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    WB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    WB_CUDA_OK(cudaEventCreate(&ev0)); WB_CUDA_OK(cudaEventCreate(&ev1));
+    return gmax.alloc(4);
+}
+bool FrontEnd::pcm_upload(const float * samples, int n_samples) {
     WB_CUDA_OK(cudaSetDevice(m->device));
     if ((size_t) n_samples > pcm.n && !pcm.alloc(std::max(n_samples, 1))) return false;
     if (n_samples > 0) { WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st)); count_h2d((uint64_t) n_samples * 4); }
@@ -74,36 +98,32 @@ bool Engine::pcm_upload(const float * samples, int n_samples) {
     pcm_resident = n_samples;
     return true;
 }
-bool Engine::pcm_to_mel(const float * samples, int n_samples) {
+bool FrontEnd::pcm_to_mel(const float * samples, int n_samples, bool samples_on_device) {
     WB_CUDA_OK(cudaSetDevice(m->device));
     if (!samples && n_samples > 0 && pcm_resident != n_samples) { set_error("pcm_to_mel: no host samples and no resident PCM of %d samples", n_samples); return false; }
     n_mel = m->n_filt_mel;
     n_len = (n_samples + 480000) / 160;                       // whisper.cpp:3202-3218
     n_len_org = 1 + (n_samples + 200 - 400) / 160;            // whisper.cpp:3220
-    if (samples) pcm_resident = 0;
-    if ((size_t) std::max(n_samples, 1) > pcm.n && !pcm.alloc(std::max(n_samples, 1))) return false;
+    if (samples && !samples_on_device) pcm_resident = 0;
+    if (!samples_on_device && (size_t) std::max(n_samples, 1) > pcm.n && !pcm.alloc(std::max(n_samples, 1))) return false;
     if ((size_t) n_mel * n_len > mel.n && !mel.alloc((size_t) n_mel * n_len)) return false;
-    WB_CUDA_OK(cudaEventRecord(ev[0], st));
-    if (n_samples > 0 && samples) { WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st)); count_h2d((uint64_t) n_samples * 4); }
-    mel_spectrogram(pcm.p, n_samples, m->filters, n_mel, mel.p, n_len, gmax.p, st);
-    WB_CUDA_OK(cudaEventRecord(ev[1], st));
+    WB_CUDA_OK(cudaEventRecord(ev0, st));
+    const float * src = pcm.p;
+    if (samples_on_device && samples) src = samples;
+    else if (n_samples > 0 && samples) { WB_CUDA_OK(cudaMemcpyAsync(pcm.p, samples, (size_t) n_samples * 4, cudaMemcpyHostToDevice, st)); count_h2d((uint64_t) n_samples * 4); }
+    mel_spectrogram(src, n_samples, m->filters, n_mel, mel.p, n_len, gmax.p, st);
+    WB_CUDA_OK(cudaEventRecord(ev1, st));
     WB_CUDA_OK(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&last_ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&last_mel_ms, ev0, ev1);
     return true;
 }
-bool Engine::set_mel(const float * data, int n_len_, int n_mel_) {
+bool FrontEnd::set_mel(const float * data, int n_len_, int n_mel_) {
     WB_CUDA_OK(cudaSetDevice(m->device));
     n_len = n_len_; n_len_org = n_len_; n_mel = n_mel_;
     if ((size_t) std::max(1, n_mel * n_len) > mel.n && !mel.alloc((size_t) std::max(1, n_mel * n_len))) return false;
     if (data) WB_CUDA_OK(cudaMemcpyAsync(mel.p, data, (size_t) n_mel * n_len * 4, cudaMemcpyHostToDevice, st));
     else      WB_CUDA_OK(cudaMemsetAsync(mel.p, 0, (size_t) n_mel * n_len * 4, st));   // whisper-bench passes NULL, 0 (bench.cpp:69)
     WB_CUDA_OK(cudaStreamSynchronize(st));
-    return true;
-}
-bool Engine::read_mel(std::vector<float> & out) {
-    WB_CUDA_OK(cudaSetDevice(m->device));
-    out.resize((size_t) n_mel * n_len);
-    if (!out.empty()) WB_CUDA_OK(cudaMemcpy(out.data(), mel.p, out.size() * 4, cudaMemcpyDeviceToHost));
     return true;
 }
 
@@ -139,7 +159,7 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
     if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, 256)) return false;
     if (!make_tmap_f16(&tm_q, E.qk.p,     64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 256)) return false;
     if (!make_tmap_f16(&tm_k, E.qk.p + d, 64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 128)) return false;
-    if (!make_tmap_f16(&tm_p, E.P.p, Tp, T, H, n_win, Tp, (uint64_t) T * Tp, (uint64_t) H * T * Tp, 128)) return false;
+    if (!E.fused_attn && !make_tmap_f16(&tm_p, E.P.p, Tp, T, H, n_win, Tp, (uint64_t) T * Tp, (uint64_t) H * T * Tp, 128)) return false;
     if (!make_tmap_f16(&tm_vt, E.vt.p, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) d * Tp, 64)) return false;
     if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, 256)) return false;
 
@@ -182,7 +202,7 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
 
 #define WB_GEMM(desc) do { cudaError_t e_ = gemm_launch(desc, st); if (e_ != cudaSuccess) { set_error("%s:%d gemm_launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return false; } } while (0)
 
-bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
+bool Engine::encode(const EncSrc * srcs, int n_win, int n_ctx) {
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
     if (n_win < 1 || n_win > cap_win) { set_error("encode: n_win=%d exceeds the state's capacity %d", n_win, cap_win); return false; }
@@ -201,8 +221,13 @@ bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
     EncPlan & PL = *plan;
 
     WB_CUDA_OK(cudaEventRecord(ev[1], st));
-    for (int w = 0; w < n_win; ++w)
-        mel_window_f16(mel.p, n_len, n_mel, seeks[w], 2*T, mel_win.p + (size_t) w * win_rows * M, st);
+    bool identity_slots = true;
+    for (int w = 0; w < n_win; ++w) {
+        if (srcs[w].n_mel != M) { set_error("encode: mel has %d bands, model expects %d", srcs[w].n_mel, M); return false; }
+        if (srcs[w].slot < 0 || srcs[w].slot >= cap_win) { set_error("encode: bad slot %d", srcs[w].slot); return false; }
+        identity_slots &= (srcs[w].slot == w);
+        mel_window_f16(srcs[w].mel, srcs[w].n_len, M, srcs[w].seek, 2*T, mel_win.p + (size_t) w * win_rows * M, st);
+    }
     WB_GEMM(PL.conv1);
     if (debug_taps) WB_GEMM(PL.conv2_tap);
     WB_GEMM(PL.conv2);
@@ -212,9 +237,13 @@ bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
         layernorm(x.p, L.ln0.w, L.ln0.b, hp.eps, NT, d, xn.p, nullptr, st);
         WB_GEMM(lp.qk);
         WB_GEMM(lp.v);
-        WB_GEMM(lp.s);
-        softmax_rows_f16(S.p, P.p, (int64_t) n_win * H * T, Tp, st);
-        WB_GEMM(lp.pv);
+        if (fused_attn) {
+            if (!fattn_encoder(qk.p, 2*d, d, vt.p, T, Tp, H, n_win, 1.0f / sqrtf(64.0f), attn.p, d, st)) { set_error("fattn_encoder launch failed"); return false; }
+        } else {
+            WB_GEMM(lp.s);
+            softmax_rows_f16(S.p, P.p, (int64_t) n_win * H * T, Tp, st);
+            WB_GEMM(lp.pv);
+        }
         WB_GEMM(lp.o);
         layernorm(x.p, L.ln1.w, L.ln1.b, hp.eps, NT, d, xn.p, nullptr, st);
         WB_GEMM(lp.fc1);
@@ -222,7 +251,16 @@ bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
     }
     layernorm(x.p, m->e_ln.w, m->e_ln.b, hp.eps, NT, d, enc16.p, debug_taps ? enc32.p : nullptr, st);
     WB_CUDA_OK(cudaEventRecord(ev[3], st));
-    WB_GEMM(PL.cross);
+    if (identity_slots) {
+        WB_GEMM(PL.cross);
+    } else {                          // windows land in arbitrary cross-KV slots: one launch per window
+        for (int w = 0; w < n_win; ++w) {
+            GemmDesc g = PL.cross;
+            g.nb1 = 1; g.b1_in_off = w;
+            g.ep.out = kv_cross.p + (size_t) srcs[w].slot * 2 * hp.n_text_layer * Tp_max * d;
+            WB_GEMM(g);
+        }
+    }
     WB_CUDA_OK(cudaEventRecord(ev[4], st));
     WB_CUDA_OK(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&last_ms[1], ev[1], ev[2]);
@@ -233,65 +271,114 @@ bool Engine::encode(const int * seeks, int n_win, int n_ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------------- decoder
-bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * logits_out) {
-    const HParams & hp = m->hp;
+bool Engine::set_samp_mask(uint64_t key, const std::vector<uint32_t> & bits) {
+    if (key == samp_mask_key) return true;
     WB_CUDA_OK(cudaSetDevice(m->device));
+    if (bits.size() != samp_mask.n) { set_error("set_samp_mask: size mismatch"); return false; }
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    WB_CUDA_OK(cudaMemcpy(samp_mask.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    samp_mask_key = key;
+    return true;
+}
+
+bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampCfg * samp) {
+    const HParams & hp = m->hp;
     const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, V = hp.n_vocab;
     const int Tp = Tp_max;                                         // kv_cross layout stride
-    const int n_keys = pad256(enc_n_ctx > 0 ? enc_n_ctx : hp.n_audio_ctx);
     const float kq_scale = powf(64.0f, -0.25f);                    // whisper.cpp:2514
-    if (ld > ld_idx) { set_error("decode: idx row length %d exceeds pool %d", ld, ld_idx); return false; }
+    const size_t nint = 56 + (size_t) 8 * ld_idx;
+    WB_CUDA_OK(cudaMemcpyAsync(dints.p, hints, nint * sizeof(int), cudaMemcpyHostToDevice, st));
+    const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_row = dints.p + 40, * d_idx = dints.p + 56;
+
+    dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
+    for (int l = 0; l < Lt; ++l) {
+        const DecLayerW & L = m->dec[l];
+        __half * kc = kv_k.p + (size_t) l * n_cells * d;
+        __half * vc = kv_v.p + (size_t) l * n_cells * d;
+        { GemvArgs a; a.W = L.qkv; a.x = dx.p; a.n_tok = n; a.ln_w = L.ln0.w; a.ln_b = L.ln0.b; a.eps = hp.eps;      // whisper.cpp:2536-2599
+          a.bias = L.qkv_bias; a.scale = L.qkv_scale; a.out = dqkv.p; a.k_cache = kc; a.v_cache = vc; a.cells = d_cell; a.kv_d = d;
+          gemv(a, st); }
+        attn_self_decode(dqkv.p, 3*d, kc, vc, d_idx, ld_idx, d_nkv, n, H, d, dattn.p, d, st);                            // 2603-2625
+        { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }    // 2647-2659
+        { GemvArgs a; a.W = L.cq; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnc.w; a.ln_b = L.lnc.b; a.eps = hp.eps;        // 2661-2681
+          a.bias = L.cq_bias; a.out = dq2.p; gemv(a, st); }
+        attn_cross_decode(dq2.p, d, kv_cross.p + (size_t) l * Tp * d, kv_cross.p + (size_t) (Lt + l) * Tp * d, d_slot,
+                          (int64_t) 2 * Lt * Tp * d, n_keys, n, H, d, kq_scale, xpart.p, xcnt.p, dattn.p, d, st);       // 2688-2705
+        { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }  // 2754-2766
+        { GemvArgs a; a.W = L.fc1; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnm.w; a.ln_b = L.lnm.b; a.eps = hp.eps;       // 2770-2794
+          a.bias = L.fc1_bias; a.act = 1; a.out = dh.p; gemv(a, st); }
+        { GemvArgs a; a.W = L.fc2; a.x = dh.p; a.n_tok = n; a.bias = L.fc2_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }   // 2797-2806
+    }
+    if (any_logits) {
+        GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
+        gemv(a, st);
+        if (samp) {
+            SampCfg c = *samp; c.mask = samp_mask.p;
+            greedy_sample(dlogits.p, V, n, d_row, c, dsamp.p, st);
+            WB_CUDA_OK(cudaMemcpyAsync(hsamp, dsamp.p, (size_t) n * sizeof(SampOut), cudaMemcpyDeviceToHost, st));
+        } else {
+            WB_CUDA_OK(cudaMemcpyAsync(hlogits, dlogits.p, (size_t) n * V * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    return true;
+}
+
+bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
+                    const SampCfg * samp, const int * rowinfo, SampOut * samp_out) {
+    const HParams & hp = m->hp;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    const int V = hp.n_vocab;
+    const int n_keys = pad256(enc_n_ctx > 0 ? enc_n_ctx : hp.n_audio_ctx);
 
     for (int r0 = 0; r0 < n_rows; r0 += 8) {
         const int n = std::min(8, n_rows - r0);
-        int * h_tok = hints, * h_pos = hints + 8, * h_cell = hints + 16, * h_slot = hints + 24, * h_nkv = hints + 32, * h_idx = hints + 40;
-        bool any_logits = false; int max_kv = 0;
+        int * h_tok = hints, * h_pos = hints + 8, * h_cell = hints + 16, * h_slot = hints + 24, * h_nkv = hints + 32, * h_row = hints + 40, * h_idx = hints + 56;
+        bool any_logits = false;
         for (int j = 0; j < n; ++j) {
             const DecToken & t = rows[r0 + j];
             if (t.token < 0 || t.token >= V || t.pos < 0 || t.pos >= hp.n_text_ctx || t.slot < 0 || t.slot >= cap_win) {
                 set_error("decode: bad token/pos/slot (%d, %d, %d)", t.token, t.pos, t.slot); return false;
             }
+            if (n_kv[r0 + j] > ld_idx || n_kv[r0 + j] > ld) { set_error("decode: %d attended cells exceed the index row (%d)", n_kv[r0 + j], ld_idx); return false; }
             h_tok[j] = t.token; h_pos[j] = t.pos; h_cell[j] = cells[r0 + j]; h_slot[j] = t.slot; h_nkv[j] = n_kv[r0 + j];
-            max_kv = std::max(max_kv, n_kv[r0 + j]);
+            h_row[2*j] = (samp && rowinfo) ? rowinfo[2*(r0 + j)] : 0; h_row[2*j + 1] = (samp && rowinfo) ? rowinfo[2*(r0 + j) + 1] : 0;
             memcpy(h_idx + (size_t) j * ld_idx, kv_idx + (size_t) (r0 + j) * ld, (size_t) n_kv[r0 + j] * sizeof(int));
             any_logits |= t.want_logits;
         }
-        const size_t nint = 40 + (size_t) (n - 1) * ld_idx + max_kv;
-        WB_CUDA_OK(cudaMemcpyAsync(dints.p, hints, nint * sizeof(int), cudaMemcpyHostToDevice, st));
-        count_h2d(nint * sizeof(int));
-        const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_idx = dints.p + 40;
+        count_h2d((56 + (size_t) 8 * ld_idx) * sizeof(int));
+        if (any_logits) count_d2h(samp ? (uint64_t) n * sizeof(SampOut) : (uint64_t) n * V * 4);
 
-        dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
-        for (int l = 0; l < Lt; ++l) {
-            const DecLayerW & L = m->dec[l];
-            __half * kc = kv_k.p + (size_t) l * n_cells * d;
-            __half * vc = kv_v.p + (size_t) l * n_cells * d;
-            { GemvArgs a; a.W = L.qkv; a.x = dx.p; a.n_tok = n; a.ln_w = L.ln0.w; a.ln_b = L.ln0.b; a.eps = hp.eps;      // whisper.cpp:2536-2599
-              a.bias = L.qkv_bias; a.scale = L.qkv_scale; a.out = dqkv.p; a.k_cache = kc; a.v_cache = vc; a.cells = d_cell; a.kv_d = d;
-              gemv(a, st); }
-            attn_self_decode(dqkv.p, 3*d, kc, vc, d_idx, ld_idx, d_nkv, n, H, d, dattn.p, d, st);                            // 2603-2625
-            { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }    // 2647-2659
-            { GemvArgs a; a.W = L.cq; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnc.w; a.ln_b = L.lnc.b; a.eps = hp.eps;        // 2661-2681
-              a.bias = L.cq_bias; a.out = dq2.p; gemv(a, st); }
-            attn_cross_decode(dq2.p, d, kv_cross.p + (size_t) l * Tp * d, kv_cross.p + (size_t) (Lt + l) * Tp * d, d_slot,
-                              (int64_t) 2 * Lt * Tp * d, n_keys, n, H, d, kq_scale, xpart.p, xcnt.p, dattn.p, d, st);       // 2688-2705
-            { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }  // 2754-2766
-            { GemvArgs a; a.W = L.fc1; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnm.w; a.ln_b = L.lnm.b; a.eps = hp.eps;       // 2770-2794
-              a.bias = L.fc1_bias; a.act = 1; a.out = dh.p; gemv(a, st); }
-            { GemvArgs a; a.W = L.fc2; a.x = dh.p; a.n_tok = n; a.bias = L.fc2_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }   // 2797-2806
-        }
-        if (any_logits) {
-            GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
-            gemv(a, st);
-            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) {
-                WB_CUDA_OK(cudaMemcpyAsync(hlogits + (size_t) j * V, dlogits.p + (size_t) j * V, (size_t) V * 4, cudaMemcpyDeviceToHost, st));
-                count_d2h((uint64_t) V * 4);
-            }
+        // One pass = 8 kernels per text layer.  After the second use of a shape the chain is replayed as a CUDA graph
+        // (all per-step values live in `dints`, so kernel arguments never change between steps).
+        uint64_t key = (uint64_t) (n | (any_logits ? 16 : 0) | (samp ? 32 : 0)) | ((uint64_t) n_keys << 8);
+        if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
+        StepGraph * sg = (use_graphs && !prof_enabled()) ? &graphs[key] : nullptr;
+        if (sg && sg->exec) {
+            WB_CUDA_OK(cudaGraphLaunch(sg->exec, st));
+            count_launch(sg->launches);
+        } else if (sg && sg->seen >= 1) {
+            const uint64_t l0 = launch_count();
+            cudaGraph_t g = nullptr;
+            WB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const bool ok = decode_pass_enqueue(n, any_logits, n_keys, samp);
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (!ok || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); set_error("decode: graph capture failed: %s", cudaGetErrorString(ce)); return false; }
+            sg->launches = launch_count() - l0;
+            const cudaError_t ie = cudaGraphInstantiate(&sg->exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { sg->exec = nullptr; set_error("decode: cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return false; }
+            WB_CUDA_OK(cudaGraphLaunch(sg->exec, st));
+        } else {
+            if (sg) sg->seen++;
+            if (!decode_pass_enqueue(n, any_logits, n_keys, samp)) return false;
         }
         WB_CUDA_OK(cudaStreamSynchronize(st));
-        if (any_logits && logits_out)
-            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits)
-                memcpy(logits_out + (size_t) (r0 + j) * V, hlogits + (size_t) j * V, (size_t) V * 4);
+        if (any_logits && samp && samp_out) {
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) samp_out[r0 + j] = hsamp[j];
+        } else if (any_logits && logits_out) {
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits && logits_out[r0 + j])
+                memcpy(logits_out[r0 + j], hlogits + (size_t) j * V, (size_t) V * 4);
+        }
     }
     return true;
 }

@@ -6,9 +6,11 @@
 // batched pass, the cross-attention KV of each window ("slot"), the paged self-attention KV pool and the decode
 // workspaces.  All work of a state is enqueued on its own CUDA stream.
 #pragma once
+#include <map>
 #include <vector>
 #include "wb_model.h"
 #include "wb_gemm.cuh"
+#include "wb_kernels.cuh"
 
 namespace wb {
 
@@ -18,17 +20,32 @@ struct DecToken { // one row of a decode batch (whisper_batch, src/whisper.cpp:4
     int32_t token, pos, seq, slot; bool want_logits;
 };
 
+// Per-state audio front-end: PCM and log-mel live on the device; independent of the (possibly shared) Engine.
+struct FrontEnd {
+    const Model * m = nullptr;
+    cudaStream_t st = nullptr;
+    DevBuf<float> pcm, mel, gmax;
+    int n_len = 0, n_len_org = 0, n_mel = 0;
+    int pcm_resident = 0;            // samples already in `pcm` (wb200_pcm_upload); pcm_to_mel(nullptr, n) then skips the H2D copy
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_mel_ms = 0.0f;
+    ~FrontEnd();
+    bool init(const Model * model);
+    bool pcm_upload(const float * samples, int n_samples);
+    bool pcm_to_mel(const float * samples, int n_samples, bool samples_on_device = false);
+    bool set_mel(const float * data, int n_len, int n_mel);
+};
+
+// one 30-s window to encode: where its mel lives and which cross-KV slot it fills
+struct EncSrc { const float * mel; int n_len; int n_mel; int seek; int slot; };
+
 struct Engine {
     const Model * m = nullptr;
     cudaStream_t  st = nullptr;
     int cap_win = 1;                 // windows that can be encoded/decoded together
     int n_cells = 0;                 // self-KV pool size (cells); GGML_PAD(n_text_ctx,256) * factor (whisper.cpp:3402, 7167-7172)
     bool debug_taps = false;
-
-    // ---- audio front-end
-    DevBuf<float> pcm, mel, gmax;
-    int n_len = 0, n_len_org = 0, n_mel = 0;
-    int pcm_resident = 0;            // samples already in `pcm` (wb200_pcm_upload); pcm_to_mel(nullptr, n) then skips the H2D copy
+    bool fused_attn = true;          // WB200_UNFUSED_ATTN=1 selects the 3-kernel path (scores -> softmax -> PV through HBM)
 
     // ---- encoder workspaces
     int Tp_max = 0;
@@ -41,12 +58,21 @@ struct Engine {
     // ---- decoder
     DevBuf<__half> kv_k, kv_v;       // [Lt][n_cells][d]
     DevBuf<float>  dx, dqkv, dattn, dq2, dh, dlogits, xpart;
-    DevBuf<int>    dints, xcnt;      // packed per-step integers: tokens | pos | cells | slot | n_kv | idx[...]
+    DevBuf<int>    dints, xcnt;      // packed per-step integers: tokens | pos | cells | slot | n_kv | rowinfo[16] | idx[...]
+    DevBuf<uint32_t> samp_mask;      // static suppression bit mask of the on-device sampler
+    uint64_t samp_mask_key = 0;
+    DevBuf<SampOut> dsamp;           // [8]
+    SampOut * hsamp = nullptr;       // pinned [8]
     int * hints = nullptr;           // pinned mirror of dints
     float * hlogits = nullptr;       // pinned [8][n_vocab]
     int ld_idx = 0;
+    // CUDA graphs of one decode pass, keyed by (rows, logits?, n_keys); rebuilt when buffers move
+    struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; int seen = 0; };
+    std::map<uint64_t, StepGraph> graphs;
+    bool use_graphs = true;
+    void drop_graphs();
 
-    // device-event timers of the last encode (mel, conv, encoder, cross)
+    // device-event timers of the last encode: [1]=conv (incl. window staging) [2]=encoder [3]=cross  ([0] unused: mel is FrontEnd)
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     float last_ms[4] = { 0, 0, 0, 0 };
 
@@ -54,18 +80,16 @@ struct Engine {
     bool init(const Model * model, int cap_windows);
     bool set_cells(int n);           // (re)allocate the self-KV pool; contents are lost
 
-    // PCM (host) -> mel on device.  Returns false on CUDA error.
-    bool pcm_upload(const float * samples, int n_samples);
-    bool pcm_to_mel(const float * samples, int n_samples);
-    bool set_mel(const float * data, int n_len, int n_mel);
-    bool read_mel(std::vector<float> & out);
-
-    // encode `n_win` windows; window w starts at mel frame seeks[w] and fills cross-KV slot w.
-    bool encode(const int * seeks, int n_win, int n_ctx);
+    // encode `n_win` windows in one batched pass; window w reads srcs[w].mel at frame srcs[w].seek and fills cross-KV slot srcs[w].slot
+    bool encode(const EncSrc * srcs, int n_win, int n_ctx);
 
     // decode a batch (<= 8 rows per pass internally).  idx lists: for row j, cells[j] is where its K/V go and
-    // (kv_idx[j*ld .. +n_kv[j]]) the cells it attends to.  logits_out: host [n_rows][n_vocab], rows with want_logits filled.
-    bool decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * logits_out);
+    // (kv_idx[j*ld .. +n_kv[j]]) the cells it attends to.  logits_out[j]: host buffer of n_vocab floats for rows with want_logits.
+    bool decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampCfg * samp);   // the kernel chain of one pass (<= 8 rows) on `st`
+    // samp != nullptr: logits stay on the device; the filter + greedy pick run there (rowinfo: 2 ints per row, samp_out: host [n_rows])
+    bool decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
+                const SampCfg * samp = nullptr, const int * rowinfo = nullptr, SampOut * samp_out = nullptr);
+    bool set_samp_mask(uint64_t key, const std::vector<uint32_t> & bits);
 };
 
 } // namespace wb

@@ -185,6 +185,51 @@ std::string to_timestamp(int64_t t, bool comma = false) {
     return buf;
 }
 
+// static part of the logits filter as a bit mask for the on-device sampler (same ids process_logits suppresses)
+void build_static_mask(const whisper_context & ctx, const whisper_full_params & params, std::vector<uint32_t> & bits, uint64_t & key) {
+    const Vocab & vocab = ctx.vocab;
+    const int n = vocab.n_vocab;
+    bits.assign((size_t) (n + 31) / 32, 0u);
+    auto sup = [&](int id) { if (id >= 0 && id < n) bits[id >> 5] |= 1u << (id & 31); };
+    sup(vocab.token_not); sup(vocab.token_sot); sup(vocab.token_nosp);
+    if (!params.tdrz_enable) sup(vocab.token_solm);
+    sup(vocab.token_translate); sup(vocab.token_transcribe); sup(vocab.token_prev);
+    for (int i = 0; i < 100; ++i) sup(vocab.token_sot + 1 + i);
+    if (params.suppress_regex) {
+        std::regex re(params.suppress_regex);
+        for (const auto & kv : vocab.token_to_id) if (std::regex_match(kv.first, re)) sup(kv.second);
+    }
+    if (params.suppress_nst) {
+        for (const char * t : k_non_speech) {
+            auto it = vocab.token_to_id.find(t); if (it != vocab.token_to_id.end()) sup(it->second);
+            it = vocab.token_to_id.find(std::string(" ") + t); if (it != vocab.token_to_id.end()) sup(it->second);
+        }
+        auto it = vocab.token_to_id.find(" -"); if (it != vocab.token_to_id.end()) sup(it->second);
+        it = vocab.token_to_id.find(" '");      if (it != vocab.token_to_id.end()) sup(it->second);
+    }
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t w : bits) { h ^= w; h *= 1099511628211ull; }
+    key = h | 1ull;
+}
+
+whisper_token_data from_samp(const SampOut & o) {
+    whisper_token_data t = blank_token();
+    t.id = o.id; t.tid = o.tid; t.p = o.p; t.plog = o.plog; t.pt = o.pt; t.ptsum = o.ptsum;
+    return t;
+}
+
+// state of the logits filter for the NEXT token of a decoder (whisper.cpp:6205, 6252, 6319-6320, 6350-6351)
+void samp_rowinfo(const Vocab & vocab, const whisper_full_params & params, const Decoder & d, int * out2) {
+    const auto & cur = d.sequence.tokens;
+    int f = 0;
+    if (cur.empty()) f |= 1;
+    if (!cur.empty() && cur.back().id >= vocab.token_beg) f |= 2;
+    if (cur.size() < 2 || cur[cur.size() - 2].id >= vocab.token_beg) f |= 4;
+    if (d.has_ts) f |= 8;
+    if (!params.no_timestamps && !params.single_segment && params.max_tokens > 0 && (int) cur.size() >= params.max_tokens) f |= 16;
+    out2[0] = f; out2[1] = d.seek_delta / 2;
+}
+
 template <typename F> void run_parallel(int n_threads, F && fn) {
     if (n_threads <= 1) { fn(); return; }
     std::vector<std::thread> th(n_threads - 1);
@@ -323,6 +368,20 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
     int seek = seek_start;
     std::vector<whisper_token> prompt; prompt.reserve(n_text_ctx);
 
+    // on-device logits filter + greedy pick (decode results come back as 32 bytes per sequence instead of n_vocab floats);
+    // used whenever the step is a pure argmax: greedy strategy at temperature 0 without a user logits callback
+    const bool dev_samp_ok = params.strategy == WHISPER_SAMPLING_GREEDY && !params.logits_filter_callback && getenv("WB200_HOST_SAMPLER") == nullptr;
+    std::vector<uint32_t> mask_bits; SampReq sreq; std::vector<int> rowinfo;
+    if (dev_samp_ok) {
+        build_static_mask(*ctx, params, mask_bits, sreq.mask_key);
+        sreq.mask_bits = &mask_bits;
+        sreq.cfg.token_eot = vocab.token_eot; sreq.cfg.token_beg = vocab.token_beg; sreq.cfg.token_nosp = vocab.token_nosp;
+        { auto it = vocab.token_to_id.find(" "); sreq.cfg.space_id = it == vocab.token_to_id.end() ? -1 : it->second; }
+        sreq.cfg.suppress_blank = params.suppress_blank ? 1 : 0;
+        sreq.cfg.no_timestamps = params.no_timestamps ? 1 : 0;
+        sreq.cfg.max_initial_tid = params.max_initial_ts > 0.0f ? (int) std::round(params.max_initial_ts / (float(WB_CHUNK_SIZE) / ctx->model.hp.n_audio_ctx)) : -1;
+    }
+
     struct BeamCand { int decoder_idx; int seek_delta; bool has_ts; Sequence sequence; };
     std::vector<std::vector<BeamCand>> bc_per_dec(n_decoders);
     std::vector<BeamCand> cands;
@@ -375,7 +434,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 if (state->kv_self_n_dec < n_cur) {
                     const int factor = n_cur > 1 ? n_cur + 2 : 1;
                     const int cells = ((n_text_ctx + 255) / 256 * 256) * factor;
-                    if (!state->eng.set_cells(cells)) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
+                    if (state->group || !state->eng->set_cells(cells)) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
                     state->kv.reset((uint32_t) cells);
                     state->kv_self_n_dec = n_cur;
                 }
@@ -385,9 +444,17 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 b_tok.assign(prompt.begin(), prompt.end()); b_pos.resize(np); b_seq.assign(np, 0); b_want.assign(np, 0);
                 for (int i = 0; i < np; ++i) b_pos[i] = i;
                 b_want[np - 1] = 1;
-                if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), np)) { logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -8; }
+                const bool dev_samp = dev_samp_ok && t_cur < 1e-6f;
+                for (int j = 0; j < n_cur; ++j) state->decoders[j].have_pending = false;
+                if (dev_samp) { rowinfo.assign((size_t) 2 * np, 0); samp_rowinfo(vocab, params, state->decoders[0], &rowinfo[2 * (np - 1)]); sreq.rowinfo = rowinfo.data(); }
+                if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), np, dev_samp ? &sreq : nullptr)) { logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -8; }
                 if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -8;
 
+                if (!state->samp_out.empty()) {      // the device already filtered and picked
+                    state->no_speech_prob = state->samp_out[np - 1].nosp_raw;
+                    state->decoders[0].pending = from_samp(state->samp_out[np - 1]);
+                    state->decoders[0].have_pending = true;
+                } else
                 { // no_speech probability from the unfiltered logits of the last prompt token (whisper.cpp:7190-7200)
                     const int n = vocab.n_vocab;
                     std::vector<float> raw(state->logits.begin() + (size_t) (np - 1) * n, state->logits.begin() + (size_t) np * n);
@@ -395,7 +462,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                     compute_logprobs(raw, n, lp); compute_probs(raw, n, lp, pr);
                     state->no_speech_prob = pr[vocab.token_nosp];
                 }
-                {
+                if (state->samp_out.empty()) {
                     const int64_t ts = time_us();
                     state->decoders[0].i_batch = np - 1;
                     process_logits(*ctx, *state, state->decoders[0], params, t_cur);
@@ -421,7 +488,8 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                             Decoder & d = state->decoders[j];
                             if (d.completed || d.failed) continue;
                             if (params.strategy == WHISPER_SAMPLING_GREEDY) {
-                                d.sequence.tokens.push_back(sample_token(*ctx, d, t_cur < 1e-6f));
+                                if (d.have_pending) { d.sequence.tokens.push_back(d.pending); d.have_pending = false; }
+                                else d.sequence.tokens.push_back(sample_token(*ctx, d, t_cur < 1e-6f));
                                 d.sequence.sum_logprobs_all += d.sequence.tokens.back().plog;
                             } else {
                                 const auto toks = sample_token_topk(*ctx, d, params.beam_search.beam_size);
@@ -503,8 +571,22 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         d.i_batch = (int) b_tok.size();
                         b_tok.push_back(d.sequence.tokens.back().id); b_pos.push_back(n_past); b_seq.push_back(j); b_want.push_back(1);
                     }
-                    if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), (int) b_tok.size())) {
+                    const bool dev_samp = dev_samp_ok && t_cur < 1e-6f;
+                    if (dev_samp) {
+                        rowinfo.assign(2 * b_tok.size(), 0);
+                        for (int j = 0; j < n_cur; ++j) { const Decoder & d = state->decoders[j]; if (!(d.failed || d.completed)) samp_rowinfo(vocab, params, d, &rowinfo[2 * d.i_batch]); }
+                        sreq.rowinfo = rowinfo.data();
+                    }
+                    if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), (int) b_tok.size(), dev_samp ? &sreq : nullptr)) {
                         logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -9;
+                    }
+                    if (!state->samp_out.empty()) {
+                        for (int j = 0; j < n_cur; ++j) {
+                            Decoder & d = state->decoders[j];
+                            if (d.failed || d.completed) continue;
+                            d.pending = from_samp(state->samp_out[d.i_batch]); d.have_pending = true;
+                        }
+                        continue;
                     }
                     if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -9;
                     const int64_t ts1 = time_us();
@@ -657,28 +739,70 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
     return ret;
 }
 
-// Independent PCM buffers on one device: n_streams states work concurrently (each on its own CUDA stream); chunk i's
-// segments are left in states_out[i] (caller frees with whisper_free_state).  Chunk semantics = whisper_full_with_state.
-WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
-                               const int * n_samples, int n_chunks, struct whisper_state ** states_out) {
+// Independent PCM buffers on one device, decoded in LOCK-STEP: up to 8 member states share one engine (one batched encoder
+// pass for all windows, one batched decode step for all live sequences -- weights are read once per step).  Chunk i's
+// segments are returned in states_out[i] (result-only states; free with whisper_free_state).  Chunk semantics are those
+// of whisper_full_with_state.  flags bit 0: `samples[i]` are DEVICE pointers (PCM already resident in HBM).
+WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
+                                  const int * n_samples, int n_chunks, struct whisper_state ** states_out, int flags) {
     if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
-    int n_streams = 4;
-    if (const char * e = getenv("WB200_BATCH_STREAMS")) n_streams = std::max(1, atoi(e));
-    n_streams = std::min(n_streams, n_chunks);
-    for (int i = 0; i < n_chunks; ++i) { states_out[i] = whisper_init_state(ctx); if (!states_out[i]) return -7; }
+    int S = 8;
+    if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(8, atoi(e)));
+    S = std::min(S, n_chunks);
+    std::lock_guard<std::mutex> batch_lock(ctx->batch_mu);
+    const int member_decoders = 5;                                    // enough for best_of / beam_size up to 5
+    const int cells_per_member = ((ctx->model.hp.n_text_ctx + 255) / 256 * 256) * (member_decoders + 2);
+    if (!ctx->batch_group || ctx->batch_group->n_members != S) {
+        ctx->batch_group.reset(new Group());
+        Group & G = *ctx->batch_group;
+        G.n_members = S; G.cells_per_member = cells_per_member;
+        if (!G.eng.init(&ctx->model, S) || !G.eng.set_cells(S * cells_per_member)) { ctx->batch_group.reset(); return -7; }
+        for (int i = 0; i < S; ++i) {
+            whisper_state * st = new whisper_state();
+            G.members.push_back(st);
+            if (!st->fe.init(&ctx->model)) { ctx->batch_group.reset(); return -7; }
+            st->eng = &G.eng; st->group = &G; st->slot = i; st->cell_off = i * cells_per_member;
+            st->kv.reset((uint32_t) cells_per_member);
+            st->kv_self_n_dec = member_decoders;
+        }
+    }
+    Group & G = *ctx->batch_group;
+    G.n_active = S;
+    G.pending.clear();
     std::atomic<int> next(0); std::atomic<int> rc(0);
     whisper_full_params pc = params;
     pc.print_progress = false; pc.print_realtime = false;
-    auto work = [&]() {
-        for (;;) {
-            const int i = next.fetch_add(1);
-            if (i >= n_chunks) break;
-            const int r = whisper_full_with_state(ctx, states_out[i], pc, samples[i], n_samples[i]);
-            if (r != 0) rc.store(r);
-        }
-    };
-    run_parallel(n_streams, work);
+    std::vector<std::thread> th;
+    for (int mi = 0; mi < S; ++mi) {
+        th.emplace_back([&, mi]() {
+            whisper_state * st = G.members[mi];
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n_chunks) break;
+                st->decoders[0].rng = std::mt19937(0);
+                st->t_sample_us = st->t_encode_us = st->t_decode_us = st->t_batchd_us = st->t_prompt_us = st->t_mel_us = 0;
+                st->n_sample = st->n_encode = st->n_decode = st->n_batchd = st->n_prompt = st->n_fail_p = st->n_fail_h = 0;
+                wb::tls_pcm_is_device() = (flags & 1) != 0;
+                const int r = whisper_full_with_state(ctx, st, pc, samples[i], n_samples[i]);
+                wb::tls_pcm_is_device() = false;
+                if (r != 0) rc.store(r);
+                whisper_state * out = new whisper_state();          // result-only
+                out->result_all = std::move(st->result_all); st->result_all.clear();
+                out->lang_id = st->lang_id;
+                out->t_sample_us = st->t_sample_us; out->t_encode_us = st->t_encode_us; out->t_decode_us = st->t_decode_us;
+                out->t_batchd_us = st->t_batchd_us; out->t_prompt_us = st->t_prompt_us; out->t_mel_us = st->t_mel_us;
+                out->n_sample = st->n_sample; out->n_encode = st->n_encode; out->n_decode = st->n_decode; out->n_batchd = st->n_batchd; out->n_prompt = st->n_prompt;
+                states_out[i] = out;
+            }
+            G.leave();
+        });
+    }
+    for (auto & t : th) t.join();
     return rc.load();
+}
+WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
+                               const int * n_samples, int n_chunks, struct whisper_state ** states_out) {
+    return wb200_full_batch_ex(ctx, params, samples, n_samples, n_chunks, states_out, 0);
 }
 
 } // extern "C"

@@ -27,7 +27,7 @@ template <int BN> struct GemmCfg {
 
 struct GemmKParams {
     int M, N, K, taps, nkb_per_tap, nb0;
-    int a_zsel0, a_zsel1, b_zsel0, b_zsel1, a_rows_per_b0;
+    int a_zsel0, a_zsel1, b_zsel0, b_zsel1, a_rows_per_b0, b1_in_off;
     // quantised A
     const void * a_base; const uint8_t * a_qs; const uint32_t * a_qh; const __half * a_d;
     GemmEpilogue ep;
@@ -114,7 +114,7 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 const uint32_t tx = Cfg::B_TILE_BYTES + (QUANT ? 0 : A_TILE_BYTES);
                 mbar_arrive_expect_tx(&full_bar[s], tx);
-                const int sel[4] = { 0, b0, b1, tap };
+                const int sel[4] = { 0, b0, b1 + p.b1_in_off, tap };
                 tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, sel[p.b_zsel0], sel[p.b_zsel1]);
                 if (!QUANT)
                     tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, mg0, sel[p.a_zsel0], sel[p.a_zsel1]);
@@ -352,7 +352,7 @@ cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
     GemmKParams kp;
     kp.M = g.M; kp.N = g.N; kp.K = g.K; kp.taps = g.taps; kp.nkb_per_tap = (g.K + 63) / 64; kp.nb0 = g.nb0;
     kp.a_zsel0 = g.a_zsel[0]; kp.a_zsel1 = g.a_zsel[1]; kp.b_zsel0 = g.b_zsel[0]; kp.b_zsel1 = g.b_zsel[1];
-    kp.a_rows_per_b0 = g.a_rows_per_b0;
+    kp.a_rows_per_b0 = g.a_rows_per_b0; kp.b1_in_off = g.b1_in_off;
     kp.a_base = g.A.base; kp.a_qs = g.A.qs; kp.a_qh = g.A.qh; kp.a_d = g.A.d;
     kp.ep = g.ep;
     switch (g.A.type) {

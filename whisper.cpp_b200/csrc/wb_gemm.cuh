@@ -40,6 +40,7 @@ struct GemmDesc {
     // what feeds TMA coordinates z2 / z3 of each operand: 0 = zero, 1 = b0, 2 = b1, 3 = tap
     int a_zsel[2] = { 0, 0 };
     int b_zsel[2] = { 1, 2 };
+    int b1_in_off = 0;                // added to b1 when it is used as a TMA coordinate (one window of a batched buffer per launch)
     int a_rows_per_b0 = 0;            // A row offset = b0 * a_rows_per_b0 (stacked weights: one launch, many matrices)
     QMat A;                           // weight side; type WT_F16 => tmA used
     CUtensorMap tmA;                  // valid when A.type == WT_F16

@@ -145,7 +145,8 @@ k_mel_frames(const float * __restrict__ pcm, int N, const float * __restrict__ f
     __shared__ float x[400];
     __shared__ float P[204];
     __shared__ float red[32];
-    const int i   = blockIdx.x;
+    __shared__ float tc[400], ts[400];                          // twiddles in shared memory: the DFT indexes them divergently,
+    const int i   = blockIdx.x;                                  // which a __constant__ array would serialise 32-way
     const int tid = threadIdx.x;
     const int n_eff  = N + 200;                               // samples handed to the worker: n_samples + stage_2_pad
     const int n_comp = min(n_eff / 160 + 1, n_len);           // frames that are really transformed (whisper.cpp:3125)
@@ -154,6 +155,7 @@ k_mel_frames(const float * __restrict__ pcm, int N, const float * __restrict__ f
         if (tid == 0) atomicMax(gmax_key, float_order_key(-10.0f));
         return;
     }
+    for (int j = tid; j < 400; j += blockDim.x) { tc[j] = c_mel_tab[400 + j]; ts[j] = c_mel_tab[800 + j]; }
     const int offset   = i * 160;
     const int n_reflect = min(200, max(0, N - 1));
     const int lim = min(400, n_eff - offset);
@@ -173,8 +175,8 @@ k_mel_frames(const float * __restrict__ pcm, int N, const float * __restrict__ f
         int idx = 0;
         for (int n = 0; n < 400; ++n) {
             const float v = x[n];
-            re += v * c_mel_tab[400 + idx];
-            im -= v * c_mel_tab[800 + idx];
+            re += v * tc[idx];
+            im -= v * ts[idx];
             idx += tid; if (idx >= 400) idx -= 400;
         }
         P[tid] = re * re + im * im;
@@ -362,7 +364,7 @@ struct GemvK {
 template <int WT> struct GemvSmem;
 
 // shared-memory carve-up (dynamic): per token  xq int8[K] | xd float[K/32] (block32) / xd float[K/256] + bs int[K/32] (K-quant)
-// or half[K] for F16.  scratch float[K] for the LayerNorm/quantise prologue (shared by all tokens).
+// or half[K] for F16.
 template <int WT>
 __device__ __forceinline__ size_t gemv_tok_bytes(int K) {
     if (WT == WT_F16) return (size_t) K * 2;
@@ -376,79 +378,93 @@ k_gemv(const GemvK a) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int K = a.W.K, N = a.W.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float * scratch = reinterpret_cast<float *>(sm);                     // [K]
-    __shared__ float red[32];
-    uint8_t * tokbase = sm + (size_t) K * 4;
+    uint8_t * tokbase = sm;
     const size_t tb = (gemv_tok_bytes<WT>(K) + 15) & ~size_t(15);
 
     // ---------------------------------------------------------------- prologue: (LN) + activation quantisation
-    for (int t = 0; t < a.n_tok; ++t) {
-        const float * xr = a.x + (int64_t) t * K;
-        if (a.ln_w) {
+    // LayerNorm statistics: one warp per token (two passes, like the reference); quantisation: the (token, block) pairs are
+    // spread over all 256 threads, each thread owning one 32-value block (no shuffles on the critical path).
+    __shared__ float s_mean[8], s_rstd[8];
+    if (a.ln_w) {
+        for (int t = warp; t < a.n_tok; t += 8) {
+            const float * xr = a.x + (int64_t) t * K;
             float s = 0.0f;
-            for (int i = tid; i < K; i += 256) s += xr[i];
-            const float mean = block_sum(s, red) / K;
+            for (int i = lane; i < K; i += 32) s += xr[i];
+            const float mean = warp_sum(s) / K;
             float v = 0.0f;
-            for (int i = tid; i < K; i += 256) { const float d0 = xr[i] - mean; v += d0 * d0; }
-            const float rstd = 1.0f / sqrtf(block_sum(v, red) / K + a.eps);
-            for (int i = tid; i < K; i += 256)
-                scratch[i] = __fadd_rn(__fmul_rn(__fmul_rn(xr[i] - mean, rstd), a.ln_w[i]), a.ln_b[i]);
-        } else {
-            for (int i = tid; i < K; i += 256) scratch[i] = xr[i];
-        }
-        __syncthreads();
-        uint8_t * tp = tokbase + t * tb;
-        if (WT == WT_F16) {
-            __half * xh = reinterpret_cast<__half *>(tp);
-            for (int i = tid; i < K; i += 256) xh[i] = __float2half_rn(scratch[i]);
-        } else if (WT == WT_Q4_K || WT == WT_Q5_K) {
-            // quantize_row_q8_K (ggml-quants.c:2768-2805): per 256: iscale = -127/max (signed max-magnitude), q = min(127, nearest(iscale*x)), d = 1/iscale
-            int8_t * xq = reinterpret_cast<int8_t *>(tp);
-            float * xd = reinterpret_cast<float *>(tp + K);
-            int *   bs = reinterpret_cast<int *>(tp + K + (K / 256) * 4);
-            for (int sb = warp; sb < K / 256; sb += 8) {
-                float v[8]; float amax = 0.0f, mx = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { v[j] = scratch[sb * 256 + j * 32 + lane]; const float av = fabsf(v[j]); if (av > amax) { amax = av; mx = v[j]; } }
-                // warp arg-max of |v| (first occurrence in element order wins in the reference; ties are measure-zero)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float oa = __shfl_xor_sync(0xffffffffu, amax, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
-                    if (oa > amax) { amax = oa; mx = om; }
-                }
-                if (amax == 0.0f) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) xq[sb * 256 + j * 32 + lane] = 0;
-                    if (lane == 0) xd[sb] = 0.0f;
-                    if (lane < 8) bs[sb * 8 + lane] = 0;
-                    continue;
-                }
-                const float iscale = -127.0f / mx;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    int q = __float2int_rn(iscale * v[j]); q = min(127, q);
-                    xq[sb * 256 + j * 32 + lane] = (int8_t) q;
-                    int ssum = q;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                    if (lane == 0) bs[sb * 8 + j] = ssum;
-                }
-                if (lane == 0) xd[sb] = 1.0f / iscale;
-            }
-        } else {
-            int8_t * xq = reinterpret_cast<int8_t *>(tp);
-            float * xd = reinterpret_cast<float *>(tp + K);
-            for (int b = warp; b < K / 32; b += 8) {
-                const float v = scratch[b * 32 + lane];
-                const float amax = warp_max(fabsf(v));
-                const float d  = amax / 127.0f;
-                const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
-                xq[b * 32 + lane] = (int8_t) __float2int_rn(v * id);
-                if (lane == 0) xd[b] = __half2float(__float2half_rn(d));
-            }
+            for (int i = lane; i < K; i += 32) { const float d0 = xr[i] - mean; v += d0 * d0; }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) / K + a.eps);
+            if (lane == 0) { s_mean[t] = mean; s_rstd[t] = rstd; }
         }
         __syncthreads();
     }
+    auto xval = [&](int t, int i) -> float {      // the (normalised) activation the contraction consumes
+        const float v = a.x[(int64_t) t * K + i];
+        return a.ln_w ? __fadd_rn(__fmul_rn(__fmul_rn(v - s_mean[t], s_rstd[t]), a.ln_w[i]), a.ln_b[i]) : v;
+    };
+    if (WT == WT_F16) {
+        for (int i = tid; i < a.n_tok * K; i += 256) {
+            const int t = i / K, e = i - t * K;
+            reinterpret_cast<__half *>(tokbase + t * tb)[e] = __float2half_rn(xval(t, e));
+        }
+    } else if (WT == WT_Q4_K || WT == WT_Q5_K) {
+        // quantize_row_q8_K (ggml-quants.c:2768-2805): per 256: iscale = -127/max (signed max-magnitude), q = min(127, nearest(iscale*x)), d = 1/iscale
+        const int nsb = K / 256;
+        for (int pidx = warp; pidx < a.n_tok * nsb; pidx += 8) {
+            const int t = pidx / nsb, sb = pidx - t * nsb;
+            uint8_t * tp = tokbase + t * tb;
+            int8_t * xq = reinterpret_cast<int8_t *>(tp);
+            float * xd = reinterpret_cast<float *>(tp + K);
+            int *   bs = reinterpret_cast<int *>(tp + K + nsb * 4);
+            float v[8]; float amax = 0.0f, mx = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = xval(t, sb * 256 + j * 32 + lane); const float av = fabsf(v[j]); if (av > amax) { amax = av; mx = v[j]; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oa = __shfl_xor_sync(0xffffffffu, amax, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
+                if (oa > amax) { amax = oa; mx = om; }
+            }
+            if (amax == 0.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xq[sb * 256 + j * 32 + lane] = 0;
+                if (lane == 0) xd[sb] = 0.0f;
+                if (lane < 8) bs[sb * 8 + lane] = 0;
+                continue;
+            }
+            const float iscale = -127.0f / mx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int q = __float2int_rn(iscale * v[j]); q = min(127, q);
+                xq[sb * 256 + j * 32 + lane] = (int8_t) q;
+                int ssum = q;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                if (lane == 0) bs[sb * 8 + j] = ssum;
+            }
+            if (lane == 0) xd[sb] = 1.0f / iscale;
+        }
+    } else {
+        const int nb = K / 32;
+        for (int pidx = tid; pidx < a.n_tok * nb; pidx += 256) {
+            const int t = pidx / nb, b = pidx - t * nb;
+            uint8_t * tp = tokbase + t * tb;
+            float v[32]; float amax = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = xval(t, b * 32 + i); amax = fmaxf(amax, fabsf(v[i])); }
+            const float d  = amax / 127.0f;
+            const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q0 = __float2int_rn(v[4*i] * id), q1 = __float2int_rn(v[4*i+1] * id), q2 = __float2int_rn(v[4*i+2] * id), q3 = __float2int_rn(v[4*i+3] * id);
+                pk[i] = (uint32_t) (q0 & 0xFF) | ((uint32_t) (q1 & 0xFF) << 8) | ((uint32_t) (q2 & 0xFF) << 16) | ((uint32_t) (q3 & 0xFF) << 24);
+            }
+            uint4 * dst = reinterpret_cast<uint4 *>(tp + b * 32);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            reinterpret_cast<float *>(tp + K)[b] = __half2float(__float2half_rn(d));
+        }
+    }
+    __syncthreads();
 
     // ---------------------------------------------------------------- rows: one warp per output row
     const int nwarps_total = gridDim.x * 8;
@@ -573,7 +589,7 @@ static void gemv_launch(const GemvK & k, cudaStream_t st) {
     else if (WT == WT_Q4_K || WT == WT_Q5_K) tokb = (size_t) K + (size_t) (K / 256) * 4 + (size_t) (K / 32) * 4;
     else tokb = (size_t) K + (size_t) (K / 32) * 4;
     tokb = (tokb + 15) & ~size_t(15);
-    const size_t smem = (size_t) K * 4 + tokb * k.n_tok;
+    const size_t smem = tokb * k.n_tok;
     auto kern = k_gemv<WT, NT>;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); smem_set = smem; }
@@ -724,6 +740,105 @@ void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half
     ProfScope prof(PC_ATTN, st, (double) n_tok * 2.0 * n_keys * d * 2, 4.0 * n_tok * n_keys * d);
     k_attn_cross<<<dim3(n_head, XSPLIT, n_tok), 128, 0, st>>>(q, ldq, kc, vc, slot, slot_stride, n_keys, d, scale, partial, counters, out, ldo);
     count_launch();
+}
+
+// =====================================================================================================================
+//  logits filter + greedy pick on the device.  Same rules, same order, same float formulas as whisper_process_logits /
+//  whisper_sample_token(best=true) (src/whisper.cpp:6196-6543); only the order of the f32 summations differs, so p/plog can
+//  move in the last bits while the chosen ids follow the reference's tie rule (strict >, lowest index).
+// =====================================================================================================================
+struct SampK { const uint32_t * mask; int eot, beg, nosp, space, suppress_blank, no_ts, max_init; };
+
+__device__ __forceinline__ bool samp_masked(const SampK & c, const uint32_t * smask, int i, int flags, int tid0) {
+    if (smask[i >> 5] & (1u << (i & 31))) return true;
+    const bool is_initial = flags & 1, last_ts = flags & 2, penult_ts = flags & 4, has_ts = flags & 8, text_off = flags & 16;
+    if (is_initial && c.suppress_blank && (i == c.eot || i == c.space)) return true;
+    if (c.no_ts && i >= c.beg) return true;
+    if (text_off && i < c.eot) return true;
+    if (last_ts) { if (penult_ts) { if (i >= c.beg) return true; } else if (i < c.eot) return true; }
+    if (is_initial && c.max_init >= 0 && i > c.beg + c.max_init) return true;
+    if (has_ts && i >= c.beg && i < c.beg + tid0) return true;
+    return false;
+}
+struct PI { float p; int i; };
+__device__ __forceinline__ PI pi_best(PI a, PI b) { return (b.p > a.p || (b.p == a.p && b.i < a.i)) ? b : a; }
+__device__ __forceinline__ PI block_best(PI v, PI * scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { PI t; t.p = __shfl_xor_sync(0xffffffffu, v.p, o); t.i = __shfl_xor_sync(0xffffffffu, v.i, o); v = pi_best(v, t); }
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    PI r = (lane < nw) ? scratch[lane] : PI{ -1.0f, 0x7fffffff };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { PI t; t.p = __shfl_xor_sync(0xffffffffu, r.p, o); t.i = __shfl_xor_sync(0xffffffffu, r.i, o); r = pi_best(r, t); }
+    return r;
+}
+
+__global__ void __launch_bounds__(1024)
+k_greedy_sample(const float * __restrict__ logits, int V, const int * __restrict__ rowinfo, const SampK c, SampOut * __restrict__ out) {
+    extern __shared__ uint32_t smask[];
+    __shared__ float red[32];
+    __shared__ PI redpi[32];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float * l = logits + (int64_t) row * V;
+    const int flags = rowinfo[2 * row], tid0 = rowinfo[2 * row + 1];
+    for (int i = tid; i < (V + 31) / 32; i += blockDim.x) smask[i] = c.mask[i];
+    __syncthreads();
+    // pass 1: maxima (raw for no_speech_prob; masked overall / text / timestamps)
+    float raw_max = -INFINITY, m_max = -INFINITY, ts_max = -INFINITY, text_max = -INFINITY;
+    for (int i = tid; i < V; i += blockDim.x) {
+        const float v = l[i];
+        raw_max = fmaxf(raw_max, v);
+        if (!samp_masked(c, smask, i, flags, tid0)) { m_max = fmaxf(m_max, v); if (i >= c.beg) ts_max = fmaxf(ts_max, v); else text_max = fmaxf(text_max, v); }
+    }
+    raw_max = block_max(raw_max, red); m_max = block_max(m_max, red); ts_max = block_max(ts_max, red); text_max = block_max(text_max, red);
+    // pass 2: sums
+    float raw_sum = 0.0f, m_sum = 0.0f, ts_sum = 0.0f;
+    for (int i = tid; i < V; i += blockDim.x) {
+        const float v = l[i];
+        raw_sum += expf(v - raw_max);
+        if (!samp_masked(c, smask, i, flags, tid0)) { m_sum += expf(v - m_max); if (i >= c.beg) ts_sum += expf(v - ts_max); }
+    }
+    raw_sum = block_sum(raw_sum, red); m_sum = block_sum(m_sum, red); ts_sum = block_sum(ts_sum, red);
+    const float lse = ::logf(m_sum) + m_max;
+    // "timestamp mass beats every text token" rule (whisper.cpp:6361-6388); evaluated on log-probabilities like the reference
+    bool text_off = false;
+    if (ts_sum > 0.0f) {
+        const float ts_lp = ::logf(ts_sum) + (ts_max - lse);
+        text_off = ts_lp > (text_max - lse);
+    }
+    // pass 3: probabilities, greedy pick, timestamp statistics
+    PI best = { 0.0f, 0x7fffffff }, best_ts = { 0.0f, 0x7fffffff };
+    double sum_ts = 0.0;
+    for (int i = tid; i < V; i += blockDim.x) {
+        if (samp_masked(c, smask, i, flags, tid0) || (text_off && i < c.beg)) continue;
+        const float pr = expf(l[i] - lse);
+        if (pr > best.p) best = { pr, i };
+        if (i >= c.beg) { sum_ts += pr; if (pr > best_ts.p) best_ts = { pr, i }; }
+    }
+    best = block_best(best, redpi);
+    best_ts = block_best(best_ts, redpi);
+    const float sts = block_sum((float) sum_ts, red);
+    if (tid == 0) {
+        SampOut o;
+        o.id = best.p > 0.0f ? best.i : 0;                       // result.id starts at 0 and only moves on a strictly larger prob
+        o.p = best.p > 0.0f ? best.p : 0.0f;
+        o.plog = best.p > 0.0f ? l[o.id] - lse : 0.0f;
+        o.tid = best_ts.p > 0.0f ? best_ts.i : 0;
+        o.pt = (float) ((double) (best_ts.p > 0.0f ? best_ts.p : 0.0f) / ((double) sts + 1e-10));
+        o.ptsum = sts;
+        if (o.id >= c.beg) { o.tid = o.id; o.pt = o.p; }
+        o.nosp_raw = expf(l[c.nosp] - (::logf(raw_sum) + raw_max));
+        o.pad = 0;
+        out[row] = o;
+    }
+}
+void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st) {
+    SampK c; c.mask = cfg.mask; c.eot = cfg.token_eot; c.beg = cfg.token_beg; c.nosp = cfg.token_nosp; c.space = cfg.space_id;
+    c.suppress_blank = cfg.suppress_blank; c.no_ts = cfg.no_timestamps; c.max_init = cfg.max_initial_tid;
+    const size_t smem = (size_t) ((V + 31) / 32) * 4;
+    k_greedy_sample<<<n, 1024, smem, st>>>(logits, V, rowinfo, c, out); count_launch();
 }
 
 } // namespace wb

@@ -31,6 +31,11 @@ void layernorm(const float * x, const float * w, const float * b, float eps, int
 // ---- unfused attention helper: softmax over rows of f32 scores -> f16 probabilities --------------------------------
 void softmax_rows_f16(const float * s, __half * p, int64_t rows, int cols, cudaStream_t st);
 
+// ---- fused encoder self-attention (wb_fattn.cu).  qk: f16 [n_win][T][ld_qk], head h at columns h*64, K at +k_off;
+// vt: f16 [n_win][H*64][Tp] (V transposed, zero beyond T); out: f16 [n_win*T][ldo]
+bool fattn_encoder(const __half * qk, int ld_qk, int k_off, const __half * vt, int T, int Tp, int H, int n_win, float scale,
+                   __half * out, int ldo, cudaStream_t st);
+
 // ---- decoder step (src/whisper.cpp:2466-2844) -----------------------------------------------------------------------
 // x[t][:] = dequant(d_te[token[t]]) + d_pe[pos[t]]   (get_rows + add, whisper.cpp:2523-2526)
 void dec_embed(const QMat & te, const float * pe, const int * tokens, const int * pos, int n_tok, int d, float * x, cudaStream_t st);
@@ -61,5 +66,18 @@ void attn_self_decode(const float * q, int ldq, const __half * kc, const __half 
 void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * slot, int64_t slot_stride,
                        int n_keys, int n_tok, int n_head, int d, float scale, float * partial, int * counters,
                        float * out, int ldo, cudaStream_t st);
+
+
+// ---- on-device logits filter + greedy pick (whisper_process_logits + whisper_sample_token(best), src/whisper.cpp:6196-6543)
+struct SampCfg {                 // uniform for all rows of a pass
+    const uint32_t * mask = nullptr;   // device bit mask [ceil(V/32)]: statically suppressed token ids
+    int token_eot = 0, token_beg = 0, token_nosp = 0, space_id = -1;
+    int suppress_blank = 1, no_timestamps = 0;
+    int max_initial_tid = -1;          // round(max_initial_ts / precision), -1 = rule disabled
+};
+struct SampOut { int id, tid; float p, plog, pt, ptsum, nosp_raw; int pad; };
+// rowinfo[2*r] flags: bit0 is_initial, bit1 last token was a timestamp, bit2 penultimate was (or < 2 tokens), bit3 has_ts,
+// bit4 text tokens disabled by max_tokens; rowinfo[2*r+1] = seek_delta/2.  logits: [n][V] f32 on device (not modified).
+void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st);
 
 } // namespace wb

@@ -2,7 +2,10 @@
 // Mirrors the roles (not the code) of whisper_context / whisper_state / whisper_decoder / whisper_kv_cache in
 // src/whisper.cpp:692-717, 783-820, 834-952.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
+#include <memory>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -40,7 +43,11 @@ struct Decoder {
     std::vector<float> probs, logits, logprobs;
     std::vector<std::pair<double, int>> logits_id;
     std::mt19937 rng;
+    bool have_pending = false;                 // next token already chosen by the on-device sampler
+    whisper_token_data pending;
 };
+
+struct Group;
 
 struct Segment {
     int64_t t0 = 0, t1 = 0;
@@ -56,11 +63,16 @@ struct whisper_state {
     int64_t t_sample_us = 0, t_encode_us = 0, t_decode_us = 0, t_batchd_us = 0, t_prompt_us = 0, t_mel_us = 0;
     int32_t n_sample = 0, n_encode = 0, n_decode = 0, n_batchd = 0, n_prompt = 0, n_fail_p = 0, n_fail_h = 0;
 
-    wb::Engine  eng;
+    wb::FrontEnd fe;                           // PCM + mel of this state
+    wb::Engine * eng = nullptr;                // own engine, or the engine shared by the members of a batch group
+    std::unique_ptr<wb::Engine> own_eng;
+    wb::Group * group = nullptr;               // non-null: encode/decode requests rendezvous with the other members
+    int cell_off = 0;                          // first self-KV cell of this state inside eng's pool
     wb::KvCells kv;
     int kv_self_n_dec = 1;
     wb::Decoder decoders[wb::MAX_DECODERS];
     std::vector<float> logits;                 // [n_tokens][n_vocab] of the last decode (rows flagged want_logits are valid)
+    std::vector<wb::SampOut> samp_out;         // per row of the last decode when the on-device sampler was used
     std::vector<wb::Segment> result_all;
     std::vector<whisper_token> prompt_past0, prompt_past1;
     int   lang_id = 0;
@@ -76,12 +88,44 @@ struct whisper_context {
     wb::Vocab vocab;
     whisper_state * state = nullptr;
     std::string path_model;
+    std::unique_ptr<wb::Group> batch_group;    // cached by wb200_full_batch
+    std::mutex batch_mu;
+    ~whisper_context();
 };
 
 namespace wb {
+
+// Lock-step batching of concurrently running states (wb200_full_batch): every member thread runs the ordinary
+// whisper_full_with_state control flow; its encode / decode requests block in submit() until all ACTIVE members have one
+// pending, then one thread executes them as a single batched device pass (weights are read once for all sequences).
+// request for the on-device logits filter + greedy pick of the rows of one decode call
+struct SampReq { SampCfg cfg; uint64_t mask_key = 0; const std::vector<uint32_t> * mask_bits = nullptr; const int * rowinfo = nullptr; };
+
+struct Group {
+    Engine eng;
+    int n_members = 0, cells_per_member = 0;
+    std::vector<whisper_state *> members;
+    std::mutex mu;
+    std::condition_variable cv;
+    int n_active = 0;
+    struct Req {
+        int kind = 0;                           // 0 = encode, 1 = decode
+        whisper_context * ctx = nullptr; whisper_state * st = nullptr;
+        int seek = 0, n_ctx = 0;                // encode
+        const int * tokens = nullptr, * pos = nullptr, * seq = nullptr; const int8_t * want = nullptr; int n = 0;   // decode
+        const SampReq * samp = nullptr;
+        bool done = false, ok = false; int64_t dt_us = 0;
+    };
+    std::vector<Req *> pending;
+    bool submit(Req & r);
+    void leave();
+    void run(std::vector<Req *> & batch);       // executes outside the lock
+};
+
 int64_t time_us();
+bool & tls_pcm_is_device();   // set by the batch driver: the next whisper_pcm_to_mel* `samples` pointer is a device pointer
 // decode one batch through the engine with the reference's KV bookkeeping (whisper_decode_internal, whisper.cpp:2856-2986)
 bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens, const int * pos, const int * seq,
-                  const int8_t * want, int n_tokens);
+                  const int8_t * want, int n_tokens, const SampReq * samp = nullptr);
 bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset);
 }
