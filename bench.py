@@ -121,6 +121,14 @@ def count_tokens(L, state):
     return n
 
 
+def ref_threads():
+    """threads for the reference CPU arm: all host cores up to 32 (whisper.cpp's ggml thread pool stops scaling -- and its
+    per-node barriers start to dominate the 1-token decode graphs -- well before that); WB200_REF_THREADS overrides"""
+    if os.environ.get("WB200_REF_THREADS"):
+        return int(os.environ["WB200_REF_THREADS"])
+    return min(os.cpu_count() or 1, 32)
+
+
 def run_reference(args, rank, world):
     """reference arm: unmodified whisper.cpp CPU path (oracle/_ref) on 1 chunk per step, all host threads"""
     if rank != 0:
@@ -133,7 +141,7 @@ def run_reference(args, rank, world):
     cp = R.whisper_context_default_params(); cp.use_gpu = False
     ctx = R.whisper_init_from_file_with_params(model.encode(), cp)
     assert ctx
-    cores = os.cpu_count() or 1
+    cores = ref_threads()
     pcm = make_inputs(0, 1)[0]
     p = full_params(R, cores)
     times = []
@@ -287,24 +295,15 @@ def main():
         out["roofline"] = roof
         out["kernel_classes"] = classes
         if not args.no_cpu_baseline:
+            # the unmodified reference on ONE chunk of the same workload, in a child process so that it can be bounded in time
             try:
-                ref_path = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
-                R = pkg.bind_whisper_api(C.CDLL(ref_path))
-                silence(R)
-                cp = R.whisper_context_default_params(); cp.use_gpu = False
-                rctx = R.whisper_init_from_file_with_params(model.encode(), cp)
-                cores = os.cpu_count() or 1
-                rp = full_params(R, cores)
-                t0 = time.perf_counter()
-                assert R.whisper_full(rctx, rp, pcms[0].ctypes.data_as(vp), len(pcms[0])) == 0
-                dt = time.perf_counter() - t0
-                tm = R.whisper_get_timings(rctx)
-                out["cpu_baseline"] = {"value": CHUNK_SECONDS / dt, "unit": "x real time", "cores": cores, "kind": "reference",
-                                       "sample": "1 x 30 s chunk of the same workload, unmodified whisper.cpp CPU (AVX2 build), n_threads=%d" % cores,
-                                       "encode_ms": float(tm.contents[1]), "decode_ms_per_token": float(tm.contents[2])}
-                R.whisper_free(rctx)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                                   capture_output=True, text=True, timeout=420)
+                j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                out["cpu_baseline"] = dict(j["cpu_baseline"], encode_ms=j.get("encode_ms"))
             except Exception as e:  # noqa: BLE001
-                out["cpu_baseline"] = {"error": str(e)}
+                out["cpu_baseline"] = {"value": None, "unit": "x real time", "cores": ref_threads(), "kind": "reference",
+                                       "sample": "1 x 30 s chunk (did not finish: %s)" % type(e).__name__}
         print(json.dumps(out), flush=True)
     eng.close()
     if world > 1:

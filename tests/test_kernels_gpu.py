@@ -60,9 +60,10 @@ def test_layernorm(lib):
         assert np.array_equal(o16.view(np.float16), o32.astype(np.float16))
 
 
+@pytest.mark.parametrize("v2", [0, 4])
 @pytest.mark.parametrize("wtype", [Q4_0, Q5_0, Q8_0, F16])
-@pytest.mark.parametrize("N,K,n_tok", [(384, 384, 1), (1280, 1280, 1), (1000, 5120, 3), (51864, 384, 1), (640, 1280, 8)])
-def test_gemv_integer_dot_matches_reference_arithmetic(lib, ref, wtype, N, K, n_tok):
+@pytest.mark.parametrize("N,K,n_tok", [(384, 384, 1), (1280, 1280, 1), (1000, 5120, 3), (51864, 384, 1), (640, 1280, 8), (1290, 1280, 5)])
+def test_gemv_integer_dot_matches_reference_arithmetic(lib, ref, wtype, N, K, n_tok, v2):
     """same integer arithmetic as the CPU mul_mat (Q8_0 activations, int dot, f32 block sums): only the f32
     summation order differs -> rel tol 2e-5 of the output scale."""
     rng = np.random.default_rng(N + K + n_tok + wtype)
@@ -74,7 +75,7 @@ def test_gemv_integer_dot_matches_reference_arithmetic(lib, ref, wtype, N, K, n_
     raw = ref_quantize(ref, wtype, w)
     out = np.empty((n_tok, N), np.float32)
     rawb = np.frombuffer(raw, dtype=np.uint8)
-    rc = lib.wb200_dbg_gemv(wtype, N, K, n_tok, _ptr(rawb), _ptr(x), _ptr(bias), _ptr(scale), _ptr(res), None, None, _ptr(out), 0)
+    rc = lib.wb200_dbg_gemv(wtype, N, K, n_tok, _ptr(rawb), _ptr(x), _ptr(bias), _ptr(scale), _ptr(res), None, None, _ptr(out), v2)
     assert rc == 0, lib.wb200_last_error()
     y = rn.mul_mat_f16(raw, N, K, x) if wtype == F16 else rn.mul_mat_q(wtype, raw, N, K, x)
     want = (y + bias[None, :]) * scale[None, :] + res
@@ -82,8 +83,9 @@ def test_gemv_integer_dot_matches_reference_arithmetic(lib, ref, wtype, N, K, n_
     assert np.abs(out - want).max() < tol, np.abs(out - want).max()
 
 
+@pytest.mark.parametrize("v2", [0, 4])
 @pytest.mark.parametrize("wtype", [Q4_K, Q5_K])
-def test_gemv_kquants_within_activation_quantisation_noise(lib, ref, wtype):
+def test_gemv_kquants_within_activation_quantisation_noise(lib, ref, wtype, v2):
     """K-quant GEMV uses Q8_K activations like the reference (ggml-quants.c:2768-2805); checked against exact math
     with the reference's own int8 noise budget (1e-2 of the output scale)."""
     rng = np.random.default_rng(5)
@@ -94,13 +96,14 @@ def test_gemv_kquants_within_activation_quantisation_noise(lib, ref, wtype):
     wd = rn.dequantize(wtype, raw, N, K).astype(np.float64)
     out = np.empty((n_tok, N), np.float32)
     rawb = np.frombuffer(raw, dtype=np.uint8)
-    rc = lib.wb200_dbg_gemv(wtype, N, K, n_tok, _ptr(rawb), _ptr(x), None, None, None, None, None, _ptr(out), 0)
+    rc = lib.wb200_dbg_gemv(wtype, N, K, n_tok, _ptr(rawb), _ptr(x), None, None, None, None, None, _ptr(out), v2)
     assert rc == 0, lib.wb200_last_error()
     want = x.astype(np.float64) @ wd.T
     assert np.abs(out - want).max() < 1e-2 * np.abs(want).max()
 
 
-def test_gemv_fused_layernorm_and_gelu(lib, ref):
+@pytest.mark.parametrize("v2", [0, 4])
+def test_gemv_fused_layernorm_and_gelu(lib, ref, v2):
     rng = np.random.default_rng(11)
     N, K, n_tok = 1536, 384, 2
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
@@ -110,7 +113,7 @@ def test_gemv_fused_layernorm_and_gelu(lib, ref):
     raw = ref_quantize(ref, Q5_0, w)
     out = np.empty((n_tok, N), np.float32)
     rawb = np.frombuffer(raw, dtype=np.uint8)
-    rc = lib.wb200_dbg_gemv(Q5_0, N, K, n_tok, _ptr(rawb), _ptr(x), _ptr(bias), None, None, _ptr(lw), _ptr(lb), _ptr(out), 3)
+    rc = lib.wb200_dbg_gemv(Q5_0, N, K, n_tok, _ptr(rawb), _ptr(x), _ptr(bias), None, None, _ptr(lw), _ptr(lb), _ptr(out), 3 | v2)
     assert rc == 0, lib.wb200_last_error()
     xn = rn.layernorm(x, lw, lb)
     want = rn.gelu(rn.mul_mat_q(Q5_0, raw, N, K, xn) + bias[None, :])

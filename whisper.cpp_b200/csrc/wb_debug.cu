@@ -81,7 +81,7 @@ int wb200_dbg_layernorm(const float * x, const float * w, const float * b, float
     return 0;
 }
 
-// y[t][n] via the decode GEMV; weights in FILE layout.  flags bit0 gelu, bit1 fused LayerNorm (ln_w, ln_b given)
+// y[t][n] via the decode GEMV; weights in FILE layout.  flags bit0 gelu, bit1 fused LayerNorm (ln_w, ln_b given), bit2 = v2 (mma) kernel
 __attribute__((visibility("default")))
 int wb200_dbg_gemv(int wtype, int N, int K, int n_tok, const void * w_file, const float * x, const float * bias,
                    const float * scale, const float * res, const float * ln_w, const float * ln_b, float * out, int flags) {
@@ -100,7 +100,9 @@ int wb200_dbg_gemv(int wtype, int N, int K, int n_tok, const void * w_file, cons
     if (res)   { dres.alloc((size_t) n_tok * N); cudaMemcpy(dres.p, res, (size_t) n_tok * N * 4, cudaMemcpyHostToDevice); a.res = dres.p; }
     if (flags & 2) { dlw.alloc(K); dlb.alloc(K); cudaMemcpy(dlw.p, ln_w, (size_t) K * 4, cudaMemcpyHostToDevice); cudaMemcpy(dlb.p, ln_b, (size_t) K * 4, cudaMemcpyHostToDevice); a.ln_w = dlw.p; a.ln_b = dlb.p; }
     a.x = dx.p; a.n_tok = n_tok; a.act = (flags & 1) ? 1 : 0; a.out = dout.p;
-    gemv(a, st);
+    DevBuf<uint8_t> scratch;
+    if (flags & 4) { if (!scratch.alloc(8 * act_tok_stride(a.W.type, K))) return -1; gemv2(a, scratch.p, st); }
+    else gemv(a, st);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("gemv: %s", cudaGetErrorString(e)); return -7; }
     cudaMemcpy(out, dout.p, (size_t) n_tok * N * 4, cudaMemcpyDeviceToHost);
@@ -131,7 +133,7 @@ int wb200_dbg_attn_cross(const float * q, const uint16_t * kc, const uint16_t * 
     const int d = n_head * 64;
     DevBuf<float> dq, dout, dpart; DevBuf<__half> dk, dv; DevBuf<int> dslot, dcnt;
     dq.alloc((size_t) n_tok * d); dout.alloc((size_t) n_tok * d); dk.alloc((size_t) n_tok * n_keys * d); dv.alloc((size_t) n_tok * n_keys * d);
-    dpart.alloc((size_t) n_tok * n_head * 8 * 66); dslot.alloc(n_tok); dcnt.alloc((size_t) n_tok * n_head, true);
+    dpart.alloc((size_t) n_tok * n_head * 32 * 66); dslot.alloc(n_tok); dcnt.alloc((size_t) n_tok * n_head, true);
     std::vector<int> slots(n_tok); for (int i = 0; i < n_tok; ++i) slots[i] = i;
     cudaMemcpy(dslot.p, slots.data(), (size_t) n_tok * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dq.p, q, (size_t) n_tok * d * 4, cudaMemcpyHostToDevice);

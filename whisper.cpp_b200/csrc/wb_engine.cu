@@ -46,13 +46,15 @@ bool Engine::init(const Model * model, int cap_windows) {
     debug_taps = getenv("WB200_DEBUG_TAPS") != nullptr;
     use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
     fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
+    gemv_v2 = getenv("WB200_GEMV_V1") == nullptr;
     if (!mel_win.alloc(B * (2*T + 2) * M, true) || !h1.alloc(B * (2*T + 2) * d, true) || !x.alloc(B * T * d) || !xn.alloc(B * T * d) ||
         !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || (!fused_attn && (!S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp))) ||
         !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d) || !kv_cross.alloc(B * 2 * Lt * Tp * d, true)) return false;
     if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
     // decoder workspaces (8 rows per pass)
     if (!dx.alloc(8 * d) || !dqkv.alloc(8 * 3 * d) || !dattn.alloc(8 * d) || !dq2.alloc(8 * d) || !dh.alloc(8 * 4 * d) ||
-        !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 8 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
+        !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 32 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
+    if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
     WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) 8 * V * sizeof(float)));
     WB_CUDA_OK(cudaMallocHost(&hsamp, 8 * sizeof(SampOut)));
@@ -297,21 +299,21 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         __half * vc = kv_v.p + (size_t) l * n_cells * d;
         { GemvArgs a; a.W = L.qkv; a.x = dx.p; a.n_tok = n; a.ln_w = L.ln0.w; a.ln_b = L.ln0.b; a.eps = hp.eps;      // whisper.cpp:2536-2599
           a.bias = L.qkv_bias; a.scale = L.qkv_scale; a.out = dqkv.p; a.k_cache = kc; a.v_cache = vc; a.cells = d_cell; a.kv_d = d;
-          gemv(a, st); }
+          { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }
         attn_self_decode(dqkv.p, 3*d, kc, vc, d_idx, ld_idx, d_nkv, n, H, d, dattn.p, d, st);                            // 2603-2625
-        { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }    // 2647-2659
+        { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }    // 2647-2659
         { GemvArgs a; a.W = L.cq; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnc.w; a.ln_b = L.lnc.b; a.eps = hp.eps;        // 2661-2681
-          a.bias = L.cq_bias; a.out = dq2.p; gemv(a, st); }
+          a.bias = L.cq_bias; a.out = dq2.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }
         attn_cross_decode(dq2.p, d, kv_cross.p + (size_t) l * Tp * d, kv_cross.p + (size_t) (Lt + l) * Tp * d, d_slot,
                           (int64_t) 2 * Lt * Tp * d, n_keys, n, H, d, kq_scale, xpart.p, xcnt.p, dattn.p, d, st);       // 2688-2705
-        { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }  // 2754-2766
+        { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }  // 2754-2766
         { GemvArgs a; a.W = L.fc1; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnm.w; a.ln_b = L.lnm.b; a.eps = hp.eps;       // 2770-2794
-          a.bias = L.fc1_bias; a.act = 1; a.out = dh.p; gemv(a, st); }
-        { GemvArgs a; a.W = L.fc2; a.x = dh.p; a.n_tok = n; a.bias = L.fc2_bias; a.res = dx.p; a.out = dx.p; gemv(a, st); }   // 2797-2806
+          a.bias = L.fc1_bias; a.act = 1; a.out = dh.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }
+        { GemvArgs a; a.W = L.fc2; a.x = dh.p; a.n_tok = n; a.bias = L.fc2_bias; a.res = dx.p; a.out = dx.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }   // 2797-2806
     }
     if (any_logits) {
         GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
-        gemv(a, st);
+        { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); }
         if (samp) {
             SampCfg c = *samp; c.mask = samp_mask.p;
             greedy_sample(dlogits.p, V, n, d_row, c, dsamp.p, st);

@@ -58,6 +58,8 @@ struct Engine {
     // ---- decoder
     DevBuf<__half> kv_k, kv_v;       // [Lt][n_cells][d]
     DevBuf<float>  dx, dqkv, dattn, dq2, dh, dlogits, xpart;
+    DevBuf<uint8_t> act_scratch;      // quantised activations of the current GEMV (k_act_quant -> k_gemv_mma)
+    bool gemv_v2 = true;             // WB200_GEMV_V1=1 selects the dp4a kernel
     DevBuf<int>    dints, xcnt;      // packed per-step integers: tokens | pos | cells | slot | n_kv | rowinfo[16] | idx[...]
     DevBuf<uint32_t> samp_mask;      // static suppression bit mask of the on-device sampler
     uint64_t samp_mask_key = 0;

@@ -623,6 +623,281 @@ void gemv(const GemvArgs & a, cudaStream_t st) {
 }
 
 // =====================================================================================================================
+//  GEMV v2 for the decode step: activation quantisation is a separate tiny kernel (k_act_quant, one CTA per token) and the
+//  contraction uses the integer tensor-core instruction mma.sync.m16n8k32.s8 so that up to 8 sequences share one pass
+//  over the weights:   D[16 rows][8 tokens] (i32) = W_q[16][32] . X_q8[32][8]   -- exactly one 32-value quant block --
+//  followed by acc += D * d_w[row] * d_x[token] in f32: the same integer-dot + block-scale arithmetic as the reference's
+//  vec_dot_q*_q8_0 (ggml-cpu/quants.c:365-406) and the dp4a kernel above; only the f32 summation order differs.
+//  One CTA = 32 output rows (two m16 tiles); its 8 warps split K and reduce through shared memory.
+// =====================================================================================================================
+template <int MODE>   // 0: Q8_0 blocks  1: Q8_K super-blocks  2: f16
+__global__ void __launch_bounds__(256)
+k_act_quant(const float * __restrict__ x, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, float eps,
+            uint8_t * __restrict__ out, size_t tok_stride) {
+    __shared__ float red[32];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float * xr = x + (int64_t) t * K;
+    uint8_t * tp = out + (size_t) t * tok_stride;
+    float mean = 0.0f, rstd = 1.0f;
+    if (ln_w) {
+        float s = 0.0f;
+        for (int i = tid; i < K; i += 256) s += xr[i];
+        mean = block_sum(s, red) / K;
+        float v = 0.0f;
+        for (int i = tid; i < K; i += 256) { const float d0 = xr[i] - mean; v += d0 * d0; }
+        rstd = 1.0f / sqrtf(block_sum(v, red) / K + eps);
+    }
+    auto xval = [&](int i) -> float {
+        const float v = xr[i];
+        return ln_w ? __fadd_rn(__fmul_rn(__fmul_rn(v - mean, rstd), ln_w[i]), ln_b[i]) : v;
+    };
+    if (MODE == 2) {
+        for (int i = tid; i < K; i += 256) reinterpret_cast<__half *>(tp)[i] = __float2half_rn(xval(i));
+    } else if (MODE == 1) {
+        const int nsb = K / 256;
+        int8_t * xq = reinterpret_cast<int8_t *>(tp);
+        float * xd = reinterpret_cast<float *>(tp + K);
+        int *   bs = reinterpret_cast<int *>(tp + K + nsb * 4);
+        for (int sb = warp; sb < nsb; sb += 8) {               // quantize_row_q8_K (ggml-quants.c:2768-2805)
+            float v[8]; float amax = 0.0f, mx = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = xval(sb * 256 + j * 32 + lane); const float av = fabsf(v[j]); if (av > amax) { amax = av; mx = v[j]; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oa = __shfl_xor_sync(0xffffffffu, amax, o), om = __shfl_xor_sync(0xffffffffu, mx, o);
+                if (oa > amax) { amax = oa; mx = om; }
+            }
+            if (amax == 0.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xq[sb * 256 + j * 32 + lane] = 0;
+                if (lane == 0) xd[sb] = 0.0f;
+                if (lane < 8) bs[sb * 8 + lane] = 0;
+                continue;
+            }
+            const float iscale = -127.0f / mx;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int q = __float2int_rn(iscale * v[j]); q = min(127, q);
+                xq[sb * 256 + j * 32 + lane] = (int8_t) q;
+                int ssum = q;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                if (lane == 0) bs[sb * 8 + j] = ssum;
+            }
+            if (lane == 0) xd[sb] = 1.0f / iscale;
+        }
+    } else {
+        for (int b = tid; b < K / 32; b += 256) {              // quantize_row_q8_0, AVX2 form (ggml-cpu/arch/x86/quants.c)
+            float v[32]; float amax = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = xval(b * 32 + i); amax = fmaxf(amax, fabsf(v[i])); }
+            const float d  = amax / 127.0f;
+            const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q0 = __float2int_rn(v[4*i] * id), q1 = __float2int_rn(v[4*i+1] * id), q2 = __float2int_rn(v[4*i+2] * id), q3 = __float2int_rn(v[4*i+3] * id);
+                pk[i] = (uint32_t) (q0 & 0xFF) | ((uint32_t) (q1 & 0xFF) << 8) | ((uint32_t) (q2 & 0xFF) << 16) | ((uint32_t) (q3 & 0xFF) << 24);
+            }
+            uint4 * dst = reinterpret_cast<uint4 *>(tp + b * 32);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            reinterpret_cast<float *>(tp + K)[b] = __half2float(__float2half_rn(d));
+        }
+    }
+}
+
+__device__ __forceinline__ void mma_s8_16832(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct Gemv2K {
+    QMat W; const uint8_t * act; size_t tok_stride; int n_tok;
+    const float * bias, * scale; int act_fn; const float * res; float * out;
+    __half * k_cache, * v_cache; const int * cells; int kv_d;
+};
+
+template <int WT>
+__global__ void __launch_bounds__(256)
+k_gemv_mma(const Gemv2K a) {
+    __shared__ float red[8][32][9];
+    const int K = a.W.K, N = a.W.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, c = lane & 3;
+    const int n0 = blockIdx.x * 32;
+    float acc[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+    // rows this lane feeds into the A fragments: (m-tile, +0 / +8); clamped for the ragged last CTA (masked at the store)
+    int rows[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rows[i] = min(N - 1, n0 + (i >> 1) * 16 + g + (i & 1) * 8);
+    const bool tok_ok = g < a.n_tok;
+    const uint8_t * actg = a.act + (size_t) (tok_ok ? g : 0) * a.tok_stride;           // token of the B fragment (column g)
+    const uint8_t * act0 = a.act + (size_t) min(2 * c,     a.n_tok - 1) * a.tok_stride; // tokens of the D fragment columns
+    const uint8_t * act1 = a.act + (size_t) min(2 * c + 1, a.n_tok - 1) * a.tok_stride;
+
+    if (WT == WT_F16) {
+        const __half * Wb = reinterpret_cast<const __half *>(a.W.base);
+        const uint32_t * xg = reinterpret_cast<const uint32_t *>(actg);
+        for (int ks = warp; ks < K / 16; ks += 8) {
+            const uint32_t b0 = tok_ok ? xg[ks * 8 + c] : 0u, b1 = tok_ok ? xg[ks * 8 + 4 + c] : 0u;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t * r0 = reinterpret_cast<const uint32_t *>(Wb + (int64_t) rows[2*mt] * K) + ks * 8;
+                const uint32_t * r1 = reinterpret_cast<const uint32_t *>(Wb + (int64_t) rows[2*mt + 1] * K) + ks * 8;
+                const uint32_t af[4] = { __ldg(r0 + c), __ldg(r1 + c), __ldg(r0 + 4 + c), __ldg(r1 + 4 + c) };
+                mma_f16_16816(acc[mt], af, b0, b1);
+            }
+        }
+    } else if (WT == WT_Q4_K || WT == WT_Q5_K) {
+        constexpr int BLK = (WT == WT_Q4_K) ? 144 : 176;
+        const int nsb = K / 256;
+        const uint32_t * xg = reinterpret_cast<const uint32_t *>(actg);
+        const float * d80 = reinterpret_cast<const float *>(act0 + K), * d81 = reinterpret_cast<const float *>(act1 + K);
+        const int * bs0 = reinterpret_cast<const int *>(act0 + K + nsb * 4), * bs1 = reinterpret_cast<const int *>(act1 + K + nsb * 4);
+        // work item = (super-block, nibble pair jj): 4 per super-block
+        for (int it = warp; it < nsb * 4; it += 8) {
+            const int sb = it >> 2, jj = it & 3;
+            uint32_t bx[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * jj + h;
+                bx[h][0] = tok_ok ? xg[(sb * 256 + j * 32) / 4 + c] : 0u;
+                bx[h][1] = tok_ok ? xg[(sb * 256 + j * 32) / 4 + 4 + c] : 0u;
+            }
+            const float x80 = d80[sb], x81 = d81[sb];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t wlo[2], whi[2], hlo[2] = { 0, 0 }, hhi[2] = { 0, 0 }; float dl[2][2], ml[2][2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint8_t * blk = reinterpret_cast<const uint8_t *>(a.W.base) + ((int64_t) rows[2*mt + r] * nsb + sb) * BLK;
+                    const uint32_t * q32 = reinterpret_cast<const uint32_t *>(blk + 16 + (WT == WT_Q5_K ? 32 : 0) + 32 * jj);
+                    wlo[r] = __ldg(q32 + c); whi[r] = __ldg(q32 + 4 + c);
+                    if (WT == WT_Q5_K) { const uint32_t * h32 = reinterpret_cast<const uint32_t *>(blk + 16); hlo[r] = __ldg(h32 + c); hhi[r] = __ldg(h32 + 4 + c); }
+                    const __half2 dm = *reinterpret_cast<const __half2 *>(blk);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { int sc, mn; kq_scale_min(2 * jj + h, blk + 4, sc, mn); dl[r][h] = __low2float(dm) * (float) sc; ml[r][h] = __high2float(dm) * (float) mn; }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * jj + h;
+                    uint32_t af[4];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        uint32_t lo = (wlo[r] >> (4 * h)) & 0x0F0F0F0Fu, hi = (whi[r] >> (4 * h)) & 0x0F0F0F0Fu;
+                        if (WT == WT_Q5_K) { lo |= ((hlo[r] >> j) & 0x01010101u) << 4; hi |= ((hhi[r] >> j) & 0x01010101u) << 4; }
+                        af[r] = lo; af[2 + r] = hi;
+                    }
+                    int dd[4]; mma_s8_16832(dd, af, bx[h][0], bx[h][1]);
+                    const float s0 = (float) bs0[sb * 8 + j], s1 = (float) bs1[sb * 8 + j];
+                    acc[mt][0] += x80 * (dl[0][h] * (float) dd[0] - ml[0][h] * s0);
+                    acc[mt][1] += x81 * (dl[0][h] * (float) dd[1] - ml[0][h] * s1);
+                    acc[mt][2] += x80 * (dl[1][h] * (float) dd[2] - ml[1][h] * s0);
+                    acc[mt][3] += x81 * (dl[1][h] * (float) dd[3] - ml[1][h] * s1);
+                }
+            }
+        }
+    } else {
+        const int nblk = K >> 5;
+        const uint32_t * xg = reinterpret_cast<const uint32_t *>(actg);
+        const float * dx0p = reinterpret_cast<const float *>(act0 + K), * dx1p = reinterpret_cast<const float *>(act1 + K);
+        constexpr int QW = (WT == WT_Q8_0) ? 8 : 4;            // 32-bit words of qs per block
+#pragma unroll 5
+        for (int b = warp; b < nblk; b += 8) {
+            const uint32_t b0 = tok_ok ? xg[b * 8 + c] : 0u, b1 = tok_ok ? xg[b * 8 + 4 + c] : 0u;
+            const float dx0 = dx0p[b], dx1 = dx1p[b];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t af[4]; float dw[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int64_t bi = (int64_t) rows[2*mt + r] * nblk + b;
+                    const uint32_t * q32 = reinterpret_cast<const uint32_t *>(a.W.qs) + bi * QW;
+                    dw[r] = __half2float(a.W.d[bi]);
+                    if (WT == WT_Q8_0) { af[r] = __ldg(q32 + c); af[2 + r] = __ldg(q32 + 4 + c); }
+                    else {
+                        const uint32_t w = __ldg(q32 + c);
+                        uint32_t lo = w & 0x0F0F0F0Fu, hi = (w >> 4) & 0x0F0F0F0Fu;
+                        if (WT == WT_Q5_0) {
+                            const uint32_t qh = __ldg(a.W.qh + bi);
+                            lo |= spread4_to_bit4(qh >> (4 * c)); hi |= spread4_to_bit4(qh >> (16 + 4 * c));
+                            af[r] = __vsub4(lo, 0x10101010u); af[2 + r] = __vsub4(hi, 0x10101010u);
+                        } else { af[r] = __vsub4(lo, 0x08080808u); af[2 + r] = __vsub4(hi, 0x08080808u); }
+                    }
+                }
+                int dd[4]; mma_s8_16832(dd, af, b0, b1);
+                acc[mt][0] = fmaf(dw[0] * dx0, (float) dd[0], acc[mt][0]);
+                acc[mt][1] = fmaf(dw[0] * dx1, (float) dd[1], acc[mt][1]);
+                acc[mt][2] = fmaf(dw[1] * dx0, (float) dd[2], acc[mt][2]);
+                acc[mt][3] = fmaf(dw[1] * dx1, (float) dd[3], acc[mt][3]);
+            }
+        }
+    }
+
+    // ---- cross-warp (split-K) reduction and epilogue: thread -> (token = tid/32, row = tid%32)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp][mt * 16 + g + (i >> 1) * 8][2 * c + (i & 1)] = acc[mt][i];
+    __syncthreads();
+    const int t = tid >> 5, rl = tid & 31, row = n0 + rl;
+    if (t < a.n_tok && row < N) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][rl][t];
+        v = (v + (a.bias ? a.bias[row] : 0.0f)) * (a.scale ? a.scale[row] : 1.0f);
+        if (a.act_fn == 1) v = gelu_ref_f16(v);
+        if (a.res) v += a.res[(int64_t) t * N + row];
+        if (a.out) a.out[(int64_t) t * N + row] = v;
+        if (a.k_cache && row >= a.kv_d) {
+            const int64_t cell = a.cells[t];
+            if (row < 2 * a.kv_d) a.k_cache[cell * a.kv_d + (row - a.kv_d)] = __float2half_rn(v);
+            else                  a.v_cache[cell * a.kv_d + (row - 2 * a.kv_d)] = __float2half_rn(v);
+        }
+    }
+}
+
+size_t act_tok_stride(int wtype, int K) {
+    size_t b;
+    if (wtype == WT_F16) b = (size_t) K * 2;
+    else if (wt_is_kquant(wtype)) b = (size_t) K + (size_t) (K / 256) * 4 + (size_t) (K / 32) * 4;
+    else b = (size_t) K + (size_t) (K / 32) * 4;
+    return (b + 15) & ~size_t(15);
+}
+
+void gemv2(const GemvArgs & a, uint8_t * act_scratch, cudaStream_t st) {
+    const int K = a.W.K, N = a.W.N;
+    const size_t ts = act_tok_stride(a.W.type, K);
+    {
+        ProfScope prof(PC_OTHER, st, 0.0, 0.0);
+        if (a.W.type == WT_F16)           k_act_quant<2><<<a.n_tok, 256, 0, st>>>(a.x, K, a.ln_w, a.ln_b, a.eps, act_scratch, ts);
+        else if (wt_is_kquant(a.W.type))  k_act_quant<1><<<a.n_tok, 256, 0, st>>>(a.x, K, a.ln_w, a.ln_b, a.eps, act_scratch, ts);
+        else                              k_act_quant<0><<<a.n_tok, 256, 0, st>>>(a.x, K, a.ln_w, a.ln_b, a.eps, act_scratch, ts);
+        count_launch();
+    }
+    ProfScope prof(PC_GEMV, st, (double) N * K * wt_bpw(a.W.type) + (double) a.n_tok * (K + N) * 4, 2.0 * N * K * a.n_tok);
+    Gemv2K k; k.W = a.W; k.act = act_scratch; k.tok_stride = ts; k.n_tok = a.n_tok; k.bias = a.bias; k.scale = a.scale; k.act_fn = a.act;
+    k.res = a.res; k.out = a.out; k.k_cache = a.k_cache; k.v_cache = a.v_cache; k.cells = a.cells; k.kv_d = a.kv_d;
+    const int grid = (N + 31) / 32;
+    switch (a.W.type) {
+        case WT_F16:  k_gemv_mma<WT_F16><<<grid, 256, 0, st>>>(k);  break;
+        case WT_Q4_0: k_gemv_mma<WT_Q4_0><<<grid, 256, 0, st>>>(k); break;
+        case WT_Q5_0: k_gemv_mma<WT_Q5_0><<<grid, 256, 0, st>>>(k); break;
+        case WT_Q8_0: k_gemv_mma<WT_Q8_0><<<grid, 256, 0, st>>>(k); break;
+        case WT_Q4_K: k_gemv_mma<WT_Q4_K><<<grid, 256, 0, st>>>(k); break;
+        case WT_Q5_K: k_gemv_mma<WT_Q5_K><<<grid, 256, 0, st>>>(k); break;
+        default: set_error("gemv2: unsupported weight type %d", a.W.type); return;
+    }
+    count_launch();
+}
+
+// =====================================================================================================================
 //  decode-step attention (ggml_flash_attn_ext on CPU: ggml-cpu/ops.cpp:8479-8715): Q is rounded to f16, K/V are f16,
 //  scores and the running sums are f32 here (the CPU accumulates V in f16; f32 is strictly closer to exact).
 // =====================================================================================================================
@@ -674,58 +949,82 @@ void attn_self_decode(const float * q, int ldq, const __half * kc, const __half 
     k_attn_self<<<dim3(n_head, n_tok), 128, smem, st>>>(q, ldq, kc, vc, idx, ld_idx, n_kv, d, out, ldo); count_launch();
 }
 
-// grid (n_head, NSPLIT, n_tok), block 128.  Split-KV with an in-kernel combine by the last CTA of each (token, head).
-static constexpr int XSPLIT = 8;
+// grid (n_head, n_split, n_tok), block 128.  Split-KV (64 keys per CTA) with an in-kernel combine by the last CTA of each
+// (token, head).  Phase 1: two threads per key (32 dims each, 4 independent 16-byte loads); phase 2: each warp owns 16 keys and
+// every lane two features, 16 independent 4-byte loads in flight -- the kernel is a pure HBM stream of the cross K/V.
+static constexpr int XKEYS = 64;
+static constexpr int XSPLIT_MAX = 32;
 __global__ void __launch_bounds__(128)
 k_attn_cross(const float * __restrict__ q, int ldq, const __half * __restrict__ kc, const __half * __restrict__ vc,
              const int * __restrict__ slot, int64_t slot_stride, int n_keys, int d, float scale,
              float * __restrict__ partial, int * __restrict__ counters, float * __restrict__ out, int ldo) {
     __shared__ float qh[64];
-    __shared__ float sc[256];
-    __shared__ float part[128];
+    __shared__ float sc[XKEYS];
+    __shared__ float part[4][64];
     __shared__ float red[32];
     __shared__ int   is_last;
-    const int h = blockIdx.x, sp = blockIdx.y, t = blockIdx.z, tid = threadIdx.x, n_head = gridDim.x;
-    const int per = (n_keys + XSPLIT - 1) / XSPLIT;          // <= 256
-    const int k0 = sp * per, k1 = min(n_keys, k0 + per);
-    const __half * kb = kc + (int64_t) slot[t] * slot_stride;
-    const __half * vb = vc + (int64_t) slot[t] * slot_stride;
+    const int h = blockIdx.x, sp = blockIdx.y, t = blockIdx.z, tid = threadIdx.x, n_head = gridDim.x, n_split = gridDim.y;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int k0 = sp * XKEYS;
+    const __half * kb = kc + (int64_t) slot[t] * slot_stride + (int64_t) k0 * d + h * 64;
+    const __half * vb = vc + (int64_t) slot[t] * slot_stride + (int64_t) k0 * d + h * 64;
     if (tid < 64) qh[tid] = __half2float(__float2half_rn(q[(int64_t) t * ldq + h * 64 + tid]));
     __syncthreads();
-    float m = -INFINITY;
-    for (int i = k0 + tid; i < k1; i += 128) {
-        const float s = dot64_f16(kb + (int64_t) i * d + h * 64, qh) * scale;
-        sc[i - k0] = s; m = fmaxf(m, s);
+    {   // scores: thread -> (key = tid/2, half = tid%2)
+        const int key = tid >> 1, hf = tid & 1;
+        float s = 0.0f;
+        if (k0 + key < n_keys) {
+            const uint4 * k4 = reinterpret_cast<const uint4 *>(kb + (int64_t) key * d + hf * 32);
+            uint4 u[4];
+#pragma unroll
+            for (int cix = 0; cix < 4; ++cix) u[cix] = __ldg(k4 + cix);
+#pragma unroll
+            for (int cix = 0; cix < 4; ++cix) {
+                const __half2 * hh = reinterpret_cast<const __half2 *>(&u[cix]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); s = fmaf(f.x, qh[hf*32 + cix*8 + 2*e], s); s = fmaf(f.y, qh[hf*32 + cix*8 + 2*e + 1], s); }
+            }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (hf == 0) sc[key] = (k0 + key < n_keys) ? s * scale : -INFINITY;
     }
-    m = block_max(m, red);
-    float l = 0.0f;
-    for (int i = k0 + tid; i < k1; i += 128) { const float p = expf(sc[i - k0] - m); sc[i - k0] = p; l += p; }
-    l = block_sum(l, red);
-    const int f = tid & 63, g = tid >> 6;
-    float acc = 0.0f;
-    for (int i = k0 + g; i < k1; i += 2) acc = fmaf(sc[i - k0], __half2float(vb[(int64_t) i * d + h * 64 + f]), acc);
-    part[g * 64 + f] = acc;
     __syncthreads();
-    float * pp = partial + (((int64_t) t * n_head + h) * XSPLIT + sp) * 66;
-    if (tid < 64) pp[2 + tid] = part[tid] + part[64 + tid];
+    float m = (tid < XKEYS) ? sc[tid] : -INFINITY;
+    m = block_max(m, red);
+    float pv = 0.0f;
+    if (tid < XKEYS) { pv = (sc[tid] > -INFINITY) ? expf(sc[tid] - m) : 0.0f; sc[tid] = pv; }
+    const float l = block_sum(pv, red);                        // block_sum ends with every thread past its barriers: sc[] is visible
+    {   // out partial: warp w -> keys 16w..16w+15, lane -> features 2*lane, 2*lane+1
+        float a0 = 0.0f, a1 = 0.0f;
+        __half2 vv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int key = warp * 16 + i;
+            vv[i] = (k0 + key < n_keys) ? *reinterpret_cast<const __half2 *>(vb + (int64_t) key * d + 2 * lane) : __float2half2_rn(0.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(vv[i]); const float pr = sc[warp * 16 + i]; a0 = fmaf(pr, f.x, a0); a1 = fmaf(pr, f.y, a1); }
+        part[warp][2 * lane] = a0; part[warp][2 * lane + 1] = a1;
+    }
+    __syncthreads();
+    float * pp = partial + (((int64_t) t * n_head + h) * XSPLIT_MAX + sp) * 66;
+    if (tid < 64) pp[2 + tid] = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
     if (tid == 0) { pp[0] = m; pp[1] = l; }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         const int prev = atomicAdd(&counters[t * n_head + h], 1);
-        is_last = (prev == XSPLIT - 1);
+        is_last = (prev == n_split - 1);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const float * p0 = partial + ((int64_t) t * n_head + h) * XSPLIT * 66;
+    const float * p0 = partial + ((int64_t) t * n_head + h) * XSPLIT_MAX * 66;
     float M = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < XSPLIT; ++s) M = fmaxf(M, p0[s * 66]);
+    for (int s = 0; s < n_split; ++s) M = fmaxf(M, p0[s * 66]);
     if (tid < 64) {
         float L = 0.0f, o = 0.0f;
-#pragma unroll
-        for (int s = 0; s < XSPLIT; ++s) {
+        for (int s = 0; s < n_split; ++s) {
             const float w = expf(p0[s * 66] - M);
             L = fmaf(p0[s * 66 + 1], w, L);
             o = fmaf(p0[s * 66 + 2 + tid], w, o);
@@ -737,11 +1036,16 @@ k_attn_cross(const float * __restrict__ q, int ldq, const __half * __restrict__ 
 void attn_cross_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * slot, int64_t slot_stride,
                        int n_keys, int n_tok, int n_head, int d, float scale, float * partial, int * counters,
                        float * out, int ldo, cudaStream_t st) {
+    const int n_split = (n_keys + XKEYS - 1) / XKEYS;          // 24 for the padded 1536 keys
+    if (n_split > XSPLIT_MAX) { set_error("attn_cross_decode: too many keys (%d)", n_keys); return; }
     ProfScope prof(PC_ATTN, st, (double) n_tok * 2.0 * n_keys * d * 2, 4.0 * n_tok * n_keys * d);
-    k_attn_cross<<<dim3(n_head, XSPLIT, n_tok), 128, 0, st>>>(q, ldq, kc, vc, slot, slot_stride, n_keys, d, scale, partial, counters, out, ldo);
+    k_attn_cross<<<dim3(n_head, n_split, n_tok), 128, 0, st>>>(q, ldq, kc, vc, slot, slot_stride, n_keys, d, scale, partial, counters, out, ldo);
     count_launch();
 }
 
+} // namespace wb
+
+namespace wb {
 // =====================================================================================================================
 //  logits filter + greedy pick on the device.  Same rules, same order, same float formulas as whisper_process_logits /
 //  whisper_sample_token(best=true) (src/whisper.cpp:6196-6543); only the order of the f32 summations differs, so p/plog can

@@ -55,7 +55,10 @@ struct GemvArgs {
     // optional KV append (decoder self-attention): rows [kv_d, 2kv_d) -> k_cache, [2kv_d, 3kv_d) -> v_cache, rounded to f16
     __half * k_cache = nullptr; __half * v_cache = nullptr; const int * cells = nullptr; int kv_d = 0;
 };
-void gemv(const GemvArgs & a, cudaStream_t st);
+void gemv(const GemvArgs & a, cudaStream_t st);            // v1: dp4a, activation quantisation inside every CTA
+// v2: k_act_quant (one CTA per token) + int8 tensor-core block dots, 32 rows per CTA.  act_scratch: >= 8 * act_tok_stride bytes
+size_t act_tok_stride(int wtype, int K);
+void gemv2(const GemvArgs & a, uint8_t * act_scratch, cudaStream_t st);
 
 // self-attention for n_tok query tokens over a paged KV cache.  q: [n_tok][d] f32 (already scaled),
 // k/v cache: [n_cells][d] f16 for this layer.  idx[t*ld_idx + i], i < n_kv[t] lists the cells token t may attend to.
