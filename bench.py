@@ -243,10 +243,22 @@ def main():
             dt = float(t.item())
         return dt, launches, (h1.value - h0.value) / steps, (d1.value - d0.value) / steps
 
+    def counters():
+        a = (C.c_double * 8)(); L.wb200_counters(a, 8); return [a[i] for i in range(8)]
+    L.wb200_counters.argtypes = [C.POINTER(C.c_double), C.c_int]
+
     # ---- device-resident inputs ("value")
     sampler = ClockSampler(local); sampler.start()
-    dt_res, launches, _, _ = timed(True, args.steps, args.warmup)
+    for _ in range(args.warmup):
+        run_pass(True)
+    c0 = counters()
+    dt_res, launches, _, _ = timed(True, args.steps, 0)
+    c1 = counters()
     clocks = sampler.stop()
+    cd = [b - a for a, b in zip(c0, c1)]
+    engine_stats = {"decode_passes_per_step": cd[0] / args.steps, "decode_rows_per_pass": cd[1] / max(cd[0], 1), "decode_gpu_ms_per_pass": cd[2] / max(cd[0], 1),
+                    "decode_host_ms_per_pass": cd[3] / max(cd[0], 1), "encode_calls_per_step": cd[4] / args.steps, "encode_windows_per_step": cd[5] / args.steps,
+                    "encode_gpu_ms_per_window": cd[6] / max(cd[5], 1), "graph_replays_per_step": cd[7] / args.steps}
     audio_s = CHUNK_SECONDS * n_chunks * args.steps * world
     value = audio_s / dt_res
     tokens = last["tokens"]
@@ -272,7 +284,7 @@ def main():
            "dtype": "f16 tcgen05 (encode) / int8 dp4a block dot (decode), f32 accumulate", "data": "synthetic",
            "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "decode": "lock-step batch of up to 8 sequences per GPU", "l2": "weights (1.08 GB) + KV (0.3 GB/sequence) streamed every step exceed the 126 MB L2"},
            "encode_ms": float(enc[1] + enc[2] + enc[3]), "encode_ms_parts": {"mel": float(enc[0]), "conv": float(enc[1]), "encoder": float(enc[2]), "cross": float(enc[3])},
-           "decoded_tokens_per_step": tokens, "clocks": clocks, "gpu_launches": int(launches),
+           "decoded_tokens_per_step": tokens, "engine": engine_stats, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
 
     if rank == 0:

@@ -432,6 +432,9 @@ WB_EXPORT int wb200_pcm_upload(struct whisper_state * state, const float * sampl
  * summed duration [ms], launches, algorithmic bytes, algorithmic flops. */
 WB_EXPORT void wb200_profile_enable(int on);
 WB_EXPORT void wb200_profile_collect(double * ms4, uint64_t * launches4, double * bytes4, double * flops4);
+/* coarse engine counters since load: [0] decode passes [1] decode rows [2] decode GPU ms [3] decode host ms [4] encode calls
+ * [5] encode windows [6] encode GPU ms [7] CUDA-graph replays */
+WB_EXPORT void wb200_counters(double * out, int n);
 /* bytes this library has copied host->device / device->host since load */
 WB_EXPORT void wb200_traffic(uint64_t * h2d, uint64_t * d2h);
 /* last CUDA error text for this thread ("" when none) */

@@ -666,6 +666,7 @@ WB_EXPORT int wb200_pcm_upload(struct whisper_state * st, const float * samples,
 }
 WB_EXPORT void wb200_profile_enable(int on) { wb::prof_enable(on != 0); }
 WB_EXPORT void wb200_profile_collect(double * ms4, uint64_t * launches4, double * bytes4, double * flops4) { wb::prof_collect(ms4, launches4, bytes4, flops4); }
+WB_EXPORT void wb200_counters(double * out, int n) { for (int i = 0; i < n && i < 16; ++i) out[i] = wb::counter_get(i); }
 WB_EXPORT void wb200_traffic(uint64_t * h2d, uint64_t * d2h) { if (h2d) *h2d = wb::h2d_bytes(); if (d2h) *d2h = wb::d2h_bytes(); }
 WB_EXPORT const char * wb200_last_error(void) { return wb::last_error(); }
 WB_EXPORT uint64_t wb200_launch_count(void)   { return wb::launch_count(); }

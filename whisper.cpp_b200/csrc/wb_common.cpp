@@ -21,6 +21,10 @@ const char * last_error() { return g_err; }
 void     count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 uint64_t launch_count()           { return g_launches.load(std::memory_order_relaxed); }
 
+static std::mutex g_cnt_mu; static double g_cnt[16] = { 0 };
+void   counter_add(int idx, double v) { std::lock_guard<std::mutex> lk(g_cnt_mu); if (idx >= 0 && idx < 16) g_cnt[idx] += v; }
+double counter_get(int idx) { std::lock_guard<std::mutex> lk(g_cnt_mu); return (idx >= 0 && idx < 16) ? g_cnt[idx] : 0.0; }
+
 static std::atomic<uint64_t> g_h2d{0}, g_d2h{0};
 void count_h2d(uint64_t n) { g_h2d.fetch_add(n, std::memory_order_relaxed); }
 void count_d2h(uint64_t n) { g_d2h.fetch_add(n, std::memory_order_relaxed); }

@@ -28,6 +28,11 @@ struct ProfScope {
 // sums since the last prof_enable(true); synchronises the device.  arrays of PC_COUNT
 void prof_collect(double * ms, uint64_t * launches, double * bytes, double * flops);
 
+// coarse engine counters (wb200_counters): [0] decode passes [1] decode rows [2] decode GPU ms (events around each pass)
+// [3] decode host ms (wall time inside Engine::decode) [4] encode calls [5] encode windows [6] encode GPU ms [7] graph replays
+void   counter_add(int idx, double v);
+double counter_get(int idx);
+
 // host<->device traffic issued by the library (bytes), for bench.py's e2e accounting
 void     count_h2d(uint64_t n);
 void     count_d2h(uint64_t n);

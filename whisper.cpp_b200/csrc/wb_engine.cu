@@ -3,6 +3,7 @@
 // reference is one tcgen05 GEMM launch (encode) or one fused GEMV launch (decode step) here.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include "wb_engine.h"
 #include "wb_kernels.cuh"
@@ -268,6 +269,7 @@ bool Engine::encode(const EncSrc * srcs, int n_win, int n_ctx) {
     cudaEventElapsedTime(&last_ms[1], ev[1], ev[2]);
     cudaEventElapsedTime(&last_ms[2], ev[2], ev[3]);
     cudaEventElapsedTime(&last_ms[3], ev[3], ev[4]);
+    counter_add(4, 1); counter_add(5, n_win); counter_add(6, last_ms[1] + last_ms[2] + last_ms[3]);
     enc_n_ctx = n_ctx; enc_n_win = n_win;
     return true;
 }
@@ -332,6 +334,7 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
     const int V = hp.n_vocab;
     const int n_keys = pad256(enc_n_ctx > 0 ? enc_n_ctx : hp.n_audio_ctx);
 
+    const int64_t t_host0 = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
     for (int r0 = 0; r0 < n_rows; r0 += 8) {
         const int n = std::min(8, n_rows - r0);
         int * h_tok = hints, * h_pos = hints + 8, * h_cell = hints + 16, * h_slot = hints + 24, * h_nkv = hints + 32, * h_row = hints + 40, * h_idx = hints + 56;
@@ -355,9 +358,11 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         uint64_t key = (uint64_t) (n | (any_logits ? 16 : 0) | (samp ? 32 : 0)) | ((uint64_t) n_keys << 8);
         if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
         StepGraph * sg = (use_graphs && !prof_enabled()) ? &graphs[key] : nullptr;
+        WB_CUDA_OK(cudaEventRecord(ev[5], st));
         if (sg && sg->exec) {
             WB_CUDA_OK(cudaGraphLaunch(sg->exec, st));
             count_launch(sg->launches);
+            counter_add(7, 1);
         } else if (sg && sg->seen >= 1) {
             const uint64_t l0 = launch_count();
             cudaGraph_t g = nullptr;
@@ -374,7 +379,9 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
             if (sg) sg->seen++;
             if (!decode_pass_enqueue(n, any_logits, n_keys, samp)) return false;
         }
+        WB_CUDA_OK(cudaEventRecord(ev[6], st));
         WB_CUDA_OK(cudaStreamSynchronize(st));
+        { float ms = 0.0f; cudaEventElapsedTime(&ms, ev[5], ev[6]); counter_add(0, 1); counter_add(1, n); counter_add(2, ms); }
         if (any_logits && samp && samp_out) {
             for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) samp_out[r0 + j] = hsamp[j];
         } else if (any_logits && logits_out) {
@@ -382,6 +389,7 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
                 memcpy(logits_out[r0 + j], hlogits + (size_t) j * V, (size_t) V * 4);
         }
     }
+    counter_add(3, 1e-3 * (std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_host0));
     return true;
 }
 

@@ -75,7 +75,7 @@ struct Engine {
     void drop_graphs();
 
     // device-event timers of the last encode: [1]=conv (incl. window staging) [2]=encoder [3]=cross  ([0] unused: mel is FrontEnd)
-    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // [5],[6]: decode pass
     float last_ms[4] = { 0, 0, 0, 0 };
 
     ~Engine();

@@ -687,21 +687,14 @@ k_act_quant(const float * __restrict__ x, int K, const float * __restrict__ ln_w
             if (lane == 0) xd[sb] = 1.0f / iscale;
         }
     } else {
-        for (int b = tid; b < K / 32; b += 256) {              // quantize_row_q8_0, AVX2 form (ggml-cpu/arch/x86/quants.c)
-            float v[32]; float amax = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = xval(b * 32 + i); amax = fmaxf(amax, fabsf(v[i])); }
+        // quantize_row_q8_0, AVX2 form (ggml-cpu/arch/x86/quants.c): warp per block, lane per element (coalesced)
+        for (int b = warp; b < K / 32; b += 8) {
+            const float v = xval(b * 32 + lane);
+            const float amax = warp_max(fabsf(v));
             const float d  = amax / 127.0f;
             const float id = (amax != 0.0f) ? 127.0f / amax : 0.0f;
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q0 = __float2int_rn(v[4*i] * id), q1 = __float2int_rn(v[4*i+1] * id), q2 = __float2int_rn(v[4*i+2] * id), q3 = __float2int_rn(v[4*i+3] * id);
-                pk[i] = (uint32_t) (q0 & 0xFF) | ((uint32_t) (q1 & 0xFF) << 8) | ((uint32_t) (q2 & 0xFF) << 16) | ((uint32_t) (q3 & 0xFF) << 24);
-            }
-            uint4 * dst = reinterpret_cast<uint4 *>(tp + b * 32);
-            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            reinterpret_cast<float *>(tp + K)[b] = __half2float(__float2half_rn(d));
+            reinterpret_cast<int8_t *>(tp)[b * 32 + lane] = (int8_t) __float2int_rn(v * id);
+            if (lane == 0) reinterpret_cast<float *>(tp + K)[b] = __half2float(__float2half_rn(d));
         }
     }
 }
@@ -723,19 +716,21 @@ struct Gemv2K {
     __half * k_cache, * v_cache; const int * cells; int kv_d;
 };
 
-template <int WT>
+template <int WT, int MT>   // MT = m16 tiles per CTA (1: 16 rows -- more CTAs for the d x d matrices; 2: 32 rows)
 __global__ void __launch_bounds__(256)
 k_gemv_mma(const Gemv2K a) {
-    __shared__ float red[8][32][9];
+    __shared__ float red[8][16 * MT][9];
     const int K = a.W.K, N = a.W.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
-    const int n0 = blockIdx.x * 32;
-    float acc[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
-    // rows this lane feeds into the A fragments: (m-tile, +0 / +8); clamped for the ragged last CTA (masked at the store)
-    int rows[4];
+    const int n0 = blockIdx.x * 16 * MT;
+    float acc[MT][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rows[i] = min(N - 1, n0 + (i >> 1) * 16 + g + (i & 1) * 8);
+    for (int mt = 0; mt < MT; ++mt) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.0f; }
+    // rows this lane feeds into the A fragments: (m-tile, +0 / +8); clamped for the ragged last CTA (masked at the store)
+    int rows[2 * MT];
+#pragma unroll
+    for (int i = 0; i < 2 * MT; ++i) rows[i] = min(N - 1, n0 + (i >> 1) * 16 + g + (i & 1) * 8);
     const bool tok_ok = g < a.n_tok;
     const uint8_t * actg = a.act + (size_t) (tok_ok ? g : 0) * a.tok_stride;           // token of the B fragment (column g)
     const uint8_t * act0 = a.act + (size_t) min(2 * c,     a.n_tok - 1) * a.tok_stride; // tokens of the D fragment columns
@@ -747,7 +742,7 @@ k_gemv_mma(const Gemv2K a) {
         for (int ks = warp; ks < K / 16; ks += 8) {
             const uint32_t b0 = tok_ok ? xg[ks * 8 + c] : 0u, b1 = tok_ok ? xg[ks * 8 + 4 + c] : 0u;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t * r0 = reinterpret_cast<const uint32_t *>(Wb + (int64_t) rows[2*mt] * K) + ks * 8;
                 const uint32_t * r1 = reinterpret_cast<const uint32_t *>(Wb + (int64_t) rows[2*mt + 1] * K) + ks * 8;
                 const uint32_t af[4] = { __ldg(r0 + c), __ldg(r1 + c), __ldg(r0 + 4 + c), __ldg(r1 + 4 + c) };
@@ -772,7 +767,7 @@ k_gemv_mma(const Gemv2K a) {
             }
             const float x80 = d80[sb], x81 = d81[sb];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 uint32_t wlo[2], whi[2], hlo[2] = { 0, 0 }, hhi[2] = { 0, 0 }; float dl[2][2], ml[2][2];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -813,7 +808,7 @@ k_gemv_mma(const Gemv2K a) {
             const uint32_t b0 = tok_ok ? xg[b * 8 + c] : 0u, b1 = tok_ok ? xg[b * 8 + 4 + c] : 0u;
             const float dx0 = dx0p[b], dx1 = dx1p[b];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 uint32_t af[4]; float dw[2];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -842,12 +837,13 @@ k_gemv_mma(const Gemv2K a) {
 
     // ---- cross-warp (split-K) reduction and epilogue: thread -> (token = tid/32, row = tid%32)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) red[warp][mt * 16 + g + (i >> 1) * 8][2 * c + (i & 1)] = acc[mt][i];
     __syncthreads();
-    const int t = tid >> 5, rl = tid & 31, row = n0 + rl;
-    if (t < a.n_tok && row < N) {
+    constexpr int RT = 16 * MT;
+    const int t = tid / RT, rl = tid % RT, row = n0 + rl;
+    if (t < 8 && t < a.n_tok && row < N) {
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += red[w][rl][t];
@@ -884,16 +880,20 @@ void gemv2(const GemvArgs & a, uint8_t * act_scratch, cudaStream_t st) {
     ProfScope prof(PC_GEMV, st, (double) N * K * wt_bpw(a.W.type) + (double) a.n_tok * (K + N) * 4, 2.0 * N * K * a.n_tok);
     Gemv2K k; k.W = a.W; k.act = act_scratch; k.tok_stride = ts; k.n_tok = a.n_tok; k.bias = a.bias; k.scale = a.scale; k.act_fn = a.act;
     k.res = a.res; k.out = a.out; k.k_cache = a.k_cache; k.v_cache = a.v_cache; k.cells = a.cells; k.kv_d = a.kv_d;
-    const int grid = (N + 31) / 32;
+    // 16-row CTAs while that still leaves every SM several CTAs; 32-row CTAs for the vocabulary-sized matrix
+    const bool small = N <= 8192;
+    const int grid = small ? (N + 15) / 16 : (N + 31) / 32;
+#define WB_GEMV2(T) do { if (small) k_gemv_mma<T, 1><<<grid, 256, 0, st>>>(k); else k_gemv_mma<T, 2><<<grid, 256, 0, st>>>(k); } while (0)
     switch (a.W.type) {
-        case WT_F16:  k_gemv_mma<WT_F16><<<grid, 256, 0, st>>>(k);  break;
-        case WT_Q4_0: k_gemv_mma<WT_Q4_0><<<grid, 256, 0, st>>>(k); break;
-        case WT_Q5_0: k_gemv_mma<WT_Q5_0><<<grid, 256, 0, st>>>(k); break;
-        case WT_Q8_0: k_gemv_mma<WT_Q8_0><<<grid, 256, 0, st>>>(k); break;
-        case WT_Q4_K: k_gemv_mma<WT_Q4_K><<<grid, 256, 0, st>>>(k); break;
-        case WT_Q5_K: k_gemv_mma<WT_Q5_K><<<grid, 256, 0, st>>>(k); break;
+        case WT_F16:  WB_GEMV2(WT_F16);  break;
+        case WT_Q4_0: WB_GEMV2(WT_Q4_0); break;
+        case WT_Q5_0: WB_GEMV2(WT_Q5_0); break;
+        case WT_Q8_0: WB_GEMV2(WT_Q8_0); break;
+        case WT_Q4_K: WB_GEMV2(WT_Q4_K); break;
+        case WT_Q5_K: WB_GEMV2(WT_Q5_K); break;
         default: set_error("gemv2: unsupported weight type %d", a.W.type); return;
     }
+#undef WB_GEMV2
     count_launch();
 }
 
@@ -914,38 +914,64 @@ __device__ __forceinline__ float dot64_f16(const __half * __restrict__ k, const 
     return s;
 }
 
-// grid (n_head, n_tok), block 128
+// grid (n_head, n_tok), block 128.  Scores: two threads per key (4 independent 16-byte loads each); values: each warp takes
+// every 4th key, each lane two features, 8 loads in flight.
 __global__ void __launch_bounds__(128)
 k_attn_self(const float * __restrict__ q, int ldq, const __half * __restrict__ kc, const __half * __restrict__ vc,
             const int * __restrict__ idx, int ld_idx, const int * __restrict__ n_kv, int d, float * __restrict__ out, int ldo) {
-    extern __shared__ float sh[];            // qh[64] | sc[max n_kv] | part[2][64]
+    extern __shared__ float sh[];            // qh[64] | sc[ld_idx] | part[4][64]
     __shared__ float red[32];
-    const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const int h = blockIdx.x, t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nk = n_kv[t];
     float * qh = sh; float * sc = sh + 64; float * part = sc + ((ld_idx + 3) & ~3);
     if (tid < 64) qh[tid] = __half2float(__float2half_rn(q[(int64_t) t * ldq + h * 64 + tid]));
     __syncthreads();
     const int * cells = idx + (int64_t) t * ld_idx;
     float m = -INFINITY;
-    for (int i = tid; i < nk; i += 128) {
-        const float s = dot64_f16(kc + (int64_t) cells[i] * d + h * 64, qh);
-        sc[i] = s; m = fmaxf(m, s);
+    for (int k0 = 0; k0 < nk; k0 += 64) {
+        const int key = k0 + (tid >> 1), hf = tid & 1;
+        float s = 0.0f;
+        if (key < nk) {
+            const uint4 * k4 = reinterpret_cast<const uint4 *>(kc + (int64_t) cells[key] * d + h * 64 + hf * 32);
+            uint4 u[4];
+#pragma unroll
+            for (int cix = 0; cix < 4; ++cix) u[cix] = k4[cix];
+#pragma unroll
+            for (int cix = 0; cix < 4; ++cix) {
+                const __half2 * hh = reinterpret_cast<const __half2 *>(&u[cix]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); s = fmaf(f.x, qh[hf*32 + cix*8 + 2*e], s); s = fmaf(f.y, qh[hf*32 + cix*8 + 2*e + 1], s); }
+            }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (key < nk && hf == 0) sc[key] = s;
+        if (key < nk) m = fmaxf(m, s);
     }
     m = block_max(m, red);
     float l = 0.0f;
     for (int i = tid; i < nk; i += 128) { const float p = expf(sc[i] - m); sc[i] = p; l += p; }
     l = block_sum(l, red);
-    const int f = tid & 63, g = tid >> 6;
-    float acc = 0.0f;
-    for (int i = g; i < nk; i += 2) acc = fmaf(sc[i], __half2float(vc[(int64_t) cells[i] * d + h * 64 + f]), acc);
-    part[g * 64 + f] = acc;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int i0 = warp; i0 < nk; i0 += 32) {             // keys i0, i0+4, ... (8 per round)
+        __half2 vv[8]; float pr[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + 4 * u;
+            const bool ok = i < nk;
+            vv[u] = ok ? *reinterpret_cast<const __half2 *>(vc + (int64_t) cells[i] * d + h * 64 + 2 * lane) : __float2half2_rn(0.0f);
+            pr[u] = ok ? sc[i] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float2 f = __half22float2(vv[u]); a0 = fmaf(pr[u], f.x, a0); a1 = fmaf(pr[u], f.y, a1); }
+    }
+    part[warp * 64 + 2 * lane] = a0; part[warp * 64 + 2 * lane + 1] = a1;
     __syncthreads();
-    if (tid < 64) out[(int64_t) t * ldo + h * 64 + tid] = (l > 0.0f) ? (part[tid] + part[64 + tid]) / l : 0.0f;
+    if (tid < 64) out[(int64_t) t * ldo + h * 64 + tid] = (l > 0.0f) ? (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) / l : 0.0f;
 }
 void attn_self_decode(const float * q, int ldq, const __half * kc, const __half * vc, const int * idx, int ld_idx,
                       const int * n_kv, int n_tok, int n_head, int d, float * out, int ldo, cudaStream_t st) {
     ProfScope prof(PC_ATTN, st, 0.0, 0.0);
-    const size_t smem = (64 + ((ld_idx + 3) & ~3) + 128) * sizeof(float);
+    const size_t smem = (64 + ((ld_idx + 3) & ~3) + 256) * sizeof(float);
     k_attn_self<<<dim3(n_head, n_tok), 128, smem, st>>>(q, ldq, kc, vc, idx, ld_idx, n_kv, d, out, ldo); count_launch();
 }
 
