@@ -91,9 +91,21 @@ def silence(lib):
     lib.whisper_log_set(_quiet, None)
 
 
-def make_inputs(rank, n_chunks):
+def make_inputs(rank, n_chunks, seconds=CHUNK_SECONDS):
+    """the chunks of one rank: independent work per GPU, seeded by rank (no data is exchanged between ranks)"""
     synth = load_pkg().synth
-    return [synth.synth_audio(seed=1000 * rank + i, seconds=CHUNK_SECONDS) for i in range(n_chunks)]
+    return [synth.synth_audio(seed=1000 * rank + i, seconds=seconds) for i in range(n_chunks)]
+
+
+def max_over_ranks(dt, world, device="cuda"):
+    """the job is as slow as its slowest rank"""
+    if world <= 1:
+        return dt
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def ensure_model(path, wtype_name="q5_0"):
@@ -237,10 +249,7 @@ def main():
         dt = time.perf_counter() - t0
         h1, d1 = C.c_uint64(), C.c_uint64(); L.wb200_traffic(C.byref(h1), C.byref(d1))
         launches = eng.launch_count() - n0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dt, world)
         return dt, launches, (h1.value - h0.value) / steps, (d1.value - d0.value) / steps
 
     def counters():

@@ -62,7 +62,7 @@ class Side:
     def decode(self, tokens, n_past):
         t = np.asarray(tokens, np.int32)
         rc = self.L.whisper_decode(self.ctx, _p(t), len(t), n_past, 4)
-        assert rc == 0, rc
+        assert rc == 0, (rc, None if self.is_ref else self.L.wb200_last_error())
         lg = self.L.whisper_get_logits(self.ctx)
         row = (len(t) - 1) * self.n_vocab
         return np.ctypeslib.as_array(lg, shape=(len(t) * self.n_vocab,))[row:row + self.n_vocab].copy()

@@ -1,0 +1,45 @@
+// wb_decode_mk.cuh -- the text decoder step (whisper_build_graph_decoder, src/whisper.cpp:2466-2844) as ONE persistent
+// cooperative kernel: one CTA per SM walks all layers, phases are separated by a grid-wide barrier instead of kernel
+// boundaries, and the weights of the next phase are pulled into L2 while the current phase computes.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include "wb_quant.cuh"
+
+namespace wb {
+
+struct MkLayer {                      // one text layer: weights (model) + this engine's KV pointers
+    QMat qkv, o, cq, co, fc1, fc2;
+    const float * ln0_w, * ln0_b, * lnc_w, * lnc_b, * lnm_w, * lnm_b;
+    const float * qkv_bias, * qkv_scale, * o_bias, * cq_bias, * co_bias, * fc1_bias, * fc2_bias;
+    __half * kc, * vc;                // self-attention KV of this layer: [n_cells][d]
+    const __half * xk, * xv;          // cross-attention K / V of this layer in slot 0: [Tp][d]
+};
+
+struct MkArgs {
+    const MkLayer * layers; int n_layer;
+    int d, n_head, n_tok, n_keys, ld_idx, n_vocab, want_logits;
+    const int * tok, * pos, * cell, * slot, * nkv, * idx;      // per-row integers of this pass (device)
+    int64_t slot_stride;              // elements between the cross KV of consecutive slots
+    float kq_scale, eps;
+    QMat te; const float * pe;        // token embedding (also the logits matrix) and positional embedding
+    const float * lnf_w, * lnf_b;     // final LayerNorm
+    float * x, * qkv, * q2, * logits;                         // f32 workspaces: [8][d], [8][3d], [8][d], [8][V]
+    uint8_t * actq, * hq;             // quantised rows handed from attention to O / from FC1 to FC2 (>= 8*d*4 and 8*4d*4 bytes)
+    float * xpart; int * xcnt;        // cross-attention chunk partials [8*H][n_chunks][66] and arrival counters [8*H]
+    unsigned long long * bar;         // grid barrier: [0] arrival counter (monotonic, never reset), [16 + 16*cta] release flag of each CTA
+    unsigned long long bar_base;      // its value when this launch starts
+    int * err;                        // set to 1 when a barrier wait times out
+    long long * trace;                // optional: phase time stamps of CTA 0 (see MK_STAMP)
+    int prefetch;                     // bit0: next-phase weights -> L2, bit1: cross KV -> L2 one phase ahead
+};
+
+// number of grid barriers one launch passes (host keeps bar_base in step)
+int  mk_barriers(int n_layer, bool want_logits);
+bool mk_supported(int wtype);
+size_t mk_smem_bytes(int wtype, int d);
+// cooperative launch on `st`; grid = number of SMs.  Returns false (with the error set) when the launch is refused.
+bool mk_launch(const MkArgs & a, int wtype, int n_sm, cudaStream_t st);
+
+} // namespace wb

@@ -26,6 +26,7 @@ void Engine::drop_graphs() {
 
 Engine::~Engine() {
     if (m) cudaSetDevice(m->device);
+    mk_trace_dump();
     drop_graphs();
     delete plan;
     if (hints) cudaFreeHost(hints);
@@ -56,6 +57,18 @@ bool Engine::init(const Model * model, int cap_windows) {
     if (!dx.alloc(8 * d) || !dqkv.alloc(8 * 3 * d) || !dattn.alloc(8 * d) || !dq2.alloc(8 * d) || !dh.alloc(8 * 4 * d) ||
         !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 32 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
     if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
+    {
+        cudaDeviceProp prop; WB_CUDA_OK(cudaGetDeviceProperties(&prop, m->device));
+        n_sm = prop.multiProcessorCount;
+        use_mk = m->dec_tm;                   // the layout decides: tile-major decoder weights <=> persistent kernel
+        if (use_mk && (!mk_supported(m->wtype == WT_F32 ? WT_F16 : m->wtype) || mk_smem_bytes(m->wtype == WT_F32 ? WT_F16 : m->wtype, hp.n_text_state) > 200 * 1024 || !prop.cooperativeLaunch)) {
+            set_error("decode: the persistent kernel cannot run on this device/model; set WB200_MEGAKERNEL=0"); return false;
+        }
+        if (const char * pf = getenv("WB200_MK_PREFETCH")) mk_prefetch = atoi(pf);
+        if (use_mk && !mk_bar.alloc(32 + 16 * (size_t) n_sm, true)) return false;
+        sm_ghz = prop.clockRate * 1e-6;
+        if (const char * tp = getenv("WB200_MK_TRACE")) { if (use_mk && *tp) { mk_trace_path = tp; if (!mk_trace.alloc(4096, true)) return false; } }
+    }
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
     WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) 8 * V * sizeof(float)));
     WB_CUDA_OK(cudaMallocHost(&hsamp, 8 * sizeof(SampOut)));
@@ -76,6 +89,55 @@ bool Engine::set_cells(int n) {
     if (hints) cudaFreeHost(hints);
     hints = nullptr;
     WB_CUDA_OK(cudaMallocHost(&hints, nints * sizeof(int)));
+    if (use_mk && !mk_build_table()) return false;
+    return true;
+}
+
+void Engine::mk_trace_collect(int n_layer, bool logits) {
+    const int ns = 1 + 24 * n_layer + (logits ? 2 : 0);
+    std::vector<long long> h(ns);
+    if (cudaMemcpy(h.data(), mk_trace.p, ns * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    if (mk_trace_sum.empty()) mk_trace_sum.assign(27, 0.0);
+    for (int l = 0; l < n_layer; ++l)
+        for (int k = 0; k < 24; ++k) mk_trace_sum[k] += (double) (h[1 + 24 * l + k] - h[24 * l + k]) / n_layer;
+    if (logits) { mk_trace_sum[24] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[25] += (double) (h[ns - 1] - h[ns - 2]); }
+    mk_trace_sum[26] += (double) (h[ns - 1] - h[0]);
+    ++mk_trace_n;
+}
+void Engine::mk_trace_dump() {
+    if (mk_trace_path.empty() || !mk_trace_n) return;
+    FILE * f = fopen(mk_trace_path.c_str(), "a");
+    if (!f) return;
+    static const char * ph[8] = { "A ln+qkv", "B self-attn", "C o-proj", "D ln+cross-q", "E cross-attn", "F cross-o", "G ln+fc1", "H fc2" };
+    const double us = 1e-3 / sm_ghz / (double) mk_trace_n;
+    fprintf(f, "# persistent decode kernel, CTA 0, average over %llu passes (us; SM clock %.3f GHz)\n", (unsigned long long) mk_trace_n, sm_ghz);
+    fprintf(f, "%-16s %10s %10s %10s\n", "phase (per layer)", "prologue", "main", "barrier");
+    double tot = 0.0;
+    for (int p = 0; p < 8; ++p) {
+        fprintf(f, "%-16s %10.2f %10.2f %10.2f\n", ph[p], mk_trace_sum[3*p] * us, mk_trace_sum[3*p + 1] * us, mk_trace_sum[3*p + 2] * us);
+        tot += (mk_trace_sum[3*p] + mk_trace_sum[3*p + 1] + mk_trace_sum[3*p + 2]) * us;
+    }
+    fprintf(f, "layer total %.2f us; final ln %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[24] * us, mk_trace_sum[25] * us, mk_trace_sum[26] * us);
+    fclose(f);
+}
+
+// per-layer descriptor table of the persistent decode kernel (weights of the model + the KV buffers of this engine)
+bool Engine::mk_build_table() {
+    const HParams & hp = m->hp;
+    const int Lt = hp.n_text_layer, d = hp.n_text_state, Tp = Tp_max;
+    std::vector<MkLayer> tab(Lt);
+    for (int l = 0; l < Lt; ++l) {
+        const DecLayerW & L = m->dec[l];
+        MkLayer & t = tab[l];
+        t.qkv = L.qkv; t.o = L.o; t.cq = L.cq; t.co = L.co; t.fc1 = L.fc1; t.fc2 = L.fc2;
+        t.ln0_w = L.ln0.w; t.ln0_b = L.ln0.b; t.lnc_w = L.lnc.w; t.lnc_b = L.lnc.b; t.lnm_w = L.lnm.w; t.lnm_b = L.lnm.b;
+        t.qkv_bias = L.qkv_bias; t.qkv_scale = L.qkv_scale; t.o_bias = L.o_bias; t.cq_bias = L.cq_bias; t.co_bias = L.co_bias;
+        t.fc1_bias = L.fc1_bias; t.fc2_bias = L.fc2_bias;
+        t.kc = kv_k.p + (size_t) l * n_cells * d; t.vc = kv_v.p + (size_t) l * n_cells * d;
+        t.xk = kv_cross.p + (size_t) l * Tp * d;  t.xv = kv_cross.p + (size_t) (Lt + l) * Tp * d;
+    }
+    if (!mk_layers.alloc(Lt)) return false;
+    WB_CUDA_OK(cudaMemcpy(mk_layers.p, tab.data(), Lt * sizeof(MkLayer), cudaMemcpyHostToDevice));
     return true;
 }
 
@@ -295,6 +357,31 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
     const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_row = dints.p + 40, * d_idx = dints.p + 56;
 
     dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
+    if (use_mk) {
+        MkArgs a;
+        a.layers = mk_layers.p; a.n_layer = Lt; a.d = d; a.n_head = H; a.n_tok = n; a.n_keys = n_keys; a.ld_idx = ld_idx; a.n_vocab = V;
+        a.want_logits = any_logits ? 1 : 0;
+        a.tok = d_tok; a.pos = d_pos; a.cell = d_cell; a.slot = d_slot; a.nkv = d_nkv; a.idx = d_idx;
+        a.slot_stride = (int64_t) 2 * Lt * Tp * d; a.kq_scale = kq_scale; a.eps = hp.eps;
+        a.te = m->d_te; a.pe = m->d_pe; a.lnf_w = m->d_ln.w; a.lnf_b = m->d_ln.b;
+        a.x = dx.p; a.qkv = dqkv.p; a.q2 = dq2.p; a.logits = dlogits.p;
+        a.actq = reinterpret_cast<uint8_t *>(dattn.p); a.hq = reinterpret_cast<uint8_t *>(dh.p);
+        a.xpart = xpart.p; a.xcnt = xcnt.p;
+        a.bar = mk_bar.p; a.bar_base = mk_bar_total; a.err = reinterpret_cast<int *>(mk_bar.p + 8); a.prefetch = mk_prefetch; a.trace = mk_trace.p;
+        // algorithmic bytes of one pass: every decoder weight once, the cross K/V of each row, the self K/V each row attends to
+        double wbytes = 0.0, flops = 0.0;
+        for (int l = 0; l < Lt; ++l) {
+            const DecLayerW & L = m->dec[l];
+            for (const QMat * W : { &L.qkv, &L.o, &L.cq, &L.co, &L.fc1, &L.fc2 }) { wbytes += (double) W->N * W->K * wt_bpw(W->type); flops += 2.0 * W->N * W->K * n; }
+        }
+        if (any_logits) { wbytes += (double) m->d_te.N * m->d_te.K * wt_bpw(m->d_te.type); flops += 2.0 * m->d_te.N * m->d_te.K * n; }
+        double kvbytes = 0.0;
+        for (int j = 0; j < n; ++j) kvbytes += (double) Lt * 2.0 * d * 2.0 * ((double) n_keys + hints[32 + j]);
+        flops += kvbytes;                                           // 2 flops per KV element (f16 = 2 bytes): same number
+        ProfScope prof(PC_GEMV, st, wbytes + kvbytes, flops);
+        if (!mk_launch(a, m->wtype == WT_F32 ? WT_F16 : m->wtype, n_sm, st)) return false;
+        mk_bar_total += (unsigned long long) n_sm * mk_barriers(Lt, any_logits);
+    } else
     for (int l = 0; l < Lt; ++l) {
         const DecLayerW & L = m->dec[l];
         __half * kc = kv_k.p + (size_t) l * n_cells * d;
@@ -315,7 +402,7 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
     }
     if (any_logits) {
         GemvArgs a; a.W = m->d_te; a.x = dx.p; a.n_tok = n; a.ln_w = m->d_ln.w; a.ln_b = m->d_ln.b; a.eps = hp.eps; a.out = dlogits.p;   // 2811-2827
-        { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); }
+        if (!use_mk) { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); }      // the persistent kernel already wrote dlogits
         if (samp) {
             SampCfg c = *samp; c.mask = samp_mask.p;
             greedy_sample(dlogits.p, V, n, d_row, c, dsamp.p, st);
@@ -357,7 +444,7 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         // (all per-step values live in `dints`, so kernel arguments never change between steps).
         uint64_t key = (uint64_t) (n | (any_logits ? 16 : 0) | (samp ? 32 : 0)) | ((uint64_t) n_keys << 8);
         if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
-        StepGraph * sg = (use_graphs && !prof_enabled()) ? &graphs[key] : nullptr;
+        StepGraph * sg = (use_graphs && !use_mk && !prof_enabled()) ? &graphs[key] : nullptr;
         WB_CUDA_OK(cudaEventRecord(ev[5], st));
         if (sg && sg->exec) {
             WB_CUDA_OK(cudaGraphLaunch(sg->exec, st));
@@ -382,6 +469,7 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         WB_CUDA_OK(cudaEventRecord(ev[6], st));
         WB_CUDA_OK(cudaStreamSynchronize(st));
         { float ms = 0.0f; cudaEventElapsedTime(&ms, ev[5], ev[6]); counter_add(0, 1); counter_add(1, n); counter_add(2, ms); }
+        if (use_mk && mk_trace.p && any_logits) mk_trace_collect(hp.n_text_layer, true);
         if (any_logits && samp && samp_out) {
             for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) samp_out[r0 + j] = hsamp[j];
         } else if (any_logits && logits_out) {

@@ -7,10 +7,12 @@
 // workspaces.  All work of a state is enqueued on its own CUDA stream.
 #pragma once
 #include <map>
+#include <string>
 #include <vector>
 #include "wb_model.h"
 #include "wb_gemm.cuh"
 #include "wb_kernels.cuh"
+#include "wb_decode_mk.cuh"
 
 namespace wb {
 
@@ -60,6 +62,17 @@ struct Engine {
     DevBuf<float>  dx, dqkv, dattn, dq2, dh, dlogits, xpart;
     DevBuf<uint8_t> act_scratch;      // quantised activations of the current GEMV (k_act_quant -> k_gemv_mma)
     bool gemv_v2 = true;             // WB200_GEMV_V1=1 selects the dp4a kernel
+    // persistent decode kernel (wb_decode_mk.cu); WB200_MEGAKERNEL=0 selects the kernel-per-op chain
+    bool use_mk = false;
+    int  n_sm = 0, mk_prefetch = 1;
+    DevBuf<MkLayer> mk_layers;
+    DevBuf<unsigned long long> mk_bar;   // [0] arrival counter, [8] error flag, [16 + 16*cta] release flags
+    unsigned long long mk_bar_total = 0;
+    bool mk_build_table();
+    // WB200_MK_TRACE=<file>: per-phase clock stamps of CTA 0, averaged over all passes, written when the engine is destroyed
+    DevBuf<long long> mk_trace; std::vector<double> mk_trace_sum, mk_fine; uint64_t mk_trace_n = 0; std::string mk_trace_path; double sm_ghz = 1.0;
+    void mk_trace_collect(int n_layer, bool logits);
+    void mk_trace_dump();
     DevBuf<int>    dints, xcnt;      // packed per-step integers: tokens | pos | cells | slot | n_kv | rowinfo[16] | idx[...]
     DevBuf<uint32_t> samp_mask;      // static suppression bit mask of the on-device sampler
     uint64_t samp_mask_key = 0;

@@ -5,48 +5,14 @@
 #include <vector>
 #include "wb_kernels.cuh"
 #include "wb_common.h"
+#include "wb_dev.cuh"
 
 namespace wb {
 
 // =====================================================================================================================
 //  small utilities
 // =====================================================================================================================
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-// block-wide sum / max for blockDim.x <= 1024 (scratch: 32 floats of shared memory)
-__device__ __forceinline__ float block_sum(float v, float * scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    float r = (lane < nw) ? scratch[lane] : 0.0f;
-    return warp_sum(r);
-}
-__device__ __forceinline__ float block_max(float v, float * scratch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = warp_max(v);
-    __syncthreads();
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    float r = (lane < nw) ? scratch[lane] : -INFINITY;
-    return warp_max(r);
-}
-__device__ __forceinline__ float gelu_ref_f16(float x) {   // ggml-cpu/vec.h:988-1001 (f16 table semantics)
-    if (x <= -10.0f) return 0.0f;
-    if (x >=  10.0f) return x;
-    const float xh = __half2float(__float2half_rn(x));
-    const float g  = 0.5f*xh*(1.0f + tanhf(0.79788456080286535587989211986876f*xh*(1.0f + 0.044715f*xh*xh)));
-    return __half2float(__float2half_rn(g));
-}
+// warp_sum / warp_max / block_sum / block_max / gelu_ref_f16 / mma wrappers: wb_dev.cuh
 
 // =====================================================================================================================
 //  conversions / re-layout
@@ -108,6 +74,71 @@ bool repack_block32(int wtype, const uint8_t * src, uint8_t * dst, int N, int K,
     if (wtype == WT_Q5_0) { out->qh = reinterpret_cast<uint32_t *>(p); p += nblk * 4; }
     out->d = reinterpret_cast<__half *>(p);
     return repack_block32_into(wtype, src, *out, N, K, st);
+}
+
+// tile-major records (wb_quant.cuh): one thread per (tile, record, lane)
+template <int WT>
+__global__ void k_repack_tm(const uint8_t * __restrict__ src, uint8_t * __restrict__ dst, int rows, int K, int64_t n_threads) {
+    constexpr int BS = (WT == WT_Q4_0) ? 18 : (WT == WT_Q5_0 ? 22 : (WT == WT_Q8_0 ? 34 : 0));
+    const int REC = wt_tm_rec_bytes(WT), nrec = K / wt_tm_rec_k(WT);
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_threads) return;
+    const int lane = (int) (i & 31), g = lane >> 2, c = lane & 3;
+    const int64_t rb = i >> 5;
+    const int b = (int) (rb % nrec);
+    const int64_t tile = rb / nrec;
+    uint8_t * rec = dst + (tile * nrec + b) * REC;
+    const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
+    if (WT == WT_F16) {
+        const __half * h = reinterpret_cast<const __half *>(src);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t r = (k & 1) ? r1 : r0;
+            const int col = b * 16 + 2 * c + ((k >> 1) ? 8 : 0);
+            const unsigned short lo = r < rows ? __half_as_ushort(h[r * K + col]) : 0, hi = r < rows ? __half_as_ushort(h[r * K + col + 1]) : 0;
+            w[k] = (uint32_t) lo | ((uint32_t) hi << 16);
+        }
+        reinterpret_cast<uint4 *>(rec)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
+    }
+    const uint8_t * b0 = src + (r0 * nrec + b) * BS, * b1 = src + (r1 * nrec + b) * BS;
+    const int qoff = (WT == WT_Q5_0) ? 6 : 2;
+    auto word = [&](const uint8_t * blk, int64_t r, int wi) -> uint32_t {
+        if (r >= rows) return 0u;
+        const uint8_t * q = blk + qoff + 4 * wi;
+        return (uint32_t) q[0] | ((uint32_t) q[1] << 8) | ((uint32_t) q[2] << 16) | ((uint32_t) q[3] << 24);
+    };
+    if (WT == WT_Q8_0) reinterpret_cast<uint4 *>(rec)[lane] = make_uint4(word(b0, r0, c), word(b1, r1, c), word(b0, r0, 4 + c), word(b1, r1, 4 + c));
+    else               reinterpret_cast<uint2 *>(rec)[lane] = make_uint2(word(b0, r0, c), word(b1, r1, c));
+    if (c == 0) {                                                // lanes 0,4,..: the per-row fields of rows g and g+8
+        const int qsb = (WT == WT_Q8_0) ? 512 : 256;
+        auto d16 = [&](const uint8_t * blk, int64_t r) -> uint32_t { return r < rows ? ((uint32_t) blk[0] | ((uint32_t) blk[1] << 8)) : 0u; };
+        if (WT == WT_Q5_0) {
+            auto h32 = [&](const uint8_t * blk, int64_t r) -> uint32_t { return r < rows ? ((uint32_t) blk[2] | ((uint32_t) blk[3] << 8) | ((uint32_t) blk[4] << 16) | ((uint32_t) blk[5] << 24)) : 0u; };
+            reinterpret_cast<uint2 *>(rec + qsb)[g] = make_uint2(h32(b0, r0), h32(b1, r1));
+            reinterpret_cast<uint32_t *>(rec + qsb + 64)[g] = d16(b0, r0) | (d16(b1, r1) << 16);
+        } else {
+            reinterpret_cast<uint32_t *>(rec + qsb)[g] = d16(b0, r0) | (d16(b1, r1) << 16);
+        }
+    }
+}
+bool repack_tile_major(int wtype, const uint8_t * src, const QMat & dst, int row_off, int rows, cudaStream_t st) {
+    if (dst.layout != 1 || (row_off & 15)) { set_error("repack_tile_major: bad destination"); return false; }
+    const int K = dst.K, nrec = K / wt_tm_rec_k(wtype);
+    const int64_t tiles = (rows + 15) / 16, n_threads = tiles * nrec * 32;
+    if (n_threads == 0) return true;
+    uint8_t * out = const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(dst.base)) + (size_t) (row_off / 16) * nrec * wt_tm_rec_bytes(wtype);
+    const unsigned blocks = (unsigned) ((n_threads + 255) / 256);
+    switch (wtype) {
+        case WT_F16:  k_repack_tm<WT_F16><<<blocks, 256, 0, st>>>(src, out, rows, K, n_threads); break;
+        case WT_Q4_0: k_repack_tm<WT_Q4_0><<<blocks, 256, 0, st>>>(src, out, rows, K, n_threads); break;
+        case WT_Q5_0: k_repack_tm<WT_Q5_0><<<blocks, 256, 0, st>>>(src, out, rows, K, n_threads); break;
+        case WT_Q8_0: k_repack_tm<WT_Q8_0><<<blocks, 256, 0, st>>>(src, out, rows, K, n_threads); break;
+        default: set_error("repack_tile_major: bad type %d", wtype); return false;
+    }
+    count_launch();
+    return cudaGetLastError() == cudaSuccess;
 }
 
 // =====================================================================================================================
@@ -306,8 +337,32 @@ void softmax_rows_f16(const float * s, __half * p, int64_t rows, int cols, cudaS
 //  decoder: token + position embedding (get_rows on the quantised table is an exact f32 dequantisation,
 //  ggml-cpu/ops.cpp:4850 -> ggml-quants.c dequantize_row_*)
 // =====================================================================================================================
+__device__ __forceinline__ float dequant_elem_tm(const QMat & W, int64_t row, int e) {     // tile-major records (wb_quant.cuh)
+    const int REC = wt_tm_rec_bytes(W.type), rk = wt_tm_rec_k(W.type), nrec = W.K / rk;
+    const int rr = (int) (row & 15), g = rr & 7, up = rr >> 3, i = e % rk;
+    const uint8_t * rec = reinterpret_cast<const uint8_t *>(W.base) + ((row >> 4) * nrec + e / rk) * REC;
+    if (W.type == WT_F16) {
+        const int c = (i & 7) >> 1, k = up + ((i >> 3) << 1);
+        const uint32_t w = reinterpret_cast<const uint32_t *>(rec)[(g * 4 + c) * 4 + k];
+        return __half2float(__ushort_as_half((unsigned short) ((i & 1) ? (w >> 16) : (w & 0xffffu))));
+    }
+    const int qsb = (W.type == WT_Q8_0) ? 512 : 256;
+    const uint32_t dd = reinterpret_cast<const uint32_t *>(rec + qsb + (W.type == WT_Q5_0 ? 64 : 0))[g];
+    const float d = __half2float(__ushort_as_half((unsigned short) (up ? (dd >> 16) : (dd & 0xffffu))));
+    if (W.type == WT_Q8_0) {
+        const int c = (i & 15) >> 2, k = up + ((i >> 4) << 1);
+        const uint32_t w = reinterpret_cast<const uint32_t *>(rec)[(g * 4 + c) * 4 + k];
+        return d * (float) (int8_t) ((w >> (8 * (i & 3))) & 0xffu);
+    }
+    const int c = (i & 15) >> 2;
+    const uint32_t w = reinterpret_cast<const uint32_t *>(rec)[(g * 4 + c) * 2 + up];
+    int q = (int) ((w >> (8 * (i & 3) + 4 * (i >> 4))) & 0xFu);
+    if (W.type == WT_Q5_0) { const uint32_t qh = reinterpret_cast<const uint32_t *>(rec + 256)[g * 2 + up]; q |= (int) ((qh >> i) & 1u) << 4; return d * (float) (q - 16); }
+    return d * (float) (q - 8);
+}
 __device__ __forceinline__ float dequant_elem(const QMat & W, int64_t row, int e) {
     const int K = W.K;
+    if (W.layout == 1) return dequant_elem_tm(W, row, e);
     switch (W.type) {
         case WT_F16: return __half2float(reinterpret_cast<const __half *>(W.base)[row * K + e]);
         case WT_Q4_0: { const int64_t b = row * (K >> 5) + (e >> 5); const int i = e & 31;
@@ -697,17 +752,6 @@ k_act_quant(const float * __restrict__ x, int K, const float * __restrict__ ln_w
             if (lane == 0) reinterpret_cast<float *>(tp + K)[b] = __half2float(__float2half_rn(d));
         }
     }
-}
-
-__device__ __forceinline__ void mma_s8_16832(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(0), "r"(0), "r"(0), "r"(0));
-}
-__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 struct Gemv2K {

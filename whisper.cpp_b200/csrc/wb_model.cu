@@ -5,6 +5,7 @@
 #include <cstring>
 #include <functional>
 #include "../../include/whisper_b200.h"
+#include <cstdlib>
 #include "wb_model.h"
 #include "wb_kernels.cuh"
 
@@ -43,8 +44,15 @@ void * dalloc(Model & m, size_t bytes, bool zero = true) {
 }
 
 // allocate an [N][K] matrix of type t in its HBM layout
-bool alloc_qmat(Model & m, int t, int N, int K, QMat & q) {
+bool alloc_qmat(Model & m, int t, int N, int K, QMat & q, bool tile_major = false) {
     q.type = t; q.N = N; q.K = K;
+    if (tile_major && wt_tm_rec_bytes(t) > 0 && K % 32 == 0) {
+        const size_t bytes = wt_tm_bytes(t, N, K);
+        q.base = dalloc(m, bytes);
+        if (!q.base) return false;
+        q.layout = 1;
+        return cudaMemset(const_cast<void *>(q.base), 0, bytes) == cudaSuccess;
+    }
     if (t == WT_F16) {
         q.base = dalloc(m, (size_t) N * K * 2);
         return q.base != nullptr;
@@ -196,7 +204,12 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         ln.w = w; ln.b = b; add_vec(base + ".weight", w, d); add_vec(base + ".bias", b, d); return true;
     };
     if (!add_ln("encoder.ln_post", m.e_ln) || !add_ln("decoder.ln", m.d_ln)) return false;
-    if (!alloc_qmat(m, wt, V, d, m.d_te)) return false;
+    {   // the persistent decode kernel (wb_decode_mk.cu) reads the decoder matrices in the tile-major layout; WB200_MEGAKERNEL=0
+        // keeps them planar for the kernel-per-op chain (K-quants and odd shapes always use the chain)
+        const char * e = getenv("WB200_MEGAKERNEL");
+        m.dec_tm = (!e || atoi(e) != 0) && wt_tm_rec_bytes(wt) > 0 && d % 128 == 0 && hp.n_text_head * 64 == d && hp.n_text_state == d;
+    }
+    if (!alloc_qmat(m, wt, V, d, m.d_te, m.dec_tm)) return false;
     add_mat("decoder.token_embedding.weight", &m.d_te, 0, V, d);
 
     m.enc.resize(La); m.dec.resize(Lt);
@@ -228,8 +241,8 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         DecLayerW & L = m.dec[i];
         const std::string p = "decoder.blocks." + std::to_string(i) + ".";
         if (!add_ln(p + "attn_ln", L.ln0) || !add_ln(p + "cross_attn_ln", L.lnc) || !add_ln(p + "mlp_ln", L.lnm)) return false;
-        if (!alloc_qmat(m, wt, 3*d, d, L.qkv) || !alloc_qmat(m, wt, d, d, L.o) || !alloc_qmat(m, wt, d, d, L.cq) ||
-            !alloc_qmat(m, wt, d, d, L.co) || !alloc_qmat(m, wt, 4*d, d, L.fc1) || !alloc_qmat(m, wt, d, 4*d, L.fc2)) return false;
+        if (!alloc_qmat(m, wt, 3*d, d, L.qkv, m.dec_tm) || !alloc_qmat(m, wt, d, d, L.o, m.dec_tm) || !alloc_qmat(m, wt, d, d, L.cq, m.dec_tm) ||
+            !alloc_qmat(m, wt, d, d, L.co, m.dec_tm) || !alloc_qmat(m, wt, 4*d, d, L.fc1, m.dec_tm) || !alloc_qmat(m, wt, d, 4*d, L.fc2, m.dec_tm)) return false;
         float * qb = fvec(3*d), * qs = fvec(3*d), * ob = fvec(d), * cqb = fvec(d), * cob = fvec(d), * f1b = fvec(4*d), * f2b = fvec(d);
         if (!qb || !qs || !ob || !cqb || !cob || !f1b || !f2b) return false;
         k_fill<<<(2*d + 255)/256, 256>>>(qs, kq_scale, 2*d);
@@ -308,7 +321,13 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
             if (ttype != file_wtype) { set_error("tensor '%s' has type %d, expected %d", name.c_str(), ttype, file_wtype); return false; }
             QMat & q = *D.mat;
             const int K = q.K;
-            if (q.type == WT_F16) {
+            if (q.layout == 1) {
+                const uint8_t * src = dstage;
+                DevBuf<__half> tmp;
+                if (q.type == WT_F16 && ttype == WT_F32) { if (!tmp.alloc(nelements)) return false; f32_to_f16((const float *) dstage, tmp.p, nelements, 0); src = (const uint8_t *) tmp.p; }
+                if (!repack_tile_major(q.type, src, q, D.row_off, D.rows, 0)) return false;
+                WB_CUDA_OK(cudaDeviceSynchronize());
+            } else if (q.type == WT_F16) {
                 __half * dst = (__half *) q.base + (size_t) D.row_off * K;
                 if (ttype == WT_F16) WB_CUDA_OK(cudaMemcpy(dst, dstage, nbytes, cudaMemcpyDeviceToDevice));
                 else f32_to_f16((const float *) dstage, dst, nelements, 0);

@@ -65,6 +65,7 @@ struct Model {
     int     mtype = 0;               // e_model (1 tiny .. 5 large)
     int     n_loaded = 0;            // 0 => weight-less test stub (src/whisper.cpp:1947-1948)
     int     device = 0;
+    bool    dec_tm = false;          // decoder matrices + token embedding are in the tile-major layout (persistent decode kernel)
     int64_t t_load_us = 0;
 
     int n_filt_mel = 0, n_filt_fft = 0;

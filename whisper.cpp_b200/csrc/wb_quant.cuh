@@ -28,7 +28,20 @@ struct QMat {            // one weight matrix resident in HBM
     const uint8_t  * qs = nullptr;
     const uint32_t * qh = nullptr;
     const __half   * d  = nullptr;
+    int   layout = 0;    // 0: rows (F16) / planar (32-blocks) / verbatim (K-quants); 1: tile-major records at `base` (see below)
 };
+
+// "Tile-major" layout of the decoder matrices (persistent decode kernel, wb_decode_mk.cu).  The matrix is cut into tiles of
+// 16 output rows; for every tile and every 32-value block (F16: every 16 values) there is ONE contiguous record holding the
+// operands in the register order of the warp-level MMA (lane = 4*g + c reads rows g and g+8 of the tile):
+//   Q4_0 (288 B): u32 qs[32 lanes][2] = { word c of row g, word c of row g+8 }            | f16 d[8][2]  = { row g, row g+8 }
+//   Q5_0 (352 B): qs as Q4_0 (256 B) | u32 qh[8][2] = { row g, row g+8 } (64 B)            | f16 d[8][2]
+//   Q8_0 (544 B): u32 qs[32 lanes][4] = { w c / row g, w c / row g+8, w 4+c / row g, w 4+c / row g+8 } | f16 d[8][2]
+//   F16  (512 B per 16 values): u32 a[32 lanes][4] = the m16n8k16 A fragment
+// so one warp fetches a record with three fully coalesced loads.  Same bytes per weight as the file; rows >= N are zero.
+__host__ __device__ inline int wt_tm_rec_bytes(int t) { return t == WT_Q4_0 ? 288 : t == WT_Q5_0 ? 352 : t == WT_Q8_0 ? 544 : t == WT_F16 ? 512 : 0; }
+__host__ __device__ inline int wt_tm_rec_k(int t)     { return t == WT_F16 ? 16 : 32; }
+__host__ __device__ inline size_t wt_tm_bytes(int t, int N, int K) { return (size_t) ((N + 15) / 16) * (K / wt_tm_rec_k(t)) * wt_tm_rec_bytes(t); }
 
 __host__ __device__ inline int wt_qs_bytes(int t)    { return t == WT_Q8_0 ? 32 : 16; }
 __host__ __device__ inline bool wt_is_block32(int t) { return t == WT_Q4_0 || t == WT_Q5_0 || t == WT_Q8_0; }
