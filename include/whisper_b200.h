@@ -413,7 +413,7 @@ WB_EXPORT void  whisper_vad_free         (struct whisper_vad_context * ctx);
  *        2 = encoder output [n_ctx][n_state] f32, 3/4 = cross K/V [n_text_layer][1536][n_state] as f32 */
 WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * state, int which, float * out, int64_t cap);
 /* run `n_chunks` independent PCM buffers through whisper_full_with_state semantics on ONE device in LOCK-STEP:
- * up to 8 member states share one engine, so every encoder pass / decode step serves all live chunks at once
+ * up to 64 member states share one engine, so every encoder pass / decode step serves all live chunks at once
  * (weights are read once per step).  Chunk i's segments land in the result-only state states_out[i] (free with
  * whisper_free_state).  _ex flags bit 0: samples[i] are DEVICE pointers (PCM already in HBM).  Returns 0 ok. */
 WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params,

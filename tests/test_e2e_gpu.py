@@ -142,7 +142,8 @@ def test_loader_fixtures_and_errors(lib):
     assert not L.whisper_init_from_file_with_params(bad.encode(), cp)       # bad magic
 
 
-def test_lockstep_batch_equals_one_by_one(lib, ref, tmp_path):
+@pytest.mark.parametrize("n_chunks", [5, 19])
+def test_lockstep_batch_equals_one_by_one(lib, ref, tmp_path, n_chunks):
     """wb200_full_batch (lock-step batched encode/decode of independent chunks) must give, chunk by chunk, exactly the
     tokens whisper_full gives for that chunk alone: batching only changes how many sequences share a weight read."""
     import ctypes as C
@@ -152,7 +153,8 @@ def test_lockstep_batch_equals_one_by_one(lib, ref, tmp_path):
     try:
         L = A.L
         vp = C.c_void_p
-        chunks = [synth.synth_audio(seed=20 + i, seconds=s) for i, s in enumerate((30.0, 12.0, 47.0, 30.0, 3.0))]
+        secs = (30.0, 12.0, 47.0, 30.0, 3.0) if n_chunks == 5 else tuple(4.0 + 1.5 * (i % 7) for i in range(n_chunks))   # 19: > 16 rows per pass
+        chunks = [synth.synth_audio(seed=20 + i, seconds=s) for i, s in enumerate(secs)]
         fp = L.whisper_full_default_params(0); fp.print_progress = False; fp.temperature_inc = 0.0; fp.greedy.best_of = 1
         L.wb200_full_batch.argtypes = [vp, FullParams, C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
         n = len(chunks)

@@ -206,7 +206,7 @@ void Group::run(std::vector<Req *> & batch) {
             std::vector<DecToken> rows; std::vector<int> cells, nkv, idx((size_t) total * ld, 0); std::vector<float *> outs;
             std::vector<int> rowinfo; std::vector<SampOut> souts((size_t) total); std::vector<std::pair<Req *, int>> origin;
             rows.reserve(total);
-            // interleave: row k of every request first, so that single-token steps of all members share one pass of <= 8 rows
+            // interleave: row k of every request first, so that single-token steps of all members share one pass (<= Engine::max_rows rows)
             // and multi-token prompts advance in lock-step (causal order inside each member is preserved)
             int maxn = 0; for (Req * q : dec) maxn = std::max(maxn, q->n);
             for (Req * q : dec) { if (all_samp) q->st->samp_out.assign(q->n, SampOut()); else { q->st->samp_out.clear(); q->st->logits.resize((size_t) q->n * n_vocab); } }

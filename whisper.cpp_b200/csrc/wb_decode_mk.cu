@@ -1,4 +1,4 @@
-// wb_decode_mk.cu -- one decoder pass (<= 8 rows) as a single persistent cooperative kernel.
+// wb_decode_mk.cu -- one decoder pass (<= 64 rows) as a single persistent cooperative kernel.
 //
 // What it computes is whisper_build_graph_decoder (src/whisper.cpp:2466-2844) for the rows of one whisper_batch:
 //   per layer:  LN -> QKV (+KV append) -> self-attention over the paged cache -> O + residual
@@ -27,12 +27,13 @@
 
 namespace wb {
 
-constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_RED = 16 * 16 * 9, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 16 * 16 * MK_REDLD, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_ROWB = 1280;            // bytes of one staged activation row chunk (1280 int8 values or 640 halves)
 
 struct MkSm {
-    uint32_t * xq;      // quantised activations of the current GEMV phase: [8][SW] words (int8x4 or half2); q staging in attention phases
-    float * xd;         // Q8_0 block scales [8][K/32]
-    float * red;        // [2][16 warps][16 rows][9]  split-K partials (double buffered)
+    uint32_t * xq;      // staged chunk of the quantised activations: [64 rows][SW] words (int8x4 or half2)
+    float * xd;         // Q8_0 block scales of the chunk [64][chunk/32]
+    float * red;        // [16 warps][16 rows][65]  split-K partials of a tile pair
     float * part;       // [2][16 warps][68]          attention warp partials: m, l, -, -, o[64]
     float * stat;       // [32] LayerNorm partial sums
     int   * flag;       // [4]
@@ -73,173 +74,160 @@ __device__ __noinline__ void mk_grid_sync(const MkArgs & a, MkSm & sm, unsigned 
     __syncthreads();
 }
 
-// ---- prologue of a GEMV phase --------------------------------------------------------------------------------------------
-// quantised activations in global memory ("actq" format, written by the producing phase): block-32 weight types:
-// int8 [8][K] followed by f32 block scales [8][K/32]; F16 weights: half [8][K].
-// Q8_0 block of the 4 values of 8 consecutive lanes (quantize_row_q8_0: d = amax/127 stored as f16, q = rint(x * 127/amax);
-// the two quotients are formed with a reciprocal multiply / __fdividef: <= 2 ulp from the IEEE quotient, which only matters when
-// a product lands within 1e-6 of a rounding boundary)
-__device__ __forceinline__ uint32_t q8_block4(const float4 & y, float & d_out) {
-    float amax = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-    d_out = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
-    const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
-    const uint32_t q0 = (uint32_t) __float2int_rn(y.x * id) & 0xffu, q1 = (uint32_t) __float2int_rn(y.y * id) & 0xffu;
-    const uint32_t q2 = (uint32_t) __float2int_rn(y.z * id) & 0xffu, q3 = (uint32_t) __float2int_rn(y.w * id) & 0xffu;
-    return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-}
+// ---- activation rows ("actq" format) ----------------------------------------------------------------------------------------
+// Rows handed from one phase to the next are quantised ONCE by their producer and live in global memory: block-32 weight types:
+// int8 [64][K] followed by f32 block scales [64][K/32]; F16 weights: half [64][K].  A GEMV phase stages them chunk-wise in smem.
+// Q8_0 rows follow quantize_row_q8_0 (d = amax/127 stored as f16, q = rint(x * 127/amax)); the two quotients are formed with a
+// reciprocal multiply / __fdividef: <= 2 ulp from the IEEE quotient, which only matters within 1e-6 of a rounding boundary.
 
-// LayerNorm (ggml-cpu/ops.cpp:3698-3765, two passes, then mul/add whisper.cpp:2536-2543) + quantisation of every row of the
-// f32 residual stream into shared memory.  Two warps per row; each lane keeps its <= 5 float4 of the row in registers.
-template <int WT>
-__device__ __noinline__ void mk_load_ln(const MkArgs & a, MkSm & sm, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = warp >> 1, hw = warp & 1;
-    const int nch = K >> 7;                                      // 128-value chunks per row; this warp takes chunks hw, hw+2, ...
-    const int SW = (WT == WT_F16) ? (K / 2 + 4) : (K / 4 + 4);
-    sm.SW = SW;
-    const bool act = t < a.n_tok;
-    const float4 * xr = reinterpret_cast<const float4 *>(src + (size_t) t * K);
-    float4 v[5];
-    float s = 0.0f;
-#pragma unroll
-    for (int u = 0; u < 5; ++u) {
-        const int j = hw + 2 * u;
-        v[u] = (act && j < nch) ? __ldcg(xr + j * 32 + lane) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
-    }
-    s = warp_sum(s);
-    if (lane == 0) sm.stat[warp] = s;
-    __syncthreads();
-    const float mean = (sm.stat[warp & ~1] + sm.stat[warp | 1]) / K;
-    float q = 0.0f;
-#pragma unroll
-    for (int u = 0; u < 5; ++u) {
-        if (hw + 2 * u < nch) {
-            v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
-            q += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
-        }
-    }
-    q = warp_sum(q);
-    if (lane == 0) sm.stat[16 + warp] = q;
-    __syncthreads();
-    const float rstd = 1.0f / sqrtf((sm.stat[16 + (warp & ~1)] + sm.stat[16 + (warp | 1)]) / K + a.eps);
-    if (act) {
-#pragma unroll
-        for (int u = 0; u < 5; ++u) {
-            const int j = hw + 2 * u;
-            if (j < nch) {
-                const float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w) + j * 32 + lane), b = __ldg(reinterpret_cast<const float4 *>(ln_b) + j * 32 + lane);
-                float4 y;
-                y.x = __fadd_rn(__fmul_rn(__fmul_rn(v[u].x, rstd), w.x), b.x);
-                y.y = __fadd_rn(__fmul_rn(__fmul_rn(v[u].y, rstd), w.y), b.y);
-                y.z = __fadd_rn(__fmul_rn(__fmul_rn(v[u].z, rstd), w.z), b.z);
-                y.w = __fadd_rn(__fmul_rn(__fmul_rn(v[u].w, rstd), w.w), b.w);
-                const int e0 = j * 128 + lane * 4;
-                if (WT == WT_F16) {
-                    const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-                    sm.xq[t * SW + e0 / 2]     = *reinterpret_cast<const uint32_t *>(&h0);
-                    sm.xq[t * SW + e0 / 2 + 1] = *reinterpret_cast<const uint32_t *>(&h1);
-                } else {
-                    float d;
-                    sm.xq[t * SW + e0 / 4] = q8_block4(y, d);
-                    if ((lane & 7) == 0) sm.xd[t * (K >> 5) + j * 4 + (lane >> 3)] = d;
-                }
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// copy already-quantised activations (written by the producing phase) into shared memory: two warps per row
-template <int WT>
-__device__ __noinline__ void mk_load_q(const MkArgs & a, MkSm & sm, const uint8_t * src, int K) {
-    const int tid = threadIdx.x, t = tid >> 6, l64 = tid & 63;
-    const int SW = (WT == WT_F16) ? (K / 2 + 4) : (K / 4 + 4);
-    sm.SW = SW;
-    const int cpr = ((WT == WT_F16) ? K * 2 : K) >> 4;           // 16-byte chunks per row
-    if (t < a.n_tok) {
-        const uint4 * s4 = reinterpret_cast<const uint4 *>(src) + (size_t) t * cpr;
-        for (int c0 = l64; c0 < cpr; c0 += 64 * 5) {
-            uint4 v[5];
-#pragma unroll
-            for (int u = 0; u < 5; ++u) if (c0 + 64 * u < cpr) v[u] = __ldcg(s4 + c0 + 64 * u);
-#pragma unroll
-            for (int u = 0; u < 5; ++u) if (c0 + 64 * u < cpr) *reinterpret_cast<uint4 *>(sm.xq + t * SW + (c0 + 64 * u) * 4) = v[u];
-        }
-        if (WT != WT_F16) {
-            const float * sc = reinterpret_cast<const float *>(src + (size_t) 8 * K) + t * (K >> 5);
-            for (int i = l64; i < (K >> 5); i += 64) sm.xd[t * (K >> 5) + i] = __ldcg(sc + i);
-        }
-    }
-    __syncthreads();
-}
-
-// one warp quantises the 32 values its lanes hold (one Q8_0 block of row t starting at element e0) into the actq format
+// one warp quantises the 32 values its lanes hold (one Q8_0 block of row t starting at element e0)
 template <int WT>
 __device__ __forceinline__ void mk_store_q(uint8_t * dst, int K, int t, int e0, int lane, float v) {
     if (WT == WT_F16) { reinterpret_cast<__half *>(dst)[(size_t) t * K + e0 + lane] = __float2half_rn(v); return; }
     const float amax = warp_max(fabsf(v));
     const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
     reinterpret_cast<int8_t *>(dst)[(size_t) t * K + e0 + lane] = (int8_t) __float2int_rn(v * id);
-    if (lane == 0) reinterpret_cast<float *>(dst + (size_t) 8 * K)[t * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
+    if (lane == 0) reinterpret_cast<float *>(dst + (size_t) MK_MAXTOK * K)[t * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
+}
+
+// LayerNorm (ggml-cpu/ops.cpp:3698-3765, two passes, then mul/add whisper.cpp:2536-2543) of the f32 residual rows, quantised into
+// `dst`.  Distributed: CTA r normalises row r (one warp per 128 values); followed by a grid barrier.
+template <int WT>
+__device__ __noinline__ void mk_lnq(const MkArgs & a, MkSm & sm, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int row = blockIdx.x; row < a.n_tok; row += gridDim.x) {
+        const bool act = warp < (K >> 7);
+        const int e0 = warp * 128 + lane * 4;
+        float4 v = act ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float s = warp_sum((v.x + v.y) + (v.z + v.w));
+        if (lane == 0) sm.stat[warp] = s;
+        __syncthreads();
+        s = (lane < MK_WARPS) ? sm.stat[lane] : 0.0f;
+        const float mean = warp_sum(s) / K;
+        float q = 0.0f;
+        if (act) { v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean; q = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w); }
+        q = warp_sum(q);
+        if (lane == 0) sm.stat[16 + warp] = q;
+        __syncthreads();
+        q = (lane < MK_WARPS) ? sm.stat[16 + lane] : 0.0f;
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / K + a.eps);
+        if (act) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w + e0)), b = __ldg(reinterpret_cast<const float4 *>(ln_b + e0));
+            float4 y;
+            y.x = __fadd_rn(__fmul_rn(__fmul_rn(v.x, rstd), w.x), b.x);
+            y.y = __fadd_rn(__fmul_rn(__fmul_rn(v.y, rstd), w.y), b.y);
+            y.z = __fadd_rn(__fmul_rn(__fmul_rn(v.z, rstd), w.z), b.z);
+            y.w = __fadd_rn(__fmul_rn(__fmul_rn(v.w, rstd), w.w), b.w);
+            if (WT == WT_F16) {
+                const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+                *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + (size_t) row * K + e0) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+            } else {
+                float amax = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
+                const uint32_t q0 = (uint32_t) __float2int_rn(y.x * id) & 0xffu, q1 = (uint32_t) __float2int_rn(y.y * id) & 0xffu;
+                const uint32_t q2 = (uint32_t) __float2int_rn(y.z * id) & 0xffu, q3 = (uint32_t) __float2int_rn(y.w * id) & 0xffu;
+                *reinterpret_cast<uint32_t *>(dst + (size_t) row * K + e0) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                if ((lane & 7) == 0) reinterpret_cast<float *>(dst + (size_t) MK_MAXTOK * K)[row * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// stage chunk `kc` (MK_ROWB bytes per row at most) of the quantised rows in shared memory.  Warp w copies rows w, w+16, ...
+template <int WT>
+__device__ __noinline__ void mk_load_chunk(const MkArgs & a, MkSm & sm, const uint8_t * src, int K, int kc, int KCe) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rowb = (WT == WT_F16) ? K * 2 : K, chb = (WT == WT_F16) ? KCe * 2 : KCe, cpr = chb >> 4, SW = (chb >> 2) + 4;
+    __syncthreads();                                             // the previous users of the staging buffer are done
+    sm.SW = SW;
+    uint4 v[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int t = warp + 16 * i, cc = lane + 32 * j;
+            if (t < a.n_tok && cc < cpr) v[i][j] = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t) t * rowb + (size_t) kc * chb) + cc);
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int t = warp + 16 * i, cc = lane + 32 * j;
+            if (t < a.n_tok && cc < cpr) *reinterpret_cast<uint4 *>(sm.xq + t * SW + cc * 4) = v[i][j];
+        }
+    if (WT != WT_F16) {
+        const int nbc = KCe >> 5;                                // scales of the chunk: [row][nbc]
+        const float * sc = reinterpret_cast<const float *>(src + (size_t) MK_MAXTOK * K) + kc * nbc;
+        for (int i = threadIdx.x; i < a.n_tok * 64; i += MK_THREADS) {
+            const int t = i >> 6, bl = i & 63;
+            if (bl < nbc) sm.xd[t * nbc + bl] = __ldcg(sc + (size_t) t * (K >> 5) + bl);
+        }
+    }
+    __syncthreads();
 }
 
 struct MkEpi {
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
-    uint8_t * outq = nullptr;            // quantised output (actq format) for the next GEMV; needs KS <= 8 (row pairs in one CTA)
+    uint8_t * outq = nullptr;            // quantised output rows (actq format) for the next GEMV
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
 };
 
-// L2 prefetch of the tiles this CTA will own in a later GEMV phase (tile-major: the records of a tile are contiguous)
-__device__ __noinline__ void mk_prefetch_w(const QMat & W, int KS) {
-    if (threadIdx.x != MK_THREADS - 32) return;                  // one lane of the last warp (idle in the LayerNorm prologue)
-    const int n_tiles = (W.N + 15) >> 4, TPC = MK_WARPS / KS;
+// L2 prefetch of the tile pairs this CTA will own in a later GEMV phase (tile-major: the records of a tile are contiguous)
+__device__ __noinline__ void mk_prefetch_w(const QMat & W) {
+    if (threadIdx.x != MK_THREADS - 32) return;
+    const int n_tiles = (W.N + 15) >> 4;
     const uint32_t tile_bytes = (uint32_t) (W.K / wt_tm_rec_k(W.type)) * wt_tm_rec_bytes(W.type);
-    for (int tile0 = blockIdx.x * TPC; tile0 < n_tiles; tile0 += gridDim.x * TPC)
-        l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile0 * tile_bytes, tile_bytes * (uint32_t) min(TPC, n_tiles - tile0));
+    for (int tile0 = blockIdx.x * 2; tile0 < n_tiles; tile0 += gridDim.x * 2)
+        l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile0 * tile_bytes, tile_bytes * (uint32_t) min(2, n_tiles - tile0));
 }
 
-// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n]   for the tiles owned by this CTA
+// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n] for the tile PAIRS (32 output rows) owned by this CTA.
+// Warp w: tile (w >> 3) of the pair, k-slice (w & 7); it multiplies its weight blocks with ALL rows (8 per MMA, <= 8 MMAs per block),
+// so a weight block is decoded once for up to 64 sequences.  x: quantised rows in global memory (actq format).
 template <int WT>
-__device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W, const MkEpi & e, int KS, int & round) {
+__device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W, const uint8_t * x, const MkEpi & e) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
-    constexpr int UB = 5;                                        // records whose loads are issued together
-    const int N = W.N, n_tok = a.n_tok;
+    constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
+    constexpr int UB = 3;                                        // records whose loads are issued together
+    const int N = W.N, K = W.K, n_tok = a.n_tok, NG = (n_tok + 7) >> 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
-    const int n_tiles = (N + 15) >> 4, nrec = W.K / ((WT == WT_F16) ? 16 : 32);
-    const int TPC = MK_WARPS / KS, tl = warp / KS, kp = warp - tl * KS;
-    const int SW = sm.SW;
-    const bool tok_ok = g < n_tok;
-    const int t0 = min(2 * c, n_tok - 1), t1 = min(2 * c + 1, n_tok - 1);
-    for (int tile0 = blockIdx.x * TPC; tile0 < n_tiles; tile0 += gridDim.x * TPC, ++round) {
-        const int tile = tile0 + tl;
-        float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-        if (tile < n_tiles) {
-            const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * nrec * REC;
-            for (int kb = kp; kb < nrec; kb += KS * UB) {
-                uint4 wq[UB]; uint2 wh[UB]; uint32_t wd[UB];
+    const int tsel = warp >> 3, ks = warp & 7;
+    const int n_tiles = (N + 15) >> 4, n_pairs = (n_tiles + 1) >> 1, nrec = K / RK;
+    const int KCe = (WT == WT_F16 && a.d > 640) ? (a.d >> 1) : a.d;   // activation chunk staged in smem (K is d or 4d)
+    const int nchunks = K / KCe, rpc = KCe / RK, nbc = KCe >> 5;
+    bool staged = false;
+    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int tile = pr * 2 + tsel;
+        float acc[8][4];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const uint8_t * rec = tb + (size_t) min(kb + u * KS, nrec - 1) * REC;
-                    if (WT == WT_F16 || WT == WT_Q8_0) wq[u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
-                    else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[u].x = q2.x; wq[u].y = q2.y; }
-                    if (WT == WT_Q5_0) wh[u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
-                    if (WT != WT_F16)  wd[u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
-                }
+        for (int gi = 0; gi < 8; ++gi) { acc[gi][0] = acc[gi][1] = acc[gi][2] = acc[gi][3] = 0.0f; }
+        for (int kc = 0; kc < nchunks; ++kc) {
+            if (nchunks > 1 || !staged) { mk_load_chunk<WT>(a, sm, x, K, kc, KCe); staged = true; }
+            const int SW = sm.SW;
+            if (tile < n_tiles) {
+                const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + ((size_t) tile * nrec + (size_t) kc * rpc) * REC;
+                for (int kb = ks; kb < rpc; kb += 8 * UB) {
+                    uint4 wq[UB]; uint2 wh[UB]; uint32_t wd[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int b = kb + u * KS;
-                    if (b < nrec) {
-                        const uint32_t b0 = tok_ok ? sm.xq[g * SW + b * 8 + c] : 0u, b1 = tok_ok ? sm.xq[g * SW + b * 8 + 4 + c] : 0u;
-                        if (WT == WT_F16) {
-                            const uint32_t af[4] = { wq[u].x, wq[u].y, wq[u].z, wq[u].w };
-                            mma_f16_16816(acc, af, b0, b1);
-                        } else {
+                    for (int u = 0; u < UB; ++u) {
+                        const uint8_t * rec = tb + (size_t) min(kb + u * 8, rpc - 1) * REC;
+                        if (WT == WT_F16 || WT == WT_Q8_0) wq[u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
+                        else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[u].x = q2.x; wq[u].y = q2.y; }
+                        if (WT == WT_Q5_0) wh[u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
+                        if (WT != WT_F16)  wd[u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int bl = kb + u * 8;               // record within the chunk
+                        if (bl < rpc) {
                             uint32_t af[4];
-                            if (WT == WT_Q8_0) { af[0] = wq[u].x; af[1] = wq[u].y; af[2] = wq[u].z; af[3] = wq[u].w; }
+                            float dw0 = 0.0f, dw1 = 0.0f;
+                            if (WT == WT_F16 || WT == WT_Q8_0) { af[0] = wq[u].x; af[1] = wq[u].y; af[2] = wq[u].z; af[3] = wq[u].w; }
                             else {
                                 uint32_t lo0 = wq[u].x & 0x0F0F0F0Fu, hi0 = (wq[u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[u].y & 0x0F0F0F0Fu, hi1 = (wq[u].y >> 4) & 0x0F0F0F0Fu;
                                 if (WT == WT_Q5_0) {
@@ -252,31 +240,48 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W
                                     af[1] = __vsub4(lo1, 0x08080808u); af[3] = __vsub4(hi1, 0x08080808u);
                                 }
                             }
-                            int dd[4]; mma_s8_16832(dd, af, b0, b1);
-                            const float dx0 = sm.xd[t0 * nrec + b], dx1 = sm.xd[t1 * nrec + b];
-                            const float dw0 = __half2float(__ushort_as_half((unsigned short) (wd[u] & 0xffffu))), dw1 = __half2float(__ushort_as_half((unsigned short) (wd[u] >> 16)));
-                            acc[0] = fmaf(dw0 * dx0, (float) dd[0], acc[0]);
-                            acc[1] = fmaf(dw0 * dx1, (float) dd[1], acc[1]);
-                            acc[2] = fmaf(dw1 * dx0, (float) dd[2], acc[2]);
-                            acc[3] = fmaf(dw1 * dx1, (float) dd[3], acc[3]);
+                            if (WT != WT_F16) {
+                                dw0 = __half2float(__ushort_as_half((unsigned short) (wd[u] & 0xffffu)));
+                                dw1 = __half2float(__ushort_as_half((unsigned short) (wd[u] >> 16)));
+                            }
+#pragma unroll
+                            for (int gi = 0; gi < 8; ++gi) {
+                                if (gi < NG) {
+                                    const int tb_ = gi * 8 + g;
+                                    const bool ok = tb_ < n_tok;
+                                    const uint32_t b0 = ok ? sm.xq[tb_ * SW + bl * 8 + c] : 0u, b1 = ok ? sm.xq[tb_ * SW + bl * 8 + 4 + c] : 0u;
+                                    if (WT == WT_F16) mma_f16_16816(acc[gi], af, b0, b1);
+                                    else {
+                                        int dd[4]; mma_s8_16832(dd, af, b0, b1);
+                                        const float dx0 = sm.xd[min(gi * 8 + 2 * c, n_tok - 1) * nbc + bl], dx1 = sm.xd[min(gi * 8 + 2 * c + 1, n_tok - 1) * nbc + bl];
+                                        acc[gi][0] = fmaf(dw0 * dx0, (float) dd[0], acc[gi][0]);
+                                        acc[gi][1] = fmaf(dw0 * dx1, (float) dd[1], acc[gi][1]);
+                                        acc[gi][2] = fmaf(dw1 * dx0, (float) dd[2], acc[gi][2]);
+                                        acc[gi][3] = fmaf(dw1 * dx1, (float) dd[3], acc[gi][3]);
+                                    }
+                                }
+                            }
                         }
                     }
                 }
             }
         }
-        float * red = sm.red + (round & 1) * MK_RED;
+        // split-K partials -> smem: red[warp][row][token]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) red[(warp * 16 + g + (i >> 1) * 8) * 9 + 2 * c + (i & 1)] = acc[i];
+        for (int gi = 0; gi < 8; ++gi)
+            if (gi < NG) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sm.red[(warp * 16 + g + (i >> 1) * 8) * MK_REDLD + gi * 8 + 2 * c + (i & 1)] = acc[gi][i];
+            }
         __syncthreads();
-        for (int o = tid; o < TPC * 128; o += MK_THREADS) {
-            // plain: 16 consecutive rows per (tile, row-of-batch); quantised output: one warp = 32 consecutive rows of one batch row
-            int tl2, t, rl;
-            if (e.outq) { const int pr = o >> 8, rem = o & 255; t = rem >> 5; tl2 = pr * 2 + ((rem & 31) >> 4); rl = rem & 15; }
-            else        { tl2 = o >> 7; t = (o & 127) >> 4; rl = o & 15; }
-            const int row = (tile0 + tl2) * 16 + rl;
+        // epilogue: one warp = the 32 rows of the pair for one batch row (one Q8_0 block when the output is handed on quantised)
+        for (int o = tid; o < 32 * NG * 8; o += MK_THREADS) {
+            const int r32 = o & 31, t = o >> 5, tl2 = r32 >> 4, rl = r32 & 15;
+            const int row = pr * 32 + r32;
             if (t < n_tok && row < N) {
                 float v = 0.0f;
-                for (int w = 0; w < KS; ++w) v += red[((tl2 * KS + w) * 16 + rl) * 9 + t];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += sm.red[((tl2 * 8 + w) * 16 + rl) * MK_REDLD + t];
                 v = (v + (e.bias ? __ldg(e.bias + row) : 0.0f)) * (e.scale ? __ldg(e.scale + row) : 1.0f);
                 if (e.act == 1) v = gelu_ref_f16(v);
                 if (e.res) v += __ldcg(e.res + (size_t) t * N + row);
@@ -289,40 +294,31 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W
                 }
             }
         }
+        __syncthreads();                                         // red[] is rewritten by the next pair
     }
 }
 
 // ---- attention -----------------------------------------------------------------------------------------------------------
-// stage the f16-rounded queries of all rows in shared memory (ggml_flash_attn_ext converts Q to f16: ggml-cpu/ops.cpp:8560-8571)
-__device__ __noinline__ void mk_stage_q(const MkArgs & a, MkSm & sm, const float * q, int ldq) {
-    float * qs = reinterpret_cast<float *>(sm.xq);
-    const int tid = threadIdx.x, t = tid >> 6, l64 = tid & 63, d = a.d, n4 = d >> 2;
-    if (t < a.n_tok) {
-        const float4 * s4 = reinterpret_cast<const float4 *>(q + (size_t) t * ldq);
-        float4 v[5];
+// the 16 query values of this lane's quarter of head h of row t, rounded to f16 (ggml_flash_attn_ext converts Q to f16:
+// ggml-cpu/ops.cpp:8560-8571)
+__device__ __forceinline__ void load_q16(const float * q, float (&qv)[16]) {
 #pragma unroll
-        for (int u = 0; u < 5; ++u) if (l64 + 64 * u < n4) v[u] = __ldcg(s4 + l64 + 64 * u);
-#pragma unroll
-        for (int u = 0; u < 5; ++u) if (l64 + 64 * u < n4) {
-            float4 r;
-            r.x = __half2float(__float2half_rn(v[u].x)); r.y = __half2float(__float2half_rn(v[u].y));
-            r.z = __half2float(__float2half_rn(v[u].z)); r.w = __half2float(__float2half_rn(v[u].w));
-            *reinterpret_cast<float4 *>(qs + t * d + (l64 + 64 * u) * 4) = r;
-        }
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(q) + i);
+        qv[4 * i]     = __half2float(__float2half_rn(v.x)); qv[4 * i + 1] = __half2float(__float2half_rn(v.y));
+        qv[4 * i + 2] = __half2float(__float2half_rn(v.z)); qv[4 * i + 3] = __half2float(__float2half_rn(v.w));
     }
-    __syncthreads();
 }
 
 struct KVFrag { uint4 k0, k1; uint32_t v[8]; };
 
-__device__ __forceinline__ float dot16(const uint4 & k0, const uint4 & k1, const float * __restrict__ q) {
+__device__ __forceinline__ float dot16(const uint4 & k0, const uint4 & k1, const float (&q)[16]) {
     float s = 0.0f;
     const __half2 * h0 = reinterpret_cast<const __half2 *>(&k0), * h1 = reinterpret_cast<const __half2 *>(&k1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float2 f = __half22float2(h0[i]), f2 = __half22float2(h1[i]);
-        const float2 qa = *reinterpret_cast<const float2 *>(q + 2 * i), qb = *reinterpret_cast<const float2 *>(q + 8 + 2 * i);
-        s = fmaf(f.x, qa.x, s); s = fmaf(f.y, qa.y, s); s = fmaf(f2.x, qb.x, s); s = fmaf(f2.y, qb.y, s);
+        s = fmaf(f.x, q[2 * i], s); s = fmaf(f.y, q[2 * i + 1], s); s = fmaf(f2.x, q[8 + 2 * i], s); s = fmaf(f2.y, q[8 + 2 * i + 1], s);
     }
     return s;
 }
@@ -369,13 +365,13 @@ template <int WT>
 __device__ __noinline__ void mk_attn_self(const MkArgs & a, MkSm & sm, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp >> 3, hw = warp & 7;
     const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
-    const float * qs = reinterpret_cast<const float *>(sm.xq);
     const int kslot = lane >> 2, r = lane & 3;
     for (int p = blockIdx.x * 2 + half; p < n_pairs; p += gridDim.x * 2) {
         const int t = p / H, h = p - t * H;
         const int nk = a.nkv[t];
         const int * cells = a.idx + (size_t) t * a.ld_idx;
-        const float * q = qs + t * d + h * 64 + r * 16;
+        float q[16];
+        load_q16(a.qkv + (size_t) t * 3 * d + h * 64 + r * 16, q);
         float m = -INFINITY, l = 0.0f, o0 = 0.0f, o1 = 0.0f;
         for (int k0 = hw * 8; k0 < nk; k0 += 64) {
             const bool ok = k0 + kslot < nk;
@@ -414,39 +410,35 @@ __device__ __forceinline__ void xkv_load(KVFrag & f, const __half * __restrict__
 }
 
 // cross-attention over the n_keys padded encoder positions, zero rows included (whisper.cpp:2688-2705).
-// Work unit = (row, head, chunk of 128 keys), pair-major.  The units are cut into equal contiguous ranges ("stream-K"): a CTA
-// walks its range chunk by chunk -- warp w owns keys 8w..8w+7 of every chunk and keeps a running (max, sum, out) per (row, head)
-// in registers -- and only merges its 16 warps when the (row, head) pair changes.  A pair that is spread over several CTAs is
-// finished by the last one to arrive (counter), merging the per-CTA partials in CTA order.
+// Work unit = (row, head, half of the keys).  Units are dealt out in contiguous ranges; a CTA walks a unit in chunks of 128 keys
+// (warp w owns keys 8w..8w+7 of every chunk, running max/sum/out in registers, next chunk prefetched into registers), merges
+// its 16 warps, and writes the unit's partial; the second half to arrive merges the two partials of the (row, head) pair in fixed
+// order -- so the result of a row does not depend on which other rows share the pass.
 template <int WT>
 __device__ __noinline__ void mk_attn_cross(const MkArgs & a, MkSm & sm, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = a.d, H = a.n_head, nc = a.n_keys / MK_XKEYS;
-    const unsigned I = (unsigned) (a.n_tok * H * nc), G = min(gridDim.x, I);   // G <= I: every participating CTA owns >= 1 unit
-    const float * qs = reinterpret_cast<const float *>(sm.xq);
-    const bool part_of = blockIdx.x < G;
-    const unsigned s0 = part_of ? (blockIdx.x * I) / G : 0u, s1 = part_of ? ((blockIdx.x + 1) * I) / G : 0u;
-    // (pair, chunk) of the unit being loaded, advanced incrementally (no divisions in the loop)
-    int pl = (int) (s0 / (unsigned) nc), jl = (int) (s0 - (unsigned) pl * nc);
-    int tl_ = pl / H, hl = pl - tl_ * H;
-    int p = pl, t = tl_, h = hl;                                 // pair of the unit being computed
+    const int d = a.d, H = a.n_head, nch = a.n_keys / (2 * MK_XKEYS);          // chunks per unit
+    const unsigned I = (unsigned) (a.n_tok * H * 2), G = min(gridDim.x, I);
+    if (blockIdx.x >= G) return;
+    const unsigned s0 = (blockIdx.x * I) / G, s1 = ((blockIdx.x + 1) * I) / G;
+    int p = (int) (s0 >> 1), t = p / H, h = p - t * H, hf = (int) (s0 & 1);
+    // loader state: unit being fetched
+    int tl_ = t, hl = h, hfl = hf, jl = 0;
+    unsigned ul = s0;
     auto load_next = [&](KVFrag & f) {
-        const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) (jl * MK_XKEYS + warp * 8) * d + hl * 64;
+        const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) ((hfl * nch + jl) * MK_XKEYS + warp * 8) * d + hl * 64;
         xkv_load(f, L.xk + off, L.xv + off, d, lane);
-        if (++jl == nc) { jl = 0; if (++hl == H) { hl = 0; ++tl_; } }
+        if (++jl == nch) { jl = 0; ++ul; if (++hfl == 2) { hfl = 0; if (++hl == H) { hl = 0; ++tl_; } } }
     };
     KVFrag cur, nxt;
-    unsigned loaded = s0;
-    if (s0 < s1) { load_next(cur); ++loaded; }
+    load_next(cur);
     int buf = 0;
-    unsigned it = s0;
-    while (it < s1) {
-        const unsigned seg_end = min(s1, (unsigned) (p + 1) * nc);
-        const int nseg = (int) (seg_end - it);
-        const float * q = qs + t * d + h * 64 + (lane & 3) * 16;
+    for (unsigned u = s0; u < s1; ++u) {
+        float q[16];
+        load_q16(a.q2 + (size_t) t * d + h * 64 + (lane & 3) * 16, q);
         float m = -INFINITY, l = 0.0f, o0 = 0.0f, o1 = 0.0f;
-        for (; it < seg_end; ++it) {
-            if (loaded < s1) { load_next(nxt); ++loaded; }
+        for (int j = 0; j < nch; ++j) {
+            if (ul < s1) load_next(nxt);
             float sc = dot16(cur.k0, cur.k1, q);
             sc += __shfl_xor_sync(0xffffffffu, sc, 1);
             sc += __shfl_xor_sync(0xffffffffu, sc, 2);
@@ -457,45 +449,34 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, MkSm & sm, const Mk
         if (lane == 0) { part[0] = m; part[1] = l; }
         *reinterpret_cast<float2 *>(part + 4 + 2 * lane) = make_float2(o0, o1);
         __syncthreads();
-        if (warp < 2) {                                          // merge the 16 warp partials of this segment
+        if (warp < 2) {                                          // merge the 16 warp partials of this unit
             const int dim = warp * 32 + lane;
             float M, Lsum;
             const float o = attn_merge(sm.part + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
-            if (nseg == nc) {
-                mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(o, Lsum));
-            } else {
-                // CTAs that share this pair: first = the one whose range contains unit p*nc, last = the one containing (p+1)*nc - 1
-                const unsigned u0 = (unsigned) p * nc, u1 = u0 + nc - 1;
-                // (CTA c owns units [c*I/G, (c+1)*I/G): the owner of unit u is ((u+1)*G - 1) / I)
-                const unsigned cf = ((u0 + 1) * G - 1) / I, cl = ((u1 + 1) * G - 1) / I;
-                const int slot = (int) (blockIdx.x - cf), n_contrib = (int) (cl - cf + 1);
-                float * gp = a.xpart + ((size_t) p * MK_XSLOTS + slot) * 66;
-                gp[2 + dim] = o;
-                if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
+            float * gp = a.xpart + ((size_t) p * 2 + hf) * 66;
+            gp[2 + dim] = o;
+            if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
+            __threadfence();
+            bar_named(3, 64);
+            if (tid == 0) sm.flag[buf] = (atomicAdd(a.xcnt + p, 1) == 1);
+            bar_named(3, 64);
+            if (sm.flag[buf]) {                                   // both halves are in: merge them (half 0 first)
                 __threadfence();
-                bar_named(3, 64);
-                if (tid == 0) sm.flag[buf] = (atomicAdd(a.xcnt + p, 1) == n_contrib - 1);
-                bar_named(3, 64);
-                if (sm.flag[buf]) {
-                    __threadfence();
-                    const float * p0 = a.xpart + (size_t) p * MK_XSLOTS * 66;
-                    float MM = -INFINITY;
-                    for (int sidx = 0; sidx < n_contrib; ++sidx) MM = fmaxf(MM, __ldcg(p0 + sidx * 66));
-                    float LL = 0.0f, oo = 0.0f;
-                    for (int sidx = 0; sidx < n_contrib; ++sidx) {
-                        const float wgt = __expf(__ldcg(p0 + sidx * 66) - MM);
-                        LL = fmaf(__ldcg(p0 + sidx * 66 + 1), wgt, LL);
-                        oo = fmaf(__ldcg(p0 + sidx * 66 + 2 + dim), wgt, oo);
-                    }
-                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
-                    if (tid == 0) a.xcnt[p] = 0;
-                }
+                const float * p0 = a.xpart + (size_t) p * 2 * 66;
+                const float m0 = __ldcg(p0), m1 = __ldcg(p0 + 66), MM = fmaxf(m0, m1);
+                const float w0 = __expf(m0 - MM), w1 = __expf(m1 - MM);
+                const float LL = fmaf(__ldcg(p0 + 67), w1, __ldcg(p0 + 1) * w0);
+                const float oo = fmaf(__ldcg(p0 + 68 + dim), w1, __ldcg(p0 + 2 + dim) * w0);
+                mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
+                if (tid == 0) a.xcnt[p] = 0;
             }
         }
         buf ^= 1;
-        ++p; if (++h == H) { h = 0; ++t; }
+        if (++hf == 2) { hf = 0; ++p; if (++h == H) { h = 0; ++t; } }
     }
 }
+
+#define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP(); } while (0)
 
 template <int WT, bool TRACE>
 __global__ void __launch_bounds__(MK_THREADS, 1)
@@ -503,97 +484,86 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     MkSm sm;
     {
-        const int KMAX = 4 * a.d;
-        const size_t xq_bytes = (WT == WT_F16) ? (size_t) 8 * (KMAX * 2 + 16) : (size_t) 8 * (KMAX + 16);
         uint8_t * p = smem_raw;
-        sm.xq = reinterpret_cast<uint32_t *>(p); p += xq_bytes;
-        sm.xd = reinterpret_cast<float *>(p);    p += (size_t) 8 * (KMAX / 32) * 4;
-        sm.red = reinterpret_cast<float *>(p);   p += (size_t) 2 * MK_RED * 4;
+        sm.xq = reinterpret_cast<uint32_t *>(p); p += (size_t) MK_MAXTOK * (MK_ROWB + 16);
+        sm.xd = reinterpret_cast<float *>(p);    p += (size_t) MK_MAXTOK * (MK_ROWB / 32) * 4;
+        sm.red = reinterpret_cast<float *>(p);   p += (size_t) MK_RED * 4;
         sm.part = reinterpret_cast<float *>(p);  p += (size_t) 2 * MK_WARPS * MK_PART * 4;
         sm.stat = reinterpret_cast<float *>(p);  p += 32 * 4;
         sm.flag = reinterpret_cast<int *>(p);
         sm.SW = 0;
     }
     unsigned long long target = a.bar_base;
-    int round = 0, n_stamp = 0;
+    int n_stamp = 0;
     const int d = a.d;
     const bool pf_w = a.prefetch & 1;
-    const int KS_LOG = 4;
     MK_STAMP();
-    if (pf_w) mk_prefetch_w(a.layers[0].qkv, 16);
+    if (pf_w) mk_prefetch_w(a.layers[0].qkv);
 
     for (int l = 0; l < a.n_layer; ++l) {
         const MkLayer & L = a.layers[l];
         MkEpi e;
-        // A: LN + QKV + KV append (whisper.cpp:2536-2599)
-        if (pf_w) mk_prefetch_w(L.o, 16);
-        mk_load_ln<WT>(a, sm, a.x, d, L.ln0_w, L.ln0_b);
-        MK_STAMP();
+        // 1: LN -> quantised rows (whisper.cpp:2536-2543)
+        mk_lnq<WT>(a, sm, a.x, d, L.ln0_w, L.ln0_b, a.actq);
+        if (pf_w) mk_prefetch_w(L.o);
+        MK_SYNC();
+        // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
-        mk_gemv<WT>(a, sm, L.qkv, e, 16, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // B: self-attention (2603-2625) -> quantised rows for the O projection
-        if (pf_w) mk_prefetch_w(L.cq, 16);
-        mk_stage_q(a, sm, a.qkv, 3 * d);
-        MK_STAMP();
+        mk_gemv<WT>(a, sm, L.qkv, a.actq, e);
+        MK_SYNC();
+        // 3: self-attention (2603-2625) -> quantised rows for the O projection
+        if (pf_w) mk_prefetch_w(L.cq);
         mk_attn_self<WT>(a, sm, L);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // C: O + residual (2647-2659)
-        if (pf_w) mk_prefetch_w(L.co, 16);
-        mk_load_q<WT>(a, sm, a.actq, d);
-        MK_STAMP();
+        MK_SYNC();
+        // 4: O + residual (2647-2659)
+        if (pf_w) mk_prefetch_w(L.co);
         e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.o, e, 16, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // D: LN + cross Q (2661-2681)
-        if (pf_w) mk_prefetch_w(L.fc1, 8);
-        mk_load_ln<WT>(a, sm, a.x, d, L.lnc_w, L.lnc_b);
-        MK_STAMP();
+        mk_gemv<WT>(a, sm, L.o, a.actq, e);
+        MK_SYNC();
+        // 5: LN -> quantised rows
+        mk_lnq<WT>(a, sm, a.x, d, L.lnc_w, L.lnc_b, a.actq);
+        if (pf_w) mk_prefetch_w(L.fc1);
+        MK_SYNC();
+        // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
-        mk_gemv<WT>(a, sm, L.cq, e, 16, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // E: cross-attention (2688-2705)
-        if (pf_w) mk_prefetch_w(L.fc2, 16);
-        mk_stage_q(a, sm, a.q2, d);
-        MK_STAMP();
+        mk_gemv<WT>(a, sm, L.cq, a.actq, e);
+        MK_SYNC();
+        // 7: cross-attention (2688-2705)
+        if (pf_w) mk_prefetch_w(L.fc2);
         mk_attn_cross<WT>(a, sm, L);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // F: cross O + residual (2754-2766)
-        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv, 16); else if (a.want_logits) mk_prefetch_w(a.te, KS_LOG); }
-        mk_load_q<WT>(a, sm, a.actq, d);
-        MK_STAMP();
+        MK_SYNC();
+        // 8: cross O + residual (2754-2766)
         e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.co, e, 16, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // G: LN + FC1 + GELU (2770-2794) -> quantised rows for FC2 (a CTA owns 32-row pairs of tiles: one Q8_0 block per row)
-        mk_load_ln<WT>(a, sm, a.x, d, L.lnm_w, L.lnm_b);
-        MK_STAMP();
+        mk_gemv<WT>(a, sm, L.co, a.actq, e);
+        MK_SYNC();
+        // 9: LN -> quantised rows
+        mk_lnq<WT>(a, sm, a.x, d, L.lnm_w, L.lnm_b, a.actq);
+        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
+        MK_SYNC();
+        // 10: FC1 + GELU (2770-2794) -> quantised rows for FC2 (a CTA owns 32 consecutive outputs: one Q8_0 block per row)
         e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.outq = a.hq;
-        mk_gemv<WT>(a, sm, L.fc1, e, 8, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
-        // H: FC2 + residual (2797-2806)
-        mk_load_q<WT>(a, sm, a.hq, 4 * d);
-        MK_STAMP();
+        mk_gemv<WT>(a, sm, L.fc1, a.actq, e);
+        MK_SYNC();
+        // 11: FC2 + residual (2797-2806)
         e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.fc2, e, 16, round);
-        MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP();
+        mk_gemv<WT>(a, sm, L.fc2, a.hq, e);
+        MK_SYNC();
     }
     if (a.want_logits) {                                         // final LN + logits (2811-2827)
-        mk_load_ln<WT>(a, sm, a.x, d, a.lnf_w, a.lnf_b);
-        MK_STAMP();
+        mk_lnq<WT>(a, sm, a.x, d, a.lnf_w, a.lnf_b, a.actq);
+        MK_SYNC();
         MkEpi e; e.out = a.logits;
-        mk_gemv<WT>(a, sm, a.te, e, KS_LOG, round);
+        mk_gemv<WT>(a, sm, a.te, a.actq, e);
         MK_STAMP();
     }
 }
 
-int mk_barriers(int n_layer, bool) { return 8 * n_layer; }
+int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
-size_t mk_smem_bytes(int wtype, int d) {
-    const size_t KMAX = (size_t) 4 * d;
-    const size_t xq = (wtype == WT_F16) ? 8 * (KMAX * 2 + 16) : 8 * (KMAX + 16);
-    return xq + 8 * (KMAX / 32) * 4 + 2 * MK_RED * 4 + 2 * MK_WARPS * MK_PART * 4 + 32 * 4 + 16 * 4;
+size_t mk_smem_bytes(int, int) {
+    return (size_t) MK_MAXTOK * (MK_ROWB + 16) + (size_t) MK_MAXTOK * (MK_ROWB / 32) * 4 + (size_t) MK_RED * 4 + 2 * MK_WARPS * MK_PART * 4 + 32 * 4 + 16 * 4;
 }
+int mk_max_rows() { return MK_MAXTOK; }
 
 template <int WT, bool TRACE>
 static bool mk_launch_t(const MkArgs & a, int n_sm, cudaStream_t st) {

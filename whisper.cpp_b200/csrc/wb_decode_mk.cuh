@@ -25,9 +25,9 @@ struct MkArgs {
     float kq_scale, eps;
     QMat te; const float * pe;        // token embedding (also the logits matrix) and positional embedding
     const float * lnf_w, * lnf_b;     // final LayerNorm
-    float * x, * qkv, * q2, * logits;                         // f32 workspaces: [8][d], [8][3d], [8][d], [8][V]
-    uint8_t * actq, * hq;             // quantised rows handed from attention to O / from FC1 to FC2 (>= 8*d*4 and 8*4d*4 bytes)
-    float * xpart; int * xcnt;        // cross-attention chunk partials [8*H][n_chunks][66] and arrival counters [8*H]
+    float * x, * qkv, * q2, * logits;                         // f32 workspaces: [R][d], [R][3d], [R][d], [R][V]   (R = mk_max_rows())
+    uint8_t * actq, * hq;             // quantised rows handed between phases: K = d (>= R*d*2 + R*d/8 bytes) and K = 4d
+    float * xpart; int * xcnt;        // cross-attention partials [R*H][16][66] and arrival counters [R*H]
     unsigned long long * bar;         // grid barrier: [0] arrival counter (monotonic, never reset), [16 + 16*cta] release flag of each CTA
     unsigned long long bar_base;      // its value when this launch starts
     int * err;                        // set to 1 when a barrier wait times out
@@ -39,6 +39,7 @@ struct MkArgs {
 int  mk_barriers(int n_layer, bool want_logits);
 bool mk_supported(int wtype);
 size_t mk_smem_bytes(int wtype, int d);
+int  mk_max_rows();                 // rows (sequences x tokens) one launch can take
 // cooperative launch on `st`; grid = number of SMs.  Returns false (with the error set) when the launch is refused.
 bool mk_launch(const MkArgs & a, int wtype, int n_sm, cudaStream_t st);
 

@@ -53,14 +53,11 @@ bool Engine::init(const Model * model, int cap_windows) {
         !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || (!fused_attn && (!S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp))) ||
         !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d) || !kv_cross.alloc(B * 2 * Lt * Tp * d, true)) return false;
     if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
-    // decoder workspaces (8 rows per pass)
-    if (!dx.alloc(8 * d) || !dqkv.alloc(8 * 3 * d) || !dattn.alloc(8 * d) || !dq2.alloc(8 * d) || !dh.alloc(8 * 4 * d) ||
-        !dlogits.alloc((size_t) 8 * V) || !xpart.alloc((size_t) 8 * H * 32 * 66) || !xcnt.alloc((size_t) 8 * H, true)) return false;
-    if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
     {
         cudaDeviceProp prop; WB_CUDA_OK(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
-        use_mk = m->dec_tm;                   // the layout decides: tile-major decoder weights <=> persistent kernel
+        use_mk = m->dec_tm;
+        max_rows = use_mk ? mk_max_rows() : 8;                   // the layout decides: tile-major decoder weights <=> persistent kernel
         if (use_mk && (!mk_supported(m->wtype == WT_F32 ? WT_F16 : m->wtype) || mk_smem_bytes(m->wtype == WT_F32 ? WT_F16 : m->wtype, hp.n_text_state) > 200 * 1024 || !prop.cooperativeLaunch)) {
             set_error("decode: the persistent kernel cannot run on this device/model; set WB200_MEGAKERNEL=0"); return false;
         }
@@ -69,10 +66,15 @@ bool Engine::init(const Model * model, int cap_windows) {
         sm_ghz = prop.clockRate * 1e-6;
         if (const char * tp = getenv("WB200_MK_TRACE")) { if (use_mk && *tp) { mk_trace_path = tp; if (!mk_trace.alloc(4096, true)) return false; } }
     }
+    // decoder workspaces (max_rows rows per pass)
+    const size_t R = max_rows;
+    if (!dx.alloc(R * d) || !dqkv.alloc(R * 3 * d) || !dattn.alloc(R * d) || !dq2.alloc(R * d) || !dh.alloc(R * 4 * d) ||
+        !dlogits.alloc(R * V) || !xpart.alloc(R * H * 32 * 66) || !xcnt.alloc(R * H, true)) return false;
+    if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
-    WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) 8 * V * sizeof(float)));
-    WB_CUDA_OK(cudaMallocHost(&hsamp, 8 * sizeof(SampOut)));
-    if (!dsamp.alloc(8) || !samp_mask.alloc((size_t) (V + 31) / 32, true)) return false;
+    WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) max_rows * V * sizeof(float)));
+    WB_CUDA_OK(cudaMallocHost(&hsamp, max_rows * sizeof(SampOut)));
+    if (!dsamp.alloc(max_rows) || !samp_mask.alloc((size_t) (V + 31) / 32, true)) return false;
     return true;
 }
 
@@ -84,7 +86,7 @@ bool Engine::set_cells(int n) {
     const size_t e = (size_t) hp.n_text_layer * n * hp.n_text_state;
     if (!kv_k.alloc(e, true) || !kv_v.alloc(e, true)) return false;
     ld_idx = pad256(hp.n_text_ctx);          // a query attends to at most n_text_ctx positions
-    const size_t nints = 56 + (size_t) 8 * ld_idx;
+    const size_t nints = (size_t) max_rows * (7 + ld_idx);
     if (!dints.alloc(nints)) return false;
     if (hints) cudaFreeHost(hints);
     hints = nullptr;
@@ -94,30 +96,30 @@ bool Engine::set_cells(int n) {
 }
 
 void Engine::mk_trace_collect(int n_layer, bool logits) {
-    const int ns = 1 + 24 * n_layer + (logits ? 2 : 0);
+    const int ns = 1 + 22 * n_layer + (logits ? 3 : 0);
     std::vector<long long> h(ns);
     if (cudaMemcpy(h.data(), mk_trace.p, ns * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
-    if (mk_trace_sum.empty()) mk_trace_sum.assign(27, 0.0);
+    if (mk_trace_sum.empty()) mk_trace_sum.assign(26, 0.0);
     for (int l = 0; l < n_layer; ++l)
-        for (int k = 0; k < 24; ++k) mk_trace_sum[k] += (double) (h[1 + 24 * l + k] - h[24 * l + k]) / n_layer;
-    if (logits) { mk_trace_sum[24] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[25] += (double) (h[ns - 1] - h[ns - 2]); }
-    mk_trace_sum[26] += (double) (h[ns - 1] - h[0]);
+        for (int k = 0; k < 22; ++k) mk_trace_sum[k] += (double) (h[1 + 22 * l + k] - h[22 * l + k]) / n_layer;
+    if (logits) { mk_trace_sum[22] += (double) (h[ns - 3] - h[ns - 4]); mk_trace_sum[23] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[24] += (double) (h[ns - 1] - h[ns - 2]); }
+    mk_trace_sum[25] += (double) (h[ns - 1] - h[0]);
     ++mk_trace_n;
 }
 void Engine::mk_trace_dump() {
     if (mk_trace_path.empty() || !mk_trace_n) return;
     FILE * f = fopen(mk_trace_path.c_str(), "a");
     if (!f) return;
-    static const char * ph[8] = { "A ln+qkv", "B self-attn", "C o-proj", "D ln+cross-q", "E cross-attn", "F cross-o", "G ln+fc1", "H fc2" };
+    static const char * ph[11] = { "1 ln->q8", "2 qkv", "3 self-attn", "4 o-proj", "5 ln->q8", "6 cross-q", "7 cross-attn", "8 cross-o", "9 ln->q8", "10 fc1+gelu", "11 fc2" };
     const double us = 1e-3 / sm_ghz / (double) mk_trace_n;
-    fprintf(f, "# persistent decode kernel, CTA 0, average over %llu passes (us; SM clock %.3f GHz)\n", (unsigned long long) mk_trace_n, sm_ghz);
-    fprintf(f, "%-16s %10s %10s %10s\n", "phase (per layer)", "prologue", "main", "barrier");
+    fprintf(f, "# persistent decode kernel, CTA 0, average over %llu passes with logits (us; SM clock %.3f GHz)\n", (unsigned long long) mk_trace_n, sm_ghz);
+    fprintf(f, "%-16s %10s %10s\n", "phase (per layer)", "work", "barrier");
     double tot = 0.0;
-    for (int p = 0; p < 8; ++p) {
-        fprintf(f, "%-16s %10.2f %10.2f %10.2f\n", ph[p], mk_trace_sum[3*p] * us, mk_trace_sum[3*p + 1] * us, mk_trace_sum[3*p + 2] * us);
-        tot += (mk_trace_sum[3*p] + mk_trace_sum[3*p + 1] + mk_trace_sum[3*p + 2]) * us;
+    for (int p = 0; p < 11; ++p) {
+        fprintf(f, "%-16s %10.2f %10.2f\n", ph[p], mk_trace_sum[2*p] * us, mk_trace_sum[2*p + 1] * us);
+        tot += (mk_trace_sum[2*p] + mk_trace_sum[2*p + 1]) * us;
     }
-    fprintf(f, "layer total %.2f us; final ln %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[24] * us, mk_trace_sum[25] * us, mk_trace_sum[26] * us);
+    fprintf(f, "layer total %.2f us; final ln %.2f + barrier %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[22] * us, mk_trace_sum[23] * us, mk_trace_sum[24] * us, mk_trace_sum[25] * us);
     fclose(f);
 }
 
@@ -352,9 +354,10 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
     const int d = hp.n_text_state, H = hp.n_text_head, Lt = hp.n_text_layer, V = hp.n_vocab;
     const int Tp = Tp_max;                                         // kv_cross layout stride
     const float kq_scale = powf(64.0f, -0.25f);                    // whisper.cpp:2514
-    const size_t nint = 56 + (size_t) 8 * ld_idx;
+    const int R = max_rows;
+    const size_t nint = (size_t) 7 * R + (size_t) n * ld_idx;          // packed: tok | pos | cell | slot | n_kv | rowinfo[2] | idx rows
     WB_CUDA_OK(cudaMemcpyAsync(dints.p, hints, nint * sizeof(int), cudaMemcpyHostToDevice, st));
-    const int * d_tok = dints.p, * d_pos = dints.p + 8, * d_cell = dints.p + 16, * d_slot = dints.p + 24, * d_nkv = dints.p + 32, * d_row = dints.p + 40, * d_idx = dints.p + 56;
+    const int * d_tok = dints.p, * d_pos = dints.p + R, * d_cell = dints.p + 2 * R, * d_slot = dints.p + 3 * R, * d_nkv = dints.p + 4 * R, * d_row = dints.p + 5 * R, * d_idx = dints.p + 7 * R;
 
     dec_embed(m->d_te, m->d_pe, d_tok, d_pos, n, d, dx.p, st);
     if (use_mk) {
@@ -376,7 +379,7 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         }
         if (any_logits) { wbytes += (double) m->d_te.N * m->d_te.K * wt_bpw(m->d_te.type); flops += 2.0 * m->d_te.N * m->d_te.K * n; }
         double kvbytes = 0.0;
-        for (int j = 0; j < n; ++j) kvbytes += (double) Lt * 2.0 * d * 2.0 * ((double) n_keys + hints[32 + j]);
+        for (int j = 0; j < n; ++j) kvbytes += (double) Lt * 2.0 * d * 2.0 * ((double) n_keys + hints[4 * R + j]);
         flops += kvbytes;                                           // 2 flops per KV element (f16 = 2 bytes): same number
         ProfScope prof(PC_GEMV, st, wbytes + kvbytes, flops);
         if (!mk_launch(a, m->wtype == WT_F32 ? WT_F16 : m->wtype, n_sm, st)) return false;
@@ -422,9 +425,10 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
     const int n_keys = pad256(enc_n_ctx > 0 ? enc_n_ctx : hp.n_audio_ctx);
 
     const int64_t t_host0 = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    for (int r0 = 0; r0 < n_rows; r0 += 8) {
-        const int n = std::min(8, n_rows - r0);
-        int * h_tok = hints, * h_pos = hints + 8, * h_cell = hints + 16, * h_slot = hints + 24, * h_nkv = hints + 32, * h_row = hints + 40, * h_idx = hints + 56;
+    const int R = max_rows;
+    for (int r0 = 0; r0 < n_rows; r0 += R) {
+        const int n = std::min(R, n_rows - r0);
+        int * h_tok = hints, * h_pos = hints + R, * h_cell = hints + 2 * R, * h_slot = hints + 3 * R, * h_nkv = hints + 4 * R, * h_row = hints + 5 * R, * h_idx = hints + 7 * R;
         bool any_logits = false;
         for (int j = 0; j < n; ++j) {
             const DecToken & t = rows[r0 + j];
@@ -437,12 +441,12 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
             memcpy(h_idx + (size_t) j * ld_idx, kv_idx + (size_t) (r0 + j) * ld, (size_t) n_kv[r0 + j] * sizeof(int));
             any_logits |= t.want_logits;
         }
-        count_h2d((56 + (size_t) 8 * ld_idx) * sizeof(int));
+        count_h2d(((size_t) 7 * R + (size_t) n * ld_idx) * sizeof(int));
         if (any_logits) count_d2h(samp ? (uint64_t) n * sizeof(SampOut) : (uint64_t) n * V * 4);
 
         // One pass = 8 kernels per text layer.  After the second use of a shape the chain is replayed as a CUDA graph
         // (all per-step values live in `dints`, so kernel arguments never change between steps).
-        uint64_t key = (uint64_t) (n | (any_logits ? 16 : 0) | (samp ? 32 : 0)) | ((uint64_t) n_keys << 8);
+        uint64_t key = (uint64_t) (n | (any_logits ? 128 : 0) | (samp ? 256 : 0)) | ((uint64_t) n_keys << 10);
         if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
         StepGraph * sg = (use_graphs && !use_mk && !prof_enabled()) ? &graphs[key] : nullptr;
         WB_CUDA_OK(cudaEventRecord(ev[5], st));

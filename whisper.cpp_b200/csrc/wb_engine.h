@@ -64,6 +64,7 @@ struct Engine {
     bool gemv_v2 = true;             // WB200_GEMV_V1=1 selects the dp4a kernel
     // persistent decode kernel (wb_decode_mk.cu); WB200_MEGAKERNEL=0 selects the kernel-per-op chain
     bool use_mk = false;
+    int  max_rows = 8;               // rows per decode pass: 64 with the persistent kernel, 8 with the chain
     int  n_sm = 0, mk_prefetch = 1;
     DevBuf<MkLayer> mk_layers;
     DevBuf<unsigned long long> mk_bar;   // [0] arrival counter, [8] error flag, [16 + 16*cta] release flags
@@ -98,9 +99,9 @@ struct Engine {
     // encode `n_win` windows in one batched pass; window w reads srcs[w].mel at frame srcs[w].seek and fills cross-KV slot srcs[w].slot
     bool encode(const EncSrc * srcs, int n_win, int n_ctx);
 
-    // decode a batch (<= 8 rows per pass internally).  idx lists: for row j, cells[j] is where its K/V go and
+    // decode a batch (<= max_rows rows per pass internally).  idx lists: for row j, cells[j] is where its K/V go and
     // (kv_idx[j*ld .. +n_kv[j]]) the cells it attends to.  logits_out[j]: host buffer of n_vocab floats for rows with want_logits.
-    bool decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampCfg * samp);   // the kernel chain of one pass (<= 8 rows) on `st`
+    bool decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampCfg * samp);   // the kernels of one pass (<= max_rows rows) on `st`
     // samp != nullptr: logits stay on the device; the filter + greedy pick run there (rowinfo: 2 ints per row, samp_out: host [n_rows])
     bool decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
                 const SampCfg * samp = nullptr, const int * rowinfo = nullptr, SampOut * samp_out = nullptr);

@@ -739,15 +739,15 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
     return ret;
 }
 
-// Independent PCM buffers on one device, decoded in LOCK-STEP: up to 8 member states share one engine (one batched encoder
+// Independent PCM buffers on one device, decoded in LOCK-STEP: up to 64 member states share one engine (one batched encoder
 // pass for all windows, one batched decode step for all live sequences -- weights are read once per step).  Chunk i's
 // segments are returned in states_out[i] (result-only states; free with whisper_free_state).  Chunk semantics are those
 // of whisper_full_with_state.  flags bit 0: `samples[i]` are DEVICE pointers (PCM already resident in HBM).
 WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
                                   const int * n_samples, int n_chunks, struct whisper_state ** states_out, int flags) {
     if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
-    int S = 8;
-    if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(8, atoi(e)));
+    int S = ctx->model.dec_tm ? 64 : 8;          // concurrent sequences: one row each in the decode pass (64 rows per launch of the persistent kernel)
+    if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));
     S = std::min(S, n_chunks);
     std::lock_guard<std::mutex> batch_lock(ctx->batch_mu);
     const int member_decoders = 5;                                    // enough for best_of / beam_size up to 5
