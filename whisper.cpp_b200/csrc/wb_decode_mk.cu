@@ -24,21 +24,29 @@
 #include "wb_decode_mk.cuh"
 #include "wb_common.h"
 #include "wb_dev.cuh"
+#include "wb_ptx.cuh"
 
 namespace wb {
 
 constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 16 * 16 * MK_REDLD, MK_PART = 68, MK_XSLOTS = 16;
 constexpr int MK_ROWB = 1280;            // bytes of one staged activation row chunk (1280 int8 values or 640 halves)
 
-struct MkSm {
-    uint32_t * xq;      // staged chunk of the quantised activations: [64 rows][SW] words (int8x4 or half2)
-    float * xd;         // Q8_0 block scales of the chunk [64][chunk/32]
-    float * red;        // [16 warps][16 rows][65]  split-K partials of a tile pair
-    float * part;       // [2][16 warps][68]          attention warp partials: m, l, -, -, o[64]
-    float * stat;       // [32] LayerNorm partial sums
-    int   * flag;       // [4]
-    int SW;
-};
+// dynamic shared memory, fixed carve-up (every phase function addresses it directly: pointers handed through a struct in
+// local memory turned every access into a generic load)
+extern __shared__ __align__(16) uint8_t mk_smem[];
+constexpr int MK_OFF_XQ   = 0;                                                   // staged activation rows [64][SW words]
+constexpr int MK_OFF_XD   = MK_OFF_XQ + MK_MAXTOK * (MK_ROWB + 16);              // their Q8_0 block scales [64][chunk/32]
+constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [16 warps][16 rows][65]
+constexpr int MK_OFF_PART = MK_OFF_RED + MK_RED * 4;                             // attention warp partials [2][16][68]: m, l, -, -, o[64]
+constexpr int MK_OFF_STAT = MK_OFF_PART + 2 * MK_WARPS * MK_PART * 4;            // LayerNorm partial sums [32]
+constexpr int MK_OFF_FLAG = MK_OFF_STAT + 32 * 4;                                // [16] ints
+constexpr int MK_SMEM     = MK_OFF_FLAG + 16 * 4;
+#define SM_XQ   (reinterpret_cast<uint32_t *>(mk_smem + MK_OFF_XQ))
+#define SM_XD   (reinterpret_cast<float *>(mk_smem + MK_OFF_XD))
+#define SM_RED  (reinterpret_cast<float *>(mk_smem + MK_OFF_RED))
+#define SM_PART (reinterpret_cast<float *>(mk_smem + MK_OFF_PART))
+#define SM_STAT (reinterpret_cast<float *>(mk_smem + MK_OFF_STAT))
+#define SM_FLAG (reinterpret_cast<int *>(mk_smem + MK_OFF_FLAG))
 
 #define MK_STAMP() do { if (TRACE) { if (blockIdx.x == 0 && threadIdx.x == 0) a.trace[n_stamp] = clock64(); ++n_stamp; } } while (0)
 
@@ -49,16 +57,16 @@ __device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.syn
 
 // Grid barrier.  Arrival = one atomic on a counter; the LAST CTA to arrive releases everybody by writing one flag per CTA
 // (each on its own 128-byte line), and every other CTA polls only its own flag.
-__device__ __noinline__ void mk_grid_sync(const MkArgs & a, MkSm & sm, unsigned long long target) {
+__device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(a.bar, 1ULL);
         __threadfence();
-        sm.flag[2] = (old + 1 == target);
+        SM_FLAG[2] = (old + 1 == target);
     }
     __syncthreads();
-    if (sm.flag[2]) {
+    if (SM_FLAG[2]) {
         if (threadIdx.x < gridDim.x)
             asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 + 16 * threadIdx.x), "l"(target) : "memory");
     } else if (threadIdx.x == 0) {
@@ -93,23 +101,23 @@ __device__ __forceinline__ void mk_store_q(uint8_t * dst, int K, int t, int e0, 
 // LayerNorm (ggml-cpu/ops.cpp:3698-3765, two passes, then mul/add whisper.cpp:2536-2543) of the f32 residual rows, quantised into
 // `dst`.  Distributed: CTA r normalises row r (one warp per 128 values); followed by a grid barrier.
 template <int WT>
-__device__ __noinline__ void mk_lnq(const MkArgs & a, MkSm & sm, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
+__device__ __noinline__ void mk_lnq(const MkArgs & a, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int row = blockIdx.x; row < a.n_tok; row += gridDim.x) {
         const bool act = warp < (K >> 7);
         const int e0 = warp * 128 + lane * 4;
         float4 v = act ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         float s = warp_sum((v.x + v.y) + (v.z + v.w));
-        if (lane == 0) sm.stat[warp] = s;
+        if (lane == 0) SM_STAT[warp] = s;
         __syncthreads();
-        s = (lane < MK_WARPS) ? sm.stat[lane] : 0.0f;
+        s = (lane < MK_WARPS) ? SM_STAT[lane] : 0.0f;
         const float mean = warp_sum(s) / K;
         float q = 0.0f;
         if (act) { v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean; q = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w); }
         q = warp_sum(q);
-        if (lane == 0) sm.stat[16 + warp] = q;
+        if (lane == 0) SM_STAT[16 + warp] = q;
         __syncthreads();
-        q = (lane < MK_WARPS) ? sm.stat[16 + lane] : 0.0f;
+        q = (lane < MK_WARPS) ? SM_STAT[16 + lane] : 0.0f;
         const float rstd = 1.0f / sqrtf(warp_sum(q) / K + a.eps);
         if (act) {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w + e0)), b = __ldg(reinterpret_cast<const float4 *>(ln_b + e0));
@@ -137,85 +145,112 @@ __device__ __noinline__ void mk_lnq(const MkArgs & a, MkSm & sm, const float * s
     }
 }
 
-// stage chunk `kc` (MK_ROWB bytes per row at most) of the quantised rows in shared memory.  Warp w copies rows w, w+16, ...
+// quantise f32 rows (no LayerNorm) into the actq format: one warp per (row, 128 values); followed by a grid barrier
 template <int WT>
-__device__ __noinline__ void mk_load_chunk(const MkArgs & a, MkSm & sm, const uint8_t * src, int K, int kc, int KCe) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rowb = (WT == WT_F16) ? K * 2 : K, chb = (WT == WT_F16) ? KCe * 2 : KCe, cpr = chb >> 4, SW = (chb >> 2) + 4;
-    __syncthreads();                                             // the previous users of the staging buffer are done
-    sm.SW = SW;
-    uint4 v[4][3];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int t = warp + 16 * i, cc = lane + 32 * j;
-            if (t < a.n_tok && cc < cpr) v[i][j] = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t) t * rowb + (size_t) kc * chb) + cc);
+__device__ __noinline__ void mk_q8_rows(const MkArgs & a, const float * src, int K, uint8_t * dst) {
+    const int lane = threadIdx.x & 31, wg = blockIdx.x * MK_WARPS + (threadIdx.x >> 5), nwg = gridDim.x * MK_WARPS;
+    const int cpr = K >> 7;
+    int row = wg / cpr, ch = wg - row * cpr;
+    const int drow = nwg / cpr, dch = nwg - drow * cpr;
+    for (; row < a.n_tok; ) {
+        const int e0 = ch * 128 + lane * 4;
+        const float4 y = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0));
+        if (WT == WT_F16) {
+            const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + (size_t) row * K + e0) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        } else {
+            float amax = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
+            const uint32_t q0 = (uint32_t) __float2int_rn(y.x * id) & 0xffu, q1 = (uint32_t) __float2int_rn(y.y * id) & 0xffu;
+            const uint32_t q2 = (uint32_t) __float2int_rn(y.z * id) & 0xffu, q3 = (uint32_t) __float2int_rn(y.w * id) & 0xffu;
+            *reinterpret_cast<uint32_t *>(dst + (size_t) row * K + e0) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            if ((lane & 7) == 0) reinterpret_cast<float *>(dst + (size_t) MK_MAXTOK * K)[row * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
         }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int t = warp + 16 * i, cc = lane + 32 * j;
-            if (t < a.n_tok && cc < cpr) *reinterpret_cast<uint4 *>(sm.xq + t * SW + cc * 4) = v[i][j];
-        }
-    if (WT != WT_F16) {
-        const int nbc = KCe >> 5;                                // scales of the chunk: [row][nbc]
-        const float * sc = reinterpret_cast<const float *>(src + (size_t) MK_MAXTOK * K) + kc * nbc;
-        for (int i = threadIdx.x; i < a.n_tok * 64; i += MK_THREADS) {
-            const int t = i >> 6, bl = i & 63;
-            if (bl < nbc) sm.xd[t * nbc + bl] = __ldcg(sc + (size_t) t * (K >> 5) + bl);
-        }
+        row += drow; ch += dch; if (ch >= cpr) { ch -= cpr; ++row; }
     }
-    __syncthreads();
+}
+
+// stage chunk `kc` (MK_ROWB bytes per row at most) of the quantised rows in shared memory: one TMA bulk copy per row (and one
+// for its block scales) into the padded row layout, completion through an mbarrier.  (Copying through registers was limited by
+// the outstanding-miss capacity of the LSU: 7 us for 83 KB.)
+__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#define SM_MBAR (reinterpret_cast<uint64_t *>(mk_smem + MK_OFF_FLAG + 32))
+
+template <int WT>
+__device__ __forceinline__ void mk_load_chunk(const MkArgs & a, const uint8_t * src, int K, int kc, int KCe) {
+    const int tid = threadIdx.x;
+    const int rowb = (WT == WT_F16) ? K * 2 : K, chb = (WT == WT_F16) ? KCe * 2 : KCe, SW = (chb >> 2) + 4;
+    const int nbc = KCe >> 5;
+    const int ph = SM_FLAG[4];                                   // staging round (mbarrier phase parity)
+    __syncthreads();                                             // everybody has read `ph`; the previous users of the buffer are done
+    if (tid == 0) {
+        SM_FLAG[4] = ph + 1;
+        mbar_arrive_expect_tx(SM_MBAR, (uint32_t) a.n_tok * (uint32_t) (chb + (WT == WT_F16 ? 0 : nbc * 4)));
+    }
+    if (tid < a.n_tok) {
+        asm volatile("fence.proxy.async;" ::: "memory");         // rows were written with ordinary stores (by other CTAs, before the grid barrier)
+        bulk_g2s(SM_XQ + tid * SW, src + (size_t) tid * rowb + (size_t) kc * chb, (uint32_t) chb, SM_MBAR);
+        if (WT != WT_F16)
+            bulk_g2s(SM_XD + tid * nbc, reinterpret_cast<const float *>(src + (size_t) MK_MAXTOK * K) + (size_t) tid * (K >> 5) + kc * nbc, (uint32_t) nbc * 4, SM_MBAR);
+    }
+    mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
 }
 
 struct MkEpi {
+    int tag = 0;                         // != 0: CTA 0 records fine-grained stamps of this call into trace[3000 + 8*tag ..]
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
     uint8_t * outq = nullptr;            // quantised output rows (actq format) for the next GEMV
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
 };
 
-// L2 prefetch of the tile pairs this CTA will own in a later GEMV phase (tile-major: the records of a tile are contiguous)
+// L2 prefetch of the tiles this CTA will own in a later GEMV phase (tile-major: the records of a tile are contiguous)
 __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
     if (threadIdx.x != MK_THREADS - 32) return;
     const int n_tiles = (W.N + 15) >> 4;
     const uint32_t tile_bytes = (uint32_t) (W.K / wt_tm_rec_k(W.type)) * wt_tm_rec_bytes(W.type);
-    for (int tile0 = blockIdx.x * 2; tile0 < n_tiles; tile0 += gridDim.x * 2)
-        l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile0 * tile_bytes, tile_bytes * (uint32_t) min(2, n_tiles - tile0));
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * tile_bytes, tile_bytes);
 }
 
-// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n] for the tile PAIRS (32 output rows) owned by this CTA.
-// Warp w: tile (w >> 3) of the pair, k-slice (w & 7); it multiplies its weight blocks with ALL rows (8 per MMA, <= 8 MMAs per block),
-// so a weight block is decoded once for up to 64 sequences.  x: quantised rows in global memory (actq format).
+// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n] for the 16-row tiles owned by this CTA (round-robin).
+// The 16 warps split K; each multiplies its weight blocks with ALL rows (8 per MMA, <= 8 MMAs per block), so a weight block is
+// decoded once for up to 64 sequences.  x: quantised rows in global memory (actq format).
 template <int WT>
-__device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W, const uint8_t * x, const MkEpi & e) {
+__device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
     constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
     constexpr int UB = 3;                                        // records whose loads are issued together
     const int N = W.N, K = W.K, n_tok = a.n_tok, NG = (n_tok + 7) >> 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
-    const int tsel = warp >> 3, ks = warp & 7;
-    const int n_tiles = (N + 15) >> 4, n_pairs = (n_tiles + 1) >> 1, nrec = K / RK;
+    const int ks = warp;
+    const int n_tiles = (N + 15) >> 4, nrec = K / RK;
     const int KCe = (WT == WT_F16 && a.d > 640) ? (a.d >> 1) : a.d;   // activation chunk staged in smem (K is d or 4d)
     const int nchunks = K / KCe, rpc = KCe / RK, nbc = KCe >> 5;
+    const int SW = (((WT == WT_F16) ? KCe * 2 : KCe) >> 2) + 4;  // words per staged row
     bool staged = false;
-    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-        const int tile = pr * 2 + tsel;
+    const bool fs = a.trace && e.tag && blockIdx.x == 0 && tid == 0;
+    if (fs) a.trace[3000 + 8 * e.tag] = clock64();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         float acc[8][4];
 #pragma unroll
         for (int gi = 0; gi < 8; ++gi) { acc[gi][0] = acc[gi][1] = acc[gi][2] = acc[gi][3] = 0.0f; }
         for (int kc = 0; kc < nchunks; ++kc) {
-            if (nchunks > 1 || !staged) { mk_load_chunk<WT>(a, sm, x, K, kc, KCe); staged = true; }
-            const int SW = sm.SW;
-            if (tile < n_tiles) {
+            if (nchunks > 1 || !staged) { mk_load_chunk<WT>(a, x, K, kc, KCe); staged = true; }
+            if (fs && kc == 0) a.trace[3000 + 8 * e.tag + 1] = clock64();
+            {
                 const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + ((size_t) tile * nrec + (size_t) kc * rpc) * REC;
-                for (int kb = ks; kb < rpc; kb += 8 * UB) {
+                for (int kb = ks; kb < rpc; kb += MK_WARPS * UB) {
                     uint4 wq[UB]; uint2 wh[UB]; uint32_t wd[UB];
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
-                        const uint8_t * rec = tb + (size_t) min(kb + u * 8, rpc - 1) * REC;
+                        const uint8_t * rec = tb + (size_t) min(kb + u * MK_WARPS, rpc - 1) * REC;
                         if (WT == WT_F16 || WT == WT_Q8_0) wq[u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
                         else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[u].x = q2.x; wq[u].y = q2.y; }
                         if (WT == WT_Q5_0) wh[u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
@@ -223,7 +258,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
-                        const int bl = kb + u * 8;               // record within the chunk
+                        const int bl = kb + u * MK_WARPS;        // record within the chunk
                         if (bl < rpc) {
                             uint32_t af[4];
                             float dw0 = 0.0f, dw1 = 0.0f;
@@ -249,11 +284,11 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W
                                 if (gi < NG) {
                                     const int tb_ = gi * 8 + g;
                                     const bool ok = tb_ < n_tok;
-                                    const uint32_t b0 = ok ? sm.xq[tb_ * SW + bl * 8 + c] : 0u, b1 = ok ? sm.xq[tb_ * SW + bl * 8 + 4 + c] : 0u;
+                                    const uint32_t b0 = ok ? SM_XQ[tb_ * SW + bl * 8 + c] : 0u, b1 = ok ? SM_XQ[tb_ * SW + bl * 8 + 4 + c] : 0u;
                                     if (WT == WT_F16) mma_f16_16816(acc[gi], af, b0, b1);
                                     else {
                                         int dd[4]; mma_s8_16832(dd, af, b0, b1);
-                                        const float dx0 = sm.xd[min(gi * 8 + 2 * c, n_tok - 1) * nbc + bl], dx1 = sm.xd[min(gi * 8 + 2 * c + 1, n_tok - 1) * nbc + bl];
+                                        const float dx0 = SM_XD[min(gi * 8 + 2 * c, n_tok - 1) * nbc + bl], dx1 = SM_XD[min(gi * 8 + 2 * c + 1, n_tok - 1) * nbc + bl];
                                         acc[gi][0] = fmaf(dw0 * dx0, (float) dd[0], acc[gi][0]);
                                         acc[gi][1] = fmaf(dw0 * dx1, (float) dd[1], acc[gi][1]);
                                         acc[gi][2] = fmaf(dw1 * dx0, (float) dd[2], acc[gi][2]);
@@ -266,51 +301,70 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, MkSm & sm, const QMat & W
                 }
             }
         }
+        if (fs) a.trace[3000 + 8 * e.tag + 2] = clock64();
         // split-K partials -> smem: red[warp][row][token]
 #pragma unroll
         for (int gi = 0; gi < 8; ++gi)
             if (gi < NG) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sm.red[(warp * 16 + g + (i >> 1) * 8) * MK_REDLD + gi * 8 + 2 * c + (i & 1)] = acc[gi][i];
+                for (int i = 0; i < 4; ++i) SM_RED[(warp * 16 + g + (i >> 1) * 8) * MK_REDLD + gi * 8 + 2 * c + (i & 1)] = acc[gi][i];
             }
         __syncthreads();
-        // epilogue: one warp = the 32 rows of the pair for one batch row (one Q8_0 block when the output is handed on quantised)
-        for (int o = tid; o < 32 * NG * 8; o += MK_THREADS) {
-            const int r32 = o & 31, t = o >> 5, tl2 = r32 >> 4, rl = r32 & 15;
-            const int row = pr * 32 + r32;
-            if (t < n_tok && row < N) {
-                float v = 0.0f;
+        if (fs) a.trace[3000 + 8 * e.tag + 3] = clock64();
+        // epilogue: half a warp = the 16 rows of the tile for one batch row; two outputs per thread with their loads issued together
+        for (int o0 = tid; o0 < 16 * NG * 8; o0 += 2 * MK_THREADS) {
+            float bias[2], scl[2], res[2]; bool ok[2]; int rowv[2], tv[2];
 #pragma unroll
-                for (int w = 0; w < 8; ++w) v += sm.red[((tl2 * 8 + w) * 16 + rl) * MK_REDLD + t];
-                v = (v + (e.bias ? __ldg(e.bias + row) : 0.0f)) * (e.scale ? __ldg(e.scale + row) : 1.0f);
-                if (e.act == 1) v = gelu_ref_f16(v);
-                if (e.res) v += __ldcg(e.res + (size_t) t * N + row);
-                if (e.out) e.out[(size_t) t * N + row] = v;
-                if (e.outq) mk_store_q<WT>(e.outq, N, t, row & ~31, lane, v);
-                if (e.kc && row >= e.kv_d) {
-                    const size_t cell = a.cell[t];
-                    if (row < 2 * e.kv_d) e.kc[cell * e.kv_d + (row - e.kv_d)] = __float2half_rn(v);
-                    else                  e.vc[cell * e.kv_d + (row - 2 * e.kv_d)] = __float2half_rn(v);
+            for (int k = 0; k < 2; ++k) {
+                const int o = o0 + k * MK_THREADS;
+                tv[k] = o >> 4; rowv[k] = tile * 16 + (o & 15);
+                ok[k] = tv[k] < n_tok && rowv[k] < N;
+                bias[k] = (ok[k] && e.bias) ? __ldg(e.bias + rowv[k]) : 0.0f;
+                scl[k]  = (ok[k] && e.scale) ? __ldg(e.scale + rowv[k]) : 1.0f;
+                res[k]  = (ok[k] && e.res) ? __ldcg(e.res + (size_t) tv[k] * N + rowv[k]) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (ok[k]) {
+                    const int rl = rowv[k] & 15, t = tv[k], row = rowv[k];
+                    float v = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < MK_WARPS; ++w) v += SM_RED[(w * 16 + rl) * MK_REDLD + t];
+                    v = (v + bias[k]) * scl[k];
+                    if (e.act == 1) v = gelu_ref_f16(v);
+                    v += res[k];
+                    if (e.out) e.out[(size_t) t * N + row] = v;
+                    if (e.kc && row >= e.kv_d) {
+                        const size_t cell = a.cell[t];
+                        if (row < 2 * e.kv_d) e.kc[cell * e.kv_d + (row - e.kv_d)] = __float2half_rn(v);
+                        else                  e.vc[cell * e.kv_d + (row - 2 * e.kv_d)] = __float2half_rn(v);
+                    }
                 }
             }
         }
-        __syncthreads();                                         // red[] is rewritten by the next pair
+        if (fs) a.trace[3000 + 8 * e.tag + 4] = clock64();
+        __syncthreads();                                         // red[] is rewritten by the next tile
     }
 }
 
 // ---- attention -----------------------------------------------------------------------------------------------------------
 // the 16 query values of this lane's quarter of head h of row t, rounded to f16 (ggml_flash_attn_ext converts Q to f16:
 // ggml-cpu/ops.cpp:8560-8571)
-__device__ __forceinline__ void load_q16(const float * q, float (&qv)[16]) {
+// Lane quarter r of a key owns dims {8r..8r+7} and {32+8r..32+8r+7} of the head: the 4 lanes of a key then cover 64 contiguous
+// bytes per load instruction (whole 32-byte sectors; 16 dims in a row per lane would use half of every sector it touches).
+__device__ __forceinline__ void load_q16(const float * qh, int r, float (&qv)[16]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(q) + i);
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(qh + 8 * r + (i >> 1) * 32) + (i & 1));
         qv[4 * i]     = __half2float(__float2half_rn(v.x)); qv[4 * i + 1] = __half2float(__float2half_rn(v.y));
         qv[4 * i + 2] = __half2float(__float2half_rn(v.z)); qv[4 * i + 3] = __half2float(__float2half_rn(v.w));
     }
 }
 
-struct KVFrag { uint4 k0, k1; uint32_t v[8]; };
+// One lane owns one key per step: it holds 16 of the 64 dims of that key's K and V rows (the 4 lanes of a key share the score) and
+// keeps its OWN running max / sum / output over the keys it has seen -- no cross-lane traffic per key beyond the 2-step score
+// reduction.  The 8 key slots of a warp are merged once at the end (warp_merge), the warps of a CTA through shared memory.
+struct KV4 { uint4 k0, k1, v0, v1; };
 
 __device__ __forceinline__ float dot16(const uint4 & k0, const uint4 & k1, const float (&q)[16]) {
     float s = 0.0f;
@@ -323,25 +377,54 @@ __device__ __forceinline__ float dot16(const uint4 & k0, const uint4 & k1, const
     return s;
 }
 
-// one 8-key group of a warp: online-softmax update of (m, l, o0, o1).  sc: this lane's key score (-inf = masked), v: the 8 value rows
-__device__ __forceinline__ void attn_update(float sc, const uint32_t (&v)[8], float & m, float & l, float & o0, float & o1) {
-    float mg = sc;
-    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 4));
-    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 8));
-    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 16));
-    const float mn = fmaxf(m, mg);                               // finite: at least one key of the group is valid
-    const float resc = __expf(m - mn);
-    const float pk = __expf(sc - mn);                            // exp(-inf) = 0 for masked keys
-    float ps = pk;
-    ps += __shfl_xor_sync(0xffffffffu, ps, 4);
-    ps += __shfl_xor_sync(0xffffffffu, ps, 8);
-    ps += __shfl_xor_sync(0xffffffffu, ps, 16);
-    l = l * resc + ps; o0 *= resc; o1 *= resc; m = mn;
+__device__ __forceinline__ float dot16s(const uint4 & k0, const uint4 & k1, const float * q) {   // q: 16 floats in shared memory
+    float s = 0.0f;
+    const __half2 * h0 = reinterpret_cast<const __half2 *>(&k0), * h1 = reinterpret_cast<const __half2 *>(&k1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float pi = __shfl_sync(0xffffffffu, pk, 4 * i);
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v[i]));
-        o0 = fmaf(pi, f.x, o0); o1 = fmaf(pi, f.y, o1);
+    for (int i = 0; i < 4; i += 2) {
+        const float4 qa = *reinterpret_cast<const float4 *>(q + 2 * i), qb = *reinterpret_cast<const float4 *>(q + 8 + 2 * i);
+        const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h0[i + 1]), g0 = __half22float2(h1[i]), g1 = __half22float2(h1[i + 1]);
+        s = fmaf(f0.x, qa.x, s); s = fmaf(f0.y, qa.y, s); s = fmaf(f1.x, qa.z, s); s = fmaf(f1.y, qa.w, s);
+        s = fmaf(g0.x, qb.x, s); s = fmaf(g0.y, qb.y, s); s = fmaf(g1.x, qb.z, s); s = fmaf(g1.y, qb.w, s);
+    }
+    return s;
+}
+
+struct LaneAcc { float m, l, o[16]; };
+__device__ __forceinline__ void lane_init(LaneAcc & A) { A.m = -INFINITY; A.l = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A.o[i] = 0.0f; }
+
+// sc: score of this lane's key (already reduced over the 4 lanes of the key and scaled); masked keys must not call this
+__device__ __forceinline__ void lane_update(LaneAcc & A, float sc, const uint4 & v0, const uint4 & v1) {
+    const float mn = fmaxf(A.m, sc);
+    const float resc = __expf(A.m - mn), p = __expf(sc - mn);
+    A.l = fmaf(A.l, resc, p); A.m = mn;
+    const __half2 * h0 = reinterpret_cast<const __half2 *>(&v0), * h1 = reinterpret_cast<const __half2 *>(&v1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h0[i]), f2 = __half22float2(h1[i]);
+        A.o[2 * i]     = fmaf(A.o[2 * i],     resc, p * f.x);  A.o[2 * i + 1] = fmaf(A.o[2 * i + 1], resc, p * f.y);
+        A.o[8 + 2 * i] = fmaf(A.o[8 + 2 * i], resc, p * f2.x); A.o[9 + 2 * i] = fmaf(A.o[9 + 2 * i], resc, p * f2.y);
+    }
+}
+// merge the 8 key slots of the warp (lanes with equal lane & 3); afterwards every lane holds the warp totals of its quarter
+__device__ __forceinline__ void warp_merge(LaneAcc & A) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, A.m, off), l2 = __shfl_xor_sync(0xffffffffu, A.l, off);
+        const float mn = fmaxf(A.m, m2);
+        const float w1 = (A.m > -INFINITY) ? __expf(A.m - mn) : 0.0f, w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.0f;
+        A.l = A.l * w1 + l2 * w2; A.m = mn;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float o2 = __shfl_xor_sync(0xffffffffu, A.o[i], off); A.o[i] = A.o[i] * w1 + o2 * w2; }
+    }
+}
+__device__ __forceinline__ void part_store(float * part, const LaneAcc & A, int lane) {    // lanes 0..3 write the warp partial
+    if (lane < 4) {
+        if (lane == 0) { part[0] = A.m; part[1] = A.l; }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(part + 4 + lane * 8 + (i >> 3) * 32 + (i & 7)) = make_float4(A.o[i], A.o[i + 1], A.o[i + 2], A.o[i + 3]);
     }
 }
 
@@ -362,7 +445,7 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
 
 // self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); each half of the CTA (8 warps) takes one.
 template <int WT>
-__device__ __noinline__ void mk_attn_self(const MkArgs & a, MkSm & sm, const MkLayer & L) {
+__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp >> 3, hw = warp & 7;
     const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
     const int kslot = lane >> 2, r = lane & 3;
@@ -371,128 +454,154 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, MkSm & sm, const MkL
         const int nk = a.nkv[t];
         const int * cells = a.idx + (size_t) t * a.ld_idx;
         float q[16];
-        load_q16(a.qkv + (size_t) t * 3 * d + h * 64 + r * 16, q);
-        float m = -INFINITY, l = 0.0f, o0 = 0.0f, o1 = 0.0f;
+        load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
+        LaneAcc A; lane_init(A);
         for (int k0 = hw * 8; k0 < nk; k0 += 64) {
             const bool ok = k0 + kslot < nk;
-            const int cell = ok ? cells[k0 + kslot] : 0;
-            uint4 ka = make_uint4(0, 0, 0, 0), kb = ka;
-            if (ok) { const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + (size_t) cell * d + h * 64 + r * 16); ka = __ldcg(kp); kb = __ldcg(kp + 1); }
-            uint32_t vv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int ci = __shfl_sync(0xffffffffu, cell, 4 * i);
-                vv[i] = (k0 + i < nk) ? __ldcg(reinterpret_cast<const uint32_t *>(L.vc + (size_t) ci * d + h * 64) + lane) : 0u;
+            KV4 f;
+            f.k0 = f.k1 = f.v0 = f.v1 = make_uint4(0, 0, 0, 0);
+            if (ok) {
+                const size_t off = (size_t) cells[k0 + kslot] * d + h * 64 + r * 8;
+                const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
+                f.k0 = __ldcg(kp); f.k1 = __ldcg(kp + 4); f.v0 = __ldcg(vp); f.v1 = __ldcg(vp + 4);
             }
-            float sc = dot16(ka, kb, q);
+            float sc = dot16(f.k0, f.k1, q);
             sc += __shfl_xor_sync(0xffffffffu, sc, 1);
             sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            attn_update(ok ? sc : -INFINITY, vv, m, l, o0, o1);
+            if (ok) lane_update(A, sc, f.v0, f.v1);
         }
-        float * part = sm.part + (half * 8 + hw) * MK_PART;
-        if (lane == 0) { part[0] = m; part[1] = l; }
-        *reinterpret_cast<float2 *>(part + 4 + 2 * lane) = make_float2(o0, o1);
+        warp_merge(A);
+        part_store(SM_PART + (half * 8 + hw) * MK_PART, A, lane);
         bar_named(1 + half, 256);
         if (hw < 2) {
             float M, Lsum;
-            const float o = attn_merge(sm.part + half * 8 * MK_PART, 8, hw * 32 + lane, M, Lsum);
+            const float o = attn_merge(SM_PART + half * 8 * MK_PART, 8, hw * 32 + lane, M, Lsum);
             mk_store_q<WT>(a.actq, d, t, h * 64 + hw * 32, lane, (Lsum > 0.0f) ? __fdividef(o, Lsum) : 0.0f);
         }
         bar_named(1 + half, 256);
     }
 }
 
-__device__ __forceinline__ void xkv_load(KVFrag & f, const __half * __restrict__ kb, const __half * __restrict__ vb, int d, int lane) {
-    const uint4 * kp = reinterpret_cast<const uint4 *>(kb + (size_t) (lane >> 2) * d + (lane & 3) * 16);
-    f.k0 = __ldg(kp); f.k1 = __ldg(kp + 1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f.v[i] = __ldg(reinterpret_cast<const uint32_t *>(vb + (size_t) i * d) + lane);
-}
-
 // cross-attention over the n_keys padded encoder positions, zero rows included (whisper.cpp:2688-2705).
 // Work unit = (row, head, half of the keys).  Units are dealt out in contiguous ranges; a CTA walks a unit in chunks of 128 keys
-// (warp w owns keys 8w..8w+7 of every chunk, running max/sum/out in registers, next chunk prefetched into registers), merges
-// its 16 warps, and writes the unit's partial; the second half to arrive merges the two partials of the (row, head) pair in fixed
-// order -- so the result of a row does not depend on which other rows share the pass.
+// (warp w, key slot s owns key 8w+s of every chunk).  K/V chunks are copied three chunks ahead with cp.async into a 4-deep ring
+// in shared memory (the GEMV staging area, idle here); every thread reads back only the 64 bytes it copied itself, so the ring
+// needs no barrier -- it is an asynchronous extension of the register file (96 KB in flight per SM).  The 16 warps are merged
+// per unit; the second half to arrive merges the two partials of the (row, head) pair in fixed order -- so the result of a row does
+// not depend on which other rows share the pass.
+constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
+static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
+
 template <int WT>
-__device__ __noinline__ void mk_attn_cross(const MkArgs & a, MkSm & sm, const MkLayer & L) {
+__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, H = a.n_head, nch = a.n_keys / (2 * MK_XKEYS);          // chunks per unit
     const unsigned I = (unsigned) (a.n_tok * H * 2), G = min(gridDim.x, I);
     if (blockIdx.x >= G) return;
     const unsigned s0 = (blockIdx.x * I) / G, s1 = ((blockIdx.x + 1) * I) / G;
     int p = (int) (s0 >> 1), t = p / H, h = p - t * H, hf = (int) (s0 & 1);
-    // loader state: unit being fetched
+    // loader state: chunk being fetched
     int tl_ = t, hl = h, hfl = hf, jl = 0;
-    unsigned ul = s0;
-    auto load_next = [&](KVFrag & f) {
-        const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) ((hfl * nch + jl) * MK_XKEYS + warp * 8) * d + hl * 64;
-        xkv_load(f, L.xk + off, L.xv + off, d, lane);
-        if (++jl == nch) { jl = 0; ++ul; if (++hfl == 2) { hfl = 0; if (++hl == H) { hl = 0; ++tl_; } } }
-    };
-    KVFrag cur, nxt;
-    load_next(cur);
-    int buf = 0;
-    for (unsigned u = s0; u < s1; ++u) {
-        float q[16];
-        load_q16(a.q2 + (size_t) t * d + h * 64 + (lane & 3) * 16, q);
-        float m = -INFINITY, l = 0.0f, o0 = 0.0f, o1 = 0.0f;
-        for (int j = 0; j < nch; ++j) {
-            if (ul < s1) load_next(nxt);
-            float sc = dot16(cur.k0, cur.k1, q);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            attn_update(sc * a.kq_scale, cur.v, m, l, o0, o1);
-            cur = nxt;
+    unsigned ul = s0, il = 0;
+    const size_t lane_off = (size_t) (warp * 8 + (lane >> 2)) * d + (lane & 3) * 8;
+    const uint32_t ring = (uint32_t) __cvta_generic_to_shared(mk_smem) + tid * 16;
+    auto issue = [&]() {                                           // copy the next chunk (if any) into ring slot il % 4; always commits a group
+        if (ul < s1) {
+            const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) ((hfl * nch + jl) * MK_XKEYS) * d + hl * 64 + lane_off;
+            const uint32_t sa = ring + (il & (MK_RING - 1)) * MK_RING_SLOT;
+            cp_async16(sa, L.xk + off); cp_async16(sa + MK_THREADS * 16, L.xk + off + 32);
+            cp_async16(sa + 2 * MK_THREADS * 16, L.xv + off); cp_async16(sa + 3 * MK_THREADS * 16, L.xv + off + 32);
+            if (++jl == nch) { jl = 0; ++ul; if (++hfl == 2) { hfl = 0; if (++hl == H) { hl = 0; ++tl_; } } }
         }
-        float * part = sm.part + (buf * MK_WARPS + warp) * MK_PART;
-        if (lane == 0) { part[0] = m; part[1] = l; }
-        *reinterpret_cast<float2 *>(part + 4 + 2 * lane) = make_float2(o0, o1);
+        ++il;
+        cp_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < MK_RING - 1; ++k) issue();
+    float * qsm = reinterpret_cast<float *>(mk_smem + MK_OFF_QSM);   // f16-rounded query of the unit: [2][64]
+    // qsm is stored in lane order: position 16*r + 8*hi + i holds dim 32*hi + 8*r + i
+    if (warp >= 2 && warp < 4) { const int dim = (warp - 2) * 32 + lane; qsm[((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) t * d + h * 64 + dim))); }
+    __syncthreads();
+    LaneAcc A; lane_init(A);
+    int j = 0, buf = 0;
+    unsigned ic = 0;
+    float keepM = 0.0f, keepL = 0.0f, keepO = 0.0f;                // half 0 of the current pair (warps 0-1, one output dim per thread)
+    for (unsigned u = s0; u < s1; ) {
+        issue();
+        cp_wait_ring();                                          // this thread's copies of chunk ic have landed
+        const uint8_t * sl = mk_smem + (ic & (MK_RING - 1)) * MK_RING_SLOT + tid * 16;
+        ++ic;
+        const uint4 k0 = *reinterpret_cast<const uint4 *>(sl), k1 = *reinterpret_cast<const uint4 *>(sl + MK_THREADS * 16);
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(sl + 2 * MK_THREADS * 16), v1 = *reinterpret_cast<const uint4 *>(sl + 3 * MK_THREADS * 16);
+        float sc = dot16s(k0, k1, qsm + buf * 64 + (lane & 3) * 16);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        lane_update(A, sc * a.kq_scale, v0, v1);
+        if (++j < nch) continue;
+        j = 0;                                                   // last chunk of the unit: merge
+        warp_merge(A);
+        part_store(SM_PART + (buf * MK_WARPS + warp) * MK_PART, A, lane);
+        if (u + 1 < s1 && warp >= 2 && warp < 4) {               // query of the next unit (same pair after half 0, else the next (row, head))
+            int tn = t, hn = h;
+            if (hf == 1) { if (++hn == H) { hn = 0; ++tn; } }
+            const int dim = (warp - 2) * 32 + lane;
+            qsm[(buf ^ 1) * 64 + ((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) tn * d + hn * 64 + dim)));
+        }
         __syncthreads();
         if (warp < 2) {                                          // merge the 16 warp partials of this unit
             const int dim = warp * 32 + lane;
             float M, Lsum;
-            const float o = attn_merge(sm.part + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
-            float * gp = a.xpart + ((size_t) p * 2 + hf) * 66;
-            gp[2 + dim] = o;
-            if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
-            __threadfence();
-            bar_named(3, 64);
-            if (tid == 0) sm.flag[buf] = (atomicAdd(a.xcnt + p, 1) == 1);
-            bar_named(3, 64);
-            if (sm.flag[buf]) {                                   // both halves are in: merge them (half 0 first)
+            const float o = attn_merge(SM_PART + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
+            // Both halves of a pair usually fall into the range of one CTA: half 0 is then kept in registers (warps 0-1 own it)
+            // and merged with half 1 by the same formula the cross-CTA path uses -- no global partial, fence or atomic.
+            const bool pair_local = (hf == 0) ? (u + 1 < s1) : (u > s0);
+            if (pair_local) {
+                if (hf == 0) { keepM = M; keepL = Lsum; keepO = o; }
+                else {
+                    const float MM = fmaxf(keepM, M);
+                    const float w0 = __expf(keepM - MM), w1 = __expf(M - MM);
+                    const float LL = fmaf(Lsum, w1, keepL * w0), oo = fmaf(o, w1, keepO * w0);
+                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
+                }
+            } else {
+                float * gp = a.xpart + ((size_t) p * 2 + hf) * 66;
+                gp[2 + dim] = o;
+                if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
                 __threadfence();
-                const float * p0 = a.xpart + (size_t) p * 2 * 66;
-                const float m0 = __ldcg(p0), m1 = __ldcg(p0 + 66), MM = fmaxf(m0, m1);
-                const float w0 = __expf(m0 - MM), w1 = __expf(m1 - MM);
-                const float LL = fmaf(__ldcg(p0 + 67), w1, __ldcg(p0 + 1) * w0);
-                const float oo = fmaf(__ldcg(p0 + 68 + dim), w1, __ldcg(p0 + 2 + dim) * w0);
-                mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
-                if (tid == 0) a.xcnt[p] = 0;
+                bar_named(3, 64);
+                if (tid == 0) SM_FLAG[buf] = (atomicAdd(a.xcnt + p, 1) == 1);
+                bar_named(3, 64);
+                if (SM_FLAG[buf]) {                               // both halves are in: merge them (half 0 first)
+                    __threadfence();
+                    const float * p0 = a.xpart + (size_t) p * 2 * 66;
+                    const float m0 = __ldcg(p0), m1 = __ldcg(p0 + 66), MM = fmaxf(m0, m1);
+                    const float w0 = __expf(m0 - MM), w1 = __expf(m1 - MM);
+                    const float LL = fmaf(__ldcg(p0 + 67), w1, __ldcg(p0 + 1) * w0);
+                    const float oo = fmaf(__ldcg(p0 + 68 + dim), w1, __ldcg(p0 + 2 + dim) * w0);
+                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
+                    if (tid == 0) a.xcnt[p] = 0;
+                }
             }
         }
         buf ^= 1;
+        ++u;
         if (++hf == 2) { hf = 0; ++p; if (++h == H) { h = 0; ++t; } }
+        lane_init(A);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-#define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, sm, target); MK_STAMP(); } while (0)
+#define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, target); MK_STAMP(); } while (0)
 
 template <int WT, bool TRACE>
 __global__ void __launch_bounds__(MK_THREADS, 1)
 k_decode_pass(const __grid_constant__ MkArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    MkSm sm;
-    {
-        uint8_t * p = smem_raw;
-        sm.xq = reinterpret_cast<uint32_t *>(p); p += (size_t) MK_MAXTOK * (MK_ROWB + 16);
-        sm.xd = reinterpret_cast<float *>(p);    p += (size_t) MK_MAXTOK * (MK_ROWB / 32) * 4;
-        sm.red = reinterpret_cast<float *>(p);   p += (size_t) MK_RED * 4;
-        sm.part = reinterpret_cast<float *>(p);  p += (size_t) 2 * MK_WARPS * MK_PART * 4;
-        sm.stat = reinterpret_cast<float *>(p);  p += 32 * 4;
-        sm.flag = reinterpret_cast<int *>(p);
-        sm.SW = 0;
-    }
+    if (threadIdx.x == 0) { mbar_init(SM_MBAR, 1); SM_FLAG[4] = 0; mbar_fence_init(); }
+    __syncthreads();
     unsigned long long target = a.bar_base;
     int n_stamp = 0;
     const int d = a.d;
@@ -504,65 +613,65 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         const MkLayer & L = a.layers[l];
         MkEpi e;
         // 1: LN -> quantised rows (whisper.cpp:2536-2543)
-        mk_lnq<WT>(a, sm, a.x, d, L.ln0_w, L.ln0_b, a.actq);
+        mk_lnq<WT>(a, a.x, d, L.ln0_w, L.ln0_b, a.actq);
         if (pf_w) mk_prefetch_w(L.o);
         MK_SYNC();
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
-        mk_gemv<WT>(a, sm, L.qkv, a.actq, e);
+        mk_gemv<WT>(a, L.qkv, a.actq, e);
         MK_SYNC();
         // 3: self-attention (2603-2625) -> quantised rows for the O projection
         if (pf_w) mk_prefetch_w(L.cq);
-        mk_attn_self<WT>(a, sm, L);
+        mk_attn_self<WT>(a, L);
         MK_SYNC();
         // 4: O + residual (2647-2659)
         if (pf_w) mk_prefetch_w(L.co);
-        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.o, a.actq, e);
+        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x; e.tag = 1;
+        mk_gemv<WT>(a, L.o, a.actq, e);
         MK_SYNC();
         // 5: LN -> quantised rows
-        mk_lnq<WT>(a, sm, a.x, d, L.lnc_w, L.lnc_b, a.actq);
+        mk_lnq<WT>(a, a.x, d, L.lnc_w, L.lnc_b, a.actq);
         if (pf_w) mk_prefetch_w(L.fc1);
         MK_SYNC();
         // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
-        mk_gemv<WT>(a, sm, L.cq, a.actq, e);
+        mk_gemv<WT>(a, L.cq, a.actq, e);
         MK_SYNC();
         // 7: cross-attention (2688-2705)
         if (pf_w) mk_prefetch_w(L.fc2);
-        mk_attn_cross<WT>(a, sm, L);
+        mk_attn_cross<WT>(a, L);
         MK_SYNC();
         // 8: cross O + residual (2754-2766)
         e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.co, a.actq, e);
+        mk_gemv<WT>(a, L.co, a.actq, e);
         MK_SYNC();
         // 9: LN -> quantised rows
-        mk_lnq<WT>(a, sm, a.x, d, L.lnm_w, L.lnm_b, a.actq);
+        mk_lnq<WT>(a, a.x, d, L.lnm_w, L.lnm_b, a.actq);
         if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
         MK_SYNC();
-        // 10: FC1 + GELU (2770-2794) -> quantised rows for FC2 (a CTA owns 32 consecutive outputs: one Q8_0 block per row)
-        e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.outq = a.hq;
-        mk_gemv<WT>(a, sm, L.fc1, a.actq, e);
+        // 10: FC1 + GELU (2770-2794), then the rows are quantised for FC2
+        e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.out = a.h;
+        mk_gemv<WT>(a, L.fc1, a.actq, e);
+        MK_SYNC();
+        mk_q8_rows<WT>(a, a.h, 4 * d, a.hq);
         MK_SYNC();
         // 11: FC2 + residual (2797-2806)
-        e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, sm, L.fc2, a.hq, e);
+        e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x; e.tag = 2;
+        mk_gemv<WT>(a, L.fc2, a.hq, e);
         MK_SYNC();
     }
     if (a.want_logits) {                                         // final LN + logits (2811-2827)
-        mk_lnq<WT>(a, sm, a.x, d, a.lnf_w, a.lnf_b, a.actq);
+        mk_lnq<WT>(a, a.x, d, a.lnf_w, a.lnf_b, a.actq);
         MK_SYNC();
         MkEpi e; e.out = a.logits;
-        mk_gemv<WT>(a, sm, a.te, a.actq, e);
+        mk_gemv<WT>(a, a.te, a.actq, e);
         MK_STAMP();
     }
 }
 
-int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
+int mk_barriers(int n_layer, bool want_logits) { return 12 * n_layer + (want_logits ? 1 : 0); }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
-size_t mk_smem_bytes(int, int) {
-    return (size_t) MK_MAXTOK * (MK_ROWB + 16) + (size_t) MK_MAXTOK * (MK_ROWB / 32) * 4 + (size_t) MK_RED * 4 + 2 * MK_WARPS * MK_PART * 4 + 32 * 4 + 16 * 4;
-}
+size_t mk_smem_bytes(int, int) { return MK_SMEM; }
 int mk_max_rows() { return MK_MAXTOK; }
 
 template <int WT, bool TRACE>

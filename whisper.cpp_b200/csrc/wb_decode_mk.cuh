@@ -26,6 +26,7 @@ struct MkArgs {
     QMat te; const float * pe;        // token embedding (also the logits matrix) and positional embedding
     const float * lnf_w, * lnf_b;     // final LayerNorm
     float * x, * qkv, * q2, * logits;                         // f32 workspaces: [R][d], [R][3d], [R][d], [R][V]   (R = mk_max_rows())
+    float * h;                        // FC1 + GELU output [R][4d]
     uint8_t * actq, * hq;             // quantised rows handed between phases: K = d (>= R*d*2 + R*d/8 bytes) and K = 4d
     float * xpart; int * xcnt;        // cross-attention partials [R*H][16][66] and arrival counters [R*H]
     unsigned long long * bar;         // grid barrier: [0] arrival counter (monotonic, never reset), [16 + 16*cta] release flag of each CTA

@@ -70,6 +70,7 @@ bool Engine::init(const Model * model, int cap_windows) {
     const size_t R = max_rows;
     if (!dx.alloc(R * d) || !dqkv.alloc(R * 3 * d) || !dattn.alloc(R * d) || !dq2.alloc(R * d) || !dh.alloc(R * 4 * d) ||
         !dlogits.alloc(R * V) || !xpart.alloc(R * H * 32 * 66) || !xcnt.alloc(R * H, true)) return false;
+    if (use_mk && !dhq.alloc(R * 4 * d * 2 + R * 4 * d / 8 + 256)) return false;
     if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
     WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) max_rows * V * sizeof(float)));
@@ -96,30 +97,39 @@ bool Engine::set_cells(int n) {
 }
 
 void Engine::mk_trace_collect(int n_layer, bool logits) {
-    const int ns = 1 + 22 * n_layer + (logits ? 3 : 0);
+    const int ns = 1 + 24 * n_layer + (logits ? 3 : 0);
     std::vector<long long> h(ns);
     if (cudaMemcpy(h.data(), mk_trace.p, ns * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
-    if (mk_trace_sum.empty()) mk_trace_sum.assign(26, 0.0);
+    if (mk_trace_sum.empty()) mk_trace_sum.assign(28, 0.0);
     for (int l = 0; l < n_layer; ++l)
-        for (int k = 0; k < 22; ++k) mk_trace_sum[k] += (double) (h[1 + 22 * l + k] - h[22 * l + k]) / n_layer;
-    if (logits) { mk_trace_sum[22] += (double) (h[ns - 3] - h[ns - 4]); mk_trace_sum[23] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[24] += (double) (h[ns - 1] - h[ns - 2]); }
-    mk_trace_sum[25] += (double) (h[ns - 1] - h[0]);
+        for (int k = 0; k < 24; ++k) mk_trace_sum[k] += (double) (h[1 + 24 * l + k] - h[24 * l + k]) / n_layer;
+    if (logits) { mk_trace_sum[24] += (double) (h[ns - 3] - h[ns - 4]); mk_trace_sum[25] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[26] += (double) (h[ns - 1] - h[ns - 2]); }
+    mk_trace_sum[27] += (double) (h[ns - 1] - h[0]);
+    {   // fine stamps of the tagged GEMV calls (last layer): tag 1 = O projection, tag 2 = FC2
+        long long f[24];
+        if (cudaMemcpy(f, mk_trace.p + 3000, sizeof(f), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (mk_fine.empty()) mk_fine.assign(24, 0.0);
+            for (int tg = 1; tg <= 2; ++tg) for (int k = 1; k < 5; ++k) mk_fine[8 * tg + k] += (double) (f[8 * tg + k] - f[8 * tg + k - 1]);
+        }
+    }
     ++mk_trace_n;
 }
 void Engine::mk_trace_dump() {
     if (mk_trace_path.empty() || !mk_trace_n) return;
     FILE * f = fopen(mk_trace_path.c_str(), "a");
     if (!f) return;
-    static const char * ph[11] = { "1 ln->q8", "2 qkv", "3 self-attn", "4 o-proj", "5 ln->q8", "6 cross-q", "7 cross-attn", "8 cross-o", "9 ln->q8", "10 fc1+gelu", "11 fc2" };
+    static const char * ph[12] = { "1 ln->q8", "2 qkv", "3 self-attn", "4 o-proj", "5 ln->q8", "6 cross-q", "7 cross-attn", "8 cross-o", "9 ln->q8", "10 fc1+gelu", "10b h->q8", "11 fc2" };
     const double us = 1e-3 / sm_ghz / (double) mk_trace_n;
     fprintf(f, "# persistent decode kernel, CTA 0, average over %llu passes with logits (us; SM clock %.3f GHz)\n", (unsigned long long) mk_trace_n, sm_ghz);
     fprintf(f, "%-16s %10s %10s\n", "phase (per layer)", "work", "barrier");
     double tot = 0.0;
-    for (int p = 0; p < 11; ++p) {
+    for (int p = 0; p < 12; ++p) {
         fprintf(f, "%-16s %10.2f %10.2f\n", ph[p], mk_trace_sum[2*p] * us, mk_trace_sum[2*p + 1] * us);
         tot += (mk_trace_sum[2*p] + mk_trace_sum[2*p + 1]) * us;
     }
-    fprintf(f, "layer total %.2f us; final ln %.2f + barrier %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[22] * us, mk_trace_sum[23] * us, mk_trace_sum[24] * us, mk_trace_sum[25] * us);
+    fprintf(f, "layer total %.2f us; final ln %.2f + barrier %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[24] * us, mk_trace_sum[25] * us, mk_trace_sum[26] * us, mk_trace_sum[27] * us);
+    if (!mk_fine.empty()) for (int tg = 1; tg <= 2; ++tg)
+        fprintf(f, "gemv tag %d (CTA 0, first tile): stage %.2f us, k-loop %.2f us, red+sync %.2f us, epilogue %.2f us\n", tg, mk_fine[8*tg+1] * us, mk_fine[8*tg+2] * us, mk_fine[8*tg+3] * us, mk_fine[8*tg+4] * us);
     fclose(f);
 }
 
@@ -368,7 +378,7 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         a.slot_stride = (int64_t) 2 * Lt * Tp * d; a.kq_scale = kq_scale; a.eps = hp.eps;
         a.te = m->d_te; a.pe = m->d_pe; a.lnf_w = m->d_ln.w; a.lnf_b = m->d_ln.b;
         a.x = dx.p; a.qkv = dqkv.p; a.q2 = dq2.p; a.logits = dlogits.p;
-        a.actq = reinterpret_cast<uint8_t *>(dattn.p); a.hq = reinterpret_cast<uint8_t *>(dh.p);
+        a.actq = reinterpret_cast<uint8_t *>(dattn.p); a.h = dh.p; a.hq = dhq.p;
         a.xpart = xpart.p; a.xcnt = xcnt.p;
         a.bar = mk_bar.p; a.bar_base = mk_bar_total; a.err = reinterpret_cast<int *>(mk_bar.p + 8); a.prefetch = mk_prefetch; a.trace = mk_trace.p;
         // algorithmic bytes of one pass: every decoder weight once, the cross K/V of each row, the self K/V each row attends to

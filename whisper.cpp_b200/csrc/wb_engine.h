@@ -60,6 +60,7 @@ struct Engine {
     // ---- decoder
     DevBuf<__half> kv_k, kv_v;       // [Lt][n_cells][d]
     DevBuf<float>  dx, dqkv, dattn, dq2, dh, dlogits, xpart;
+    DevBuf<uint8_t> dhq;              // quantised FC1 output rows of the persistent kernel
     DevBuf<uint8_t> act_scratch;      // quantised activations of the current GEMV (k_act_quant -> k_gemv_mma)
     bool gemv_v2 = true;             // WB200_GEMV_V1=1 selects the dp4a kernel
     // persistent decode kernel (wb_decode_mk.cu); WB200_MEGAKERNEL=0 selects the kernel-per-op chain
