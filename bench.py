@@ -296,7 +296,8 @@ def main():
     out = {"metric": "xRT (audio-s/wall-s)", "value": value, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f16 tcgen05 (encode) / int8 mma block dot (decode), f32 accumulate", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "decode": "lock-step batch of up to 64 sequences per GPU, one persistent cooperative kernel per token step", "l2": "weights (1.08 GB) + KV (0.3 GB/sequence) streamed every step exceed the 126 MB L2"},
+           "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "decode": "lock-step batch of up to 64 sequences per GPU, one persistent cooperative kernel per token step", "l2": "weights (1.08 GB) + KV (0.3 GB/sequence) streamed every step exceed the 126 MB L2",
+                      "timing": "host wall clock between device synchronisations around whole steps (a step contains host control flow), max over ranks; per-kernel numbers from CUDA events on the launching stream"},
            "encode_ms": float(enc[1] + enc[2] + enc[3]), "encode_ms_parts": {"mel": float(enc[0]), "conv": float(enc[1]), "encoder": float(enc[2]), "cross": float(enc[3])},
            "decoded_tokens_per_step": tokens, "engine": engine_stats, "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
@@ -318,6 +319,16 @@ def main():
             roof = {"kernel": names[0], "bound": "tensor", "achieved": classes[names[0]]["TFLOPs"], "peak": tf, "unit": "TFLOP/s", "frac": classes[names[0]]["TFLOPs"] / tf, "traffic": None, "peak_source": how + " (sustained bf16)"}
         else:
             roof = {"kernel": names[dom], "bound": "hbm", "achieved": classes[names[dom]]["GBps"], "peak": hbm, "unit": "GB/s", "frac": classes[names[dom]]["GBps"] / hbm, "traffic": None, "peak_source": how}
+        # DRAM traffic of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if it is the same kernel
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_decode_pass.json")) as f:
+                cap = json.load(f)
+            if dom == 1 and cap.get("rows") == min(n_chunks, 64):
+                roof["traffic"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+                roof["traffic_source"] = "profiles/r01_ncu_decode_pass.json (one launch, %d rows)" % cap["rows"]
+                roof["algorithmic_bytes_per_launch"] = (by[dom] / ln[dom]) if ln[dom] else None
+        except Exception:  # noqa: BLE001
+            pass
         out["roofline"] = roof
         out["kernel_classes"] = classes
         if not args.no_cpu_baseline:

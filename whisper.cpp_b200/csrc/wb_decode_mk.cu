@@ -62,8 +62,8 @@ __device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long t
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(a.bar, 1ULL);
-        __threadfence();
         SM_FLAG[2] = (old + 1 == target);
+        if (old + 1 == target) __threadfence();                  // the last arriver acquires what the others released
     }
     __syncthreads();
     if (SM_FLAG[2]) {
@@ -456,19 +456,23 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
         float q[16];
         load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
         LaneAcc A; lane_init(A);
+        bool ok = hw * 8 + kslot < nk;
+        int cell = ok ? cells[hw * 8 + kslot] : 0;
         for (int k0 = hw * 8; k0 < nk; k0 += 64) {
-            const bool ok = k0 + kslot < nk;
             KV4 f;
             f.k0 = f.k1 = f.v0 = f.v1 = make_uint4(0, 0, 0, 0);
-            if (ok) {
-                const size_t off = (size_t) cells[k0 + kslot] * d + h * 64 + r * 8;
+            const bool okc = ok;
+            if (okc) {
+                const size_t off = (size_t) cell * d + h * 64 + r * 8;
                 const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
                 f.k0 = __ldcg(kp); f.k1 = __ldcg(kp + 4); f.v0 = __ldcg(vp); f.v1 = __ldcg(vp + 4);
             }
+            ok = k0 + 64 + kslot < nk;                           // the cell of the next group is fetched while this group's K/V are in flight
+            cell = ok ? cells[k0 + 64 + kslot] : 0;
             float sc = dot16(f.k0, f.k1, q);
             sc += __shfl_xor_sync(0xffffffffu, sc, 1);
             sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            if (ok) lane_update(A, sc, f.v0, f.v1);
+            if (okc) lane_update(A, sc, f.v0, f.v1);
         }
         warp_merge(A);
         part_store(SM_PART + (half * 8 + hw) * MK_PART, A, lane);
