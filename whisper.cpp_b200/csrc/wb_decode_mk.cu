@@ -28,7 +28,9 @@
 
 namespace wb {
 
-constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 16 * 16 * MK_REDLD, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 2 * 4 * 16 * 16 * 9, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_TP = 4;                // weight tiles a GEMV phase keeps in flight per iteration
+static_assert(2 * MK_TP * 16 * 16 * 9 <= MK_RED, "split-K reduction buffer");
 constexpr int MK_ROWB = 1280;            // bytes of one staged activation row chunk (1280 int8 values or 640 halves)
 
 // dynamic shared memory, fixed carve-up (every phase function addresses it directly: pointers handed through a struct in
@@ -36,7 +38,7 @@ constexpr int MK_ROWB = 1280;            // bytes of one staged activation row c
 extern __shared__ __align__(16) uint8_t mk_smem[];
 constexpr int MK_OFF_XQ   = 0;                                                   // staged activation rows [64][SW words]
 constexpr int MK_OFF_XD   = MK_OFF_XQ + MK_MAXTOK * (MK_ROWB + 16);              // their Q8_0 block scales [64][chunk/32]
-constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [16 warps][16 rows][65]
+constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [2][MK_TP tiles][16 warps][16 rows][9]
 constexpr int MK_OFF_PART = MK_OFF_RED + MK_RED * 4;                             // attention warp partials [2][16][68]: m, l, -, -, o[64]
 constexpr int MK_OFF_STAT = MK_OFF_PART + 2 * MK_WARPS * MK_PART * 4;            // LayerNorm partial sums [32]
 constexpr int MK_OFF_FLAG = MK_OFF_STAT + 32 * 4;                                // [16] ints
@@ -173,43 +175,19 @@ __device__ __noinline__ void mk_q8_rows(const MkArgs & a, const float * src, int
     }
 }
 
-// stage chunk `kc` (MK_ROWB bytes per row at most) of the quantised rows in shared memory: one TMA bulk copy per row (and one
-// for its block scales) into the padded row layout, completion through an mbarrier.  (Copying through registers was limited by
-// the outstanding-miss capacity of the LSU: 7 us for 83 KB.)
+// TMA bulk copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 #define SM_MBAR (reinterpret_cast<uint64_t *>(mk_smem + MK_OFF_FLAG + 32))
 
-template <int WT>
-__device__ __forceinline__ void mk_load_chunk(const MkArgs & a, const uint8_t * src, int K, int kc, int KCe) {
-    const int tid = threadIdx.x;
-    const int rowb = (WT == WT_F16) ? K * 2 : K, chb = (WT == WT_F16) ? KCe * 2 : KCe, SW = (chb >> 2) + 4;
-    const int nbc = KCe >> 5;
-    const int ph = SM_FLAG[4];                                   // staging round (mbarrier phase parity)
-    __syncthreads();                                             // everybody has read `ph`; the previous users of the buffer are done
-    if (tid == 0) {
-        SM_FLAG[4] = ph + 1;
-        mbar_arrive_expect_tx(SM_MBAR, (uint32_t) a.n_tok * (uint32_t) (chb + (WT == WT_F16 ? 0 : nbc * 4)));
-    }
-    if (tid < a.n_tok) {
-        asm volatile("fence.proxy.async;" ::: "memory");         // rows were written with ordinary stores (by other CTAs, before the grid barrier)
-        bulk_g2s(SM_XQ + tid * SW, src + (size_t) tid * rowb + (size_t) kc * chb, (uint32_t) chb, SM_MBAR);
-        if (WT != WT_F16)
-            bulk_g2s(SM_XD + tid * nbc, reinterpret_cast<const float *>(src + (size_t) MK_MAXTOK * K) + (size_t) tid * (K >> 5) + kc * nbc, (uint32_t) nbc * 4, SM_MBAR);
-    }
-    mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
-}
-
 struct MkEpi {
-    int tag = 0;                         // != 0: CTA 0 records fine-grained stamps of this call into trace[3000 + 8*tag ..]
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
-    uint8_t * outq = nullptr;            // quantised output rows (actq format) for the next GEMV
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
 };
 
-// L2 prefetch of the tiles this CTA will own in a later GEMV phase (tile-major: the records of a tile are contiguous)
+// L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per grid
 __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
     if (threadIdx.x != MK_THREADS - 32) return;
     const int n_tiles = (W.N + 15) >> 4;
@@ -218,56 +196,81 @@ __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
         l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * tile_bytes, tile_bytes);
 }
 
-// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n] for the 16-row tiles owned by this CTA (round-robin).
-// The 16 warps split K; each multiplies its weight blocks with ALL rows (8 per MMA, <= 8 MMAs per block), so a weight block is
-// decoded once for up to 64 sequences.  x: quantised rows in global memory (actq format).
+// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n].
+// With up to 64 rows the activations (64 x K bytes) outweigh a weight tile (16 x K x ~0.7 bytes), so the work is cut by ROW GROUP
+// first: CTA c serves the 8 rows of group c % NG, stages only those rows (one TMA bulk copy per row + one for its block scales,
+// completion on an mbarrier) and walks every NG-th... every tile of the matrix that its group-mates do not take.  The 16 warps
+// split K of a tile (one mma.sync.m16n8k32.s8 per weight block), partials are reduced through smem.  x: quantised rows in global
+// memory (actq format).  Weight tiles are read by NG CTAs (from L2); their decode costs ~25 instructions per block.
 template <int WT>
 __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
     constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
     constexpr int UB = 3;                                        // records whose loads are issued together
-    const int N = W.N, K = W.K, n_tok = a.n_tok, NG = (n_tok + 7) >> 3;
+    const int N = W.N, K = W.K, NG = (a.n_tok + 7) >> 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
-    const int ks = warp;
-    const int n_tiles = (N + 15) >> 4, nrec = K / RK;
-    const int KCe = (WT == WT_F16 && a.d > 640) ? (a.d >> 1) : a.d;   // activation chunk staged in smem (K is d or 4d)
-    const int nchunks = K / KCe, rpc = KCe / RK, nbc = KCe >> 5;
-    const int SW = (((WT == WT_F16) ? KCe * 2 : KCe) >> 2) + 4;  // words per staged row
-    bool staged = false;
-    const bool fs = a.trace && e.tag && blockIdx.x == 0 && tid == 0;
-    if (fs) a.trace[3000 + 8 * e.tag] = clock64();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        float acc[8][4];
+    const int n_tiles = (N + 15) >> 4, nrec = K / RK, nb = K >> 5;
+    const int grp = blockIdx.x % NG, ci = blockIdx.x / NG, cg = ((int) gridDim.x - grp + NG - 1) / NG;   // row group, index / count of its CTAs
+    const int t_base = grp * 8, nt = min(8, a.n_tok - t_base);
+    const int rowb = (WT == WT_F16) ? K * 2 : K, SW = (rowb >> 2) + 4;
+    {   // stage the rows of the group
+        const int ph = SM_FLAG[4];                               // staging round (mbarrier phase parity)
+        __syncthreads();                                         // everybody has read `ph`; the previous users of the buffer are done
+        if (tid == 0) {
+            SM_FLAG[4] = ph + 1;
+            mbar_arrive_expect_tx(SM_MBAR, (uint32_t) nt * (uint32_t) (rowb + (WT == WT_F16 ? 0 : nb * 4)));
+        }
+        if (tid < nt) {
+            asm volatile("fence.proxy.async;" ::: "memory");     // rows were written with ordinary stores (by other CTAs, before the grid barrier)
+            bulk_g2s(SM_XQ + tid * SW, x + (size_t) (t_base + tid) * rowb, (uint32_t) rowb, SM_MBAR);
+            if (WT != WT_F16)
+                bulk_g2s(SM_XD + tid * nb, reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) (t_base + tid) * nb, (uint32_t) nb * 4, SM_MBAR);
+        }
+        mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
+    }
+    const bool tok_ok = g < nt;
+    const int t0 = min(2 * c, nt - 1), t1 = min(2 * c + 1, nt - 1);
+    constexpr int TP = MK_TP;                                    // tiles in flight per iteration: their weight loads are issued together
+    int round = 0;
+    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP, ++round) {
+        float acc[TP][4];
 #pragma unroll
-        for (int gi = 0; gi < 8; ++gi) { acc[gi][0] = acc[gi][1] = acc[gi][2] = acc[gi][3] = 0.0f; }
-        for (int kc = 0; kc < nchunks; ++kc) {
-            if (nchunks > 1 || !staged) { mk_load_chunk<WT>(a, x, K, kc, KCe); staged = true; }
-            if (fs && kc == 0) a.trace[3000 + 8 * e.tag + 1] = clock64();
-            {
-                const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + ((size_t) tile * nrec + (size_t) kc * rpc) * REC;
-                for (int kb = ks; kb < rpc; kb += MK_WARPS * UB) {
-                    uint4 wq[UB]; uint2 wh[UB]; uint32_t wd[UB];
+        for (int j = 0; j < TP; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+        for (int kb = warp; kb < nrec; kb += MK_WARPS * UB) {
+            uint4 wq[TP][UB]; uint2 wh[TP][UB]; uint32_t wd[TP][UB];
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        const uint8_t * rec = tb + (size_t) min(kb + u * MK_WARPS, rpc - 1) * REC;
-                        if (WT == WT_F16 || WT == WT_Q8_0) wq[u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
-                        else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[u].x = q2.x; wq[u].y = q2.y; }
-                        if (WT == WT_Q5_0) wh[u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
-                        if (WT != WT_F16)  wd[u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
-                    }
+            for (int j = 0; j < TP; ++j) {
+                const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + (size_t) min(tile0 + j * cg, n_tiles - 1) * nrec * REC;
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        const int bl = kb + u * MK_WARPS;        // record within the chunk
-                        if (bl < rpc) {
+                for (int u = 0; u < UB; ++u) {
+                    const uint8_t * rec = tb + (size_t) min(kb + u * MK_WARPS, nrec - 1) * REC;
+                    if (WT == WT_F16 || WT == WT_Q8_0) wq[j][u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
+                    else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[j][u].x = q2.x; wq[j][u].y = q2.y; }
+                    if (WT == WT_Q5_0) wh[j][u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
+                    if (WT != WT_F16)  wd[j][u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int b = kb + u * MK_WARPS;
+                if (b < nrec) {
+                    const uint32_t b0 = tok_ok ? SM_XQ[g * SW + b * 8 + c] : 0u, b1 = tok_ok ? SM_XQ[g * SW + b * 8 + 4 + c] : 0u;
+                    float dx0 = 0.0f, dx1 = 0.0f;
+                    if (WT != WT_F16) { dx0 = SM_XD[t0 * nb + b]; dx1 = SM_XD[t1 * nb + b]; }
+#pragma unroll
+                    for (int j = 0; j < TP; ++j) {
+                        if (WT == WT_F16) {
+                            const uint32_t af[4] = { wq[j][u].x, wq[j][u].y, wq[j][u].z, wq[j][u].w };
+                            mma_f16_16816(acc[j], af, b0, b1);
+                        } else {
                             uint32_t af[4];
-                            float dw0 = 0.0f, dw1 = 0.0f;
-                            if (WT == WT_F16 || WT == WT_Q8_0) { af[0] = wq[u].x; af[1] = wq[u].y; af[2] = wq[u].z; af[3] = wq[u].w; }
+                            if (WT == WT_Q8_0) { af[0] = wq[j][u].x; af[1] = wq[j][u].y; af[2] = wq[j][u].z; af[3] = wq[j][u].w; }
                             else {
-                                uint32_t lo0 = wq[u].x & 0x0F0F0F0Fu, hi0 = (wq[u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[u].y & 0x0F0F0F0Fu, hi1 = (wq[u].y >> 4) & 0x0F0F0F0Fu;
+                                uint32_t lo0 = wq[j][u].x & 0x0F0F0F0Fu, hi0 = (wq[j][u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[j][u].y & 0x0F0F0F0Fu, hi1 = (wq[j][u].y >> 4) & 0x0F0F0F0Fu;
                                 if (WT == WT_Q5_0) {
-                                    lo0 |= spread4_to_bit4(wh[u].x >> (4 * c)); hi0 |= spread4_to_bit4(wh[u].x >> (16 + 4 * c));
-                                    lo1 |= spread4_to_bit4(wh[u].y >> (4 * c)); hi1 |= spread4_to_bit4(wh[u].y >> (16 + 4 * c));
+                                    lo0 |= spread4_to_bit4(wh[j][u].x >> (4 * c)); hi0 |= spread4_to_bit4(wh[j][u].x >> (16 + 4 * c));
+                                    lo1 |= spread4_to_bit4(wh[j][u].y >> (4 * c)); hi1 |= spread4_to_bit4(wh[j][u].y >> (16 + 4 * c));
                                     af[0] = __vsub4(lo0, 0x10101010u); af[2] = __vsub4(hi0, 0x10101010u);
                                     af[1] = __vsub4(lo1, 0x10101010u); af[3] = __vsub4(hi1, 0x10101010u);
                                 } else {
@@ -275,75 +278,40 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
                                     af[1] = __vsub4(lo1, 0x08080808u); af[3] = __vsub4(hi1, 0x08080808u);
                                 }
                             }
-                            if (WT != WT_F16) {
-                                dw0 = __half2float(__ushort_as_half((unsigned short) (wd[u] & 0xffffu)));
-                                dw1 = __half2float(__ushort_as_half((unsigned short) (wd[u] >> 16)));
-                            }
-#pragma unroll
-                            for (int gi = 0; gi < 8; ++gi) {
-                                if (gi < NG) {
-                                    const int tb_ = gi * 8 + g;
-                                    const bool ok = tb_ < n_tok;
-                                    const uint32_t b0 = ok ? SM_XQ[tb_ * SW + bl * 8 + c] : 0u, b1 = ok ? SM_XQ[tb_ * SW + bl * 8 + 4 + c] : 0u;
-                                    if (WT == WT_F16) mma_f16_16816(acc[gi], af, b0, b1);
-                                    else {
-                                        int dd[4]; mma_s8_16832(dd, af, b0, b1);
-                                        const float dx0 = SM_XD[min(gi * 8 + 2 * c, n_tok - 1) * nbc + bl], dx1 = SM_XD[min(gi * 8 + 2 * c + 1, n_tok - 1) * nbc + bl];
-                                        acc[gi][0] = fmaf(dw0 * dx0, (float) dd[0], acc[gi][0]);
-                                        acc[gi][1] = fmaf(dw0 * dx1, (float) dd[1], acc[gi][1]);
-                                        acc[gi][2] = fmaf(dw1 * dx0, (float) dd[2], acc[gi][2]);
-                                        acc[gi][3] = fmaf(dw1 * dx1, (float) dd[3], acc[gi][3]);
-                                    }
-                                }
-                            }
+                            int dd[4]; mma_s8_16832(dd, af, b0, b1);
+                            const float dw0 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] & 0xffffu))), dw1 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] >> 16)));
+                            acc[j][0] = fmaf(dw0 * dx0, (float) dd[0], acc[j][0]);
+                            acc[j][1] = fmaf(dw0 * dx1, (float) dd[1], acc[j][1]);
+                            acc[j][2] = fmaf(dw1 * dx0, (float) dd[2], acc[j][2]);
+                            acc[j][3] = fmaf(dw1 * dx1, (float) dd[3], acc[j][3]);
                         }
                     }
                 }
             }
         }
-        if (fs) a.trace[3000 + 8 * e.tag + 2] = clock64();
-        // split-K partials -> smem: red[warp][row][token]
+        float * red = SM_RED + (round & 1) * (TP * MK_WARPS * 16 * 9);  // double buffered: one barrier per iteration
 #pragma unroll
-        for (int gi = 0; gi < 8; ++gi)
-            if (gi < NG) {
+        for (int j = 0; j < TP; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) SM_RED[(warp * 16 + g + (i >> 1) * 8) * MK_REDLD + gi * 8 + 2 * c + (i & 1)] = acc[gi][i];
-            }
+            for (int i = 0; i < 4; ++i) red[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * 9 + 2 * c + (i & 1)] = acc[j][i];
         __syncthreads();
-        if (fs) a.trace[3000 + 8 * e.tag + 3] = clock64();
-        // epilogue: half a warp = the 16 rows of the tile for one batch row; two outputs per thread with their loads issued together
-        for (int o0 = tid; o0 < 16 * NG * 8; o0 += 2 * MK_THREADS) {
-            float bias[2], scl[2], res[2]; bool ok[2]; int rowv[2], tv[2];
+        if (tid < TP * 128) {                                    // epilogue: TP tiles x 16 rows x 8 batch rows
+            const int j = tid >> 7, tl = (tid & 127) >> 4, rl = tid & 15, tile = tile0 + j * cg, row = tile * 16 + rl, t = t_base + tl;
+            if (tile < n_tiles && tl < nt && row < N) {
+                float v = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int o = o0 + k * MK_THREADS;
-                tv[k] = o >> 4; rowv[k] = tile * 16 + (o & 15);
-                ok[k] = tv[k] < n_tok && rowv[k] < N;
-                bias[k] = (ok[k] && e.bias) ? __ldg(e.bias + rowv[k]) : 0.0f;
-                scl[k]  = (ok[k] && e.scale) ? __ldg(e.scale + rowv[k]) : 1.0f;
-                res[k]  = (ok[k] && e.res) ? __ldcg(e.res + (size_t) tv[k] * N + rowv[k]) : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (ok[k]) {
-                    const int rl = rowv[k] & 15, t = tv[k], row = rowv[k];
-                    float v = 0.0f;
-#pragma unroll
-                    for (int w = 0; w < MK_WARPS; ++w) v += SM_RED[(w * 16 + rl) * MK_REDLD + t];
-                    v = (v + bias[k]) * scl[k];
-                    if (e.act == 1) v = gelu_ref_f16(v);
-                    v += res[k];
-                    if (e.out) e.out[(size_t) t * N + row] = v;
-                    if (e.kc && row >= e.kv_d) {
-                        const size_t cell = a.cell[t];
-                        if (row < 2 * e.kv_d) e.kc[cell * e.kv_d + (row - e.kv_d)] = __float2half_rn(v);
-                        else                  e.vc[cell * e.kv_d + (row - 2 * e.kv_d)] = __float2half_rn(v);
-                    }
+                for (int w = 0; w < MK_WARPS; ++w) v += red[((j * MK_WARPS + w) * 16 + rl) * 9 + tl];
+                v = (v + (e.bias ? __ldg(e.bias + row) : 0.0f)) * (e.scale ? __ldg(e.scale + row) : 1.0f);
+                if (e.act == 1) v = gelu_ref_f16(v);
+                if (e.res) v += __ldcg(e.res + (size_t) t * N + row);
+                if (e.out) e.out[(size_t) t * N + row] = v;
+                if (e.kc && row >= e.kv_d) {
+                    const size_t cell = a.cell[t];
+                    if (row < 2 * e.kv_d) e.kc[cell * e.kv_d + (row - e.kv_d)] = __float2half_rn(v);
+                    else                  e.vc[cell * e.kv_d + (row - 2 * e.kv_d)] = __float2half_rn(v);
                 }
             }
         }
-        if (fs) a.trace[3000 + 8 * e.tag + 4] = clock64();
-        __syncthreads();                                         // red[] is rewritten by the next tile
     }
 }
 
@@ -630,7 +598,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 4: O + residual (2647-2659)
         if (pf_w) mk_prefetch_w(L.co);
-        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x; e.tag = 1;
+        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
         mk_gemv<WT>(a, L.o, a.actq, e);
         MK_SYNC();
         // 5: LN -> quantised rows
@@ -660,7 +628,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         mk_q8_rows<WT>(a, a.h, 4 * d, a.hq);
         MK_SYNC();
         // 11: FC2 + residual (2797-2806)
-        e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x; e.tag = 2;
+        e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
         mk_gemv<WT>(a, L.fc2, a.hq, e);
         MK_SYNC();
     }

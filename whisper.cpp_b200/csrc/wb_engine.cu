@@ -105,13 +105,6 @@ void Engine::mk_trace_collect(int n_layer, bool logits) {
         for (int k = 0; k < 24; ++k) mk_trace_sum[k] += (double) (h[1 + 24 * l + k] - h[24 * l + k]) / n_layer;
     if (logits) { mk_trace_sum[24] += (double) (h[ns - 3] - h[ns - 4]); mk_trace_sum[25] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[26] += (double) (h[ns - 1] - h[ns - 2]); }
     mk_trace_sum[27] += (double) (h[ns - 1] - h[0]);
-    {   // fine stamps of the tagged GEMV calls (last layer): tag 1 = O projection, tag 2 = FC2
-        long long f[24];
-        if (cudaMemcpy(f, mk_trace.p + 3000, sizeof(f), cudaMemcpyDeviceToHost) == cudaSuccess) {
-            if (mk_fine.empty()) mk_fine.assign(24, 0.0);
-            for (int tg = 1; tg <= 2; ++tg) for (int k = 1; k < 5; ++k) mk_fine[8 * tg + k] += (double) (f[8 * tg + k] - f[8 * tg + k - 1]);
-        }
-    }
     ++mk_trace_n;
 }
 void Engine::mk_trace_dump() {
@@ -128,8 +121,6 @@ void Engine::mk_trace_dump() {
         tot += (mk_trace_sum[2*p] + mk_trace_sum[2*p + 1]) * us;
     }
     fprintf(f, "layer total %.2f us; final ln %.2f + barrier %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[24] * us, mk_trace_sum[25] * us, mk_trace_sum[26] * us, mk_trace_sum[27] * us);
-    if (!mk_fine.empty()) for (int tg = 1; tg <= 2; ++tg)
-        fprintf(f, "gemv tag %d (CTA 0, first tile): stage %.2f us, k-loop %.2f us, red+sync %.2f us, epilogue %.2f us\n", tg, mk_fine[8*tg+1] * us, mk_fine[8*tg+2] * us, mk_fine[8*tg+3] * us, mk_fine[8*tg+4] * us);
     fclose(f);
 }
 
