@@ -8,6 +8,9 @@
 #include <regex>
 #include <thread>
 #include "wb_state.h"
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include "wb_kernels.cuh"
 
 using namespace wb;
@@ -142,31 +145,41 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
 }
 
 // ---------------------------------------------------------------------------------------------------- batch group
+// A member blocks on the futex word of its own request; the thread that completes the rendezvous runs the batch and wakes the
+// others one by one.  (A condition variable made all 63 sleepers re-acquire one mutex after every decode step.)
+static void req_wait(Group::Req & r) {
+    while (r.done.load(std::memory_order_acquire) == 0)
+        syscall(SYS_futex, reinterpret_cast<int *>(&r.done), FUTEX_WAIT_PRIVATE, 0, nullptr, nullptr, 0);
+}
+static void req_wake(Group::Req & r) {
+    r.done.store(1, std::memory_order_release);
+    syscall(SYS_futex, reinterpret_cast<int *>(&r.done), FUTEX_WAKE_PRIVATE, 1, nullptr, nullptr, 0);
+}
 bool Group::submit(Req & r) {
-    std::unique_lock<std::mutex> lk(mu);
-    pending.push_back(&r);
-    if ((int) pending.size() >= n_active) {
-        std::vector<Req *> batch; batch.swap(pending);
-        lk.unlock();
+    std::vector<Req *> batch;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        pending.push_back(&r);
+        if ((int) pending.size() >= n_active) batch.swap(pending);
+    }
+    if (!batch.empty()) {
         run(batch);
-        lk.lock();
-        for (Req * q : batch) q->done = true;
-        cv.notify_all();
+        for (Req * q : batch) if (q != &r) req_wake(*q);         // q may be gone as soon as it is woken: nothing of it is touched afterwards
     } else {
-        cv.wait(lk, [&] { return r.done; });
+        req_wait(r);
     }
     return r.ok;
 }
 void Group::leave() {
-    std::unique_lock<std::mutex> lk(mu);
-    n_active--;
-    if (!pending.empty() && (int) pending.size() >= n_active) {
-        std::vector<Req *> batch; batch.swap(pending);
-        lk.unlock();
+    std::vector<Req *> batch;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        n_active--;
+        if (!pending.empty() && (int) pending.size() >= n_active) batch.swap(pending);
+    }
+    if (!batch.empty()) {
         run(batch);
-        lk.lock();
-        for (Req * q : batch) q->done = true;
-        cv.notify_all();
+        for (Req * q : batch) req_wake(*q);
     }
 }
 void Group::run(std::vector<Req *> & batch) {

@@ -2,6 +2,7 @@
 // Mirrors the roles (not the code) of whisper_context / whisper_state / whisper_decoder / whisper_kv_cache in
 // src/whisper.cpp:692-717, 783-820, 834-952.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <memory>
@@ -114,7 +115,8 @@ struct Group {
         int seek = 0, n_ctx = 0;                // encode
         const int * tokens = nullptr, * pos = nullptr, * seq = nullptr; const int8_t * want = nullptr; int n = 0;   // decode
         const SampReq * samp = nullptr;
-        bool done = false, ok = false; int64_t dt_us = 0;
+        std::atomic<int> done{0};                // futex word: the member sleeps on its OWN request (no shared mutex to re-acquire on wake-up)
+        bool ok = false; int64_t dt_us = 0;
     };
     std::vector<Req *> pending;
     bool submit(Req & r);
