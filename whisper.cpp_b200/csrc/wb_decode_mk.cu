@@ -28,9 +28,9 @@
 
 namespace wb {
 
-constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 2 * 4 * 16 * 16 * 9, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 4 * 16 * 16 * 17, MK_PART = 68, MK_XSLOTS = 16;
 constexpr int MK_TP = 4;                // weight tiles a GEMV phase keeps in flight per iteration
-static_assert(2 * MK_TP * 16 * 16 * 9 <= MK_RED, "split-K reduction buffer");
+static_assert(MK_TP * 16 * 16 * 17 <= MK_RED, "split-K reduction buffer");
 constexpr int MK_ROWB = 1280;            // bytes of one staged activation row chunk (1280 int8 values or 640 halves)
 
 // dynamic shared memory, fixed carve-up (every phase function addresses it directly: pointers handed through a struct in
@@ -38,7 +38,7 @@ constexpr int MK_ROWB = 1280;            // bytes of one staged activation row c
 extern __shared__ __align__(16) uint8_t mk_smem[];
 constexpr int MK_OFF_XQ   = 0;                                                   // staged activation rows [64][SW words]
 constexpr int MK_OFF_XD   = MK_OFF_XQ + MK_MAXTOK * (MK_ROWB + 16);              // their Q8_0 block scales [64][chunk/32]
-constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [2][MK_TP tiles][16 warps][16 rows][9]
+constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [MK_TP tiles][16 warps][16 rows][17]
 constexpr int MK_OFF_PART = MK_OFF_RED + MK_RED * 4;                             // attention warp partials [2][16][68]: m, l, -, -, o[64]
 constexpr int MK_OFF_STAT = MK_OFF_PART + 2 * MK_WARPS * MK_PART * 4;            // LayerNorm partial sums [32]
 constexpr int MK_OFF_FLAG = MK_OFF_STAT + 32 * 4;                                // [16] ints
@@ -198,22 +198,27 @@ __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
 
 // y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n].
 // With up to 64 rows the activations (64 x K bytes) outweigh a weight tile (16 x K x ~0.7 bytes), so the work is cut by ROW GROUP
-// first: CTA c serves the 8 rows of group c % NG, stages only those rows (one TMA bulk copy per row + one for its block scales,
-// completion on an mbarrier) and walks every NG-th... every tile of the matrix that its group-mates do not take.  The 16 warps
-// split K of a tile (one mma.sync.m16n8k32.s8 per weight block), partials are reduced through smem.  x: quantised rows in global
-// memory (actq format).  Weight tiles are read by NG CTAs (from L2); their decode costs ~25 instructions per block.
+// first: CTA c serves the 16 rows of group c % NGc (8 rows for the widest F16 matrices), stages only those rows (one TMA bulk copy
+// per row + one for its block scales, completion on an mbarrier) and walks the weight tiles its group-mates do not take, four
+// tiles per iteration with their loads issued together.  The 16 warps split K of a tile; every weight block is decoded once and
+// multiplied with both 8-row halves (mma.sync.m16n8k32.s8); partials are reduced through smem.  x: quantised rows in global
+// memory (actq format).  A weight tile is read by the NGc CTAs of the different groups (from L2, prefetched a phase ahead).
 template <int WT>
 __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
     constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
     constexpr int UB = 3;                                        // records whose loads are issued together
-    const int N = W.N, K = W.K, NG = (a.n_tok + 7) >> 3;
+    constexpr int TP = MK_TP;                                    // tiles per iteration
+    constexpr int RLD = 17;                                      // row stride of the reduction buffer (16 batch rows + pad)
+    const int N = W.N, K = W.K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
     const int n_tiles = (N + 15) >> 4, nrec = K / RK, nb = K >> 5;
-    const int grp = blockIdx.x % NG, ci = blockIdx.x / NG, cg = ((int) gridDim.x - grp + NG - 1) / NG;   // row group, index / count of its CTAs
-    const int t_base = grp * 8, nt = min(8, a.n_tok - t_base);
     const int rowb = (WT == WT_F16) ? K * 2 : K, SW = (rowb >> 2) + 4;
+    const int RG = (16 * (rowb + 16) <= MK_MAXTOK * (MK_ROWB + 16)) ? 16 : 8;   // rows per CTA (what fits the staging area)
+    const int NGc = (a.n_tok + RG - 1) / RG;
+    const int grp = blockIdx.x % NGc, ci = blockIdx.x / NGc, cg = ((int) gridDim.x - grp + NGc - 1) / NGc;   // row group, index / count of its CTAs
+    const int t_base = grp * RG, nt = min(RG, a.n_tok - t_base), NH = (nt + 7) >> 3;
     {   // stage the rows of the group
         const int ph = SM_FLAG[4];                               // staging round (mbarrier phase parity)
         __syncthreads();                                         // everybody has read `ph`; the previous users of the buffer are done
@@ -229,14 +234,12 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
         }
         mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
     }
-    const bool tok_ok = g < nt;
-    const int t0 = min(2 * c, nt - 1), t1 = min(2 * c + 1, nt - 1);
-    constexpr int TP = MK_TP;                                    // tiles in flight per iteration: their weight loads are issued together
-    int round = 0;
-    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP, ++round) {
-        float acc[TP][4];
+    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP) {
+        float acc[TP][2][4];
 #pragma unroll
-        for (int j = 0; j < TP; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+        for (int j = 0; j < TP; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { acc[j][h][0] = acc[j][h][1] = acc[j][h][2] = acc[j][h][3] = 0.0f; }
         for (int kb = warp; kb < nrec; kb += MK_WARPS * UB) {
             uint4 wq[TP][UB]; uint2 wh[TP][UB]; uint32_t wd[TP][UB];
 #pragma unroll
@@ -255,52 +258,67 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
             for (int u = 0; u < UB; ++u) {
                 const int b = kb + u * MK_WARPS;
                 if (b < nrec) {
-                    const uint32_t b0 = tok_ok ? SM_XQ[g * SW + b * 8 + c] : 0u, b1 = tok_ok ? SM_XQ[g * SW + b * 8 + 4 + c] : 0u;
-                    float dx0 = 0.0f, dx1 = 0.0f;
-                    if (WT != WT_F16) { dx0 = SM_XD[t0 * nb + b]; dx1 = SM_XD[t1 * nb + b]; }
+                    uint32_t bf[2][2]; float dx[2][2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool ok = h * 8 + g < nt;
+                        bf[h][0] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + c] : 0u;
+                        bf[h][1] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + 4 + c] : 0u;
+                        dx[h][0] = dx[h][1] = 0.0f;
+                        if (WT != WT_F16) { dx[h][0] = SM_XD[min(h * 8 + 2 * c, nt - 1) * nb + b]; dx[h][1] = SM_XD[min(h * 8 + 2 * c + 1, nt - 1) * nb + b]; }
+                    }
 #pragma unroll
                     for (int j = 0; j < TP; ++j) {
-                        if (WT == WT_F16) {
-                            const uint32_t af[4] = { wq[j][u].x, wq[j][u].y, wq[j][u].z, wq[j][u].w };
-                            mma_f16_16816(acc[j], af, b0, b1);
-                        } else {
-                            uint32_t af[4];
-                            if (WT == WT_Q8_0) { af[0] = wq[j][u].x; af[1] = wq[j][u].y; af[2] = wq[j][u].z; af[3] = wq[j][u].w; }
-                            else {
-                                uint32_t lo0 = wq[j][u].x & 0x0F0F0F0Fu, hi0 = (wq[j][u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[j][u].y & 0x0F0F0F0Fu, hi1 = (wq[j][u].y >> 4) & 0x0F0F0F0Fu;
-                                if (WT == WT_Q5_0) {
-                                    lo0 |= spread4_to_bit4(wh[j][u].x >> (4 * c)); hi0 |= spread4_to_bit4(wh[j][u].x >> (16 + 4 * c));
-                                    lo1 |= spread4_to_bit4(wh[j][u].y >> (4 * c)); hi1 |= spread4_to_bit4(wh[j][u].y >> (16 + 4 * c));
-                                    af[0] = __vsub4(lo0, 0x10101010u); af[2] = __vsub4(hi0, 0x10101010u);
-                                    af[1] = __vsub4(lo1, 0x10101010u); af[3] = __vsub4(hi1, 0x10101010u);
-                                } else {
-                                    af[0] = __vsub4(lo0, 0x08080808u); af[2] = __vsub4(hi0, 0x08080808u);
-                                    af[1] = __vsub4(lo1, 0x08080808u); af[3] = __vsub4(hi1, 0x08080808u);
+                        uint32_t af[4];
+                        float dw0 = 0.0f, dw1 = 0.0f;
+                        if (WT == WT_F16 || WT == WT_Q8_0) { af[0] = wq[j][u].x; af[1] = wq[j][u].y; af[2] = wq[j][u].z; af[3] = wq[j][u].w; }
+                        else {
+                            uint32_t lo0 = wq[j][u].x & 0x0F0F0F0Fu, hi0 = (wq[j][u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[j][u].y & 0x0F0F0F0Fu, hi1 = (wq[j][u].y >> 4) & 0x0F0F0F0Fu;
+                            if (WT == WT_Q5_0) {
+                                lo0 |= spread4_to_bit4(wh[j][u].x >> (4 * c)); hi0 |= spread4_to_bit4(wh[j][u].x >> (16 + 4 * c));
+                                lo1 |= spread4_to_bit4(wh[j][u].y >> (4 * c)); hi1 |= spread4_to_bit4(wh[j][u].y >> (16 + 4 * c));
+                                af[0] = __vsub4(lo0, 0x10101010u); af[2] = __vsub4(hi0, 0x10101010u);
+                                af[1] = __vsub4(lo1, 0x10101010u); af[3] = __vsub4(hi1, 0x10101010u);
+                            } else {
+                                af[0] = __vsub4(lo0, 0x08080808u); af[2] = __vsub4(hi0, 0x08080808u);
+                                af[1] = __vsub4(lo1, 0x08080808u); af[3] = __vsub4(hi1, 0x08080808u);
+                            }
+                        }
+                        if (WT != WT_F16) {
+                            dw0 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] & 0xffffu)));
+                            dw1 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] >> 16)));
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h < NH) {
+                                if (WT == WT_F16) mma_f16_16816(acc[j][h], af, bf[h][0], bf[h][1]);
+                                else {
+                                    int dd[4]; mma_s8_16832(dd, af, bf[h][0], bf[h][1]);
+                                    acc[j][h][0] = fmaf(dw0 * dx[h][0], (float) dd[0], acc[j][h][0]);
+                                    acc[j][h][1] = fmaf(dw0 * dx[h][1], (float) dd[1], acc[j][h][1]);
+                                    acc[j][h][2] = fmaf(dw1 * dx[h][0], (float) dd[2], acc[j][h][2]);
+                                    acc[j][h][3] = fmaf(dw1 * dx[h][1], (float) dd[3], acc[j][h][3]);
                                 }
                             }
-                            int dd[4]; mma_s8_16832(dd, af, b0, b1);
-                            const float dw0 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] & 0xffffu))), dw1 = __half2float(__ushort_as_half((unsigned short) (wd[j][u] >> 16)));
-                            acc[j][0] = fmaf(dw0 * dx0, (float) dd[0], acc[j][0]);
-                            acc[j][1] = fmaf(dw0 * dx1, (float) dd[1], acc[j][1]);
-                            acc[j][2] = fmaf(dw1 * dx0, (float) dd[2], acc[j][2]);
-                            acc[j][3] = fmaf(dw1 * dx1, (float) dd[3], acc[j][3]);
                         }
                     }
                 }
             }
         }
-        float * red = SM_RED + (round & 1) * (TP * MK_WARPS * 16 * 9);  // double buffered: one barrier per iteration
+        // split-K partials -> smem: red[tile j][warp][row][batch row]
 #pragma unroll
         for (int j = 0; j < TP; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) red[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * 9 + 2 * c + (i & 1)] = acc[j][i];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) SM_RED[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * RLD + h * 8 + 2 * c + (i & 1)] = acc[j][h][i];
         __syncthreads();
-        if (tid < TP * 128) {                                    // epilogue: TP tiles x 16 rows x 8 batch rows
-            const int j = tid >> 7, tl = (tid & 127) >> 4, rl = tid & 15, tile = tile0 + j * cg, row = tile * 16 + rl, t = t_base + tl;
+        for (int o = tid; o < TP * 256; o += MK_THREADS) {        // epilogue: TP tiles x 16 batch rows x 16 weight rows
+            const int j = o >> 8, tl = (o & 255) >> 4, rl = o & 15, tile = tile0 + j * cg, row = tile * 16 + rl, t = t_base + tl;
             if (tile < n_tiles && tl < nt && row < N) {
                 float v = 0.0f;
 #pragma unroll
-                for (int w = 0; w < MK_WARPS; ++w) v += red[((j * MK_WARPS + w) * 16 + rl) * 9 + tl];
+                for (int w = 0; w < MK_WARPS; ++w) v += SM_RED[((j * MK_WARPS + w) * 16 + rl) * RLD + tl];
                 v = (v + (e.bias ? __ldg(e.bias + row) : 0.0f)) * (e.scale ? __ldg(e.scale + row) : 1.0f);
                 if (e.act == 1) v = gelu_ref_f16(v);
                 if (e.res) v += __ldcg(e.res + (size_t) t * N + row);
@@ -312,6 +330,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
                 }
             }
         }
+        __syncthreads();                                         // SM_RED is rewritten by the next iteration
     }
 }
 
