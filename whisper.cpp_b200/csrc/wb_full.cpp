@@ -10,6 +10,9 @@
 #include <map>
 #include <regex>
 #include <thread>
+#include <fstream>
+#include <memory>
+#include <mutex>
 #include "wb_state.h"
 
 using namespace wb;
@@ -218,6 +221,16 @@ whisper_token_data from_samp(const SampOut & o) {
     return t;
 }
 
+// uniform part of the on-device filter: special ids and the switches of whisper_full_params (whisper.cpp:6205-6346)
+void make_samp_cfg(const whisper_context & ctx, const whisper_full_params & params, SampCfg & cfg) {
+    const Vocab & vocab = ctx.vocab;
+    cfg.token_eot = vocab.token_eot; cfg.token_beg = vocab.token_beg; cfg.token_nosp = vocab.token_nosp;
+    { auto it = vocab.token_to_id.find(" "); cfg.space_id = it == vocab.token_to_id.end() ? -1 : it->second; }
+    cfg.suppress_blank = params.suppress_blank ? 1 : 0;
+    cfg.no_timestamps = params.no_timestamps ? 1 : 0;
+    cfg.max_initial_tid = params.max_initial_ts > 0.0f ? (int) std::round(params.max_initial_ts / (float(WB_CHUNK_SIZE) / ctx.model.hp.n_audio_ctx)) : -1;
+}
+
 // state of the logits filter for the NEXT token of a decoder (whisper.cpp:6205, 6252, 6319-6320, 6350-6351)
 void samp_rowinfo(const Vocab & vocab, const whisper_full_params & params, const Decoder & d, int * out2) {
     const auto & cur = d.sequence.tokens;
@@ -375,11 +388,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
     if (dev_samp_ok) {
         build_static_mask(*ctx, params, mask_bits, sreq.mask_key);
         sreq.mask_bits = &mask_bits;
-        sreq.cfg.token_eot = vocab.token_eot; sreq.cfg.token_beg = vocab.token_beg; sreq.cfg.token_nosp = vocab.token_nosp;
-        { auto it = vocab.token_to_id.find(" "); sreq.cfg.space_id = it == vocab.token_to_id.end() ? -1 : it->second; }
-        sreq.cfg.suppress_blank = params.suppress_blank ? 1 : 0;
-        sreq.cfg.no_timestamps = params.no_timestamps ? 1 : 0;
-        sreq.cfg.max_initial_tid = params.max_initial_ts > 0.0f ? (int) std::round(params.max_initial_ts / (float(WB_CHUNK_SIZE) / ctx->model.hp.n_audio_ctx)) : -1;
+        make_samp_cfg(*ctx, params, sreq.cfg);
     }
 
     struct BeamCand { int decoder_idx; int seek_delta; bool has_ts; Sequence sequence; };
@@ -800,6 +809,77 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
     for (auto & t : th) t.join();
     return rc.load();
 }
+// Host-only test hook (no CUDA): the logits filter + greedy pick of this library on injected logits, with the vocabulary of
+// `model_path`.  Same contract as the oracle's wref_process_logits (oracle/ref_harness.cpp), so the two can be compared bit for
+// bit on a CPU-only box.  history: ids already in the decoder's sequence.  Returns 0, or -1 when the file cannot be parsed.
+static whisper_context * dbg_vocab_ctx(const char * model_path) {       // header + vocabulary of a model file, no CUDA
+    static std::mutex mu; static std::map<std::string, std::unique_ptr<whisper_context>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto & slot = cache[model_path];
+    if (!slot) {
+        std::ifstream fin(model_path, std::ios::binary);
+        if (!fin) return nullptr;
+        whisper_model_loader loader = {};
+        loader.context = &fin;
+        loader.read  = [](void * c, void * out, size_t n) -> size_t { auto * f = (std::ifstream *) c; f->read((char *) out, (std::streamsize) n); return (size_t) f->gcount(); };
+        loader.eof   = [](void * c) -> bool { return ((std::ifstream *) c)->eof(); };
+        loader.close = [](void * c) { ((std::ifstream *) c)->close(); };
+        std::unique_ptr<whisper_context> c(new whisper_context());
+        if (!wb::model_load(&loader, c->model, c->vocab, -1)) return nullptr;
+        slot = std::move(c);
+    }
+    return slot.get();
+}
+
+// The ON-DEVICE logits filter + greedy pick (k_greedy_sample) on injected logits: same inputs as wb200_dbg_process_logits at
+// temperature 0; fills `sampled`.  Needs a CUDA device.
+WB_EXPORT int wb200_dbg_greedy_sample(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
+                                      int n_history, int has_ts, int seek_delta, const float * logits_in, whisper_token_data * sampled) {
+    if (!model_path || !params || !logits_in || !sampled) return -1;
+    whisper_context * pc = dbg_vocab_ctx(model_path);
+    if (!pc) return -1;
+    whisper_context & ctx = *pc;
+    const int n = ctx.vocab.n_vocab;
+    Decoder dec;
+    for (int i = 0; i < n_history; ++i) { whisper_token_data td = blank_token(); td.id = history[i]; dec.sequence.tokens.push_back(td); }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta;
+    std::vector<uint32_t> bits; uint64_t key = 0;
+    build_static_mask(ctx, *params, bits, key);
+    SampCfg cfg; make_samp_cfg(ctx, *params, cfg);
+    int rowinfo[2]; samp_rowinfo(ctx.vocab, *params, dec, rowinfo);
+    DevBuf<float> dl; DevBuf<uint32_t> dm; DevBuf<int> dr; DevBuf<SampOut> dout;
+    if (!dl.alloc(n) || !dm.alloc(bits.size()) || !dr.alloc(2) || !dout.alloc(1)) return -2;
+    SampOut o;
+    if (cudaMemcpy(dl.p, logits_in, (size_t) n * 4, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dm.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dr.p, rowinfo, sizeof(rowinfo), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    cfg.mask = dm.p;
+    greedy_sample(dl.p, n, 1, dr.p, cfg, dout.p, nullptr);
+    if (cudaMemcpy(&o, dout.p, sizeof(o), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    *sampled = from_samp(o);
+    return 0;
+}
+
+WB_EXPORT int wb200_dbg_process_logits(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
+                                       int n_history, int has_ts, int seek_delta, float temperature, const float * logits_in,
+                                       float * logits_out, float * logprobs_out, float * probs_out, whisper_token_data * sampled) {
+    if (!model_path || !params || !logits_in) return -1;
+    whisper_context * pc = dbg_vocab_ctx(model_path);
+    if (!pc) return -1;
+    whisper_context & ctx = *pc;
+    const int n = ctx.vocab.n_vocab;
+    whisper_state st;
+    Decoder & dec = st.decoders[0];
+    for (int i = 0; i < n_history; ++i) { whisper_token_data td = blank_token(); td.id = history[i]; dec.sequence.tokens.push_back(td); }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta; dec.i_batch = 0;
+    st.logits.assign(logits_in, logits_in + n);
+    process_logits(ctx, st, dec, *params, temperature);
+    if (logits_out)   memcpy(logits_out,   dec.logits.data(),   (size_t) n * sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), (size_t) n * sizeof(float));
+    if (probs_out)    memcpy(probs_out,    dec.probs.data(),    (size_t) n * sizeof(float));
+    if (sampled)      *sampled = sample_token(ctx, dec, true);
+    return 0;
+}
+
 WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
                                const int * n_samples, int n_chunks, struct whisper_state ** states_out) {
     return wb200_full_batch_ex(ctx, params, samples, n_samples, n_chunks, states_out, 0);

@@ -100,7 +100,7 @@ __global__ void k_fill(float * p, float v, int64_t n) {
 bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int device) {
     const auto t0 = std::chrono::steady_clock::now();
     m.device = device;
-    WB_CUDA_OK(cudaSetDevice(device));
+    if (device >= 0) WB_CUDA_OK(cudaSetDevice(device));          // device < 0: header + vocabulary only, nothing touches CUDA (host-side test hooks)
     Reader R{loader};
 
     uint32_t magic = 0;
@@ -175,6 +175,7 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         }
     }
     if (!R.ok) { set_error("truncated model file (vocab)"); return false; }
+    if (device < 0) return true;
 
     // ------------------------------------------------------------------ allocate the HBM image
     const int d = hp.n_audio_state, La = hp.n_audio_layer, Lt = hp.n_text_layer, V = hp.n_vocab, M = hp.n_mels;
