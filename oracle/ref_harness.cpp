@@ -97,6 +97,16 @@ WREF_API int wref_process_logits(
     return 0;
 }
 
+// beam-search candidates: k draws of whisper_sample_token_topk (src/whisper.cpp:6545-6618) from the distribution left in
+// decoders[0] by the last wref_process_logits call, with decoder.rng = std::mt19937(seed) as whisper_full seeds it (7199)
+WREF_API int wref_sample_topk(struct whisper_context * ctx, struct whisper_state * st, int k, int seed, whisper_token_data * out) {
+    auto & dec = st->decoders[0];
+    dec.rng = std::mt19937(seed);
+    const auto r = whisper_sample_token_topk(*ctx, dec, k);
+    for (int i = 0; i < k; ++i) out[i] = r[i];
+    return 0;
+}
+
 // ---- block quantisers (ggml/src/ggml-quants.c) ------------------------------------------------
 WREF_API int64_t wref_row_size(int type, int64_t n_per_row) { return (int64_t) ggml_row_size((ggml_type) type, n_per_row); }
 WREF_API int64_t wref_quantize(int type, const float * src, void * dst, int64_t nrows, int64_t n_per_row) {

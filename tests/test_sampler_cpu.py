@@ -74,3 +74,33 @@ def test_logits_filter_and_greedy_pick_match_reference(lib, ref, stub):
         assert (td_a.id, td_a.tid) == (td_b.id, td_b.tid)
         assert td_a.p == td_b.p and td_a.plog == td_b.plog and td_a.pt == td_b.pt and td_a.ptsum == td_b.ptsum
     R.whisper_free(rctx)
+
+
+@pytest.mark.parametrize("stub", ["for-tests-ggml-tiny.en.bin", "for-tests-ggml-tiny.bin"])
+def test_beam_candidates_match_reference(lib, ref, stub):
+    """beam search draws its k candidates per beam from std::discrete_distribution(probs) with std::mt19937(j)
+    (whisper_sample_token_topk, src/whisper.cpp:6545-6618): same probabilities + same libstdc++ => the same draws."""
+    L, R, path, rctx = _setup(lib, ref, stub)
+    if not hasattr(R, "wref_sample_topk"):
+        pytest.skip("oracle/_ref predates wref_sample_topk (rebuild with make -C oracle)")
+    n_vocab = R.whisper_n_vocab(rctx)
+    beg, eot = R.whisper_token_beg(rctx), R.whisper_token_eot(rctx)
+    K = 5
+    R.wref_sample_topk.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(TokenData)]
+    L.wb200_dbg_sample_topk.argtypes = [C.c_char_p, C.POINTER(FullParams), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_float, vp,
+                                        C.c_int, C.c_int, C.POINTER(TokenData)]
+    rng = np.random.default_rng(9)
+    for trial in range(12):
+        fp = R.whisper_full_default_params(1)
+        hist, has_ts, sd = ([], 0, 0) if trial % 3 == 0 else ([100, 200, beg + 20], 1, 40) if trial % 3 == 1 else ([int(x) for x in rng.integers(0, eot, 5)], 0, 0)
+        logits = (rng.standard_normal(n_vocab) * (3.0 if trial % 2 else 8.0)).astype(np.float32)      # flat and peaked distributions
+        temp = 0.0 if trial % 4 else 0.4
+        _run_both(L, R, path, rctx, fp, hist, has_ts, sd, temp, logits)               # leaves the distribution in the reference's decoder 0
+        h = (C.c_int * max(1, len(hist)))(*hist)
+        a = (TokenData * K)(); b = (TokenData * K)()
+        assert R.wref_sample_topk(rctx, R.wref_ctx_state(rctx), K, trial, b) == 0
+        assert L.wb200_dbg_sample_topk(path, C.byref(fp), h, len(hist), has_ts, sd, C.c_float(temp), logits.ctypes.data_as(vp), K, trial, a) == 0
+        for i in range(K):
+            assert (a[i].id, a[i].tid) == (b[i].id, b[i].tid), (trial, i)
+            assert a[i].p == b[i].p and a[i].plog == b[i].plog and a[i].pt == b[i].pt and a[i].ptsum == b[i].ptsum
+    R.whisper_free(rctx)

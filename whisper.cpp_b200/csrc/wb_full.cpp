@@ -880,6 +880,26 @@ WB_EXPORT int wb200_dbg_process_logits(const char * model_path, const struct whi
     return 0;
 }
 
+// Host-only: the k beam-search candidates (sample_token_topk) for the same inputs, decoder.rng = std::mt19937(seed)
+WB_EXPORT int wb200_dbg_sample_topk(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
+                                    int n_history, int has_ts, int seek_delta, float temperature, const float * logits_in, int k, int seed,
+                                    whisper_token_data * out) {
+    if (!model_path || !params || !logits_in || !out || k <= 0) return -1;
+    whisper_context * pc = dbg_vocab_ctx(model_path);
+    if (!pc) return -1;
+    whisper_context & ctx = *pc;
+    whisper_state st;
+    Decoder & dec = st.decoders[0];
+    for (int i = 0; i < n_history; ++i) { whisper_token_data td = blank_token(); td.id = history[i]; dec.sequence.tokens.push_back(td); }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta; dec.i_batch = 0;
+    st.logits.assign(logits_in, logits_in + ctx.vocab.n_vocab);
+    process_logits(ctx, st, dec, *params, temperature);
+    dec.rng = std::mt19937(seed);
+    const auto r = sample_token_topk(ctx, dec, k);
+    for (int i = 0; i < k; ++i) out[i] = r[i];
+    return 0;
+}
+
 WB_EXPORT int wb200_full_batch(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
                                const int * n_samples, int n_chunks, struct whisper_state ** states_out) {
     return wb200_full_batch_ex(ctx, params, samples, n_samples, n_chunks, states_out, 0);
