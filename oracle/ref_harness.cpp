@@ -107,6 +107,35 @@ WREF_API int wref_sample_topk(struct whisper_context * ctx, struct whisper_state
     return 0;
 }
 
+// ---- self-attention KV bookkeeping (src/whisper.cpp:1019-1137) on a stand-alone cell table ------------------------------
+// ops: n_ops x 5 ints { op, a, b, c, d }: 0 find_slot(n_tokens=a, first pos=b, seq=c)  1 seq_rm(seq=a, p0=b, p1=c)
+// 2 seq_cp(src=a, dst=b, p0=c, p1=d)  3 clear.  trace: 3 ints per op { return, head, cell_max }; cells_out: 2 ints per cell
+// { pos, bit mask of seq ids }.
+WREF_API int wref_kv_script(int size, const int * ops, int n_ops, int * trace, int * cells_out) {
+    whisper_kv_cache cache;
+    cache.size = size; cache.head = 0; cache.n = 0; cache.k = nullptr; cache.v = nullptr;
+    cache.cells.clear(); cache.cells.resize(size);
+    for (int o = 0; o < n_ops; ++o) {
+        const int * q = ops + 5 * o;
+        int ret = 1;
+        if (q[0] == 0) {
+            whisper_batch b = whisper_batch_init(q[1], 1);
+            b.n_tokens = q[1];
+            for (int i = 0; i < q[1]; ++i) { b.token[i] = 0; b.pos[i] = q[2] + i; b.n_seq_id[i] = 1; b.seq_id[i][0] = q[3]; b.logits[i] = 0; }
+            ret = whisper_kv_cache_find_slot(cache, b) ? 1 : 0;
+            whisper_batch_free(b);
+        } else if (q[0] == 1) whisper_kv_cache_seq_rm(cache, q[1], q[2], q[3]);
+        else if (q[0] == 2)   whisper_kv_cache_seq_cp(cache, q[1], q[2], q[3], q[4]);
+        else { for (auto & c : cache.cells) { c.pos = -1; c.seq_id.clear(); } cache.head = 0; }      // whisper_kv_cache_clear without the buffer
+        trace[3 * o] = ret; trace[3 * o + 1] = (int) cache.head; trace[3 * o + 2] = whisper_kv_cache_cell_max(cache);
+    }
+    for (int i = 0; i < size; ++i) {
+        int m = 0; for (int sid : cache.cells[i].seq_id) m |= 1 << sid;
+        cells_out[2 * i] = cache.cells[i].pos; cells_out[2 * i + 1] = m;
+    }
+    return 0;
+}
+
 // ---- block quantisers (ggml/src/ggml-quants.c) ------------------------------------------------
 WREF_API int64_t wref_row_size(int type, int64_t n_per_row) { return (int64_t) ggml_row_size((ggml_type) type, n_per_row); }
 WREF_API int64_t wref_quantize(int type, const float * src, void * dst, int64_t nrows, int64_t n_per_row) {

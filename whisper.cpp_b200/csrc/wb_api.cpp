@@ -68,6 +68,27 @@ void KvCells::seq_cp(int src, int dst, int p0, int p1) {                        
     for (auto & c : cells) if ((c.seqs & (1u << src)) && c.pos >= p0 && c.pos < p1) c.seqs |= 1u << dst;
 }
 
+// host-only test hook: run a script of KV bookkeeping operations on a stand-alone cell table (same encoding as the oracle's
+// wref_kv_script, oracle/ref_harness.cpp)
+extern "C" WB_EXPORT int wb200_dbg_kv_script(int size, const int * ops, int n_ops, int * trace, int * cells_out) {
+    if (size <= 0 || !ops || !trace || !cells_out) return -1;
+    KvCells kv; kv.reset((uint32_t) size);
+    for (int o = 0; o < n_ops; ++o) {
+        const int * q = ops + 5 * o;
+        int ret = 1;
+        if (q[0] == 0) {
+            std::vector<int> pos(q[1]), seq(q[1], q[3]);
+            for (int i = 0; i < q[1]; ++i) pos[i] = q[2] + i;
+            ret = kv.find_slot(pos.data(), seq.data(), (uint32_t) q[1]) ? 1 : 0;
+        } else if (q[0] == 1) kv.seq_rm(q[1], q[2], q[3]);
+        else if (q[0] == 2)   kv.seq_cp(q[1], q[2], q[3], q[4]);
+        else                  kv.clear();
+        trace[3 * o] = ret; trace[3 * o + 1] = (int) kv.head; trace[3 * o + 2] = kv.cell_max();
+    }
+    for (int i = 0; i < size; ++i) { cells_out[2 * i] = kv.cells[i].pos; cells_out[2 * i + 1] = (int) kv.cells[i].seqs; }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- engine glue
 namespace {
 // host-side preparation of one decode request: KV slot search + attention index lists (whisper.cpp:2876-2948)

@@ -831,6 +831,10 @@ static whisper_context * dbg_vocab_ctx(const char * model_path) {       // heade
     return slot.get();
 }
 
+// Host-only: a context that holds only the header + vocabulary of a model file (no CUDA, no weights, no state).  Valid for the
+// vocabulary / tokenizer / special-token / model-shape getters of whisper.h; owned by the library.
+WB_EXPORT struct whisper_context * wb200_dbg_vocab_context(const char * model_path) { return model_path ? dbg_vocab_ctx(model_path) : nullptr; }
+
 // The ON-DEVICE logits filter + greedy pick (k_greedy_sample) on injected logits: same inputs as wb200_dbg_process_logits at
 // temperature 0; fills `sampled`.  Needs a CUDA device.
 WB_EXPORT int wb200_dbg_greedy_sample(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
