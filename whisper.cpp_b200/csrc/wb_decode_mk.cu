@@ -8,18 +8,18 @@
 // The arithmetic per op is the one of the stand-alone kernels in wb_kernels.cu (Q8_0 activation blocks + integer block
 // dots like the reference CPU path, f16-rounded Q, f32 softmax); this file changes HOW the ops are scheduled:
 //   * grid = one CTA of 16 warps per SM, launched cooperatively; a phase boundary is a grid barrier instead of a kernel
-//     boundary (the decode step is latency-bound: ~270 dependent phases of a few microseconds each);
-//   * every CTA rebuilds the (tiny) quantised activation vector of a GEMV phase in its own shared memory, so LayerNorm and
-//     activation quantisation need no phase of their own; attention and FC1 hand their outputs over already quantised;
-//   * a GEMV phase hands 16-row tiles round-robin to the CTAs; the warps of a CTA split K and reduce through smem.  Weights
-//     are stored tile-major (wb_quant.cuh): a warp fetches the MMA operands of one (tile, block) with three fully coalesced
-//     loads -- the planar layout cost 16 sectors per 128 useful bytes and made the phase L1-sector bound;
-//   * cross-attention (the HBM-heavy part: 2*n_keys*d f16 per row and layer) is cut into (row, head, 128-key) units that are
-//     distributed stream-K style, register-prefetched one unit ahead.
-// The kernel is written for a small instruction footprint: the ~20 phase bodies of a layer are executed once per layer by
-// every warp, so code that does not fit the instruction cache is fetched from L2 again in every layer (measured: 25 cycles
-// per instruction with a 160 KB kernel).  Hence: no 64-bit divisions, approximate reciprocals where they only feed a
-// rounding, shared (noinline) phase functions, modest unrolling.
+//     boundary (the decode step is a chain of ~400 dependent phases of a few microseconds each);
+//   * rows handed from one phase to the next are quantised once by their producer ("actq" rows in global memory): a
+//     distributed LayerNorm -> Q8_0 phase, attention epilogues, and a quantise phase after FC1;
+//   * a GEMV phase is cut by row group first: a CTA stages the 16 rows of its group with TMA bulk copies and walks 16-row
+//     weight tiles, its 16 warps split K and reduce through smem.  Weights are stored tile-major (wb_quant.cuh): a warp fetches
+//     the MMA operands of one (tile, block) with three fully coalesced loads -- with the planar layout every 4-byte gather cost
+//     16 sectors per 128 useful bytes and the phase was L1-sector bound;
+//   * cross-attention (the HBM-heavy part: 2*n_keys*d f16 per row and layer) is cut into (row, head, half of the keys) units,
+//     streamed through a cp.async ring; one lane owns one key-quarter and keeps its own online-softmax state.
+// Lessons that shaped the code (profiles/): no pointers handed through structs (they turn shared-memory accesses into generic
+// loads), no 64-bit divisions in loops, approximate reciprocals where they only feed a rounding, no register moves of
+// in-flight loads, whole 32-byte sectors per load instruction, bulk copies instead of register staging for anything > 16 KB.
 #include <cmath>
 #include "wb_decode_mk.cuh"
 #include "wb_common.h"
@@ -28,7 +28,7 @@
 
 namespace wb {
 
-constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_REDLD = MK_MAXTOK + 1, MK_RED = 4 * 16 * 16 * 17, MK_PART = 68, MK_XSLOTS = 16;
+constexpr int MK_THREADS = 512, MK_WARPS = 16, MK_XKEYS = 128, MK_MAXTOK = 64, MK_RED = 4 * 16 * 16 * 17, MK_PART = 68;
 constexpr int MK_TP = 4;                // weight tiles a GEMV phase keeps in flight per iteration
 static_assert(MK_TP * 16 * 16 * 17 <= MK_RED, "split-K reduction buffer");
 constexpr int MK_ROWB = 1280;            // bytes of one staged activation row chunk (1280 int8 values or 640 halves)
