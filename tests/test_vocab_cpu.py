@@ -52,3 +52,19 @@ def test_vocabulary_and_tokenizer_match_reference(lib, ref, stub):
         assert L.whisper_token_count(lctx, t) == R.whisper_token_count(rctx, t), text
         assert L.whisper_tokenize(lctx, t, a, 1) == R.whisper_tokenize(rctx, t, b, 1), text      # too-small buffer: -n
     R.whisper_free(rctx)
+
+
+def test_header_parser_rejects_bad_files(lib, tmp_path):
+    """loader error paths that need no device (src/whisper.cpp:1497-1500, 1589-1600): bad magic, truncated header / vocabulary"""
+    L = bind_whisper_api(lib)
+    L.wb200_dbg_vocab_context.restype = vp; L.wb200_dbg_vocab_context.argtypes = [C.c_char_p]
+    good = open(os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"), "rb").read()
+    cases = {"magic.bin": b"\x00\x01\x02\x03" + good[4:], "short_header.bin": good[:30], "short_vocab.bin": good[:4 + 44 + 8 + 80 * 201 * 4 + 4 + 1000],
+             "empty.bin": b""}
+    for name, blob in cases.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        assert not L.wb200_dbg_vocab_context(str(p).encode()), name
+    assert not L.wb200_dbg_vocab_context(b"/nonexistent/model.bin")
+    ok = tmp_path / "ok.bin"; ok.write_bytes(good)
+    assert L.wb200_dbg_vocab_context(str(ok).encode())
