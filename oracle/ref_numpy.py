@@ -186,3 +186,109 @@ def log_mel(pcm, filters):
     mmax = mel.max() - 8.0
     mel = np.maximum(mel, mmax)
     return ((mel + 4.0) / 4.0).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# model file (legacy ggml container, src/whisper.cpp:1485-1962) and the text decoder step (src/whisper.cpp:2466-2844)
+# ----------------------------------------------------------------------------------------------------------------------
+def read_model(path):
+    """-> (hparams dict, {tensor name: (ggml type, shape as stored [rows, cols] or [n], raw bytes)})"""
+    import struct
+    with open(path, "rb") as f:
+        blob = f.read()
+    off = 0
+
+    def rd(fmt):
+        nonlocal off
+        v = struct.unpack_from(fmt, blob, off)
+        off += struct.calcsize(fmt)
+        return v
+    assert rd("<I")[0] == 0x67676d6c
+    names = ["n_vocab", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer", "n_text_ctx", "n_text_state", "n_text_head", "n_text_layer", "n_mels", "ftype"]
+    hp = dict(zip(names, rd("<11i")))
+    n_mel, n_fft = rd("<2i")
+    off += n_mel * n_fft * 4
+    for _ in range(rd("<i")[0]):
+        n_bytes = rd("<I")[0]                              # (rd advances `off`: read it before adding)
+        off += n_bytes
+    bpb = {F32: (1, 4), F16: (1, 2), Q4_0: (32, 18), Q5_0: (32, 22), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176)}
+    tensors = {}
+    while off < len(blob):
+        n_dims, length, ttype = rd("<3i")
+        ne = list(rd("<%di" % n_dims))
+        name = blob[off:off + length].decode(); off += length
+        n = int(np.prod(ne))
+        nbytes = n // bpb[ttype][0] * bpb[ttype][1]
+        shape = [ne[1], ne[0]] if n_dims == 2 else ([ne[2], ne[1], ne[0]] if n_dims == 3 else [ne[0]])
+        tensors[name] = (ttype, shape, blob[off:off + nbytes]); off += nbytes
+    return hp, tensors
+
+
+def _vec(t):
+    ttype, shape, raw = t
+    return (np.frombuffer(raw, np.float32) if ttype == F32 else np.frombuffer(raw, np.float16).astype(np.float32)).reshape(shape)
+
+
+def _mul_mat(t, x):
+    """ggml_mul_mat(W, x) as the CPU backend computes it for this weight type (ggml-cpu/ggml-cpu.c:1254-1452)"""
+    ttype, (rows, k), raw = t
+    if ttype == F16:
+        return mul_mat_f16(raw, rows, k, x)
+    if ttype == F32:
+        return (np.asarray(x, np.float64).reshape(-1, k) @ np.frombuffer(raw, np.float32).reshape(rows, k).astype(np.float64).T).astype(np.float32)
+    return mul_mat_q(ttype, raw, rows, k, x)
+
+
+def _rows(t, ids):
+    ttype, (rows, k), raw = t
+    if ttype == F32:
+        return np.frombuffer(raw, np.float32).reshape(rows, k)[ids]
+    return dequantize(ttype, raw, rows, k)[ids]                 # get_rows on a quantised table dequantises exactly (ops.cpp:4850)
+
+
+class DecoderOracle:
+    """whisper_build_graph_decoder for ONE sequence, step by step (flash-attention path, CPU arithmetic):
+    Q/K scaled by 64^-1/4, K/V stored as f16, Q rounded to f16 inside attention, cross-attention over all padded keys."""
+
+    def __init__(self, path):
+        self.hp, self.t = read_model(path)
+        L, d = self.hp["n_text_layer"], self.hp["n_text_state"]
+        self.k = [np.zeros((0, d), np.float32) for _ in range(L)]
+        self.v = [np.zeros((0, d), np.float32) for _ in range(L)]
+
+    def step(self, tokens, n_past, cross_k, cross_v):
+        """tokens: ids fed in this call (positions n_past..); cross_k/v: [L][Tp][d] float32 views of the f16 cross KV.
+        Returns the logits of the LAST fed token."""
+        hp, t = self.hp, self.t
+        d, H, L = hp["n_text_state"], hp["n_text_head"], hp["n_text_layer"]
+        kq = np.float32(64.0) ** np.float32(-0.25)
+        ids = np.asarray(tokens, np.int64)
+        n = len(ids)
+        x = _rows(t["decoder.token_embedding.weight"], ids) + _vec(t["decoder.positional_embedding"])[n_past:n_past + n]
+        f16 = lambda a: np.asarray(a, np.float32).astype(np.float16).astype(np.float32)   # noqa: E731
+        for l in range(L):
+            p = "decoder.blocks.%d." % l
+            cur = layernorm(x, _vec(t[p + "attn_ln.weight"]), _vec(t[p + "attn_ln.bias"]))
+            q = (_mul_mat(t[p + "attn.query.weight"], cur) + _vec(t[p + "attn.query.bias"])) * kq
+            k = _mul_mat(t[p + "attn.key.weight"], cur) * kq
+            v = _mul_mat(t[p + "attn.value.weight"], cur) + _vec(t[p + "attn.value.bias"])
+            self.k[l] = np.concatenate([self.k[l][:n_past], f16(k)]); self.v[l] = np.concatenate([self.v[l][:n_past], f16(v)])
+            att = np.empty((n, d), np.float32)
+            for i in range(n):                                   # causal: token i sees positions <= n_past + i
+                nk = n_past + i + 1
+                for h in range(H):
+                    sl = slice(64 * h, 64 * h + 64)
+                    att[i, sl] = attention(q[i:i + 1, sl], self.k[l][:nk, sl], self.v[l][:nk, sl], 1.0)[0]
+            x = x + _mul_mat(t[p + "attn.out.weight"], att) + _vec(t[p + "attn.out.bias"])
+            cur = layernorm(x, _vec(t[p + "cross_attn_ln.weight"]), _vec(t[p + "cross_attn_ln.bias"]))
+            qc = _mul_mat(t[p + "cross_attn.query.weight"], cur) + _vec(t[p + "cross_attn.query.bias"])
+            att = np.empty((n, d), np.float32)
+            for h in range(H):
+                sl = slice(64 * h, 64 * h + 64)
+                att[:, sl] = attention(qc[:, sl], cross_k[l][:, sl], cross_v[l][:, sl], float(kq))    # all Tp keys, zero rows included
+            x = x + _mul_mat(t[p + "cross_attn.out.weight"], att) + _vec(t[p + "cross_attn.out.bias"])
+            cur = layernorm(x, _vec(t[p + "mlp_ln.weight"]), _vec(t[p + "mlp_ln.bias"]))
+            hcur = gelu(_mul_mat(t[p + "mlp.0.weight"], cur) + _vec(t[p + "mlp.0.bias"]))
+            x = x + _mul_mat(t[p + "mlp.2.weight"], hcur) + _vec(t[p + "mlp.2.bias"])
+        cur = layernorm(x[-1:], _vec(t["decoder.ln.weight"]), _vec(t["decoder.ln.bias"]))
+        return _mul_mat(t["decoder.token_embedding.weight"], cur)[0]
