@@ -1,5 +1,7 @@
 // wb_common.cpp -- error text, launch accounting, logging sink.
 #include "wb_common.h"
+#include <utility>
+#include <map>
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -81,6 +83,20 @@ void logf(int level, const char * fmt, ...) {
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_log_cb(level, buf, g_log_ud);
+}
+
+cudaError_t ensure_dyn_smem(const void * kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t & have = done[std::make_pair(dev, kernel)];
+    if (have >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 
 } // namespace wb

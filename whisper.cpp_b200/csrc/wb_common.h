@@ -13,6 +13,9 @@ const char * last_error();
 
 // every kernel launch issued by this library bumps this counter (bench.py reports it as gpu_launches)
 void     count_launch(uint64_t n = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember (device, kernel) -> bytes so that a process that opens
+// contexts on several GPUs configures every kernel on each of them (thread-safe; a no-op once the size is covered)
+cudaError_t ensure_dyn_smem(const void * kernel, size_t bytes);
 uint64_t launch_count();
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream); off by default.  bench.py uses it for

@@ -667,13 +667,9 @@ int mk_max_rows() { return MK_MAXTOK; }
 
 template <int WT, bool TRACE>
 static bool mk_launch_t(const MkArgs & a, int n_sm, cudaStream_t st) {
-    static bool configured = false;
     const size_t smem = mk_smem_bytes(WT, a.d);
-    if (!configured) {
-        if (cudaFuncSetAttribute(k_decode_pass<WT, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-            set_error("decode megakernel: cannot raise the shared-memory limit"); return false;
-        }
-        configured = true;
+    if (ensure_dyn_smem(reinterpret_cast<const void *>(k_decode_pass<WT, TRACE>), 200 * 1024) != cudaSuccess) {
+        set_error("decode megakernel: cannot raise the shared-memory limit"); return false;
     }
     if (smem > 200 * 1024) { set_error("decode megakernel: %zu bytes of shared memory needed", smem); return false; }
     cudaLaunchConfig_t cfg = {};

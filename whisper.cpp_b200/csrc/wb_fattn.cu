@@ -233,8 +233,7 @@ bool fattn_encoder(const __half * qk, int ld_qk, int k_off, const __half * vt, i
     if (!make_tmap_f16(&tmQ, qk,         64, T, H, n_win, ld_qk, 64, (uint64_t) T * ld_qk, 128)) return false;
     if (!make_tmap_f16(&tmK, qk + k_off, 64, T, H, n_win, ld_qk, 64, (uint64_t) T * ld_qk, 128)) return false;
     if (!make_tmap_f16(&tmV, vt, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) H * 64 * Tp, 64)) return false;
-    static bool attr = false;
-    if (!attr) { WB_CUDA_OK(cudaFuncSetAttribute(fattn_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM)); attr = true; }
+    WB_CUDA_OK(ensure_dyn_smem(reinterpret_cast<const void *>(fattn_enc_kernel), FA_SMEM));
     FattnParams p; p.T = T; p.n_kb = Tp / 128; p.scale_log2e = scale * 1.4426950408889634f; p.out = out; p.ldo = ldo; p.out_win = (int64_t) T * ldo;
     ProfScope prof(PC_ATTN, st, 0.0, (double) n_win * H * (3.0 * 2 * T * (double) Tp * 64));   // QK twice + PV
     fattn_enc_kernel<<<dim3((T + 127) / 128, H, n_win), FA_THREADS, FA_SMEM, st>>>(p, tmQ, tmK, tmV);

@@ -323,11 +323,9 @@ bool make_tmap_f16(CUtensorMap * out, const void * base, uint64_t k, uint64_t ro
 template <int BN, int WT>
 static cudaError_t launch_t(const GemmDesc & g, const GemmKParams & kp, cudaStream_t st) {
     auto kern = gemm_kernel<BN, WT>;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM);
+    {
+        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(kern), GemmCfg<BN>::SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     dim3 grid((g.M + 127) / 128, (g.N + BN - 1) / BN, g.nb0 * g.nb1);
     kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM, st>>>(kp, g.tmA, g.tmB);

@@ -646,8 +646,7 @@ static void gemv_launch(const GemvK & k, cudaStream_t st) {
     tokb = (tokb + 15) & ~size_t(15);
     const size_t smem = tokb * k.n_tok;
     auto kern = k_gemv<WT, NT>;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); smem_set = smem; }
+    if (smem > 48 * 1024) ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem);
     int grid = (N + 7) / 8;                  // one row per warp per pass
     const int cap = 148 * 4;                 // keep the per-CTA prologue amortised over several rows
     if (grid > cap) grid = cap;
