@@ -107,6 +107,38 @@ WREF_API int wref_sample_topk(struct whisper_context * ctx, struct whisper_state
     return 0;
 }
 
+// ---- experimental token-level timestamps + max_len wrapping on an injected segment (src/whisper.cpp:8640-8820, 6096-6147) ----
+// carry[3] = { t_beg, t_last, tid_last } in/out.  tok_out: per token of the ORIGINAL segment { t0, t1 } and vlen; piece_out: per
+// resulting segment { t0, t1, n_tokens }.  Returns the number of segments the injected one was wrapped into.
+WREF_API int wref_token_timestamps(struct whisper_context * ctx, struct whisper_state * st, const int * ids, const int * tids, const float * pt,
+                                   const float * ptsum, int n, int64_t seg_t0, int64_t seg_t1, const float * energy, int n_energy,
+                                   float thold_pt, float thold_ptsum, int max_len, int split_on_word, int64_t * carry,
+                                   int64_t * tok_out, float * vlen_out, int64_t * piece_out, int max_pieces) {
+    st->result_all.clear();
+    st->energy.assign(energy, energy + n_energy);
+    st->t_beg = carry[0]; st->t_last = carry[1]; st->tid_last = (whisper_token) carry[2];
+    whisper_segment seg = { seg_t0, seg_t1, "", 0.0f, {}, false };
+    for (int i = 0; i < n; ++i) {
+        whisper_token_data td = { ids[i], tids[i], 0.0f, 0.0f, pt[i], ptsum[i], -1, -1, -1, 0.0f };
+        seg.tokens.push_back(td);
+    }
+    st->result_all.push_back(seg);
+    whisper_exp_compute_token_level_timestamps(*ctx, *st, 0, thold_pt, thold_ptsum);
+    for (int i = 0; i < n; ++i) { tok_out[2 * i] = st->result_all[0].tokens[i].t0; tok_out[2 * i + 1] = st->result_all[0].tokens[i].t1; vlen_out[i] = st->result_all[0].tokens[i].vlen; }
+    int pieces = 1;
+    if (max_len > 0) pieces = whisper_wrap_segment(*ctx, *st, max_len, split_on_word != 0);
+    for (int i = 0; i < (int) st->result_all.size() && i < max_pieces; ++i) {
+        piece_out[3 * i] = st->result_all[i].t0; piece_out[3 * i + 1] = st->result_all[i].t1; piece_out[3 * i + 2] = (int64_t) st->result_all[i].tokens.size();
+    }
+    carry[0] = st->t_beg; carry[1] = st->t_last; carry[2] = st->tid_last;
+    return pieces;
+}
+WREF_API int wref_signal_energy(const float * pcm, int n, int hw, float * out) {
+    const auto e = get_signal_energy(pcm, n, hw);
+    memcpy(out, e.data(), (size_t) n * sizeof(float));
+    return 0;
+}
+
 // ---- self-attention KV bookkeeping (src/whisper.cpp:1019-1137) on a stand-alone cell table ------------------------------
 // ops: n_ops x 5 ints { op, a, b, c, d }: 0 find_slot(n_tokens=a, first pos=b, seq=c)  1 seq_rm(seq=a, p0=b, p1=c)
 // 2 seq_cp(src=a, dst=b, p0=c, p1=d)  3 clear.  trace: 3 ints per op { return, head, cell_max }; cells_out: 2 ints per cell

@@ -188,6 +188,160 @@ std::string to_timestamp(int64_t t, bool comma = false) {
     return buf;
 }
 
+// ---- experimental token-level timestamps (params.token_timestamps; src/whisper.cpp:8500-8820) and max_len wrapping (6096-6147) ----
+// weight of a token's text in the split of a time interval: spaces ~0, letters 1, commas 2, sentence marks and digits 3
+// (UTF-8 aware, full-width forms count like their ASCII twins; src/whisper.cpp:8512-8590)
+float voice_length(const std::string & text) {
+    const unsigned char * s = (const unsigned char *) text.data();
+    const size_t n = text.size();
+    float res = 0.0f;
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char c = s[i];
+        int len = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 1;
+        uint32_t cp = len == 1 ? c : len == 2 ? (c & 0x1Fu) : len == 3 ? (c & 0x0Fu) : (c & 0x07u);
+        bool ok = i + (size_t) len <= n;
+        for (int k = 1; ok && k < len; ++k) {
+            if ((s[i + k] & 0xC0) != 0x80) ok = false; else cp = (cp << 6) | (s[i + k] & 0x3Fu);
+        }
+        if (!ok) { cp = c; len = 1; }                            // invalid sequence: the lead byte counts as one symbol
+        i += (size_t) len;
+        if (cp == ' ' || cp == 0x3000) res += 0.01f;
+        else if (cp == ',' || cp == 0xFF0C || cp == 0x3001 || cp == 0xFF1B || cp == 0xFF1A) res += 2.00f;
+        else if (cp == '.' || cp == '!' || cp == '?' || cp == 0x3002 || cp == 0xFF0E || cp == 0xFF01 || cp == 0xFF1F || cp == 0x2026) res += 3.00f;
+        else if ((cp >= '0' && cp <= '9') || (cp >= 0xFF10 && cp <= 0xFF19)) res += 3.00f;
+        else res += 1.00f;
+    }
+    return res;
+}
+
+// mean |signal| over a window of 2*hw+1 samples, window clipped at the ends but always divided by 2*hw+1 (whisper.cpp:8593-8609)
+std::vector<float> signal_energy(const float * signal, int n_samples, int hw) {
+    std::vector<float> out((size_t) std::max(n_samples, 0));
+    for (int i = 0; i < n_samples; ++i) {
+        float sum = 0;
+        for (int j = std::max(0, i - hw); j <= std::min(n_samples - 1, i + hw); ++j) sum += fabs(signal[j]);
+        out[i] = sum / (2 * hw + 1);
+    }
+    return out;
+}
+
+// token t0/t1 of segment `i_segment`: anchor on confident timestamp predictions (pt, ptsum), share the gaps in proportion to the
+// voice length, then snap to the signal energy.  state.t_beg / t_last / tid_last carry over between segments.
+void token_level_timestamps(whisper_context & ctx, whisper_state & st, int i_segment, float thold_pt, float thold_ptsum) {
+    Segment & seg = st.result_all[i_segment];
+    auto & tk = seg.tokens;
+    const int n_samples = (int) st.energy.size(), n = (int) tk.size();
+    if (n_samples == 0) { logf(LOG_ERROR, "%s: no signal data available\n", __func__); return; }
+    if (n == 0) return;
+    const int64_t t0 = seg.t0, t1 = seg.t1;
+    if (n == 1) { tk[0].t0 = t0; tk[0].t1 = t1; return; }
+    const whisper_token beg = ctx.vocab.token_beg, eot = ctx.vocab.token_eot;
+
+    for (int j = 0; j < n; ++j) {
+        if (j == 0) {
+            if (tk[0].id == beg) { tk[0].t0 = t0; tk[0].t1 = t0; tk[1].t0 = t0; st.t_beg = t0; st.t_last = t0; st.tid_last = beg; }
+            else tk[0].t0 = st.t_last;
+        }
+        const int64_t tt = st.t_beg + 2 * (tk[j].tid - beg);
+        tk[j].vlen = voice_length(whisper_token_to_str(&ctx, tk[j].id));
+        if (tk[j].pt > thold_pt && tk[j].ptsum > thold_ptsum && tk[j].tid > st.tid_last && tt <= t1) {
+            if (j > 0) tk[j - 1].t1 = tt;
+            tk[j].t0 = tt;
+            st.tid_last = tk[j].tid;
+        }
+    }
+    tk[n - 2].t1 = t1; tk[n - 1].t0 = t1; tk[n - 1].t1 = t1;
+    st.t_last = t1;
+
+    // runs of tokens without an end time share [t0 of the first, t1 of the last] in proportion to their voice length
+    for (int p0 = 0; p0 < n; ) {
+        int p1 = p0;
+        while (p1 < n && tk[p1].t1 < 0) ++p1;
+        if (p1 >= n) p1 = n - 1;
+        if (p1 > p0) {
+            double psum = 0.0;
+            for (int j = p0; j <= p1; ++j) psum += tk[j].vlen;
+            const double dt = tk[p1].t1 - tk[p0].t0;
+            for (int j = p0 + 1; j <= p1; ++j) {
+                const double ct = tk[j - 1].t0 + dt * tk[j - 1].vlen / psum;
+                tk[j - 1].t1 = ct; tk[j].t0 = ct;
+            }
+        }
+        p0 = p1 + 1;
+    }
+    for (int j = 0; j < n - 1; ++j) {                            // keep the intervals ordered
+        if (tk[j].t1 < 0) tk[j + 1].t0 = tk[j].t1;
+        if (j > 0 && tk[j - 1].t1 > tk[j].t0) { tk[j].t0 = tk[j - 1].t1; tk[j].t1 = std::max(tk[j].t0, tk[j].t1); }
+    }
+
+    // stretch or shrink every text token to the region where the signal is above half of its local mean
+    auto to_sample = [&](int64_t t) { return std::max(0, std::min(n_samples - 1, (int) (((t - seg.t0) * WB_SAMPLE_RATE) / 100))); };
+    auto to_time   = [&](int k) -> int64_t { return (100ll * k) / WB_SAMPLE_RATE + seg.t0; };
+    const int hw = WB_SAMPLE_RATE / 8;
+    for (int j = 0; j < n; ++j) {
+        if (tk[j].id >= eot) continue;
+        int s0 = to_sample(tk[j].t0), s1 = to_sample(tk[j].t1);
+        const int ss0 = std::max(s0 - hw, 0), ss1 = std::min(s1 + hw, n_samples);
+        float sum = 0.0f;
+        for (int k = ss0; k < ss1; ++k) sum += st.energy[k];
+        const float thold = 0.5 * sum / (ss1 - ss0);
+        {
+            int k = s0;
+            if (st.energy[k] > thold && j > 0) {
+                while (k > 0 && st.energy[k] > thold) --k;
+                tk[j].t0 = to_time(k);
+                if (tk[j].t0 < tk[j - 1].t1) tk[j].t0 = tk[j - 1].t1; else s0 = k;
+            } else {
+                while (st.energy[k] < thold && k < s1) ++k;
+                s0 = k;
+                tk[j].t0 = to_time(k);
+            }
+        }
+        {
+            int k = s1;
+            if (st.energy[k] > thold) {
+                while (k < n_samples - 1 && st.energy[k] > thold) ++k;
+                tk[j].t1 = to_time(k);
+                if (j < n - 1 && tk[j].t1 > tk[j + 1].t0) tk[j].t1 = tk[j + 1].t0; else s1 = k;
+            } else {
+                while (st.energy[k] < thold && k > s0) --k;
+                s1 = k;
+                tk[j].t1 = to_time(k);
+            }
+        }
+    }
+}
+
+// split the last segment so that no piece has more than max_len characters (UTF-8 code points); returns the number of pieces
+int wrap_segment(whisper_context & ctx, whisper_state & st, int max_len, bool split_on_word) {
+    Segment cur = st.result_all.back();
+    int pieces = 1, acc = 0;
+    std::string text;
+    for (int i = 0; i < (int) cur.tokens.size(); ++i) {
+        const whisper_token_data & tok = cur.tokens[i];
+        if (tok.id >= ctx.vocab.token_eot) continue;
+        const char * txt = whisper_token_to_str(&ctx, tok.id);
+        int chars = 0;
+        for (const char * q = txt; *q; ++q) if ((*q & 0xC0) != 0x80) ++chars;
+        if (acc + chars > max_len && i > 0 && (!split_on_word || txt[0] == ' ')) {
+            Segment & head = st.result_all.back();
+            head.text = std::move(text); head.t1 = tok.t0; head.tokens.resize(i); head.speaker_turn_next = false;
+            Segment tail;
+            tail.t0 = tok.t0; tail.t1 = cur.t1; tail.tokens.assign(cur.tokens.begin() + i, cur.tokens.end()); tail.speaker_turn_next = cur.speaker_turn_next;
+            st.result_all.push_back(tail);
+            acc = 0; text.clear();
+            cur = st.result_all.back();
+            i = -1;
+            ++pieces;
+        } else {
+            acc += chars; text += txt;
+        }
+    }
+    st.result_all.back().text = std::move(text);
+    return pieces;
+}
+
 // static part of the logits filter as a bit mask for the on-device sampler (same ids process_logits suppresses)
 void build_static_mask(const whisper_context & ctx, const whisper_full_params & params, std::vector<uint32_t> & bits, uint64_t & key) {
     const Vocab & vocab = ctx.vocab;
@@ -300,9 +454,21 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
         logf(LOG_INFO, "%s: auto-detected language: %s (p = %f)\n", __func__, params.language, probs[lang_id]);
         if (params.detect_language) return 0;
     }
-    if (params.token_timestamps) {
-        static std::atomic<bool> warned{false};
-        if (!warned.exchange(true)) logf(LOG_WARN, "%s: token_timestamps (experimental) is not implemented by this engine; token t0/t1 stay -1\n", __func__);
+    if (params.token_timestamps) {                               // whisper.cpp:6868-6875
+        state->t_beg = 0; state->t_last = 0; state->tid_last = 0;
+        if (n_samples > 0) {
+            std::vector<float> host;
+            const float * pcm = samples;
+            if (!samples || wb::tls_pcm_is_device()) {            // PCM lives in HBM (wb200_pcm_upload / device-pointer batch): bring it back once
+                host.resize((size_t) n_samples);
+                const float * src = samples ? samples : state->fe.pcm.p;
+                if (!src || cudaMemcpy(host.data(), src, (size_t) n_samples * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    logf(LOG_ERROR, "%s: cannot read the PCM back for token_timestamps\n", __func__); return -2;
+                }
+                pcm = host.data();
+            }
+            state->energy = signal_energy(pcm, n_samples, 32);
+        }
     }
     if (params.grammar_rules && params.n_grammar_rules > 0) {
         static std::atomic<bool> warned{false};
@@ -658,7 +824,12 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                     Segment sg; sg.t0 = a; sg.t1 = b; sg.text = text; sg.no_speech_prob = state->no_speech_prob; sg.speaker_turn_next = speaker_turn_next;
                     for (int j = from; j <= to_incl; ++j) sg.tokens.push_back(cur[j]);
                     result_all.push_back(std::move(sg));
-                    if (params.new_segment_callback) params.new_segment_callback(ctx, state, 1, params.new_segment_callback_user_data);
+                    int n_new = 1;
+                    if (params.token_timestamps) {               // whisper.cpp:7688-7695
+                        token_level_timestamps(*ctx, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
+                        if (params.max_len > 0) n_new = wrap_segment(*ctx, *state, params.max_len, params.split_on_word);
+                    }
+                    if (params.new_segment_callback) params.new_segment_callback(ctx, state, n_new, params.new_segment_callback_user_data);
                 };
                 for (int i = 0; i < (int) cur.size(); ++i) {
                     if (params.print_special || cur[i].id < vocab.token_eot) text += whisper_token_to_str(ctx, cur[i].id);
@@ -881,6 +1052,37 @@ WB_EXPORT int wb200_dbg_process_logits(const char * model_path, const struct whi
     if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), (size_t) n * sizeof(float));
     if (probs_out)    memcpy(probs_out,    dec.probs.data(),    (size_t) n * sizeof(float));
     if (sampled)      *sampled = sample_token(ctx, dec, true);
+    return 0;
+}
+
+// Host-only: experimental token-level timestamps + max_len wrapping on an injected segment (same contract as the oracle's
+// wref_token_timestamps) and the signal-energy envelope they use
+WB_EXPORT int wb200_dbg_token_timestamps(const char * model_path, const int * ids, const int * tids, const float * pt, const float * ptsum, int n,
+                                         int64_t seg_t0, int64_t seg_t1, const float * energy, int n_energy, float thold_pt, float thold_ptsum,
+                                         int max_len, int split_on_word, int64_t * carry, int64_t * tok_out, float * vlen_out,
+                                         int64_t * piece_out, int max_pieces) {
+    whisper_context * pc = model_path ? dbg_vocab_ctx(model_path) : nullptr;
+    if (!pc || !ids || !tids || !pt || !ptsum || !energy || !carry || !tok_out || !vlen_out || !piece_out) return -1;
+    whisper_state st;
+    st.energy.assign(energy, energy + n_energy);
+    st.t_beg = carry[0]; st.t_last = carry[1]; st.tid_last = (whisper_token) carry[2];
+    Segment seg; seg.t0 = seg_t0; seg.t1 = seg_t1;
+    for (int i = 0; i < n; ++i) { whisper_token_data td = blank_token(); td.id = ids[i]; td.tid = tids[i]; td.pt = pt[i]; td.ptsum = ptsum[i]; seg.tokens.push_back(td); }
+    st.result_all.push_back(seg);
+    token_level_timestamps(*pc, st, 0, thold_pt, thold_ptsum);
+    for (int i = 0; i < n; ++i) { tok_out[2 * i] = st.result_all[0].tokens[i].t0; tok_out[2 * i + 1] = st.result_all[0].tokens[i].t1; vlen_out[i] = st.result_all[0].tokens[i].vlen; }
+    int pieces = 1;
+    if (max_len > 0) pieces = wrap_segment(*pc, st, max_len, split_on_word != 0);
+    for (int i = 0; i < (int) st.result_all.size() && i < max_pieces; ++i) {
+        piece_out[3 * i] = st.result_all[i].t0; piece_out[3 * i + 1] = st.result_all[i].t1; piece_out[3 * i + 2] = (int64_t) st.result_all[i].tokens.size();
+    }
+    carry[0] = st.t_beg; carry[1] = st.t_last; carry[2] = st.tid_last;
+    return pieces;
+}
+WB_EXPORT int wb200_dbg_signal_energy(const float * pcm, int n, int hw, float * out) {
+    if (!pcm || !out || n < 0) return -1;
+    const auto e = signal_energy(pcm, n, hw);
+    memcpy(out, e.data(), (size_t) n * sizeof(float));
     return 0;
 }
 

@@ -80,6 +80,9 @@ struct whisper_state {
     float no_speech_prob = 0.0f;
     int   exp_n_audio_ctx = 0;
     int   slot = 0;                            // cross-KV slot used by this state's decodes
+    // experimental token-level timestamps (src/whisper.cpp:907-912, 8640-8820)
+    int64_t t_beg = 0, t_last = 0; whisper_token tid_last = 0;
+    std::vector<float> energy;                 // |PCM| averaged over +-32 samples
 };
 
 struct whisper_context {
