@@ -97,6 +97,34 @@ WREF_API int wref_process_logits(
     return 0;
 }
 
+// the same with a grammar (params->grammar_rules): the decoder's parse state is initialised from the rules and advanced over
+// `accepted` (whisper_grammar_accept_token, src/whisper.cpp:5901-5923) before the logits are filtered
+WREF_API int wref_process_logits_grammar(
+        struct whisper_context * ctx, struct whisper_state * st, const struct whisper_full_params * params,
+        const whisper_token * history, int n_history, int has_ts, int seek_delta, float temperature,
+        const whisper_token * accepted, int n_accepted,
+        const float * logits_in, float * logits_out, float * logprobs_out, float * probs_out, whisper_token_data * sampled, int * n_stacks_out) {
+    const int n_vocab = ctx->vocab.n_vocab;
+    auto & dec = st->decoders[0];
+    dec.sequence.tokens.clear();
+    for (int i = 0; i < n_history; ++i) {
+        whisper_token_data td = { history[i], 0, 0.0f, 0.0f, 0.0f, 0.0f, -1, -1, -1, 0.0f };
+        dec.sequence.tokens.push_back(td);
+    }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta; dec.i_batch = 0;
+    dec.grammar = whisper_grammar_init(params->grammar_rules, params->n_grammar_rules, params->i_start_rule);
+    for (int i = 0; i < n_accepted; ++i) whisper_grammar_accept_token(*ctx, dec.grammar, accepted[i]);
+    if (n_stacks_out) *n_stacks_out = (int) dec.grammar.stacks.size();
+    st->logits.assign(logits_in, logits_in + n_vocab);
+    whisper_process_logits(*ctx, *st, dec, *params, temperature);
+    if (logits_out)   memcpy(logits_out,   dec.logits.data(),   n_vocab*sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), n_vocab*sizeof(float));
+    if (probs_out)    memcpy(probs_out,    dec.probs.data(),    n_vocab*sizeof(float));
+    if (sampled)      *sampled = whisper_sample_token(*ctx, dec, true);
+    dec.grammar = {};
+    return 0;
+}
+
 // beam-search candidates: k draws of whisper_sample_token_topk (src/whisper.cpp:6545-6618) from the distribution left in
 // decoders[0] by the last wref_process_logits call, with decoder.rng = std::mt19937(seed) as whisper_full seeds it (7199)
 WREF_API int wref_sample_topk(struct whisper_context * ctx, struct whisper_state * st, int k, int seed, whisper_token_data * out) {

@@ -37,7 +37,7 @@ void compute_probs(const std::vector<float> & logits, int n, const std::vector<f
     for (int i = 0; i < n; ++i) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
 }
 
-// src/whisper.cpp:6196-6471 without the grammar branch (grammar sampling is out of scope)
+// src/whisper.cpp:6196-6471
 void process_logits(whisper_context & ctx, whisper_state & st, Decoder & dec, const whisper_full_params & params, float temperature) {
     const Vocab & vocab = ctx.vocab;
     const auto & cur = dec.sequence.tokens;
@@ -108,6 +108,10 @@ void process_logits(whisper_context & ctx, whisper_state & st, Decoder & dec, co
         }
         const float max_text = *std::max_element(logprobs.begin(), logprobs.begin() + vocab.token_beg);
         if (ts_logprob > max_text) for (int i = 0; i < vocab.token_beg; ++i) { logits[i] = -INFINITY; logprobs[i] = -INFINITY; }
+        else if (params.n_grammar_rules > 0) {                   // whisper.cpp:6388-6410: penalise what the grammar cannot continue with
+            grammar_penalize(vocab, dec.grammar, params.grammar_penalty, logits);
+            compute_logprobs(logits, n, logprobs);
+        }
     }
     compute_probs(logits, n, logprobs, probs);
 }
@@ -470,10 +474,6 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
             state->energy = signal_energy(pcm, n_samples, 32);
         }
     }
-    if (params.grammar_rules && params.n_grammar_rules > 0) {
-        static std::atomic<bool> warned{false};
-        if (!warned.exchange(true)) logf(LOG_WARN, "%s: grammar-constrained sampling is out of scope for this engine; grammar ignored\n", __func__);
-    }
 
     const int seek_start = params.offset_ms / 10;
     const int seek_end = params.duration_ms == 0 ? whisper_n_len_from_state(state) : seek_start + params.duration_ms / 10;
@@ -549,7 +549,8 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
 
     // on-device logits filter + greedy pick (decode results come back as 32 bytes per sequence instead of n_vocab floats);
     // used whenever the step is a pure argmax: greedy strategy at temperature 0 without a user logits callback
-    const bool dev_samp_ok = params.strategy == WHISPER_SAMPLING_GREEDY && !params.logits_filter_callback && getenv("WB200_HOST_SAMPLER") == nullptr;
+    const bool dev_samp_ok = params.strategy == WHISPER_SAMPLING_GREEDY && !params.logits_filter_callback && !(params.grammar_rules && params.n_grammar_rules > 0) &&
+                             getenv("WB200_HOST_SAMPLER") == nullptr;
     std::vector<uint32_t> mask_bits; SampReq sreq; std::vector<int> rowinfo;
     if (dev_samp_ok) {
         build_static_mask(*ctx, params, mask_bits, sreq.mask_key);
@@ -557,7 +558,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
         make_samp_cfg(*ctx, params, sreq.cfg);
     }
 
-    struct BeamCand { int decoder_idx; int seek_delta; bool has_ts; Sequence sequence; };
+    struct BeamCand { int decoder_idx; int seek_delta; bool has_ts; Sequence sequence; Grammar grammar; };
     std::vector<std::vector<BeamCand>> bc_per_dec(n_decoders);
     std::vector<BeamCand> cands;
     std::vector<int> b_tok, b_pos, b_seq; std::vector<int8_t> b_want;
@@ -589,6 +590,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 d.sequence.sum_logprobs = -INFINITY; d.sequence.avg_logprobs = -INFINITY; d.sequence.entropy = 0.0; d.sequence.score = -INFINITY;
                 d.seek_delta = 100 * WB_CHUNK_SIZE;
                 d.failed = d.completed = d.has_ts = false;
+                d.grammar = params.grammar_rules ? grammar_init(params.grammar_rules, params.n_grammar_rules, params.i_start_rule) : Grammar();   // whisper.cpp:7117-7121
             }
 
             { // prompt + KV cache for this attempt (whisper.cpp:7126-7221)
@@ -669,7 +671,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                             } else {
                                 const auto toks = sample_token_topk(*ctx, d, params.beam_search.beam_size);
                                 for (const auto & tk : toks) {
-                                    bc_per_dec[j].push_back({ j, d.seek_delta, d.has_ts, d.sequence });
+                                    bc_per_dec[j].push_back({ j, d.seek_delta, d.has_ts, d.sequence, d.grammar });
                                     bc_per_dec[j].back().sequence.tokens.push_back(tk);
                                     bc_per_dec[j].back().sequence.sum_logprobs_all += tk.plog;
                                 }
@@ -693,7 +695,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         if (cur_c >= cands.size()) cur_c = 0;
                         BeamCand & c = cands[cur_c++];
                         while (cands.size() > cur_c && tokens_equal(cands[cur_c].sequence, c.sequence) && i > 0) ++cur_c;
-                        d.seek_delta = c.seek_delta; d.has_ts = c.has_ts; d.sequence = c.sequence;
+                        d.seek_delta = c.seek_delta; d.has_ts = c.has_ts; d.sequence = c.sequence; d.grammar = c.grammar;
                         state->kv.seq_cp(c.decoder_idx, MAX_DECODERS + j, -1, -1);
                     }
                     for (int j = 0; j < n_cur; ++j) {
@@ -716,6 +718,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                             if (d.has_ts && d.seek_delta > sd_new && result_len < i) { d.failed = true; continue; }
                             d.seek_delta = sd_new; result_len = i + 1; d.has_ts = true;
                         }
+                        grammar_accept_token(vocab, d.grammar, tk.id);       // whisper.cpp:7395
                         if (tk.id == vocab.token_eot || (params.max_tokens > 0 && i >= params.max_tokens) ||
                             (d.has_ts && seek + d.seek_delta + delta_min >= seek_end)) {
                             if (result_len == 0 && !params.no_timestamps) {
@@ -1083,6 +1086,33 @@ WB_EXPORT int wb200_dbg_signal_energy(const float * pcm, int n, int hw, float * 
     if (!pcm || !out || n < 0) return -1;
     const auto e = signal_energy(pcm, n, hw);
     memcpy(out, e.data(), (size_t) n * sizeof(float));
+    return 0;
+}
+
+// Host-only: logits filter with a grammar; the parse state is built from params->grammar_rules and advanced over `accepted` first
+// (same contract as the oracle's wref_process_logits_grammar)
+WB_EXPORT int wb200_dbg_process_logits_grammar(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
+                                               int n_history, int has_ts, int seek_delta, float temperature, const whisper_token * accepted, int n_accepted,
+                                               const float * logits_in, float * logits_out, float * logprobs_out, float * probs_out,
+                                               whisper_token_data * sampled, int * n_stacks_out) {
+    if (!model_path || !params || !logits_in) return -1;
+    whisper_context * pc = dbg_vocab_ctx(model_path);
+    if (!pc) return -1;
+    whisper_context & ctx = *pc;
+    const int n = ctx.vocab.n_vocab;
+    whisper_state st;
+    Decoder & dec = st.decoders[0];
+    for (int i = 0; i < n_history; ++i) { whisper_token_data td = blank_token(); td.id = history[i]; dec.sequence.tokens.push_back(td); }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta; dec.i_batch = 0;
+    dec.grammar = grammar_init(params->grammar_rules, params->n_grammar_rules, params->i_start_rule);
+    for (int i = 0; i < n_accepted; ++i) grammar_accept_token(ctx.vocab, dec.grammar, accepted[i]);
+    if (n_stacks_out) *n_stacks_out = (int) dec.grammar.stacks.size();
+    st.logits.assign(logits_in, logits_in + n);
+    process_logits(ctx, st, dec, *params, temperature);
+    if (logits_out)   memcpy(logits_out,   dec.logits.data(),   (size_t) n * sizeof(float));
+    if (logprobs_out) memcpy(logprobs_out, dec.logprobs.data(), (size_t) n * sizeof(float));
+    if (probs_out)    memcpy(probs_out,    dec.probs.data(),    (size_t) n * sizeof(float));
+    if (sampled)      *sampled = sample_token(ctx, dec, true);
     return 0;
 }
 

@@ -12,6 +12,7 @@
 #include <vector>
 #include "../../include/whisper_b200.h"
 #include "wb_engine.h"
+#include "wb_grammar.h"
 
 namespace wb {
 
@@ -44,6 +45,7 @@ struct Decoder {
     std::vector<float> probs, logits, logprobs;
     std::vector<std::pair<double, int>> logits_id;
     std::mt19937 rng;
+    Grammar grammar;                           // GBNF parse state of the tokens generated so far (params.grammar_rules)
     bool have_pending = false;                 // next token already chosen by the on-device sampler
     whisper_token_data pending;
 };
