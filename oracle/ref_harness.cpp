@@ -10,6 +10,7 @@
 //   cross / self KV caches     whisper_state::kv_cross/self  (src/whisper.cpp:2278-2354, 2567-2599)
 //   logits filter + sampler    whisper_process_logits / whisper_sample_token (src/whisper.cpp:6196-6543)
 //   block (de)quantisers       ggml_quantize_chunk / type traits (ggml/src/ggml-quants.c)
+//   VAD segments / PCM cut     whisper_vad_segments_from_probs, whisper_vad (src/whisper.cpp:5229-5463, 6669-6829)
 //
 // The whisper.h API of the reference is exported unchanged by the same library.
 
@@ -194,6 +195,43 @@ WREF_API int wref_kv_script(int size, const int * ops, int n_ops, int * trace, i
         cells_out[2 * i] = cache.cells[i].pos; cells_out[2 * i + 1] = m;
     }
     return 0;
+}
+
+// ---- voice-activity detection (src/whisper.cpp:4367-5515, 6669-6829, 7959-8130) -------------------------------------
+// probabilities -> segments with the reference's own whisper_vad_segments_from_probs (it reads only n_window and probs)
+WREF_API int wref_vad_segments(const float * probs, int n_probs, struct whisper_vad_params params, int64_t * t0, int64_t * t1, int cap) {
+    whisper_vad_context v;
+    v.n_window = 512;
+    v.probs.assign(probs, probs + n_probs);
+    whisper_vad_segments * s = whisper_vad_segments_from_probs(&v, params);
+    if (!s) return -1;
+    const int n = (int) s->data.size();
+    if (n > cap) { whisper_vad_free_segments(s); return -2; }
+    for (int i = 0; i < n; ++i) { t0[i] = s->data[i].start; t1[i] = s->data[i].end; }
+    whisper_vad_free_segments(s);
+    return n;
+}
+// the static whisper_vad() of whisper_full (params.vad_model_path must name a VAD model): filtered PCM, mapping table,
+// per-segment info, and the two time mappings evaluated at the query times q
+WREF_API int wref_vad_cut(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples,
+                          float * filtered, int cap, int64_t * table, int * n_table, int64_t * info, int * n_info,
+                          const int64_t * q, int n_q, int64_t * q_seg, int64_t * q_tok) {
+    std::vector<float> out;
+    whisper_state * st = ctx->state;
+    if (!whisper_vad(ctx, st, params, samples, n_samples, out)) return -1;
+    if ((int) out.size() > cap) return -2;
+    memcpy(filtered, out.data(), out.size()*sizeof(float));
+    *n_table = (int) st->vad_mapping_table.size(); *n_info = (int) st->vad_segments.size();
+    for (size_t i = 0; i < st->vad_mapping_table.size(); ++i) { table[2*i] = st->vad_mapping_table[i].processed_time; table[2*i + 1] = st->vad_mapping_table[i].original_time; }
+    for (size_t i = 0; i < st->vad_segments.size(); ++i) {
+        info[4*i] = st->vad_segments[i].orig_start; info[4*i + 1] = st->vad_segments[i].orig_end;
+        info[4*i + 2] = st->vad_segments[i].vad_start; info[4*i + 3] = st->vad_segments[i].vad_end;
+    }
+    for (int i = 0; i < n_q; ++i) {
+        q_seg[i] = map_processed_to_original_time(q[i], st->vad_mapping_table);
+        q_tok[i] = whisper_map_token_time_segment_aware(q[i], st->vad_segments);
+    }
+    return (int) out.size();
 }
 
 // ---- block quantisers (ggml/src/ggml-quants.c) ------------------------------------------------

@@ -599,10 +599,19 @@ WB_EXPORT int whisper_full_n_segments_from_state(struct whisper_state * st) { re
 WB_EXPORT int whisper_full_n_segments(struct whisper_context * ctx)         { return (int) ctx->state->result_all.size(); }
 WB_EXPORT int whisper_full_lang_id_from_state(struct whisper_state * st)    { return st->lang_id; }
 WB_EXPORT int whisper_full_lang_id(struct whisper_context * ctx)            { return ctx->state->lang_id; }
-WB_EXPORT int64_t whisper_full_get_segment_t0_from_state(struct whisper_state * st, int i) { return SEG(st, i).t0; }
-WB_EXPORT int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).t0; }
-WB_EXPORT int64_t whisper_full_get_segment_t1_from_state(struct whisper_state * st, int i) { return SEG(st, i).t1; }
-WB_EXPORT int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).t1; }
+// with VAD the stored times are on the cut timeline; map them back to the original audio (whisper.cpp:8001-8033)
+WB_EXPORT int64_t whisper_full_get_segment_t0_from_state(struct whisper_state * st, int i) {
+    const int64_t t0 = SEG(st, i).t0;
+    return (!st->vad.has_segments || st->vad.table.empty()) ? t0 : vad_map_segment_time(t0, st->vad.table);
+}
+WB_EXPORT int64_t whisper_full_get_segment_t1_from_state(struct whisper_state * st, int i) {
+    const int64_t t1 = SEG(st, i).t1;
+    if (!st->vad.has_segments || st->vad.table.empty()) return t1;
+    const int64_t o0 = whisper_full_get_segment_t0_from_state(st, i);
+    return std::max(vad_map_segment_time(t1, st->vad.table), o0 + 10);               // never a zero-length segment
+}
+WB_EXPORT int64_t whisper_full_get_segment_t0(struct whisper_context * ctx, int i)         { return whisper_full_get_segment_t0_from_state(ctx->state, i); }
+WB_EXPORT int64_t whisper_full_get_segment_t1(struct whisper_context * ctx, int i)         { return whisper_full_get_segment_t1_from_state(ctx->state, i); }
 WB_EXPORT bool whisper_full_get_segment_speaker_turn_next_from_state(struct whisper_state * st, int i) { return SEG(st, i).speaker_turn_next; }
 WB_EXPORT bool whisper_full_get_segment_speaker_turn_next(struct whisper_context * ctx, int i)         { return SEG(ctx->state, i).speaker_turn_next; }
 WB_EXPORT const char * whisper_full_get_segment_text_from_state(struct whisper_state * st, int i) { return SEG(st, i).text.c_str(); }
@@ -617,41 +626,27 @@ WB_EXPORT whisper_token whisper_full_get_token_id_from_state(struct whisper_stat
 WB_EXPORT whisper_token whisper_full_get_token_id(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].id; }
 WB_EXPORT whisper_token_data whisper_full_get_token_data_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t]; }
 WB_EXPORT whisper_token_data whisper_full_get_token_data(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t]; }
-WB_EXPORT int64_t whisper_full_get_token_t0_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].t0; }
-WB_EXPORT int64_t whisper_full_get_token_t0(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].t0; }
-WB_EXPORT int64_t whisper_full_get_token_t1_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].t1; }
-WB_EXPORT int64_t whisper_full_get_token_t1(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].t1; }
+WB_EXPORT int64_t whisper_full_get_token_t0_from_state(struct whisper_state * st, int i, int t) {       // whisper.cpp:8132-8158
+    const int64_t t0 = SEG(st, i).tokens[t].t0;
+    return (!st->vad.has_segments || st->vad.segments.empty()) ? t0 : vad_map_token_time(t0, st->vad.segments);
+}
+WB_EXPORT int64_t whisper_full_get_token_t1_from_state(struct whisper_state * st, int i, int t) {
+    const int64_t t1 = SEG(st, i).tokens[t].t1;
+    if (!st->vad.has_segments || st->vad.segments.empty()) return t1;
+    return std::max(vad_map_token_time(t1, st->vad.segments), whisper_full_get_token_t0_from_state(st, i, t) + 1);
+}
+WB_EXPORT int64_t whisper_full_get_token_t0(struct whisper_context * ctx, int i, int t)         { return whisper_full_get_token_t0_from_state(ctx->state, i, t); }
+WB_EXPORT int64_t whisper_full_get_token_t1(struct whisper_context * ctx, int i, int t)         { return whisper_full_get_token_t1_from_state(ctx->state, i, t); }
 WB_EXPORT float whisper_full_get_token_p_from_state(struct whisper_state * st, int i, int t) { return SEG(st, i).tokens[t].p; }
 WB_EXPORT float whisper_full_get_token_p(struct whisper_context * ctx, int i, int t)         { return SEG(ctx->state, i).tokens[t].p; }
 
-WB_EXPORT int     whisper_full_n_vad_segments(struct whisper_context *)                       { return 0; }
-WB_EXPORT int     whisper_full_n_vad_segments_from_state(struct whisper_state *)              { return 0; }
-WB_EXPORT int64_t whisper_full_get_vad_segment_t0(struct whisper_context *, int)              { return 0; }
-WB_EXPORT int64_t whisper_full_get_vad_segment_t0_from_state(struct whisper_state *, int)     { return 0; }
-WB_EXPORT int64_t whisper_full_get_vad_segment_t1(struct whisper_context *, int)              { return 0; }
-WB_EXPORT int64_t whisper_full_get_vad_segment_t1_from_state(struct whisper_state *, int)     { return 0; }
-
-// ---------------------------------------------------------------------------------------------------- VAD (out of scope)
-WB_EXPORT struct whisper_vad_params whisper_vad_default_params(void) {               // whisper.cpp VAD defaults
-    whisper_vad_params p; p.threshold = 0.5f; p.min_speech_duration_ms = 250; p.min_silence_duration_ms = 100;
-    p.max_speech_duration_s = 3.4028235e38f; p.speech_pad_ms = 30; p.samples_overlap = 0.1f; return p;
-}
-WB_EXPORT struct whisper_vad_context_params whisper_vad_default_context_params(void) { whisper_vad_context_params p; p.n_threads = 4; p.use_gpu = false; p.gpu_device = 0; return p; }
-static void vad_unsupported(const char * fn) { logf(LOG_ERROR, "%s: Silero VAD is not part of libwhisper_b200 (SURVEY.md section 2: out of scope)\n", fn); }
-WB_EXPORT struct whisper_vad_context * whisper_vad_init_from_file_with_params(const char *, struct whisper_vad_context_params) { vad_unsupported(__func__); return nullptr; }
-WB_EXPORT struct whisper_vad_context * whisper_vad_init_with_params(struct whisper_model_loader * l, struct whisper_vad_context_params) { if (l && l->close) l->close(l->context); vad_unsupported(__func__); return nullptr; }
-WB_EXPORT bool    whisper_vad_detect_speech(struct whisper_vad_context *, const float *, int)          { return false; }
-WB_EXPORT bool    whisper_vad_detect_speech_no_reset(struct whisper_vad_context *, const float *, int) { return false; }
-WB_EXPORT void    whisper_vad_reset_state(struct whisper_vad_context *) {}
-WB_EXPORT int     whisper_vad_n_probs(struct whisper_vad_context *) { return 0; }
-WB_EXPORT float * whisper_vad_probs(struct whisper_vad_context *)   { return nullptr; }
-WB_EXPORT struct whisper_vad_segments * whisper_vad_segments_from_probs(struct whisper_vad_context *, struct whisper_vad_params) { return nullptr; }
-WB_EXPORT struct whisper_vad_segments * whisper_vad_segments_from_samples(struct whisper_vad_context *, struct whisper_vad_params, const float *, int) { return nullptr; }
-WB_EXPORT int   whisper_vad_segments_n_segments(struct whisper_vad_segments *)         { return 0; }
-WB_EXPORT float whisper_vad_segments_get_segment_t0(struct whisper_vad_segments *, int) { return 0.0f; }
-WB_EXPORT float whisper_vad_segments_get_segment_t1(struct whisper_vad_segments *, int) { return 0.0f; }
-WB_EXPORT void  whisper_vad_free_segments(struct whisper_vad_segments *) {}
-WB_EXPORT void  whisper_vad_free(struct whisper_vad_context *) {}
+WB_EXPORT int     whisper_full_n_vad_segments_from_state(struct whisper_state * st)               { return (int) st->vad.segments.size(); }   // whisper.cpp:8133-8158
+WB_EXPORT int     whisper_full_n_vad_segments(struct whisper_context * ctx)                       { return (int) ctx->state->vad.segments.size(); }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t0_from_state(struct whisper_state * st, int i)    { return st->vad.segments[(size_t) i].orig_start; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t0(struct whisper_context * ctx, int i)            { return ctx->state->vad.segments[(size_t) i].orig_start; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t1_from_state(struct whisper_state * st, int i)    { return st->vad.segments[(size_t) i].orig_end; }
+WB_EXPORT int64_t whisper_full_get_vad_segment_t1(struct whisper_context * ctx, int i)            { return ctx->state->vad.segments[(size_t) i].orig_end; }
+// whisper_vad_* : wb_vad.cpp
 
 // ---------------------------------------------------------------------------------------------------- engine extensions
 WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float * out, int64_t cap) {

@@ -864,16 +864,55 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
     return 0;
 }
 
+} // extern "C"
+
+// params.vad: run the detector on the whole clip and keep only the speech (whisper_vad, src/whisper.cpp:6669-6829).  The
+// network runs on the context's GPU; cutting the PCM is a host copy because the C ABI hands the samples over in host memory.
+static bool vad_filter(whisper_context * ctx, whisper_state * st, const whisper_full_params & params, const float * samples, int n_samples,
+                       std::vector<float> & filtered) {
+    st->vad.table.clear(); st->vad.has_segments = false;
+    if (!st->vad_context) {
+        whisper_vad_context_params vp = whisper_vad_default_context_params();
+        vp.gpu_device = ctx->params.gpu_device;
+        whisper_vad_context * v = whisper_vad_init_from_file_with_params(params.vad_model_path, vp);
+        if (!v) { logf(LOG_ERROR, "%s: failed to initialize VAD context\n", __func__); return false; }
+        st->vad_context.reset(v);
+    }
+    whisper_vad_segments * segs = whisper_vad_segments_from_samples(st->vad_context.get(), params.vad_params, samples, n_samples);
+    if (!segs) return false;
+    if (!segs->data.empty()) {
+        logf(LOG_INFO, "%s: detected %d speech segments\n", __func__, (int) segs->data.size());
+        try { vad_cut_samples(segs->data, params.vad_params, samples, n_samples, filtered, st->vad); }
+        catch (...) { whisper_vad_free_segments(segs); logf(LOG_ERROR, "%s: failed to allocate memory for filtered samples\n", __func__); return false; }
+    }
+    whisper_vad_free_segments(segs);
+    return true;
+}
+
+extern "C" {
+
 WB_EXPORT int whisper_full(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples) {
     if (!ctx || !ctx->state) return -1;
-    if (params.vad) { logf(LOG_ERROR, "%s: VAD is not part of libwhisper_b200 (whisper_full returns -1 as for a failed VAD)\n", __func__); return -1; }
+    std::vector<float> speech;
+    if (params.vad) {                                                                      // whisper.cpp:7796-7809
+        logf(LOG_INFO, "%s: VAD is enabled, processing speech segments only\n", __func__);
+        if (!vad_filter(ctx, ctx->state, params, samples, n_samples, speech)) { logf(LOG_ERROR, "%s: failed to compute VAD\n", __func__); return -1; }
+        if (speech.empty()) { ctx->state->result_all.clear(); return 0; }
+        samples = speech.data(); n_samples = (int) speech.size();
+    }
     return whisper_full_with_state(ctx, ctx->state, params, samples, n_samples);
 }
 
 WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper_full_params params, const float * samples, int n_samples, int n_processors) {
     if (n_processors <= 1) return whisper_full(ctx, params, samples, n_samples);          // whisper.cpp:7813-7941
     if (!ctx || !ctx->state) return -1;
-    if (params.vad) { logf(LOG_ERROR, "%s: VAD is not part of libwhisper_b200\n", __func__); return -1; }
+    std::vector<float> speech;
+    if (params.vad) {                                                                      // whisper.cpp:7824-7836
+        logf(LOG_INFO, "%s: VAD is enabled, processing speech segments only\n", __func__);
+        if (!vad_filter(ctx, ctx->state, params, samples, n_samples, speech)) { logf(LOG_ERROR, "%s: failed to compute VAD\n", __func__); return -1; }
+        if (speech.empty()) return 0;
+        samples = speech.data(); n_samples = (int) speech.size();
+    }
     int ret = 0;
     std::vector<whisper_state *> states;
     const int offset_samples = (WB_SAMPLE_RATE * params.offset_ms) / 1000;
@@ -929,6 +968,7 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
 WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
                                   const int * n_samples, int n_chunks, struct whisper_state ** states_out, int flags) {
     if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
+    if (params.vad) { set_error("wb200_full_batch: params.vad is not applied to pre-cut chunks; run whisper_vad_* first"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
     int S = ctx->model.dec_tm ? 64 : 8;          // concurrent sequences: one row each in the decode pass (64 rows per launch of the persistent kernel)
     if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));
     S = std::min(S, n_chunks);

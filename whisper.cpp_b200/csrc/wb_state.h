@@ -13,6 +13,7 @@
 #include "../../include/whisper_b200.h"
 #include "wb_engine.h"
 #include "wb_grammar.h"
+#include "wb_vad.h"
 
 namespace wb {
 
@@ -85,6 +86,10 @@ struct whisper_state {
     // experimental token-level timestamps (src/whisper.cpp:907-912, 8640-8820)
     int64_t t_beg = 0, t_last = 0; whisper_token tid_last = 0;
     std::vector<float> energy;                 // |PCM| averaged over +-32 samples
+    // voice-activity detection in front of whisper_full (params.vad; src/whisper.cpp:923-934)
+    struct VadFree { void operator()(whisper_vad_context * v) const { whisper_vad_free(v); } };
+    std::unique_ptr<whisper_vad_context, VadFree> vad_context;
+    wb::VadCut vad;                            // what the last whisper_full cut out, for mapping times back
 };
 
 struct whisper_context {
