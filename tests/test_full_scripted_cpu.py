@@ -1,0 +1,190 @@
+"""CPU: the complete whisper_full control flow of libwhisper_b200.so against the reference, with the model taken out of the equation.
+
+Both libraries run whisper_full / whisper_full_parallel with the SAME logits_filter_callback, which overwrites every logit with a value
+scripted from the decoder's token history (the callback runs before the timestamp rules, src/whisper.cpp:6246-6249, so all later
+filtering, sampling and bookkeeping still happens inside the libraries).  The reference runs its real CPU graphs on a synthetic 1-layer
+model; the product runs on an engine-less test context (wb200_dbg_scripted_context) whose decodes return zeros.  Everything downstream of
+the logits -- seek loop, prompt / context carry-over, temperature fallback with std::mt19937 draws, beam search, timestamp pairing,
+segment emission, max_tokens / single_segment, token-level timestamps + max_len wrapping, grammar, callbacks, whisper_full_parallel --
+must then agree EXACTLY: same segments, times, text, and per token id / tid / p / plog / pt / ptsum / t0 / t1 / vlen."""
+import ctypes as C
+import os
+import zlib
+import numpy as np
+import pytest
+
+from wbtest import DATA_DIR, F16, TokenData, bind_whisper_api
+from e2e_util import synth
+from test_grammar_cpu import build as build_grammar, lit, ALT, REF, CHAR, RNG
+
+vp = C.c_void_p
+LOGITS_CB = C.CFUNCTYPE(None, vp, vp, C.POINTER(TokenData), C.c_int, C.POINTER(C.c_float), vp)
+SEG_CB = C.CFUNCTYPE(None, vp, vp, C.c_int, vp)
+PROG_CB = C.CFUNCTYPE(None, vp, vp, C.c_int, vp)
+LOG_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, vp)
+_quiet = LOG_CB(lambda level, text, ud: None)
+
+
+class Script:
+    """deterministic logits from (token history, number of segments emitted so far, scenario seed)"""
+
+    def __init__(self, L, ctx, seed, style, timestamps=True, use_segments=True):
+        self.L, self.seed, self.style, self.timestamps, self.use_segments = L, seed, style, timestamps, use_segments
+        self.V = L.whisper_n_vocab(ctx)
+        self.beg, self.eot = L.whisper_token_beg(ctx), L.whisper_token_eot(ctx)
+        self.calls = 0
+        L.whisper_full_n_segments_from_state.argtypes = [vp]
+        self.cb = LOGITS_CB(self._cb)
+
+    def _cb(self, ctx, st, toks, n, logits, ud):
+        self.calls += 1
+        ids = np.fromiter((toks[i].id for i in range(n)), np.int32, n)
+        nseg = self.L.whisper_full_n_segments_from_state(st) if self.use_segments else 0
+        rng = np.random.default_rng((zlib.crc32(ids.tobytes()) ^ self.seed ^ (nseg * 7919)) & 0xFFFFFFFF)
+        V, beg, eot = self.V, self.beg, self.eot
+        x = rng.standard_normal(V).astype(np.float32)
+        x[beg:] -= 10.0                                                        # timestamps only when the script calls for one
+        ts = ids[ids >= beg]
+        last_ts = int(ts[-1] - beg) if len(ts) else 0
+        since = n - (int(np.nonzero(ids >= beg)[0][-1]) + 1) if len(ts) else n
+        peak = {"peaked": 14.0, "medium": 10.5, "flat": 8.5}[self.style]
+        x[int(rng.integers(300, 20000))] += peak                               # the word this history "wants"
+        if self.style != "peaked":
+            x[rng.integers(300, 20000, 6)] += peak * 0.6
+        if self.timestamps:
+            if n == 0:
+                x[beg + int(rng.integers(0, 12))] += 30.0                      # open the window with a timestamp near 0
+            elif since >= int(rng.integers(4, 14)) or (len(ts) % 2 == 1 and since == 0):
+                step = int(rng.integers(8, 90))
+                x[min(beg + last_ts + step, V - 1)] += 28.0                    # close / reopen a segment a little later
+        if (self.timestamps and last_ts > int(rng.integers(1250, 1480))) or n > int(rng.integers(110, 190)):
+            x[eot] += 25.0
+        np.ctypeslib.as_array(logits, (V,))[:] = x
+
+
+def make_models(tmp_path):
+    en = str(tmp_path / "s1.en.bin"); ml = str(tmp_path / "s1.multi.bin")
+    synth.write_model(en, (51864, 1500, 384, 6, 1, 448, 384, 6, 1, 80), F16, seed=21, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    synth.write_model(ml, (51865, 1500, 384, 6, 1, 448, 384, 6, 1, 80), F16, seed=22, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.bin"))
+    return en, ml
+
+
+def collect(L, ctx):
+    L.whisper_full_get_segment_speaker_turn_next.restype = C.c_bool
+    L.whisper_full_get_segment_speaker_turn_next.argtypes = [vp, C.c_int]
+    out = []
+    for i in range(L.whisper_full_n_segments(ctx)):
+        toks = []
+        for j in range(L.whisper_full_n_tokens(ctx, i)):
+            t = L.whisper_full_get_token_data(ctx, i, j)
+            toks.append((t.id, t.tid, t.p, t.plog, t.pt, t.ptsum, t.t0, t.t1, t.t_dtw, t.vlen))
+        out.append((L.whisper_full_get_segment_t0(ctx, i), L.whisper_full_get_segment_t1(ctx, i), L.whisper_full_get_segment_text(ctx, i),
+                    bool(L.whisper_full_get_segment_speaker_turn_next(ctx, i)), toks))
+    return out
+
+
+SCENARIOS = [
+    # name, model, seconds, style, params, extras
+    ("greedy_default",      "en", 65.0, "peaked", dict(), {}),
+    ("greedy_fallback",     "en", 40.0, "flat",   dict(best_of=2, logprob_thold=-2.0, temperature_inc=0.4), {}),
+    ("greedy_medium_bo3",   "en", 31.0, "medium", dict(best_of=3, temperature=0.4, temperature_inc=0.3, logprob_thold=-3.5), {}),
+    ("beam3",               "en", 42.0, "medium", dict(strategy=1, beam_size=3), {}),
+    ("beam5_fallback",      "en", 25.0, "flat",   dict(strategy=1, beam_size=5, best_of=3, temperature_inc=0.5, logprob_thold=-2.5), {}),
+    ("no_timestamps_maxtok", "en", 50.0, "peaked", dict(no_timestamps=True, max_tokens=12), {"timestamps": False}),
+    ("single_segment_prompt", "en", 58.0, "peaked", dict(single_segment=True, initial_prompt=b" Hello world, previous context.", carry_initial_prompt=True), {}),
+    ("prompt_tokens_ctx",   "en", 66.0, "medium", dict(n_max_text_ctx=64, prompt=[1000, 2000, 3000, 4000, 5000]), {}),
+    ("token_ts_wrap",       "en", 35.0, "peaked", dict(token_timestamps=True, max_len=20, split_on_word=True), {}),
+    ("token_ts_plain",      "en", 20.0, "medium", dict(token_timestamps=True, thold_pt=0.0005, thold_ptsum=0.0005), {}),
+    ("multi_translate",     "ml", 33.0, "peaked", dict(language=b"de", translate=True, suppress_nst=True, suppress_blank=False), {}),
+    ("offset_duration_actx", "en", 70.0, "peaked", dict(offset_ms=12000, duration_ms=37000, audio_ctx=768, max_initial_ts=0.5), {}),
+    ("no_context_special",  "en", 45.0, "medium", dict(no_context=True, print_special=True, tdrz_enable=True, length_penalty=0.2, strategy=1, beam_size=2), {}),
+    ("grammar",             "en", 28.0, "medium", dict(grammar=True, grammar_penalty=30.0, no_timestamps=True, max_tokens=24), {"timestamps": False}),
+    ("parallel2",           "en", 64.0, "peaked", dict(n_processors=2), {"use_segments": False}),
+    ("short_input",         "en", 0.05, "peaked", dict(), {}),
+]
+
+
+def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
+    kw = dict(kw)
+    fp = L.whisper_full_default_params(kw.pop("strategy", 0))
+    fp.print_progress = False; fp.n_threads = 1; fp.no_speech_thold = 2.0          # the model's own no-speech probability plays no role
+    keep = []
+    if "best_of" in kw:
+        fp.greedy.best_of = kw.pop("best_of")
+    if "beam_size" in kw:
+        fp.beam_search.beam_size = kw.pop("beam_size")
+    if "prompt" in kw:
+        arr = (C.c_int32 * len(kw["prompt"]))(*kw.pop("prompt")); keep.append(arr)
+        fp.prompt_tokens = arr; fp.prompt_n_tokens = len(arr)
+    if kw.pop("grammar", False):
+        # root ::= " " word rest ; rest ::= " " word rest | "." ; word ::= [a-z] tail ; tail ::= [a-z] tail | ()
+        rules = [[(CHAR, 32), (REF, 2), (REF, 1)], [(CHAR, 32), (REF, 2), (REF, 1), (ALT, 0), (CHAR, ord("."))],
+                 [(CHAR, ord("a")), (RNG, ord("z")), (REF, 3)], [(CHAR, ord("a")), (RNG, ord("z")), (REF, 3), (ALT, 0)]]
+        ptrs, arrs = build_grammar(rules); keep += [ptrs, arrs]
+        fp.grammar_rules = C.cast(ptrs, vp); fp.n_grammar_rules = len(rules); fp.i_start_rule = 0
+    n_proc = kw.pop("n_processors", 1)
+    for k, v in kw.items():
+        assert hasattr(fp, k), k
+        setattr(fp, k, v)
+    script = Script(L, ctx, seed, style, **extras)
+    fp.logits_filter_callback = C.cast(script.cb, vp)
+    events = []
+    seg_cb = SEG_CB(lambda c, s, n_new, ud: events.append(("seg", n_new)))
+    prog_cb = PROG_CB(lambda c, s, p, ud: events.append(("prog", p)))
+    fp.new_segment_callback = C.cast(seg_cb, vp); fp.progress_callback = C.cast(prog_cb, vp)
+    if n_proc > 1:
+        rc = L.whisper_full_parallel(ctx, fp, pcm.ctypes.data_as(vp), len(pcm), n_proc)
+    else:
+        rc = L.whisper_full(ctx, fp, pcm.ctypes.data_as(vp), len(pcm))
+    return rc, collect(L, ctx), events, script.calls, L.whisper_full_lang_id(ctx)
+
+
+def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp_path):
+    if not hasattr(lib, "wb200_dbg_scripted_context"):
+        pytest.skip("library predates wb200_dbg_scripted_context")
+    L = bind_whisper_api(lib); R = bind_whisper_api(ref)
+    for X in (L, R):
+        X.whisper_log_set.argtypes = [LOG_CB, vp]
+        if not os.environ.get("WB200_VERBOSE"):
+            X.whisper_log_set(_quiet, None)
+    L.wb200_dbg_scripted_context.restype = vp; L.wb200_dbg_scripted_context.argtypes = [C.c_char_p]
+    paths = dict(zip(("en", "ml"), make_models(tmp_path)))
+    ctxs = {}
+    for key, path in paths.items():
+        cp = R.whisper_context_default_params(); cp.use_gpu = False
+        rctx = R.whisper_init_from_file_with_params(path.encode(), cp)
+        lctx = L.wb200_dbg_scripted_context(path.encode())
+        assert rctx and lctx
+        ctxs[key] = (lctx, rctx)
+    rng = np.random.default_rng(99)
+    stats = []
+    only = os.environ.get("WB200_SCENARIO")
+    for idx, (name, model, seconds, style, kw, extras) in enumerate(SCENARIOS):
+        if only and only != name:
+            continue
+        pcm = (rng.standard_normal(int(seconds * 16000)) * 0.01).astype(np.float32)
+        lctx, rctx = ctxs[model]
+        a = run_side(L, lctx, name, seconds, style, kw, extras, pcm, 1000 + idx)
+        b = run_side(R, rctx, name, seconds, style, kw, extras, pcm, 1000 + idx)
+        n_tok = sum(len(s[4]) for s in b[1])
+        stats.append((name, b[0], len(b[1]), n_tok, b[3]))
+        assert a[0] == b[0], (name, "return code", a[0], b[0])
+        assert len(a[1]) == len(b[1]), (name, "segments", len(a[1]), len(b[1]), [s[2] for s in a[1]][:3], [s[2] for s in b[1]][:3])
+        for i, (sa, sb) in enumerate(zip(a[1], b[1])):
+            assert sa[:4] == sb[:4], (name, i, sa[:4], sb[:4])
+            assert len(sa[4]) == len(sb[4]), (name, i, "tokens")
+            for j, (ta, tb) in enumerate(zip(sa[4], sb[4])):
+                assert ta == tb, (name, i, j, ta, tb)
+        assert a[4] == b[4], (name, "lang id")
+        if kw.get("n_processors", 1) == 1:
+            assert a[2] == b[2], (name, "callback events", a[2][:8], b[2][:8])
+            assert a[3] == b[3], (name, "logits callback calls", a[3], b[3])
+    for s in stats:
+        print("scripted %-22s rc=%d segments=%3d tokens=%4d logits-callback calls=%d" % s)
+    if not only:
+        assert sum(s[2] for s in stats) > 40 and sum(s[3] for s in stats) > 600       # the scripts did produce transcripts
+        by = {s[0]: s for s in stats}
+        assert by["greedy_fallback"][4] > 2 * by["greedy_fallback"][3]                 # fallback really re-decoded windows
+        assert by["short_input"][2] == 0
+    for lctx, rctx in ctxs.values():
+        L.whisper_free(lctx); R.whisper_free(rctx)

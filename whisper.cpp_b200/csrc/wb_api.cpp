@@ -124,6 +124,7 @@ void account_decode(whisper_state & st, int n_tokens, int64_t dt) {             
 bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset) {
     const int64_t t0 = time_us();
     const int n_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
+    if (st.scripted) { st.n_encode++; return true; }                       // test hook: no engine
     if (st.fe.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.fe.n_mel, ctx.model.hp.n_mels); return false; }
     if (st.group) {
         Group::Req r; r.kind = 0; r.ctx = &ctx; r.st = &st; r.seek = mel_offset; r.n_ctx = n_ctx;
@@ -150,6 +151,11 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
     }
     PreparedDecode P;
     if (!prepare_decode(st, tokens, pos, seq, want, n_tokens, P)) return false;
+    if (st.scripted) {                                                       // test hook: KV bookkeeping only, the caller's logits callback supplies the values
+        st.samp_out.clear(); st.logits.assign((size_t) n_tokens * n_vocab, 0.0f);
+        account_decode(st, n_tokens, time_us() - t0);
+        return true;
+    }
     if (samp) {
         if (!st.eng->set_samp_mask(samp->mask_key, *samp->mask_bits)) return false;
         st.samp_out.assign(n_tokens, SampOut());
@@ -382,6 +388,14 @@ WB_EXPORT struct whisper_context * whisper_init_from_buffer_with_params_no_state
 WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx) {  // whisper.cpp:3386-3557
     if (!ctx) return nullptr;
     whisper_state * st = nullptr;
+    if (ctx->scripted) {                                                     // test hook: engine-less state
+        st = new whisper_state();
+        st->scripted = true;
+        st->kv.reset((uint32_t) ((ctx->model.hp.n_text_ctx + 255) / 256 * 256));
+        st->kv_self_n_dec = 1;
+        st->decoders[0].rng = std::mt19937(0);
+        return st;
+    }
     try {
         st = new whisper_state();
         st->own_eng.reset(new Engine());
@@ -421,6 +435,10 @@ WB_EXPORT int whisper_ctx_init_openvino_encoder(struct whisper_context *, const 
 WB_EXPORT int whisper_pcm_to_mel_with_state(struct whisper_context * ctx, struct whisper_state * st, const float * samples, int n_samples, int) {
     if (!ctx || !st || n_samples < 0) return -1;     // samples == NULL is legal after wb200_pcm_upload (device-resident input)
     const int64_t t0 = time_us();
+    if (st->scripted) {                                                      // test hook: only the frame counts of whisper.cpp:3202-3220
+        st->fe.n_mel = ctx->model.hp.n_mels; st->fe.n_len = (n_samples + 480000) / 160; st->fe.n_len_org = 1 + (n_samples + 200 - 400) / 160;
+        return 0;
+    }
     if (!st->fe.pcm_to_mel(samples, n_samples, wb::tls_pcm_is_device())) { logf(LOG_ERROR, "%s: failed to compute mel spectrogram\n", __func__); return -1; }
     st->t_mel_us += time_us() - t0;
     return 0;

@@ -611,7 +611,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 if (state->kv_self_n_dec < n_cur) {
                     const int factor = n_cur > 1 ? n_cur + 2 : 1;
                     const int cells = ((n_text_ctx + 255) / 256 * 256) * factor;
-                    if (state->group || !state->eng->set_cells(cells)) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
+                    if (state->group || !(state->scripted || state->eng->set_cells(cells))) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
                     state->kv.reset((uint32_t) cells);
                     state->kv_self_n_dec = n_cur;
                 }
@@ -1048,6 +1048,28 @@ static whisper_context * dbg_vocab_ctx(const char * model_path) {       // heade
 // Host-only: a context that holds only the header + vocabulary of a model file (no CUDA, no weights, no state).  Valid for the
 // vocabulary / tokenizer / special-token / model-shape getters of whisper.h; owned by the library.
 WB_EXPORT struct whisper_context * wb200_dbg_vocab_context(const char * model_path) { return model_path ? dbg_vocab_ctx(model_path) : nullptr; }
+
+// Host-only: an ENGINE-LESS context + state for tests/test_full_scripted_cpu.py.  whisper_full* run their complete control flow on it (seek
+// loop, prompts, temperature fallback, beam search, segment emission, token timestamps, whisper_full_parallel) but every decode leaves zero
+// logits: the transcript is scripted by the caller's logits_filter_callback, exactly as it can be scripted on the reference.  The caller
+// owns the context (whisper_free).  Not reachable from whisper.h.
+WB_EXPORT struct whisper_context * wb200_dbg_scripted_context(const char * model_path) {
+    if (!model_path) return nullptr;
+    std::ifstream fin(model_path, std::ios::binary);
+    if (!fin) return nullptr;
+    whisper_model_loader loader = {};
+    loader.context = &fin;
+    loader.read  = [](void * c, void * out, size_t n) -> size_t { auto * f = (std::ifstream *) c; f->read((char *) out, (std::streamsize) n); return (size_t) f->gcount(); };
+    loader.eof   = [](void * c) -> bool { return ((std::ifstream *) c)->eof(); };
+    loader.close = [](void * c) { ((std::ifstream *) c)->close(); };
+    std::unique_ptr<whisper_context> c(new whisper_context());
+    if (!wb::model_load(&loader, c->model, c->vocab, -1)) return nullptr;
+    c->params = whisper_context_default_params();
+    c->scripted = true;
+    c->model.n_loaded = 1;                       // "has weights" as far as the segment emission of whisper_full is concerned (whisper.cpp:7635)
+    c->state = whisper_init_state(c.get());
+    return c->state ? c.release() : nullptr;
+}
 
 // The ON-DEVICE logits filter + greedy pick (k_greedy_sample) on injected logits: same inputs as wb200_dbg_process_logits at
 // temperature 0; fills `sampled`.  Needs a CUDA device.

@@ -90,6 +90,10 @@ struct whisper_state {
     struct VadFree { void operator()(whisper_vad_context * v) const { whisper_vad_free(v); } };
     std::unique_ptr<whisper_vad_context, VadFree> vad_context;
     wb::VadCut vad;                            // what the last whisper_full cut out, for mapping times back
+    // TEST HOOK (wb200_dbg_scripted_context, tests/test_full_scripted_cpu.py): a state without an engine.  Mel / encode are no-ops and a
+    // decode leaves all-zero logits, so the transcript is whatever the caller's logits_filter_callback scripts.  It computes nothing and
+    // cannot be created through any whisper.h entry point.
+    bool scripted = false;
 };
 
 struct whisper_context {
@@ -99,6 +103,7 @@ struct whisper_context {
     wb::Vocab vocab;
     whisper_state * state = nullptr;
     std::string path_model;
+    bool scripted = false;                     // TEST HOOK: see whisper_state::scripted
     std::unique_ptr<wb::Group> batch_group;    // cached by wb200_full_batch
     std::mutex batch_mu;
     ~whisper_context();
