@@ -188,3 +188,77 @@ def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp
         assert by["short_input"][2] == 0
     for lctx, rctx in ctxs.values():
         L.whisper_free(lctx); R.whisper_free(rctx)
+
+
+def test_lockstep_batch_driver_equals_reference_chunk_by_chunk(lib, ref, tmp_path, monkeypatch):
+    """wb200_full_batch on the engine-less context: 3 member threads rendezvous for every encode / decode while they work through 8 chunks
+    of very different lengths (one too short to decode, one of three windows) with temperature fallback; every chunk must come out exactly
+    as the reference's whisper_full_with_state gives it on a fresh state."""
+    if not hasattr(lib, "wb200_dbg_scripted_context"):
+        pytest.skip("library predates wb200_dbg_scripted_context")
+    monkeypatch.setenv("WB200_BATCH_MEMBERS", "3")
+    L = bind_whisper_api(lib); R = bind_whisper_api(ref)
+    for X in (L, R):
+        X.whisper_log_set.argtypes = [LOG_CB, vp]
+        X.whisper_log_set(_quiet, None)
+    L.wb200_dbg_scripted_context.restype = vp; L.wb200_dbg_scripted_context.argtypes = [C.c_char_p]
+    en, _ = make_models(tmp_path)
+    cp = R.whisper_context_default_params(); cp.use_gpu = False
+    rctx = R.whisper_init_from_file_with_params(en.encode(), cp)
+    lctx = L.wb200_dbg_scripted_context(en.encode())
+    assert rctx and lctx
+    rng = np.random.default_rng(7)
+    lengths = [31.0, 0.04, 12.5, 64.0, 29.9, 3.0, 30.0, 8.2]
+    chunks = [(rng.standard_normal(int(s * 16000)) * 0.01).astype(np.float32) for s in lengths]
+
+    def params(X, ctx):
+        fp = X.whisper_full_default_params(0)
+        fp.print_progress = False; fp.n_threads = 1; fp.no_speech_thold = 2.0
+        fp.greedy.best_of = 2; fp.logprob_thold = -1.2; fp.temperature_inc = 0.4
+        script = Script(X, ctx, 4242, "medium", use_segments=True)
+        fp.logits_filter_callback = C.cast(script.cb, vp)
+        return fp, script
+
+    # product: all chunks through the lock-step driver
+    fp, script = params(L, lctx)
+    n = len(chunks)
+    ptrs = (C.POINTER(C.c_float) * n)(*[c.ctypes.data_as(C.POINTER(C.c_float)) for c in chunks])
+    lens = (C.c_int * n)(*[len(c) for c in chunks])
+    states = (vp * n)()
+    L.wb200_full_batch.argtypes = [vp, type(fp), vp, vp, C.c_int, vp]
+    assert L.wb200_full_batch(lctx, fp, ptrs, lens, n, states) == 0
+    for fn in ("whisper_full_n_segments_from_state",):
+        getattr(L, fn).argtypes = [vp]; getattr(R, fn).argtypes = [vp]
+    for X in (L, R):
+        X.whisper_full_n_tokens_from_state.argtypes = [vp, C.c_int]
+        X.whisper_full_get_token_data_from_state.restype = TokenData
+        X.whisper_full_get_token_data_from_state.argtypes = [vp, C.c_int, C.c_int]
+
+    def collect_state(X, st):
+        out = []
+        for i in range(X.whisper_full_n_segments_from_state(st)):
+            toks = []
+            for j in range(X.whisper_full_n_tokens_from_state(st, i)):
+                t = X.whisper_full_get_token_data_from_state(st, i, j)
+                toks.append((t.id, t.tid, t.p, t.plog, t.pt, t.ptsum, t.t0, t.t1, t.vlen))
+            out.append((X.whisper_full_get_segment_t0_from_state(st, i), X.whisper_full_get_segment_t1_from_state(st, i),
+                        X.whisper_full_get_segment_text_from_state(st, i), toks))
+        return out
+
+    got = [collect_state(L, states[i]) for i in range(n)]
+    # reference: one fresh state per chunk
+    rfp, rscript = params(R, rctx)
+    n_tok = 0
+    for i, c in enumerate(chunks):
+        st = R.whisper_init_state(rctx)
+        assert R.whisper_full_with_state(rctx, st, rfp, c.ctypes.data_as(vp), len(c)) == 0
+        want = collect_state(R, st)
+        R.whisper_free_state(st)
+        assert got[i] == want, (i, lengths[i], len(got[i]), len(want))
+        n_tok += sum(len(s[3]) for s in want)
+    assert script.calls == rscript.calls                      # the same number of decoder evaluations, fallback re-decodes included
+    assert n_tok > 300 and got[1] == []
+    print("lock-step batch: %d chunks, %d tokens, %d logits-callback calls" % (n, n_tok, script.calls))
+    for i in range(n):
+        L.whisper_free_state(states[i])
+    L.whisper_free(lctx); R.whisper_free(rctx)

@@ -124,7 +124,7 @@ void account_decode(whisper_state & st, int n_tokens, int64_t dt) {             
 bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset) {
     const int64_t t0 = time_us();
     const int n_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
-    if (st.scripted) { st.n_encode++; return true; }                       // test hook: no engine
+    if (st.scripted && !st.group) { st.n_encode++; return true; }          // test hook: no engine
     if (st.fe.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.fe.n_mel, ctx.model.hp.n_mels); return false; }
     if (st.group) {
         Group::Req r; r.kind = 0; r.ctx = &ctx; r.st = &st; r.seek = mel_offset; r.n_ctx = n_ctx;
@@ -218,7 +218,9 @@ void Group::run(std::vector<Req *> & batch) {
         bool same_ctx = true;
         for (Req * q : enc) same_ctx &= (q->n_ctx == enc[0]->n_ctx);
         bool ok = true;
-        if (same_ctx) {
+        if (scripted) {
+            // test hook: nothing to encode
+        } else if (same_ctx) {
             std::vector<EncSrc> srcs;
             for (Req * q : enc) srcs.push_back({ q->st->fe.mel.p, q->st->fe.n_len, q->st->fe.n_mel, q->seek, q->st->slot });
             ok = eng.encode(srcs.data(), (int) srcs.size(), enc[0]->n_ctx);
@@ -230,7 +232,7 @@ void Group::run(std::vector<Req *> & batch) {
     }
     if (!dec.empty()) {
         const int64_t t0 = time_us();
-        const int n_vocab = eng.m->hp.n_vocab;
+        const int n_vocab = dec[0]->ctx->model.hp.n_vocab;
         std::vector<PreparedDecode> preps(dec.size());
         bool ok = true; int total = 0, ld = 1;
         for (size_t i = 0; i < dec.size(); ++i) {
@@ -238,9 +240,14 @@ void Group::run(std::vector<Req *> & batch) {
             ok &= prepare_decode(*q->st, q->tokens, q->pos, q->seq, q->want, q->n, preps[i]);
             total += q->n; ld = std::max(ld, preps[i].ld);
         }
-        bool all_samp = true;
-        for (Req * q : dec) all_samp &= (q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key &&
-                                         memcmp(&q->samp->cfg, &dec[0]->samp->cfg, sizeof(SampCfg)) == 0);
+        // the on-device filter + pick serves the pass only if EVERY request asked for it with the same configuration (a member that fell
+        // back to temperature > 0 samples on the host and needs full logits, so the whole pass returns logits then)
+        bool all_samp = dec[0]->samp != nullptr;
+        for (Req * q : dec) all_samp = all_samp && q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key &&
+                                       memcmp(&q->samp->cfg, &dec[0]->samp->cfg, sizeof(SampCfg)) == 0;
+        if (scripted) {                                               // test hook: KV bookkeeping done above, logits are the callback's business
+            for (Req * q : dec) { q->st->samp_out.clear(); q->st->logits.assign((size_t) q->n * n_vocab, 0.0f); }
+        } else {
         if (ok && all_samp) ok = eng.set_samp_mask(dec[0]->samp->mask_key, *dec[0]->samp->mask_bits);
         if (ok) {
             std::vector<DecToken> rows; std::vector<int> cells, nkv, idx((size_t) total * ld, 0); std::vector<float *> outs;
@@ -268,6 +275,7 @@ void Group::run(std::vector<Req *> & batch) {
             } else {
                 ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), outs.data());
             }
+        }
         }
         const int64_t dt = (time_us() - t0) / (int64_t) dec.size();
         for (Req * q : dec) { q->ok = ok; q->dt_us = dt; }

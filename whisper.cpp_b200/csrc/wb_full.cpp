@@ -979,11 +979,13 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
         ctx->batch_group.reset(new Group());
         Group & G = *ctx->batch_group;
         G.n_members = S; G.cells_per_member = cells_per_member;
-        if (!G.eng.init(&ctx->model, S) || !G.eng.set_cells(S * cells_per_member)) { ctx->batch_group.reset(); return -7; }
+        G.scripted = ctx->scripted;                                   // test hook: members without an engine (see whisper_state::scripted)
+        if (!G.scripted && (!G.eng.init(&ctx->model, S) || !G.eng.set_cells(S * cells_per_member))) { ctx->batch_group.reset(); return -7; }
         for (int i = 0; i < S; ++i) {
             whisper_state * st = new whisper_state();
             G.members.push_back(st);
-            if (!st->fe.init(&ctx->model)) { ctx->batch_group.reset(); return -7; }
+            st->scripted = G.scripted;
+            if (!G.scripted && !st->fe.init(&ctx->model)) { ctx->batch_group.reset(); return -7; }
             st->eng = &G.eng; st->group = &G; st->slot = i; st->cell_off = i * cells_per_member;
             st->kv.reset((uint32_t) cells_per_member);
             st->kv_self_n_dec = member_decoders;

@@ -120,7 +120,9 @@ struct SampReq { SampCfg cfg; uint64_t mask_key = 0; const std::vector<uint32_t>
 struct Group {
     Engine eng;
     int n_members = 0, cells_per_member = 0;
-    std::vector<whisper_state *> members;
+    bool scripted = false;                      // test hook: no engine, decodes leave zero logits
+    std::vector<whisper_state *> members;       // owned
+    ~Group() { for (whisper_state * m : members) delete m; }
     std::mutex mu;
     std::condition_variable cv;
     int n_active = 0;
