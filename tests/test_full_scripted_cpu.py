@@ -16,6 +16,8 @@ import pytest
 from wbtest import DATA_DIR, F16, TokenData, bind_whisper_api
 from e2e_util import synth
 from test_grammar_cpu import build as build_grammar, lit, ALT, REF, CHAR, RNG
+from test_vad_cpu import SILERO
+from wbtest import read_wav_f32
 
 vp = C.c_void_p
 LOGITS_CB = C.CFUNCTYPE(None, vp, vp, C.POINTER(TokenData), C.c_int, C.POINTER(C.c_float), vp)
@@ -72,12 +74,15 @@ def make_models(tmp_path):
 def collect(L, ctx):
     L.whisper_full_get_segment_speaker_turn_next.restype = C.c_bool
     L.whisper_full_get_segment_speaker_turn_next.argtypes = [vp, C.c_int]
+    for fn in ("whisper_full_get_token_t0", "whisper_full_get_token_t1"):
+        getattr(L, fn).restype = C.c_int64; getattr(L, fn).argtypes = [vp, C.c_int, C.c_int]
     out = []
     for i in range(L.whisper_full_n_segments(ctx)):
         toks = []
         for j in range(L.whisper_full_n_tokens(ctx, i)):
             t = L.whisper_full_get_token_data(ctx, i, j)
-            toks.append((t.id, t.tid, t.p, t.plog, t.pt, t.ptsum, t.t0, t.t1, t.t_dtw, t.vlen))
+            toks.append((t.id, t.tid, t.p, t.plog, t.pt, t.ptsum, t.t0, t.t1, t.t_dtw, t.vlen,
+                         L.whisper_full_get_token_t0(ctx, i, j), L.whisper_full_get_token_t1(ctx, i, j)))      # mapped back through the VAD cut, if any
         out.append((L.whisper_full_get_segment_t0(ctx, i), L.whisper_full_get_segment_t1(ctx, i), L.whisper_full_get_segment_text(ctx, i),
                     bool(L.whisper_full_get_segment_speaker_turn_next(ctx, i)), toks))
     return out
@@ -101,6 +106,9 @@ SCENARIOS = [
     ("grammar",             "en", 28.0, "medium", dict(grammar=True, grammar_penalty=30.0, no_timestamps=True, max_tokens=24), {"timestamps": False}),
     ("parallel2",           "en", 64.0, "peaked", dict(n_processors=2), {"use_segments": False}),
     ("short_input",         "en", 0.05, "peaked", dict(), {}),
+    # params.vad on jfk.wav with the Silero weights of the reference's tests (product side: host walk of the VAD kernels' phases)
+    ("vad_token_ts",        "en", "jfk", "peaked", dict(vad=True, token_timestamps=True, max_len=30), {}),
+    ("vad_beam",            "en", "jfk", "medium", dict(vad=True, strategy=1, beam_size=2, samples_overlap=0.3), {}),
 ]
 
 
@@ -123,6 +131,9 @@ def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
         ptrs, arrs = build_grammar(rules); keep += [ptrs, arrs]
         fp.grammar_rules = C.cast(ptrs, vp); fp.n_grammar_rules = len(rules); fp.i_start_rule = 0
     n_proc = kw.pop("n_processors", 1)
+    if kw.pop("vad", False):
+        fp.vad = True; fp.vad_model_path = SILERO.encode()
+        fp.vad_params.samples_overlap = kw.pop("samples_overlap", 0.1)
     for k, v in kw.items():
         assert hasattr(fp, k), k
         setattr(fp, k, v)
@@ -136,7 +147,11 @@ def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
         rc = L.whisper_full_parallel(ctx, fp, pcm.ctypes.data_as(vp), len(pcm), n_proc)
     else:
         rc = L.whisper_full(ctx, fp, pcm.ctypes.data_as(vp), len(pcm))
-    return rc, collect(L, ctx), events, script.calls, L.whisper_full_lang_id(ctx)
+    for fn in ("whisper_full_get_vad_segment_t0", "whisper_full_get_vad_segment_t1"):
+        getattr(L, fn).restype = C.c_int64; getattr(L, fn).argtypes = [vp, C.c_int]
+    L.whisper_full_n_vad_segments.argtypes = [vp]
+    vad_segs = [(L.whisper_full_get_vad_segment_t0(ctx, i), L.whisper_full_get_vad_segment_t1(ctx, i)) for i in range(L.whisper_full_n_vad_segments(ctx))] if fp.vad else []
+    return rc, collect(L, ctx), events, script.calls, (L.whisper_full_lang_id(ctx), vad_segs)
 
 
 def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp_path):
@@ -162,7 +177,12 @@ def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp
     for idx, (name, model, seconds, style, kw, extras) in enumerate(SCENARIOS):
         if only and only != name:
             continue
-        pcm = (rng.standard_normal(int(seconds * 16000)) * 0.01).astype(np.float32)
+        if seconds == "jfk":
+            if not os.path.exists(SILERO):
+                continue
+            pcm = np.ascontiguousarray(read_wav_f32(os.path.join(DATA_DIR, "jfk.wav")), np.float32)
+        else:
+            pcm = (rng.standard_normal(int(seconds * 16000)) * 0.01).astype(np.float32)
         lctx, rctx = ctxs[model]
         a = run_side(L, lctx, name, seconds, style, kw, extras, pcm, 1000 + idx)
         b = run_side(R, rctx, name, seconds, style, kw, extras, pcm, 1000 + idx)
@@ -175,7 +195,9 @@ def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp
             assert len(sa[4]) == len(sb[4]), (name, i, "tokens")
             for j, (ta, tb) in enumerate(zip(sa[4], sb[4])):
                 assert ta == tb, (name, i, j, ta, tb)
-        assert a[4] == b[4], (name, "lang id")
+        assert a[4] == b[4], (name, "lang id / VAD segments", a[4], b[4])
+        if kw.get("vad"):
+            assert len(a[4][1]) == 4                                                    # the reference's KAT for jfk.wav (tests/test-vad.cpp)
         if kw.get("n_processors", 1) == 1:
             assert a[2] == b[2], (name, "callback events", a[2][:8], b[2][:8])
             assert a[3] == b[3], (name, "logits callback calls", a[3], b[3])

@@ -874,7 +874,17 @@ static bool vad_filter(whisper_context * ctx, whisper_state * st, const whisper_
     if (!st->vad_context) {
         whisper_vad_context_params vp = whisper_vad_default_context_params();
         vp.gpu_device = ctx->params.gpu_device;
-        whisper_vad_context * v = whisper_vad_init_from_file_with_params(params.vad_model_path, vp);
+        whisper_vad_context * v = nullptr;
+        if (ctx->scripted) {                                                            // engine-less test context: host-only VAD context
+            std::ifstream fin(params.vad_model_path ? params.vad_model_path : "", std::ios::binary);
+            whisper_model_loader loader = {};
+            loader.context = &fin;
+            loader.read  = [](void * c, void * out, size_t n) -> size_t { auto * f = (std::ifstream *) c; f->read((char *) out, (std::streamsize) n); return (size_t) f->gcount(); };
+            loader.eof   = [](void * c) -> bool { return ((std::ifstream *) c)->eof(); };
+            loader.close = [](void *) {};
+            if (fin) v = vad_load(&loader, -1);
+        } else
+        v = whisper_vad_init_from_file_with_params(params.vad_model_path, vp);
         if (!v) { logf(LOG_ERROR, "%s: failed to initialize VAD context\n", __func__); return false; }
         st->vad_context.reset(v);
     }

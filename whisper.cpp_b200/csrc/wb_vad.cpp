@@ -362,6 +362,7 @@ WB_EXPORT struct whisper_vad_context * whisper_vad_init_from_file_with_params(co
 }
 
 WB_EXPORT void whisper_vad_reset_state(struct whisper_vad_context * v) {
+    if (v && v->device < 0) { v->h_state.assign(2 * VAD_HID, 0.0f); return; }      // host-only test context
     if (!v || !v->d_state) return;
     cudaSetDevice(v->device);
     cudaMemset(v->d_state, 0, 2 * VAD_HID * sizeof(float));
@@ -371,7 +372,15 @@ WB_EXPORT bool whisper_vad_detect_speech_no_reset(struct whisper_vad_context * v
     if (v->model.n_loaded == 0) { set_error("vad: the model file held no tensors"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return false; }
     const int64_t t0 = time_us();
     logf(LOG_INFO, "%s: detecting speech in %d samples\n", __func__, n_samples);
-    const bool ok = vad_forward_device(v->model, v->device, v->d_state, samples, n_samples, v->probs);
+    bool ok;
+    if (v->device < 0) {
+        // Only the engine-less TEST context (wb200_dbg_scripted_context -> vad_filter) owns a host-only VAD context; every context made by
+        // whisper_vad_init_* lives on a GPU.  The host walk of the kernels' phases stands in for the device there.
+        if (v->h_state.empty()) v->h_state.assign(2 * VAD_HID, 0.0f);
+        vad_forward_emulated(v->model, v->h_state.data(), samples, n_samples, v->probs);
+        ok = true;
+    } else
+    ok = vad_forward_device(v->model, v->device, v->d_state, samples, n_samples, v->probs);
     v->t_vad_us += time_us() - t0;
     if (!ok) { logf(LOG_ERROR, "%s: failed to compute VAD graph: %s\n", __func__, last_error()); return false; }
     logf(LOG_INFO, "%s: vad time = %.2f ms processing %d samples\n", __func__, 1e-3f * v->t_vad_us, n_samples);

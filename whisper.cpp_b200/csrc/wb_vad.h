@@ -62,7 +62,8 @@ int64_t vad_map_token_time(int64_t t, const std::vector<VadSegmentInfo> & segs);
 bool vad_upload(VadModel & m, int device);
 void vad_free_device(VadModel & m, int device);
 bool vad_forward_device(const VadModel & m, int device, float * d_state, const float * samples, int n_samples, std::vector<float> & probs);
-// the same arithmetic walked thread by thread on the host: TEST HOOK ONLY (wb200_dbg_vad_probs); never used by the API
+// the same arithmetic walked thread by thread on the host: TEST HOOKS ONLY (wb200_dbg_vad_probs, and the host-only VAD context of
+// the engine-less test context); no context created through whisper.h reaches it
 void vad_forward_emulated(const VadModel & m, float * state, const float * samples, int n_samples, std::vector<float> & probs);
 
 } // namespace wb
@@ -72,6 +73,7 @@ struct whisper_vad_context {
     int n_threads = 4, device = 0;
     wb::VadModel model;
     float * d_state = nullptr;                      // LSTM h | c
+    std::vector<float> h_state;                     // the same for the host-only test context (device < 0)
     std::vector<float> probs;
 };
 struct whisper_vad_segments { std::vector<wb::VadSegment> data; };
