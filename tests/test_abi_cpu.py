@@ -81,3 +81,46 @@ def test_no_cpu_fallback_fails_loudly():
     assert b"no CUDA device" in L.wb200_last_error() or b"CPU fallback" in L.wb200_last_error()
     cp.use_gpu = False
     assert not L.whisper_init_from_file_with_params(os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin").encode(), cp)
+
+
+C_PROGRAM = r"""
+#include "whisper_b200.h"
+#include <stdio.h>
+#include <string.h>
+/* a C99 client of the header, as tests/test-c.c of the reference is for whisper.h: structs by value, callbacks, enums */
+static void on_segment(struct whisper_context * ctx, struct whisper_state * st, int n_new, void * ud) { (void) ctx; (void) st; (void) n_new; (void) ud; }
+int main(void) {
+    struct whisper_context_params cp = whisper_context_default_params();
+    struct whisper_full_params fp = whisper_full_default_params(WHISPER_SAMPLING_BEAM_SEARCH);
+    struct whisper_vad_params vp = whisper_vad_default_params();
+    struct whisper_vad_context_params vcp = whisper_vad_default_context_params();
+    fp.new_segment_callback = on_segment;
+    printf("%zu %zu %zu %zu %zu\n", sizeof(cp), sizeof(fp), sizeof(whisper_token_data), sizeof(vp), sizeof(vcp));
+    printf("%d %d %d %.2f %d %d\n", (int) cp.use_gpu, (int) cp.flash_attn, fp.beam_search.beam_size, (double) fp.entropy_thold, fp.greedy.best_of, vp.speech_pad_ms);
+    printf("%s %d %s\n", whisper_lang_str(whisper_lang_id("de")), whisper_lang_max_id(), whisper_version());
+    /* no GPU here: init must fail cleanly, not crash */
+    cp.use_gpu = 0;
+    printf("%d\n", whisper_init_from_file_with_params("/nonexistent.bin", cp) == NULL);
+    return 0;
+}
+"""
+
+
+def test_header_is_valid_c_and_links(tmp_path, ref):
+    """the reference keeps tests/test-c.c to guarantee that whisper.h stays C; same for include/whisper_b200.h, plus a link + run"""
+    src = tmp_path / "client.c"
+    src.write_text(C_PROGRAM)
+    exe = str(tmp_path / "client")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", exe, "-L", libdir, "-lwhisper_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].split()[:3] == ["48", "304", "56"], lines[0]            # the reference's struct sizes (test_struct_sizes_match_reference)
+    rp = bind_whisper_api(ref).whisper_full_default_params(1)
+    assert lines[1] == "1 1 %d %.2f %d 30" % (rp.beam_search.beam_size, rp.entropy_thold, rp.greedy.best_of), lines[1]
+    assert lines[2].split()[0] == "de" and lines[2].split()[1] == "99"
+    assert lines[3] == "1"
