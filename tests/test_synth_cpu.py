@@ -42,3 +42,23 @@ def test_written_model_loads_in_reference(ref, tmp_path, wtype):
     assert ref.whisper_model_ftype(ctx) == synth.FTYPE_OF[wtype]
     assert ref.whisper_token_to_str(ctx, 220) == b" "
     ref.whisper_free(ctx)
+
+
+@pytest.mark.parametrize("wtype", [synth.Q5_1, synth.Q6_K, synth.Q4_1, synth.Q2_K, synth.Q3_K])
+def test_host_expanded_formats_load_in_reference_and_parse_here(lib, ref, tmp_path, wtype):
+    """files in the formats this engine expands to F16 at load time (csrc/wb_dequant_host.cpp): written with ggml's own quantisers, they load
+    in the reference, and this library's header parser accepts the ftype (the weight upload itself needs a GPU: tests/test_wider_formats_gpu.py)"""
+    from wbtest import ref_quantize
+    bind_whisper_api(ref); bind_whisper_api(lib)
+    path = str(tmp_path / "m.bin")
+    cfg = "test-2l-512.en" if wtype in (synth.Q2_K, synth.Q3_K, synth.Q6_K) else "test-2l.en"          # K-quants need rows of 256
+    synth.write_model(path, cfg, wtype, seed=1, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"), quantizer=lambda t, w: ref_quantize(ref, t, w))
+    cp = ref.whisper_context_default_params(); cp.use_gpu = False
+    ctx = ref.whisper_init_from_file_with_params(path.encode(), cp)
+    assert ctx
+    assert ref.whisper_model_ftype(ctx) == synth.FTYPE_OF[wtype]
+    ref.whisper_free(ctx)
+    lib.wb200_dbg_vocab_context.restype = C.c_void_p; lib.wb200_dbg_vocab_context.argtypes = [C.c_char_p]
+    mine = lib.wb200_dbg_vocab_context(path.encode())
+    assert mine, lib.wb200_last_error()
+    assert lib.whisper_model_ftype(mine) == synth.FTYPE_OF[wtype] and lib.whisper_model_n_text_layer(mine) == 2

@@ -1,6 +1,7 @@
 // wb_model.cu -- legacy-ggml model file -> HBM (see wb_model.h for the layout decisions).
 // Follows whisper_model_load (src/whisper.cpp:1485-1962) record by record; tensor names from src/whisper-arch.h:42-109.
 #include <chrono>
+#include "wb_dequant_host.h"
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -117,13 +118,21 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
     }
     m.mtype = hp.n_audio_layer == 4 ? 1 : hp.n_audio_layer == 6 ? 2 : hp.n_audio_layer == 12 ? 3 : hp.n_audio_layer == 24 ? 4 : hp.n_audio_layer == 32 ? 5 : 0;
     hp.ftype %= 1000; // strip GGML_QNT_VERSION (src/whisper.cpp:1549-1551)
+    int host_dq = -1;
     switch (hp.ftype) {  // ggml_ftype_to_ggml_type (ggml/src/ggml.c:1426-1463)
         case 0: m.wtype = WT_F32; break;  case 1: m.wtype = WT_F16; break; case 2: m.wtype = WT_Q4_0; break;
         case 7: m.wtype = WT_Q8_0; break; case 8: m.wtype = WT_Q5_0; break; case 12: m.wtype = WT_Q4_K; break;
         case 13: m.wtype = WT_Q5_K; break;
+        // formats without device kernels: expanded on the host at load time, kept in HBM as F16 (wb_dequant_host.h)
+        case 3: host_dq = HT_Q4_1; break; case 9: host_dq = HT_Q5_1; break; case 10: host_dq = HT_Q2_K; break;
+        case 11: host_dq = HT_Q3_K; break; case 14: host_dq = HT_Q6_K; break;
         default: set_error("invalid model (ftype %d is not supported by this engine)", hp.ftype); return false;
     }
-    const int file_wtype = m.wtype;
+    if (host_dq >= 0) {
+        m.wtype = WT_F16;
+        logf(LOG_WARN, "%s: ftype %d (ggml type %d) has no device kernels in this engine: matrices are expanded to F16 at load time\n", __func__, hp.ftype, host_dq);
+    }
+    const int file_wtype = host_dq >= 0 ? host_dq : m.wtype;
     const int wt = (m.wtype == WT_F32) ? WT_F16 : m.wtype;   // F32 matrices are stored as F16 in HBM
     logf(LOG_INFO, "%s: n_vocab=%d n_audio_ctx=%d n_audio_state=%d n_audio_head=%d n_audio_layer=%d n_text_ctx=%d n_text_state=%d n_text_head=%d n_text_layer=%d n_mels=%d ftype=%d\n",
          __func__, hp.n_vocab, hp.n_audio_ctx, hp.n_audio_state, hp.n_audio_head, hp.n_audio_layer, hp.n_text_ctx, hp.n_text_state, hp.n_text_head, hp.n_text_layer, hp.n_mels, hp.ftype);
@@ -295,10 +304,24 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
             const int bs = wt_is_kquant(ttype) ? 256 : 32;
             if (ne[0] % bs) { set_error("tensor '%s': row length %lld not divisible by block size", name.c_str(), (long long) ne[0]); return false; }
             nbytes = (size_t) ((double) nelements * wt_bpw(ttype) + 0.5);
+        } else if (host_dq_supported(ttype) && ttype == host_dq) {
+            if (ne[0] % host_dq_block_values(ttype)) { set_error("tensor '%s': row length %lld not divisible by block size", name.c_str(), (long long) ne[0]); return false; }
+            nbytes = (size_t) (nelements / host_dq_block_values(ttype)) * host_dq_block_bytes(ttype);
         } else { set_error("tensor '%s' has unsupported type %d", name.c_str(), ttype); return false; }
-        if (nbytes > max_bytes) { set_error("tensor '%s' is larger than expected", name.c_str()); return false; }
-        R.rdn(hstage, nbytes);
-        if (!R.ok) { set_error("truncated data for tensor '%s'", name.c_str()); return false; }
+        const bool expand = host_dq_supported(ttype);             // blocks -> f32 on the host, then the ordinary F32 -> F16 upload
+        if (nbytes > max_bytes || (expand && (size_t) nelements * 4 > max_bytes)) { set_error("tensor '%s' is larger than expected", name.c_str()); return false; }
+        const int file_ttype = ttype;                              // what the record says; `ttype` below is what is staged on the device
+        const size_t file_bytes = nbytes;
+        if (expand) {
+            std::vector<uint8_t> blocks(nbytes);
+            R.rdn(blocks.data(), nbytes);
+            if (!R.ok) { set_error("truncated data for tensor '%s'", name.c_str()); return false; }
+            host_dequantize(ttype, blocks.data(), reinterpret_cast<float *>(hstage), nelements);
+            nbytes = (size_t) nelements * 4; ttype = WT_F32;
+        } else {
+            R.rdn(hstage, nbytes);
+            if (!R.ok) { set_error("truncated data for tensor '%s'", name.c_str()); return false; }
+        }
         WB_CUDA_OK(cudaMemcpy(dstage, hstage, nbytes, cudaMemcpyHostToDevice));
 
         if (D.kind == Dest::VEC_F32) {
@@ -319,7 +342,7 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
                 set_error("tensor '%s' has wrong shape in model file: got [%lld, %lld], expected [%d, %d]", name.c_str(), (long long) ne[0], (long long) ne[1], D.cols, D.rows);
                 return false;
             }
-            if (ttype != file_wtype) { set_error("tensor '%s' has type %d, expected %d", name.c_str(), ttype, file_wtype); return false; }
+            if (file_ttype != file_wtype) { set_error("tensor '%s' has type %d, expected %d", name.c_str(), file_ttype, file_wtype); return false; }
             QMat & q = *D.mat;
             const int K = q.K;
             if (q.layout == 1) {
@@ -344,7 +367,7 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         }
         WB_CUDA_OK(cudaDeviceSynchronize());
         D.seen = true;
-        total += nbytes;
+        total += file_bytes;
         m.n_loaded++;
     }
     logf(LOG_INFO, "%s: model size = %.2f MB (%d tensors), HBM image = %.2f MB\n", __func__, total / 1e6, m.n_loaded, m.bytes_weights / 1e6);
