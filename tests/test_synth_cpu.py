@@ -44,7 +44,7 @@ def test_written_model_loads_in_reference(ref, tmp_path, wtype):
     ref.whisper_free(ctx)
 
 
-@pytest.mark.parametrize("wtype", [synth.Q5_1, synth.Q6_K, synth.Q4_1, synth.Q2_K, synth.Q3_K])
+@pytest.mark.parametrize("wtype", [synth.Q5_1, synth.Q6_K, synth.Q4_1, synth.Q2_K, synth.Q3_K, synth.BF16])
 def test_host_expanded_formats_load_in_reference_and_parse_here(lib, ref, tmp_path, wtype):
     """files in the formats this engine expands to F16 at load time (csrc/wb_dequant_host.cpp): written with ggml's own quantisers, they load
     in the reference, and this library's header parser accepts the ftype (the weight upload itself needs a GPU: tests/test_wider_formats_gpu.py)"""

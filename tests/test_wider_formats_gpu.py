@@ -1,4 +1,4 @@
-"""GPU: checkpoints in ggml formats that have no device kernels here (Q5_1, Q4_1, Q6_K, Q3_K, Q2_K) -- expanded to F16 on the host at load
+"""GPU: checkpoints in ggml formats that have no device kernels here (Q5_1, Q4_1, Q6_K, Q3_K, Q2_K, BF16) -- expanded to F16 on the host at load
 time (csrc/wb_dequant_host.cpp, pinned against ggml's to_float by tests/test_dequant_cpu.py) and run by the F16 kernels -- against the
 reference CPU build on the same file.  The reference multiplies these blocks with int8 activation blocks (Q8_1 / Q8_K), so its own
 outputs carry the same ~1e-2 activation-quantisation noise as for Q5_0 / Q4_K; the tolerances are those of tests/test_e2e_gpu.py for the
@@ -16,10 +16,11 @@ pytestmark = pytest.mark.gpu
 #                 cfg,               enc rms, kv rms, logits rms (of std), argmax margin (std)
 CASES = {synth.Q5_1: ("test-2l.en",     3e-2, 3.5e-2, 5e-2, 0.3), synth.Q4_1: ("test-2l.en",     4e-2, 5e-2, 7e-2, 0.4),
          synth.Q6_K: ("test-2l-512.en", 2e-2, 2.5e-2, 4e-2, 0.25), synth.Q3_K: ("test-2l-512.en", 8e-2, 1e-1, 1.2e-1, 0.6),
-         synth.Q2_K: ("test-2l-512.en", 1.5e-1, 1.8e-1, 2.2e-1, 1.0)}
+         synth.Q2_K: ("test-2l-512.en", 1.5e-1, 1.8e-1, 2.2e-1, 1.0),
+         synth.BF16: ("test-2l.en",     1.5e-2, 2e-2, 3e-2, 0.2)}        # the reference rounds activations to bf16 (8 mantissa bits)
 
 
-@pytest.mark.parametrize("wt", [synth.Q5_1, synth.Q6_K, synth.Q4_1, synth.Q3_K, synth.Q2_K])
+@pytest.mark.parametrize("wt", [synth.Q5_1, synth.Q6_K, synth.Q4_1, synth.Q3_K, synth.Q2_K, synth.BF16])
 def test_host_expanded_formats_match_reference(lib, ref, tmp_path, wt):
     cfg, e_enc, e_kv, e_log, margin = CASES[wt]
     path = str(tmp_path / "m.bin")

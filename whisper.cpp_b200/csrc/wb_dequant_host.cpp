@@ -89,9 +89,9 @@ void dq_q6_k(const uint8_t * b, float * y) {
 
 } // namespace
 
-bool   host_dq_supported(int t)    { return t == HT_Q4_1 || t == HT_Q5_1 || t == HT_Q2_K || t == HT_Q3_K || t == HT_Q6_K; }
-int    host_dq_block_values(int t) { return (t == HT_Q4_1 || t == HT_Q5_1) ? 32 : 256; }
-size_t host_dq_block_bytes(int t)  { switch (t) { case HT_Q4_1: return 20; case HT_Q5_1: return 24; case HT_Q2_K: return 84; case HT_Q3_K: return 110; case HT_Q6_K: return 210; } return 0; }
+bool   host_dq_supported(int t)    { return t == HT_Q4_1 || t == HT_Q5_1 || t == HT_Q2_K || t == HT_Q3_K || t == HT_Q6_K || t == HT_BF16; }
+int    host_dq_block_values(int t) { return t == HT_BF16 ? 1 : (t == HT_Q4_1 || t == HT_Q5_1) ? 32 : 256; }
+size_t host_dq_block_bytes(int t)  { switch (t) { case HT_Q4_1: return 20; case HT_Q5_1: return 24; case HT_Q2_K: return 84; case HT_Q3_K: return 110; case HT_Q6_K: return 210; case HT_BF16: return 2; } return 0; }
 
 void host_dequantize(int t, const void * src, float * dst, int64_t n) {
     const int bv = host_dq_block_values(t); const size_t bb = host_dq_block_bytes(t);
@@ -100,6 +100,7 @@ void host_dequantize(int t, const void * src, float * dst, int64_t n) {
         switch (t) {
             case HT_Q4_1: dq_q4_1(p, dst); break; case HT_Q5_1: dq_q5_1(p, dst); break; case HT_Q2_K: dq_q2_k(p, dst); break;
             case HT_Q3_K: dq_q3_k(p, dst); break; case HT_Q6_K: dq_q6_k(p, dst); break;
+            case HT_BF16: { uint16_t h; memcpy(&h, p, 2); const uint32_t u = (uint32_t) h << 16; memcpy(dst, &u, 4); } break;   // bf16 = upper half of an f32
         }
     }
 }

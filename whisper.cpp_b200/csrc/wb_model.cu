@@ -125,7 +125,7 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         case 13: m.wtype = WT_Q5_K; break;
         // formats without device kernels: expanded on the host at load time, kept in HBM as F16 (wb_dequant_host.h)
         case 3: host_dq = HT_Q4_1; break; case 9: host_dq = HT_Q5_1; break; case 10: host_dq = HT_Q2_K; break;
-        case 11: host_dq = HT_Q3_K; break; case 14: host_dq = HT_Q6_K; break;
+        case 11: host_dq = HT_Q3_K; break; case 14: host_dq = HT_Q6_K; break; case 24: host_dq = HT_BF16; break;
         default: set_error("invalid model (ftype %d is not supported by this engine)", hp.ftype); return false;
     }
     if (host_dq >= 0) {

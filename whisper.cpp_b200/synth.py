@@ -16,8 +16,8 @@ import zlib
 import numpy as np
 
 F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K = 0, 1, 2, 6, 8, 12, 13
-Q4_1, Q5_1, Q2_K, Q3_K, Q6_K = 3, 7, 10, 11, 14              # no NumPy quantiser here: pass quantizer= (ggml's own, via the oracle build)
-FTYPE_OF = {F32: 0, F16: 1, Q4_0: 2, Q8_0: 7, Q5_0: 8, Q4_K: 12, Q5_K: 13, Q4_1: 3, Q5_1: 9, Q2_K: 10, Q3_K: 11, Q6_K: 14}
+Q4_1, Q5_1, Q2_K, Q3_K, Q6_K, BF16 = 3, 7, 10, 11, 14, 30              # no NumPy quantiser here: pass quantizer= (ggml's own, via the oracle build)
+FTYPE_OF = {F32: 0, F16: 1, Q4_0: 2, Q8_0: 7, Q5_0: 8, Q4_K: 12, Q5_K: 13, Q4_1: 3, Q5_1: 9, Q2_K: 10, Q3_K: 11, Q6_K: 14, BF16: 24}
 
 CONFIGS = {
     # name: n_vocab, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels
