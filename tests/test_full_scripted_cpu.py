@@ -151,7 +151,17 @@ def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
         getattr(L, fn).restype = C.c_int64; getattr(L, fn).argtypes = [vp, C.c_int]
     L.whisper_full_n_vad_segments.argtypes = [vp]
     vad_segs = [(L.whisper_full_get_vad_segment_t0(ctx, i), L.whisper_full_get_vad_segment_t1(ctx, i)) for i in range(L.whisper_full_n_vad_segments(ctx))] if fp.vad else []
-    return rc, collect(L, ctx), events, script.calls, (L.whisper_full_lang_id(ctx), vad_segs)
+    # the run counters whisper_print_timings reports (fallbacks, sample / encode / decode / batchd / prompt runs)
+    lines = []
+    grab = LOG_CB(lambda level, text, ud: lines.append(text.decode("utf-8", "replace")))
+    L.whisper_log_set(grab, None)
+    L.whisper_print_timings(ctx); L.whisper_reset_timings(ctx)
+    L.whisper_log_set(_quiet, None)
+    import re
+    txt = "".join(lines)
+    counters = tuple(int(v) for v in re.findall(r"fallbacks =\s*(\d+) p /\s*(\d+) h", txt)[0]) + tuple(int(v) for v in re.findall(r"/\s*(\d+) runs", txt))
+    assert len(counters) == 7, txt
+    return rc, collect(L, ctx), events, script.calls, (L.whisper_full_lang_id(ctx), vad_segs, counters if n_proc == 1 else None)
 
 
 def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp_path):
