@@ -1,0 +1,89 @@
+"""Drive the reference's unmodified whisper-cli (oracle/_ref/whisper-cli-*) and compare what it writes with the same run through the C ABI.
+TEST INFRASTRUCTURE shared by tests/test_cli_cpu.py (reference CLI on the reference library, on the CPU) and
+tests/test_zz_reference_cli_gpu.py (the same CLI sources linked against libwhisper_b200.so, on the GPU)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import numpy as np
+
+from wbtest import ROOT, DATA_DIR, TokenData, read_wav_f32
+from e2e_util import Side
+
+vp = C.c_void_p
+SILERO = os.path.join(DATA_DIR, "for-tests-silero-v6.2.0-ggml.bin")
+
+
+def _needs_more(b):
+    """utf8_trailing_bytes_needed of the reference's examples/common-whisper.cpp:201-227"""
+    i = len(b) - 1
+    while i >= 0 and (b[i] & 0xC0) == 0x80:
+        i -= 1
+    if i < 0:
+        return 0
+    c = b[i]
+    expected = 1 if c & 0x80 == 0 else 2 if c & 0xE0 == 0xC0 else 3 if c & 0xF0 == 0xE0 else 4 if c & 0xF8 == 0xF0 else 0
+    return max(0, expected - (len(b) - i)) if expected else 0
+
+
+def _merge(toks):
+    """cli.cpp:760-780 writes one JSON entry per run of tokens that completes a UTF-8 sequence, with the id / p of the first one"""
+    out = []; j = 0
+    while j < len(toks):
+        tid, p, text = toks[j]; j += 1
+        while j < len(toks) and _needs_more(text) > 0:
+            text += toks[j][2]; j += 1
+        out.append((tid, p))
+    return out
+
+
+def api_run(lib, path, pcm, vad, is_ref):
+    A = Side(lib, path, is_ref)
+    try:
+        L = A.L
+        L.whisper_full_get_token_data.restype = TokenData
+        L.whisper_full_get_token_data.argtypes = [vp, C.c_int, C.c_int]
+        fp = L.whisper_full_default_params(0)                       # what cli.cpp sets for: -bs 1 -bo 1 -nf -ojf
+        fp.print_progress = False; fp.print_realtime = False; fp.n_threads = 4
+        fp.greedy.best_of = 1; fp.beam_search.beam_size = 1; fp.temperature_inc = 0.0
+        fp.token_timestamps = True; fp.initial_prompt = b""; fp.language = b"en"
+        if vad:
+            fp.vad = True; fp.vad_model_path = SILERO.encode()
+        assert L.whisper_full(A.ctx, fp, pcm.ctypes.data_as(vp), len(pcm)) == 0
+        eot = L.whisper_token_eot(A.ctx)
+        segs = []
+        for i in range(L.whisper_full_n_segments(A.ctx)):
+            toks = [L.whisper_full_get_token_data(A.ctx, i, j) for j in range(L.whisper_full_n_tokens(A.ctx, i))]
+            segs.append((L.whisper_full_get_segment_t0(A.ctx, i) * 10, L.whisper_full_get_segment_t1(A.ctx, i) * 10,
+                         L.whisper_full_get_segment_text(A.ctx, i).decode("utf-8", "replace"), _merge([(t.id, t.p, L.whisper_token_to_str(A.ctx, t.id)) for t in toks])))
+        return segs, eot
+    finally:
+        A.free()
+
+
+
+
+def check_cli_against_api(cli, lib, is_ref, model_path, tmp_path, vad):
+    lib.whisper_full_get_segment_t0.restype = C.c_int64; lib.whisper_full_get_segment_t1.restype = C.c_int64
+    lib.whisper_token_to_str.restype = C.c_char_p; lib.whisper_token_to_str.argtypes = [vp, C.c_int]
+    wav = os.path.join(DATA_DIR, "jfk.wav")
+    out = str(tmp_path / "cli_out")
+    cmd = [cli, "-m", model_path, "-f", wav, "-bs", "1", "-bo", "1", "-nf", "-np", "-ojf", "-of", out]
+    if vad:
+        cmd += ["--vad", "--vad-model", SILERO]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.returncode, r.stderr[-800:])
+    doc = json.loads(open(out + ".json", encoding="utf-8", errors="replace").read(), strict=False)   # token text may hold raw control characters
+    got = doc["transcription"]
+    assert len(got) >= 1
+    pcm = np.ascontiguousarray(read_wav_f32(wav), np.float32)
+    api, eot = api_run(lib, model_path, pcm, vad, is_ref)
+    assert len(got) == len(api), (len(got), len(api))
+    for c, a in zip(got, api):
+        assert (c["offsets"]["from"], c["offsets"]["to"]) == (a[0], a[1])
+        assert c["text"] == a[2]
+        assert [t["id"] for t in c["tokens"]] == [t[0] for t in a[3]]
+        assert np.allclose([t["p"] for t in c["tokens"]], [t[1] for t in a[3]], rtol=2e-5, atol=2e-6)
+    if vad:
+        assert all(0 <= c["offsets"]["from"] <= c["offsets"]["to"] <= 11100 for c in got)      # times on the ORIGINAL timeline of the 11 s clip
+    return got

@@ -124,3 +124,26 @@ def test_header_is_valid_c_and_links(tmp_path, ref):
     assert lines[1] == "1 1 %d %.2f %d 30" % (rp.beam_search.beam_size, rp.entropy_thold, rp.greedy.best_of), lines[1]
     assert lines[2].split()[0] == "de" and lines[2].split()[1] == "99"
     assert lines[3] == "1"
+
+
+def test_unmodified_reference_cli_links_against_this_library(tmp_path):
+    """oracle/_ref/whisper-cli-b200 = the reference's examples/cli/cli.cpp (+ common*.cpp, grammar-parser.cpp), compiled from the reference tree
+    without a change and linked against libwhisper_b200.so: every whisper_* symbol it imports binds to this library, and on a box without
+    a GPU it stops with the loud no-CPU-fallback error (exit code 3 of cli.cpp), not with a transcript."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "whisper-cli-b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/whisper-cli-b200 not built (make -C oracle cli)")
+    env = dict(os.environ, LD_DEBUG="bindings")
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True, env=env, timeout=120)
+    bound = re.findall(r"binding file \S*whisper-cli-b200 \[0\] to (\S+) \[0\]: normal symbol `(whisper_\w+)'", r.stderr + r.stdout)
+    assert bound, "no whisper_* bindings seen"
+    assert all(lib.endswith("libwhisper_b200.so") for lib, _ in bound), sorted({lib for lib, _ in bound})
+    model = os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"); wav = os.path.join(DATA_DIR, "jfk.wav")
+    r = subprocess.run([exe, "-m", model, "-f", wav], capture_output=True, text=True, timeout=120)
+    import ctypes
+    try:
+        ctypes.CDLL("libcuda.so.1"); has_driver = True
+    except OSError:
+        has_driver = False
+    if not has_driver:
+        assert r.returncode == 3 and "no CPU fallback" in (r.stderr + r.stdout), (r.returncode, r.stderr[-400:])

@@ -1,0 +1,23 @@
+"""CPU: validates the CLI-vs-API harness (tests/cli_util.py) on the reference pair -- the reference's whisper-cli linked against the reference
+library must write exactly what the reference's C ABI returns for the mirrored parameters -- so that the GPU test of the same harness on
+libwhisper_b200.so (tests/test_zz_reference_cli_gpu.py) checks the engine, not the harness."""
+import os
+import pytest
+
+from wbtest import ROOT, DATA_DIR, F16
+from e2e_util import synth
+from cli_util import check_cli_against_api, SILERO
+
+CLI_REF = os.path.join(ROOT, "oracle", "_ref", "whisper-cli-ref")
+
+
+@pytest.mark.parametrize("vad", [False, True])
+def test_reference_cli_equals_reference_api(ref, tmp_path, vad):
+    if not os.path.exists(CLI_REF):
+        pytest.skip("oracle/_ref/whisper-cli-ref not built (make -C oracle cli)")
+    if vad and not os.path.exists(SILERO):
+        pytest.skip("silero fixture missing")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", F16, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    got = check_cli_against_api(CLI_REF, ref, True, path, tmp_path, vad)
+    assert sum(len(c["tokens"]) for c in got) > 50

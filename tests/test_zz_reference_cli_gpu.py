@@ -1,0 +1,25 @@
+"""GPU: the reference's UNMODIFIED whisper-cli (examples/cli/cli.cpp, compiled from the reference tree into oracle/_ref/whisper-cli-b200 and
+linked against libwhisper_b200.so) transcribes on this engine, and what it writes (-ojf: full JSON with token ids and probabilities) is what the
+same parameters give through the C ABI directly.  With --vad it goes through params.vad with the Silero weights of the reference's tests.
+The harness itself is validated on the CPU with the reference pair (tests/test_cli_cpu.py).
+(Written after the GPU budget of round 1 was spent: not yet run on a GPU.)"""
+import os
+import pytest
+
+from wbtest import ROOT, DATA_DIR, F16, Q5_0
+from e2e_util import synth
+from cli_util import check_cli_against_api, SILERO
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "oracle", "_ref", "whisper-cli-b200")
+
+
+@pytest.mark.parametrize("wt,vad", [(F16, False), (Q5_0, False), (F16, True)])
+def test_reference_cli_runs_on_this_engine(lib, tmp_path, wt, vad):
+    if not os.path.exists(CLI):
+        pytest.skip("oracle/_ref/whisper-cli-b200 not built")
+    if vad and not os.path.exists(SILERO):
+        pytest.skip("silero fixture missing")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", wt, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    check_cli_against_api(CLI, lib, False, path, tmp_path, vad)
