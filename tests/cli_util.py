@@ -87,3 +87,18 @@ def check_cli_against_api(cli, lib, is_ref, model_path, tmp_path, vad):
     if vad:
         assert all(0 <= c["offsets"]["from"] <= c["offsets"]["to"] <= 11100 for c in got)      # times on the ORIGINAL timeline of the 11 s clip
     return got
+
+
+def run_reference_bench(exe, model_path, threads=4):
+    """the reference's examples/bench/bench.cpp: returns {name: (total ms, runs, ms per run)} parsed from whisper_print_timings"""
+    import re
+    r = subprocess.run([exe, "-m", model_path, "-t", str(threads)], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, (r.returncode, r.stderr[-800:])
+    out = {}
+    for name, total, runs, per in re.findall(r"(\w+) time =\s*([\d.]+) ms /\s*(\d+) runs \(\s*([\d.]+) ms per run\)", r.stderr + r.stdout):
+        out[name] = (float(total), int(runs), float(per))
+    # what bench.cpp:120-150 executes after whisper_reset_timings: 1 encode, 256 single-token decodes, 64 batches of 5, 16 prompts of 256
+    # (batched and prompt "runs" count tokens, src/whisper.cpp:2974-2983)
+    assert {k: v[1] for k, v in out.items() if k in ("encode", "decode", "batchd", "prompt")} == {"encode": 1, "decode": 256, "batchd": 64 * 5, "prompt": 16 * 256}, out
+    assert all(out[k][0] > 0 for k in ("encode", "decode", "batchd", "prompt"))
+    return out

@@ -21,3 +21,15 @@ def test_reference_cli_equals_reference_api(ref, tmp_path, vad):
     synth.write_model(path, "test-2l.en", F16, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
     got = check_cli_against_api(CLI_REF, ref, True, path, tmp_path, vad)
     assert sum(len(c["tokens"]) for c in got) > 50
+
+
+def test_reference_bench_harness_on_reference(tmp_path):
+    """the parser / expectations used for whisper-bench on the engine (GPU test), validated here on the reference's own build"""
+    from cli_util import run_reference_bench
+    exe = os.path.join(ROOT, "oracle", "_ref", "whisper-bench-ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/whisper-bench-ref not built (make -C oracle cli)")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, (51864, 1500, 384, 6, 1, 448, 384, 6, 1, 80), F16, seed=3, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    t = run_reference_bench(exe, path)
+    print("reference whisper-bench on a 1-layer synthetic model:", {k: round(v[2], 2) for k, v in t.items()})

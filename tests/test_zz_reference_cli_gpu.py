@@ -23,3 +23,16 @@ def test_reference_cli_runs_on_this_engine(lib, tmp_path, wt, vad):
     path = str(tmp_path / "m.bin")
     synth.write_model(path, "test-2l.en", wt, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
     check_cli_against_api(CLI, lib, False, path, tmp_path, vad)
+
+
+def test_reference_bench_program_runs_on_this_engine(lib, tmp_path):
+    """examples/bench/bench.cpp of the reference, unmodified, linked against libwhisper_b200.so: whisper_set_mel(NULL, 0), whisper_encode,
+    256-token prompts, 256 single-token steps, 64 batches of 5 through whisper_decode, then whisper_print_timings with the expected run counts"""
+    from cli_util import run_reference_bench
+    exe = os.path.join(ROOT, "oracle", "_ref", "whisper-bench-b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/whisper-bench-b200 not built")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", Q5_0, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    t = run_reference_bench(exe, path)
+    print("whisper-bench on the engine (test-2l.en Q5_0):", {k: round(v[2], 3) for k, v in t.items()})
