@@ -102,3 +102,11 @@ def run_reference_bench(exe, model_path, threads=4):
     assert {k: v[1] for k, v in out.items() if k in ("encode", "decode", "batchd", "prompt")} == {"encode": 1, "decode": 256, "batchd": 64 * 5, "prompt": 16 * 256}, out
     assert all(out[k][0] > 0 for k in ("encode", "decode", "batchd", "prompt"))
     return out
+
+
+def run_reference_vad_example(exe):
+    """examples/vad-speech-segments of the reference on jfk.wav with the Silero fixture: [(start cs, end cs)] it prints"""
+    import re
+    r = subprocess.run([exe, "-vm", SILERO, "-f", os.path.join(DATA_DIR, "jfk.wav"), "-np"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-800:])
+    return [(float(a), float(b)) for a, b in re.findall(r"Speech segment \d+: start = ([\d.]+), end = ([\d.]+)", r.stdout)]

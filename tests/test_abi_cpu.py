@@ -147,3 +147,26 @@ def test_unmodified_reference_cli_links_against_this_library(tmp_path):
         has_driver = False
     if not has_driver:
         assert r.returncode == 3 and "no CPU fallback" in (r.stderr + r.stdout), (r.returncode, r.stderr[-400:])
+
+
+def test_vad_init_fails_loudly_without_cuda(tmp_path):
+    """whisper_vad_init_* has no CPU path either"""
+    import ctypes
+    try:
+        ctypes.CDLL("libcuda.so.1")
+        pytest.skip("a CUDA driver is present")
+    except OSError:
+        pass
+    lib = load_lib()
+    silero = os.path.join(DATA_DIR, "for-tests-silero-v6.2.0-ggml.bin")
+    if not os.path.exists(silero):
+        pytest.skip("silero fixture missing")
+
+    class VadCtxParams(C.Structure):
+        _fields_ = [("n_threads", C.c_int), ("use_gpu", C.c_bool), ("gpu_device", C.c_int)]
+    lib.whisper_vad_default_context_params.restype = VadCtxParams
+    lib.whisper_vad_init_from_file_with_params.restype = C.c_void_p
+    lib.whisper_vad_init_from_file_with_params.argtypes = [C.c_char_p, VadCtxParams]
+    lib.wb200_last_error.restype = C.c_char_p
+    assert not lib.whisper_vad_init_from_file_with_params(silero.encode(), lib.whisper_vad_default_context_params())
+    assert b"no CPU fallback" in lib.wb200_last_error()

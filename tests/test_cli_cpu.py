@@ -33,3 +33,13 @@ def test_reference_bench_harness_on_reference(tmp_path):
     synth.write_model(path, (51864, 1500, 384, 6, 1, 448, 384, 6, 1, 80), F16, seed=3, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
     t = run_reference_bench(exe, path)
     print("reference whisper-bench on a 1-layer synthetic model:", {k: round(v[2], 2) for k, v in t.items()})
+
+
+def test_reference_vad_example_prints_the_golden_segments():
+    from cli_util import run_reference_vad_example
+    import numpy as np
+    exe = os.path.join(ROOT, "oracle", "_ref", "vad-segments-ref")
+    if not os.path.exists(exe) or not os.path.exists(SILERO):
+        pytest.skip("oracle/_ref/vad-segments-ref or the silero fixture missing")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vad_r01.npz"))
+    assert run_reference_vad_example(exe) == list(zip(g["seg_t0"].astype(float).tolist(), g["seg_t1"].astype(float).tolist()))

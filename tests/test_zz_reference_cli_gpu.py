@@ -36,3 +36,14 @@ def test_reference_bench_program_runs_on_this_engine(lib, tmp_path):
     synth.write_model(path, "test-2l.en", Q5_0, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
     t = run_reference_bench(exe, path)
     print("whisper-bench on the engine (test-2l.en Q5_0):", {k: round(v[2], 3) for k, v in t.items()})
+
+
+def test_reference_vad_example_runs_on_this_engine():
+    """examples/vad-speech-segments/speech.cpp of the reference, unmodified, on libwhisper_b200.so: prints the reference's known answer"""
+    import numpy as np
+    from cli_util import run_reference_vad_example
+    exe = os.path.join(ROOT, "oracle", "_ref", "vad-segments-b200")
+    if not os.path.exists(exe) or not os.path.exists(SILERO):
+        pytest.skip("oracle/_ref/vad-segments-b200 or the silero fixture missing")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vad_r01.npz"))
+    assert run_reference_vad_example(exe) == list(zip(g["seg_t0"].astype(float).tolist(), g["seg_t1"].astype(float).tolist()))

@@ -343,6 +343,12 @@ WB_EXPORT struct whisper_vad_context_params whisper_vad_default_context_params(v
 // use_gpu is ignored: this engine has no CPU path, the network always runs on GPU `gpu_device`.
 WB_EXPORT struct whisper_vad_context * whisper_vad_init_with_params(struct whisper_model_loader * loader, struct whisper_vad_context_params params) {
     if (!loader || !loader->read || !loader->eof) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available: libwhisper_b200 has no CPU fallback (VAD)"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error());
+        return nullptr;
+    }
+    if (params.gpu_device >= ndev) { set_error("vad: gpu_device %d out of range (%d devices)", params.gpu_device, ndev); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return nullptr; }
     whisper_vad_context * v = nullptr;
     try { v = vad_load(loader, params.gpu_device < 0 ? 0 : params.gpu_device); } catch (...) { set_error("vad: allocation failed"); v = nullptr; }
     if (v) v->n_threads = params.n_threads;
