@@ -23,6 +23,7 @@ vp = C.c_void_p
 LOGITS_CB = C.CFUNCTYPE(None, vp, vp, C.POINTER(TokenData), C.c_int, C.POINTER(C.c_float), vp)
 SEG_CB = C.CFUNCTYPE(None, vp, vp, C.c_int, vp)
 PROG_CB = C.CFUNCTYPE(None, vp, vp, C.c_int, vp)
+ENC_CB = C.CFUNCTYPE(C.c_bool, vp, vp, vp)
 LOG_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, vp)
 _quiet = LOG_CB(lambda level, text, ud: None)
 
@@ -106,6 +107,7 @@ SCENARIOS = [
     ("grammar",             "en", 28.0, "medium", dict(grammar=True, grammar_penalty=30.0, no_timestamps=True, max_tokens=24), {"timestamps": False}),
     ("parallel2",           "en", 64.0, "peaked", dict(n_processors=2), {"use_segments": False}),
     ("short_input",         "en", 0.05, "peaked", dict(), {}),
+    ("encoder_begin_stop",  "en", 95.0, "peaked", dict(stop_at_window=3), {}),
     ("suppress_regex_nst",  "en", 26.0, "medium", dict(suppress_regex=b"^ ?[a-mA-M]", suppress_nst=True, best_of=2, temperature_inc=0.5), {}),
     ("max_initial_ts_tdrz", "en", 12.0, "medium", dict(max_initial_ts=0.04, tdrz_enable=True, entropy_thold=3.5, n_max_text_ctx=0), {}),
     # params.vad on jfk.wav with the Silero weights of the reference's tests (product side: host walk of the VAD kernels' phases)
@@ -133,6 +135,14 @@ def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
         ptrs, arrs = build_grammar(rules); keep += [ptrs, arrs]
         fp.grammar_rules = C.cast(ptrs, vp); fp.n_grammar_rules = len(rules); fp.i_start_rule = 0
     n_proc = kw.pop("n_processors", 1)
+    stop_at = kw.pop("stop_at_window", 0)
+    windows = [0]
+    if stop_at:                                        # encoder_begin_callback returning false ends the run with what was transcribed so far
+        def _begin(c, st, ud):
+            windows[0] += 1
+            return windows[0] < stop_at
+        begin_cb = ENC_CB(_begin); keep.append(begin_cb)
+        fp.encoder_begin_callback = C.cast(begin_cb, vp)
     if kw.pop("vad", False):
         fp.vad = True; fp.vad_model_path = SILERO.encode()
         fp.vad_params.samples_overlap = kw.pop("samples_overlap", 0.1)
