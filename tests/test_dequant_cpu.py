@@ -8,7 +8,7 @@ import pytest
 
 from wbtest import ref_quantize, ref_dequantize
 
-TYPES = {"Q4_1": 3, "Q5_1": 7, "Q2_K": 10, "Q3_K": 11, "Q6_K": 14, "BF16": 30}
+TYPES = {"Q4_1": 3, "Q5_1": 7, "Q2_K": 10, "Q3_K": 11, "Q6_K": 14, "BF16": 30, "Q4_K": 12, "Q5_K": 13}
 
 
 @pytest.mark.parametrize("name", sorted(TYPES))
@@ -36,4 +36,4 @@ def test_host_dequantisers_match_ggml(lib, ref, name):
     # what goes to HBM: the f16 rounding of these values
     assert np.array_equal(got.astype(np.float16), want.astype(np.float16)) or np.mean(got.astype(np.float16) != want.astype(np.float16)) < 1e-3
     assert lib.wb200_dbg_dequantize(t, buf.ctypes.data, got.ctypes.data, 17) == (0 if name == "BF16" else -1)
-    assert lib.wb200_dbg_dequantize(2, buf.ctypes.data, got.ctypes.data, 32) == -1   # Q4_0 has device kernels, not this path
+    assert lib.wb200_dbg_dequantize(2, buf.ctypes.data, got.ctypes.data, 32) == -1   # Q4_0 only has device kernels

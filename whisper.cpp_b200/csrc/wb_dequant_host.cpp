@@ -87,11 +87,33 @@ void dq_q6_k(const uint8_t * b, float * y) {
     }
 }
 
+// Q4_K / Q5_K: d, dmin | 12 bytes holding 8 six-bit (scale, min) pairs | [Q5_K: 32 bytes of fifth bits] | 128 bytes of nibbles   (144 / 176 bytes)
+// These two formats HAVE device kernels (kernel chain); the host expansion serves the opt-in WB200_KQUANT_AS_F16 load mode.
+inline void k4_scale_min(int j, const uint8_t * q, int & sc, int & mn) {
+    if (j < 4) { sc = q[j] & 63; mn = q[j + 4] & 63; }
+    else       { sc = (q[j + 4] & 0x0F) | ((q[j - 4] >> 6) << 4); mn = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+void dq_q45_k(const uint8_t * b, float * y, bool five) {
+    const float d = h2f(b), dmin = h2f(b + 2);
+    const uint8_t * scales = b + 4, * qh = b + 16, * q = b + (five ? 48 : 16);
+    for (int pair = 0; pair < 4; ++pair, q += 32) {
+        for (int part = 0; part < 2; ++part) {
+            int sc, mn; k4_scale_min(2 * pair + part, scales, sc, mn);
+            const float dl = d * (float) sc, ml = dmin * (float) mn;
+            for (int l = 0; l < 32; ++l) {
+                int v = part ? (q[l] >> 4) : (q[l] & 0x0F);
+                if (five && (qh[l] & (1u << (2 * pair + part)))) v += 16;
+                *y++ = dl * (float) v - ml;
+            }
+        }
+    }
+}
+
 } // namespace
 
-bool   host_dq_supported(int t)    { return t == HT_Q4_1 || t == HT_Q5_1 || t == HT_Q2_K || t == HT_Q3_K || t == HT_Q6_K || t == HT_BF16; }
+bool   host_dq_supported(int t)    { return t == HT_Q4_1 || t == HT_Q5_1 || t == HT_Q2_K || t == HT_Q3_K || t == HT_Q6_K || t == HT_BF16 || t == HT_Q4_K || t == HT_Q5_K; }
 int    host_dq_block_values(int t) { return t == HT_BF16 ? 1 : (t == HT_Q4_1 || t == HT_Q5_1) ? 32 : 256; }
-size_t host_dq_block_bytes(int t)  { switch (t) { case HT_Q4_1: return 20; case HT_Q5_1: return 24; case HT_Q2_K: return 84; case HT_Q3_K: return 110; case HT_Q6_K: return 210; case HT_BF16: return 2; } return 0; }
+size_t host_dq_block_bytes(int t)  { switch (t) { case HT_Q4_1: return 20; case HT_Q5_1: return 24; case HT_Q2_K: return 84; case HT_Q3_K: return 110; case HT_Q6_K: return 210; case HT_BF16: return 2; case HT_Q4_K: return 144; case HT_Q5_K: return 176; } return 0; }
 
 void host_dequantize(int t, const void * src, float * dst, int64_t n) {
     const int bv = host_dq_block_values(t); const size_t bb = host_dq_block_bytes(t);
@@ -100,6 +122,7 @@ void host_dequantize(int t, const void * src, float * dst, int64_t n) {
         switch (t) {
             case HT_Q4_1: dq_q4_1(p, dst); break; case HT_Q5_1: dq_q5_1(p, dst); break; case HT_Q2_K: dq_q2_k(p, dst); break;
             case HT_Q3_K: dq_q3_k(p, dst); break; case HT_Q6_K: dq_q6_k(p, dst); break;
+            case HT_Q4_K: dq_q45_k(p, dst, false); break; case HT_Q5_K: dq_q45_k(p, dst, true); break;
             case HT_BF16: { uint16_t h; memcpy(&h, p, 2); const uint32_t u = (uint32_t) h << 16; memcpy(dst, &u, 4); } break;   // bf16 = upper half of an f32
         }
     }

@@ -9,7 +9,7 @@
 
 namespace wb {
 
-enum HostDqType : int { HT_Q4_1 = 3, HT_Q5_1 = 7, HT_Q2_K = 10, HT_Q3_K = 11, HT_Q6_K = 14, HT_BF16 = 30 };   // ggml_type ids
+enum HostDqType : int { HT_Q4_1 = 3, HT_Q5_1 = 7, HT_Q2_K = 10, HT_Q3_K = 11, HT_Q6_K = 14, HT_BF16 = 30, HT_Q4_K = 12, HT_Q5_K = 13 };   // ggml_type ids
 
 bool   host_dq_supported(int ggml_type);
 int    host_dq_block_values(int ggml_type);        // 32 or 256 (1 for BF16)

@@ -128,9 +128,14 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
         case 11: host_dq = HT_Q3_K; break; case 14: host_dq = HT_Q6_K; break; case 24: host_dq = HT_BF16; break;
         default: set_error("invalid model (ftype %d is not supported by this engine)", hp.ftype); return false;
     }
+    if (wt_is_kquant(m.wtype) && getenv("WB200_KQUANT_AS_F16") && atoi(getenv("WB200_KQUANT_AS_F16")) != 0) {
+        // opt-in: Q4_K / Q5_K run on the kernel chain (8 rows per decode pass); expanded to F16 they run in the persistent kernel (64 rows)
+        host_dq = m.wtype == WT_Q4_K ? HT_Q4_K : HT_Q5_K;
+    }
     if (host_dq >= 0) {
         m.wtype = WT_F16;
-        logf(LOG_WARN, "%s: ftype %d (ggml type %d) has no device kernels in this engine: matrices are expanded to F16 at load time\n", __func__, hp.ftype, host_dq);
+        logf(LOG_WARN, "%s: ftype %d (ggml type %d): matrices are expanded to F16 on the host at load time (%s)\n", __func__, hp.ftype, host_dq,
+             (host_dq == HT_Q4_K || host_dq == HT_Q5_K) ? "WB200_KQUANT_AS_F16" : "no device kernels for this block format");
     }
     const int file_wtype = host_dq >= 0 ? host_dq : m.wtype;
     const int wt = (m.wtype == WT_F32) ? WT_F16 : m.wtype;   // F32 matrices are stored as F16 in HBM
@@ -308,7 +313,7 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
             if (ne[0] % host_dq_block_values(ttype)) { set_error("tensor '%s': row length %lld not divisible by block size", name.c_str(), (long long) ne[0]); return false; }
             nbytes = (size_t) (nelements / host_dq_block_values(ttype)) * host_dq_block_bytes(ttype);
         } else { set_error("tensor '%s' has unsupported type %d", name.c_str(), ttype); return false; }
-        const bool expand = host_dq_supported(ttype);             // blocks -> f32 on the host, then the ordinary F32 -> F16 upload
+        const bool expand = host_dq >= 0 && ttype == host_dq;     // blocks -> f32 on the host, then the ordinary F32 -> F16 upload
         if (nbytes > max_bytes || (expand && (size_t) nelements * 4 > max_bytes)) { set_error("tensor '%s' is larger than expected", name.c_str()); return false; }
         const int file_ttype = ttype;                              // what the record says; `ttype` below is what is staged on the device
         const size_t file_bytes = nbytes;
