@@ -49,3 +49,29 @@ def test_host_expanded_formats_match_reference(lib, ref, tmp_path, wt):
             toks.append(int(lb.argmax()))
     finally:
         A.free(); B.free()
+
+
+@pytest.mark.parametrize("wt", [synth.Q4_K, synth.Q5_K])
+def test_kquants_expanded_to_f16_opt_in(lib, ref, tmp_path, monkeypatch, wt):
+    """WB200_KQUANT_AS_F16=1: Q4_K / Q5_K files through the persistent decode kernel as F16 matrices (default: kernel chain on the blocks)"""
+    monkeypatch.setenv("WB200_KQUANT_AS_F16", "1")
+    e_enc, e_kv, e_log, margin = (4e-2, 5e-2, 7e-2, 0.4) if wt == synth.Q4_K else (3e-2, 3.5e-2, 5e-2, 0.3)     # tests/test_e2e_gpu.py TOL
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l-512.en", wt, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"), quantizer=lambda t, w: ref_quantize(ref, t, w))
+    pcm = read_wav_f32(os.path.join(DATA_DIR, "jfk.wav"))
+    A = Side(lib, path, False); B = Side(ref, path, True)
+    try:
+        A.pcm_to_mel(pcm); B.pcm_to_mel(pcm)
+        A.encode(0); B.encode(0)
+        ta, tb = taps(A), taps(B)
+        assert rms_err(ta["enc"], tb["enc"]) < e_enc
+        sot = A.L.whisper_token_sot(A.ctx)
+        toks = [sot]; n_past = 0
+        for step in range(6):
+            feed = toks if step == 0 else toks[-1:]
+            la = A.decode(feed, n_past); lb = B.decode(feed, n_past)
+            n_past += len(feed)
+            assert rms_err(la - lb.mean(), lb - lb.mean()) < e_log, step
+            toks.append(int(lb.argmax()))
+    finally:
+        A.free(); B.free()
