@@ -6,7 +6,7 @@ __graft_entry__.smoke() do, and only as a checker.
 Pinning: every function here is checked in tests/test_oracle_cpu.py against the UNMODIFIED reference built from
 /root/reference (oracle/_ref/libwhisper_ref.so): block decoders against ggml's own `to_float` traits, the Q8_0
 activation quantiser + integer dot against ggml_quantize_chunk output, log-mel against `whisper_pcm_to_mel`, the
-logits filter against `whisper_process_logits`.  The reference ships no numeric golden vectors for this path
+conv stem / encoder / cross K,V (EncoderOracle) and the decoder step (DecoderOracle) against the reference's own tensors and logits.  The reference ships no numeric golden vectors for this path
 (SURVEY.md section 8c), so the compiled reference is the pin.
 
 Citations are file:line in ggml-org/whisper.cpp @ 233fe1fc.
@@ -292,3 +292,91 @@ class DecoderOracle:
             x = x + _mul_mat(t[p + "mlp.2.weight"], hcur) + _vec(t[p + "mlp.2.bias"])
         cur = layernorm(x[-1:], _vec(t["decoder.ln.weight"]), _vec(t["decoder.ln.bias"]))
         return _mul_mat(t["decoder.token_embedding.weight"], cur)[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# conv stem, encoder and cross K/V (src/whisper.cpp:1982-2042, 2044-2275, 2278-2354) on one 30-second window
+# ----------------------------------------------------------------------------------------------------------------------
+def _mul_mat_rows(t, x, chunk=128):
+    """_mul_mat for many activation rows (the encoder has 1500): same arithmetic, evaluated in row chunks"""
+    ttype, (rows, k), raw = t
+    x = np.asarray(x, np.float32).reshape(-1, k)
+    if ttype in (F16, F32):
+        return _mul_mat(t, x)
+    wi, wd = _block_ints(ttype, raw)
+    wi = wi.reshape(rows, k // 32, 32).astype(np.float32); wd = wd.reshape(rows, k // 32)      # |sum of 32 products| < 2^24: exact in f32
+    out = np.empty((x.shape[0], rows), np.float32)
+    for r0 in range(0, x.shape[0], chunk):
+        xs = x[r0:r0 + chunk]
+        xq, xd = quantize_q8_0(xs.reshape(-1))
+        xq = xq.reshape(len(xs), k // 32, 32).astype(np.float32); xd = xd.reshape(len(xs), k // 32)
+        sumi = np.einsum("nbk,tbk->tnb", wi, xq)
+        out[r0:r0 + chunk] = (sumi * (wd[None] * xd[:, None, :])).astype(np.float32).sum(axis=2, dtype=np.float32)
+    return out
+
+
+def conv1d_f16(w_t, x, stride):
+    """ggml_conv_1d_ph (3 taps, padding 1) as the CPU backend runs it: im2col in F16, F16 x F16 products summed in f32
+    (ggml/src/ggml.c ggml_conv_1d -> ggml_im2col(..., GGML_TYPE_F16) + ggml_mul_mat).  w_t: (type, [oc, ic, 3], raw); x: [ic][T] -> [oc][T/stride]"""
+    ttype, (oc, ic, kw), raw = w_t
+    assert kw == 3 and ttype in (F16, F32)
+    w = (np.frombuffer(raw, np.float16) if ttype == F16 else np.frombuffer(raw, np.float32).astype(np.float16)).astype(np.float64).reshape(oc, ic, 3)
+    xh = np.asarray(x, np.float32).astype(np.float16).astype(np.float64)
+    T = xh.shape[1]
+    xp = np.pad(xh, ((0, 0), (1, 1)))
+    To = (T + 2 - 3) // stride + 1
+    cols = np.stack([xp[:, k:k + stride * To:stride] for k in range(3)], axis=1)          # [ic][3][To]
+    return np.einsum("oik,ikt->ot", w, cols).astype(np.float32)
+
+
+class EncoderOracle:
+    """whisper_build_graph_conv / _encoder / _cross for one window (flash-attention path, CPU arithmetic: F16 im2col, F16-rounded
+    activations in front of F16 matrices / Q8_0 blocks in front of quantised ones, K and V of the attention rounded to F16 and padded with
+    unmasked zero keys to 1536, f16-table GELU).  Accumulations are f64 here where the reference sums in f32 (or, for P.V of many query
+    rows, in F16): the comparison with the compiled reference in tests/test_oracle_cpu.py carries that as its tolerance."""
+
+    def __init__(self, path):
+        self.hp, self.t = read_model(path)
+
+    def conv(self, mel_window):
+        """mel_window: [n_mels][2*n_ctx] f32 (frames past n_len zero, src/whisper.cpp:2389-2411) -> embd_conv [d][n_ctx]"""
+        t = self.t
+        x = conv1d_f16(t["encoder.conv1.weight"], mel_window, 1) + _vec(t["encoder.conv1.bias"]).reshape(-1, 1)
+        x = gelu(x)
+        x = conv1d_f16(t["encoder.conv2.weight"], x, 2) + _vec(t["encoder.conv2.bias"]).reshape(-1, 1)
+        return gelu(x)
+
+    def encode(self, embd_conv):
+        """embd_conv [d][T] -> embd_enc [T][d]"""
+        hp, t = self.hp, self.t
+        d, H, L = hp["n_audio_state"], hp["n_audio_head"], hp["n_audio_layer"]
+        T = embd_conv.shape[1]
+        Tp = (T + 255) // 256 * 256                                                       # GGML_PAD(n_ctx, 256): 36 zero keys at T = 1500
+        x = embd_conv.T + _vec(t["encoder.positional_embedding"])[:T]
+        f16 = lambda a: np.asarray(a, np.float32).astype(np.float16).astype(np.float32)   # noqa: E731
+        for l in range(L):
+            p = "encoder.blocks.%d." % l
+            cur = layernorm(x, _vec(t[p + "attn_ln.weight"]), _vec(t[p + "attn_ln.bias"]))
+            q = _mul_mat_rows(t[p + "attn.query.weight"], cur) + _vec(t[p + "attn.query.bias"])
+            k = f16(_mul_mat_rows(t[p + "attn.key.weight"], cur))
+            v = f16(_mul_mat_rows(t[p + "attn.value.weight"], cur) + _vec(t[p + "attn.value.bias"]))
+            att = np.empty((T, d), np.float32)
+            for h in range(H):
+                sl = slice(64 * h, 64 * h + 64)
+                att[:, sl] = attention(q[:, sl], k[:, sl], v[:, sl], 1.0 / np.sqrt(64.0), n_zero_keys=Tp - T)
+            x = x + _mul_mat_rows(t[p + "attn.out.weight"], att) + _vec(t[p + "attn.out.bias"])
+            cur = layernorm(x, _vec(t[p + "mlp_ln.weight"]), _vec(t[p + "mlp_ln.bias"]))
+            hcur = gelu(_mul_mat_rows(t[p + "mlp.0.weight"], cur) + _vec(t[p + "mlp.0.bias"]))
+            x = x + _mul_mat_rows(t[p + "mlp.2.weight"], hcur) + _vec(t[p + "mlp.2.bias"])
+        return layernorm(x, _vec(t["encoder.ln_post.weight"]), _vec(t["encoder.ln_post.bias"]))
+
+    def cross(self, embd_enc):
+        """-> (K [L][T][d], V [L][T][d]) as stored in kv_cross: K scaled by 64^-1/4 before the F16 rounding, V with bias"""
+        hp, t = self.hp, self.t
+        kq = np.float32(64.0) ** np.float32(-0.25)
+        ks, vs = [], []
+        for l in range(hp["n_text_layer"]):
+            p = "decoder.blocks.%d." % l
+            ks.append((_mul_mat_rows(t[p + "cross_attn.key.weight"], embd_enc) * kq).astype(np.float16).astype(np.float32))
+            vs.append((_mul_mat_rows(t[p + "cross_attn.value.weight"], embd_enc) + _vec(t[p + "cross_attn.value.bias"])).astype(np.float16).astype(np.float32))
+        return np.stack(ks), np.stack(vs)

@@ -135,3 +135,55 @@ def test_decoder_step_restatement_vs_reference(ref, tmp_path, wtype, tol):
         srt = np.sort(want)
         assert int(got.argmax()) == int(want.argmax()) or srt[-1] - srt[-2] < 10 * tol * want.std()
     ref.whisper_free(ctx)
+
+
+@pytest.mark.parametrize("wtype,tol_enc,tol_kv", [(F16, 1e-3, 1e-4), (Q5_0, 1e-2, 1e-4)])     # measured: 2.2e-4 / 3.1e-3 and 7e-6
+def test_encoder_restatement_vs_reference(ref, tmp_path, wtype, tol_enc, tol_kv):
+    """oracle/ref_numpy.EncoderOracle (conv stem, encoder, cross K/V of src/whisper.cpp:1982-2354 in NumPy with the CPU backend's rounding
+    points) against the reference's own tensors on the synthetic 2-layer model.  F16 weights: the difference is accumulation order / width
+    (f64 here, f32 and F16 P.V there).  Q5_0: additionally every row's Q8_0 activation blocks can round differently once the inputs differ
+    in the last bit, the same ~1e-2 noise floor the GPU parity tests allow (tests/test_e2e_gpu.py TOL)."""
+    import importlib.util
+    from wbtest import ROOT
+    spec = importlib.util.spec_from_file_location("wb_synth", os.path.join(ROOT, "whisper.cpp_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", wtype, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    bind_whisper_api(ref)
+    cp = ref.whisper_context_default_params(); cp.use_gpu = False
+    ctx = ref.whisper_init_from_file_with_params(path.encode(), cp)
+    assert ctx
+    pcm = synth.synth_audio(seed=5, seconds=4.0)
+    assert ref.whisper_pcm_to_mel(ctx, pcm.ctypes.data, len(pcm), 4) == 0
+    assert ref.whisper_encode(ctx, 0, 4) == 0
+    vp = C.c_void_p
+    ref.wref_ctx_state.restype = vp; ref.wref_ctx_state.argtypes = [vp]
+    st = ref.wref_ctx_state(ctx)
+    ref.wref_mel_n_len.argtypes = [vp]; ref.wref_mel_n_mel.argtypes = [vp]; ref.wref_mel_copy.argtypes = [vp, vp, C.c_int64]
+    n_len, n_mel = ref.wref_mel_n_len(st), ref.wref_mel_n_mel(st)
+    mel = np.empty((n_mel, n_len), np.float32)
+    assert ref.wref_mel_copy(st, mel.ctypes.data, mel.size) == 0
+    L, d, T, Tp = 2, 384, 1500, 1536
+    for nme in ("wref_embd_conv", "wref_embd_enc", "wref_kv_cross_k", "wref_kv_cross_v"):
+        getattr(ref, nme).restype = C.c_int64; getattr(ref, nme).argtypes = [vp, vp, C.c_int64]
+    conv = np.empty((d, T), np.float32); enc = np.empty((T, d), np.float32)
+    assert ref.wref_embd_conv(st, conv.ctypes.data, conv.size) == conv.size and ref.wref_embd_enc(st, enc.ctypes.data, enc.size) == enc.size
+    kc = np.empty((L, Tp, d), np.float16); vc = np.empty((L, Tp, d), np.float16)
+    assert ref.wref_kv_cross_k(st, kc.ctypes.data, kc.size) == kc.size and ref.wref_kv_cross_v(st, vc.ctypes.data, vc.size) == vc.size
+    ref.whisper_free(ctx)
+
+    def rms(a, b):
+        return float(np.sqrt(((np.asarray(a, np.float64) - b) ** 2).mean()) / np.sqrt((np.asarray(b, np.float64) ** 2).mean()))
+
+    E = rn.EncoderOracle(path)
+    my_conv = E.conv(mel[:, :2 * T])
+    e_conv = rms(my_conv, conv)
+    my_enc = E.encode(conv)                                       # fed with the reference's conv output: errors do not compound
+    e_enc = rms(my_enc, enc)
+    my_k, my_v = E.cross(enc)
+    e_k, e_v = rms(my_k, kc[:, :T].astype(np.float32)), rms(my_v, vc[:, :T].astype(np.float32))
+    print("encoder restatement (%d): conv %.2e  enc %.2e  cross K %.2e  V %.2e" % (wtype, e_conv, e_enc, e_k, e_v))
+    assert e_conv < 1e-4                                          # F16 x F16 products, f32 vs f64 sums (measured 7e-6)
+    assert e_enc < tol_enc
+    assert e_k < tol_kv and e_v < tol_kv
+    assert np.abs(kc[:, T:].astype(np.float32)).max() == 0 and np.abs(vc[:, T:].astype(np.float32)).max() == 0      # the 36 padded keys
