@@ -113,6 +113,7 @@ SCENARIOS = [
     # params.vad on jfk.wav with the Silero weights of the reference's tests (product side: host walk of the VAD kernels' phases)
     ("vad_token_ts",        "en", "jfk", "peaked", dict(vad=True, token_timestamps=True, max_len=30), {}),
     ("vad_beam",            "en", "jfk", "medium", dict(vad=True, strategy=1, beam_size=2, samples_overlap=0.3), {}),
+    ("vad_parallel2",       "en", "jfk", "peaked", dict(vad=True, n_processors=2), {"use_segments": False}),
 ]
 
 
