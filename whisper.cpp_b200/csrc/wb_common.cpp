@@ -1,4 +1,6 @@
 // wb_common.cpp -- error text, launch accounting, logging sink.
+#include <nvtx3/nvToolsExt.h>
+#include <cstdlib>
 #include "wb_common.h"
 #include <utility>
 #include <map>
@@ -84,6 +86,10 @@ void logf(int level, const char * fmt, ...) {
     va_end(ap);
     g_log_cb(level, buf, g_log_ud);
 }
+
+static bool nvtx_enabled() { static const bool on = [] { const char * e = getenv("WB200_NVTX"); return e && atoi(e) != 0; }(); return on; }
+NvtxRange::NvtxRange(const char * name) : on(nvtx_enabled()) { if (on) nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { if (on) nvtxRangePop(); }
 
 cudaError_t ensure_dyn_smem(const void * kernel, size_t bytes) {
     static std::mutex mu;

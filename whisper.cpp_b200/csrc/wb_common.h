@@ -42,6 +42,10 @@ void     count_d2h(uint64_t n);
 uint64_t h2d_bytes();
 uint64_t d2h_bytes();
 
+// NVTX range around the engine's coarse steps (mel, encode, decode pass, VAD) for `ncu --nvtx` / Nsight filtering; active only with
+// WB200_NVTX=1 (header-only NVTX3, no link dependency; a no-op without a profiler attached)
+struct NvtxRange { bool on; explicit NvtxRange(const char * name); ~NvtxRange(); NvtxRange(const NvtxRange &) = delete; NvtxRange & operator=(const NvtxRange &) = delete; };
+
 // logging through the whisper_log_set callback (default: stderr)
 enum LogLevel { LOG_DEBUG = 1, LOG_INFO = 2, LOG_WARN = 3, LOG_ERROR = 4 };
 void logf(int level, const char * fmt, ...) __attribute__((format(printf, 2, 3)));

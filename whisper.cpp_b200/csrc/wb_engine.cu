@@ -167,6 +167,7 @@ bool FrontEnd::pcm_upload(const float * samples, int n_samples) {
     return true;
 }
 bool FrontEnd::pcm_to_mel(const float * samples, int n_samples, bool samples_on_device) {
+    NvtxRange nvtx("wb200.mel");
     WB_CUDA_OK(cudaSetDevice(m->device));
     if (!samples && n_samples > 0 && pcm_resident != n_samples) { set_error("pcm_to_mel: no host samples and no resident PCM of %d samples", n_samples); return false; }
     n_mel = m->n_filt_mel;
@@ -271,6 +272,7 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
 #define WB_GEMM(desc) do { cudaError_t e_ = gemm_launch(desc, st); if (e_ != cudaSuccess) { set_error("%s:%d gemm_launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return false; } } while (0)
 
 bool Engine::encode(const EncSrc * srcs, int n_win, int n_ctx) {
+    NvtxRange nvtx("wb200.encode");
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
     if (n_win < 1 || n_win > cap_win) { set_error("encode: n_win=%d exceeds the state's capacity %d", n_win, cap_win); return false; }
@@ -420,6 +422,7 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
 
 bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
                     const SampCfg * samp, const int * rowinfo, SampOut * samp_out) {
+    NvtxRange nvtx("wb200.decode");
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
     const int V = hp.n_vocab;

@@ -213,6 +213,7 @@ void vad_free_device(VadModel & m, int device) {
 }
 
 bool vad_forward_device(const VadModel & m, int device, float * d_state, const float * samples, int n_samples, std::vector<float> & probs) {
+    NvtxRange nvtx("wb200.vad");
     if (!m.dev_blob || !d_state) { set_error("vad: the model is not resident on a GPU"); return false; }
     WB_CUDA_OK(cudaSetDevice(device));
     const int n_win = (n_samples + VAD_WIN - 1) / VAD_WIN;
