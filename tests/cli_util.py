@@ -110,3 +110,80 @@ def run_reference_vad_example(exe):
     r = subprocess.run([exe, "-vm", SILERO, "-f", os.path.join(DATA_DIR, "jfk.wav"), "-np"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stderr[-800:])
     return [(float(a), float(b)) for a, b in re.findall(r"Speech segment \d+: start = ([\d.]+), end = ([\d.]+)", r.stdout)]
+
+
+# ---- the reference's HTTP server (examples/server/server.cpp) -----------------------------------------------------------------
+def _free_port():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def check_server_against_api(exe, lib, is_ref, model_path):
+    """start the server on 127.0.0.1, POST samples/jfk.wav to /inference (greedy, no fallback) as json and verbose_json, and compare with
+    the same parameters through the C ABI: texts, segment times (verbose_json turns token timestamps and the 60-character wrap on,
+    server.cpp:627-637, 941-942) and token ids."""
+    import time
+    import requests
+    lib.whisper_full_get_segment_t0.restype = C.c_int64; lib.whisper_full_get_segment_t1.restype = C.c_int64
+    wav = os.path.join(DATA_DIR, "jfk.wav")
+    port = _free_port()
+    proc = subprocess.Popen([exe, "-m", model_path, "--host", "127.0.0.1", "--port", str(port), "-t", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        base = "http://127.0.0.1:%d" % port
+        for _ in range(600):                                        # model load + first CUDA initialisation
+            if proc.poll() is not None:
+                raise AssertionError("server exited: %s" % proc.stderr.read().decode("utf-8", "replace")[-800:])
+            try:
+                if requests.get(base + "/", timeout=1).status_code == 200:
+                    break
+            except requests.RequestException:
+                time.sleep(0.2)
+        else:
+            raise AssertionError("server did not come up")
+        common = {"temperature": "0.0", "temperature_inc": "0.0", "best_of": "1"}
+        out = {}
+        for fmt in ("json", "verbose_json"):
+            with open(wav, "rb") as f:
+                r = requests.post(base + "/inference", files={"file": ("jfk.wav", f, "audio/wav")}, data=dict(common, response_format=fmt), timeout=900)
+            assert r.status_code == 200, (r.status_code, r.text[:400])
+            out[fmt] = json.loads(r.content.decode("utf-8", "replace"), strict=False)
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill(); proc.wait()
+
+    pcm = np.ascontiguousarray(read_wav_f32(wav), np.float32)
+
+    def api(token_ts):
+        A = Side(lib, model_path, is_ref)
+        try:
+            L = A.L
+            L.whisper_full_get_token_data.restype = TokenData; L.whisper_full_get_token_data.argtypes = [vp, C.c_int, C.c_int]
+            fp = L.whisper_full_default_params(0)                   # server.cpp:925-965 with the request above
+            fp.print_progress = False; fp.print_realtime = False; fp.n_threads = 4
+            fp.greedy.best_of = 1; fp.beam_search.beam_size = -1; fp.temperature = 0.0; fp.temperature_inc = 0.0
+            fp.initial_prompt = b""; fp.language = b"en"; fp.max_len = 60; fp.token_timestamps = token_ts; fp.no_context = True
+            assert L.whisper_full(A.ctx, fp, pcm.ctypes.data_as(vp), len(pcm)) == 0
+            eot = L.whisper_token_eot(A.ctx)
+            segs = []
+            for i in range(L.whisper_full_n_segments(A.ctx)):
+                ids = [L.whisper_full_get_token_data(A.ctx, i, j).id for j in range(L.whisper_full_n_tokens(A.ctx, i))]
+                segs.append((L.whisper_full_get_segment_text(A.ctx, i).decode("utf-8", "replace"), L.whisper_full_get_segment_t0(A.ctx, i),
+                             L.whisper_full_get_segment_t1(A.ctx, i), [t for t in ids if t < eot]))
+            return segs
+        finally:
+            A.free()
+
+    plain = api(False)
+    assert out["json"]["text"] == "".join(s[0] + "\n" for s in plain)
+    wrapped = api(True)
+    vs = out["verbose_json"]["segments"]
+    assert len(vs) == len(wrapped), (len(vs), len(wrapped))
+    for v, a in zip(vs, wrapped):
+        assert v["text"] == a[0]
+        assert abs(v["start"] - a[1] * 0.01) < 1e-6 and abs(v["end"] - a[2] * 0.01) < 1e-6
+        assert v.get("tokens", []) == a[3]
+    return out

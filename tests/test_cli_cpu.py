@@ -43,3 +43,17 @@ def test_reference_vad_example_prints_the_golden_segments():
         pytest.skip("oracle/_ref/vad-segments-ref or the silero fixture missing")
     g = np.load(os.path.join(ROOT, "tests", "golden", "vad_r01.npz"))
     assert run_reference_vad_example(exe) == list(zip(g["seg_t0"].astype(float).tolist(), g["seg_t1"].astype(float).tolist()))
+
+
+def test_reference_server_harness_on_reference(ref, tmp_path):
+    """examples/server/server.cpp on the reference library answers /inference with what the reference's C ABI gives for the mirrored
+    parameters: validates tests/cli_util.check_server_against_api before it is pointed at libwhisper_b200.so on the GPU"""
+    from cli_util import check_server_against_api
+    exe = os.path.join(ROOT, "oracle", "_ref", "whisper-server-ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/whisper-server-ref not built (make -C oracle cli)")
+    pytest.importorskip("requests")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", F16, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    out = check_server_against_api(exe, ref, True, path)
+    assert len(out["verbose_json"]["segments"]) >= 2                  # the 60-character wrap produced several segments

@@ -47,3 +47,16 @@ def test_reference_vad_example_runs_on_this_engine():
         pytest.skip("oracle/_ref/vad-segments-b200 or the silero fixture missing")
     g = np.load(os.path.join(ROOT, "tests", "golden", "vad_r01.npz"))
     assert run_reference_vad_example(exe) == list(zip(g["seg_t0"].astype(float).tolist(), g["seg_t1"].astype(float).tolist()))
+
+
+def test_reference_server_runs_on_this_engine(lib, tmp_path):
+    """examples/server/server.cpp of the reference, unmodified, linked against libwhisper_b200.so: HTTP /inference (json and verbose_json)
+    answers with what the C ABI returns directly"""
+    from cli_util import check_server_against_api
+    exe = os.path.join(ROOT, "oracle", "_ref", "whisper-server-b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/whisper-server-b200 not built")
+    pytest.importorskip("requests")
+    path = str(tmp_path / "m.bin")
+    synth.write_model(path, "test-2l.en", Q5_0, seed=7, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    check_server_against_api(exe, lib, False, path)
