@@ -114,6 +114,9 @@ SCENARIOS = [
     ("vad_token_ts",        "en", "jfk", "peaked", dict(vad=True, token_timestamps=True, max_len=30), {}),
     ("vad_beam",            "en", "jfk", "medium", dict(vad=True, strategy=1, beam_size=2, samples_overlap=0.3), {}),
     ("vad_parallel2",       "en", "jfk", "peaked", dict(vad=True, n_processors=2), {"use_segments": False}),
+    # two consecutive calls on the same context with no_context = false: the text context of the first carries into the second
+    ("context_carry_1",     "en", 31.0, "peaked", dict(no_context=False), {}),
+    ("context_carry_2",     "en", 47.0, "medium", dict(no_context=False, n_max_text_ctx=96, best_of=2, temperature_inc=0.5), {}),
 ]
 
 
