@@ -197,6 +197,15 @@ WREF_API int wref_kv_script(int size, const int * ops, int n_ops, int * trace, i
     return 0;
 }
 
+// the batch of the most recent whisper_decode_internal of this state (tokens, positions, sequence ids, logits flags): read from inside a
+// logits_filter_callback it shows exactly what was fed to the decoder for the step being filtered (tests/test_full_scripted_cpu.py)
+WREF_API int wref_last_batch(struct whisper_state * st, int * tok, int * pos, int * seq, int8_t * want, int cap) {
+    const whisper_batch & b = st->batch;
+    if (b.n_tokens > cap) return -1;
+    for (int i = 0; i < b.n_tokens; ++i) { tok[i] = b.token[i]; pos[i] = b.pos[i]; seq[i] = b.seq_id[i][0]; want[i] = b.logits[i]; }
+    return b.n_tokens;
+}
+
 // ---- voice-activity detection (src/whisper.cpp:4367-5515, 6669-6829, 7959-8130) -------------------------------------
 // probabilities -> segments with the reference's own whisper_vad_segments_from_probs (it reads only n_window and probs)
 WREF_API int wref_vad_segments(const float * probs, int n_probs, struct whisper_vad_params params, int64_t * t0, int64_t * t1, int cap) {

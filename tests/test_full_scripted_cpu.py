@@ -36,12 +36,21 @@ class Script:
         self.V = L.whisper_n_vocab(ctx)
         self.beg, self.eot = L.whisper_token_beg(ctx), L.whisper_token_eot(ctx)
         self.calls = 0
+        self.batches = []                                  # crc of (tokens, positions, sequence ids, logits flags) fed to the decoder before each filtered step
+        self.tap = getattr(L, "wref_last_batch", None) or getattr(L, "wb200_dbg_last_batch", None)
+        if self.tap is not None:
+            self.tap.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+            self._tb = [np.empty(2048, np.int32) for _ in range(3)] + [np.empty(2048, np.int8)]
         L.whisper_full_n_segments_from_state.argtypes = [vp]
         self.cb = LOGITS_CB(self._cb)
 
     def _cb(self, ctx, st, toks, n, logits, ud):
         self.calls += 1
         ids = np.fromiter((toks[i].id for i in range(n)), np.int32, n)
+        if self.tap is not None:
+            tb = self._tb
+            nb = self.tap(st, tb[0].ctypes.data, tb[1].ctypes.data, tb[2].ctypes.data, tb[3].ctypes.data, 2048)
+            self.batches.append((nb, zlib.crc32(b"".join(a[:max(nb, 0)].tobytes() for a in tb))))
         nseg = self.L.whisper_full_n_segments_from_state(st) if self.use_segments else 0
         rng = np.random.default_rng((zlib.crc32(ids.tobytes()) ^ self.seed ^ (nseg * 7919)) & 0xFFFFFFFF)
         V, beg, eot = self.V, self.beg, self.eot
@@ -177,7 +186,7 @@ def run_side(L, ctx, name, seconds, style, kw, extras, pcm, seed):
     txt = "".join(lines)
     counters = tuple(int(v) for v in re.findall(r"fallbacks =\s*(\d+) p /\s*(\d+) h", txt)[0]) + tuple(int(v) for v in re.findall(r"/\s*(\d+) runs", txt))
     assert len(counters) == 7, txt
-    return rc, collect(L, ctx), events, script.calls, (L.whisper_full_lang_id(ctx), vad_segs, counters if n_proc == 1 else None)
+    return rc, collect(L, ctx), events, script.calls, (L.whisper_full_lang_id(ctx), vad_segs, counters if n_proc == 1 else None), script.batches
 
 
 def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp_path):
@@ -227,6 +236,9 @@ def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp
         if kw.get("n_processors", 1) == 1:
             assert a[2] == b[2], (name, "callback events", a[2][:8], b[2][:8])
             assert a[3] == b[3], (name, "logits callback calls", a[3], b[3])
+            assert len(a[5]) == len(b[5]) > 0 or a[3] == 0
+            for k, (x, y) in enumerate(zip(a[5], b[5])):                                # what the decoder was fed: prompt assembly, positions, beam sequence ids
+                assert x == y, (name, "decoder input of filtered step", k, x, y)
     for s in stats:
         print("scripted %-22s rc=%d segments=%3d tokens=%4d logits-callback calls=%d" % s)
     if not only:

@@ -143,6 +143,10 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
                   const int8_t * want, int n_tokens, const SampReq * samp) {
     const int64_t t0 = time_us();
     const int n_vocab = ctx.model.hp.n_vocab;
+    if (st.scripted) {                                                       // test hook: what was fed to the decoder (wb200_dbg_last_batch)
+        st.dbg_tok.assign(tokens, tokens + n_tokens); st.dbg_pos.assign(pos, pos + n_tokens);
+        st.dbg_seq.assign(seq, seq + n_tokens); st.dbg_want.assign(want, want + n_tokens);
+    }
     if (st.group) {
         Group::Req r; r.kind = 1; r.ctx = &ctx; r.st = &st; r.tokens = tokens; r.pos = pos; r.seq = seq; r.want = want; r.n = n_tokens; r.samp = samp;
         if (!st.group->submit(r)) return false;
@@ -673,6 +677,14 @@ WB_EXPORT int64_t whisper_full_get_vad_segment_t0(struct whisper_context * ctx, 
 WB_EXPORT int64_t whisper_full_get_vad_segment_t1_from_state(struct whisper_state * st, int i)    { return st->vad.segments[(size_t) i].orig_end; }
 WB_EXPORT int64_t whisper_full_get_vad_segment_t1(struct whisper_context * ctx, int i)            { return ctx->state->vad.segments[(size_t) i].orig_end; }
 // whisper_vad_* : wb_vad.cpp
+
+// host-only test hook: the last decode request of an engine-less (scripted) state
+WB_EXPORT int wb200_dbg_last_batch(struct whisper_state * st, int * tok, int * pos, int * seq, int8_t * want, int cap) {
+    if (!st || !st->scripted || (int) st->dbg_tok.size() > cap) return -1;
+    const int n = (int) st->dbg_tok.size();
+    for (int i = 0; i < n; ++i) { tok[i] = st->dbg_tok[i]; pos[i] = st->dbg_pos[i]; seq[i] = st->dbg_seq[i]; want[i] = st->dbg_want[i]; }
+    return n;
+}
 
 // ---------------------------------------------------------------------------------------------------- engine extensions
 WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float * out, int64_t cap) {

@@ -94,6 +94,7 @@ struct whisper_state {
     // decode leaves all-zero logits, so the transcript is whatever the caller's logits_filter_callback scripts.  It computes nothing and
     // cannot be created through any whisper.h entry point.
     bool scripted = false;
+    std::vector<int> dbg_tok, dbg_pos, dbg_seq; std::vector<int8_t> dbg_want;      // scripted states only: the last decode request (wb200_dbg_last_batch)
 };
 
 struct whisper_context {
