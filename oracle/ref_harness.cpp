@@ -206,6 +206,24 @@ WREF_API int wref_last_batch(struct whisper_state * st, int * tok, int * pos, in
     return b.n_tokens;
 }
 
+// per token of the last decoded batch: FNV-1a hash of the sorted positions of the self-attention KV cells it attended to, read back from the
+// KQ mask the reference built for that decode (src/whisper.cpp:2917-2947) -- the observable result of all KV bookkeeping before it
+WREF_API int wref_last_attended(struct whisper_state * st, uint64_t * out, int cap) {
+    const whisper_batch & b = st->batch;
+    const int n_kv = (int) st->kv_self.n;
+    if (b.n_tokens > cap || (int64_t) st->inp_mask.size() < (int64_t) n_kv * b.n_tokens) return -1;
+    std::vector<int> pos;
+    for (int j = 0; j < b.n_tokens; ++j) {
+        pos.clear();
+        for (int i = 0; i < n_kv; ++i) if (st->inp_mask[(size_t) j * n_kv + i] == 0.0f) pos.push_back(st->kv_self.cells[i].pos);
+        std::sort(pos.begin(), pos.end());
+        uint64_t h = 1469598103934665603ull;
+        for (int v : pos) for (int k = 0; k < 4; ++k) { h ^= (uint64_t) ((v >> (8 * k)) & 0xff); h *= 1099511628211ull; }
+        out[j] = h;
+    }
+    return b.n_tokens;
+}
+
 // ---- voice-activity detection (src/whisper.cpp:4367-5515, 6669-6829, 7959-8130) -------------------------------------
 // probabilities -> segments with the reference's own whisper_vad_segments_from_probs (it reads only n_window and probs)
 WREF_API int wref_vad_segments(const float * probs, int n_probs, struct whisper_vad_params params, int64_t * t0, int64_t * t1, int cap) {

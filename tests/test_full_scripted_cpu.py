@@ -38,6 +38,10 @@ class Script:
         self.calls = 0
         self.batches = []                                  # crc of (tokens, positions, sequence ids, logits flags) fed to the decoder before each filtered step
         self.tap = getattr(L, "wref_last_batch", None) or getattr(L, "wb200_dbg_last_batch", None)
+        self.tap_att = getattr(L, "wref_last_attended", None) or getattr(L, "wb200_dbg_last_attended", None)
+        if self.tap_att is not None:
+            self.tap_att.argtypes = [vp, vp, C.c_int]
+            self._ta = np.empty(2048, np.uint64)
         if self.tap is not None:
             self.tap.argtypes = [vp, vp, vp, vp, vp, C.c_int]
             self._tb = [np.empty(2048, np.int32) for _ in range(3)] + [np.empty(2048, np.int8)]
@@ -50,7 +54,8 @@ class Script:
         if self.tap is not None:
             tb = self._tb
             nb = self.tap(st, tb[0].ctypes.data, tb[1].ctypes.data, tb[2].ctypes.data, tb[3].ctypes.data, 2048)
-            self.batches.append((nb, zlib.crc32(b"".join(a[:max(nb, 0)].tobytes() for a in tb))))
+            na = self.tap_att(st, self._ta.ctypes.data, 2048) if self.tap_att is not None else 0
+            self.batches.append((nb, zlib.crc32(b"".join(a[:max(nb, 0)].tobytes() for a in tb)), na, zlib.crc32(self._ta[:max(na, 0)].tobytes()) if na > 0 else 0))
         nseg = self.L.whisper_full_n_segments_from_state(st) if self.use_segments else 0
         rng = np.random.default_rng((zlib.crc32(ids.tobytes()) ^ self.seed ^ (nseg * 7919)) & 0xFFFFFFFF)
         V, beg, eot = self.V, self.beg, self.eot
@@ -237,6 +242,7 @@ def test_whisper_full_control_flow_identical_under_scripted_logits(lib, ref, tmp
             assert a[2] == b[2], (name, "callback events", a[2][:8], b[2][:8])
             assert a[3] == b[3], (name, "logits callback calls", a[3], b[3])
             assert len(a[5]) == len(b[5]) > 0 or a[3] == 0
+            assert a[3] == 0 or (all(x[0] > 0 and x[2] == x[0] for x in a[5]) and all(y[0] > 0 and y[2] == y[0] for y in b[5]))   # both taps delivered
             for k, (x, y) in enumerate(zip(a[5], b[5])):                                # what the decoder was fed: prompt assembly, positions, beam sequence ids
                 assert x == y, (name, "decoder input of filtered step", k, x, y)
     for s in stats:

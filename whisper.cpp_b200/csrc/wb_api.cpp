@@ -156,6 +156,16 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
     PreparedDecode P;
     if (!prepare_decode(st, tokens, pos, seq, want, n_tokens, P)) return false;
     if (st.scripted) {                                                       // test hook: KV bookkeeping only, the caller's logits callback supplies the values
+        st.dbg_att.resize((size_t) n_tokens);
+        std::vector<int> ps;
+        for (int j = 0; j < n_tokens; ++j) {                                 // what each row attends to, as positions (the index lists the kernels get)
+            ps.clear();
+            for (int c = 0; c < P.nkv[j]; ++c) ps.push_back(st.kv.cells[(size_t) (P.idx[(size_t) j * P.ld + c] - st.cell_off)].pos);
+            std::sort(ps.begin(), ps.end());
+            uint64_t h = 1469598103934665603ull;
+            for (int v : ps) for (int k = 0; k < 4; ++k) { h ^= (uint64_t) ((v >> (8 * k)) & 0xff); h *= 1099511628211ull; }
+            st.dbg_att[(size_t) j] = h;
+        }
         st.samp_out.clear(); st.logits.assign((size_t) n_tokens * n_vocab, 0.0f);
         account_decode(st, n_tokens, time_us() - t0);
         return true;
@@ -684,6 +694,12 @@ WB_EXPORT int wb200_dbg_last_batch(struct whisper_state * st, int * tok, int * p
     const int n = (int) st->dbg_tok.size();
     for (int i = 0; i < n; ++i) { tok[i] = st->dbg_tok[i]; pos[i] = st->dbg_pos[i]; seq[i] = st->dbg_seq[i]; want[i] = st->dbg_want[i]; }
     return n;
+}
+
+WB_EXPORT int wb200_dbg_last_attended(struct whisper_state * st, uint64_t * out, int cap) {
+    if (!st || !st->scripted || (int) st->dbg_att.size() > cap) return -1;
+    for (size_t i = 0; i < st->dbg_att.size(); ++i) out[i] = st->dbg_att[i];
+    return (int) st->dbg_att.size();
 }
 
 // ---------------------------------------------------------------------------------------------------- engine extensions

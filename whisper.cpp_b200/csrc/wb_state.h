@@ -95,6 +95,7 @@ struct whisper_state {
     // cannot be created through any whisper.h entry point.
     bool scripted = false;
     std::vector<int> dbg_tok, dbg_pos, dbg_seq; std::vector<int8_t> dbg_want;      // scripted states only: the last decode request (wb200_dbg_last_batch)
+    std::vector<uint64_t> dbg_att;             // ... and per row a hash of the sorted positions it attends to (wb200_dbg_last_attended)
 };
 
 struct whisper_context {
