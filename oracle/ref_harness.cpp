@@ -224,6 +224,19 @@ WREF_API int wref_last_attended(struct whisper_state * st, uint64_t * out, int c
     return b.n_tokens;
 }
 
+// ---- DTW token timestamps (src/whisper.cpp:8880-9167) ------------------------------------------------------------------------------
+// the alignment-head cross-attention weights the LAST whisper_exp_compute_token_level_timestamps_dtw call copied to the host
+// (state->aheads_cross_QKs_data: [n_heads][n_audio_ctx][n_tokens], src/whisper.cpp:9075-9079)
+WREF_API int64_t wref_dtw_qks(struct whisper_state * st, float * out, int64_t cap, int * n_tokens, int * n_audio_ctx, int * n_heads) {
+    if (!st->aheads_cross_QKs) return -1;
+    *n_tokens = (int) st->aheads_cross_QKs->ne[0]; *n_audio_ctx = (int) st->aheads_cross_QKs->ne[1]; *n_heads = (int) st->aheads_cross_QKs->ne[2];
+    const int64_t n = (int64_t) st->aheads_cross_QKs_data.size();
+    if (!out) return n;
+    if (n > cap) return -2;
+    memcpy(out, st->aheads_cross_QKs_data.data(), (size_t) n*sizeof(float));
+    return n;
+}
+
 // ---- voice-activity detection (src/whisper.cpp:4367-5515, 6669-6829, 7959-8130) -------------------------------------
 // probabilities -> segments with the reference's own whisper_vad_segments_from_probs (it reads only n_window and probs)
 WREF_API int wref_vad_segments(const float * probs, int n_probs, struct whisper_vad_params params, int64_t * t0, int64_t * t1, int cap) {
