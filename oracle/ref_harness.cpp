@@ -237,6 +237,14 @@ WREF_API int64_t wref_dtw_qks(struct whisper_state * st, float * out, int64_t ca
     return n;
 }
 
+// (layer, head) pairs in the order aheads_cross_QKs concatenates them (get_alignment_heads_by_layer, src/whisper.cpp:8856-8875)
+WREF_API int wref_dtw_heads(struct whisper_context_params cp, int n_text_layer, int n_head, int * out, int cap) {
+    int n = 0;
+    for (int il = 0; il < n_text_layer; ++il)
+        for (uint32_t h : get_alignment_heads_by_layer(cp, il, n_text_layer, n_head)) { if (n >= cap) return -1; out[2*n] = il; out[2*n + 1] = (int) h; ++n; }
+    return n;
+}
+
 // ---- voice-activity detection (src/whisper.cpp:4367-5515, 6669-6829, 7959-8130) -------------------------------------
 // probabilities -> segments with the reference's own whisper_vad_segments_from_probs (it reads only n_window and probs)
 WREF_API int wref_vad_segments(const float * probs, int n_probs, struct whisper_vad_params params, int64_t * t0, int64_t * t1, int cap) {

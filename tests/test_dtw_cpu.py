@@ -69,3 +69,53 @@ def test_dtw_host_math_matches_reference(lib, ref, tmp_path, preset):
     assert npath > 0
     assert list(got) == want, [(a, b) for a, b in zip(got, want) if a != b][:8]
     R.whisper_free(ctx)
+
+
+def test_dtw_qk_kernel_phases_match_numpy(lib):
+    """the phases of k_dtw_qk walked on the host (wb200_dbg_dtw_qk): softmax over the audio positions of f16(q) . K^T * 64^-1/4, for alignment
+    heads spread over several layers, written [head][audio][token] like the reference's host copy"""
+    rng = np.random.default_rng(3)
+    d, Tp, n_ctx, n_tok, n_layers = 384, 1536, 1500, 7, 3
+    heads = [(0, 1, 4), (0, 1, 0), (1, 2, 5)]                       # (captured-layer slot, text layer, head)
+    q = (rng.standard_normal((2, n_tok, d)) * 3).astype(np.float32)
+    k = (rng.standard_normal((n_layers, Tp, d)) * 0.5).astype(np.float16)
+    out = np.empty((len(heads), n_ctx, n_tok), np.float32)
+    tri = np.asarray(heads, np.int32)
+    scale = np.float32(64.0) ** np.float32(-0.25)
+    lib.wb200_dbg_dtw_qk.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp]
+    assert lib.wb200_dbg_dtw_qk(q.ctypes.data, k.ctypes.data, Tp, d, tri.ctypes.data, len(heads), n_tok, n_ctx, C.c_float(float(scale)), out.ctypes.data) == 0
+    for e, (ls, ly, hd) in enumerate(heads):
+        qh = q[ls, :, 64 * hd:64 * hd + 64].astype(np.float16).astype(np.float64)
+        kh = k[ly, :n_ctx, 64 * hd:64 * hd + 64].astype(np.float64)
+        s = (qh @ kh.T) * float(scale)
+        p = np.exp(s - s.max(axis=1, keepdims=True)); p /= p.sum(axis=1, keepdims=True)
+        assert np.abs(out[e].T - p).max() < 2e-6 * max(1.0, p.max() * 1e3), e
+        assert np.allclose(out[e].sum(axis=0), 1.0, atol=1e-5)
+
+
+def test_alignment_head_tables_and_order_match_reference(lib, ref):
+    """every preset of whisper_alignment_heads_preset resolves to the same (layer, head) list, in the same order, as the reference's tables"""
+    if not hasattr(ref, "wref_dtw_heads"):
+        pytest.skip("oracle/_ref predates wref_dtw_heads")
+    from wbtest import ContextParams
+    R = bind_whisper_api(ref)
+    sig = [ContextParams, C.c_int, C.c_int, vp, C.c_int]
+    ref.wref_dtw_heads.argtypes = sig; lib.wb200_dbg_dtw_heads.argtypes = sig
+    shapes = {3: (4, 6), 4: (4, 6), 5: (6, 8), 6: (6, 8), 7: (12, 12), 8: (12, 12), 9: (24, 16), 10: (24, 16), 11: (32, 20), 12: (32, 20), 13: (32, 20), 14: (4, 20)}
+    n_checked = 0
+    for preset, (n_layer, n_head) in shapes.items():
+        cp = R.whisper_context_default_params(); cp.dtw_token_timestamps = True; cp.dtw_aheads_preset = preset
+        a = (C.c_int * 256)(); b = (C.c_int * 256)()
+        na = lib.wb200_dbg_dtw_heads(cp, n_layer, n_head, a, 128); nb = ref.wref_dtw_heads(cp, n_layer, n_head, b, 128)
+        assert na == nb > 0 and list(a[: 2 * na]) == list(b[: 2 * nb]), preset
+        n_checked += na
+    assert n_checked == 8 + 6 + 5 + 8 + 19 + 10 + 18 + 6 + 9 + 23 + 10 + 6
+    cp = R.whisper_context_default_params(); cp.dtw_aheads_preset = 1; cp.dtw_n_top = 3
+    a = (C.c_int * 256)(); b = (C.c_int * 256)()
+    assert lib.wb200_dbg_dtw_heads(cp, 6, 8, a, 128) == ref.wref_dtw_heads(cp, 6, 8, b, 128) == 24 and list(a[:48]) == list(b[:48])
+    cp.dtw_n_top = 7
+    assert lib.wb200_dbg_dtw_heads(cp, 6, 8, a, 128) == -2                          # more layers than the model has
+    cp.dtw_aheads_preset = 0
+    assert lib.wb200_dbg_dtw_heads(cp, 6, 8, a, 128) == -2                          # DTW without a selection
+    cp.dtw_aheads_preset = 5                                                        # base.en heads on a 4-layer model
+    assert lib.wb200_dbg_dtw_heads(cp, 4, 6, a, 128) == -2

@@ -8,6 +8,7 @@
 #include <regex>
 #include <thread>
 #include "wb_state.h"
+#include "wb_dtw.h"
 #include <linux/futex.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -367,6 +368,9 @@ WB_EXPORT struct whisper_context * whisper_init_with_params_no_state(struct whis
                 ctx = new whisper_context();
                 ctx->params = params;
                 ctx->t_start_us = time_us();
+                // DTW token timestamps need the cross-attention queries layer by layer: such a context keeps the decoder weights planar and
+                // decodes with the kernel-per-op chain (the persistent kernel never materialises them)
+                ctx->model.force_planar = params.dtw_token_timestamps;
                 ok = model_load(loader, ctx->model, ctx->vocab, params.gpu_device);
                 ctx->t_load_us = ctx->model.t_load_us;
             }
@@ -417,6 +421,13 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
         st->kv_self_n_dec = 1;
         st->decoders[0].rng = std::mt19937(0);
         return st;
+    }
+    if (ctx->params.dtw_token_timestamps && ctx->dtw_heads.empty()) {     // aheads_masks_init, src/whisper.cpp:3442-3450: a bad selection fails the state
+        if (!dtw_resolve_heads(ctx->params, ctx->model.hp.n_text_layer, ctx->model.hp.n_text_head, ctx->dtw_heads)) {
+            logf(LOG_ERROR, "%s: aheads_masks_init() failed for alignment heads masks: %s\n", __func__, last_error());
+            return nullptr;
+        }
+        logf(LOG_INFO, "%s: alignment heads masks: %d heads\n", __func__, (int) ctx->dtw_heads.size());
     }
     try {
         st = new whisper_state();
@@ -700,6 +711,17 @@ WB_EXPORT int wb200_dbg_last_attended(struct whisper_state * st, uint64_t * out,
     if (!st || !st->scripted || (int) st->dbg_att.size() > cap) return -1;
     for (size_t i = 0; i < st->dbg_att.size(); ++i) out[i] = st->dbg_att[i];
     return (int) st->dbg_att.size();
+}
+
+// test hook: alignment-head weights of the last DTW pass of this state [heads][n_audio_ctx][tokens]; shape = {tokens, n_audio_ctx, heads}
+WB_EXPORT int64_t wb200_dbg_last_dtw_qks(struct whisper_state * st, float * out, int64_t cap, int * shape) {
+    if (!st) return -1;
+    if (shape) { shape[0] = st->dtw_last_shape[0]; shape[1] = st->dtw_last_shape[1]; shape[2] = st->dtw_last_shape[2]; }
+    const int64_t n = (int64_t) st->dtw_qk_last.size();
+    if (!out) return n;
+    if (n > cap) return -2;
+    memcpy(out, st->dtw_qk_last.data(), (size_t) n * sizeof(float));
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------------- engine extensions

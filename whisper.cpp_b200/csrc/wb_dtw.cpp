@@ -178,3 +178,11 @@ extern "C" WB_EXPORT int wb200_dbg_dtw(const float * qk, int n_tokens, int n_aud
     for (const Segment & s : segs) for (const whisper_token_data & t : s.tokens) t_dtw_out[k++] = t.t_dtw;
     return (int) ti.size();
 }
+
+extern "C" WB_EXPORT int wb200_dbg_dtw_heads(struct whisper_context_params cp, int n_text_layer, int n_head, int * out, int cap) {
+    std::vector<std::pair<int, int>> heads;
+    if (!wb::dtw_resolve_heads(cp, n_text_layer, n_head, heads)) return -2;
+    if ((int) heads.size() > cap) return -1;
+    for (size_t i = 0; i < heads.size(); ++i) { out[2 * i] = heads[i].first; out[2 * i + 1] = heads[i].second; }
+    return (int) heads.size();
+}

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstring>
 #include "wb_engine.h"
+#include "wb_dtw_kernel.cuh"
 #include "wb_kernels.cuh"
 
 namespace wb {
@@ -399,6 +400,8 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         { GemvArgs a; a.W = L.o; a.x = dattn.p; a.n_tok = n; a.bias = L.o_bias; a.res = dx.p; a.out = dx.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }    // 2647-2659
         { GemvArgs a; a.W = L.cq; a.x = dx.p; a.n_tok = n; a.ln_w = L.lnc.w; a.ln_b = L.lnc.b; a.eps = hp.eps;        // 2661-2681
           a.bias = L.cq_bias; a.out = dq2.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }
+        if (dtw_cap.active && dtw_cap.layer_slot[l] >= 0)            // DTW pass: keep this layer's cross-attention queries of the rows of this pass
+            WB_CUDA_OK(cudaMemcpyAsync(dtw_q.p + ((size_t) dtw_cap.layer_slot[l] * dtw_cap.n_total + dtw_cap.row0) * d, dq2.p, (size_t) n * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
         attn_cross_decode(dq2.p, d, kv_cross.p + (size_t) l * Tp * d, kv_cross.p + (size_t) (Lt + l) * Tp * d, d_slot,
                           (int64_t) 2 * Lt * Tp * d, n_keys, n, H, d, kq_scale, xpart.p, xcnt.p, dattn.p, d, st);       // 2688-2705
         { GemvArgs a; a.W = L.co; a.x = dattn.p; a.n_tok = n; a.bias = L.co_bias; a.res = dx.p; a.out = dx.p; { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); } }  // 2754-2766
@@ -452,7 +455,8 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         // (all per-step values live in `dints`, so kernel arguments never change between steps).
         uint64_t key = (uint64_t) (n | (any_logits ? 128 : 0) | (samp ? 256 : 0)) | ((uint64_t) n_keys << 10);
         if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
-        StepGraph * sg = (use_graphs && !use_mk && !prof_enabled()) ? &graphs[key] : nullptr;
+        StepGraph * sg = (use_graphs && !use_mk && !prof_enabled() && !dtw_cap.active) ? &graphs[key] : nullptr;
+        dtw_cap.row0 = r0;
         WB_CUDA_OK(cudaEventRecord(ev[5], st));
         if (sg && sg->exec) {
             WB_CUDA_OK(cudaGraphLaunch(sg->exec, st));
@@ -489,4 +493,45 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
     return true;
 }
 
+} // namespace wb
+
+namespace wb {
+// ---------------------------------------------------------------------------------------------------- DTW capture
+bool Engine::dtw_begin(const std::vector<std::pair<int, int>> & heads, int n_tokens) {
+    const HParams & hp = m->hp;
+    if (use_mk) { set_error("dtw: this context decodes with the persistent kernel; DTW needs a context created with dtw_token_timestamps"); return false; }
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    dtw_cap.layer_slot.assign((size_t) hp.n_text_layer, -1);
+    dtw_cap.n_sel = 0;
+    for (const auto & lh : heads) if (dtw_cap.layer_slot[(size_t) lh.first] < 0) dtw_cap.layer_slot[(size_t) lh.first] = dtw_cap.n_sel++;
+    dtw_cap.n_total = n_tokens; dtw_cap.row0 = 0;
+    const size_t need = (size_t) dtw_cap.n_sel * n_tokens * hp.n_text_state;
+    if (need > dtw_q.n && !dtw_q.alloc(need)) return false;
+    dtw_cap.active = true;
+    return true;
+}
+bool Engine::dtw_finish(const std::vector<std::pair<int, int>> & heads, int slot, int n_audio_ctx, std::vector<float> & qk) {
+    const HParams & hp = m->hp;
+    dtw_cap.active = false;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    const int nh = (int) heads.size(), n = dtw_cap.n_total, d = hp.n_text_state, Lt = hp.n_text_layer;
+    std::vector<int> idx((size_t) 3 * nh);
+    for (int e = 0; e < nh; ++e) { idx[(size_t) e] = dtw_cap.layer_slot[(size_t) heads[(size_t) e].first]; idx[(size_t) nh + e] = heads[(size_t) e].first; idx[(size_t) 2 * nh + e] = heads[(size_t) e].second; }
+    if ((size_t) 3 * nh > dtw_idx.n && !dtw_idx.alloc((size_t) 3 * nh)) return false;
+    const size_t n_out = (size_t) nh * n_audio_ctx * n;
+    if (n_out > dtw_out.n && !dtw_out.alloc(n_out)) return false;
+    WB_CUDA_OK(cudaMemcpyAsync(dtw_idx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    DtwQkArgs a;
+    a.q = dtw_q.p;
+    a.k_cross = kv_cross.p + (size_t) slot * 2 * Lt * Tp_max * d;        // K part of this slot: [Lt][Tp][d]
+    a.layer_stride = (int64_t) Tp_max * d;
+    a.head_layer_slot = dtw_idx.p; a.head_layer = dtw_idx.p + nh; a.head_index = dtw_idx.p + 2 * nh;
+    a.n_heads = nh; a.n_tokens = n; a.n_audio_ctx = n_audio_ctx; a.d = d; a.scale = powf(64.0f, -0.25f); a.out = dtw_out.p;
+    if (!dtw_qk_launch(a, st)) return false;
+    qk.resize(n_out);
+    WB_CUDA_OK(cudaMemcpyAsync(qk.data(), dtw_out.p, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    count_d2h(n_out * sizeof(float));
+    return true;
+}
 } // namespace wb

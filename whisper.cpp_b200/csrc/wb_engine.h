@@ -8,6 +8,7 @@
 #pragma once
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 #include "wb_model.h"
 #include "wb_gemm.cuh"
@@ -64,6 +65,11 @@ struct Engine {
     DevBuf<uint8_t> act_scratch;      // quantised activations of the current GEMV (k_act_quant -> k_gemv_mma)
     bool gemv_v2 = true;             // WB200_GEMV_V1=1 selects the dp4a kernel
     // persistent decode kernel (wb_decode_mk.cu); WB200_MEGAKERNEL=0 selects the kernel-per-op chain
+    // DTW token timestamps: while `dtw_cap.active` every chain pass copies the cross-attention queries of the selected layers aside
+    struct DtwCapture { bool active = false; std::vector<int> layer_slot; int n_sel = 0, n_total = 0, row0 = 0; } dtw_cap;
+    DevBuf<float> dtw_q, dtw_out; DevBuf<int> dtw_idx;
+    bool dtw_begin(const std::vector<std::pair<int, int>> & heads, int n_tokens);
+    bool dtw_finish(const std::vector<std::pair<int, int>> & heads, int slot, int n_audio_ctx, std::vector<float> & qk);
     bool use_mk = false;
     int  max_rows = 8;               // rows per decode pass: 64 with the persistent kernel, 8 with the chain
     int  n_sm = 0, mk_prefetch = 1;

@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include "wb_state.h"
+#include "wb_dtw.h"
 
 using namespace wb;
 
@@ -409,6 +410,37 @@ template <typename F> void run_parallel(int n_threads, F && fn) {
     for (auto & t : th) t.join();
 }
 
+
+// One extra decoder pass over [sot, (lang), no_timestamps, text tokens of the window's segments, eot] with the cross-attention queries of the
+// alignment-head layers captured, their softmax weights over the audio computed on the device, then the host DTW (wb_dtw.cpp).
+bool dtw_window(whisper_context & ctx, whisper_state & st, const whisper_full_params & params, int i_segment, int n_segments, int seek, int n_frames) {
+    const Vocab & vocab = ctx.vocab;
+    const int n_audio_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
+    if (st.group || !st.eng) { set_error("dtw: not available for the members of a lock-step batch"); return false; }
+    if (n_frames > 2 * n_audio_ctx) { set_error("dtw: %d frames exceed the audio context", n_frames); return false; }
+    std::vector<int> tokens = { vocab.token_sot };
+    if (vocab.is_multilingual()) { const int lang_id = whisper_lang_id(params.language); st.lang_id = lang_id; tokens.push_back(vocab.token_sot + 1 + lang_id); }
+    const int sot_len = (int) tokens.size();
+    tokens.push_back(vocab.token_not);
+    for (int i = i_segment; i < i_segment + n_segments; ++i) for (const auto & t : st.result_all[(size_t) i].tokens) if (t.id < vocab.token_eot) tokens.push_back(t.id);
+    tokens.push_back(vocab.token_eot);
+    const int n = (int) tokens.size();
+    if (n > ctx.model.hp.n_text_ctx) { set_error("dtw: %d tokens exceed the text context", n); return false; }
+    std::vector<int> pos((size_t) n), seq((size_t) n, 0); std::vector<int8_t> want((size_t) n, 0);
+    for (int i = 0; i < n; ++i) pos[(size_t) i] = i;
+    want[(size_t) n - 1] = 1;
+    st.kv.clear();
+    st.kv.seq_rm(0, 0, -1);
+    if (!st.eng->dtw_begin(ctx.dtw_heads, n)) return false;
+    const bool ok = decode_batch(ctx, st, tokens.data(), pos.data(), seq.data(), want.data(), n);
+    if (!ok) { st.eng->dtw_cap.active = false; return false; }
+    if (!st.eng->dtw_finish(ctx.dtw_heads, st.slot, n_audio_ctx, st.dtw_qk_last)) return false;
+    st.dtw_last_shape[0] = n; st.dtw_last_shape[1] = n_audio_ctx; st.dtw_last_shape[2] = (int) ctx.dtw_heads.size();
+    std::vector<int32_t> ti, tj;
+    dtw_path(st.dtw_qk_last.data(), n, n_audio_ctx, (int) ctx.dtw_heads.size(), n_frames / 2, sot_len, 7, ti, tj);
+    dtw_assign(ti, tj, seek, vocab.token_eot, st.result_all, i_segment, n_segments);
+    return true;
+}
 } // namespace
 
 extern "C" {
@@ -803,6 +835,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
         }
 
         { // emit segments (whisper.cpp:7612-7784)
+            const size_t n_segments_before = result_all.size();
             const Decoder & best = state->decoders[best_decoder_id];
             int seek_delta = best.seek_delta;
             const int result_len = best.sequence.result_len;
@@ -832,7 +865,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         token_level_timestamps(*ctx, *state, (int) result_all.size() - 1, params.thold_pt, params.thold_ptsum);
                         if (params.max_len > 0) n_new = wrap_segment(*ctx, *state, params.max_len, params.split_on_word);
                     }
-                    if (params.new_segment_callback) params.new_segment_callback(ctx, state, n_new, params.new_segment_callback_user_data);
+                    if (params.new_segment_callback && !ctx->params.dtw_token_timestamps) params.new_segment_callback(ctx, state, n_new, params.new_segment_callback_user_data);
                 };
                 for (int i = 0; i < (int) cur.size(); ++i) {
                     if (params.print_special || cur[i].id < vocab.token_eot) text += whisper_token_to_str(ctx, cur[i].id);
@@ -852,6 +885,15 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                     }
                 }
                 if (!text.empty()) push_segment(t0, seek + seek_delta, i0, (int) cur.size() - 1);
+            }
+
+            // DTW token timestamps for the segments of this window (whisper.cpp:7750-7765, 9009-9160)
+            if (ctx->params.dtw_token_timestamps && result_all.size() > n_segments_before) {
+                const int n_segments = (int) (result_all.size() - n_segments_before);
+                const int n_frames = std::min(std::min(WB_CHUNK_SIZE * 100, seek_delta), seek_end - seek);
+                if (!dtw_window(*ctx, *state, params, (int) n_segments_before, n_segments, seek, n_frames)) { logf(LOG_ERROR, "%s: DTW pass failed: %s\n", __func__, last_error()); return -8; }
+                if (params.new_segment_callback)                      // same (peculiar) range as the reference
+                    for (int seg = (int) result_all.size() - n_segments; seg < n_segments; seg++) params.new_segment_callback(ctx, state, seg, params.new_segment_callback_user_data);
             }
 
             const bool max_tokens_ts_ending = params.max_tokens > 0 && !params.single_segment && cur.size() > (size_t) params.max_tokens;
@@ -978,6 +1020,7 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
 WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
                                   const int * n_samples, int n_chunks, struct whisper_state ** states_out, int flags) {
     if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
+    if (ctx->params.dtw_token_timestamps) { set_error("wb200_full_batch: DTW token timestamps are not available in the lock-step driver"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
     if (params.vad) { set_error("wb200_full_batch: params.vad is not applied to pre-cut chunks; run whisper_vad_* first"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
     int S = ctx->model.dec_tm ? 64 : 8;          // concurrent sequences: one row each in the decode pass (64 rows per launch of the persistent kernel)
     if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <random>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/whisper_b200.h"
 #include "wb_engine.h"
@@ -93,6 +94,8 @@ struct whisper_state {
     // TEST HOOK (wb200_dbg_scripted_context, tests/test_full_scripted_cpu.py): a state without an engine.  Mel / encode are no-ops and a
     // decode leaves all-zero logits, so the transcript is whatever the caller's logits_filter_callback scripts.  It computes nothing and
     // cannot be created through any whisper.h entry point.
+    std::vector<float> dtw_qk_last;            // alignment-head weights of the last DTW pass [heads][n_audio_ctx][tokens] (wb200_dbg_last_dtw_qks)
+    int dtw_last_shape[3] = {0, 0, 0};
     bool scripted = false;
     std::vector<int> dbg_tok, dbg_pos, dbg_seq; std::vector<int8_t> dbg_want;      // scripted states only: the last decode request (wb200_dbg_last_batch)
     std::vector<uint64_t> dbg_att;             // ... and per row a hash of the sorted positions it attends to (wb200_dbg_last_attended)
@@ -106,6 +109,7 @@ struct whisper_context {
     whisper_state * state = nullptr;
     std::string path_model;
     bool scripted = false;                     // TEST HOOK: see whisper_state::scripted
+    std::vector<std::pair<int, int>> dtw_heads; // (text layer, head) of the alignment heads when params.dtw_token_timestamps survived init
     std::unique_ptr<wb::Group> batch_group;    // cached by wb200_full_batch
     std::mutex batch_mu;
     ~whisper_context();
