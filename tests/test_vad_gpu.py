@@ -20,6 +20,31 @@ def _probs(L, vctx, pcm, pieces=None):
     return ref_probs(L, vctx, pcm, pieces)            # same whisper_vad_* calls on either library
 
 
+def test_vad_device_real_silero_weights_golden(lib):
+    """device kernels on the Silero weights of the reference's tests/test-vad.cpp: the committed reference probabilities
+    (tests/golden/vad_r01.npz) and the reference's own KAT -- 344 probabilities, 4 segments with the default parameters"""
+    if not os.path.exists(SILERO):
+        pytest.skip("oracle/_ref/data lacks the silero fixture")
+    bind_vad(lib)
+    g = np.load(GOLDEN)
+    pcm = np.ascontiguousarray(read_wav_f32(os.path.join(DATA_DIR, "jfk.wav")), np.float32)
+    lv = lib.whisper_vad_init_from_file_with_params(SILERO.encode(), lib.whisper_vad_default_context_params())
+    assert lv, lib.wb200_last_error()
+    got = _probs(lib, lv, pcm)
+    assert len(got) == 344
+    d = np.abs(got - g["probs"])
+    print("silero v6.2.0 on jfk.wav (device): max|d|=%.2e median %.2e" % (d.max(), np.median(d)))
+    assert d.max() < 1.5e-3 and np.median(d) < 5e-5
+    lib.whisper_vad_segments_from_probs.restype = vp
+    lib.whisper_vad_segments_from_probs.argtypes = [vp, type(lib.whisper_vad_default_params())]
+    segs = lib.whisper_vad_segments_from_probs(lv, lib.whisper_vad_default_params())
+    n = lib.whisper_vad_segments_n_segments(segs)
+    assert n == 4
+    assert [int(lib.whisper_vad_segments_get_segment_t0(segs, i)) for i in range(n)] == g["seg_t0"].tolist()
+    assert [int(lib.whisper_vad_segments_get_segment_t1(segs, i)) for i in range(n)] == g["seg_t1"].tolist()
+    lib.whisper_vad_free_segments(segs); lib.whisper_vad_free(lv)
+
+
 def test_vad_device_probs_match_reference(lib, ref, tmp_path):
     bind_vad(lib); bind_vad(ref)
     lib.wb200_dbg_vad_probs.argtypes = [C.c_char_p, vp, C.c_int, C.c_int, vp, C.c_int]
@@ -45,31 +70,6 @@ def test_vad_device_probs_match_reference(lib, ref, tmp_path):
         parts = _probs(lib, lv, pcm, pieces=512 * 77)
         assert np.array_equal(one, parts)
         ref.whisper_vad_free(rv); lib.whisper_vad_free(lv)
-
-
-def test_vad_device_real_silero_weights_golden(lib):
-    """device kernels on the Silero weights of the reference's tests/test-vad.cpp: the committed reference probabilities
-    (tests/golden/vad_r01.npz) and the reference's own KAT -- 344 probabilities, 4 segments with the default parameters"""
-    if not os.path.exists(SILERO):
-        pytest.skip("oracle/_ref/data lacks the silero fixture")
-    bind_vad(lib)
-    g = np.load(GOLDEN)
-    pcm = np.ascontiguousarray(read_wav_f32(os.path.join(DATA_DIR, "jfk.wav")), np.float32)
-    lv = lib.whisper_vad_init_from_file_with_params(SILERO.encode(), lib.whisper_vad_default_context_params())
-    assert lv, lib.wb200_last_error()
-    got = _probs(lib, lv, pcm)
-    assert len(got) == 344
-    d = np.abs(got - g["probs"])
-    print("silero v6.2.0 on jfk.wav (device): max|d|=%.2e median %.2e" % (d.max(), np.median(d)))
-    assert d.max() < 1.5e-3 and np.median(d) < 5e-5
-    lib.whisper_vad_segments_from_probs.restype = vp
-    lib.whisper_vad_segments_from_probs.argtypes = [vp, type(lib.whisper_vad_default_params())]
-    segs = lib.whisper_vad_segments_from_probs(lv, lib.whisper_vad_default_params())
-    n = lib.whisper_vad_segments_n_segments(segs)
-    assert n == 4
-    assert [int(lib.whisper_vad_segments_get_segment_t0(segs, i)) for i in range(n)] == g["seg_t0"].tolist()
-    assert [int(lib.whisper_vad_segments_get_segment_t1(segs, i)) for i in range(n)] == g["seg_t1"].tolist()
-    lib.whisper_vad_free_segments(segs); lib.whisper_vad_free(lv)
 
 
 def test_whisper_full_with_vad_cuts_the_same_audio(lib, ref, tmp_path):
