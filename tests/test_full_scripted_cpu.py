@@ -35,7 +35,7 @@ class Script:
         self.L, self.seed, self.style, self.timestamps, self.use_segments = L, seed, style, timestamps, use_segments
         self.V = L.whisper_n_vocab(ctx)
         self.beg, self.eot = L.whisper_token_beg(ctx), L.whisper_token_eot(ctx)
-        self.calls = 0
+        self._calls = []                                  # list.append is atomic: callbacks can arrive from several member threads
         self.batches = []                                  # crc of (tokens, positions, sequence ids, logits flags) fed to the decoder before each filtered step
         self.tap = getattr(L, "wref_last_batch", None) or getattr(L, "wb200_dbg_last_batch", None)
         self.tap_att = getattr(L, "wref_last_attended", None) or getattr(L, "wb200_dbg_last_attended", None)
@@ -48,14 +48,19 @@ class Script:
         L.whisper_full_n_segments_from_state.argtypes = [vp]
         self.cb = LOGITS_CB(self._cb)
 
+    @property
+    def calls(self):
+        return len(self._calls)
+
     def _cb(self, ctx, st, toks, n, logits, ud):
-        self.calls += 1
+        self._calls.append(None)
         ids = np.fromiter((toks[i].id for i in range(n)), np.int32, n)
         if self.tap is not None:
-            tb = self._tb
-            nb = self.tap(st, tb[0].ctypes.data, tb[1].ctypes.data, tb[2].ctypes.data, tb[3].ctypes.data, 2048)
-            na = self.tap_att(st, self._ta.ctypes.data, 2048) if self.tap_att is not None else 0
-            self.batches.append((nb, zlib.crc32(b"".join(a[:max(nb, 0)].tobytes() for a in tb)), na, zlib.crc32(self._ta[:max(na, 0)].tobytes()) if na > 0 else 0))
+            tb = [np.empty(512, np.int32) for _ in range(3)] + [np.empty(512, np.int8)]
+            nb = self.tap(st, tb[0].ctypes.data, tb[1].ctypes.data, tb[2].ctypes.data, tb[3].ctypes.data, 512)
+            ta = np.empty(512, np.uint64)
+            na = self.tap_att(st, ta.ctypes.data, 512) if self.tap_att is not None else 0
+            self.batches.append((nb, zlib.crc32(b"".join(a[:max(nb, 0)].tobytes() for a in tb)), na, zlib.crc32(ta[:max(na, 0)].tobytes()) if na > 0 else 0))
         nseg = self.L.whisper_full_n_segments_from_state(st) if self.use_segments else 0
         rng = np.random.default_rng((zlib.crc32(ids.tobytes()) ^ self.seed ^ (nseg * 7919)) & 0xFFFFFFFF)
         V, beg, eot = self.V, self.beg, self.eot
