@@ -11,14 +11,19 @@ import pytest
 
 from wbtest import DATA_DIR, read_wav_f32, Q5_0, TokenData
 from e2e_util import Side, synth
+from test_full_scripted_cpu import Script
 
 pytestmark = pytest.mark.gpu
 vp = C.c_void_p
 
 
-def test_token_timestamps_and_max_len(lib, ref, tmp_path):
+@pytest.mark.parametrize("scripted", [False, True])
+def test_token_timestamps_and_max_len(lib, ref, tmp_path, scripted):
+    """scripted = False: 2-layer model (the reference's distil rule forces no_timestamps), tokens picked by the on-device sampler;
+    scripted = True: 3-text-layer model with the transcript scripted through logits_filter_callback (timestamps, several segments, host sampler)"""
     path = str(tmp_path / "m.bin")
-    synth.write_model(path, "test-2l.en", Q5_0, seed=11, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
+    cfg = (51864, 1500, 384, 6, 1, 448, 384, 6, 3, 80) if scripted else "test-2l.en"
+    synth.write_model(path, cfg, Q5_0, seed=11, vocab_from=os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin"))
     pcm = read_wav_f32(os.path.join(DATA_DIR, "jfk.wav"))
     A = Side(lib, path, False)
     try:
@@ -28,10 +33,15 @@ def test_token_timestamps_and_max_len(lib, ref, tmp_path):
         L.whisper_full_get_segment_text.restype = C.c_char_p
         eot = L.whisper_token_eot(A.ctx)
 
+        keep = []
+
         def run(max_len):
             fp = L.whisper_full_default_params(0)
             fp.print_progress = False; fp.temperature_inc = 0.0; fp.greedy.best_of = 1
             fp.token_timestamps = True; fp.max_len = max_len; fp.split_on_word = False
+            if scripted:
+                script = Script(L, A.ctx, 31, "peaked", use_segments=False); keep.append(script)    # history-only script: the wrapped run must see the same logits
+                fp.logits_filter_callback = C.cast(script.cb, vp); fp.no_speech_thold = 2.0
             assert L.whisper_full(A.ctx, fp, pcm.ctypes.data_as(C.c_void_p), len(pcm)) == 0, L.wb200_last_error()
             segs = []
             for i in range(L.whisper_full_n_segments(A.ctx)):
@@ -42,6 +52,8 @@ def test_token_timestamps_and_max_len(lib, ref, tmp_path):
 
         plain = run(0)
         assert len(plain) >= 1 and sum(len(s[3]) for s in plain) > 0
+        if scripted:
+            assert len(plain) >= 3 and sum(len(s[3]) for s in plain) > 30
         # replay through the reference
         B = Side(ref, path, True)
         try:
