@@ -1,7 +1,7 @@
 #!/bin/bash
 # Host logic under AddressSanitizer / UBSan (no GPU needed): builds an instrumented copy of the library OUT OF TREE, swaps it in for the
 # CPU tests that drive this library's host code (grammar, VAD, DTW, dequantisers, sampler, KV, vocabulary, timestamps, the scripted
-# whisper_full flows incl. the 3-thread lock-step driver) and restores the original.   usage: scripts/sanitize_host.sh address|undefined
+# whisper_full flows incl. the 3-thread lock-step driver) and restores the original.   usage: scripts/sanitize_host.sh address|undefined|thread
 set -e
 SAN=${1:-address}
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -14,8 +14,9 @@ make -C $W -j8 > $W/build.log 2>&1
 LIB=$ROOT/whisper.cpp_b200/libwhisper_b200.so
 cp $LIB $W/orig.so; trap 'cp $W/orig.so $LIB' EXIT
 cp $W/libwhisper_b200.so $LIB
-RT=$(gcc -print-file-name=lib$([ $SAN = address ] && echo asan || echo ubsan).so)
+case $SAN in address) RT=asan;; undefined) RT=ubsan;; thread) RT=tsan;; esac
+RT=$(gcc -print-file-name=lib$RT.so)
 cd $ROOT
-LD_PRELOAD=$RT ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:verify_asan_link_order=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=0 \
+LD_PRELOAD=$RT TSAN_OPTIONS=halt_on_error=0:report_signal_unsafe=0 ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:verify_asan_link_order=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=0 \
   python -m pytest tests/test_grammar_cpu.py tests/test_vad_cpu.py tests/test_dtw_cpu.py tests/test_dequant_cpu.py tests/test_sampler_cpu.py tests/test_kv_cpu.py \
-  tests/test_vocab_cpu.py tests/test_token_timestamps_cpu.py tests/test_full_scripted_cpu.py -x -q 2>&1 | grep -i "passed\|failed\|ERROR: AddressSanitizer\|runtime error" | sort | uniq -c
+  tests/test_vocab_cpu.py tests/test_token_timestamps_cpu.py tests/test_full_scripted_cpu.py -x -q 2>&1 | grep -i "passed\|failed\|ERROR: AddressSanitizer\|runtime error\|WARNING: ThreadSanitizer" | sort | uniq -c
