@@ -127,6 +127,8 @@ SCENARIOS = [
     ("parallel2",           "en", 64.0, "peaked", dict(n_processors=2), {"use_segments": False}),
     ("short_input",         "en", 0.05, "peaked", dict(), {}),
     ("encoder_begin_stop",  "en", 95.0, "peaked", dict(stop_at_window=3), {}),
+    ("err_too_many_decoders", "en", 5.0, "peaked", dict(best_of=9, temperature=0.4), {}),            # -4
+    ("err_audio_ctx",       "en", 5.0, "peaked", dict(audio_ctx=1600), {}),                        # -5
     ("suppress_regex_nst",  "en", 26.0, "medium", dict(suppress_regex=b"^ ?[a-mA-M]", suppress_nst=True, best_of=2, temperature_inc=0.5), {}),
     ("max_initial_ts_tdrz", "en", 12.0, "medium", dict(max_initial_ts=0.04, tdrz_enable=True, entropy_thold=3.5, n_max_text_ctx=0), {}),
     # params.vad on jfk.wav with the Silero weights of the reference's tests (product side: host walk of the VAD kernels' phases)
