@@ -341,6 +341,17 @@ def main():
             except Exception as e:  # noqa: BLE001
                 out["cpu_baseline"] = {"value": None, "unit": "x real time", "cores": ref_threads(), "kind": "reference",
                                        "sample": "1 x 30 s chunk (did not finish: %s)" % type(e).__name__}
+        if os.environ.get("WB200_BENCH_REF_TOOL") == "1" and world == 1:
+            # opt-in (not yet exercised on a GPU): the reference's OWN benchmark program, unmodified, linked against this library
+            # (oracle/_ref/whisper-bench-b200 = examples/bench/bench.cpp): encode / decode / batched / prompt ms per run as whisper_print_timings reports
+            try:
+                import re
+                exe = os.path.join(ROOT, "oracle", "_ref", "whisper-bench-b200")
+                r = subprocess.run([exe, "-m", model, "-t", "4"], capture_output=True, text=True, timeout=300)
+                out["whisper_bench_tool"] = {name: {"ms_per_run": float(per), "runs": int(runs)} for name, total, runs, per in
+                                             re.findall(r"(\w+) time =\s*([\d.]+) ms /\s*(\d+) runs \(\s*([\d.]+) ms per run\)", r.stderr + r.stdout)}
+            except Exception as e:  # noqa: BLE001
+                out["whisper_bench_tool"] = {"error": type(e).__name__}
         print(json.dumps(out), flush=True)
     eng.close()
     if world > 1:
