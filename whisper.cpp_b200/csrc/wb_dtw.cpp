@@ -82,7 +82,7 @@ void dtw_path(const float * qk, int n_tokens, int n_audio_ctx, int n_heads, int 
               std::vector<int32_t> & tok_idx, std::vector<int32_t> & time_idx) {
     tok_idx.clear(); time_idx.clear();
     const int N = n_tokens - sot_len - 1, M = n_audio_tokens;                        // rows: "not" + text tokens; columns: 20 ms steps
-    if (N <= 0 || M <= 0 || n_heads <= 0) return;
+    if (N <= 0 || M <= medfilt_width || n_heads <= 0) return;                          // (the reference asserts filter_width < n_audio_tokens; here: no stamps)
     // 1. per (head, time): normalise over the tokens (ggml_norm, eps 1e-9: double sum -> f32 mean, see centered_sumsq, scale 1/sqrt(var + eps))
     std::vector<float> w((size_t) n_heads * M * n_tokens);
     for (int h = 0; h < n_heads; ++h) for (int j = 0; j < M; ++j) {
