@@ -115,6 +115,26 @@ bool prepare_decode(whisper_state & st, const int * tokens, const int * pos, con
     }
     return true;
 }
+// test hook (engine-less states): per row a hash of the positions it attends to, i.e. of the index list the kernels would get
+void scripted_attended(whisper_state & st, const PreparedDecode & P, int n_tokens) {
+    st.dbg_att.resize((size_t) n_tokens);
+    std::vector<int> ps;
+    for (int j = 0; j < n_tokens; ++j) {
+        ps.clear();
+        for (int c = 0; c < P.nkv[j]; ++c) ps.push_back(st.kv.cells[(size_t) (P.idx[(size_t) j * P.ld + c] - st.cell_off)].pos);
+        std::sort(ps.begin(), ps.end());
+        uint64_t h = 1469598103934665603ull;
+        for (int v : ps) for (int k = 0; k < 4; ++k) { h ^= (uint64_t) ((v >> (8 * k)) & 0xff); h *= 1099511628211ull; }
+        st.dbg_att[(size_t) j] = h;
+    }
+}
+// row 0 of the state's logits buffer is refreshed only by a decode that asked logits for its first token (whisper.cpp:2957-2963);
+// with the on-device sampler only that row's no-speech probability exists on the host
+void note_row0(whisper_state & st, const int8_t * want) {
+    if (!want[0]) return;
+    st.row0_on_device = !st.samp_out.empty();
+    if (st.row0_on_device) st.row0_nosp_dev = st.samp_out[0].nosp_raw;
+}
 void account_decode(whisper_state & st, int n_tokens, int64_t dt) {                    // whisper.cpp:2974-2983
     if (n_tokens == 1)      { st.t_decode_us += dt; st.n_decode++; }
     else if (n_tokens < 16) { st.t_batchd_us += dt; st.n_batchd += n_tokens; }
@@ -125,7 +145,7 @@ void account_decode(whisper_state & st, int n_tokens, int64_t dt) {             
 bool encode_window(whisper_context & ctx, whisper_state & st, int mel_offset) {
     const int64_t t0 = time_us();
     const int n_ctx = st.exp_n_audio_ctx > 0 ? st.exp_n_audio_ctx : ctx.model.hp.n_audio_ctx;
-    if (st.scripted && !st.group) { st.n_encode++; return true; }          // test hook: no engine
+
     if (st.fe.n_mel != ctx.model.hp.n_mels) { set_error("encode: mel has %d bands, model expects %d", st.fe.n_mel, ctx.model.hp.n_mels); return false; }
     if (st.group) {
         Group::Req r; r.kind = 0; r.ctx = &ctx; r.st = &st; r.seek = mel_offset; r.n_ctx = n_ctx;
@@ -152,21 +172,13 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
         Group::Req r; r.kind = 1; r.ctx = &ctx; r.st = &st; r.tokens = tokens; r.pos = pos; r.seq = seq; r.want = want; r.n = n_tokens; r.samp = samp;
         if (!st.group->submit(r)) return false;
         account_decode(st, n_tokens, r.dt_us);
+        note_row0(st, want);
         return true;
     }
     PreparedDecode P;
     if (!prepare_decode(st, tokens, pos, seq, want, n_tokens, P)) return false;
     if (st.scripted) {                                                       // test hook: KV bookkeeping only, the caller's logits callback supplies the values
-        st.dbg_att.resize((size_t) n_tokens);
-        std::vector<int> ps;
-        for (int j = 0; j < n_tokens; ++j) {                                 // what each row attends to, as positions (the index lists the kernels get)
-            ps.clear();
-            for (int c = 0; c < P.nkv[j]; ++c) ps.push_back(st.kv.cells[(size_t) (P.idx[(size_t) j * P.ld + c] - st.cell_off)].pos);
-            std::sort(ps.begin(), ps.end());
-            uint64_t h = 1469598103934665603ull;
-            for (int v : ps) for (int k = 0; k < 4; ++k) { h ^= (uint64_t) ((v >> (8 * k)) & 0xff); h *= 1099511628211ull; }
-            st.dbg_att[(size_t) j] = h;
-        }
+        scripted_attended(st, P, n_tokens);
         st.samp_out.clear(); st.logits.assign((size_t) n_tokens * n_vocab, 0.0f);
         account_decode(st, n_tokens, time_us() - t0);
         return true;
@@ -183,6 +195,7 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
         if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), outs.data())) return false;
     }
     account_decode(st, n_tokens, time_us() - t0);
+    note_row0(st, want);
     return true;
 }
 
@@ -197,37 +210,147 @@ static void req_wake(Group::Req & r) {
     r.done.store(1, std::memory_order_release);
     syscall(SYS_futex, reinterpret_cast<int *>(&r.done), FUTEX_WAKE_PRIVATE, 1, nullptr, nullptr, 0);
 }
+// ---- pool management -----------------------------------------------------------------------------------------------------------
+static int pool_cells_for(const Model & m, int n_decoders) {                          // whisper.cpp:3402, 7167-7172
+    const int base = (m.hp.n_text_ctx + 255) / 256 * 256;
+    return base * (n_decoders > 1 ? n_decoders + 2 : 1);
+}
+
+// Reallocate the pool for `new_cap` slots of `new_cps` cells.  Waits until no batch is executing and keeps `mu` so that none can start;
+// states blocked in submit() keep their slot contents (Engine::resize copies them).
+bool Group::grow_locked(std::unique_lock<std::mutex> & lk, int new_cap, int new_cps) {
+    cv.wait(lk, [&] { return !running; });
+    if (!scripted) {
+        if (cap == 0) {
+            if (!eng.init(model, 1)) return false;                                   // one slot, GGML_PAD(n_text_ctx, 256) cells
+            cap = 1; cps = eng.cps;
+        }
+        if ((new_cap != cap || new_cps != cps) && !eng.resize(new_cap, new_cps)) return false;
+    }
+    cap = new_cap; cps = new_cps;
+    slot_used.resize((size_t) cap, 0);
+    return true;
+}
+
+bool Group::attach(whisper_state * st) {
+    std::unique_lock<std::mutex> lk(mu);
+    int slot = -1;
+    for (int i = 0; i < cap; ++i) if (!slot_used[(size_t) i]) { slot = i; break; }
+    if (slot < 0) {
+        const int base_cps = cps > 0 ? cps : pool_cells_for(*model, 1);
+        const int new_cap = cap == 0 ? 1 : cap * 2;
+        if (new_cap > 1024) { set_error("whisper_init_state: too many states on one context (%d)", cap); return false; }
+        slot = cap;
+        if (!grow_locked(lk, new_cap, base_cps)) return false;
+    }
+    slot_used[(size_t) slot] = 1;
+    ++n_registered;
+    st->group = this; st->eng = scripted ? nullptr : &eng; st->slot = slot; st->cell_off = slot * cps;
+    st->kv.reset((uint32_t) pool_cells_for(*model, 1));
+    st->kv_self_n_dec = 1;
+    return true;
+}
+
+std::unique_ptr<FrontEnd> Group::take_fe() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (fe_cache.empty()) return nullptr;
+    std::unique_ptr<FrontEnd> f = std::move(fe_cache.back());
+    fe_cache.pop_back();
+    return f;
+}
+
+void Group::detach(whisper_state * st) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (st->slot >= 0 && st->slot < cap) slot_used[(size_t) st->slot] = 0;
+    --n_registered;
+    if (st->fe_own && st->fe_own->st && fe_cache.size() < 256) fe_cache.push_back(std::move(st->fe_own));
+    st->group = nullptr; st->eng = nullptr;
+}
+
+bool Group::ensure_cells(whisper_state * st, int cells) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (cells > cps) {
+        // another state may hold cells beyond `cells` only if cps already covered them, so growing never truncates anybody
+        if (!grow_locked(lk, cap, cells)) return false;
+    }
+    st->cell_off = st->slot * cps;
+    st->kv.reset((uint32_t) cells);
+    return true;
+}
+
+// ---- rendezvous ------------------------------------------------------------------------------------------------------------------
+// Gathering: callers of whisper_full_with_state on different states start within microseconds of each other but not at the same
+// instant.  A complete batch that contains an encode request (the first request of a window) is held back for a moment while states
+// are still entering, so that the windows of near-simultaneous callers share one batched encoder pass instead of chasing each other
+// one step apart.  Costs a lone caller on a multi-state context at most kGatherUs once per 30-s window.
+static const int64_t kGatherUs = 300;
+int64_t Group::grace_left_us() const {
+    if (n_registered <= n_active) return 0;                  // nobody left who could still join
+    bool has_enc = false;
+    for (const Req * q : pending) has_enc |= (q->kind == 0);
+    if (!has_enc) return 0;
+    return kGatherUs - (time_us() - t_last_enter_us);
+}
+
+void Group::enter(whisper_state * st) {
+    std::lock_guard<std::mutex> lk(mu);
+    ++n_active; t_last_enter_us = time_us();
+    st->in_group_call = true;
+    st->cell_off = st->slot * cps;
+}
+
 bool Group::submit(Req & r) {
     std::vector<Req *> batch;
     {
-        std::lock_guard<std::mutex> lk(mu);
+        std::unique_lock<std::mutex> lk(mu);
+        r.st->cell_off = r.st->slot * cps;                    // the pool may have been re-laid out since the last request
         pending.push_back(&r);
-        if ((int) pending.size() >= n_active) batch.swap(pending);
+        for (;;) {
+            if (r.taken || (int) pending.size() < n_active) { lk.unlock(); req_wait(r); return r.ok; }   // somebody else runs (or ran) it
+            const int64_t w = grace_left_us();
+            if (w <= 0) break;
+            lk.unlock();
+            std::this_thread::sleep_for(std::chrono::microseconds(w));
+            lk.lock();
+        }
+        batch.swap(pending);
+        for (Req * q : batch) q->taken = true;
+        running = true;
     }
-    if (!batch.empty()) {
-        run(batch);
-        for (Req * q : batch) if (q != &r) req_wake(*q);         // q may be gone as soon as it is woken: nothing of it is touched afterwards
-    } else {
-        req_wait(r);
-    }
+    run(batch);
+    { std::lock_guard<std::mutex> lk(mu); running = false; }
+    cv.notify_all();
+    for (Req * q : batch) if (q != &r) req_wake(*q);             // q may be gone as soon as it is woken: nothing of it is touched afterwards
     return r.ok;
 }
-void Group::leave() {
+
+void Group::leave(whisper_state * st) {
     std::vector<Req *> batch;
     {
         std::lock_guard<std::mutex> lk(mu);
+        st->in_group_call = false;
         n_active--;
-        if (!pending.empty() && (int) pending.size() >= n_active) batch.swap(pending);
+        if (!pending.empty() && (int) pending.size() >= n_active && !pending[0]->taken) {
+            batch.swap(pending);
+            for (Req * q : batch) q->taken = true;
+            running = true;
+        }
     }
     if (!batch.empty()) {
         run(batch);
+        { std::lock_guard<std::mutex> lk(mu); running = false; }
+        cv.notify_all();
         for (Req * q : batch) req_wake(*q);
     }
 }
 void Group::run(std::vector<Req *> & batch) {
+    for (Req * q : batch) q->st->cell_off = q->st->slot * cps;      // the pool may have been re-laid out since the request was queued
     // encode requests first (they only touch the encoder workspaces and the members' cross-KV slots)
     std::vector<Req *> enc, dec;
     for (Req * q : batch) (q->kind == 0 ? enc : dec).push_back(q);
+    auto by_slot = [](const Req * a, const Req * b) { return a->st->slot < b->st->slot; };
+    std::sort(enc.begin(), enc.end(), by_slot);                      // slots 0..n-1 in order: the cross K/V of all windows is one launch
+    std::sort(dec.begin(), dec.end(), by_slot);                      // and the row order of a pass does not depend on thread timing
     if (!enc.empty()) {
         const int64_t t0 = time_us();
         bool same_ctx = true;
@@ -261,7 +384,11 @@ void Group::run(std::vector<Req *> & batch) {
         for (Req * q : dec) all_samp = all_samp && q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key &&
                                        memcmp(&q->samp->cfg, &dec[0]->samp->cfg, sizeof(SampCfg)) == 0;
         if (scripted) {                                               // test hook: KV bookkeeping done above, logits are the callback's business
-            for (Req * q : dec) { q->st->samp_out.clear(); q->st->logits.assign((size_t) q->n * n_vocab, 0.0f); }
+            for (size_t i = 0; i < dec.size(); ++i) {
+                Req * q = dec[i];
+                if (ok) scripted_attended(*q->st, preps[i], q->n);
+                q->st->samp_out.clear(); q->st->logits.assign((size_t) q->n * n_vocab, 0.0f);
+            }
         } else {
         if (ok && all_samp) ok = eng.set_samp_mask(dec[0]->samp->mask_key, *dec[0]->samp->mask_bits);
         if (ok) {
@@ -414,15 +541,7 @@ WB_EXPORT struct whisper_context * whisper_init_from_buffer_with_params_no_state
 WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx) {  // whisper.cpp:3386-3557
     if (!ctx) return nullptr;
     whisper_state * st = nullptr;
-    if (ctx->scripted) {                                                     // test hook: engine-less state
-        st = new whisper_state();
-        st->scripted = true;
-        st->kv.reset((uint32_t) ((ctx->model.hp.n_text_ctx + 255) / 256 * 256));
-        st->kv_self_n_dec = 1;
-        st->decoders[0].rng = std::mt19937(0);
-        return st;
-    }
-    if (ctx->params.dtw_token_timestamps && ctx->dtw_heads.empty()) {     // aheads_masks_init, src/whisper.cpp:3442-3450: a bad selection fails the state
+    if (ctx->params.dtw_token_timestamps && !ctx->scripted && ctx->dtw_heads.empty()) {     // aheads_masks_init, src/whisper.cpp:3442-3450: a bad selection fails the state
         if (!dtw_resolve_heads(ctx->params, ctx->model.hp.n_text_layer, ctx->model.hp.n_text_head, ctx->dtw_heads)) {
             logf(LOG_ERROR, "%s: aheads_masks_init() failed for alignment heads masks: %s\n", __func__, last_error());
             return nullptr;
@@ -430,12 +549,28 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
         logf(LOG_INFO, "%s: alignment heads masks: %d heads\n", __func__, (int) ctx->dtw_heads.size());
     }
     try {
-        st = new whisper_state();
-        st->own_eng.reset(new Engine());
-        st->eng = st->own_eng.get();
-        if (!st->fe.init(&ctx->model) || !st->eng->init(&ctx->model, 1)) { delete st; return nullptr; }
-        st->kv.reset((uint32_t) st->eng->n_cells);
-        st->kv_self_n_dec = 1;
+        if (ctx->params.dtw_token_timestamps && !ctx->scripted) {
+            // DTW contexts decode with the kernel-per-op chain and capture queries layer by layer: a private engine per state, no pool
+            st = new whisper_state();
+            st->own_eng.reset(new Engine());
+            st->eng = st->own_eng.get();
+            if (!st->fe.init(&ctx->model) || !st->eng->init(&ctx->model, 1)) { delete st; return nullptr; }
+            st->kv.reset((uint32_t) st->eng->n_cells);
+            st->kv_self_n_dec = 1;
+            st->decoders[0].rng = std::mt19937(0);
+            return st;
+        }
+        // every other state is a slot of the context's pool (created with the first state); see wb_state.h
+        {
+            static std::mutex pool_mu;
+            std::lock_guard<std::mutex> lk(pool_mu);
+            if (!ctx->pool) { ctx->pool.reset(new Group()); ctx->pool->model = &ctx->model; ctx->pool->scripted = ctx->scripted; }
+        }
+        std::unique_ptr<FrontEnd> fe = ctx->pool->take_fe();
+        st = fe ? new whisper_state(std::move(fe)) : new whisper_state();
+        st->scripted = ctx->scripted;
+        if (!ctx->scripted && !st->fe.st && !st->fe.init(&ctx->model)) { delete st; return nullptr; }
+        if (!ctx->pool->attach(st)) { logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); delete st; return nullptr; }
         st->decoders[0].rng = std::mt19937(0);
     } catch (...) { set_error("whisper_init_state: allocation failed"); delete st; return nullptr; }
     return st;
@@ -445,8 +580,18 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
     whisper_context * ctx = call; if (!ctx) return nullptr; \
     ctx->state = whisper_init_state(ctx); if (!ctx->state) { whisper_free(ctx); return nullptr; } return ctx;
 
-WB_EXPORT void whisper_free_state(struct whisper_state * st) { delete st; }
-WB_EXPORT void whisper_free(struct whisper_context * ctx) { if (ctx) { whisper_free_state(ctx->state); delete ctx; } }
+WB_EXPORT void whisper_free_state(struct whisper_state * st) {
+    if (!st) return;
+    if (st->group) st->group->detach(st);          // the slot and the front end go back to the context's pool
+    delete st;
+}
+WB_EXPORT void whisper_free(struct whisper_context * ctx) {
+    if (!ctx) return;
+    for (whisper_state * s : ctx->batch_states) whisper_free_state(s);
+    ctx->batch_states.clear();
+    whisper_free_state(ctx->state);
+    delete ctx;
+}
 } // extern "C"
 whisper_context::~whisper_context() {}
 extern "C" {
@@ -489,6 +634,7 @@ WB_EXPORT int whisper_set_mel(struct whisper_context * ctx, const float * data, 
 }
 WB_EXPORT int whisper_encode_with_state(struct whisper_context * ctx, struct whisper_state * st, int offset, int) {
     if (!ctx || !st) return -1;
+    GroupCall gc(st);
     if (!encode_window(*ctx, *st, offset)) { logf(LOG_ERROR, "%s: failed to eval\n", __func__); return -1; }
     return 0;
 }
@@ -499,6 +645,7 @@ WB_EXPORT int whisper_decode_with_state(struct whisper_context * ctx, struct whi
     std::vector<int> pos(n_tokens), seq(n_tokens, 0); std::vector<int8_t> want(n_tokens, 0);
     for (int i = 0; i < n_tokens; ++i) pos[i] = n_past + i;
     want[n_tokens - 1] = 1;                                                          // whisper_batch_prep_legacy, whisper.cpp:511-523
+    GroupCall gc(st);
     st->kv.seq_rm(0, n_past, -1);
     if (!decode_batch(*ctx, *st, tokens, pos.data(), seq.data(), want.data(), n_tokens)) { logf(LOG_ERROR, "%s: failed to eval\n", __func__); return 1; }
     return 0;

@@ -50,10 +50,8 @@ bool Engine::init(const Model * model, int cap_windows) {
     use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
     fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
     gemv_v2 = getenv("WB200_GEMV_V1") == nullptr;
-    if (!mel_win.alloc(B * (2*T + 2) * M, true) || !h1.alloc(B * (2*T + 2) * d, true) || !x.alloc(B * T * d) || !xn.alloc(B * T * d) ||
-        !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || (!fused_attn && (!S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp))) ||
-        !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d) || !kv_cross.alloc(B * 2 * Lt * Tp * d, true)) return false;
-    if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
+    (void) B; (void) H; (void) M; (void) Tp;
+    if (!alloc_encoder_ws() || !kv_cross.alloc((size_t) cap_win * 2 * Lt * Tp * d, true)) return false;
     {
         cudaDeviceProp prop; WB_CUDA_OK(cudaGetDeviceProperties(&prop, m->device));
         n_sm = prop.multiProcessorCount;
@@ -80,11 +78,61 @@ bool Engine::init(const Model * model, int cap_windows) {
     return true;
 }
 
+// encoder workspaces for cap_win windows per batched pass (transient contents)
+bool Engine::alloc_encoder_ws() {
+    const HParams & hp = m->hp;
+    const int d = hp.n_audio_state, H = hp.n_audio_head, T = hp.n_audio_ctx, Tp = pad256(T), M = hp.n_mels;
+    const size_t B = cap_win;
+    if (!mel_win.alloc(B * (2*T + 2) * M, true) || !h1.alloc(B * (2*T + 2) * d, true) || !x.alloc(B * T * d) || !xn.alloc(B * T * d) ||
+        !qk.alloc(B * T * 2 * d) || !vt.alloc(B * d * Tp, true) || (!fused_attn && (!S.alloc(B * H * T * Tp) || !P.alloc(B * H * T * Tp))) ||
+        !attn.alloc(B * T * d) || !hfc.alloc(B * T * 4 * d) || !enc16.alloc(B * T * d)) return false;
+    if (debug_taps && (!enc32.alloc(B * T * d) || !conv32.alloc(B * T * d))) return false;
+    delete plan; plan = nullptr;                                  // tensor maps point into the old buffers
+    return true;
+}
+
+bool Engine::resize(int new_cap, int new_cps) {
+    const HParams & hp = m->hp;
+    WB_CUDA_OK(cudaSetDevice(m->device));
+    WB_CUDA_OK(cudaStreamSynchronize(st));
+    const int Lt = hp.n_text_layer, d = hp.n_text_state, Tp = Tp_max;
+    const int old_cap = cap_win, old_cps = cps, keep = std::min(old_cap, new_cap);
+    drop_graphs();
+    if (new_cap != old_cap) {
+        cap_win = new_cap;
+        if (!alloc_encoder_ws()) return false;
+        const size_t slot_e = (size_t) 2 * Lt * Tp * d;
+        DevBuf<__half> nx;
+        if (!nx.alloc((size_t) new_cap * slot_e, true)) return false;
+        if (kv_cross.p) WB_CUDA_OK(cudaMemcpy(nx.p, kv_cross.p, (size_t) keep * slot_e * sizeof(__half), cudaMemcpyDeviceToDevice));
+        std::swap(nx.p, kv_cross.p); std::swap(nx.n, kv_cross.n);
+    }
+    if (new_cap != old_cap || new_cps != old_cps || !kv_k.p) {
+        const size_t e = (size_t) Lt * new_cap * new_cps * d;
+        DevBuf<__half> nk, nv;
+        if (!nk.alloc(e, true) || !nv.alloc(e, true)) return false;
+        if (kv_k.p && old_cps > 0) {
+            const size_t w = (size_t) std::min(old_cps, new_cps) * d * sizeof(__half);
+            for (int s = 0; s < keep; ++s) {                       // [layer][slot][cell][d]: one 2-D copy per slot, a row per layer
+                WB_CUDA_OK(cudaMemcpy2D(nk.p + (size_t) s * new_cps * d, (size_t) new_cap * new_cps * d * sizeof(__half),
+                                        kv_k.p + (size_t) s * old_cps * d, (size_t) old_cap * old_cps * d * sizeof(__half), w, Lt, cudaMemcpyDeviceToDevice));
+                WB_CUDA_OK(cudaMemcpy2D(nv.p + (size_t) s * new_cps * d, (size_t) new_cap * new_cps * d * sizeof(__half),
+                                        kv_v.p + (size_t) s * old_cps * d, (size_t) old_cap * old_cps * d * sizeof(__half), w, Lt, cudaMemcpyDeviceToDevice));
+            }
+        }
+        std::swap(nk.p, kv_k.p); std::swap(nk.n, kv_k.n); std::swap(nv.p, kv_v.p); std::swap(nv.n, kv_v.n);
+        cps = new_cps; n_cells = new_cap * new_cps;
+    }
+    WB_CUDA_OK(cudaDeviceSynchronize());
+    if (use_mk && !mk_build_table()) return false;
+    return true;
+}
+
 bool Engine::set_cells(int n) {
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
     drop_graphs();
-    n_cells = n;
+    n_cells = n; cps = n / std::max(1, cap_win);
     const size_t e = (size_t) hp.n_text_layer * n * hp.n_text_state;
     if (!kv_k.alloc(e, true) || !kv_v.alloc(e, true)) return false;
     ld_idx = pad256(hp.n_text_ctx);          // a query attends to at most n_text_ctx positions

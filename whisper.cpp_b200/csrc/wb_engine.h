@@ -46,7 +46,8 @@ struct Engine {
     const Model * m = nullptr;
     cudaStream_t  st = nullptr;
     int cap_win = 1;                 // windows that can be encoded/decoded together
-    int n_cells = 0;                 // self-KV pool size (cells); GGML_PAD(n_text_ctx,256) * factor (whisper.cpp:3402, 7167-7172)
+    int n_cells = 0;                 // self-KV pool size (cells) = cap_win * cps
+    int cps = 0;                     // self-KV cells per slot; GGML_PAD(n_text_ctx,256) * factor (whisper.cpp:3402, 7167-7172)
     bool debug_taps = false;
     bool fused_attn = true;          // WB200_UNFUSED_ATTN=1 selects the 3-kernel path (scores -> softmax -> PV through HBM)
 
@@ -101,7 +102,13 @@ struct Engine {
 
     ~Engine();
     bool init(const Model * model, int cap_windows);
-    bool set_cells(int n);           // (re)allocate the self-KV pool; contents are lost
+    bool set_cells(int n);           // private engine (one slot): (re)allocate the self-KV pool; contents are lost
+    // change the number of slots and/or the self-KV cells per slot; cross-KV and self-KV contents of the surviving slots are preserved.
+    // The caller guarantees that no pass is in flight (Group::grow_locked).
+    bool resize(int new_cap, int new_cps);
+  private:
+    bool alloc_encoder_ws();
+  public:
 
     // encode `n_win` windows in one batched pass; window w reads srcs[w].mel at frame srcs[w].seek and fills cross-KV slot srcs[w].slot
     bool encode(const EncSrc * srcs, int n_win, int n_ctx);

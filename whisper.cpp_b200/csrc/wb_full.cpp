@@ -402,6 +402,16 @@ void samp_rowinfo(const Vocab & vocab, const whisper_full_params & params, const
     out2[0] = f; out2[1] = d.seek_delta / 2;
 }
 
+// P(no-speech token) of row 0 of the state's logits buffer, with the reference's refresh rule (see the call site)
+float row0_nosp(const whisper_context & ctx, const whisper_state & st) {
+    const int n = ctx.vocab.n_vocab;
+    if (st.row0_on_device) return st.row0_nosp_dev;
+    if ((int) st.logits.size() < n) return 1.0f / (float) n;             // untouched buffer: all-zero logits
+    std::vector<float> raw(st.logits.begin(), st.logits.begin() + n), lp(n), pr(n);
+    compute_logprobs(raw, n, lp); compute_probs(raw, n, lp, pr);
+    return pr[ctx.vocab.token_nosp];
+}
+
 template <typename F> void run_parallel(int n_threads, F && fn) {
     if (n_threads <= 1) { fn(); return; }
     std::vector<std::thread> th(n_threads - 1);
@@ -471,6 +481,7 @@ WB_EXPORT struct whisper_full_params * whisper_full_default_params_by_ref(enum w
 WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisper_state * state, struct whisper_full_params params,
                                       const float * samples, int n_samples) {
     if (!ctx || !state) return -1;
+    GroupCall group_call(state);                  // this state takes part in the context's lock-step passes until the call returns
     auto & result_all = state->result_all;
     result_all.clear();
     const Vocab & vocab = ctx->vocab;
@@ -643,8 +654,12 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 if (state->kv_self_n_dec < n_cur) {
                     const int factor = n_cur > 1 ? n_cur + 2 : 1;
                     const int cells = ((n_text_ctx + 255) / 256 * 256) * factor;
-                    if (state->group || !(state->scripted || state->eng->set_cells(cells))) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
-                    state->kv.reset((uint32_t) cells);
+                    if (state->group) {                                                // pool state: more cells per slot (contents of all slots preserved)
+                        if (!state->group->ensure_cells(state, cells)) { logf(LOG_ERROR, "%s: KV cache allocation failed: %s\n", __func__, last_error()); return -7; }
+                    } else {
+                        if (!(state->scripted || state->eng->set_cells(cells))) { logf(LOG_ERROR, "%s: KV cache allocation failed\n", __func__); return -7; }
+                        state->kv.reset((uint32_t) cells);
+                    }
                     state->kv_self_n_dec = n_cur;
                 }
                 state->kv.clear();
@@ -659,17 +674,15 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), np, dev_samp ? &sreq : nullptr)) { logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -8; }
                 if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -8;
 
+                // no_speech probability (whisper.cpp:7190-7200).  The reference takes it from ROW 0 of state->logits, a buffer in which a
+                // decode only refreshes the rows it was asked logits for (whisper.cpp:2957-2963): for a one-token prompt that is the SOT
+                // row of this decode; for longer prompts (language / task tokens, previous context) it is whatever the last decode with a
+                // flagged row 0 left there -- the last single-token step of the previous window, or zeros on a fresh state (p = 1/n_vocab).
+                // row0_nosp() follows exactly that rule on both the host-logits and the device-sampler path.
+                state->no_speech_prob = row0_nosp(*ctx, *state);
                 if (!state->samp_out.empty()) {      // the device already filtered and picked
-                    state->no_speech_prob = state->samp_out[np - 1].nosp_raw;
                     state->decoders[0].pending = from_samp(state->samp_out[np - 1]);
                     state->decoders[0].have_pending = true;
-                } else
-                { // no_speech probability from the unfiltered logits of the last prompt token (whisper.cpp:7190-7200)
-                    const int n = vocab.n_vocab;
-                    std::vector<float> raw(state->logits.begin() + (size_t) (np - 1) * n, state->logits.begin() + (size_t) np * n);
-                    std::vector<float> lp(n), pr(n);
-                    compute_logprobs(raw, n, lp); compute_probs(raw, n, lp, pr);
-                    state->no_speech_prob = pr[vocab.token_nosp];
                 }
                 if (state->samp_out.empty()) {
                     const int64_t ts = time_us();
@@ -790,6 +803,7 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                     if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), (int) b_tok.size(), dev_samp ? &sreq : nullptr)) {
                         logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -9;
                     }
+                    if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -9;
                     if (!state->samp_out.empty()) {
                         for (int j = 0; j < n_cur; ++j) {
                             Decoder & d = state->decoders[j];
@@ -798,7 +812,6 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         }
                         continue;
                     }
-                    if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -9;
                     const int64_t ts1 = time_us();
                     std::atomic<int> j_cur(0);
                     auto work = [&]() {
@@ -971,9 +984,16 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
     const int per = (n_samples - offset_samples) / n_processors;
     std::vector<std::thread> workers(n_processors - 1);
     std::vector<int> rets(n_processors - 1, 0);
-    for (int i = 0; i < n_processors - 1; ++i) {
+    for (int i = 0; i < n_processors - 1; ++i) {                                          // whisper.cpp:7848-7852: one new state per extra processor
         states.push_back(whisper_init_state(ctx));
-        if (!states.back()) { for (int k = 0; k < i; ++k) { workers[k].join(); whisper_free_state(states[k]); } return -7; }
+        if (!states.back()) { states.pop_back(); for (whisper_state * s : states) whisper_free_state(s); return -7; }
+    }
+    // The states of one context advance in lock-step (wb_state.h).  All of them join the rendezvous BEFORE the first thread starts, so the
+    // very first pass already carries every processor's window; each one leaves as soon as its own slice is done.
+    whisper_state * main_state = ctx->state;
+    if (main_state->group) main_state->group->enter(main_state);
+    for (whisper_state * s : states) if (s->group) s->group->enter(s);
+    for (int i = 0; i < n_processors - 1; ++i) {
         const int start = offset_samples + (i + 1) * per;
         const int n_cur = (i == n_processors - 2) ? n_samples - start : per;
         whisper_full_params pc = params;
@@ -981,11 +1001,15 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
         pc.new_segment_callback = nullptr; pc.new_segment_callback_user_data = nullptr;
         pc.progress_callback = nullptr; pc.progress_callback_user_data = nullptr;
         whisper_state * s = states[i]; int * r = &rets[i];
-        workers[i] = std::thread([ctx, s, pc, samples, start, n_cur, r]() { *r = whisper_full_with_state(ctx, s, pc, samples + start, n_cur); });
+        workers[i] = std::thread([ctx, s, pc, samples, start, n_cur, r]() {
+            *r = whisper_full_with_state(ctx, s, pc, samples + start, n_cur);
+            if (s->group) s->group->leave(s);
+        });
     }
     {
         whisper_full_params pc = params; pc.print_realtime = false;
         ret = whisper_full_with_state(ctx, ctx->state, pc, samples, offset_samples + per);
+        if (main_state->group) main_state->group->leave(main_state);
     }
     for (auto & w : workers) w.join();
     const int64_t offset_t = (int64_t) (params.offset_ms / 10.0);
@@ -1013,8 +1037,8 @@ WB_EXPORT int whisper_full_parallel(struct whisper_context * ctx, struct whisper
     return ret;
 }
 
-// Independent PCM buffers on one device, decoded in LOCK-STEP: up to 64 member states share one engine (one batched encoder
-// pass for all windows, one batched decode step for all live sequences -- weights are read once per step).  Chunk i's
+// Convenience driver on top of the context's pool: independent PCM buffers, a queue of chunks served by up to 64 pool states that
+// call whisper_full_with_state concurrently (the same lock-step passes any concurrent whisper.h callers get).  Chunk i's
 // segments are returned in states_out[i] (result-only states; free with whisper_free_state).  Chunk semantics are those
 // of whisper_full_with_state.  flags bit 0: `samples[i]` are DEVICE pointers (PCM already resident in HBM).
 WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_full_params params, const float * const * samples,
@@ -1026,38 +1050,29 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
     if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));
     S = std::min(S, n_chunks);
     std::lock_guard<std::mutex> batch_lock(ctx->batch_mu);
-    const int member_decoders = 5;                                    // enough for best_of / beam_size up to 5
-    const int cells_per_member = ((ctx->model.hp.n_text_ctx + 255) / 256 * 256) * (member_decoders + 2);
-    if (!ctx->batch_group || ctx->batch_group->n_members != S) {
-        ctx->batch_group.reset(new Group());
-        Group & G = *ctx->batch_group;
-        G.n_members = S; G.cells_per_member = cells_per_member;
-        G.scripted = ctx->scripted;                                   // test hook: members without an engine (see whisper_state::scripted)
-        if (!G.scripted && (!G.eng.init(&ctx->model, S) || !G.eng.set_cells(S * cells_per_member))) { ctx->batch_group.reset(); return -7; }
-        for (int i = 0; i < S; ++i) {
-            whisper_state * st = new whisper_state();
-            G.members.push_back(st);
-            st->scripted = G.scripted;
-            if (!G.scripted && !st->fe.init(&ctx->model)) { ctx->batch_group.reset(); return -7; }
-            st->eng = &G.eng; st->group = &G; st->slot = i; st->cell_off = i * cells_per_member;
-            st->kv.reset((uint32_t) cells_per_member);
-            st->kv_self_n_dec = member_decoders;
-        }
+    // the members are ordinary states of the context's pool (whisper_init_state), kept for the next call
+    while ((int) ctx->batch_states.size() < S) {
+        whisper_state * st = whisper_init_state(ctx);
+        if (!st) return -7;
+        ctx->batch_states.push_back(st);
     }
-    Group & G = *ctx->batch_group;
-    G.n_active = S;
-    G.pending.clear();
+    std::vector<whisper_state *> members(ctx->batch_states.begin(), ctx->batch_states.begin() + S);
+    for (whisper_state * st : members) if (st->group) st->group->enter(st);      // all of them before the first request (see whisper_full_parallel)
     std::atomic<int> next(0); std::atomic<int> rc(0);
     whisper_full_params pc = params;
     pc.print_progress = false; pc.print_realtime = false;
     std::vector<std::thread> th;
     for (int mi = 0; mi < S; ++mi) {
         th.emplace_back([&, mi]() {
-            whisper_state * st = G.members[mi];
+            whisper_state * st = members[mi];
             for (;;) {
                 const int i = next.fetch_add(1);
                 if (i >= n_chunks) break;
+                // a chunk starts from what a fresh state would hold
                 st->decoders[0].rng = std::mt19937(0);
+                st->prompt_past0.clear(); st->prompt_past1.clear();
+                st->t_beg = st->t_last = 0; st->tid_last = 0; st->energy.clear(); st->no_speech_prob = 0.0f;
+                st->logits.clear(); st->row0_on_device = false; st->lang_id = 0;
                 st->t_sample_us = st->t_encode_us = st->t_decode_us = st->t_batchd_us = st->t_prompt_us = st->t_mel_us = 0;
                 st->n_sample = st->n_encode = st->n_decode = st->n_batchd = st->n_prompt = st->n_fail_p = st->n_fail_h = 0;
                 wb::tls_pcm_is_device() = (flags & 1) != 0;
@@ -1072,7 +1087,7 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
                 out->n_sample = st->n_sample; out->n_encode = st->n_encode; out->n_decode = st->n_decode; out->n_batchd = st->n_batchd; out->n_prompt = st->n_prompt;
                 states_out[i] = out;
             }
-            G.leave();
+            if (st->group) st->group->leave(st);
         });
     }
     for (auto & t : th) t.join();

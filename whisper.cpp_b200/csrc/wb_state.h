@@ -65,19 +65,26 @@ struct Segment {
 } // namespace wb
 
 struct whisper_state {
+    whisper_state() : fe_own(new wb::FrontEnd()), fe(*fe_own) {}
+    explicit whisper_state(std::unique_ptr<wb::FrontEnd> f) : fe_own(std::move(f)), fe(*fe_own) {}
     int64_t t_sample_us = 0, t_encode_us = 0, t_decode_us = 0, t_batchd_us = 0, t_prompt_us = 0, t_mel_us = 0;
     int32_t n_sample = 0, n_encode = 0, n_decode = 0, n_batchd = 0, n_prompt = 0, n_fail_p = 0, n_fail_h = 0;
 
-    wb::FrontEnd fe;                           // PCM + mel of this state
-    wb::Engine * eng = nullptr;                // own engine, or the engine shared by the members of a batch group
+    std::unique_ptr<wb::FrontEnd> fe_own;      // PCM + mel of this state (handed back to the context's pool by whisper_free_state)
+    wb::FrontEnd & fe;                         // = *fe_own
+    wb::Engine * eng = nullptr;                // own engine (DTW contexts), or the engine shared by all states of the context
     std::unique_ptr<wb::Engine> own_eng;
-    wb::Group * group = nullptr;               // non-null: encode/decode requests rendezvous with the other members
+    wb::Group * group = nullptr;               // non-null: this state lives in the context's pool; its encode/decode requests rendezvous
+                                               // with those of the other states that are inside whisper_full* at the same time
+    bool in_group_call = false;                // between Group::enter and Group::leave
     int cell_off = 0;                          // first self-KV cell of this state inside eng's pool
     wb::KvCells kv;
     int kv_self_n_dec = 1;
     wb::Decoder decoders[wb::MAX_DECODERS];
     std::vector<float> logits;                 // [n_tokens][n_vocab] of the last decode (rows flagged want_logits are valid)
     std::vector<wb::SampOut> samp_out;         // per row of the last decode when the on-device sampler was used
+    bool  row0_on_device = false;              // row 0 of `logits` was last refreshed by a device-sampled decode: only its no-speech
+    float row0_nosp_dev = 0.0f;                // probability came back (whisper.cpp:7196-7198 reads row 0 of the logits buffer)
     std::vector<wb::Segment> result_all;
     std::vector<whisper_token> prompt_past0, prompt_past1;
     int   lang_id = 0;
@@ -110,41 +117,69 @@ struct whisper_context {
     std::string path_model;
     bool scripted = false;                     // TEST HOOK: see whisper_state::scripted
     std::vector<std::pair<int, int>> dtw_heads; // (text layer, head) of the alignment heads when params.dtw_token_timestamps survived init
-    std::unique_ptr<wb::Group> batch_group;    // cached by wb200_full_batch
+    std::unique_ptr<wb::Group> pool;           // device pool shared by every state of this context (created with the first state)
+    std::vector<whisper_state *> batch_states; // pool states kept by wb200_full_batch between calls
     std::mutex batch_mu;
     ~whisper_context();
 };
 
 namespace wb {
 
-// Lock-step batching of concurrently running states (wb200_full_batch): every member thread runs the ordinary
-// whisper_full_with_state control flow; its encode / decode requests block in submit() until all ACTIVE members have one
-// pending, then one thread executes them as a single batched device pass (weights are read once for all sequences).
+// The device pool of a context and the lock-step batching of its states.  whisper.h allows concurrent whisper_full_with_state calls on
+// DISTINCT states of one context (include/whisper.h:45-46), and whisper_full_parallel does exactly that (src/whisper.cpp:7848-7869).
+// Every state created by whisper_init_state is a slot of this pool: one engine, one copy of the workspaces, a cross-KV slot and a range
+// of self-KV cells per state.  Each calling thread runs the ordinary whisper_full_with_state control flow; its encode / decode requests
+// block in submit() until all ACTIVE states (those inside a whisper_full* call) have one pending, then one of the threads executes them
+// as a single batched device pass: one batched encoder pass for all windows, one decode launch for all live sequences (weights are read
+// once per step).  A state that runs alone gets a 1-row pass immediately.
 // request for the on-device logits filter + greedy pick of the rows of one decode call
 struct SampReq { SampCfg cfg; uint64_t mask_key = 0; const std::vector<uint32_t> * mask_bits = nullptr; const int * rowinfo = nullptr; };
 
 struct Group {
     Engine eng;
-    int n_members = 0, cells_per_member = 0;
     bool scripted = false;                      // test hook: no engine, decodes leave zero logits
-    std::vector<whisper_state *> members;       // owned
-    ~Group() { for (whisper_state * m : members) delete m; }
+    const Model * model = nullptr;
+    // ---- slots: one cross-KV slot + `cps` self-KV cells per state; the pool grows (contents preserved) while no pass is in flight
+    int cap = 0, cps = 0;
+    std::vector<uint8_t> slot_used;
+    std::vector<std::unique_ptr<FrontEnd>> fe_cache;     // front ends of freed states (stream + PCM/mel buffers are reused)
+    int n_registered = 0;                       // states attached
+    std::unique_ptr<FrontEnd> take_fe();
+    bool attach(whisper_state * st);            // whisper_init_state
+    void detach(whisper_state * st);            // whisper_free_state
+    bool ensure_cells(whisper_state * st, int cells);    // a state needs `cells` self-KV cells (n_decoders grew): kv.reset + pool relayout if needed
+    // ---- rendezvous
     std::mutex mu;
     std::condition_variable cv;
-    int n_active = 0;
+    bool running = false;                       // a batch is executing (outside the lock)
+    int n_active = 0;                           // states between enter() and leave()
+    int64_t t_last_enter_us = 0;
     struct Req {
         int kind = 0;                           // 0 = encode, 1 = decode
         whisper_context * ctx = nullptr; whisper_state * st = nullptr;
         int seek = 0, n_ctx = 0;                // encode
         const int * tokens = nullptr, * pos = nullptr, * seq = nullptr; const int8_t * want = nullptr; int n = 0;   // decode
         const SampReq * samp = nullptr;
+        bool taken = false;                      // (under mu) some thread took the batch that contains this request
         std::atomic<int> done{0};                // futex word: the member sleeps on its OWN request (no shared mutex to re-acquire on wake-up)
         bool ok = false; int64_t dt_us = 0;
     };
     std::vector<Req *> pending;
+    void enter(whisper_state * st);             // the state starts issuing requests (whisper_full_with_state, or one low-level call)
+    void leave(whisper_state * st);
     bool submit(Req & r);
-    void leave();
     void run(std::vector<Req *> & batch);       // executes outside the lock
+  private:
+    bool grow_locked(std::unique_lock<std::mutex> & lk, int new_cap, int new_cps);
+    int64_t grace_left_us() const;
+};
+
+// RAII: a state that is not inside whisper_full* joins the rendezvous for the duration of one low-level call
+struct GroupCall {
+    whisper_state * st; bool did = false;
+    explicit GroupCall(whisper_state * s) : st(s) { if (st && st->group && !st->in_group_call) { st->group->enter(st); did = true; } }
+    ~GroupCall() { if (did) st->group->leave(st); }
+    GroupCall(const GroupCall &) = delete; GroupCall & operator=(const GroupCall &) = delete;
 };
 
 int64_t time_us();
