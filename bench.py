@@ -6,8 +6,12 @@ Workload (BASELINE.json configs[3]): large-v3 Q5_0, synthetic weights (no checkp
 rank's 64 chunks (all 64 sequences advance in lock-step: one batched encoder pass, one decode launch per token step).  Multi-GPU = independent chunks per rank, no collective on the data path
 (weak scaling); torch.distributed is used only for the barrier and the max-over-ranks time.
 
-  value  : xRT with the PCM already resident in HBM (wb200_pcm_upload before the timed region)
-  e2e    : xRT through whisper_full_with_state with HOST PCM buffers (H2D of the samples, D2H of the logits inside)
+  value  : xRT with the PCM already resident in HBM before the timed region (device pointers through the library's queue driver
+           wb200_full_batch_ex, which runs whisper_full_with_state on pool states -- an input mode whisper.h itself does not have)
+  e2e    : xRT through whisper.h ONLY, host PCM in, segments out: ONE call of whisper_full_parallel(ctx, params, pcm, n, 64) on the
+           concatenation of the rank's 64 chunks (src/whisper.cpp:7813-7941 semantics: 64 states, one slice each).  H2D of the samples
+           and D2H of the sampled tokens happen inside the timed region.  `e2e_threads` is the other reference-legal form: 64 caller
+           threads x whisper_full_with_state on 64 states of the context (include/whisper.h:45-46).
   roofline / cpu_baseline : see DESIGN.md section 6
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, unmodified whisper.cpp) on a bounded
@@ -190,7 +194,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chunks", type=int, default=CHUNKS_PER_GPU)
+    ap.add_argument("--chunks", type=int, default=CHUNKS_PER_GPU, help="chunks per GPU (weak scaling)")
+    ap.add_argument("--chunks-total", type=int, default=0, help="strong scaling: this many chunks in total, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -220,6 +225,10 @@ def main():
     L.wb200_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.wb200_last_encode_ms.argtypes = [vp, C.POINTER(C.c_float)]
     n_chunks = args.chunks
+    scaling = "weak"
+    if args.chunks_total > 0:
+        assert args.chunks_total % world == 0, "--chunks-total must be a multiple of the number of ranks"
+        n_chunks = args.chunks_total // world; scaling = "strong"
     pcms = make_inputs(rank, n_chunks)
     pinned = [torch.from_numpy(p).pin_memory() for p in pcms]          # e2e copies start from pinned host memory
     resident = [t.cuda(local, non_blocking=False) for t in pinned]     # `value`: PCM already in HBM
@@ -230,18 +239,41 @@ def main():
     dev_ptrs = (vp * n_chunks)(*[t.data_ptr() for t in resident])
     last = {"tokens": 0, "enc": None}
 
-    def run_pass(on_device):
-        """one step: all chunks of this rank through the lock-step batch driver (whisper_full_with_state semantics per chunk)"""
+    concat = torch.from_numpy(np.concatenate(pcms)).pin_memory()       # whisper_full_parallel input: one host buffer, sliced by the library
+    states = []
+
+    def run_pass(mode):
+        """one step = all chunks of this rank.  mode "device": PCM resident in HBM (library queue driver); "parallel": one
+        whisper_full_parallel call on host PCM; "threads": one caller thread per chunk, whisper_full_with_state on its own state"""
+        if mode == "parallel":
+            rc = L.whisper_full_parallel(eng.ctx, p, vp(concat.data_ptr()), concat.numel(), n_chunks)
+            assert rc == 0, (rc, L.wb200_last_error())
+            last["tokens"] = sum(L.whisper_full_n_tokens(eng.ctx, i) for i in range(L.whisper_full_n_segments(eng.ctx)))
+            return
+        if mode == "threads":
+            while len(states) < n_chunks:
+                st = L.whisper_init_state(eng.ctx); assert st, L.wb200_last_error()
+                states.append(st)
+            rcs = [None] * n_chunks
+
+            def work(i):
+                rcs[i] = L.whisper_full_with_state(eng.ctx, states[i], p, host_ptrs[i], n_arr[i])
+            th = [threading.Thread(target=work, args=(i,)) for i in range(n_chunks)]
+            for t in th: t.start()
+            for t in th: t.join()
+            assert rcs == [0] * n_chunks, (rcs, L.wb200_last_error())
+            last["tokens"] = sum(count_tokens(L, st) for st in states)
+            return
         outs = (vp * n_chunks)()
-        rc = L.wb200_full_batch_ex(eng.ctx, p, dev_ptrs if on_device else host_ptrs, n_arr, n_chunks, outs, 1 if on_device else 0)
+        rc = L.wb200_full_batch_ex(eng.ctx, p, dev_ptrs, n_arr, n_chunks, outs, 1)
         assert rc == 0, (rc, L.wb200_last_error())
         last["tokens"] = sum(count_tokens(L, outs[i]) for i in range(n_chunks))
         for i in range(n_chunks):
             L.whisper_free_state(outs[i])
 
-    def timed(on_device, steps, warmup):
+    def timed(mode, steps, warmup):
         for _ in range(warmup):
-            run_pass(on_device)
+            run_pass(mode)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -249,7 +281,7 @@ def main():
         n0 = eng.launch_count()
         t0 = time.perf_counter()
         for _ in range(steps):
-            run_pass(on_device)
+            run_pass(mode)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         h1, d1 = C.c_uint64(), C.c_uint64(); L.wb200_traffic(C.byref(h1), C.byref(d1))
@@ -264,9 +296,9 @@ def main():
     # ---- device-resident inputs ("value")
     sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
-        run_pass(True)
+        run_pass("device")
     c0 = counters()
-    dt_res, launches, _, _ = timed(True, args.steps, 0)
+    dt_res, launches, _, _ = timed("device", args.steps, 0)
     c1 = counters()
     clocks = sampler.stop()
     cd = [b - a for a, b in zip(c0, c1)]
@@ -278,8 +310,11 @@ def main():
     tokens = last["tokens"]
 
     # ---- host buffers through the C ABI ("e2e")
-    dt_e2e, _, h2d, d2h = timed(False, args.steps, 1)
+    dt_e2e, _, h2d, d2h = timed("parallel", args.steps, max(1, args.warmup))
     e2e = audio_s / dt_e2e
+    tokens_e2e = last["tokens"]
+    dt_thr, _, h2d_t, d2h_t = timed("threads", args.steps, max(1, args.warmup))
+    e2e_threads = audio_s / dt_thr
 
     # ---- encode ms of ONE 30 s window (whisper-bench "Enc." semantics: conv + encoder + cross, bench.cpp:63-150) on the default state
     st0 = L.wb200_ctx_state(eng.ctx)
@@ -294,19 +329,22 @@ def main():
     enc = enc_runs[-1]
 
     out = {"metric": "xRT (audio-s/wall-s)", "value": value, "unit": "x real time", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": 1e3 * dt_res / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
            "dtype": "f16 tcgen05 (encode) / int8 mma block dot (decode), f32 accumulate", "data": "synthetic",
            "config": {"workload": WORKLOAD, "chunks_per_gpu": n_chunks, "decode": "lock-step batch of up to 64 sequences per GPU, one persistent cooperative kernel per token step", "l2": "weights (1.08 GB) + KV (0.3 GB/sequence) streamed every step exceed the 126 MB L2",
                       "timing": "host wall clock between device synchronisations around whole steps (a step contains host control flow), max over ranks; per-kernel numbers from CUDA events on the launching stream"},
            "encode_ms": float(enc[1] + enc[2] + enc[3]), "encode_ms_parts": {"mel": float(enc[0]), "conv": float(enc[1]), "encoder": float(enc[2]), "cross": float(enc[3])},
            "decoded_tokens_per_step": tokens, "engine": engine_stats, "clocks": clocks, "gpu_launches": int(launches),
-           "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
+           "e2e": {"value": e2e, "unit": "x real time", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt_e2e / args.steps,
+                   "api": "whisper_full_parallel(ctx, params, host_pcm, n_samples, n_processors=%d) -- whisper.h only" % n_chunks, "decoded_tokens_per_step": tokens_e2e},
+           "e2e_threads": {"value": e2e_threads, "unit": "x real time", "h2d_bytes_per_step": int(h2d_t), "d2h_bytes_per_step": int(d2h_t),
+                           "api": "%d threads x whisper_full_with_state(ctx, state_i, params, host_pcm_i, n) -- whisper.h only" % n_chunks}}
 
     if rank == 0:
         # ---- roofline of the dominant kernel class: separate pass of ONE chunk with per-launch CUDA events (library side,
         # on the launching stream); not inside the timed region so the event overhead does not perturb `value`
         L.wb200_profile_enable(1)
-        run_pass(True)
+        run_pass("device")
         ms = (C.c_double * 4)(); ln = (C.c_uint64 * 4)(); by = (C.c_double * 4)(); fl = (C.c_double * 4)()
         L.wb200_profile_collect(ms, ln, by, fl)
         L.wb200_profile_enable(0)
@@ -341,8 +379,8 @@ def main():
             except Exception as e:  # noqa: BLE001
                 out["cpu_baseline"] = {"value": None, "unit": "x real time", "cores": ref_threads(), "kind": "reference",
                                        "sample": "1 x 30 s chunk (did not finish: %s)" % type(e).__name__}
-        if os.environ.get("WB200_BENCH_REF_TOOL") == "1" and world == 1:
-            # opt-in (not yet exercised on a GPU): the reference's OWN benchmark program, unmodified, linked against this library
+        if os.environ.get("WB200_BENCH_REF_TOOL", "1") == "1" and world == 1:
+            # the reference's OWN benchmark program, unmodified, linked against this library
             # (oracle/_ref/whisper-bench-b200 = examples/bench/bench.cpp): encode / decode / batched / prompt ms per run as whisper_print_timings reports
             try:
                 import re

@@ -238,7 +238,7 @@ bool Group::attach(whisper_state * st) {
     for (int i = 0; i < cap; ++i) if (!slot_used[(size_t) i]) { slot = i; break; }
     if (slot < 0) {
         const int base_cps = cps > 0 ? cps : pool_cells_for(*model, 1);
-        const int new_cap = cap == 0 ? 1 : cap * 2;
+        const int new_cap = cap == 0 ? 1 : (cap < 8 ? cap * 2 : cap + std::max(8, cap / 4));     // 1 2 4 8 16 24 32 40 50 62 77 ...
         if (new_cap > 1024) { set_error("whisper_init_state: too many states on one context (%d)", cap); return false; }
         slot = cap;
         if (!grow_locked(lk, new_cap, base_cps)) return false;
@@ -324,13 +324,13 @@ bool Group::submit(Req & r) {
     return r.ok;
 }
 
-void Group::leave(whisper_state * st) {
+void Group::deactivate(whisper_state * st, bool clear_flag) {
     std::vector<Req *> batch;
     {
         std::lock_guard<std::mutex> lk(mu);
-        st->in_group_call = false;
+        if (clear_flag) st->in_group_call = false;
         n_active--;
-        if (!pending.empty() && (int) pending.size() >= n_active && !pending[0]->taken) {
+        if (!pending.empty() && (int) pending.size() >= n_active) {      // everybody else was only waiting for this state
             batch.swap(pending);
             for (Req * q : batch) q->taken = true;
             running = true;
@@ -343,6 +343,27 @@ void Group::leave(whisper_state * st) {
         for (Req * q : batch) req_wake(*q);
     }
 }
+void Group::leave(whisper_state * st)   { deactivate(st, true); }
+void Group::suspend(whisper_state * st) { deactivate(st, false); }
+void Group::resume(whisper_state *)     { std::lock_guard<std::mutex> lk(mu); ++n_active; }
+
+static thread_local std::vector<whisper_state *> tls_call_stack;       // states this thread is executing a whisper.h call for, innermost last
+GroupCall::GroupCall(whisper_state * s) : st(s) {
+    if (!st || !st->group) return;
+    if (!tls_call_stack.empty() && tls_call_stack.back() != st && tls_call_stack.back()->group == st->group && tls_call_stack.back()->in_group_call) {
+        suspended = tls_call_stack.back();
+        st->group->suspend(suspended);
+    }
+    if (!st->in_group_call) { st->group->enter(st); entered = true; }
+    tls_call_stack.push_back(st);
+}
+GroupCall::~GroupCall() {
+    if (!st || !st->group) return;
+    tls_call_stack.pop_back();
+    if (entered) st->group->leave(st);
+    if (suspended) suspended->group->resume(suspended);
+}
+
 void Group::run(std::vector<Req *> & batch) {
     for (Req * q : batch) q->st->cell_off = q->st->slot * cps;      // the pool may have been re-laid out since the request was queued
     // encode requests first (they only touch the encoder workspaces and the members' cross-KV slots)
@@ -587,8 +608,6 @@ WB_EXPORT void whisper_free_state(struct whisper_state * st) {
 }
 WB_EXPORT void whisper_free(struct whisper_context * ctx) {
     if (!ctx) return;
-    for (whisper_state * s : ctx->batch_states) whisper_free_state(s);
-    ctx->batch_states.clear();
     whisper_free_state(ctx->state);
     delete ctx;
 }

@@ -1049,14 +1049,13 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
     int S = ctx->model.dec_tm ? 64 : 8;          // concurrent sequences: one row each in the decode pass (64 rows per launch of the persistent kernel)
     if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));
     S = std::min(S, n_chunks);
-    std::lock_guard<std::mutex> batch_lock(ctx->batch_mu);
-    // the members are ordinary states of the context's pool (whisper_init_state), kept for the next call
-    while ((int) ctx->batch_states.size() < S) {
+    // the members are ordinary states of the context's pool (whisper_init_state): slots and front ends are recycled, so this is cheap
+    std::vector<whisper_state *> members;
+    for (int i = 0; i < S; ++i) {
         whisper_state * st = whisper_init_state(ctx);
-        if (!st) return -7;
-        ctx->batch_states.push_back(st);
+        if (!st) { for (whisper_state * m : members) whisper_free_state(m); return -7; }
+        members.push_back(st);
     }
-    std::vector<whisper_state *> members(ctx->batch_states.begin(), ctx->batch_states.begin() + S);
     for (whisper_state * st : members) if (st->group) st->group->enter(st);      // all of them before the first request (see whisper_full_parallel)
     std::atomic<int> next(0); std::atomic<int> rc(0);
     whisper_full_params pc = params;
@@ -1091,6 +1090,7 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
         });
     }
     for (auto & t : th) t.join();
+    for (whisper_state * m : members) whisper_free_state(m);
     return rc.load();
 }
 // Host-only test hook (no CUDA): the logits filter + greedy pick of this library on injected logits, with the vocabulary of

@@ -118,8 +118,6 @@ struct whisper_context {
     bool scripted = false;                     // TEST HOOK: see whisper_state::scripted
     std::vector<std::pair<int, int>> dtw_heads; // (text layer, head) of the alignment heads when params.dtw_token_timestamps survived init
     std::unique_ptr<wb::Group> pool;           // device pool shared by every state of this context (created with the first state)
-    std::vector<whisper_state *> batch_states; // pool states kept by wb200_full_batch between calls
-    std::mutex batch_mu;
     ~whisper_context();
 };
 
@@ -167,18 +165,24 @@ struct Group {
     std::vector<Req *> pending;
     void enter(whisper_state * st);             // the state starts issuing requests (whisper_full_with_state, or one low-level call)
     void leave(whisper_state * st);
+    void suspend(whisper_state * st);           // the state's thread is busy with a nested call on another state
+    void resume(whisper_state * st);
     bool submit(Req & r);
     void run(std::vector<Req *> & batch);       // executes outside the lock
   private:
+    void deactivate(whisper_state * st, bool clear_flag);
     bool grow_locked(std::unique_lock<std::mutex> & lk, int new_cap, int new_cps);
     int64_t grace_left_us() const;
 };
 
-// RAII: a state that is not inside whisper_full* joins the rendezvous for the duration of one low-level call
+// RAII around every whisper.h call that issues device work for a state: joins the rendezvous unless the state already has
+// (whisper_full_parallel enters all its states up front).  A call made from INSIDE a callback of another active state on the same
+// thread (legal with the reference: states are independent) suspends the outer state for its duration -- the outer state cannot
+// submit anything while its thread is busy here, and the lock-step rendezvous must not wait for it.
 struct GroupCall {
-    whisper_state * st; bool did = false;
-    explicit GroupCall(whisper_state * s) : st(s) { if (st && st->group && !st->in_group_call) { st->group->enter(st); did = true; } }
-    ~GroupCall() { if (did) st->group->leave(st); }
+    whisper_state * st; bool entered = false; whisper_state * suspended = nullptr;
+    explicit GroupCall(whisper_state * s);
+    ~GroupCall();
     GroupCall(const GroupCall &) = delete; GroupCall & operator=(const GroupCall &) = delete;
 };
 
