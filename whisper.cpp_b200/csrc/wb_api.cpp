@@ -402,8 +402,11 @@ void Group::run(std::vector<Req *> & batch) {
         // the on-device filter + pick serves the pass only if EVERY request asked for it with the same configuration (a member that fell
         // back to temperature > 0 samples on the host and needs full logits, so the whole pass returns logits then)
         bool all_samp = dec[0]->samp != nullptr;
-        for (Req * q : dec) all_samp = all_samp && q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key &&
-                                       memcmp(&q->samp->cfg, &dec[0]->samp->cfg, sizeof(SampCfg)) == 0;
+        auto same_cfg = [](const SampCfg & a, const SampCfg & b) {            // field by field: the struct has padding bytes
+            return a.token_eot == b.token_eot && a.token_beg == b.token_beg && a.token_nosp == b.token_nosp && a.space_id == b.space_id &&
+                   a.suppress_blank == b.suppress_blank && a.no_timestamps == b.no_timestamps && a.max_initial_tid == b.max_initial_tid;
+        };
+        for (Req * q : dec) all_samp = all_samp && q->samp != nullptr && q->samp->mask_key == dec[0]->samp->mask_key && same_cfg(q->samp->cfg, dec[0]->samp->cfg);
         if (scripted) {                                               // test hook: KV bookkeeping done above, logits are the callback's business
             for (size_t i = 0; i < dec.size(); ++i) {
                 Req * q = dec[i];
