@@ -128,12 +128,27 @@ void scripted_attended(whisper_state & st, const PreparedDecode & P, int n_token
         st.dbg_att[(size_t) j] = h;
     }
 }
-// row 0 of the state's logits buffer is refreshed only by a decode that asked logits for its first token (whisper.cpp:2957-2963);
-// with the on-device sampler only that row's no-speech probability exists on the host
-void note_row0(whisper_state & st, const int8_t * want) {
-    if (!want[0]) return;
-    st.row0_on_device = !st.samp_out.empty();
-    if (st.row0_on_device) st.row0_nosp_dev = st.samp_out[0].nosp_raw;
+// keep whisper_state::lrows / row0_copy in step with what the reference's logits buffer would hold after this decode
+void note_rows(const whisper_context & ctx, whisper_state & st, const int8_t * want, int n_tokens) {
+    const int n = ctx.vocab.n_vocab, nosp = ctx.vocab.token_nosp;
+    whisper_state::LogitRow zero; zero.mx = 0.0f; zero.sum = (float) n; zero.nosp = 0.0f;          // a zero-filled row
+    st.lrows.resize((size_t) n_tokens, zero);
+    const bool dev = !st.samp_out.empty();
+    for (int j = 0; j < n_tokens; ++j) {
+        if (!want[j]) continue;
+        whisper_state::LogitRow & r = st.lrows[(size_t) j];
+        if (dev) { const SampOut & o = st.samp_out[(size_t) j]; r.mx = o.raw_max; r.sum = o.raw_sum; r.nosp = o.raw_nosp; }
+        else if (st.logits.size() >= (size_t) (j + 1) * n) {
+            const float * l = st.logits.data() + (size_t) j * n;
+            float mx = -INFINITY; for (int i = 0; i < n; ++i) mx = std::max(mx, l[i]);
+            float sum = 0.0f; for (int i = 0; i < n; ++i) if (l[i] > -INFINITY) sum += expf(l[i] - mx);
+            r.mx = mx; r.sum = sum; r.nosp = l[nosp];
+        }
+        if (j == 0) {
+            st.row0_is_copy = !dev && st.logits.size() >= (size_t) n;
+            if (st.row0_is_copy) st.row0_copy.assign(st.logits.begin(), st.logits.begin() + n);
+        }
+    }
 }
 void account_decode(whisper_state & st, int n_tokens, int64_t dt) {                    // whisper.cpp:2974-2983
     if (n_tokens == 1)      { st.t_decode_us += dt; st.n_decode++; }
@@ -172,7 +187,7 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
         Group::Req r; r.kind = 1; r.ctx = &ctx; r.st = &st; r.tokens = tokens; r.pos = pos; r.seq = seq; r.want = want; r.n = n_tokens; r.samp = samp;
         if (!st.group->submit(r)) return false;
         account_decode(st, n_tokens, r.dt_us);
-        note_row0(st, want);
+        note_rows(ctx, st, want, n_tokens);
         return true;
     }
     PreparedDecode P;
@@ -181,6 +196,7 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
         scripted_attended(st, P, n_tokens);
         st.samp_out.clear(); st.logits.assign((size_t) n_tokens * n_vocab, 0.0f);
         account_decode(st, n_tokens, time_us() - t0);
+        note_rows(ctx, st, want, n_tokens);
         return true;
     }
     if (samp) {
@@ -195,7 +211,7 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
         if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), outs.data())) return false;
     }
     account_decode(st, n_tokens, time_us() - t0);
-    note_row0(st, want);
+    note_rows(ctx, st, want, n_tokens);
     return true;
 }
 

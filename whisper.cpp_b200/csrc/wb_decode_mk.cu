@@ -203,8 +203,9 @@ __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
 // tiles per iteration with their loads issued together.  The 16 warps split K of a tile; every weight block is decoded once and
 // multiplied with both 8-row halves (mma.sync.m16n8k32.s8); partials are reduced through smem.  x: quantised rows in global
 // memory (actq format).  A weight tile is read by the NGc CTAs of the different groups (from L2, prefetched a phase ahead).
+#define MK_FINE(j) do { if (fb >= 0 && blockIdx.x == 0 && threadIdx.x == 0) a.trace[fb + (j)] = clock64(); } while (0)
 template <int WT>
-__device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e) {
+__device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e, int fb = -1) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
     constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
@@ -219,6 +220,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
     const int NGc = (a.n_tok + RG - 1) / RG;
     const int grp = blockIdx.x % NGc, ci = blockIdx.x / NGc, cg = ((int) gridDim.x - grp + NGc - 1) / NGc;   // row group, index / count of its CTAs
     const int t_base = grp * RG, nt = min(RG, a.n_tok - t_base), NH = (nt + 7) >> 3;
+    MK_FINE(0);
     {   // stage the rows of the group
         const int ph = SM_FLAG[4];                               // staging round (mbarrier phase parity)
         __syncthreads();                                         // everybody has read `ph`; the previous users of the buffer are done
@@ -234,7 +236,9 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
         }
         mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
     }
-    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP) {
+    MK_FINE(1);
+    int fine_it = 0;
+    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP, ++fine_it) {
         float acc[TP][2][4];
 #pragma unroll
         for (int j = 0; j < TP; ++j)
@@ -305,6 +309,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
                 }
             }
         }
+        if (fine_it == 0) MK_FINE(2);
         // split-K partials -> smem: red[tile j][warp][row][batch row]
 #pragma unroll
         for (int j = 0; j < TP; ++j)
@@ -313,6 +318,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
 #pragma unroll
                 for (int i = 0; i < 4; ++i) SM_RED[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * RLD + h * 8 + 2 * c + (i & 1)] = acc[j][h][i];
         __syncthreads();
+        if (fine_it == 0) MK_FINE(3);
         for (int o = tid; o < TP * 256; o += MK_THREADS) {        // epilogue: TP tiles x 16 batch rows x 16 weight rows
             const int j = o >> 8, tl = (o & 255) >> 4, rl = o & 15, tile = tile0 + j * cg, row = tile * 16 + rl, t = t_base + tl;
             if (tile < n_tiles && tl < nt && row < N) {
@@ -331,7 +337,9 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
             }
         }
         __syncthreads();                                         // SM_RED is rewritten by the next iteration
+        if (fine_it == 0) MK_FINE(4);
     }
+    MK_FINE(5);
 }
 
 // ---- attention -----------------------------------------------------------------------------------------------------------
@@ -609,7 +617,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
-        mk_gemv<WT>(a, L.qkv, a.actq, e);
+        mk_gemv<WT>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
         MK_SYNC();
         // 3: self-attention (2603-2625) -> quantised rows for the O projection
         if (pf_w) mk_prefetch_w(L.cq);
@@ -618,7 +626,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         // 4: O + residual (2647-2659)
         if (pf_w) mk_prefetch_w(L.co);
         e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.o, a.actq, e);
+        mk_gemv<WT>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
         MK_SYNC();
         // 5: LN -> quantised rows
         mk_lnq<WT>(a, a.x, d, L.lnc_w, L.lnc_b, a.actq);
@@ -626,7 +634,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
-        mk_gemv<WT>(a, L.cq, a.actq, e);
+        mk_gemv<WT>(a, L.cq, a.actq, e, (TRACE && l == 1) ? 2048 + 16 : -1);
         MK_SYNC();
         // 7: cross-attention (2688-2705)
         if (pf_w) mk_prefetch_w(L.fc2);
@@ -634,7 +642,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 8: cross O + residual (2754-2766)
         e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.co, a.actq, e);
+        mk_gemv<WT>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
         MK_SYNC();
         // 9: LN -> quantised rows
         mk_lnq<WT>(a, a.x, d, L.lnm_w, L.lnm_b, a.actq);
@@ -642,13 +650,13 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 10: FC1 + GELU (2770-2794), then the rows are quantised for FC2
         e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.out = a.h;
-        mk_gemv<WT>(a, L.fc1, a.actq, e);
+        mk_gemv<WT>(a, L.fc1, a.actq, e, (TRACE && l == 1) ? 2048 + 32 : -1);
         MK_SYNC();
         mk_q8_rows<WT>(a, a.h, 4 * d, a.hq);
         MK_SYNC();
         // 11: FC2 + residual (2797-2806)
         e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.fc2, a.hq, e);
+        mk_gemv<WT>(a, L.fc2, a.hq, e, (TRACE && l == 1) ? 2048 + 40 : -1);
         MK_SYNC();
     }
     if (a.want_logits) {                                         // final LN + logits (2811-2827)

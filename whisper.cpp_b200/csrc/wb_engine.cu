@@ -154,6 +154,13 @@ void Engine::mk_trace_collect(int n_layer, bool logits) {
         for (int k = 0; k < 24; ++k) mk_trace_sum[k] += (double) (h[1 + 24 * l + k] - h[24 * l + k]) / n_layer;
     if (logits) { mk_trace_sum[24] += (double) (h[ns - 3] - h[ns - 4]); mk_trace_sum[25] += (double) (h[ns - 2] - h[ns - 3]); mk_trace_sum[26] += (double) (h[ns - 1] - h[ns - 2]); }
     mk_trace_sum[27] += (double) (h[ns - 1] - h[0]);
+    {   // sub-phase stamps of the six GEMV phases of layer 1 (MK_FINE)
+        std::vector<long long> f(48);
+        if (cudaMemcpy(f.data(), mk_trace.p + 2048, 48 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (mk_fine.empty()) mk_fine.assign(30, 0.0);
+            for (int g = 0; g < 6; ++g) for (int k = 0; k < 5; ++k) mk_fine[5 * g + k] += (double) (f[8 * g + k + 1] - f[8 * g + k]);
+        }
+    }
     ++mk_trace_n;
 }
 void Engine::mk_trace_dump() {
@@ -168,6 +175,11 @@ void Engine::mk_trace_dump() {
     for (int p = 0; p < 12; ++p) {
         fprintf(f, "%-16s %10.2f %10.2f\n", ph[p], mk_trace_sum[2*p] * us, mk_trace_sum[2*p + 1] * us);
         tot += (mk_trace_sum[2*p] + mk_trace_sum[2*p + 1]) * us;
+    }
+    if (!mk_fine.empty()) {
+        static const char * gn[6] = { "qkv", "o", "cross-q", "cross-o", "fc1", "fc2" };
+        fprintf(f, "GEMV sub-phases, layer 1 (us): stage rows | k-loop of the first iteration | partials->smem + sync | epilogue + sync | remaining iterations\n");
+        for (int g = 0; g < 6; ++g) fprintf(f, "  %-8s %7.2f %7.2f %7.2f %7.2f %7.2f\n", gn[g], mk_fine[5*g] * us, mk_fine[5*g+1] * us, mk_fine[5*g+2] * us, mk_fine[5*g+3] * us, mk_fine[5*g+4] * us);
     }
     fprintf(f, "layer total %.2f us; final ln %.2f + barrier %.2f us, logits %.2f us; whole pass %.1f us\n", tot, mk_trace_sum[24] * us, mk_trace_sum[25] * us, mk_trace_sum[26] * us, mk_trace_sum[27] * us);
     fclose(f);

@@ -402,14 +402,24 @@ void samp_rowinfo(const Vocab & vocab, const whisper_full_params & params, const
     out2[0] = f; out2[1] = d.seek_delta / 2;
 }
 
-// P(no-speech token) of row 0 of the state's logits buffer, with the reference's refresh rule (see the call site)
+// P(no-speech token) exactly as whisper.cpp:7190-7200 computes it: row 0 of the logits buffer, normalised with the log-sum-exp that
+// whisper_compute_logprobs (whisper.cpp:6156-6176) forms against the maximum of the WHOLE buffer (see whisper_state::lrows)
 float row0_nosp(const whisper_context & ctx, const whisper_state & st) {
     const int n = ctx.vocab.n_vocab;
-    if (st.row0_on_device) return st.row0_nosp_dev;
-    if ((int) st.logits.size() < n) return 1.0f / (float) n;             // untouched buffer: all-zero logits
-    std::vector<float> raw(st.logits.begin(), st.logits.begin() + n), lp(n), pr(n);
-    compute_logprobs(raw, n, lp); compute_probs(raw, n, lp, pr);
-    return pr[ctx.vocab.token_nosp];
+    if (st.lrows.empty()) return 1.0f / (float) n;
+    float mx_all = -INFINITY;
+    for (const auto & r : st.lrows) mx_all = std::max(mx_all, r.mx);
+    float lse, l_nosp;
+    if (st.row0_is_copy && (int) st.row0_copy.size() >= n) {                  // the row itself is here: the reference's loop, term by term
+        float s = 0.0f;
+        for (int i = 0; i < n; ++i) if (st.row0_copy[i] > -INFINITY) s += expf(st.row0_copy[i] - mx_all);
+        lse = logf(s) + mx_all; l_nosp = st.row0_copy[ctx.vocab.token_nosp];
+    } else {                                                                   // summary of the row (on-device sampler, or a zero-filled row)
+        const auto & r = st.lrows[0];
+        lse = logf(r.sum * expf(r.mx - mx_all)) + mx_all; l_nosp = r.nosp;     // underflows to log(0) where the reference's sum does
+    }
+    if (l_nosp == -INFINITY) return 0.0f;
+    return expf(l_nosp - lse);
 }
 
 template <typename F> void run_parallel(int n_threads, F && fn) {
@@ -1071,7 +1081,7 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
                 st->decoders[0].rng = std::mt19937(0);
                 st->prompt_past0.clear(); st->prompt_past1.clear();
                 st->t_beg = st->t_last = 0; st->tid_last = 0; st->energy.clear(); st->no_speech_prob = 0.0f;
-                st->logits.clear(); st->row0_on_device = false; st->lang_id = 0;
+                st->logits.clear(); st->lrows.clear(); st->row0_is_copy = false; st->lang_id = 0;
                 st->t_sample_us = st->t_encode_us = st->t_decode_us = st->t_batchd_us = st->t_prompt_us = st->t_mel_us = 0;
                 st->n_sample = st->n_encode = st->n_decode = st->n_batchd = st->n_prompt = st->n_fail_p = st->n_fail_h = 0;
                 wb::tls_pcm_is_device() = (flags & 1) != 0;

@@ -1203,7 +1203,7 @@ k_greedy_sample(const float * __restrict__ logits, int V, const int * __restrict
         o.ptsum = sts;
         if (o.id >= c.beg) { o.tid = o.id; o.pt = o.p; }
         o.nosp_raw = expf(l[c.nosp] - (::logf(raw_sum) + raw_max));
-        o.pad = 0;
+        o.raw_max = raw_max; o.raw_sum = raw_sum; o.raw_nosp = l[c.nosp];
         out[row] = o;
     }
 }

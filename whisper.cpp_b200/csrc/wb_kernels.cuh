@@ -80,7 +80,8 @@ struct SampCfg {                 // uniform for all rows of a pass
     int suppress_blank = 1, no_timestamps = 0;
     int max_initial_tid = -1;          // round(max_initial_ts / precision), -1 = rule disabled
 };
-struct SampOut { int id, tid; float p, plog, pt, ptsum, nosp_raw; int pad; };
+struct SampOut { int id, tid; float p, plog, pt, ptsum, nosp_raw;
+                 float raw_max, raw_sum, raw_nosp; };    // unfiltered row: max logit, sum of exp(l - max), logit of the no-speech token
 // rowinfo[2*r] flags: bit0 is_initial, bit1 last token was a timestamp, bit2 penultimate was (or < 2 tokens), bit3 has_ts,
 // bit4 text tokens disabled by max_tokens; rowinfo[2*r+1] = seek_delta/2.  logits: [n][V] f32 on device (not modified).
 void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st);

@@ -83,8 +83,15 @@ struct whisper_state {
     wb::Decoder decoders[wb::MAX_DECODERS];
     std::vector<float> logits;                 // [n_tokens][n_vocab] of the last decode (rows flagged want_logits are valid)
     std::vector<wb::SampOut> samp_out;         // per row of the last decode when the on-device sampler was used
-    bool  row0_on_device = false;              // row 0 of `logits` was last refreshed by a device-sampled decode: only its no-speech
-    float row0_nosp_dev = 0.0f;                // probability came back (whisper.cpp:7196-7198 reads row 0 of the logits buffer)
+    // What whisper.cpp:7190-7200 reads for the no-speech probability: ROW 0 of the logits buffer, log-sum-exp'ed against the maximum of
+    // the WHOLE buffer (whisper_compute_logprobs takes max_element over all n_tokens rows, whisper.cpp:6160).  A decode resizes that
+    // buffer to n_tokens rows (new rows are zero-filled) and refreshes only the rows it was asked logits for (whisper.cpp:2957-2963), so
+    // row 0 is often stale.  `lrows` mirrors the buffer row by row as (max, sum exp(l - max), no-speech logit) so that the rule can be
+    // followed on the device-sampler path too, where logits never reach the host; `row0_copy` holds row 0 itself when the host wrote it.
+    struct LogitRow { float mx = 0.0f, sum = 0.0f, nosp = 0.0f; };
+    std::vector<LogitRow> lrows;
+    std::vector<float> row0_copy;
+    bool row0_is_copy = false;
     std::vector<wb::Segment> result_all;
     std::vector<whisper_token> prompt_past0, prompt_past1;
     int   lang_id = 0;

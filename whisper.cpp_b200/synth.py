@@ -28,7 +28,8 @@ CONFIGS = {
     # the large-v3 width (d = 1280, 20 heads, 128 mels, 51866 ids) at a depth the CPU reference finishes in seconds
     "large-v3-4l":    (51866, 1500, 1280, 20, 4, 448, 1280, 20, 4, 128),
     # reduced shapes for parity tests the CPU reference finishes in seconds
-    "test-2l.en":     (51864, 1500, 384, 6, 2, 448, 384, 6, 2, 80),
+    "test-2l.en":     (51864, 1500, 384, 6, 2, 448, 384, 6, 2, 80),     # NB: 2 text layers + an English vocabulary = "distilled": whisper_full forces no_timestamps (whisper.cpp:7078-7084)
+    "test-3l.en":     (51864, 1500, 384, 6, 2, 448, 384, 6, 3, 80),     # 3 text layers: timestamps stay on
     "test-2l-512.en": (51864, 1500, 512, 8, 2, 448, 512, 8, 2, 80),
     "test-2l-multi":  (51866, 1500, 256, 4, 2, 448, 256, 4, 2, 128),
 }
