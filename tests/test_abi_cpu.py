@@ -32,6 +32,14 @@ def test_same_whisper_symbols_as_reference():
     assert mine == theirs
 
 
+def test_nothing_else_is_exported():
+    """linker version script (whisper.cpp_b200/exports.map): no libstdc++ template instantiations or CUDA runtime symbols leak out"""
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    stray = [n for n in names if not (n.startswith("whisper_") or n.startswith("wb200_"))]
+    assert not stray, stray[:10]
+
+
 def test_struct_sizes_match_reference(ref):
     assert C.sizeof(FullParams) == ref.wref_sizeof_full_params() == 304
     assert C.sizeof(ContextParams) == ref.wref_sizeof_context_params() == 48
