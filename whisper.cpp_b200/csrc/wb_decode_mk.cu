@@ -21,6 +21,7 @@
 // loads), no 64-bit divisions in loops, approximate reciprocals where they only feed a rounding, no register moves of
 // in-flight loads, whole 32-byte sectors per load instruction, bulk copies instead of register staging for anything > 16 KB.
 #include <cmath>
+#include <type_traits>
 #include "wb_decode_mk.cuh"
 #include "wb_common.h"
 #include "wb_dev.cuh"
@@ -185,6 +186,7 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
 struct MkEpi {
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
+    uint8_t * qout = nullptr;            // PAIR epilogue: quantised rows [64][N] (+ block scales) for the next GEMV
 };
 
 // L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per grid
@@ -196,59 +198,33 @@ __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
         l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * tile_bytes, tile_bytes);
 }
 
-// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n].
-// With up to 64 rows the activations (64 x K bytes) outweigh a weight tile (16 x K x ~0.7 bytes), so the work is cut by ROW GROUP
-// first: CTA c serves the 16 rows of group c % NGc (8 rows for the widest F16 matrices), stages only those rows (one TMA bulk copy
-// per row + one for its block scales, completion on an mbarrier) and walks the weight tiles its group-mates do not take, four
-// tiles per iteration with their loads issued together.  The 16 warps split K of a tile; every weight block is decoded once and
-// multiplied with both 8-row halves (mma.sync.m16n8k32.s8); partials are reduced through smem.  x: quantised rows in global
-// memory (actq format).  A weight tile is read by the NGc CTAs of the different groups (from L2, prefetched a phase ahead).
 #define MK_FINE(j) do { if (fb >= 0 && blockIdx.x == 0 && threadIdx.x == 0) a.trace[fb + (j)] = clock64(); } while (0)
-template <int WT>
-__device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e, int fb = -1) {
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// k-loop of one iteration of mk_gemv for NV valid tile slots (compile-time: predicated slots made the register allocator spill);
+// leaves the split-K partials in SM_RED
+template <int WT, int NV, int TU>
+__device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * wbase, int tile0, int tstep, int nrec, int nb, int SW, int nt, int NH, bool & staged, int fb) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
-    constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
-    constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
-    constexpr int UB = 3;                                        // records whose loads are issued together
-    constexpr int TP = MK_TP;                                    // tiles per iteration
-    constexpr int RLD = 17;                                      // row stride of the reduction buffer (16 batch rows + pad)
-    const int N = W.N, K = W.K;
+    constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;
+    constexpr int UB = 3;
+    constexpr int RLD = 17;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
-    const int n_tiles = (N + 15) >> 4, nrec = K / RK, nb = K >> 5;
-    const int rowb = (WT == WT_F16) ? K * 2 : K, SW = (rowb >> 2) + 4;
-    const int RG = (16 * (rowb + 16) <= MK_MAXTOK * (MK_ROWB + 16)) ? 16 : 8;   // rows per CTA (what fits the staging area)
-    const int NGc = (a.n_tok + RG - 1) / RG;
-    const int grp = blockIdx.x % NGc, ci = blockIdx.x / NGc, cg = ((int) gridDim.x - grp + NGc - 1) / NGc;   // row group, index / count of its CTAs
-    const int t_base = grp * RG, nt = min(RG, a.n_tok - t_base), NH = (nt + 7) >> 3;
-    MK_FINE(0);
-    {   // stage the rows of the group
-        const int ph = SM_FLAG[4];                               // staging round (mbarrier phase parity)
-        __syncthreads();                                         // everybody has read `ph`; the previous users of the buffer are done
-        if (tid == 0) {
-            SM_FLAG[4] = ph + 1;
-            mbar_arrive_expect_tx(SM_MBAR, (uint32_t) nt * (uint32_t) (rowb + (WT == WT_F16 ? 0 : nb * 4)));
-        }
-        if (tid < nt) {
-            asm volatile("fence.proxy.async;" ::: "memory");     // rows were written with ordinary stores (by other CTAs, before the grid barrier)
-            bulk_g2s(SM_XQ + tid * SW, x + (size_t) (t_base + tid) * rowb, (uint32_t) rowb, SM_MBAR);
-            if (WT != WT_F16)
-                bulk_g2s(SM_XD + tid * nb, reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) (t_base + tid) * nb, (uint32_t) nb * 4, SM_MBAR);
-        }
-        mbar_wait(SM_MBAR, (uint32_t) ph & 1u);
-    }
-    MK_FINE(1);
-    int fine_it = 0;
-    for (int tile0 = ci; tile0 < n_tiles; tile0 += cg * TP, ++fine_it) {
-        float acc[TP][2][4];
+    float acc[NV][2][4];
 #pragma unroll
-        for (int j = 0; j < TP; ++j)
+    for (int j = 0; j < NV; ++j)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) { acc[j][h][0] = acc[j][h][1] = acc[j][h][2] = acc[j][h][3] = 0.0f; }
-        for (int kb = warp; kb < nrec; kb += MK_WARPS * UB) {
-            uint4 wq[TP][UB]; uint2 wh[TP][UB]; uint32_t wd[TP][UB];
+        for (int h = 0; h < 2; ++h) { acc[j][h][0] = acc[j][h][1] = acc[j][h][2] = acc[j][h][3] = 0.0f; }
+    for (int kb0 = 0; kb0 < nrec; kb0 += MK_WARPS * UB) {    // every warp walks the same trip count (the staging wait below is a block barrier)
+        const int kb = kb0 + warp;
+        uint4 wq[NV][UB]; uint2 wh[NV][UB]; uint32_t wd[NV][UB];
 #pragma unroll
-            for (int j = 0; j < TP; ++j) {
-                const uint8_t * tb = reinterpret_cast<const uint8_t *>(W.base) + (size_t) min(tile0 + j * cg, n_tiles - 1) * nrec * REC;
+        for (int j = 0; j < NV; ++j) {
+            if (kb < nrec) {
+                const uint8_t * tb = wbase + (size_t) ((tile0 + (j / TU) * tstep) * TU + j % TU) * nrec * REC;
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
                     const uint8_t * rec = tb + (size_t) min(kb + u * MK_WARPS, nrec - 1) * REC;
@@ -258,21 +234,24 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
                     if (WT != WT_F16)  wd[j][u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
                 }
             }
+        }
+        if (!staged) { cp_wait_all(); __syncthreads(); staged = true; MK_FINE(1); }       // the rows have landed (weights are in flight)
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int b = kb + u * MK_WARPS;
-                if (b < nrec) {
-                    uint32_t bf[2][2]; float dx[2][2];
+        for (int u = 0; u < UB; ++u) {
+            const int b = kb + u * MK_WARPS;
+            if (b < nrec) {
+                uint32_t bf[2][2]; float dx[2][2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const bool ok = h * 8 + g < nt;
-                        bf[h][0] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + c] : 0u;
-                        bf[h][1] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + 4 + c] : 0u;
-                        dx[h][0] = dx[h][1] = 0.0f;
-                        if (WT != WT_F16) { dx[h][0] = SM_XD[min(h * 8 + 2 * c, nt - 1) * nb + b]; dx[h][1] = SM_XD[min(h * 8 + 2 * c + 1, nt - 1) * nb + b]; }
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    const bool ok = h * 8 + g < nt;
+                    bf[h][0] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + c] : 0u;
+                    bf[h][1] = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + 4 + c] : 0u;
+                    dx[h][0] = dx[h][1] = 0.0f;
+                    if (WT != WT_F16) { dx[h][0] = SM_XD[min(h * 8 + 2 * c, nt - 1) * nb + b]; dx[h][1] = SM_XD[min(h * 8 + 2 * c + 1, nt - 1) * nb + b]; }
+                }
 #pragma unroll
-                    for (int j = 0; j < TP; ++j) {
+                for (int j = 0; j < NV; ++j) {
+                    {
                         uint32_t af[4];
                         float dw0 = 0.0f, dw1 = 0.0f;
                         if (WT == WT_F16 || WT == WT_Q8_0) { af[0] = wq[j][u].x; af[1] = wq[j][u].y; af[2] = wq[j][u].z; af[3] = wq[j][u].w; }
@@ -309,25 +288,118 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
                 }
             }
         }
-        if (fine_it == 0) MK_FINE(2);
-        // split-K partials -> smem: red[tile j][warp][row][batch row]
+    }
+    if (!staged) { cp_wait_all(); __syncthreads(); staged = true; }
+    // split-K partials -> smem: red[tile slot j][warp][row][batch row]
 #pragma unroll
-        for (int j = 0; j < TP; ++j)
+    for (int j = 0; j < NV; ++j)
+        {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) SM_RED[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * RLD + h * 8 + 2 * c + (i & 1)] = acc[j][h][i];
-        __syncthreads();
-        if (fine_it == 0) MK_FINE(3);
-        for (int o = tid; o < TP * 256; o += MK_THREADS) {        // epilogue: TP tiles x 16 batch rows x 16 weight rows
-            const int j = o >> 8, tl = (o & 255) >> 4, rl = o & 15, tile = tile0 + j * cg, row = tile * 16 + rl, t = t_base + tl;
-            if (tile < n_tiles && tl < nt && row < N) {
-                float v = 0.0f;
+        }
+}
+
+// y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n].
+// With up to 64 rows the activations (64 x K bytes) outweigh a weight tile (16 x K x ~0.7 bytes), so the work is cut by ROW GROUP
+// first: CTA c serves the 16 rows of group c % NGc (8 rows for the widest F16 matrices), stages only those rows (cp.async, every
+// thread a few 16-byte pieces) and walks the weight tiles its group-mates do not take, up to four tiles per iteration with their
+// loads issued together.  The 16 warps split K of a tile; every weight block is decoded once and multiplied with both 8-row halves
+// (mma.sync.m16n8k32.s8); partials are reduced through smem.  x: quantised rows in global memory (actq format).  A weight tile is
+// read by the NGc CTAs of the different groups (from L2, prefetched a phase ahead).
+// Latency hiding inside a phase (each phase is a chain barrier -> stage -> weights -> reduce -> epilogue of a few microseconds):
+// the weight loads of the first iteration are issued BEFORE the staged rows are waited for, the epilogue's bias / scale / residual
+// operands are fetched before the k-loop, tiles are dealt out evenly over the iterations and slots without a tile cost nothing.
+// PAIR (FC1): tiles are dealt out in pairs = 32 consecutive output features, and the epilogue writes GELU(y) straight into the
+// quantised-row format FC2 consumes (one warp = one Q8_0 block of one row) -- no f32 round trip, no extra phase.
+template <int WT, bool PAIR>
+__device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uint8_t * x, const MkEpi & e, int fb = -1) {
+    constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
+    constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;             // bytes of the qs part of a record
+    constexpr int RK = (WT == WT_F16) ? 16 : 32;                 // K values per record
+    constexpr int UB = 3;                                        // records whose loads are issued together
+    constexpr int TP = MK_TP;                                    // tile slots per iteration
+    constexpr int TU = PAIR ? 2 : 1;                             // tiles per unit of distribution
+    constexpr int RLD = 17;                                      // row stride of the reduction buffer (16 batch rows + pad)
+    const int N = W.N, K = W.K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    const int n_tiles = (N + 15) >> 4, nrec = K / RK, nb = K >> 5;
+    const int rowb = (WT == WT_F16) ? K * 2 : K, SW = (rowb >> 2) + 4;
+    const int RG = (16 * (rowb + 16) <= MK_MAXTOK * (MK_ROWB + 16)) ? 16 : 8;   // rows per CTA (what fits the staging area)
+    const int NGc = (a.n_tok + RG - 1) / RG;
+    const int grp = blockIdx.x % NGc, ci = blockIdx.x / NGc, cg = ((int) gridDim.x - grp + NGc - 1) / NGc;   // row group, index / count of its CTAs
+    const int t_base = grp * RG, nt = min(RG, a.n_tok - t_base), NH = (nt + 7) >> 3;
+    const int n_units = n_tiles / TU;                            // PAIR: N is a multiple of 32
+    const int upc = ci < n_units ? (n_units - ci + cg - 1) / cg : 0;            // units of this CTA: ci, ci + cg, ...
+    const int n_it = (upc * TU + TP - 1) / TP, upi = n_it ? (upc + n_it - 1) / n_it : 0;   // iterations, units per iteration (even split)
+    MK_FINE(0);
+    __syncthreads();                                             // the previous users of the staging area are done
+    {   // stage the rows of the group: rows t_base .. t_base+nt-1 are contiguous in global memory
+        const int cpr = rowb >> 4, total = nt * cpr;
+        const uint32_t sx = smem_u32(SM_XQ);
+        const uint8_t * src = x + (size_t) t_base * rowb;
+        for (int q = tid; q < total; q += MK_THREADS) {
+            const int r = q / cpr, cc = q - r * cpr;
+            cp_async16(sx + (uint32_t) (r * SW * 4 + cc * 16), src + (size_t) q * 16);
+        }
+        if (WT != WT_F16) {
+            const int sc = (nt * nb) >> 2;                       // 16-byte pieces of the block scales (nb is a multiple of 4)
+            const uint32_t sd = smem_u32(SM_XD);
+            const float * ssrc = reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) t_base * nb;
+            for (int q = tid; q < sc; q += MK_THREADS) cp_async16(sd + (uint32_t) q * 16, ssrc + (size_t) q * 4);
+        }
+        cp_commit();
+    }
+    bool staged = false;
+    for (int it = 0; it < n_it; ++it) {
+        const int u0 = it * upi, nv = TU * (min(upc, u0 + upi) - u0);           // valid tile slots of this iteration (CTA-uniform)
+        {
+            const uint8_t * wbase = reinterpret_cast<const uint8_t *>(W.base);
+            const int unit0 = ci + u0 * cg;                      // slot j holds tile (unit0 + (j / TU) * cg) * TU + j % TU
+            switch (nv) {
+                case 1: if (!PAIR) { mk_gemv_kloop<WT, 1, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break; }
+                case 2: mk_gemv_kloop<WT, 2, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break;
+                case 3: if (!PAIR) { mk_gemv_kloop<WT, 3, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break; }
+                default: mk_gemv_kloop<WT, 4, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break;
+            }
+        }
+        if (it == 0) MK_FINE(2);
+        float pb[2], ps[2], pr[2];
+        // epilogue operands of this thread's (at most two) outputs, fetched before the partials go through smem (their latency hides behind the reduction)
 #pragma unroll
-                for (int w = 0; w < MK_WARPS; ++w) v += SM_RED[((j * MK_WARPS + w) * 16 + rl) * RLD + tl];
-                v = (v + (e.bias ? __ldg(e.bias + row) : 0.0f)) * (e.scale ? __ldg(e.scale + row) : 1.0f);
+        for (int i = 0; i < 2; ++i) {
+            int jj, tl, rl;
+            if (PAIR) { const int idx = warp + MK_WARPS * i; jj = (idx >> 4) * 2 + (lane >> 4); tl = idx & 15; rl = lane & 15; }
+            else      { const int o = tid + MK_THREADS * i; jj = o >> 8; tl = (o & 255) >> 4; rl = o & 15; }
+            const int row = ((ci + (u0 + jj / TU) * cg) * TU + jj % TU) * 16 + rl;
+            const bool ok = jj < nv && tl < nt && row < N;
+            pb[i] = (ok && e.bias) ? __ldg(e.bias + row) : 0.0f;
+            ps[i] = (ok && e.scale) ? __ldg(e.scale + row) : 1.0f;
+            pr[i] = (ok && e.res) ? __ldcg(e.res + (size_t) (t_base + tl) * N + row) : 0.0f;
+        }
+        __syncthreads();
+        if (it == 0) MK_FINE(3);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                            // epilogue: up to TP tiles x 16 batch rows x 16 weight rows, two outputs per thread
+            int jj, tl, rl;
+            if (PAIR) { const int idx = warp + MK_WARPS * i; jj = (idx >> 4) * 2 + (lane >> 4); tl = idx & 15; rl = lane & 15; }
+            else      { const int o = tid + MK_THREADS * i; jj = o >> 8; tl = (o & 255) >> 4; rl = o & 15; }
+            const int row = ((ci + (u0 + jj / TU) * cg) * TU + jj % TU) * 16 + rl, t = t_base + tl;
+            const bool ok = jj < nv && tl < nt && row < N;
+            float v = 0.0f;
+            if (ok) {
+#pragma unroll
+                for (int w = 0; w < MK_WARPS; ++w) v += SM_RED[((jj * MK_WARPS + w) * 16 + rl) * RLD + tl];
+                v = (v + pb[i]) * ps[i];
                 if (e.act == 1) v = gelu_ref_f16(v);
-                if (e.res) v += __ldcg(e.res + (size_t) t * N + row);
+                v += pr[i];
+            }
+            if (PAIR) {
+                // (row slot pair, token) is warp-uniform: the 32 lanes hold one Q8_0 block of the FC2 input row t (features row0 .. row0+31)
+                const int idx = warp + MK_WARPS * i;
+                if ((idx >> 4) * 2 < nv && tl < nt) mk_store_q<WT>(e.qout, N, t, row - lane, lane, v);
+            } else if (ok) {
                 if (e.out) e.out[(size_t) t * N + row] = v;
                 if (e.kc && row >= e.kv_d) {
                     const size_t cell = a.cell[t];
@@ -337,8 +409,9 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
             }
         }
         __syncthreads();                                         // SM_RED is rewritten by the next iteration
-        if (fine_it == 0) MK_FINE(4);
+        if (it == 0) MK_FINE(4);
     }
+    if (!staged) { cp_wait_all(); __syncthreads(); }             // a CTA without tiles still drains its copies before the area is reused
     MK_FINE(5);
 }
 
@@ -491,8 +564,6 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
 constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
 static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
 
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
 
 template <int WT>
@@ -617,7 +688,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
-        mk_gemv<WT>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
+        mk_gemv<WT, false>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
         MK_SYNC();
         // 3: self-attention (2603-2625) -> quantised rows for the O projection
         if (pf_w) mk_prefetch_w(L.cq);
@@ -626,7 +697,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         // 4: O + residual (2647-2659)
         if (pf_w) mk_prefetch_w(L.co);
         e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
+        mk_gemv<WT, false>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
         MK_SYNC();
         // 5: LN -> quantised rows
         mk_lnq<WT>(a, a.x, d, L.lnc_w, L.lnc_b, a.actq);
@@ -634,7 +705,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
-        mk_gemv<WT>(a, L.cq, a.actq, e, (TRACE && l == 1) ? 2048 + 16 : -1);
+        mk_gemv<WT, false>(a, L.cq, a.actq, e, (TRACE && l == 1) ? 2048 + 16 : -1);
         MK_SYNC();
         // 7: cross-attention (2688-2705)
         if (pf_w) mk_prefetch_w(L.fc2);
@@ -642,33 +713,32 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         MK_SYNC();
         // 8: cross O + residual (2754-2766)
         e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
+        mk_gemv<WT, false>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
         MK_SYNC();
         // 9: LN -> quantised rows
         mk_lnq<WT>(a, a.x, d, L.lnm_w, L.lnm_b, a.actq);
         if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
         MK_SYNC();
         // 10: FC1 + GELU (2770-2794), then the rows are quantised for FC2
-        e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.out = a.h;
-        mk_gemv<WT>(a, L.fc1, a.actq, e, (TRACE && l == 1) ? 2048 + 32 : -1);
-        MK_SYNC();
-        mk_q8_rows<WT>(a, a.h, 4 * d, a.hq);
+        e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.qout = a.hq;
+        mk_gemv<WT, true>(a, L.fc1, a.actq, e, (TRACE && l == 1) ? 2048 + 32 : -1);
+        MK_STAMP(); MK_STAMP();                                  // (trace slot of the former FC1 -> Q8_0 phase)
         MK_SYNC();
         // 11: FC2 + residual (2797-2806)
         e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
-        mk_gemv<WT>(a, L.fc2, a.hq, e, (TRACE && l == 1) ? 2048 + 40 : -1);
+        mk_gemv<WT, false>(a, L.fc2, a.hq, e, (TRACE && l == 1) ? 2048 + 40 : -1);
         MK_SYNC();
     }
     if (a.want_logits) {                                         // final LN + logits (2811-2827)
         mk_lnq<WT>(a, a.x, d, a.lnf_w, a.lnf_b, a.actq);
         MK_SYNC();
         MkEpi e; e.out = a.logits;
-        mk_gemv<WT>(a, a.te, a.actq, e);
+        mk_gemv<WT, false>(a, a.te, a.actq, e);
         MK_STAMP();
     }
 }
 
-int mk_barriers(int n_layer, bool want_logits) { return 12 * n_layer + (want_logits ? 1 : 0); }
+int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
 size_t mk_smem_bytes(int, int) { return MK_SMEM; }
 int mk_max_rows() { return MK_MAXTOK; }
