@@ -11,11 +11,13 @@ sharpens the softmax (final LayerNorm gain x100), so every decision has a margin
 CPU (reference only) such that the reference's own smallest top-2 margin over the whole transcript is >= 2e-3 sigma, the transcript uses
 >= 40 distinct ids, and -- for attn > 0 -- another audio clip changes the transcript (the audio path is attenuated, not cut).
 
-  F16,  attn 1e-3 : reference noise across thread counts 1.4e-4 sigma
-  Q5_0, attn 1e-4 : int8 activation blocks make tiny perturbations occasionally jump (one rounding flip = up to 1e-2 sigma); seed 1 is
-                    the instance on which the reference agrees with itself for 1 / 4 / 8 threads
-  Q5_0, attn 0    : the value path removed; everything else (token + position embeddings, 2 x (LN, int8 GEMVs, GELU table), logits
-                    GEMV, filters, samplers, KV bookkeeping, seek loop) is live
+  F16,  attn 1e-3 : reference noise across thread counts 1.4e-4 sigma; seeds 3 and 16: the reference gives the same transcript on 1 / 4 / 8
+                    threads (greedy and beam), 427 .. 525 tokens, 6 .. 8 segments with real timestamp tokens, ragged windows
+  Q5_0, attn 0    : the value path removed; everything else (token + position embeddings, 3 x (LN, int8 GEMVs, GELU table), logits
+                    GEMV, filters, samplers, KV bookkeeping, timestamp rules, seek loop) is live; exact
+  Q5_0, attn 1e-4 : int8 activation blocks make tiny perturbations occasionally jump (one rounding flip = up to 1e-2 sigma): in a search
+                    over 30 seeds the reference never reproduced its own 4-thread transcript on 1 thread.  Asserted instead: this engine
+                    follows the 4-thread reference at least as far as the 1-thread reference does
 Everything that is not attention is mirrored arithmetic (Q8_0 activation blocks, integer block dots, f16 GELU table), so identity is
 expected and asserted token for token, with segment times.
 """
@@ -31,13 +33,15 @@ from e2e_util import Side, synth
 pytestmark = pytest.mark.gpu
 vp = C.c_void_p
 
-CASES = [(F16, 10, 1e-3), (F16, 16, 1e-3), (Q5_0, 1, 1e-4), (Q5_0, 2, 0.0)]
+# (weight type, model seed, attenuation of the attention value path, exact?)  -- the model is "test-3l.en": three text layers, so that
+# whisper_full keeps timestamps on (two text layers + an English vocabulary count as "distilled" and force no_timestamps)
+CASES = [(F16, 3, 1e-3, True), (F16, 16, 1e-3, True), (Q5_0, 0, 0.0, True), (Q5_0, 7, 1e-4, False)]
 
 
 def _model(tmp_path, wt, seed, attn):
     stub = os.path.join(DATA_DIR, "for-tests-ggml-tiny.en.bin")
     path = str(tmp_path / ("cond-%d-%d-%g.bin" % (wt, seed, attn)))
-    synth.write_model(path, "test-2l.en", wt, seed=seed, vocab_from=stub, scale=lambda n: synth.conditioned(n, attn, 100.0))
+    synth.write_model(path, "test-3l.en", wt, seed=seed, vocab_from=stub, scale=lambda n: synth.conditioned(n, attn, 100.0))
     return path
 
 
@@ -54,8 +58,15 @@ def _run(S, pcm, strategy, n_threads=4):
     return segs
 
 
-@pytest.mark.parametrize("wt,seed,attn", CASES)
-def test_free_running_transcripts_are_token_identical(lib, ref, tmp_path, wt, seed, attn):
+def _common(a, b):
+    k = 0
+    while k < min(len(a), len(b)) and a[k] == b[k]:
+        k += 1
+    return k
+
+
+@pytest.mark.parametrize("wt,seed,attn,exact", CASES)
+def test_free_running_transcripts_are_token_identical(lib, ref, tmp_path, wt, seed, attn, exact):
     path = _model(tmp_path, wt, seed, attn)
     pcm = synth.synth_audio(seed=500 + seed, seconds=60.0)
     A = Side(lib, path, False); B = Side(ref, path, True)
@@ -70,8 +81,18 @@ def test_free_running_transcripts_are_token_identical(lib, ref, tmp_path, wt, se
                 k += 1
             print("%s: %d tokens (reference %d), %d distinct, identical prefix %d" % (name, len(ta), len(tb), len(set(tb)), k))
             assert len(tb) >= 200
-            assert ta == tb, (name, k, ta[max(0, k - 3):k + 3], tb[max(0, k - 3):k + 3])
-            assert [(s[0], s[1]) for s in sa] == [(s[0], s[1]) for s in sb]
+            if exact:
+                assert ta == tb, (name, k, ta[max(0, k - 3):k + 3], tb[max(0, k - 3):k + 3])
+                assert [(s[0], s[1]) for s in sa] == [(s[0], s[1]) for s in sb]
+            else:
+                # Q5_0 with a live attention path: the reference does not reproduce ITS OWN transcript when it runs on 1 thread instead of 4
+                # (int8 activation blocks turn a 1e-7 difference in the F16-accumulated attention output into an occasional 1e-2 sigma
+                # jump).  The yardstick is the reference itself: this engine must stay with the 4-thread reference at least as long as
+                # the 1-thread reference does.
+                s1 = _run(B, pcm, strategy, n_threads=1)
+                t1 = [t for s in s1 for t in s[2]]
+                print("   reference 1 thread vs 4 threads: identical prefix %d" % _common(t1, tb))
+                assert k >= min(_common(t1, tb), len(tb)), (name, k, _common(t1, tb))
         if attn > 0:                                     # the audio path is attenuated, not cut: another clip changes the transcript
             other = synth.synth_audio(seed=9000 + seed, seconds=60.0)
             assert _run(A, other, 0) != _run(A, pcm, 0)

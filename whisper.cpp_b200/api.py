@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwhisper_b200.so")
+LIB_PATH = os.environ.get("WB200_LIB") or os.path.join(HERE, "libwhisper_b200.so")      # WB200_LIB: A/B builds of the same ABI
 
 
 # by-value ABI structs (whisper.h:116-151, 487-591)

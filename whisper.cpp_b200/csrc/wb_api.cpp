@@ -938,6 +938,11 @@ WB_EXPORT int64_t wb200_read_tensor(struct whisper_state * st, int which, float 
         std::vector<__half> tmp((size_t) n);
         const __half * src = E.kv_cross.p + (size_t) st->slot * 2 * n + (which == 4 ? n : 0);
         if (cudaMemcpy(tmp.data(), src, (size_t) n * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+        if (E.use_mk && mk_cross_head_major()) {                          // head-major in HBM: hand out the [Lt][Tp][d] view the tests expect
+            const int Tp = E.Tp_max;
+            for (int l = 0; l < Lt; ++l) for (int hh = 0; hh < d / 64; ++hh) for (int k = 0; k < Tp; ++k) for (int f = 0; f < 64; ++f)
+                out[((size_t) l * Tp + k) * d + hh * 64 + f] = __half2float(tmp[(((size_t) l * (d / 64) + hh) * Tp + k) * 64 + f]);
+        } else
         for (int64_t i = 0; i < n; ++i) out[i] = __half2float(tmp[(size_t) i]);
         return n;
     }

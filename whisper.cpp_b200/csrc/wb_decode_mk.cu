@@ -207,7 +207,7 @@ __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;
 // k-loop of one iteration of mk_gemv for NV valid tile slots (compile-time: predicated slots made the register allocator spill);
 // leaves the split-K partials in SM_RED
 template <int WT, int NV, int TU>
-__device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * wbase, int tile0, int tstep, int nrec, int nb, int SW, int nt, int NH, bool & staged, int fb) {
+__device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * wbase, int tile0, int tstep, int nrec, int nb, int SW, int nt, int NH, bool & staged, uint32_t stage_parity, int fb) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;
     constexpr int UB = 3;
@@ -218,12 +218,11 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
     for (int j = 0; j < NV; ++j)
 #pragma unroll
         for (int h = 0; h < 2; ++h) { acc[j][h][0] = acc[j][h][1] = acc[j][h][2] = acc[j][h][3] = 0.0f; }
-    for (int kb0 = 0; kb0 < nrec; kb0 += MK_WARPS * UB) {    // every warp walks the same trip count (the staging wait below is a block barrier)
-        const int kb = kb0 + warp;
+    for (int kb = warp; kb < nrec; kb += MK_WARPS * UB) {
         uint4 wq[NV][UB]; uint2 wh[NV][UB]; uint32_t wd[NV][UB];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (kb < nrec) {
+            {
                 const uint8_t * tb = wbase + (size_t) ((tile0 + (j / TU) * tstep) * TU + j % TU) * nrec * REC;
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
@@ -235,7 +234,7 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
                 }
             }
         }
-        if (!staged) { cp_wait_all(); __syncthreads(); staged = true; MK_FINE(1); }       // the rows have landed (weights are in flight)
+        if (!staged) { mbar_wait(SM_MBAR, stage_parity); staged = true; MK_FINE(1); }     // the rows have landed (this warp's weights are in flight)
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int b = kb + u * MK_WARPS;
@@ -289,7 +288,7 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
             }
         }
     }
-    if (!staged) { cp_wait_all(); __syncthreads(); staged = true; }
+    if (!staged) { mbar_wait(SM_MBAR, stage_parity); staged = true; }
     // split-K partials -> smem: red[tile slot j][warp][row][batch row]
 #pragma unroll
     for (int j = 0; j < NV; ++j)
@@ -303,8 +302,8 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
 
 // y[t][n] = act((W[n,:] . x[t,:] + bias[n]) * scale[n]) + res[t][n].
 // With up to 64 rows the activations (64 x K bytes) outweigh a weight tile (16 x K x ~0.7 bytes), so the work is cut by ROW GROUP
-// first: CTA c serves the 16 rows of group c % NGc (8 rows for the widest F16 matrices), stages only those rows (cp.async, every
-// thread a few 16-byte pieces) and walks the weight tiles its group-mates do not take, up to four tiles per iteration with their
+// first: CTA c serves the 16 rows of group c % NGc (8 rows for the widest F16 matrices), stages only those rows (one TMA bulk copy
+// per row + one for its block scales) and walks the weight tiles its group-mates do not take, up to four tiles per iteration with their
 // loads issued together.  The 16 warps split K of a tile; every weight block is decoded once and multiplied with both 8-row halves
 // (mma.sync.m16n8k32.s8); partials are reduced through smem.  x: quantised rows in global memory (actq format).  A weight tile is
 // read by the NGc CTAs of the different groups (from L2, prefetched a phase ahead).
@@ -334,22 +333,22 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
     const int upc = ci < n_units ? (n_units - ci + cg - 1) / cg : 0;            // units of this CTA: ci, ci + cg, ...
     const int n_it = (upc * TU + TP - 1) / TP, upi = n_it ? (upc + n_it - 1) / n_it : 0;   // iterations, units per iteration (even split)
     MK_FINE(0);
-    __syncthreads();                                             // the previous users of the staging area are done
-    {   // stage the rows of the group: rows t_base .. t_base+nt-1 are contiguous in global memory
-        const int cpr = rowb >> 4, total = nt * cpr;
-        const uint32_t sx = smem_u32(SM_XQ);
-        const uint8_t * src = x + (size_t) t_base * rowb;
-        for (int q = tid; q < total; q += MK_THREADS) {
-            const int r = q / cpr, cc = q - r * cpr;
-            cp_async16(sx + (uint32_t) (r * SW * 4 + cc * 16), src + (size_t) q * 16);
+    uint32_t stage_parity;
+    {   // stage the rows of the group: one TMA bulk copy per row (+ one for its block scales), completion on an mbarrier that every
+        // thread waits for on its own, after it has issued its first weight loads
+        const int ph = SM_FLAG[4];                               // staging round (mbarrier phase parity)
+        __syncthreads();                                         // everybody has read `ph`; the previous users of the buffer are done
+        stage_parity = (uint32_t) ph & 1u;
+        if (tid == 0) {
+            SM_FLAG[4] = ph + 1;
+            mbar_arrive_expect_tx(SM_MBAR, (uint32_t) nt * (uint32_t) (rowb + (WT == WT_F16 ? 0 : nb * 4)));
         }
-        if (WT != WT_F16) {
-            const int sc = (nt * nb) >> 2;                       // 16-byte pieces of the block scales (nb is a multiple of 4)
-            const uint32_t sd = smem_u32(SM_XD);
-            const float * ssrc = reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) t_base * nb;
-            for (int q = tid; q < sc; q += MK_THREADS) cp_async16(sd + (uint32_t) q * 16, ssrc + (size_t) q * 4);
+        if (tid < nt) {
+            asm volatile("fence.proxy.async;" ::: "memory");     // rows were written with ordinary stores (by other CTAs, before the grid barrier)
+            bulk_g2s(SM_XQ + tid * SW, x + (size_t) (t_base + tid) * rowb, (uint32_t) rowb, SM_MBAR);
+            if (WT != WT_F16)
+                bulk_g2s(SM_XD + tid * nb, reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) (t_base + tid) * nb, (uint32_t) nb * 4, SM_MBAR);
         }
-        cp_commit();
     }
     bool staged = false;
     for (int it = 0; it < n_it; ++it) {
@@ -358,10 +357,10 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
             const uint8_t * wbase = reinterpret_cast<const uint8_t *>(W.base);
             const int unit0 = ci + u0 * cg;                      // slot j holds tile (unit0 + (j / TU) * cg) * TU + j % TU
             switch (nv) {
-                case 1: if (!PAIR) { mk_gemv_kloop<WT, 1, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break; }
-                case 2: mk_gemv_kloop<WT, 2, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break;
-                case 3: if (!PAIR) { mk_gemv_kloop<WT, 3, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break; }
-                default: mk_gemv_kloop<WT, 4, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, fb); break;
+                case 1: if (!PAIR) { mk_gemv_kloop<WT, 1, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break; }
+                case 2: mk_gemv_kloop<WT, 2, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break;
+                case 3: if (!PAIR) { mk_gemv_kloop<WT, 3, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break; }
+                default: mk_gemv_kloop<WT, 4, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break;
             }
         }
         if (it == 0) MK_FINE(2);
@@ -411,7 +410,7 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
         __syncthreads();                                         // SM_RED is rewritten by the next iteration
         if (it == 0) MK_FINE(4);
     }
-    if (!staged) { cp_wait_all(); __syncthreads(); }             // a CTA without tiles still drains its copies before the area is reused
+    if (!staged) mbar_wait(SM_MBAR, stage_parity);               // a CTA without tiles still waits for its copies before the area is reused
     MK_FINE(5);
 }
 
@@ -511,6 +510,174 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
     return o;
 }
 
+#ifndef MK_OLD_ATTN
+// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); a pair of warps takes one (8 items per CTA at a time:
+// with 64 rows x 20 heads every item has its warps in the first round).  A lane owns a key quarter; the cells and the K / V pieces of
+// four key groups are requested together, so a row with 200 keys costs a handful of memory round trips instead of one per group.
+template <int WT>
+__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
+    constexpr int WPI = 2, SB = 4;                               // warps per item, key groups whose loads are issued together
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp / WPI, hw = warp % WPI;
+    const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
+    const int kslot = lane >> 2, r = lane & 3;
+    for (int p = blockIdx.x * (MK_WARPS / WPI) + grp; p < n_pairs; p += gridDim.x * (MK_WARPS / WPI)) {
+        const int t = p / H, h = p - t * H;
+        const int nk = a.nkv[t];
+        const int * cells = a.idx + (size_t) t * a.ld_idx;
+        float q[16];
+        load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
+        LaneAcc A; lane_init(A);
+        for (int k0 = hw * 8; k0 < nk; k0 += WPI * 8 * SB) {
+            int cell[SB]; KV4 f[SB];
+#pragma unroll
+            for (int s = 0; s < SB; ++s) { const int k = k0 + s * WPI * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+                f[s].k0 = f[s].k1 = f[s].v0 = f[s].v1 = make_uint4(0, 0, 0, 0);
+                if (cell[s] >= 0) {
+                    const size_t off = (size_t) cell[s] * d + h * 64 + r * 8;
+                    const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
+                    f[s].k0 = __ldcg(kp); f[s].k1 = __ldcg(kp + 4); f[s].v0 = __ldcg(vp); f[s].v1 = __ldcg(vp + 4);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+                float sc = dot16(f[s].k0, f[s].k1, q);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                if (cell[s] >= 0) lane_update(A, sc, f[s].v0, f[s].v1);
+            }
+        }
+        warp_merge(A);
+        part_store(SM_PART + (grp * WPI + hw) * MK_PART, A, lane);
+        bar_named(1 + grp, WPI * 32);
+        {
+            float M, Lsum;
+            const float o = attn_merge(SM_PART + grp * WPI * MK_PART, WPI, hw * 32 + lane, M, Lsum);
+            mk_store_q<WT>(a.actq, d, t, h * 64 + hw * 32, lane, (Lsum > 0.0f) ? __fdividef(o, Lsum) : 0.0f);
+        }
+        bar_named(1 + grp, WPI * 32);
+    }
+}
+
+// cross-attention over the n_keys padded encoder positions, zero rows included (whisper.cpp:2688-2705).
+// K and V of a window live HEAD-MAJOR in HBM ([layer][head][key][64], written that way by the cross GEMM's epilogue): the keys of one
+// (row, head) pair are one contiguous 192 KB stream instead of 128-byte pieces 2.5 KB apart.
+// The work is the flat sequence of 128-key CHUNKS of all (row, head) pairs; CTA b takes the contiguous range [b*Q/G, (b+1)*Q/G) -- at
+// most one chunk of imbalance.  Warp w, key slot s owns key 8w+s of every chunk; chunks are copied three ahead with cp.async into a
+// 4-deep ring in shared memory (the GEMV staging area, idle here); every thread reads back only the 64 bytes it copied itself, so the
+// ring needs no barrier -- it is an asynchronous extension of the register file (96 KB in flight per SM).  A "piece" is what one CTA
+// sees of one pair.  A pair that lies inside one CTA's range is finished there; otherwise every piece leaves (m, l, o[64]) in global
+// memory and the LAST piece to arrive merges all of them in key order -- so the result of a row does not depend on which other rows
+// share the pass, nor on timing.
+constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
+constexpr int MK_XPIECES = 32;                                    // partial slots per pair in a.xpart
+static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
+
+__device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
+
+template <int WT>
+__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = a.d, H = a.n_head, nchp = a.n_keys / MK_XKEYS;               // chunks per pair
+    const unsigned Q = (unsigned) (a.n_tok * H * nchp), G = min(gridDim.x, Q);
+    if (blockIdx.x >= G) return;
+    const unsigned q0 = (blockIdx.x * Q) / G, q1 = ((blockIdx.x + 1) * Q) / G;
+    // loader state: chunk being fetched
+    unsigned ql = q0, il = 0;
+    int jl = (int) (q0 % (unsigned) nchp), pl = (int) (q0 / (unsigned) nchp), tl_ = pl / H, hl = pl - tl_ * H;
+    const size_t head_stride = (size_t) a.n_keys * 64;
+    const size_t lane_off = (size_t) (warp * 8 + (lane >> 2)) * 64 + (lane & 3) * 8;       // key 8w+s of the chunk, dims {8r.., 32+8r..}
+    const uint32_t ring = (uint32_t) __cvta_generic_to_shared(mk_smem) + tid * 16;
+    auto issue = [&]() {                                           // copy the next chunk (if any) into ring slot il % 4; always commits a group
+        if (ql < q1) {
+            const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) hl * head_stride + (size_t) (jl * MK_XKEYS) * 64 + lane_off;
+            const uint32_t sa = ring + (il & (MK_RING - 1)) * MK_RING_SLOT;
+            cp_async16(sa, L.xk + off); cp_async16(sa + MK_THREADS * 16, L.xk + off + 32);
+            cp_async16(sa + 2 * MK_THREADS * 16, L.xv + off); cp_async16(sa + 3 * MK_THREADS * 16, L.xv + off + 32);
+            ++ql;
+            if (++jl == nchp) { jl = 0; if (++hl == H) { hl = 0; ++tl_; } }
+        }
+        ++il;
+        cp_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < MK_RING - 1; ++k) issue();
+    int j = (int) (q0 % (unsigned) nchp), p = (int) (q0 / (unsigned) nchp), t = p / H, h = p - t * H, jstart = j;
+    float * qsm = reinterpret_cast<float *>(mk_smem + MK_OFF_QSM);   // f16-rounded query of the pair: [2][64]
+    // qsm is stored in lane order: position 16*r + 8*hi + i holds dim 32*hi + 8*r + i
+    if (warp >= 2 && warp < 4) { const int dim = (warp - 2) * 32 + lane; qsm[((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) t * d + h * 64 + dim))); }
+    __syncthreads();
+    LaneAcc A; lane_init(A);
+    int buf = 0;
+    unsigned ic = 0;
+    for (unsigned q = q0; q < q1; ) {
+        issue();
+        cp_wait_ring();                                          // this thread's copies of chunk ic have landed
+        const uint8_t * sl = mk_smem + (ic & (MK_RING - 1)) * MK_RING_SLOT + tid * 16;
+        ++ic;
+        const uint4 k0 = *reinterpret_cast<const uint4 *>(sl), k1 = *reinterpret_cast<const uint4 *>(sl + MK_THREADS * 16);
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(sl + 2 * MK_THREADS * 16), v1 = *reinterpret_cast<const uint4 *>(sl + 3 * MK_THREADS * 16);
+        float sc = dot16s(k0, k1, qsm + buf * 64 + (lane & 3) * 16);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        lane_update(A, sc * a.kq_scale, v0, v1);
+        ++q; ++j;
+        if (j < nchp && q < q1) continue;
+        // the piece [jstart, j) of pair p ends here: merge the CTA, then either finish the pair or hand the partial over
+        warp_merge(A);
+        part_store(SM_PART + (buf * MK_WARPS + warp) * MK_PART, A, lane);
+        const bool pair_done = (j == nchp);
+        if (q < q1 && warp >= 2 && warp < 4) {                   // query of the next pair
+            int tn = t, hn = h;
+            if (++hn == H) { hn = 0; ++tn; }
+            const int dim = (warp - 2) * 32 + lane;
+            qsm[(buf ^ 1) * 64 + ((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) tn * d + hn * 64 + dim)));
+        }
+        __syncthreads();
+        if (warp < 2) {                                          // merge the 16 warp partials of this piece (one output dim per thread)
+            const int dim = warp * 32 + lane;
+            float M, Lsum;
+            const float o = attn_merge(SM_PART + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
+            if (jstart == 0 && pair_done) {
+                mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(o, Lsum));
+            } else {
+                // pieces of pair p are numbered by the CTAs that hold them: CTA c(x) = floor(((x + 1) * G - 1) / Q) holds chunk x
+                const unsigned first = (unsigned) p * (unsigned) nchp;
+                const unsigned b_first = ((first + 1) * G - 1) / Q, b_last = ((first + (unsigned) nchp) * G - 1) / Q;
+                const int ord = (int) (blockIdx.x - b_first), cnt = (int) (b_last - b_first + 1);
+                float * gp = a.xpart + ((size_t) p * MK_XPIECES + ord) * 66;
+                gp[2 + dim] = o;
+                if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
+                __threadfence();
+                bar_named(3, 64);
+                if (tid == 0) SM_FLAG[buf] = (atomicAdd(a.xcnt + p, 1) == cnt - 1);
+                bar_named(3, 64);
+                if (SM_FLAG[buf]) {                               // all pieces are in: merge them in key order
+                    __threadfence();
+                    const float * p0 = a.xpart + (size_t) p * MK_XPIECES * 66;
+                    float MM = -INFINITY;
+                    for (int k = 0; k < cnt; ++k) MM = fmaxf(MM, __ldcg(p0 + k * 66));
+                    float LL = 0.0f, oo = 0.0f;
+                    for (int k = 0; k < cnt; ++k) {
+                        const float wk = __expf(__ldcg(p0 + k * 66) - MM);
+                        LL = fmaf(__ldcg(p0 + k * 66 + 1), wk, LL);
+                        oo = fmaf(__ldcg(p0 + k * 66 + 2 + dim), wk, oo);
+                    }
+                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
+                    if (tid == 0) a.xcnt[p] = 0;
+                }
+            }
+        }
+        buf ^= 1;
+        lane_init(A);
+        if (pair_done) { j = 0; ++p; if (++h == H) { h = 0; ++t; } }
+        jstart = j;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+#else
 // self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); each half of the CTA (8 warps) takes one.
 template <int WT>
 __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
@@ -665,6 +832,7 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) 
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+#endif
 #define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, target); MK_STAMP(); } while (0)
 
 template <int WT, bool TRACE>
@@ -738,6 +906,13 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
     }
 }
 
+bool mk_cross_head_major() {
+#ifndef MK_OLD_ATTN
+    return true;
+#else
+    return false;
+#endif
+}
 int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
 size_t mk_smem_bytes(int, int) { return MK_SMEM; }

@@ -40,6 +40,7 @@ struct MkArgs {
 int  mk_barriers(int n_layer, bool want_logits);
 bool mk_supported(int wtype);
 size_t mk_smem_bytes(int wtype, int d);
+bool mk_cross_head_major();        // cross K/V of a window is expected head-major ([layer][head][key][64])
 int  mk_max_rows();                 // rows (sequences x tokens) one launch can take
 // cooperative launch on `st`; grid = number of SMs.  Returns false (with the error set) when the launch is refused.
 bool mk_launch(const MkArgs & a, int wtype, int n_sm, cudaStream_t st);

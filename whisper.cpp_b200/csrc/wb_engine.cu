@@ -282,24 +282,26 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
         g.ep.bias_m = m.conv2_b; g.ep.act = 1; g.ep.res = m.e_pe; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; g.ep.out_b0 = (int64_t) T * d;
         P.conv2_tap = g; P.conv2_tap.ep.res = nullptr; P.conv2_tap.ep.out = E.conv32.p;
     }
+    // activation-side tile: 256 tokens per CTA, or 128 when a d x NT GEMM would otherwise leave SMs idle (one window: 10 x 6 = 60 CTAs)
+    const int bn = (((NT + 255) / 256) * ((d + 127) / 128) < E.n_sm) ? 128 : 256;
     CUtensorMap tm_xn, tm_xn_win, tm_attn, tm_hfc, tm_q, tm_k, tm_p, tm_vt, tm_enc;
-    if (!make_tmap_f16(&tm_xn, E.xn.p, d, NT, 1, 1, d, 0, 0, 256)) return false;
-    if (!make_tmap_f16(&tm_xn_win, E.xn.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, 256)) return false;
-    if (!make_tmap_f16(&tm_attn, E.attn.p, d, NT, 1, 1, d, 0, 0, 256)) return false;
-    if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_xn, E.xn.p, d, NT, 1, 1, d, 0, 0, bn)) return false;
+    if (!make_tmap_f16(&tm_xn_win, E.xn.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bn)) return false;
+    if (!make_tmap_f16(&tm_attn, E.attn.p, d, NT, 1, 1, d, 0, 0, bn)) return false;
+    if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, bn)) return false;
     if (!make_tmap_f16(&tm_q, E.qk.p,     64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 256)) return false;
     if (!make_tmap_f16(&tm_k, E.qk.p + d, 64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 128)) return false;
     if (!E.fused_attn && !make_tmap_f16(&tm_p, E.P.p, Tp, T, H, n_win, Tp, (uint64_t) T * Tp, (uint64_t) H * T * Tp, 128)) return false;
     if (!make_tmap_f16(&tm_vt, E.vt.p, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) d * Tp, 64)) return false;
-    if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, 256)) return false;
+    if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bn)) return false;
 
     P.layers.resize(La);
     for (int l = 0; l < La; ++l) {
         const EncLayerW & L = m.enc[l]; EncLayerPlan & lp = P.layers[l];
-        { GemmDesc & g = lp.qk; g.M = 2*d; g.N = NT; g.K = d; g.BN = 256; g.A = L.qk; g.tmB = tm_xn;        // whisper.cpp:2119-2130
+        { GemmDesc & g = lp.qk; g.M = 2*d; g.N = NT; g.K = d; g.BN = bn; g.A = L.qk; g.tmB = tm_xn;        // whisper.cpp:2119-2130
           if (L.qk.type == WT_F16 && !make_tmap_f16(&g.tmA, L.qk.base, d, 2*d, 1, 1, d, 0, 0, 128)) return false;
           g.ep.bias_m = L.qk_bias; g.ep.out = E.qk.p; g.ep.out_f16 = 1; g.ep.ldo = 2*d; }
-        { GemmDesc & g = lp.v; g.M = d; g.N = T; g.K = d; g.BN = 256; g.nb0 = n_win; g.A = L.v; g.tmB = tm_xn_win; g.b_zsel[0] = 1; g.b_zsel[1] = 0;  // 2134-2138
+        { GemmDesc & g = lp.v; g.M = d; g.N = T; g.K = d; g.BN = bn; g.nb0 = n_win; g.A = L.v; g.tmB = tm_xn_win; g.b_zsel[0] = 1; g.b_zsel[1] = 0;  // 2134-2138
           if (L.v.type == WT_F16 && !make_tmap_f16(&g.tmA, L.v.base, d, d, 1, 1, d, 0, 0, 128)) return false;
           g.ep.bias_m = L.v_bias; g.ep.out = E.vt.p; g.ep.out_f16 = 1; g.ep.out_mmajor = 1; g.ep.ldo = Tp; g.ep.out_b0 = (int64_t) d * Tp; }
         { GemmDesc & g = lp.s; g.M = Tp; g.N = T; g.K = 64; g.BN = 256; g.nb0 = H; g.nb1 = n_win; g.A = f16A; g.A.base = E.qk.p + d;     // K.Q^T, 1536 padded keys
@@ -308,24 +310,25 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
         { GemmDesc & g = lp.pv; g.M = T; g.N = 64; g.K = Tp; g.BN = 64; g.nb0 = H; g.nb1 = n_win; g.A = f16A; g.A.base = E.P.p;
           g.tmA = tm_p; g.tmB = tm_vt; g.a_zsel[0] = 1; g.a_zsel[1] = 2;
           g.ep.out = E.attn.p; g.ep.out_f16 = 1; g.ep.out_mmajor = 1; g.ep.ldo = d; g.ep.out_b0 = 64; g.ep.out_b1 = (int64_t) T * d; }
-        { GemmDesc & g = lp.o; g.M = d; g.N = NT; g.K = d; g.BN = 256; g.A = L.o; g.tmB = tm_attn;           // 2200-2208
+        { GemmDesc & g = lp.o; g.M = d; g.N = NT; g.K = d; g.BN = bn; g.A = L.o; g.tmB = tm_attn;           // 2200-2208
           if (L.o.type == WT_F16 && !make_tmap_f16(&g.tmA, L.o.base, d, d, 1, 1, d, 0, 0, 128)) return false;
           g.ep.bias_m = L.o_bias; g.ep.res = E.x.p; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; }
-        { GemmDesc & g = lp.fc1; g.M = 4*d; g.N = NT; g.K = d; g.BN = 256; g.A = L.fc1; g.tmB = tm_xn;       // 2225-2232
+        { GemmDesc & g = lp.fc1; g.M = 4*d; g.N = NT; g.K = d; g.BN = bn; g.A = L.fc1; g.tmB = tm_xn;       // 2225-2232
           if (L.fc1.type == WT_F16 && !make_tmap_f16(&g.tmA, L.fc1.base, d, 4*d, 1, 1, d, 0, 0, 128)) return false;
           g.ep.bias_m = L.fc1_bias; g.ep.act = 1; g.ep.out = E.hfc.p; g.ep.out_f16 = 1; g.ep.ldo = 4*d; }
-        { GemmDesc & g = lp.fc2; g.M = d; g.N = NT; g.K = 4*d; g.BN = 256; g.A = L.fc2; g.tmB = tm_hfc;      // 2235-2242
+        { GemmDesc & g = lp.fc2; g.M = d; g.N = NT; g.K = 4*d; g.BN = bn; g.A = L.fc2; g.tmB = tm_hfc;      // 2235-2242
           if (L.fc2.type == WT_F16 && !make_tmap_f16(&g.tmA, L.fc2.base, 4*d, d, 1, 1, 4*d, 0, 0, 128)) return false;
           g.ep.bias_m = L.fc2_bias; g.ep.res = E.x.p; g.ep.ldr = d; g.ep.out = E.x.p; g.ep.ldo = d; }
     }
     { // cross K/V of every text layer in one launch (whisper.cpp:2306-2347)
-        GemmDesc & g = P.cross; g.M = d; g.N = T; g.K = d; g.BN = 256; g.nb0 = 2 * Lt; g.nb1 = n_win; g.A = m.cross_kv; g.a_rows_per_b0 = d;
+        GemmDesc & g = P.cross; g.M = d; g.N = T; g.K = d; g.BN = bn; g.nb0 = 2 * Lt; g.nb1 = n_win; g.A = m.cross_kv; g.a_rows_per_b0 = d;
         g.tmB = tm_enc; g.b_zsel[0] = 2; g.b_zsel[1] = 0;
         if (m.cross_kv.type == WT_F16) {
             if (!make_tmap_f16(&g.tmA, m.cross_kv.base, d, (uint64_t) 2 * Lt * d, 1, 1, d, 0, 0, 128)) return false;
         }
         g.ep.bias_m = m.cross_bias; g.ep.scale_m = m.cross_scale; g.ep.out = E.kv_cross.p; g.ep.out_f16 = 1; g.ep.ldo = d;
         g.ep.out_b0 = (int64_t) E.Tp_max * d; g.ep.out_b1 = (int64_t) 2 * Lt * E.Tp_max * d;
+        if (E.use_mk && mk_cross_head_major()) g.ep.hm_rows = E.Tp_max;                  // the persistent decode kernel streams K/V head by head (wb_decode_mk.cu)
     }
     return true;
 }

@@ -234,7 +234,14 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
                 }
             }
             if (!e.out_mmajor) {
-                if (e.out_f16) {
+                if (e.out_f16 && e.hm_rows > 0) {                     // head-major: 64 consecutive features of a key are one 128-byte row
+                    __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) (m >> 6) * e.hm_rows * 64 + (m & 63);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + col + j;
+                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * 64] = __float2half_rn(f[j]);
+                    }
+                } else if (e.out_f16) {
                     __half * o = reinterpret_cast<__half *>(e.out) + ooff;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {

@@ -30,6 +30,7 @@ struct GemmEpilogue {
     int64_t out_b0 = 0, out_b1 = 0;   // element strides of the two batch indices
     int64_t res_b0 = 0, res_b1 = 0;
     int     n_row_off = 0;            // written row index = n + n_row_off (used to leave a padding row in front)
+    int64_t hm_rows = 0;              // > 0 (with out_mmajor = 0): head-major output [m / 64][hm_rows][64] instead of [n][ldo] (cross K/V)
 };
 
 struct GemmDesc {
