@@ -563,15 +563,14 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
 // cross-attention over the n_keys padded encoder positions, zero rows included (whisper.cpp:2688-2705).
 // K and V of a window live HEAD-MAJOR in HBM ([layer][head][key][64], written that way by the cross GEMM's epilogue): the keys of one
 // (row, head) pair are one contiguous 192 KB stream instead of 128-byte pieces 2.5 KB apart.
-// The work is the flat sequence of 128-key CHUNKS of all (row, head) pairs; CTA b takes the contiguous range [b*Q/G, (b+1)*Q/G) -- at
-// most one chunk of imbalance.  Warp w, key slot s owns key 8w+s of every chunk; chunks are copied three ahead with cp.async into a
-// 4-deep ring in shared memory (the GEMV staging area, idle here); every thread reads back only the 64 bytes it copied itself, so the
-// ring needs no barrier -- it is an asynchronous extension of the register file (96 KB in flight per SM).  A "piece" is what one CTA
-// sees of one pair.  A pair that lies inside one CTA's range is finished there; otherwise every piece leaves (m, l, o[64]) in global
-// memory and the LAST piece to arrive merges all of them in key order -- so the result of a row does not depend on which other rows
-// share the pass, nor on timing.
+// Work unit = one (row, head) pair over ALL keys; CTA b takes the contiguous range of pairs [b*P/G, (b+1)*P/G).  Warp w, key slot s owns
+// key 8w+s of every 128-key chunk; chunks are copied three ahead with cp.async into a 4-deep ring in shared memory (the GEMV staging
+// area, idle here); every thread reads back only the 64 bytes it copied itself, so the ring needs no barrier -- it is an asynchronous
+// extension of the register file (96 KB in flight per SM).  The arithmetic of a pair (per-lane online softmax over its keys, 8 key slots
+// merged per warp, 16 warps merged per CTA, all in fixed order) never depends on which other rows share the pass: a batch of 64 and a
+// single row give bit-identical results.  (The phase is HBM-bound: a CTA with one pair more than its neighbour is not a cost, the
+// others simply draw more bandwidth meanwhile.)
 constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
-constexpr int MK_XPIECES = 32;                                    // partial slots per pair in a.xpart
 static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
 
 __device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
@@ -580,38 +579,37 @@ template <int WT>
 __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, H = a.n_head, nchp = a.n_keys / MK_XKEYS;               // chunks per pair
-    const unsigned Q = (unsigned) (a.n_tok * H * nchp), G = min(gridDim.x, Q);
+    const unsigned P = (unsigned) (a.n_tok * H), G = min(gridDim.x, P);
     if (blockIdx.x >= G) return;
-    const unsigned q0 = (blockIdx.x * Q) / G, q1 = ((blockIdx.x + 1) * Q) / G;
+    const unsigned p0 = (blockIdx.x * P) / G, p1 = ((blockIdx.x + 1) * P) / G;
     // loader state: chunk being fetched
-    unsigned ql = q0, il = 0;
-    int jl = (int) (q0 % (unsigned) nchp), pl = (int) (q0 / (unsigned) nchp), tl_ = pl / H, hl = pl - tl_ * H;
+    unsigned pl = p0, il = 0;
+    int jl = 0, tl_ = (int) p0 / H, hl = (int) p0 - tl_ * H;
     const size_t head_stride = (size_t) a.n_keys * 64;
     const size_t lane_off = (size_t) (warp * 8 + (lane >> 2)) * 64 + (lane & 3) * 8;       // key 8w+s of the chunk, dims {8r.., 32+8r..}
     const uint32_t ring = (uint32_t) __cvta_generic_to_shared(mk_smem) + tid * 16;
     auto issue = [&]() {                                           // copy the next chunk (if any) into ring slot il % 4; always commits a group
-        if (ql < q1) {
+        if (pl < p1) {
             const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) hl * head_stride + (size_t) (jl * MK_XKEYS) * 64 + lane_off;
             const uint32_t sa = ring + (il & (MK_RING - 1)) * MK_RING_SLOT;
             cp_async16(sa, L.xk + off); cp_async16(sa + MK_THREADS * 16, L.xk + off + 32);
             cp_async16(sa + 2 * MK_THREADS * 16, L.xv + off); cp_async16(sa + 3 * MK_THREADS * 16, L.xv + off + 32);
-            ++ql;
-            if (++jl == nchp) { jl = 0; if (++hl == H) { hl = 0; ++tl_; } }
+            if (++jl == nchp) { jl = 0; ++pl; if (++hl == H) { hl = 0; ++tl_; } }
         }
         ++il;
         cp_commit();
     };
 #pragma unroll
     for (int k = 0; k < MK_RING - 1; ++k) issue();
-    int j = (int) (q0 % (unsigned) nchp), p = (int) (q0 / (unsigned) nchp), t = p / H, h = p - t * H, jstart = j;
+    int t = (int) p0 / H, h = (int) p0 - t * H;
     float * qsm = reinterpret_cast<float *>(mk_smem + MK_OFF_QSM);   // f16-rounded query of the pair: [2][64]
     // qsm is stored in lane order: position 16*r + 8*hi + i holds dim 32*hi + 8*r + i
     if (warp >= 2 && warp < 4) { const int dim = (warp - 2) * 32 + lane; qsm[((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) t * d + h * 64 + dim))); }
     __syncthreads();
     LaneAcc A; lane_init(A);
-    int buf = 0;
+    int buf = 0, j = 0;
     unsigned ic = 0;
-    for (unsigned q = q0; q < q1; ) {
+    for (unsigned p = p0; p < p1; ) {
         issue();
         cp_wait_ring();                                          // this thread's copies of chunk ic have landed
         const uint8_t * sl = mk_smem + (ic & (MK_RING - 1)) * MK_RING_SLOT + tid * 16;
@@ -622,57 +620,27 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) 
         sc += __shfl_xor_sync(0xffffffffu, sc, 1);
         sc += __shfl_xor_sync(0xffffffffu, sc, 2);
         lane_update(A, sc * a.kq_scale, v0, v1);
-        ++q; ++j;
-        if (j < nchp && q < q1) continue;
-        // the piece [jstart, j) of pair p ends here: merge the CTA, then either finish the pair or hand the partial over
+        if (++j < nchp) continue;
+        j = 0;                                                   // last chunk of the pair: merge the CTA and write the row's head
         warp_merge(A);
         part_store(SM_PART + (buf * MK_WARPS + warp) * MK_PART, A, lane);
-        const bool pair_done = (j == nchp);
-        if (q < q1 && warp >= 2 && warp < 4) {                   // query of the next pair
+        if (p + 1 < p1 && warp >= 2 && warp < 4) {               // query of the next pair
             int tn = t, hn = h;
             if (++hn == H) { hn = 0; ++tn; }
             const int dim = (warp - 2) * 32 + lane;
             qsm[(buf ^ 1) * 64 + ((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) tn * d + hn * 64 + dim)));
         }
         __syncthreads();
-        if (warp < 2) {                                          // merge the 16 warp partials of this piece (one output dim per thread)
+        if (warp < 2) {                                          // merge the 16 warp partials (one output dim per thread)
             const int dim = warp * 32 + lane;
             float M, Lsum;
             const float o = attn_merge(SM_PART + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
-            if (jstart == 0 && pair_done) {
-                mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(o, Lsum));
-            } else {
-                // pieces of pair p are numbered by the CTAs that hold them: CTA c(x) = floor(((x + 1) * G - 1) / Q) holds chunk x
-                const unsigned first = (unsigned) p * (unsigned) nchp;
-                const unsigned b_first = ((first + 1) * G - 1) / Q, b_last = ((first + (unsigned) nchp) * G - 1) / Q;
-                const int ord = (int) (blockIdx.x - b_first), cnt = (int) (b_last - b_first + 1);
-                float * gp = a.xpart + ((size_t) p * MK_XPIECES + ord) * 66;
-                gp[2 + dim] = o;
-                if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
-                __threadfence();
-                bar_named(3, 64);
-                if (tid == 0) SM_FLAG[buf] = (atomicAdd(a.xcnt + p, 1) == cnt - 1);
-                bar_named(3, 64);
-                if (SM_FLAG[buf]) {                               // all pieces are in: merge them in key order
-                    __threadfence();
-                    const float * p0 = a.xpart + (size_t) p * MK_XPIECES * 66;
-                    float MM = -INFINITY;
-                    for (int k = 0; k < cnt; ++k) MM = fmaxf(MM, __ldcg(p0 + k * 66));
-                    float LL = 0.0f, oo = 0.0f;
-                    for (int k = 0; k < cnt; ++k) {
-                        const float wk = __expf(__ldcg(p0 + k * 66) - MM);
-                        LL = fmaf(__ldcg(p0 + k * 66 + 1), wk, LL);
-                        oo = fmaf(__ldcg(p0 + k * 66 + 2 + dim), wk, oo);
-                    }
-                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
-                    if (tid == 0) a.xcnt[p] = 0;
-                }
-            }
+            mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(o, Lsum));
         }
         buf ^= 1;
         lane_init(A);
-        if (pair_done) { j = 0; ++p; if (++h == H) { h = 0; ++t; } }
-        jstart = j;
+        ++p;
+        if (++h == H) { h = 0; ++t; }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
