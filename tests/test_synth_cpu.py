@@ -62,3 +62,17 @@ def test_host_expanded_formats_load_in_reference_and_parse_here(lib, ref, tmp_pa
     mine = lib.wb200_dbg_vocab_context(path.encode())
     assert mine, lib.wb200_last_error()
     assert lib.whisper_model_ftype(mine) == synth.FTYPE_OF[wtype] and lib.whisper_model_n_text_layer(mine) == 2
+
+
+def test_simple_q4_k_writer_is_valid_q4_k(ref):
+    """synth.quantize_q4_k_simple (the multi-GB benchmark model of BASELINE config 3) writes super-blocks the reference's
+    dequantize_row_q4_K reads back close to the input; it is NOT ggml's quantiser (parity tests use ggml_quantize_chunk)"""
+    from wbtest import ref_dequantize, Q4_K
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal((6, 1024)) * 0.02).astype(np.float32)
+    w[1, :300] = 0.0
+    raw = synth.quantize(Q4_K, w)
+    assert len(raw) == 6 * 4 * 144
+    deq = ref_dequantize(ref, Q4_K, raw, 6, 1024)
+    assert np.sqrt(((deq - w) ** 2).mean()) / w.std() < 0.12
+    assert np.abs(deq[1, :256]).max() < 1e-6

@@ -57,7 +57,7 @@ bool Engine::init(const Model * model, int cap_windows) {
         n_sm = prop.multiProcessorCount;
         use_mk = m->dec_tm;
         max_rows = use_mk ? mk_max_rows() : 8;                   // the layout decides: tile-major decoder weights <=> persistent kernel
-        if (use_mk && (!mk_supported(m->wtype == WT_F32 ? WT_F16 : m->wtype) || mk_smem_bytes(m->wtype == WT_F32 ? WT_F16 : m->wtype, hp.n_text_state) > 200 * 1024 || !prop.cooperativeLaunch)) {
+        if (use_mk && (!mk_supported(m->wtype == WT_F32 ? WT_F16 : m->wtype) || mk_smem_bytes(m->wtype == WT_F32 ? WT_F16 : m->wtype, hp.n_text_state) > 227 * 1024 || !prop.cooperativeLaunch)) {
             set_error("decode: the persistent kernel cannot run on this device/model; set WB200_MEGAKERNEL=0"); return false;
         }
         if (const char * pf = getenv("WB200_MK_PREFETCH")) mk_prefetch = atoi(pf);

@@ -108,7 +108,37 @@ def quantize(wtype, w):
         out[:, 2:6] = qh.view(np.uint8).reshape(nb, 4)
         out[:, 6:] = ((q[:, :16] & 0xF) | ((q[:, 16:] & 0xF) << 4)).astype(np.uint8)
         return out.tobytes()
+    if wtype == Q4_K:
+        return quantize_q4_k_simple(w)
     raise ValueError(f"synth.quantize: type {wtype} needs an external quantiser (pass quantizer=...)")
+
+
+def quantize_q4_k_simple(w):
+    """float32 [rows][k] -> block_q4_K bytes (ggml-common.h:327-340).  A plain min/max quantiser, NOT ggml's iterative make_qkx2_quants:
+    every output is a valid Q4_K super-block that dequantises (ggml-quants.c:1529-1551) close to the input, which is all the multi-GB
+    benchmark model of BASELINE config 3 needs; parity tests quantise with the reference's own ggml_quantize_chunk instead."""
+    x = np.ascontiguousarray(w, np.float32).reshape(-1, 8, 32)
+    nb = x.shape[0]
+    mn = np.minimum(x.min(axis=2), 0.0); mx = x.max(axis=2)
+    mf = -mn                                                    # >= 0
+    sf = np.maximum((mx + mf) / np.float32(15.0), 1e-12)
+    d = (sf.max(axis=1) / np.float32(63.0)).astype(np.float16).astype(np.float32); d = np.where(d > 0, d, 1e-8).astype(np.float32)
+    dmin = (mf.max(axis=1) / np.float32(63.0)).astype(np.float16).astype(np.float32); dmin_safe = np.where(dmin > 0, dmin, 1.0).astype(np.float32)
+    sc = np.clip(np.rint(sf / d[:, None]), 1, 63).astype(np.uint8)
+    m = np.clip(np.rint(mf / dmin_safe[:, None]), 0, 63).astype(np.uint8)
+    q = np.clip(np.rint((x + (dmin[:, None] * m)[:, :, None]) / (d[:, None] * sc)[:, :, None]), 0, 15).astype(np.uint8)
+    out = np.zeros((nb, 144), np.uint8)
+    out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(nb, 2)
+    out[:, 2:4] = dmin.astype(np.float16).view(np.uint8).reshape(nb, 2)
+    scales = np.zeros((nb, 12), np.uint8)
+    for j in range(4):
+        scales[:, j] = (sc[:, j] & 63) | ((sc[:, j + 4] >> 4) << 6)
+        scales[:, j + 4] = (m[:, j] & 63) | ((m[:, j + 4] >> 4) << 6)
+        scales[:, j + 8] = (sc[:, j + 4] & 0xF) | ((m[:, j + 4] & 0xF) << 4)
+    out[:, 4:16] = scales
+    for jp in range(4):                                          # 64 values per 32 bytes: low nibbles = sub-block 2jp, high = 2jp+1
+        out[:, 16 + 32 * jp:16 + 32 * (jp + 1)] = q[:, 2 * jp] | (q[:, 2 * jp + 1] << 4)
+    return out.tobytes()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -261,7 +291,7 @@ def cached_model(config, wtype, seed=0, fast_pool=False, tag=None):
     """a synthetic model in the temp directory, written once per box (the multi-GB ones take a while); returns its path"""
     import os
     import tempfile
-    names = {F16: "f16", Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0"}
+    names = {F16: "f16", Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0", Q4_K: "q4_k"}
     path = os.path.join(tempfile.gettempdir(), "wb200-%s-%s%s.bin" % (config, names[wtype], ("-" + tag) if tag else ""))
     if not os.path.exists(path):
         tmp = path + ".tmp.%d" % os.getpid()
