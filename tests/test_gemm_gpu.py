@@ -42,7 +42,14 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("wtype,M,N,K,BN,flags", CASES)
+CASES_V2 = [(w, M, N, K, BN, f | 4) for (w, M, N, K, BN, f) in CASES] + [
+    (Q5_0, 1280, 6000, 1280, 256, 4),      # 10 x 24 = 240 tiles on 148 persistent CTAs: several tiles per CTA, both accumulators in use
+    (Q5_0, 2560, 3000, 1280, 256, 5),
+    (F16,  640,  4500, 320,  128, 4),
+]
+
+
+@pytest.mark.parametrize("wtype,M,N,K,BN,flags", CASES + CASES_V2)
 def test_gemm_matches_dequantised_reference(lib, ref, wtype, M, N, K, BN, flags):
     rng = np.random.default_rng(1234 + M + 7 * N + 13 * K + wtype)
     w = (rng.standard_normal((M, K)) * 0.05).astype(np.float32)

@@ -11,7 +11,8 @@ using namespace wb;
 extern "C" {
 
 // C[n][m] (f32, token-major) = sum_k W[m][k] * X[n][k] ; W given in FILE layout (f16 rows or ggml quant blocks),
-// X given as f32 and rounded to f16 on the way in (as the engine does).  flags bit0: apply gelu; bit1: m-major output.
+// X given as f32 and rounded to f16 on the way in (as the engine does).  flags bit0: apply gelu; bit1: m-major output;
+// bit2: the persistent double-buffered kernel (quantised weights expanded to f16 once, both operands through TMA).
 __attribute__((visibility("default")))
 int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const float * x, const float * bias,
                    float * out, int BN, int flags) {
@@ -37,6 +38,15 @@ int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const fl
         g.A.type = wtype; g.A.N = M; g.A.K = K; g.A.base = wraw.p;
     } else { set_error("wb200_dbg_gemm: unsupported wtype %d", wtype); return -5; }
     if (!make_tmap_f16(&g.tmB, xh.p, K, N, 1, 1, K, 0, 0, BN)) return -3;
+    DevBuf<__half> a16;
+    if (flags & 4) {
+        g.v2 = 1;
+        if (wtype != WT_F16) {
+            if (!a16.alloc((size_t) M * K)) return -1;
+            g.a16 = a16.p;
+            if (!make_tmap_f16(&g.tmA, a16.p, K, M, 1, 1, K, 0, 0, 128)) return -3;
+        }
+    }
     g.ep.bias_m = bias ? dbias.p : nullptr;
     g.ep.act = (flags & 1) ? 1 : 0;
     g.ep.out = dout.p; g.ep.out_f16 = 0;

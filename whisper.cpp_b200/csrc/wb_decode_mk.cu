@@ -40,13 +40,10 @@ extern __shared__ __align__(16) uint8_t mk_smem[];
 constexpr int MK_OFF_XQ   = 0;                                                   // staged activation rows [64][SW words]
 constexpr int MK_OFF_XD   = MK_OFF_XQ + MK_MAXTOK * (MK_ROWB + 16);              // their Q8_0 block scales [64][chunk/32]
 constexpr int MK_OFF_RED  = MK_OFF_XD + MK_MAXTOK * (MK_ROWB / 32) * 4;          // split-K partials [MK_TP tiles][16 warps][16 rows][17]
-constexpr int MK_OFF_TOP  = 200 * 1024;                                          // small fixed areas above everything the phases stream through
-constexpr int MK_OFF_PART = MK_OFF_TOP;                                          // attention warp partials [2][16][68]: m, l, -, -, o[64]
+constexpr int MK_OFF_PART = MK_OFF_RED + MK_RED * 4;                             // attention warp partials [2][16][68]: m, l, -, -, o[64]
 constexpr int MK_OFF_STAT = MK_OFF_PART + 2 * MK_WARPS * MK_PART * 4;            // LayerNorm partial sums [32]
 constexpr int MK_OFF_FLAG = MK_OFF_STAT + 32 * 4;                                // [16] ints
 constexpr int MK_SMEM     = MK_OFF_FLAG + 16 * 4;
-static_assert(MK_OFF_RED + MK_RED * 4 <= MK_OFF_TOP, "GEMV areas must stay below the fixed areas");
-static_assert(MK_SMEM <= 227 * 1024, "shared memory per CTA");
 #define SM_XQ   (reinterpret_cast<uint32_t *>(mk_smem + MK_OFF_XQ))
 #define SM_XD   (reinterpret_cast<float *>(mk_smem + MK_OFF_XD))
 #define SM_RED  (reinterpret_cast<float *>(mk_smem + MK_OFF_RED))
@@ -567,13 +564,14 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
 // K and V of a window live HEAD-MAJOR in HBM ([layer][head][key][64], written that way by the cross GEMM's epilogue): the keys of one
 // (row, head) pair are one contiguous 192 KB stream instead of 128-byte pieces 2.5 KB apart.
 // Work unit = one (row, head) pair over ALL keys; CTA b takes the contiguous range of pairs [b*P/G, (b+1)*P/G).  Warp w, key slot s owns
-// key 8w+s of every 128-key chunk; chunks are copied five ahead with cp.async into a 6-deep ring in shared memory (the GEMV staging
+// key 8w+s of every 128-key chunk; chunks are copied three ahead with cp.async into a 4-deep ring in shared memory (the GEMV staging
 // area, idle here); every thread reads back only the 64 bytes it copied itself, so the ring needs no barrier -- it is an asynchronous
-// extension of the register file (160 KB in flight per SM).  The arithmetic of a pair (per-lane online softmax over its keys, 8 key slots
+// extension of the register file (96 KB in flight per SM; a 6-deep ring was measured slower: the 40 KB of L1 it takes away cost the other
+// phases more than the tail of this one gains).  The arithmetic of a pair (per-lane online softmax over its keys, 8 key slots
 // merged per warp, 16 warps merged per CTA, all in fixed order) never depends on which other rows share the pass: a batch of 64 and a
 // single row give bit-identical results.  (The phase is HBM-bound: a CTA with one pair more than its neighbour is not a cost, the
 // others simply draw more bandwidth meanwhile.)
-constexpr int MK_RING = 6, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
+constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
 static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
 
 __device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }

@@ -49,6 +49,11 @@ bool Engine::init(const Model * model, int cap_windows) {
     debug_taps = getenv("WB200_DEBUG_TAPS") != nullptr;
     use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
     fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
+    gemm_v2 = getenv("WB200_GEMM_V1") == nullptr;
+    if (gemm_v2 && m->wtype != WT_F16 && m->wtype != WT_F32) {
+        const size_t dd = (size_t) hp.n_audio_state * hp.n_audio_state;
+        if (!wf16.alloc(std::max<size_t>(4 * dd, (size_t) 2 * hp.n_text_layer * dd))) return false;
+    }
     gemv_v2 = getenv("WB200_GEMV_V1") == nullptr;
     (void) B; (void) H; (void) M; (void) Tp;
     if (!alloc_encoder_ws() || !kv_cross.alloc((size_t) cap_win * 2 * Lt * Tp * d, true)) return false;
@@ -330,6 +335,21 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
         g.ep.out_b0 = (int64_t) E.Tp_max * d; g.ep.out_b1 = (int64_t) 2 * Lt * E.Tp_max * d;
         if (E.use_mk && mk_cross_head_major()) g.ep.hm_rows = E.Tp_max;                  // the persistent decode kernel streams K/V head by head (wb_decode_mk.cu)
     }
+    if (E.gemm_v2) {
+        // second-generation kernel: quantised weights are expanded to f16 once per launch into E.wf16 (every launch of the stream reuses the
+        // same scratch: the previous GEMM has finished reading it when the next expansion starts) and reach the tensor cores through TMA
+        auto to_v2 = [&](GemmDesc & g, int64_t rows) -> bool {
+            g.v2 = 1;
+            if (g.A.type == WT_F16) return true;
+            if (!E.wf16.p) { g.v2 = 0; return true; }
+            g.a16 = E.wf16.p;
+            return make_tmap_f16(&g.tmA, E.wf16.p, g.K, rows, 1, 1, g.K, 0, 0, 128);
+        };
+        if (!to_v2(P.conv1, 0) || !to_v2(P.conv2, 0) || !to_v2(P.conv2_tap, 0)) return false;
+        for (auto & lp : P.layers)
+            if (!to_v2(lp.qk, 2*d) || !to_v2(lp.v, d) || !to_v2(lp.o, d) || !to_v2(lp.fc1, 4*d) || !to_v2(lp.fc2, d)) return false;
+        if (!to_v2(P.cross, (int64_t) 2 * Lt * d)) return false;
+    }
     return true;
 }
 
@@ -390,7 +410,7 @@ bool Engine::encode(const EncSrc * srcs, int n_win, int n_ctx) {
     } else {                          // windows land in arbitrary cross-KV slots: one launch per window
         for (int w = 0; w < n_win; ++w) {
             GemmDesc g = PL.cross;
-            g.nb1 = 1; g.b1_in_off = w;
+            g.nb1 = 1; g.b1_in_off = w; g.a16_keep = (w > 0);
             g.ep.out = kv_cross.p + (size_t) srcs[w].slot * 2 * hp.n_text_layer * Tp_max * d;
             WB_GEMM(g);
         }

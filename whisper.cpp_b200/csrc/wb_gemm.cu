@@ -10,6 +10,7 @@
 // Layout facts relied on (guides: blackwell_cuda_programming.md "UMMA", B300_MICROARCH.md "tcgen05"):
 //   * K-major SW128 tile: row r at byte r*128, 16-byte chunk c stored at chunk (c ^ (r & 7)); 8-row groups 1024 B apart
 //   * a warp may only tcgen05.ld the TMEM lane quarter (warp_id % 4)
+#include <algorithm>
 #include "wb_gemm.cuh"
 #include "wb_ptx.cuh"
 #include "wb_common.h"
@@ -57,6 +58,95 @@ __device__ __forceinline__ void raw_load(const GemmKParams & p, int m, int k, Ra
         r.q0 = __ldg(reinterpret_cast<const uint4 *>(p.a_qs) + 2*bi);
         r.q1 = __ldg(reinterpret_cast<const uint4 *>(p.a_qs) + 2*bi + 1);
         r.d = p.a_d[bi];
+    }
+}
+
+// Epilogue of one 128 x BN tile held in TMEM columns [tmem_acc, tmem_acc + BN): TMEM -> registers -> bias / scale / GELU / residual -> global.
+// Called by the 8 epilogue warps (warp = 2..9): warp & 3 selects the TMEM lane quarter the warp may read, (warp - 2) >> 2 the column half.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmKParams & p, uint32_t tmem_base, int m0, int n0, int b0, int b1, int warp, int lane) {
+    const int q    = warp & 3;                 // TMEM lane quarter this warp may read
+    const int hsel = (warp - 2) >> 2;          // which half of the columns
+    const int m    = m0 + q * 32 + lane;
+    const bool mval = m < p.M;
+    const GemmEpilogue & e = p.ep;
+    const int mg = m + b0 * p.a_rows_per_b0;   // bias / scale follow the stacked-matrix row
+    const float bias = (mval && e.bias_m)  ? e.bias_m[mg]  : 0.0f;
+    const float scl  = ((mval && e.scale_m) ? e.scale_m[mg] : 1.0f) * e.alpha;
+    const int64_t ooff = (int64_t) b0 * e.out_b0 + (int64_t) b1 * e.out_b1;
+    const int64_t roff = (int64_t) b0 * e.res_b0 + (int64_t) b1 * e.res_b1;
+    constexpr int CH = BN / 2 / 32;            // 32-column chunks per warp
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c) {
+        const int col = hsel * (BN / 2) + c * 32;
+        if (n0 + col >= p.N) break;            // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) col, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = (__uint_as_float(v[j]) + bias) * scl;
+            if (e.act == 1) x = gelu_ref_f16(x);
+            f[j] = x;
+        }
+        if (e.res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + col + j;
+                if (mval && n < p.N) f[j] += e.res[roff + (int64_t) n * e.ldr + m];
+            }
+        }
+        if (!e.out_mmajor) {
+            if (e.out_f16 && e.hm_rows > 0) {                     // head-major: 64 consecutive features of a key are one 128-byte row
+                __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) (m >> 6) * e.hm_rows * 64 + (m & 63);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + col + j;
+                    if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * 64] = __float2half_rn(f[j]);
+                }
+            } else if (e.out_f16) {
+                __half * o = reinterpret_cast<__half *>(e.out) + ooff;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + col + j;
+                    if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = __float2half_rn(f[j]);
+                }
+            } else {
+                float * o = reinterpret_cast<float *>(e.out) + ooff;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + col + j;
+                    if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = f[j];
+                }
+            }
+        } else if (mval) {
+            const int nb = n0 + col;
+            const bool full = (nb + 32 <= p.N);
+            if (e.out_f16) {
+                __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
+                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __half2 h0 = __floats2half2_rn(f[j], f[j+1]),   h1 = __floats2half2_rn(f[j+2], f[j+3]);
+                        __half2 h2 = __floats2half2_rn(f[j+4], f[j+5]), h3 = __floats2half2_rn(f[j+6], f[j+7]);
+                        uint4 u = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
+                                             *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+                        *reinterpret_cast<uint4 *>(o + j) = u;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
+                }
+            } else {
+                float * o = reinterpret_cast<float *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
+                if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j+1], f[j+2], f[j+3]);
+                } else {
+                    for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = f[j];
+                }
+            }
+        }
     }
 }
 
@@ -201,94 +291,140 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
         // ------------------------------------------------------------------ epilogue
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int q    = warp & 3;                 // TMEM lane quarter this warp may read
-        const int hsel = (warp - 2) >> 2;          // which half of the columns
-        const int m    = m0 + q * 32 + lane;
-        const bool mval = m < p.M;
-        const GemmEpilogue & e = p.ep;
-        const int mg = m + b0 * p.a_rows_per_b0;   // bias / scale follow the stacked-matrix row
-        const float bias = (mval && e.bias_m)  ? e.bias_m[mg]  : 0.0f;
-        const float scl  = ((mval && e.scale_m) ? e.scale_m[mg] : 1.0f) * e.alpha;
-        const int64_t ooff = (int64_t) b0 * e.out_b0 + (int64_t) b1 * e.out_b1;
-        const int64_t roff = (int64_t) b0 * e.res_b0 + (int64_t) b1 * e.res_b1;
-        constexpr int CH = BN / 2 / 32;            // 32-column chunks per warp
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
-            const int col = hsel * (BN / 2) + c * 32;
-            if (n0 + col >= p.N) break;            // warp-uniform
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) col, v);
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = (__uint_as_float(v[j]) + bias) * scl;
-                if (e.act == 1) x = gelu_ref_f16(x);
-                f[j] = x;
-            }
-            if (e.res) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + col + j;
-                    if (mval && n < p.N) f[j] += e.res[roff + (int64_t) n * e.ldr + m];
-                }
-            }
-            if (!e.out_mmajor) {
-                if (e.out_f16 && e.hm_rows > 0) {                     // head-major: 64 consecutive features of a key are one 128-byte row
-                    __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) (m >> 6) * e.hm_rows * 64 + (m & 63);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + col + j;
-                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * 64] = __float2half_rn(f[j]);
-                    }
-                } else if (e.out_f16) {
-                    __half * o = reinterpret_cast<__half *>(e.out) + ooff;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + col + j;
-                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = __float2half_rn(f[j]);
-                    }
-                } else {
-                    float * o = reinterpret_cast<float *>(e.out) + ooff;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + col + j;
-                        if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = f[j];
-                    }
-                }
-            } else if (mval) {
-                const int nb = n0 + col;
-                const bool full = (nb + 32 <= p.N);
-                if (e.out_f16) {
-                    __half * o = reinterpret_cast<__half *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __half2 h0 = __floats2half2_rn(f[j], f[j+1]),   h1 = __floats2half2_rn(f[j+2], f[j+3]);
-                            __half2 h2 = __floats2half2_rn(f[j+4], f[j+5]), h3 = __floats2half2_rn(f[j+6], f[j+7]);
-                            uint4 u = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
-                                                 *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
-                            *reinterpret_cast<uint4 *>(o + j) = u;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = __float2half_rn(f[j]);
-                    }
-                } else {
-                    float * o = reinterpret_cast<float *>(e.out) + ooff + (int64_t) m * e.ldo + nb;
-                    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j+1], f[j+2], f[j+3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) o[j] = f[j];
-                    }
-                }
-            }
-        }
+        gemm_epilogue_tile<BN>(p, tmem_base, m0, n0, b0, b1, warp, lane);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<BN>(tmem_base);
+}
+
+// =============================================================================================== persistent f16 x f16 GEMM
+// Second generation of the encode-path GEMM.  Both operands are f16 tiles fetched by TMA (quantised weights are expanded ONCE per
+// launch into an f16 scratch by k_dequant_f16 -- a 128-row weight tile used to be re-decoded by every one of the up to 375 CTAs that
+// shared it), the kernel is PERSISTENT (one CTA per SM walks the tile list, weight-tile index fastest so that concurrently running CTAs
+// share activation tiles in L2) and the accumulator is DOUBLE-BUFFERED in tensor memory (2 x BN columns): the epilogue of tile i
+// (TMEM -> registers -> bias / GELU / residual -> global) overlaps the main loop of tile i+1.
+//   warp 0      : TMA producer   -- A and B tiles into a STAGES-deep smem ring (full / empty mbarriers)
+//   warp 1      : MMA issuer     -- one thread, 4 x tcgen05.mma (K = 16) per 64-wide k-block; commits the stage's "empty" barrier and,
+//                                   after the last k-block of a tile, the accumulator's "full" barrier
+//   warps 2..9  : epilogue       -- wait "full", drain the accumulator (gemm_epilogue_tile), arrive on its "empty" barrier
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int n_mt, int n_nt, int n_tiles) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t * smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t * sA = smem;
+    uint8_t * sB = smem + STAGES * A_TILE_BYTES;
+    uint64_t * bars      = reinterpret_cast<uint64_t *>(sB + STAGES * Cfg::B_TILE_BYTES);
+    uint64_t * full_bar  = bars;
+    uint64_t * empty_bar = bars + STAGES;
+    uint64_t * tfull     = bars + 2*STAGES;          // [2] accumulator ready for the epilogue
+    uint64_t * tempty    = bars + 2*STAGES + 2;      // [2] accumulator drained
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 2*STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nkb = p.taps * p.nkb_per_tap;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmA); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int mt = t % n_mt, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
+                const int b0 = z % p.nb0, b1 = z / p.nb0;
+                const int mg0 = mt * 128 + b0 * p.a_rows_per_b0, n0 = nt * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int tap = kb / p.nkb_per_tap;
+                    const int k0  = (kb - tap * p.nkb_per_tap) * 64;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::B_TILE_BYTES + A_TILE_BYTES);
+                    const int sel[4] = { 0, b0, b1 + p.b1_in_off, tap };
+                    tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, sel[p.b_zsel0], sel[p.b_zsel1]);
+                    tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, mg0, sel[p.a_zsel0], sel[p.a_zsel1]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, BN);
+            int s = 0; uint32_t ph = 0;
+            int i = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const int acc = i & 1;
+                mbar_wait(&tempty[acc], (uint32_t) ((i >> 1) & 1) ^ 1u);       // the epilogue has drained this accumulator (first use: free)
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t) (acc * BN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_TILE_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * Cfg::B_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tacc, adesc + 2*k, bdesc + 2*k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int mt = t % n_mt, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
+            const int b0 = z % p.nb0, b1 = z / p.nb0;
+            const int acc = i & 1;
+            mbar_wait(&tfull[acc], (uint32_t) ((i >> 1) & 1));
+            tc_fence_after();
+            gemm_epilogue_tile<BN>(p, tmem_base + (uint32_t) (acc * BN), mt * 128, nt * BN, b0, b1, warp, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// expand a quantised matrix (planar 32-blocks or verbatim K-quant super-blocks) to f16 rows [rows][K]; one thread = one 32-value block.
+// Each value is the f16 rounding of the exact d * (q - off), i.e. what dequantize_row_* gives after one f16 store (wb_quant.cuh).
+template <int WT>
+__global__ void __launch_bounds__(256)
+k_dequant_f16(const void * base, const uint8_t * qs, const uint32_t * qh, const __half * dd, int64_t row0, int64_t n_blocks, int K, __half * out) {
+    const int64_t bi = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= n_blocks) return;
+    const int64_t nblk = K >> 5;
+    uint4 o[4];
+    if (WT == WT_Q4_K || WT == WT_Q5_K) {
+        constexpr int BLK = (WT == WT_Q4_K) ? 144 : 176;
+        const int64_t row = bi / nblk, kb = bi - row * nblk;
+        const uint8_t * sb = reinterpret_cast<const uint8_t *>(base) + ((row0 + row) * (K >> 8) + (kb >> 3)) * BLK;
+        dequant_kq_sub<WT == WT_Q5_K>(sb, (int) (kb & 7), o);
+    } else {
+        const int64_t g = row0 * nblk + bi;
+        if (WT == WT_Q4_0)      dequant_q4_0(__ldg(reinterpret_cast<const uint4 *>(qs) + g), dd[g], o);
+        else if (WT == WT_Q5_0) dequant_q5_0(__ldg(reinterpret_cast<const uint4 *>(qs) + g), __ldg(qh + g), dd[g], o);
+        else                    dequant_q8_0(__ldg(reinterpret_cast<const uint4 *>(qs) + 2*g), __ldg(reinterpret_cast<const uint4 *>(qs) + 2*g + 1), dd[g], o);
+    }
+    uint4 * dst = reinterpret_cast<uint4 *>(out + bi * 32);
+    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2]; dst[3] = o[3];
 }
 
 // =============================================================================================== host side
@@ -350,6 +486,40 @@ static cudaError_t launch_bn(const GemmDesc & g, const GemmKParams & kp, cudaStr
     return cudaErrorInvalidValue;
 }
 
+static int gemm_n_sm() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) n = pr.multiProcessorCount; else n = 148; }
+    return n;
+}
+
+template <int BN>
+static cudaError_t launch2_t(const GemmDesc & g, const GemmKParams & kp, cudaStream_t st) {
+    auto kern = gemm2_kernel<BN>;
+    const size_t smem = GemmCfg<BN>::SMEM + 64;
+    { const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem); if (e != cudaSuccess) return e; }
+    const int n_mt = (g.M + 127) / 128, n_nt = (g.N + BN - 1) / BN, n_tiles = n_mt * n_nt * g.nb0 * g.nb1;
+    kern<<<std::min(n_tiles, gemm_n_sm()), GEMM_THREADS, smem, st>>>(kp, g.tmA, g.tmB, n_mt, n_nt, n_tiles);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// expand the rows of g.A that this launch uses into g.a16 (f16 [rows][K]); rows = M x (stacked matrices)
+static cudaError_t dequant_launch(const GemmDesc & g, cudaStream_t st) {
+    const int64_t rows = g.a_rows_per_b0 ? (int64_t) g.a_rows_per_b0 * g.nb0 : g.M;
+    const int64_t n_blocks = rows * (g.K >> 5);
+    const unsigned grid = (unsigned) ((n_blocks + 255) / 256);
+    switch (g.A.type) {
+        case WT_Q4_0: k_dequant_f16<WT_Q4_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+        case WT_Q5_0: k_dequant_f16<WT_Q5_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+        case WT_Q8_0: k_dequant_f16<WT_Q8_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+        case WT_Q4_K: k_dequant_f16<WT_Q4_K><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+        case WT_Q5_K: k_dequant_f16<WT_Q5_K><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+        default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
     const double nb = (double) g.nb0 * g.nb1;
     ProfScope prof(PC_GEMM, st, nb * ((double) g.M * g.K * g.taps * wt_bpw(g.A.type) + (double) g.N * g.K * g.taps * 2 + (double) g.M * g.N * (g.ep.out_f16 ? 2 : 4)),
@@ -360,6 +530,15 @@ cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
     kp.a_rows_per_b0 = g.a_rows_per_b0; kp.b1_in_off = g.b1_in_off;
     kp.a_base = g.A.base; kp.a_qs = g.A.qs; kp.a_qh = g.A.qh; kp.a_d = g.A.d;
     kp.ep = g.ep;
+    if (g.v2 && (g.A.type == WT_F16 || g.a16)) {                  // persistent kernel: both operands f16 through TMA
+        if (g.A.type != WT_F16 && !g.a16_keep) { const cudaError_t e = dequant_launch(g, st); if (e != cudaSuccess) return e; }
+        switch (g.BN) {
+            case 64:  return launch2_t<64>(g, kp, st);
+            case 128: return launch2_t<128>(g, kp, st);
+            case 256: return launch2_t<256>(g, kp, st);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (g.A.type) {
         case WT_F16:  return launch_bn<WT_F16>(g, kp, st);
         case WT_Q4_0: return launch_bn<WT_Q4_0>(g, kp, st);

@@ -44,7 +44,10 @@ struct GemmDesc {
     int b1_in_off = 0;                // added to b1 when it is used as a TMA coordinate (one window of a batched buffer per launch)
     int a_rows_per_b0 = 0;            // A row offset = b0 * a_rows_per_b0 (stacked weights: one launch, many matrices)
     QMat A;                           // weight side; type WT_F16 => tmA used
-    CUtensorMap tmA;                  // valid when A.type == WT_F16
+    CUtensorMap tmA;                  // valid when A.type == WT_F16, or when a16 is set (then it maps a16)
+    __half * a16 = nullptr;           // quantised A: f16 scratch [rows][K] the persistent kernel's launch expands A into (shared by all launches of a stream)
+    int v2 = 0;                       // 1: persistent double-buffered kernel (gemm2_kernel)
+    int a16_keep = 0;                 // 1: a16 already holds this matrix (a launch sequence over the same weights expands them once)
     CUtensorMap tmB;
     GemmEpilogue ep;
 };
