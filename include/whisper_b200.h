@@ -424,6 +424,10 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
                                   struct whisper_state ** states_out, int flags);
 /* the default state owned by a context created with a *_with_params (non-_no_state) call; NULL otherwise */
 WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx);
+/* In-library multi-GPU (environment WB200_DEVICES = "all" | "0,1,.." at whisper_init_from_file*): number of GPUs that hold a replica of
+   the weights, and the GPU a state was placed on by whisper_init_state (the one with the fewest states). */
+WB_EXPORT int wb200_n_devices(struct whisper_context * ctx);
+WB_EXPORT int wb200_state_device(struct whisper_state * state);
 /* stage PCM in HBM ahead of time: a following whisper_full_with_state(ctx, state, params, NULL, n_samples) (or
  * whisper_pcm_to_mel_with_state with samples == NULL) then starts from the device-resident samples (bench.py `value`) */
 WB_EXPORT int wb200_pcm_upload(struct whisper_state * state, const float * samples, int n_samples);

@@ -564,6 +564,31 @@ WB_EXPORT struct whisper_context * whisper_init_from_file_with_params_no_state(c
     loader.close = [](void * c) { ((std::ifstream *) c)->close(); };
     whisper_context * ctx = whisper_init_with_params_no_state(&loader, params);
     if (ctx) ctx->path_model = path_model;
+    if (ctx && !ctx->params.dtw_token_timestamps) {
+        // WB200_DEVICES = "all" | "0,1,5": one more copy of the weights per listed GPU (the context's own device is always first)
+        if (const char * e = getenv("WB200_DEVICES")) {
+            int ndev = 0; cudaGetDeviceCount(&ndev);
+            std::vector<int> devs;
+            if (!strcmp(e, "all")) { for (int d = 0; d < ndev; ++d) devs.push_back(d); }
+            else { for (const char * q = e; *q; ) { char * end = nullptr; const long d = strtol(q, &end, 10); if (end == q) break; if (d >= 0 && d < ndev) devs.push_back((int) d); q = (*end == ',') ? end + 1 : end; } }
+            for (int d : devs) {
+                if (d == params.gpu_device) continue;
+                std::ifstream f2(path_model, std::ios::binary);
+                if (!f2) break;
+                whisper_model_loader l2 = {};
+                l2.context = &f2;
+                l2.read  = [](void * c, void * out, size_t n) -> size_t { auto * f = (std::ifstream *) c; f->read((char *) out, (std::streamsize) n); return (size_t) f->gcount(); };
+                l2.eof   = [](void * c) -> bool { return ((std::ifstream *) c)->eof(); };
+                l2.close = [](void * c) { ((std::ifstream *) c)->close(); };
+                std::unique_ptr<Replica> r(new Replica());
+                Vocab vtmp;
+                if (!model_load(&l2, r->model, vtmp, d)) { logf(LOG_WARN, "%s: no replica on GPU %d: %s\n", __func__, d, last_error()); continue; }
+                logf(LOG_INFO, "%s: replica of the weights on GPU %d\n", __func__, d);
+                ctx->replicas.push_back(std::move(r));
+            }
+            cudaSetDevice(params.gpu_device);
+        }
+    }
     return ctx;
 }
 
@@ -600,17 +625,23 @@ WB_EXPORT struct whisper_state * whisper_init_state(struct whisper_context * ctx
             st->decoders[0].rng = std::mt19937(0);
             return st;
         }
-        // every other state is a slot of the context's pool (created with the first state); see wb_state.h
+        // every other state is a slot of a device pool of the context (created with the first state); see wb_state.h.  With replicas on
+        // several GPUs the new state goes to the GPU that holds the fewest states (ties: the context's own device first).
+        Group * pool = nullptr; const Model * model = &ctx->model;
         {
-            static std::mutex pool_mu;
-            std::lock_guard<std::mutex> lk(pool_mu);
+            std::lock_guard<std::mutex> lk(ctx->replicas_mu);
             if (!ctx->pool) { ctx->pool.reset(new Group()); ctx->pool->model = &ctx->model; ctx->pool->scripted = ctx->scripted; }
+            pool = ctx->pool.get();
+            for (auto & r : ctx->replicas) {
+                if (!r->pool) { r->pool.reset(new Group()); r->pool->model = &r->model; }
+                if (r->pool->n_registered < pool->n_registered) { pool = r->pool.get(); model = &r->model; }
+            }
         }
-        std::unique_ptr<FrontEnd> fe = ctx->pool->take_fe();
+        std::unique_ptr<FrontEnd> fe = pool->take_fe();
         st = fe ? new whisper_state(std::move(fe)) : new whisper_state();
         st->scripted = ctx->scripted;
-        if (!ctx->scripted && !st->fe.st && !st->fe.init(&ctx->model)) { delete st; return nullptr; }
-        if (!ctx->pool->attach(st)) { logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); delete st; return nullptr; }
+        if (!ctx->scripted && !st->fe.st && !st->fe.init(model)) { delete st; return nullptr; }
+        if (!pool->attach(st)) { logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); delete st; return nullptr; }
         st->decoders[0].rng = std::mt19937(0);
     } catch (...) { set_error("whisper_init_state: allocation failed"); delete st; return nullptr; }
     return st;
@@ -955,6 +986,8 @@ WB_EXPORT int wb200_last_encode_ms(struct whisper_state * st, float * out4) {
     return 0;
 }
 WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx) { return ctx ? ctx->state : nullptr; }
+WB_EXPORT int wb200_state_device(struct whisper_state * st) { return (st && st->eng && st->eng->m) ? st->eng->m->device : -1; }
+WB_EXPORT int wb200_n_devices(struct whisper_context * ctx) { return ctx ? 1 + (int) ctx->replicas.size() : 0; }
 WB_EXPORT int wb200_pcm_upload(struct whisper_state * st, const float * samples, int n_samples) {
     if (!st || !samples || n_samples <= 0) return -1;
     return st->fe.pcm_upload(samples, n_samples) ? 0 : -1;

@@ -1055,6 +1055,7 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
                                   const int * n_samples, int n_chunks, struct whisper_state ** states_out, int flags) {
     if (!ctx || !samples || !n_samples || !states_out || n_chunks <= 0) return -1;
     if (ctx->params.dtw_token_timestamps) { set_error("wb200_full_batch: DTW token timestamps are not available in the lock-step driver"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
+    if ((flags & 1) && !ctx->replicas.empty()) { set_error("wb200_full_batch: device-pointer input needs a single-GPU context (WB200_DEVICES is set)"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
     if (params.vad) { set_error("wb200_full_batch: params.vad is not applied to pre-cut chunks; run whisper_vad_* first"); logf(LOG_ERROR, "%s: %s\n", __func__, last_error()); return -1; }
     int S = ctx->model.dec_tm ? 64 : 8;          // concurrent sequences: one row each in the decode pass (64 rows per launch of the persistent kernel)
     if (const char * e = getenv("WB200_BATCH_MEMBERS")) S = std::max(1, std::min(64, atoi(e)));

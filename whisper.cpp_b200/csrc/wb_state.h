@@ -115,6 +115,11 @@ struct whisper_state {
     std::vector<uint64_t> dbg_att;             // ... and per row a hash of the sorted positions it attends to (wb200_dbg_last_attended)
 };
 
+namespace wb {
+// a further copy of the weights on another GPU of the box, with its own device pool (WB200_DEVICES, wb_api.cpp)
+struct Replica { Model model; std::unique_ptr<Group> pool; };
+}
+
 struct whisper_context {
     int64_t t_load_us = 0, t_start_us = 0;
     whisper_context_params params;
@@ -125,6 +130,12 @@ struct whisper_context {
     bool scripted = false;                     // TEST HOOK: see whisper_state::scripted
     std::vector<std::pair<int, int>> dtw_heads; // (text layer, head) of the alignment heads when params.dtw_token_timestamps survived init
     std::unique_ptr<wb::Group> pool;           // device pool shared by every state of this context (created with the first state)
+    // In-library multi-GPU: with WB200_DEVICES=all (or a list "0,1,..") a context loaded from a FILE keeps one replica of the weights per
+    // listed GPU.  whisper_init_state places each new state on the GPU that holds the fewest, so whisper_full_parallel and concurrent
+    // whisper_full_with_state callers spread over the box without any change on their side; every GPU batches its own states (no
+    // collective, no data crosses GPUs: the chunks are independent -- src/whisper.cpp:7848-7869 semantics, N devices).
+    std::vector<std::unique_ptr<wb::Replica>> replicas;
+    std::mutex replicas_mu;
     ~whisper_context();
 };
 
