@@ -148,6 +148,46 @@ __device__ __noinline__ void mk_lnq(const MkArgs & a, const float * src, int K, 
     }
 }
 
+// LayerNorm + quantisation of ONE row by ONE warp (same arithmetic as mk_lnq: two passes, (x - mean) * rstd * w + b, Q8_0 blocks of 32)
+template <int WT>
+__device__ __forceinline__ void mk_ln_row_warp(const float * src, int row, int K, float eps, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst, int lane) {
+    const int nch = K >> 7;                                      // chunks of 128 values (a lane holds 4 consecutive values of each)
+    float s = 0.0f;
+    for (int ch = 0; ch < nch; ++ch) { const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + ch * 128 + lane * 4)); s += (v.x + v.y) + (v.z + v.w); }
+    const float mean = warp_sum(s) / K;
+    float q = 0.0f;
+    for (int ch = 0; ch < nch; ++ch) {
+        float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + ch * 128 + lane * 4));
+        v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / K + eps);
+    for (int ch = 0; ch < nch; ++ch) {
+        const int e0 = ch * 128 + lane * 4;
+        float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0));
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w + e0)), b = __ldg(reinterpret_cast<const float4 *>(ln_b + e0));
+        float4 y;
+        y.x = __fadd_rn(__fmul_rn(__fmul_rn(v.x - mean, rstd), w.x), b.x);
+        y.y = __fadd_rn(__fmul_rn(__fmul_rn(v.y - mean, rstd), w.y), b.y);
+        y.z = __fadd_rn(__fmul_rn(__fmul_rn(v.z - mean, rstd), w.z), b.z);
+        y.w = __fadd_rn(__fmul_rn(__fmul_rn(v.w - mean, rstd), w.w), b.w);
+        if (WT == WT_F16) {
+            const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + (size_t) row * K + e0) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        } else {
+            float amax = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
+            const uint32_t q0 = (uint32_t) __float2int_rn(y.x * id) & 0xffu, q1 = (uint32_t) __float2int_rn(y.y * id) & 0xffu;
+            const uint32_t q2 = (uint32_t) __float2int_rn(y.z * id) & 0xffu, q3 = (uint32_t) __float2int_rn(y.w * id) & 0xffu;
+            *reinterpret_cast<uint32_t *>(dst + (size_t) row * K + e0) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            if ((lane & 7) == 0) reinterpret_cast<float *>(dst + (size_t) MK_MAXTOK * K)[row * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
+        }
+    }
+}
+
 // quantise f32 rows (no LayerNorm) into the actq format: one warp per (row, 128 values); followed by a grid barrier
 template <int WT>
 __device__ __noinline__ void mk_q8_rows(const MkArgs & a, const float * src, int K, uint8_t * dst) {
@@ -187,6 +227,9 @@ struct MkEpi {
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
     uint8_t * qout = nullptr;            // PAIR epilogue: quantised rows [64][N] (+ block scales) for the next GEMV
+    // LayerNorm of the freshly written residual rows, done by the LAST CTA of each row group to finish (no separate phase, no extra
+    // grid barrier): weights of the norm that follows this matrix, destination of the quantised rows, arrival counters [row groups]
+    const float * ln_w = nullptr, * ln_b = nullptr; uint8_t * ln_dst = nullptr; int * ln_cnt = nullptr;
 };
 
 // L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per grid
@@ -411,6 +454,18 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
         if (it == 0) MK_FINE(4);
     }
     if (!staged) mbar_wait(SM_MBAR, stage_parity);               // a CTA without tiles still waits for its copies before the area is reused
+    if (e.ln_w) {
+        // the residual rows of this row group are complete once all of its `cg` CTAs are through: the last one to get here normalises
+        // and quantises them for the next matrix
+        __syncthreads();
+        if (tid == 0) { __threadfence(); SM_FLAG[3] = (atomicAdd(e.ln_cnt + grp, 1) == cg - 1); }
+        __syncthreads();
+        if (SM_FLAG[3]) {
+            __threadfence();
+            for (int r = warp; r < nt; r += MK_WARPS) mk_ln_row_warp<WT>(e.out, t_base + r, N, a.eps, e.ln_w, e.ln_b, e.ln_dst, lane);
+            if (tid == 0) e.ln_cnt[grp] = 0;
+        }
+    }
     MK_FINE(5);
 }
 
@@ -511,26 +566,28 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
 }
 
 #ifndef MK_OLD_ATTN
-// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); a pair of warps takes one (8 items per CTA at a time:
-// with 64 rows x 20 heads every item has its warps in the first round).  A lane owns a key quarter; the cells and the K / V pieces of
-// four key groups are requested together, so a row with 200 keys costs a handful of memory round trips instead of one per group.
+// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); ONE WARP takes one item (16 items per CTA at a time:
+// 64 rows x 20 heads = 1280 items all run in the first round on 148 x 16 warps, and no block-level merge is needed).  A lane owns a
+// key quarter of one of 8 key slots; the cells and the K / V pieces of four key groups are requested together, so a row with 200 keys
+// costs a handful of memory round trips instead of one per group.
 template <int WT>
 __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
-    constexpr int WPI = 2, SB = 4;                               // warps per item, key groups whose loads are issued together
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp / WPI, hw = warp % WPI;
+    constexpr int SB = 4;                                        // key groups whose loads are issued together
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
     const int kslot = lane >> 2, r = lane & 3;
-    for (int p = blockIdx.x * (MK_WARPS / WPI) + grp; p < n_pairs; p += gridDim.x * (MK_WARPS / WPI)) {
+    float * part = SM_PART + warp * MK_PART;
+    for (int p = blockIdx.x * MK_WARPS + warp; p < n_pairs; p += gridDim.x * MK_WARPS) {
         const int t = p / H, h = p - t * H;
         const int nk = a.nkv[t];
         const int * cells = a.idx + (size_t) t * a.ld_idx;
         float q[16];
         load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
         LaneAcc A; lane_init(A);
-        for (int k0 = hw * 8; k0 < nk; k0 += WPI * 8 * SB) {
+        for (int k0 = 0; k0 < nk; k0 += 8 * SB) {
             int cell[SB]; KV4 f[SB];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) { const int k = k0 + s * WPI * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
+            for (int s = 0; s < SB; ++s) { const int k = k0 + s * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
 #pragma unroll
             for (int s = 0; s < SB; ++s) {
                 f[s].k0 = f[s].k1 = f[s].v0 = f[s].v1 = make_uint4(0, 0, 0, 0);
@@ -548,15 +605,14 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
                 if (cell[s] >= 0) lane_update(A, sc, f[s].v0, f[s].v1);
             }
         }
-        warp_merge(A);
-        part_store(SM_PART + (grp * WPI + hw) * MK_PART, A, lane);
-        bar_named(1 + grp, WPI * 32);
-        {
-            float M, Lsum;
-            const float o = attn_merge(SM_PART + grp * WPI * MK_PART, WPI, hw * 32 + lane, M, Lsum);
-            mk_store_q<WT>(a.actq, d, t, h * 64 + hw * 32, lane, (Lsum > 0.0f) ? __fdividef(o, Lsum) : 0.0f);
-        }
-        bar_named(1 + grp, WPI * 32);
+        warp_merge(A);                                           // every lane now holds the totals of its quarter
+        part_store(part, A, lane);                               // lanes 0..3 -> (m, l, o[64]) in dimension order
+        __syncwarp();
+        const float Lsum = part[1];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+            mk_store_q<WT>(a.actq, d, t, h * 64 + hh * 32, lane, (Lsum > 0.0f) ? __fdividef(part[4 + hh * 32 + lane], Lsum) : 0.0f);
+        __syncwarp();
     }
 }
 
@@ -816,13 +872,13 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
     MK_STAMP();
     if (pf_w) mk_prefetch_w(a.layers[0].qkv);
 
+    // 1: LN -> quantised rows of the first layer (whisper.cpp:2536-2543); later layers get theirs from the FC2 phase in front of them
+    mk_lnq<WT>(a, a.x, d, a.layers[0].ln0_w, a.layers[0].ln0_b, a.actq);
     for (int l = 0; l < a.n_layer; ++l) {
         const MkLayer & L = a.layers[l];
         MkEpi e;
-        // 1: LN -> quantised rows (whisper.cpp:2536-2543)
-        mk_lnq<WT>(a, a.x, d, L.ln0_w, L.ln0_b, a.actq);
         if (pf_w) mk_prefetch_w(L.o);
-        MK_SYNC();
+        if (l == 0) { MK_SYNC(); } else { MK_STAMP(); MK_STAMP(); }
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
         mk_gemv<WT, false>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
@@ -831,13 +887,11 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         if (pf_w) mk_prefetch_w(L.cq);
         mk_attn_self<WT>(a, L);
         MK_SYNC();
-        // 4: O + residual (2647-2659)
+        // 4: O + residual (2647-2659), then LN of the finished rows (5) by the last CTA of each row group
         if (pf_w) mk_prefetch_w(L.co);
-        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
+        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnc_w; e.ln_b = L.lnc_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
         mk_gemv<WT, false>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
-        MK_SYNC();
-        // 5: LN -> quantised rows
-        mk_lnq<WT>(a, a.x, d, L.lnc_w, L.lnc_b, a.actq);
+        MK_STAMP(); MK_STAMP();                                  // (trace slots of the former LN phase)
         if (pf_w) mk_prefetch_w(L.fc1);
         MK_SYNC();
         // 6: cross Q (2661-2681)
@@ -848,27 +902,26 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
         if (pf_w) mk_prefetch_w(L.fc2);
         mk_attn_cross<WT>(a, L);
         MK_SYNC();
-        // 8: cross O + residual (2754-2766)
-        e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
+        // 8: cross O + residual (2754-2766), then LN (9)
+        e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnm_w; e.ln_b = L.lnm_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
         mk_gemv<WT, false>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
-        MK_SYNC();
-        // 9: LN -> quantised rows
-        mk_lnq<WT>(a, a.x, d, L.lnm_w, L.lnm_b, a.actq);
+        MK_STAMP(); MK_STAMP();
         if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
         MK_SYNC();
-        // 10: FC1 + GELU (2770-2794), then the rows are quantised for FC2
+        // 10: FC1 + GELU (2770-2794); the epilogue writes the quantised rows FC2 consumes
         e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.qout = a.hq;
         mk_gemv<WT, true>(a, L.fc1, a.actq, e, (TRACE && l == 1) ? 2048 + 32 : -1);
         MK_STAMP(); MK_STAMP();                                  // (trace slot of the former FC1 -> Q8_0 phase)
         MK_SYNC();
-        // 11: FC2 + residual (2797-2806)
+        // 11: FC2 + residual (2797-2806), then the LN in front of the next matrix: next layer's ln0, or the final norm before the logits
         e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
+        if (l + 1 < a.n_layer) { e.ln_w = a.layers[l + 1].ln0_w; e.ln_b = a.layers[l + 1].ln0_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt; }
+        else if (a.want_logits) { e.ln_w = a.lnf_w; e.ln_b = a.lnf_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt; }
         mk_gemv<WT, false>(a, L.fc2, a.hq, e, (TRACE && l == 1) ? 2048 + 40 : -1);
         MK_SYNC();
     }
-    if (a.want_logits) {                                         // final LN + logits (2811-2827)
-        mk_lnq<WT>(a, a.x, d, a.lnf_w, a.lnf_b, a.actq);
-        MK_SYNC();
+    if (a.want_logits) {                                         // logits (2811-2827); the final LN came with the last FC2
+        MK_STAMP(); MK_STAMP();
         MkEpi e; e.out = a.logits;
         mk_gemv<WT, false>(a, a.te, a.actq, e);
         MK_STAMP();
@@ -882,7 +935,7 @@ bool mk_cross_head_major() {
     return false;
 #endif
 }
-int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
+int mk_barriers(int n_layer, bool) { return 8 * n_layer + 1; }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
 size_t mk_smem_bytes(int, int) { return MK_SMEM; }
 int mk_max_rows() { return MK_MAXTOK; }
