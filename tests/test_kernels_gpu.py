@@ -153,3 +153,18 @@ def test_attention_decode_kernels(lib):
             sl = slice(h * 64, h * 64 + 64)
             want = rn.attention(q[t:t + 1, sl], kx[t, :1500, sl].astype(np.float32), vx[t, :1500, sl].astype(np.float32), scale, n_zero_keys=36)
             assert np.abs(out[t, sl] - want[0]).max() < 1e-4
+
+
+def test_whisper_bench_entry_points_measure_the_device(lib):
+    """whisper_bench_memcpy_str / whisper_bench_ggml_mul_mat_str (whisper.h:746-753, `whisper-bench -w 1|2`) report device copy bandwidth
+    and tcgen05 GEMM throughput"""
+    import ctypes as C
+    import re
+    lib.whisper_bench_memcpy_str.restype = C.c_char_p; lib.whisper_bench_ggml_mul_mat_str.restype = C.c_char_p
+    s = lib.whisper_bench_memcpy_str(1).decode()
+    gbs = [float(x) for x in re.findall(r"([\d.]+) GB/s", s)]
+    assert gbs and gbs[0] > 1000.0, s
+    s = lib.whisper_bench_ggml_mul_mat_str(1).decode()
+    tf = [float(x) for x in re.findall(r"([\d.]+) TFLOP/s", s)]
+    assert len(tf) == 6 and max(tf) > 300.0, s
+    print(s)

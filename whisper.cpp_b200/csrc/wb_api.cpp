@@ -13,6 +13,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 #include "wb_kernels.cuh"
+#include "wb_gemm.cuh"
 
 using namespace wb;
 
@@ -855,10 +856,60 @@ WB_EXPORT const char * whisper_print_system_info(void) {
 WB_EXPORT void whisper_log_set(ggml_log_callback cb, void * user_data) {
     set_log_sink(reinterpret_cast<void (*)(int, const char *, void *)>(cb), user_data);
 }
-WB_EXPORT int          whisper_bench_memcpy(int)           { logf(LOG_WARN, "whisper_bench_memcpy: ggml CPU micro-benchmark not available in this engine\n"); return 0; }
-WB_EXPORT const char * whisper_bench_memcpy_str(int)       { return "not supported by libwhisper_b200 (ggml CPU micro-benchmark)\n"; }
-WB_EXPORT int          whisper_bench_ggml_mul_mat(int)     { logf(LOG_WARN, "whisper_bench_ggml_mul_mat: ggml CPU micro-benchmark not available in this engine\n"); return 0; }
-WB_EXPORT const char * whisper_bench_ggml_mul_mat_str(int) { return "not supported by libwhisper_b200 (ggml CPU micro-benchmark)\n"; }
+// whisper_bench_memcpy / whisper_bench_ggml_mul_mat (whisper.h:746-753; `whisper-bench -w 1|2`): the reference measures its CPU backend's
+// memcpy and ggml_mul_mat; here the same entry points measure what this engine runs on -- device copy bandwidth and the tcgen05 GEMM.
+static std::string bench_memcpy_str() {
+    std::string out;
+    char line[256];
+    int dev = 0; cudaGetDevice(&dev);
+    const size_t bytes = (size_t) 1 << 30;
+    DevBuf<uint8_t> a, b;
+    if (!a.alloc(bytes, true) || !b.alloc(bytes)) return "memcpy: device allocation failed\n";
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int it = 0; it < 6; ++it) {
+        cudaEventRecord(e0); cudaMemcpyAsync(b.p, a.p, bytes, cudaMemcpyDeviceToDevice); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (it) best = std::max(best, 2.0 * bytes / 1e9 / (ms * 1e-3));
+    }
+    snprintf(line, sizeof(line), "memcpy: %8.2f GB/s (device %d, HBM read + write, 1 GiB copy, best of 5)\n", best, dev); out += line;
+    std::vector<uint8_t> h((size_t) 256 << 20, 1);
+    double h2d = 0.0;
+    for (int it = 0; it < 3; ++it) {
+        const int64_t t0 = time_us(); cudaMemcpy(a.p, h.data(), h.size(), cudaMemcpyHostToDevice); const int64_t t1 = time_us();
+        h2d = std::max(h2d, h.size() / 1e9 / ((t1 - t0) * 1e-6));
+    }
+    snprintf(line, sizeof(line), "memcpy: %8.2f GB/s (pageable host -> device, 256 MiB)\n", h2d); out += line;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return out;
+}
+static std::string bench_mul_mat_str() {
+    std::string out;
+    char line[256];
+    out += "tcgen05 GEMM, f16 x f16 -> f32 (persistent kernel, wb_gemm.cu); C[N][M] = A[M][K] . B[N][K]^T\n";
+    const int sizes[] = { 256, 512, 1024, 2048, 4096, 8192 };
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int n : sizes) {
+        DevBuf<__half> A, B; DevBuf<float> Cd;
+        if (!A.alloc((size_t) n * n, true) || !B.alloc((size_t) n * n, true) || !Cd.alloc((size_t) n * n)) break;
+        GemmDesc g; g.M = n; g.N = n; g.K = n; g.BN = 256; g.v2 = 1; g.A.type = WT_F16; g.A.base = A.p;
+        if (!make_tmap_f16(&g.tmA, A.p, n, n, 1, 1, n, 0, 0, 128) || !make_tmap_f16(&g.tmB, B.p, n, n, 1, 1, n, 0, 0, 256)) break;
+        g.ep.out = Cd.p; g.ep.ldo = n;
+        double best = 0.0;
+        for (int it = 0; it < 6; ++it) {
+            cudaEventRecord(e0); if (gemm_launch(g, 0) != cudaSuccess) break; cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            if (it) best = std::max(best, 2.0 * n * n * (double) n / 1e12 / (ms * 1e-3));
+        }
+        snprintf(line, sizeof(line), "%5d x %5d x %5d: %8.1f TFLOP/s\n", n, n, n, best); out += line;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return out;
+}
+WB_EXPORT const char * whisper_bench_memcpy_str(int)       { static std::string s; s = bench_memcpy_str(); return s.c_str(); }
+WB_EXPORT int          whisper_bench_memcpy(int n)         { logf(LOG_INFO, "%s", whisper_bench_memcpy_str(n)); return 0; }
+WB_EXPORT const char * whisper_bench_ggml_mul_mat_str(int) { static std::string s; s = bench_mul_mat_str(); return s.c_str(); }
+WB_EXPORT int          whisper_bench_ggml_mul_mat(int n)   { logf(LOG_INFO, "%s", whisper_bench_ggml_mul_mat_str(n)); return 0; }
 
 // ---------------------------------------------------------------------------------------------------- results
 #define SEG(st, i) ((st)->result_all[(size_t) (i)])
