@@ -50,7 +50,7 @@ bool Engine::init(const Model * model, int cap_windows) {
     use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
     fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
     gemm_v2 = getenv("WB200_GEMM_V1") == nullptr;
-    if (gemm_v2 && m->wtype != WT_F16 && m->wtype != WT_F32) {
+    if (gemm_v2 && m->wtype != WT_F16 && m->wtype != WT_F32 && !m->cross_kv.f16) {
         const size_t dd = (size_t) hp.n_audio_state * hp.n_audio_state;
         if (!wf16.alloc(std::max<size_t>(4 * dd, (size_t) 2 * hp.n_text_layer * dd))) return false;
     }
@@ -341,6 +341,10 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
         auto to_v2 = [&](GemmDesc & g, int64_t rows) -> bool {
             g.v2 = 1;
             if (g.A.type == WT_F16) return true;
+            if (g.A.f16) {                                        // expanded once at load (wb_model.cu)
+                g.a16 = const_cast<__half *>(g.A.f16); g.a16_keep = 1;
+                return make_tmap_f16(&g.tmA, g.A.f16, g.K, rows, 1, 1, g.K, 0, 0, 128);
+            }
             if (!E.wf16.p) { g.v2 = 0; return true; }
             g.a16 = E.wf16.p;
             return make_tmap_f16(&g.tmA, E.wf16.p, g.K, rows, 1, 1, g.K, 0, 0, 128);
@@ -410,7 +414,7 @@ bool Engine::encode(const EncSrc * srcs, int n_win, int n_ctx) {
     } else {                          // windows land in arbitrary cross-KV slots: one launch per window
         for (int w = 0; w < n_win; ++w) {
             GemmDesc g = PL.cross;
-            g.nb1 = 1; g.b1_in_off = w; g.a16_keep = (w > 0);
+            g.nb1 = 1; g.b1_in_off = w; g.a16_keep = (w > 0) || g.A.f16 != nullptr;
             g.ep.out = kv_cross.p + (size_t) srcs[w].slot * 2 * hp.n_text_layer * Tp_max * d;
             WB_GEMM(g);
         }

@@ -503,21 +503,26 @@ static cudaError_t launch2_t(const GemmDesc & g, const GemmKParams & kp, cudaStr
     return cudaGetLastError();
 }
 
-// expand the rows of g.A that this launch uses into g.a16 (f16 [rows][K]); rows = M x (stacked matrices)
-static cudaError_t dequant_launch(const GemmDesc & g, cudaStream_t st) {
-    const int64_t rows = g.a_rows_per_b0 ? (int64_t) g.a_rows_per_b0 * g.nb0 : g.M;
-    const int64_t n_blocks = rows * (g.K >> 5);
+cudaError_t dequant_to_f16(const QMat & W, int64_t rows, __half * out, cudaStream_t st) {
+    const int64_t n_blocks = rows * (W.K >> 5);
     const unsigned grid = (unsigned) ((n_blocks + 255) / 256);
-    switch (g.A.type) {
-        case WT_Q4_0: k_dequant_f16<WT_Q4_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
-        case WT_Q5_0: k_dequant_f16<WT_Q5_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
-        case WT_Q8_0: k_dequant_f16<WT_Q8_0><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
-        case WT_Q4_K: k_dequant_f16<WT_Q4_K><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
-        case WT_Q5_K: k_dequant_f16<WT_Q5_K><<<grid, 256, 0, st>>>(g.A.base, g.A.qs, g.A.qh, g.A.d, 0, n_blocks, g.K, g.a16); break;
+    switch (W.type) {
+        case WT_Q4_0: k_dequant_f16<WT_Q4_0><<<grid, 256, 0, st>>>(W.base, W.qs, W.qh, W.d, 0, n_blocks, W.K, out); break;
+        case WT_Q5_0: k_dequant_f16<WT_Q5_0><<<grid, 256, 0, st>>>(W.base, W.qs, W.qh, W.d, 0, n_blocks, W.K, out); break;
+        case WT_Q8_0: k_dequant_f16<WT_Q8_0><<<grid, 256, 0, st>>>(W.base, W.qs, W.qh, W.d, 0, n_blocks, W.K, out); break;
+        case WT_Q4_K: k_dequant_f16<WT_Q4_K><<<grid, 256, 0, st>>>(W.base, W.qs, W.qh, W.d, 0, n_blocks, W.K, out); break;
+        case WT_Q5_K: k_dequant_f16<WT_Q5_K><<<grid, 256, 0, st>>>(W.base, W.qs, W.qh, W.d, 0, n_blocks, W.K, out); break;
         default: return cudaErrorInvalidValue;
     }
     count_launch();
     return cudaGetLastError();
+}
+
+// expand the rows of g.A that this launch uses into g.a16 (f16 [rows][K]); rows = M x (stacked matrices)
+static cudaError_t dequant_launch(const GemmDesc & g, cudaStream_t st) {
+    const int64_t rows = g.a_rows_per_b0 ? (int64_t) g.a_rows_per_b0 * g.nb0 : g.M;
+    QMat W = g.A; W.K = g.K;
+    return dequant_to_f16(W, rows, g.a16, st);
 }
 
 cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {

@@ -60,4 +60,7 @@ bool make_tmap_f16(CUtensorMap * out, const void * base, uint64_t k, uint64_t ro
 // enqueue on `stream`; returns cudaError
 cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t stream);
 
+// expand `rows` rows of a quantised matrix (planar 32-blocks or verbatim K-quants) to f16 [rows][K]
+cudaError_t dequant_to_f16(const QMat & W, int64_t rows, __half * out, cudaStream_t stream);
+
 } // namespace wb

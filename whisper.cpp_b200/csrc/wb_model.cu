@@ -8,6 +8,7 @@
 #include "../../include/whisper_b200.h"
 #include <cstdlib>
 #include "wb_model.h"
+#include "wb_gemm.cuh"
 #include "wb_kernels.cuh"
 
 namespace wb {
@@ -381,6 +382,24 @@ bool model_load(whisper_model_loader * loader, Model & m, Vocab & vocab, int dev
     } else if (m.n_loaded != (int) dests.size()) {
         set_error("not all tensors loaded from model file - expected %zu, got %d", dests.size(), m.n_loaded);
         return false;
+    }
+    // Encoder-side matrices of a quantised model are kept a second time as f16 [N][K] (large-v3: 1.26 GB + 0.21 GB cross K/V projections
+    // next to the 0.58 GB of blocks): the persistent tensor-core GEMM takes both operands through TMA, and a 30-s window multiplies every
+    // weight by 1500 activations -- expanding once at load instead of once per launch (or, first generation, once per CTA) is free on a
+    // 180 GB part.  WB200_ENC_F16=0 keeps only the blocks (the GEMM then expands each matrix into a scratch per launch).
+    if (m.n_loaded > 0 && device >= 0 && m.wtype != WT_F16 && m.wtype != WT_F32 && !(getenv("WB200_ENC_F16") && atoi(getenv("WB200_ENC_F16")) == 0) &&
+        getenv("WB200_GEMM_V1") == nullptr) {
+        auto expand = [&](QMat & W) -> bool {
+            void * p = nullptr;
+            if (cudaMalloc(&p, (size_t) W.N * W.K * sizeof(__half)) != cudaSuccess) { set_error("cudaMalloc of the f16 expansion failed"); return false; }
+            m.allocs.push_back(p);
+            if (dequant_to_f16(W, W.N, (__half *) p, 0) != cudaSuccess) { set_error("dequant_to_f16 failed"); return false; }
+            W.f16 = (const __half *) p;
+            return true;
+        };
+        for (auto & L : m.enc) if (!expand(L.qk) || !expand(L.v) || !expand(L.o) || !expand(L.fc1) || !expand(L.fc2)) return false;
+        if (!expand(m.cross_kv)) return false;
+        WB_CUDA_OK(cudaDeviceSynchronize());
     }
     m.t_load_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     return true;

@@ -29,6 +29,8 @@ struct QMat {            // one weight matrix resident in HBM
     const uint32_t * qh = nullptr;
     const __half   * d  = nullptr;
     int   layout = 0;    // 0: rows (F16) / planar (32-blocks) / verbatim (K-quants); 1: tile-major records at `base` (see below)
+    const __half * f16 = nullptr;  // encoder-side matrices of quantised models: f16 expansion [N][K] made once at load (TMA operand of the
+                                   // persistent GEMM; each value is the f16 rounding of the exact d * (q - off)); nullptr = expand per launch
 };
 
 // "Tile-major" layout of the decoder matrices (persistent decode kernel, wb_decode_mk.cu).  The matrix is cut into tiles of
