@@ -541,11 +541,11 @@ def main():
             roof = {"kernel": names[dom], "bound": "hbm", "achieved": classes[names[dom]]["GBps"], "peak": hbm, "unit": "GB/s", "frac": classes[names[dom]]["GBps"] / hbm, "traffic": None, "peak_source": how}
         # DRAM traffic of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), if it is the same kernel
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_decode_pass.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_decode_pass.json")) as f:
                 cap = json.load(f)
             if dom == 1 and cap.get("rows") == min(n_chunks, 64):
                 roof["traffic"] = cap["dram_bytes_read"] + cap["dram_bytes_write"]
-                roof["traffic_source"] = "profiles/r01_ncu_decode_pass.json (one launch, %d rows)" % cap["rows"]
+                roof["traffic_source"] = "profiles/r02_ncu_decode_pass.json (one launch, %d rows)" % cap["rows"]
                 roof["algorithmic_bytes_per_launch"] = (by[dom] / ln[dom]) if ln[dom] else None
         except Exception:  # noqa: BLE001
             pass

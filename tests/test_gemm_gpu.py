@@ -49,7 +49,10 @@ CASES_V2 = [(w, M, N, K, BN, f | 4) for (w, M, N, K, BN, f) in CASES] + [
 ]
 
 
-@pytest.mark.parametrize("wtype,M,N,K,BN,flags", CASES + CASES_V2)
+CASES_CL2 = [(w, M, N, K, BN, f | 8) for (w, M, N, K, BN, f) in CASES_V2 if BN >= 128]     # CTA pairs + TMA multicast
+
+
+@pytest.mark.parametrize("wtype,M,N,K,BN,flags", CASES + CASES_V2 + CASES_CL2)
 def test_gemm_matches_dequantised_reference(lib, ref, wtype, M, N, K, BN, flags):
     rng = np.random.default_rng(1234 + M + 7 * N + 13 * K + wtype)
     w = (rng.standard_normal((M, K)) * 0.05).astype(np.float32)

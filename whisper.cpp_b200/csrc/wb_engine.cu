@@ -50,6 +50,7 @@ bool Engine::init(const Model * model, int cap_windows) {
     use_graphs = getenv("WB200_NO_GRAPHS") == nullptr;
     fused_attn = getenv("WB200_UNFUSED_ATTN") == nullptr;
     gemm_v2 = getenv("WB200_GEMM_V1") == nullptr;
+    gemm_cluster = !(getenv("WB200_GEMM_CLUSTER") && atoi(getenv("WB200_GEMM_CLUSTER")) == 0);
     if (gemm_v2 && m->wtype != WT_F16 && m->wtype != WT_F32 && !m->cross_kv.f16) {
         const size_t dd = (size_t) hp.n_audio_state * hp.n_audio_state;
         if (!wf16.alloc(std::max<size_t>(4 * dd, (size_t) 2 * hp.n_text_layer * dd))) return false;
@@ -289,16 +290,19 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
     }
     // activation-side tile: 256 tokens per CTA, or 128 when a d x NT GEMM would otherwise leave SMs idle (one window: 10 x 6 = 60 CTAs)
     const int bn = (((NT + 255) / 256) * ((d + 127) / 128) < E.n_sm) ? 128 : 256;
+    // CTA pairs share the activation tile by TMA multicast (gemm2_kernel<BN, 2>): each CTA of a pair fetches half of it, so the box is bn / 2 rows
+    const bool cl2 = E.gemm_v2 && E.gemm_cluster && (E.wf16.p || m.cross_kv.f16 || m.wtype == WT_F16 || m.wtype == WT_F32);
+    const int bbox = cl2 ? bn / 2 : bn;
     CUtensorMap tm_xn, tm_xn_win, tm_attn, tm_hfc, tm_q, tm_k, tm_p, tm_vt, tm_enc;
-    if (!make_tmap_f16(&tm_xn, E.xn.p, d, NT, 1, 1, d, 0, 0, bn)) return false;
-    if (!make_tmap_f16(&tm_xn_win, E.xn.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bn)) return false;
-    if (!make_tmap_f16(&tm_attn, E.attn.p, d, NT, 1, 1, d, 0, 0, bn)) return false;
-    if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, bn)) return false;
+    if (!make_tmap_f16(&tm_xn, E.xn.p, d, NT, 1, 1, d, 0, 0, bbox)) return false;
+    if (!make_tmap_f16(&tm_xn_win, E.xn.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bbox)) return false;
+    if (!make_tmap_f16(&tm_attn, E.attn.p, d, NT, 1, 1, d, 0, 0, bbox)) return false;
+    if (!make_tmap_f16(&tm_hfc, E.hfc.p, 4*d, NT, 1, 1, 4*d, 0, 0, bbox)) return false;
     if (!make_tmap_f16(&tm_q, E.qk.p,     64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 256)) return false;
     if (!make_tmap_f16(&tm_k, E.qk.p + d, 64, T, H, n_win, 2*d, 64, (uint64_t) T * 2 * d, 128)) return false;
     if (!E.fused_attn && !make_tmap_f16(&tm_p, E.P.p, Tp, T, H, n_win, Tp, (uint64_t) T * Tp, (uint64_t) H * T * Tp, 128)) return false;
     if (!make_tmap_f16(&tm_vt, E.vt.p, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) d * Tp, 64)) return false;
-    if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bn)) return false;
+    if (!make_tmap_f16(&tm_enc, E.enc16.p, d, T, n_win, 1, d, (uint64_t) T * d, 0, bbox)) return false;
 
     P.layers.resize(La);
     for (int l = 0; l < La; ++l) {
@@ -350,9 +354,12 @@ static bool build_plan(Engine & E, int n_ctx, int n_win) {
             return make_tmap_f16(&g.tmA, E.wf16.p, g.K, rows, 1, 1, g.K, 0, 0, 128);
         };
         if (!to_v2(P.conv1, 0) || !to_v2(P.conv2, 0) || !to_v2(P.conv2_tap, 0)) return false;
-        for (auto & lp : P.layers)
+        for (auto & lp : P.layers) {
             if (!to_v2(lp.qk, 2*d) || !to_v2(lp.v, d) || !to_v2(lp.o, d) || !to_v2(lp.fc1, 4*d) || !to_v2(lp.fc2, d)) return false;
+            for (GemmDesc * g : { &lp.qk, &lp.v, &lp.o, &lp.fc1, &lp.fc2 }) g->cluster2 = (cl2 && g->v2) ? 1 : 0;
+        }
         if (!to_v2(P.cross, (int64_t) 2 * Lt * d)) return false;
+        P.cross.cluster2 = (cl2 && P.cross.v2) ? 1 : 0;
     }
     return true;
 }

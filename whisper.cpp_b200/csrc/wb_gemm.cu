@@ -309,7 +309,11 @@ gemm_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const 
 //   warp 1      : MMA issuer     -- one thread, 4 x tcgen05.mma (K = 16) per 64-wide k-block; commits the stage's "empty" barrier and,
 //                                   after the last k-block of a tile, the accumulator's "full" barrier
 //   warps 2..9  : epilogue       -- wait "full", drain the accumulator (gemm_epilogue_tile), arrive on its "empty" barrier
-template <int BN>
+// CL = 2: CTA PAIRS (thread-block cluster of 2 along the weight-row direction) share the activation tile: each CTA fetches HALF of it and
+// multicasts it into both CTAs' shared memory, so a CTA pulls 32 KB instead of 48 KB from L2 per k-block.  (Measured: the 1-CTA kernel
+// sits at ~0.8 of what L2 can feed -- 48 KB per 128 x 256 x 64 block at ~42 B/clk/SM is twice the 542 clocks the tensor pipe needs.)  A stage
+// is refilled only when BOTH CTAs have consumed it: the MMA thread's commit arrives on the "empty" barrier of both (count 2).
+template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int n_mt, int n_nt, int n_tiles) {
     using Cfg = GemmCfg<BN>;
@@ -331,21 +335,25 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmA); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                               // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // tile list: with CL = 2 the CTAs of a pair take weight tiles 2q and 2q+1 of the same activation tile (n_mt is the number of PAIRS then)
+    const int crank = (CL > 1) ? (int) cluster_ctarank() : 0;
+    const int t_first = (CL > 1) ? (int) (blockIdx.x / CL) : (int) blockIdx.x, t_step = (int) gridDim.x / CL;
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int mt = t % n_mt, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
+            for (int t = t_first; t < n_tiles; t += t_step) {
+                const int mt = (t % n_mt) * CL + crank, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
                 const int b0 = z % p.nb0, b1 = z / p.nb0;
                 const int mg0 = mt * 128 + b0 * p.a_rows_per_b0, n0 = nt * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -354,7 +362,10 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[s], Cfg::B_TILE_BYTES + A_TILE_BYTES);
                     const int sel[4] = { 0, b0, b1 + p.b1_in_off, tap };
-                    tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, sel[p.b_zsel0], sel[p.b_zsel1]);
+                    if (CL > 1)                                    // my half of the activation tile, into both CTAs of the pair
+                        tma_load_4d_mc(sB + s * Cfg::B_TILE_BYTES + crank * (Cfg::B_TILE_BYTES / 2), &tmB, &full_bar[s], k0, n0 + crank * (BN / 2), sel[p.b_zsel0], sel[p.b_zsel1], (uint16_t) 3);
+                    else
+                        tma_load_4d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], k0, n0, sel[p.b_zsel0], sel[p.b_zsel1]);
                     tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], k0, mg0, sel[p.a_zsel0], sel[p.a_zsel1]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -365,7 +376,7 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
             const uint32_t idesc = umma_idesc_f16(128, BN);
             int s = 0; uint32_t ph = 0;
             int i = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            for (int t = t_first; t < n_tiles; t += t_step, ++i) {
                 const int acc = i & 1;
                 mbar_wait(&tempty[acc], (uint32_t) ((i >> 1) & 1) ^ 1u);       // the epilogue has drained this accumulator (first use: free)
                 tc_fence_after();
@@ -377,7 +388,7 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * Cfg::B_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16_ss(tacc, adesc + 2*k, bdesc + 2*k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
+                    if (CL > 1) umma_commit_mc(&empty_bar[s], (uint16_t) 3); else umma_commit(&empty_bar[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
@@ -385,8 +396,8 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
         }
     } else {
         int i = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-            const int mt = t % n_mt, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
+        for (int t = t_first; t < n_tiles; t += t_step, ++i) {
+            const int mt = (t % n_mt) * CL + crank, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
             const int b0 = z % p.nb0, b1 = z / p.nb0;
             const int acc = i & 1;
             mbar_wait(&tfull[acc], (uint32_t) ((i >> 1) & 1));
@@ -400,6 +411,7 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                               // nobody leaves while the peer may still multicast into it or arrive on its barriers
     if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
 }
 
@@ -492,15 +504,20 @@ static int gemm_n_sm() {
     return n;
 }
 
-template <int BN>
+template <int BN, int CL>
 static cudaError_t launch2_t(const GemmDesc & g, const GemmKParams & kp, cudaStream_t st) {
-    auto kern = gemm2_kernel<BN>;
+    auto kern = gemm2_kernel<BN, CL>;
     const size_t smem = GemmCfg<BN>::SMEM + 64;
     { const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem); if (e != cudaSuccess) return e; }
-    const int n_mt = (g.M + 127) / 128, n_nt = (g.N + BN - 1) / BN, n_tiles = n_mt * n_nt * g.nb0 * g.nb1;
-    kern<<<std::min(n_tiles, gemm_n_sm()), GEMM_THREADS, smem, st>>>(kp, g.tmA, g.tmB, n_mt, n_nt, n_tiles);
+    const int n_mt = ((g.M + 127) / 128 + CL - 1) / CL, n_nt = (g.N + BN - 1) / BN, n_tiles = n_mt * n_nt * g.nb0 * g.nb1;   // CL = 2: pairs of weight tiles
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) (CL * std::min(n_tiles, gemm_n_sm() / CL))); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = CL > 1 ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp, g.tmA, g.tmB, n_mt, n_nt, n_tiles);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t dequant_to_f16(const QMat & W, int64_t rows, __half * out, cudaStream_t st) {
@@ -537,10 +554,17 @@ cudaError_t gemm_launch(const GemmDesc & g, cudaStream_t st) {
     kp.ep = g.ep;
     if (g.v2 && (g.A.type == WT_F16 || g.a16)) {                  // persistent kernel: both operands f16 through TMA
         if (g.A.type != WT_F16 && !g.a16_keep) { const cudaError_t e = dequant_launch(g, st); if (e != cudaSuccess) return e; }
+        if (g.cluster2) {                                          // tmB's box holds BN / 2 rows then
+            switch (g.BN) {
+                case 128: return launch2_t<128, 2>(g, kp, st);
+                case 256: return launch2_t<256, 2>(g, kp, st);
+            }
+            return cudaErrorInvalidValue;
+        }
         switch (g.BN) {
-            case 64:  return launch2_t<64>(g, kp, st);
-            case 128: return launch2_t<128>(g, kp, st);
-            case 256: return launch2_t<256>(g, kp, st);
+            case 64:  return launch2_t<64, 1>(g, kp, st);
+            case 128: return launch2_t<128, 1>(g, kp, st);
+            case 256: return launch2_t<256, 1>(g, kp, st);
         }
         return cudaErrorInvalidValue;
     }

@@ -47,6 +47,7 @@ struct GemmDesc {
     CUtensorMap tmA;                  // valid when A.type == WT_F16, or when a16 is set (then it maps a16)
     __half * a16 = nullptr;           // quantised A: f16 scratch [rows][K] the persistent kernel's launch expands A into (shared by all launches of a stream)
     int v2 = 0;                       // 1: persistent double-buffered kernel (gemm2_kernel)
+    int cluster2 = 0;                 // 1 (with v2): CTA pairs share the activation tile by TMA multicast; tmB must then be built with box_rows = BN / 2
     int a16_keep = 0;                 // 1: a16 already holds this matrix (a launch sequence over the same weights expands them once)
     CUtensorMap tmB;
     GemmEpilogue ep;

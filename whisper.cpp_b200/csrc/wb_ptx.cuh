@@ -56,6 +56,20 @@ __device__ __forceinline__ void tma_load_4d(void * smem_dst, const CUtensorMap *
            "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// 4-D tiled load MULTICAST to the CTAs of the cluster named in cta_mask: the tile lands at the same CTA-relative smem offset in each of them and
+// completes bytes on the mbarrier at the same offset in each
+__device__ __forceinline__ void tma_load_4d_mc(void * smem_dst, const CUtensorMap * m, uint64_t * bar, int c0, int c1, int c2, int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+           "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t * smem_dst) { // whole warp
@@ -136,6 +150,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
         :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, on the mbarrier at this offset in EVERY CTA of the cluster named in cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t * bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 // arrive on an mbarrier once every previously issued tcgen05 op of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {
