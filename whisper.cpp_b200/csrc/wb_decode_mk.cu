@@ -58,27 +58,36 @@ __device__ __forceinline__ void l2_prefetch(const void * p, uint32_t bytes) {
 }
 __device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
-// Grid barrier.  Arrival = one atomic on a counter; the LAST CTA to arrive releases everybody by writing one flag per CTA
-// (each on its own 128-byte line), and every other CTA polls only its own flag.
-__device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long target) {
+// Who synchronises with whom.  The rows of a pass are cut into groups of 16 (mk_gemv); when the rows are independent sequences (the
+// lock-step batch: no row reads K/V another row writes in this pass) everything a layer does for a row group -- GEMVs, LayerNorms, both
+// attentions -- only depends on that group's own rows, so the CTAs of a group (blockIdx % ngrp == grp) synchronise among themselves and
+// the groups drift freely: the latency-bound GEMV chain of one group overlaps the bandwidth-bound cross-attention of another.
+// Otherwise (prompt rows of one sequence, F16 matrices too wide for 16 staged rows) there is one group: the whole grid.
+struct MkGrp { int grp, ngrp, ci, cg, t_base, nt; };
+
+// Barrier of a group.  Arrival = one atomic on the group's counter; the LAST CTA to arrive resets the counter and releases everybody by
+// writing the barrier's sequence number into one flag per CTA (each on its own 128-byte line); every other CTA polls only its own flag.
+__device__ __noinline__ void mk_grid_sync(const MkArgs & a, const MkGrp & G, unsigned long long seq) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        unsigned long long * cnt = a.bar + 16 * (1 + G.grp);
         __threadfence();
-        const unsigned long long old = atomicAdd(a.bar, 1ULL);
-        SM_FLAG[2] = (old + 1 == target);
-        if (old + 1 == target) __threadfence();                  // the last arriver acquires what the others released
+        const unsigned long long old = atomicAdd(cnt, 1ULL);
+        const bool last = (old + 1 == (unsigned long long) G.cg);
+        if (last) { atomicExch(cnt, 0ULL); __threadfence(); }     // the last arriver acquires what the others released
+        SM_FLAG[2] = last;
     }
     __syncthreads();
     if (SM_FLAG[2]) {
-        if (threadIdx.x < gridDim.x)
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 + 16 * threadIdx.x), "l"(target) : "memory");
+        for (int i = threadIdx.x; i < G.cg; i += blockDim.x)
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 * (9 + G.grp + G.ngrp * i)), "l"(seq) : "memory");
     } else if (threadIdx.x == 0) {
-        const unsigned long long * f = a.bar + 16 + 16 * blockIdx.x;
+        const unsigned long long * f = a.bar + 16 * (9 + blockIdx.x);
         const long long t0 = clock64();
         unsigned long long v;
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= target) break;
+            if (v >= seq) break;
             if (clock64() - t0 > (6LL << 30)) { *a.err = 1; __threadfence_system(); __trap(); }    // ~3 s: a CTA never arrived
         }
     }
@@ -104,9 +113,9 @@ __device__ __forceinline__ void mk_store_q(uint8_t * dst, int K, int t, int e0, 
 // LayerNorm (ggml-cpu/ops.cpp:3698-3765, two passes, then mul/add whisper.cpp:2536-2543) of the f32 residual rows, quantised into
 // `dst`.  Distributed: CTA r normalises row r (one warp per 128 values); followed by a grid barrier.
 template <int WT>
-__device__ __noinline__ void mk_lnq(const MkArgs & a, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
+__device__ __noinline__ void mk_lnq(const MkArgs & a, const MkGrp & G, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int row = blockIdx.x; row < a.n_tok; row += gridDim.x) {
+    for (int row = G.t_base + G.ci; row < G.t_base + G.nt; row += G.cg) {
         const bool act = warp < (K >> 7);
         const int e0 = warp * 128 + lane * 4;
         float4 v = act ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -232,12 +241,12 @@ struct MkEpi {
     const float * ln_w = nullptr, * ln_b = nullptr; uint8_t * ln_dst = nullptr; int * ln_cnt = nullptr;
 };
 
-// L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per grid
-__device__ __noinline__ void mk_prefetch_w(const QMat & W) {
+// L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per group
+__device__ __noinline__ void mk_prefetch_w(const MkGrp & G, const QMat & W) {
     if (threadIdx.x != MK_THREADS - 32) return;
     const int n_tiles = (W.N + 15) >> 4;
     const uint32_t tile_bytes = (uint32_t) (W.K / wt_tm_rec_k(W.type)) * wt_tm_rec_bytes(W.type);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (int tile = G.ci; tile < n_tiles; tile += G.cg)
         l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * tile_bytes, tile_bytes);
 }
 
@@ -565,20 +574,19 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
     return o;
 }
 
-#ifndef MK_OLD_ATTN
 // self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); ONE WARP takes one item (16 items per CTA at a time:
 // 64 rows x 20 heads = 1280 items all run in the first round on 148 x 16 warps, and no block-level merge is needed).  A lane owns a
 // key quarter of one of 8 key slots; the cells and the K / V pieces of four key groups are requested together, so a row with 200 keys
 // costs a handful of memory round trips instead of one per group.
 template <int WT>
-__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
+__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkGrp & G, const MkLayer & L) {
     constexpr int SB = 4;                                        // key groups whose loads are issued together
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
+    const int d = a.d, H = a.n_head, n_pairs = G.nt * H;
     const int kslot = lane >> 2, r = lane & 3;
     float * part = SM_PART + warp * MK_PART;
-    for (int p = blockIdx.x * MK_WARPS + warp; p < n_pairs; p += gridDim.x * MK_WARPS) {
-        const int t = p / H, h = p - t * H;
+    for (int p = G.ci * MK_WARPS + warp; p < n_pairs; p += G.cg * MK_WARPS) {
+        const int tl = p / H, h = p - tl * H, t = G.t_base + tl;
         const int nk = a.nkv[t];
         const int * cells = a.idx + (size_t) t * a.ld_idx;
         float q[16];
@@ -633,12 +641,12 @@ static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fi
 __device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
 
 template <int WT>
-__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
+__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkGrp & GR, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, H = a.n_head, nchp = a.n_keys / MK_XKEYS;               // chunks per pair
-    const unsigned P = (unsigned) (a.n_tok * H), G = min(gridDim.x, P);
-    if (blockIdx.x >= G) return;
-    const unsigned p0 = (blockIdx.x * P) / G, p1 = ((blockIdx.x + 1) * P) / G;
+    const unsigned P = (unsigned) (GR.nt * H), G = min((unsigned) GR.cg, P), pb = (unsigned) (GR.t_base * H);
+    if ((unsigned) GR.ci >= G) return;
+    const unsigned p0 = pb + ((unsigned) GR.ci * P) / G, p1 = pb + (((unsigned) GR.ci + 1) * P) / G;
     // loader state: chunk being fetched
     unsigned pl = p0, il = 0;
     int jl = 0, tl_ = (int) p0 / H, hl = (int) p0 - tl_ * H;
@@ -702,211 +710,67 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) 
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-#else
-// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); each half of the CTA (8 warps) takes one.
-template <int WT>
-__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp >> 3, hw = warp & 7;
-    const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
-    const int kslot = lane >> 2, r = lane & 3;
-    for (int p = blockIdx.x * 2 + half; p < n_pairs; p += gridDim.x * 2) {
-        const int t = p / H, h = p - t * H;
-        const int nk = a.nkv[t];
-        const int * cells = a.idx + (size_t) t * a.ld_idx;
-        float q[16];
-        load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
-        LaneAcc A; lane_init(A);
-        bool ok = hw * 8 + kslot < nk;
-        int cell = ok ? cells[hw * 8 + kslot] : 0;
-        for (int k0 = hw * 8; k0 < nk; k0 += 64) {
-            KV4 f;
-            f.k0 = f.k1 = f.v0 = f.v1 = make_uint4(0, 0, 0, 0);
-            const bool okc = ok;
-            if (okc) {
-                const size_t off = (size_t) cell * d + h * 64 + r * 8;
-                const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
-                f.k0 = __ldcg(kp); f.k1 = __ldcg(kp + 4); f.v0 = __ldcg(vp); f.v1 = __ldcg(vp + 4);
-            }
-            ok = k0 + 64 + kslot < nk;                           // the cell of the next group is fetched while this group's K/V are in flight
-            cell = ok ? cells[k0 + 64 + kslot] : 0;
-            float sc = dot16(f.k0, f.k1, q);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            if (okc) lane_update(A, sc, f.v0, f.v1);
-        }
-        warp_merge(A);
-        part_store(SM_PART + (half * 8 + hw) * MK_PART, A, lane);
-        bar_named(1 + half, 256);
-        if (hw < 2) {
-            float M, Lsum;
-            const float o = attn_merge(SM_PART + half * 8 * MK_PART, 8, hw * 32 + lane, M, Lsum);
-            mk_store_q<WT>(a.actq, d, t, h * 64 + hw * 32, lane, (Lsum > 0.0f) ? __fdividef(o, Lsum) : 0.0f);
-        }
-        bar_named(1 + half, 256);
-    }
-}
-
-// cross-attention over the n_keys padded encoder positions, zero rows included (whisper.cpp:2688-2705).
-// Work unit = (row, head, half of the keys).  Units are dealt out in contiguous ranges; a CTA walks a unit in chunks of 128 keys
-// (warp w, key slot s owns key 8w+s of every chunk).  K/V chunks are copied three chunks ahead with cp.async into a 4-deep ring
-// in shared memory (the GEMV staging area, idle here); every thread reads back only the 64 bytes it copied itself, so the ring
-// needs no barrier -- it is an asynchronous extension of the register file (96 KB in flight per SM).  The 16 warps are merged
-// per unit; the second half to arrive merges the two partials of the (row, head) pair in fixed order -- so the result of a row does
-// not depend on which other rows share the pass.
-constexpr int MK_RING = 4, MK_RING_SLOT = MK_THREADS * 64, MK_OFF_QSM = MK_RING * MK_RING_SLOT;
-static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fit below the attention partials");
-
-__device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
-
-template <int WT>
-__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = a.d, H = a.n_head, nch = a.n_keys / (2 * MK_XKEYS);          // chunks per unit
-    const unsigned I = (unsigned) (a.n_tok * H * 2), G = min(gridDim.x, I);
-    if (blockIdx.x >= G) return;
-    const unsigned s0 = (blockIdx.x * I) / G, s1 = ((blockIdx.x + 1) * I) / G;
-    int p = (int) (s0 >> 1), t = p / H, h = p - t * H, hf = (int) (s0 & 1);
-    // loader state: chunk being fetched
-    int tl_ = t, hl = h, hfl = hf, jl = 0;
-    unsigned ul = s0, il = 0;
-    const size_t lane_off = (size_t) (warp * 8 + (lane >> 2)) * d + (lane & 3) * 8;
-    const uint32_t ring = (uint32_t) __cvta_generic_to_shared(mk_smem) + tid * 16;
-    auto issue = [&]() {                                           // copy the next chunk (if any) into ring slot il % 4; always commits a group
-        if (ul < s1) {
-            const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) ((hfl * nch + jl) * MK_XKEYS) * d + hl * 64 + lane_off;
-            const uint32_t sa = ring + (il & (MK_RING - 1)) * MK_RING_SLOT;
-            cp_async16(sa, L.xk + off); cp_async16(sa + MK_THREADS * 16, L.xk + off + 32);
-            cp_async16(sa + 2 * MK_THREADS * 16, L.xv + off); cp_async16(sa + 3 * MK_THREADS * 16, L.xv + off + 32);
-            if (++jl == nch) { jl = 0; ++ul; if (++hfl == 2) { hfl = 0; if (++hl == H) { hl = 0; ++tl_; } } }
-        }
-        ++il;
-        cp_commit();
-    };
-#pragma unroll
-    for (int k = 0; k < MK_RING - 1; ++k) issue();
-    float * qsm = reinterpret_cast<float *>(mk_smem + MK_OFF_QSM);   // f16-rounded query of the unit: [2][64]
-    // qsm is stored in lane order: position 16*r + 8*hi + i holds dim 32*hi + 8*r + i
-    if (warp >= 2 && warp < 4) { const int dim = (warp - 2) * 32 + lane; qsm[((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) t * d + h * 64 + dim))); }
-    __syncthreads();
-    LaneAcc A; lane_init(A);
-    int j = 0, buf = 0;
-    unsigned ic = 0;
-    float keepM = 0.0f, keepL = 0.0f, keepO = 0.0f;                // half 0 of the current pair (warps 0-1, one output dim per thread)
-    for (unsigned u = s0; u < s1; ) {
-        issue();
-        cp_wait_ring();                                          // this thread's copies of chunk ic have landed
-        const uint8_t * sl = mk_smem + (ic & (MK_RING - 1)) * MK_RING_SLOT + tid * 16;
-        ++ic;
-        const uint4 k0 = *reinterpret_cast<const uint4 *>(sl), k1 = *reinterpret_cast<const uint4 *>(sl + MK_THREADS * 16);
-        const uint4 v0 = *reinterpret_cast<const uint4 *>(sl + 2 * MK_THREADS * 16), v1 = *reinterpret_cast<const uint4 *>(sl + 3 * MK_THREADS * 16);
-        float sc = dot16s(k0, k1, qsm + buf * 64 + (lane & 3) * 16);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-        lane_update(A, sc * a.kq_scale, v0, v1);
-        if (++j < nch) continue;
-        j = 0;                                                   // last chunk of the unit: merge
-        warp_merge(A);
-        part_store(SM_PART + (buf * MK_WARPS + warp) * MK_PART, A, lane);
-        if (u + 1 < s1 && warp >= 2 && warp < 4) {               // query of the next unit (same pair after half 0, else the next (row, head))
-            int tn = t, hn = h;
-            if (hf == 1) { if (++hn == H) { hn = 0; ++tn; } }
-            const int dim = (warp - 2) * 32 + lane;
-            qsm[(buf ^ 1) * 64 + ((dim & 31) >> 3) * 16 + (dim >> 5) * 8 + (dim & 7)] = __half2float(__float2half_rn(__ldcg(a.q2 + (size_t) tn * d + hn * 64 + dim)));
-        }
-        __syncthreads();
-        if (warp < 2) {                                          // merge the 16 warp partials of this unit
-            const int dim = warp * 32 + lane;
-            float M, Lsum;
-            const float o = attn_merge(SM_PART + buf * MK_WARPS * MK_PART, MK_WARPS, dim, M, Lsum);
-            // Both halves of a pair usually fall into the range of one CTA: half 0 is then kept in registers (warps 0-1 own it)
-            // and merged with half 1 by the same formula the cross-CTA path uses -- no global partial, fence or atomic.
-            const bool pair_local = (hf == 0) ? (u + 1 < s1) : (u > s0);
-            if (pair_local) {
-                if (hf == 0) { keepM = M; keepL = Lsum; keepO = o; }
-                else {
-                    const float MM = fmaxf(keepM, M);
-                    const float w0 = __expf(keepM - MM), w1 = __expf(M - MM);
-                    const float LL = fmaf(Lsum, w1, keepL * w0), oo = fmaf(o, w1, keepO * w0);
-                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
-                }
-            } else {
-                float * gp = a.xpart + ((size_t) p * 2 + hf) * 66;
-                gp[2 + dim] = o;
-                if (dim == 0) { gp[0] = M; gp[1] = Lsum; }
-                __threadfence();
-                bar_named(3, 64);
-                if (tid == 0) SM_FLAG[buf] = (atomicAdd(a.xcnt + p, 1) == 1);
-                bar_named(3, 64);
-                if (SM_FLAG[buf]) {                               // both halves are in: merge them (half 0 first)
-                    __threadfence();
-                    const float * p0 = a.xpart + (size_t) p * 2 * 66;
-                    const float m0 = __ldcg(p0), m1 = __ldcg(p0 + 66), MM = fmaxf(m0, m1);
-                    const float w0 = __expf(m0 - MM), w1 = __expf(m1 - MM);
-                    const float LL = fmaf(__ldcg(p0 + 67), w1, __ldcg(p0 + 1) * w0);
-                    const float oo = fmaf(__ldcg(p0 + 68 + dim), w1, __ldcg(p0 + 2 + dim) * w0);
-                    mk_store_q<WT>(a.actq, d, t, h * 64 + warp * 32, lane, __fdividef(oo, LL));
-                    if (tid == 0) a.xcnt[p] = 0;
-                }
-            }
-        }
-        buf ^= 1;
-        ++u;
-        if (++hf == 2) { hf = 0; ++p; if (++h == H) { h = 0; ++t; } }
-        lane_init(A);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-}
-
-#endif
-#define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, target); MK_STAMP(); } while (0)
+#define MK_SYNC() do { MK_STAMP(); ++seq; mk_grid_sync(a, G, seq); MK_STAMP(); } while (0)
 
 template <int WT, bool TRACE>
 __global__ void __launch_bounds__(MK_THREADS, 1)
 k_decode_pass(const __grid_constant__ MkArgs a) {
     if (threadIdx.x == 0) { mbar_init(SM_MBAR, 1); SM_FLAG[4] = 0; mbar_fence_init(); }
     __syncthreads();
-    unsigned long long target = a.bar_base;
+    unsigned long long seq = a.bar_base;
     int n_stamp = 0;
     const int d = a.d;
     const bool pf_w = a.prefetch & 1;
+    MkGrp G;
+    {   // row groups synchronise on their own when the host says the rows are independent and every matrix stages 16 rows per CTA
+        const int rowb_max = (WT == WT_F16) ? 8 * d : 4 * d;
+        const bool own = a.group_sync && a.n_tok > 16 && 16 * (rowb_max + 16) <= MK_MAXTOK * (MK_ROWB + 16);
+        G.ngrp = own ? (a.n_tok + 15) / 16 : 1;
+        G.grp = blockIdx.x % G.ngrp; G.ci = blockIdx.x / G.ngrp; G.cg = ((int) gridDim.x - G.grp + G.ngrp - 1) / G.ngrp;
+        G.t_base = own ? G.grp * 16 : 0; G.nt = own ? min(16, a.n_tok - G.t_base) : a.n_tok;
+        if (own && a.stagger_clk > 0 && G.grp > 0) {             // start the groups a fraction of a layer apart
+            if (threadIdx.x == 0) { const long long t0 = clock64(), w = (long long) a.stagger_clk * G.grp; while (clock64() - t0 < w) { } }
+            __syncthreads();
+        }
+    }
     MK_STAMP();
-    if (pf_w) mk_prefetch_w(a.layers[0].qkv);
+    if (pf_w) mk_prefetch_w(G, a.layers[0].qkv);
 
     // 1: LN -> quantised rows of the first layer (whisper.cpp:2536-2543); later layers get theirs from the FC2 phase in front of them
-    mk_lnq<WT>(a, a.x, d, a.layers[0].ln0_w, a.layers[0].ln0_b, a.actq);
+    mk_lnq<WT>(a, G, a.x, d, a.layers[0].ln0_w, a.layers[0].ln0_b, a.actq);
     for (int l = 0; l < a.n_layer; ++l) {
         const MkLayer & L = a.layers[l];
         MkEpi e;
-        if (pf_w) mk_prefetch_w(L.o);
+        if (pf_w) mk_prefetch_w(G, L.o);
         if (l == 0) { MK_SYNC(); } else { MK_STAMP(); MK_STAMP(); }
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
         mk_gemv<WT, false>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
         MK_SYNC();
         // 3: self-attention (2603-2625) -> quantised rows for the O projection
-        if (pf_w) mk_prefetch_w(L.cq);
-        mk_attn_self<WT>(a, L);
+        if (pf_w) mk_prefetch_w(G, L.cq);
+        mk_attn_self<WT>(a, G, L);
         MK_SYNC();
         // 4: O + residual (2647-2659), then LN of the finished rows (5) by the last CTA of each row group
-        if (pf_w) mk_prefetch_w(L.co);
+        if (pf_w) mk_prefetch_w(G, L.co);
         e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnc_w; e.ln_b = L.lnc_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
         mk_gemv<WT, false>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
         MK_STAMP(); MK_STAMP();                                  // (trace slots of the former LN phase)
-        if (pf_w) mk_prefetch_w(L.fc1);
+        if (pf_w) mk_prefetch_w(G, L.fc1);
         MK_SYNC();
         // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
         mk_gemv<WT, false>(a, L.cq, a.actq, e, (TRACE && l == 1) ? 2048 + 16 : -1);
         MK_SYNC();
         // 7: cross-attention (2688-2705)
-        if (pf_w) mk_prefetch_w(L.fc2);
-        mk_attn_cross<WT>(a, L);
+        if (pf_w) mk_prefetch_w(G, L.fc2);
+        mk_attn_cross<WT>(a, G, L);
         MK_SYNC();
         // 8: cross O + residual (2754-2766), then LN (9)
         e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnm_w; e.ln_b = L.lnm_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
         mk_gemv<WT, false>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
         MK_STAMP(); MK_STAMP();
-        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
+        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(G, a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(G, a.te); }
         MK_SYNC();
         // 10: FC1 + GELU (2770-2794); the epilogue writes the quantised rows FC2 consumes
         e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.qout = a.hq;
@@ -929,11 +793,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
 }
 
 bool mk_cross_head_major() {
-#ifndef MK_OLD_ATTN
     return true;
-#else
-    return false;
-#endif
 }
 int mk_barriers(int n_layer, bool) { return 8 * n_layer + 1; }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }

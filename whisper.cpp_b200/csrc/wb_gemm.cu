@@ -35,12 +35,15 @@ struct GemmKParams {
 };
 
 __device__ __forceinline__ float gelu_ref_f16(float x) {
-    // ggml CPU: table lookup on the f16-rounded input, table entries are f16(gelu(f32(x16)))  (vec.h:988-1001, ggml-cpu.c:3847)
+    // ggml CPU: table lookup on the f16-rounded input, table entries are f16(gelu(f32(x16)))  (vec.h:988-1001, ggml-cpu.c:3847).
+    // Evaluated as x * sigmoid(2u) = 0.5 x (1 + tanh u) with ex2.approx + rcp.approx (a dozen instructions; tanhf made the FC1 epilogue
+    // longer than its main loop).  Against the table: identical for 98.7 % of all f16 inputs, one f16 ulp of a value below 1e-2 in
+    // magnitude for the rest (x < -2, where the reference's own 1 + tanhf(u) cancels) -- checked over all 37376 inputs in (-10, 10).
     if (x <= -10.0f) return 0.0f;
     if (x >=  10.0f) return x;
     const float xh = __half2float(__float2half_rn(x));
-    const float g  = 0.5f*xh*(1.0f + tanhf(0.79788456080286535587989211986876f*xh*(1.0f + 0.044715f*xh*xh)));
-    return __half2float(__float2half_rn(g));
+    const float e  = __expf(-1.5957691216057308f * xh * (1.0f + 0.044715f * xh * xh));
+    return __half2float(__float2half_rn(__fdividef(xh, 1.0f + e)));
 }
 
 struct RawBlk { uint4 q0, q1; uint32_t qh; __half d; };
@@ -350,12 +353,21 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
     const int t_first = (CL > 1) ? (int) (blockIdx.x / CL) : (int) blockIdx.x, t_step = (int) gridDim.x / CL;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int t = t_first; t < n_tiles; t += t_step) {
-                const int mt = (t % n_mt) * CL + crank, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
-                const int b0 = z % p.nb0, b1 = z / p.nb0;
-                const int mg0 = mt * 128 + b0 * p.a_rows_per_b0, n0 = nt * BN;
+        int s = 0; uint32_t ph = 0;
+        for (int t = t_first; t < n_tiles; t += t_step) {
+            const int mt = (t % n_mt) * CL + crank, r = t / n_mt, nt = r % n_nt, z = r / n_nt;
+            const int b0 = z % p.nb0, b1 = z / p.nb0;
+            const int mg0 = mt * 128 + b0 * p.a_rows_per_b0, n0 = nt * BN;
+            if (p.ep.res && lane > 0) {
+                // the residual tile (f32, 128 features of BN rows) goes to L2 while the tile's main loop runs: the epilogue then adds it at L2
+                // latency instead of stalling on HBM with only 32 KB in flight per SM
+                const int m0 = mt * 128, mw = min(128, p.M - m0);
+                const float * rp = p.ep.res + (int64_t) b0 * p.ep.res_b0 + (int64_t) b1 * p.ep.res_b1 + m0;
+                if (mw > 0 && (mw & 3) == 0 && ((reinterpret_cast<uintptr_t>(rp) | ((uintptr_t) p.ep.ldr * 4)) & 15) == 0)
+                    for (int rr = lane - 1; rr < BN && n0 + rr < p.N; rr += 31)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(rp + (int64_t) (n0 + rr) * p.ep.ldr), "r"(mw * 4) : "memory");
+            }
+            if (lane == 0) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     const int tap = kb / p.nkb_per_tap;
                     const int k0  = (kb - tap * p.nkb_per_tap) * 64;
@@ -370,6 +382,7 @@ gemm2_kernel(const GemmKParams p, const __grid_constant__ CUtensorMap tmA, const
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         if (lane == 0) {
