@@ -70,6 +70,15 @@ void prof_collect(double * ms, uint64_t * launches, double * bytes, double * flo
         if (cudaEventElapsedTime(&t, e.e0, e.e1) != cudaSuccess) continue;
         ms[e.cls] += t; launches[e.cls]++; bytes[e.cls] += e.bytes; flops[e.cls] += e.flops;
     }
+    if (const char * path = getenv("WB200_PROF_DUMP")) {         // every scope on its own line: class, ms, bytes, flops (launch order)
+        if (FILE * f = fopen(path, "w")) {
+            for (auto & e : g_prof_entries) {
+                float t = 0.0f;
+                if (cudaEventElapsedTime(&t, e.e0, e.e1) == cudaSuccess) fprintf(f, "%d %.6f %.0f %.0f\n", e.cls, t, e.bytes, e.flops);
+            }
+            fclose(f);
+        }
+    }
 }
 
 // log sink: installed by whisper_log_set (wb_api.cpp); signature mirrors ggml_log_callback

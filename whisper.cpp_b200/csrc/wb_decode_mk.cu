@@ -56,38 +56,28 @@ constexpr int MK_SMEM     = MK_OFF_FLAG + 16 * 4;
 __device__ __forceinline__ void l2_prefetch(const void * p, uint32_t bytes) {
     if (bytes >= 16) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes & ~15u) : "memory");
 }
-__device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
-// Who synchronises with whom.  The rows of a pass are cut into groups of 16 (mk_gemv); when the rows are independent sequences (the
-// lock-step batch: no row reads K/V another row writes in this pass) everything a layer does for a row group -- GEMVs, LayerNorms, both
-// attentions -- only depends on that group's own rows, so the CTAs of a group (blockIdx % ngrp == grp) synchronise among themselves and
-// the groups drift freely: the latency-bound GEMV chain of one group overlaps the bandwidth-bound cross-attention of another.
-// Otherwise (prompt rows of one sequence, F16 matrices too wide for 16 staged rows) there is one group: the whole grid.
-struct MkGrp { int grp, ngrp, ci, cg, t_base, nt; };
-
-// Barrier of a group.  Arrival = one atomic on the group's counter; the LAST CTA to arrive resets the counter and releases everybody by
-// writing the barrier's sequence number into one flag per CTA (each on its own 128-byte line); every other CTA polls only its own flag.
-__device__ __noinline__ void mk_grid_sync(const MkArgs & a, const MkGrp & G, unsigned long long seq) {
+// Grid barrier.  Arrival = one atomic on a counter; the LAST CTA to arrive releases everybody by writing one flag per CTA
+// (each on its own 128-byte line), and every other CTA polls only its own flag.
+__device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long * cnt = a.bar + 16 * (1 + G.grp);
         __threadfence();
-        const unsigned long long old = atomicAdd(cnt, 1ULL);
-        const bool last = (old + 1 == (unsigned long long) G.cg);
-        if (last) { atomicExch(cnt, 0ULL); __threadfence(); }     // the last arriver acquires what the others released
-        SM_FLAG[2] = last;
+        const unsigned long long old = atomicAdd(a.bar, 1ULL);
+        SM_FLAG[2] = (old + 1 == target);
+        if (old + 1 == target) __threadfence();                  // the last arriver acquires what the others released
     }
     __syncthreads();
     if (SM_FLAG[2]) {
-        for (int i = threadIdx.x; i < G.cg; i += blockDim.x)
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 * (9 + G.grp + G.ngrp * i)), "l"(seq) : "memory");
+        if (threadIdx.x < gridDim.x)
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 + 16 * threadIdx.x), "l"(target) : "memory");
     } else if (threadIdx.x == 0) {
-        const unsigned long long * f = a.bar + 16 * (9 + blockIdx.x);
+        const unsigned long long * f = a.bar + 16 + 16 * blockIdx.x;
         const long long t0 = clock64();
         unsigned long long v;
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= seq) break;
+            if (v >= target) break;
             if (clock64() - t0 > (6LL << 30)) { *a.err = 1; __threadfence_system(); __trap(); }    // ~3 s: a CTA never arrived
         }
     }
@@ -113,9 +103,9 @@ __device__ __forceinline__ void mk_store_q(uint8_t * dst, int K, int t, int e0, 
 // LayerNorm (ggml-cpu/ops.cpp:3698-3765, two passes, then mul/add whisper.cpp:2536-2543) of the f32 residual rows, quantised into
 // `dst`.  Distributed: CTA r normalises row r (one warp per 128 values); followed by a grid barrier.
 template <int WT>
-__device__ __noinline__ void mk_lnq(const MkArgs & a, const MkGrp & G, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
+__device__ __noinline__ void mk_lnq(const MkArgs & a, const float * src, int K, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int row = G.t_base + G.ci; row < G.t_base + G.nt; row += G.cg) {
+    for (int row = blockIdx.x; row < a.n_tok; row += gridDim.x) {
         const bool act = warp < (K >> 7);
         const int e0 = warp * 128 + lane * 4;
         float4 v = act ? __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -154,46 +144,6 @@ __device__ __noinline__ void mk_lnq(const MkArgs & a, const MkGrp & G, const flo
             }
         }
         __syncthreads();
-    }
-}
-
-// LayerNorm + quantisation of ONE row by ONE warp (same arithmetic as mk_lnq: two passes, (x - mean) * rstd * w + b, Q8_0 blocks of 32)
-template <int WT>
-__device__ __forceinline__ void mk_ln_row_warp(const float * src, int row, int K, float eps, const float * __restrict__ ln_w, const float * __restrict__ ln_b, uint8_t * dst, int lane) {
-    const int nch = K >> 7;                                      // chunks of 128 values (a lane holds 4 consecutive values of each)
-    float s = 0.0f;
-    for (int ch = 0; ch < nch; ++ch) { const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + ch * 128 + lane * 4)); s += (v.x + v.y) + (v.z + v.w); }
-    const float mean = warp_sum(s) / K;
-    float q = 0.0f;
-    for (int ch = 0; ch < nch; ++ch) {
-        float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + ch * 128 + lane * 4));
-        v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
-        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) / K + eps);
-    for (int ch = 0; ch < nch; ++ch) {
-        const int e0 = ch * 128 + lane * 4;
-        float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (size_t) row * K + e0));
-        const float4 w = __ldg(reinterpret_cast<const float4 *>(ln_w + e0)), b = __ldg(reinterpret_cast<const float4 *>(ln_b + e0));
-        float4 y;
-        y.x = __fadd_rn(__fmul_rn(__fmul_rn(v.x - mean, rstd), w.x), b.x);
-        y.y = __fadd_rn(__fmul_rn(__fmul_rn(v.y - mean, rstd), w.y), b.y);
-        y.z = __fadd_rn(__fmul_rn(__fmul_rn(v.z - mean, rstd), w.z), b.z);
-        y.w = __fadd_rn(__fmul_rn(__fmul_rn(v.w - mean, rstd), w.w), b.w);
-        if (WT == WT_F16) {
-            const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
-            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(dst) + (size_t) row * K + e0) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-        } else {
-            float amax = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-            const float id = (amax != 0.0f) ? __fdividef(127.0f, amax) : 0.0f;
-            const uint32_t q0 = (uint32_t) __float2int_rn(y.x * id) & 0xffu, q1 = (uint32_t) __float2int_rn(y.y * id) & 0xffu;
-            const uint32_t q2 = (uint32_t) __float2int_rn(y.z * id) & 0xffu, q3 = (uint32_t) __float2int_rn(y.w * id) & 0xffu;
-            *reinterpret_cast<uint32_t *>(dst + (size_t) row * K + e0) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-            if ((lane & 7) == 0) reinterpret_cast<float *>(dst + (size_t) MK_MAXTOK * K)[row * (K >> 5) + (e0 >> 5)] = __half2float(__float2half_rn(amax * (1.0f / 127.0f)));
-        }
     }
 }
 
@@ -236,17 +186,14 @@ struct MkEpi {
     const float * bias = nullptr, * scale = nullptr; int act = 0; const float * res = nullptr; float * out = nullptr;
     __half * kc = nullptr, * vc = nullptr; int kv_d = 0;
     uint8_t * qout = nullptr;            // PAIR epilogue: quantised rows [64][N] (+ block scales) for the next GEMV
-    // LayerNorm of the freshly written residual rows, done by the LAST CTA of each row group to finish (no separate phase, no extra
-    // grid barrier): weights of the norm that follows this matrix, destination of the quantised rows, arrival counters [row groups]
-    const float * ln_w = nullptr, * ln_b = nullptr; uint8_t * ln_dst = nullptr; int * ln_cnt = nullptr;
 };
 
-// L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per group
-__device__ __noinline__ void mk_prefetch_w(const MkGrp & G, const QMat & W) {
+// L2 prefetch of weight tiles for a later GEMV phase (tile-major: the records of a tile are contiguous); every tile once per grid
+__device__ __noinline__ void mk_prefetch_w(const QMat & W) {
     if (threadIdx.x != MK_THREADS - 32) return;
     const int n_tiles = (W.N + 15) >> 4;
     const uint32_t tile_bytes = (uint32_t) (W.K / wt_tm_rec_k(W.type)) * wt_tm_rec_bytes(W.type);
-    for (int tile = G.ci; tile < n_tiles; tile += G.cg)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         l2_prefetch(reinterpret_cast<const uint8_t *>(W.base) + (size_t) tile * tile_bytes, tile_bytes);
 }
 
@@ -463,18 +410,6 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
         if (it == 0) MK_FINE(4);
     }
     if (!staged) mbar_wait(SM_MBAR, stage_parity);               // a CTA without tiles still waits for its copies before the area is reused
-    if (e.ln_w) {
-        // the residual rows of this row group are complete once all of its `cg` CTAs are through: the last one to get here normalises
-        // and quantises them for the next matrix
-        __syncthreads();
-        if (tid == 0) { __threadfence(); SM_FLAG[3] = (atomicAdd(e.ln_cnt + grp, 1) == cg - 1); }
-        __syncthreads();
-        if (SM_FLAG[3]) {
-            __threadfence();
-            for (int r = warp; r < nt; r += MK_WARPS) mk_ln_row_warp<WT>(e.out, t_base + r, N, a.eps, e.ln_w, e.ln_b, e.ln_dst, lane);
-            if (tid == 0) e.ln_cnt[grp] = 0;
-        }
-    }
     MK_FINE(5);
 }
 
@@ -574,28 +509,26 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
     return o;
 }
 
-// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); ONE WARP takes one item (16 items per CTA at a time:
-// 64 rows x 20 heads = 1280 items all run in the first round on 148 x 16 warps, and no block-level merge is needed).  A lane owns a
-// key quarter of one of 8 key slots; the cells and the K / V pieces of four key groups are requested together, so a row with 200 keys
-// costs a handful of memory round trips instead of one per group.
+// self-attention over the paged cache (whisper.cpp:2603-2625).  Item = (row, head); a pair of warps takes one (8 items per CTA at a time:
+// with 64 rows x 20 heads every item has its warps in the first round).  A lane owns a key quarter; the cells and the K / V pieces of
+// four key groups are requested together, so a row with 200 keys costs a handful of memory round trips instead of one per group.
 template <int WT>
-__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkGrp & G, const MkLayer & L) {
-    constexpr int SB = 4;                                        // key groups whose loads are issued together
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = a.d, H = a.n_head, n_pairs = G.nt * H;
+__device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
+    constexpr int WPI = 2, SB = 4;                               // warps per item, key groups whose loads are issued together
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp / WPI, hw = warp % WPI;
+    const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
     const int kslot = lane >> 2, r = lane & 3;
-    float * part = SM_PART + warp * MK_PART;
-    for (int p = G.ci * MK_WARPS + warp; p < n_pairs; p += G.cg * MK_WARPS) {
-        const int tl = p / H, h = p - tl * H, t = G.t_base + tl;
+    for (int p = blockIdx.x * (MK_WARPS / WPI) + grp; p < n_pairs; p += gridDim.x * (MK_WARPS / WPI)) {
+        const int t = p / H, h = p - t * H;
         const int nk = a.nkv[t];
         const int * cells = a.idx + (size_t) t * a.ld_idx;
         float q[16];
         load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
         LaneAcc A; lane_init(A);
-        for (int k0 = 0; k0 < nk; k0 += 8 * SB) {
+        for (int k0 = hw * 8; k0 < nk; k0 += WPI * 8 * SB) {
             int cell[SB]; KV4 f[SB];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) { const int k = k0 + s * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
+            for (int s = 0; s < SB; ++s) { const int k = k0 + s * WPI * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
 #pragma unroll
             for (int s = 0; s < SB; ++s) {
                 f[s].k0 = f[s].k1 = f[s].v0 = f[s].v1 = make_uint4(0, 0, 0, 0);
@@ -613,14 +546,15 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkGrp & G, con
                 if (cell[s] >= 0) lane_update(A, sc, f[s].v0, f[s].v1);
             }
         }
-        warp_merge(A);                                           // every lane now holds the totals of its quarter
-        part_store(part, A, lane);                               // lanes 0..3 -> (m, l, o[64]) in dimension order
-        __syncwarp();
-        const float Lsum = part[1];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-            mk_store_q<WT>(a.actq, d, t, h * 64 + hh * 32, lane, (Lsum > 0.0f) ? __fdividef(part[4 + hh * 32 + lane], Lsum) : 0.0f);
-        __syncwarp();
+        warp_merge(A);
+        part_store(SM_PART + (grp * WPI + hw) * MK_PART, A, lane);
+        bar_named(1 + grp, WPI * 32);
+        {
+            float M, Lsum;
+            const float o = attn_merge(SM_PART + grp * WPI * MK_PART, WPI, hw * 32 + lane, M, Lsum);
+            mk_store_q<WT>(a.actq, d, t, h * 64 + hw * 32, lane, (Lsum > 0.0f) ? __fdividef(o, Lsum) : 0.0f);
+        }
+        bar_named(1 + grp, WPI * 32);
     }
 }
 
@@ -641,12 +575,12 @@ static_assert(MK_OFF_QSM + 2 * 64 * 4 <= MK_OFF_PART, "the cp.async ring must fi
 __device__ __forceinline__ void cp_wait_ring() { asm volatile("cp.async.wait_group %0;" :: "n"(MK_RING - 1) : "memory"); }
 
 template <int WT>
-__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkGrp & GR, const MkLayer & L) {
+__device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = a.d, H = a.n_head, nchp = a.n_keys / MK_XKEYS;               // chunks per pair
-    const unsigned P = (unsigned) (GR.nt * H), G = min((unsigned) GR.cg, P), pb = (unsigned) (GR.t_base * H);
-    if ((unsigned) GR.ci >= G) return;
-    const unsigned p0 = pb + ((unsigned) GR.ci * P) / G, p1 = pb + (((unsigned) GR.ci + 1) * P) / G;
+    const unsigned P = (unsigned) (a.n_tok * H), G = min(gridDim.x, P);
+    if (blockIdx.x >= G) return;
+    const unsigned p0 = (blockIdx.x * P) / G, p1 = ((blockIdx.x + 1) * P) / G;
     // loader state: chunk being fetched
     unsigned pl = p0, il = 0;
     int jl = 0, tl_ = (int) p0 / H, hl = (int) p0 - tl_ * H;
@@ -710,82 +644,73 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkGrp & GR, c
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-#define MK_SYNC() do { MK_STAMP(); ++seq; mk_grid_sync(a, G, seq); MK_STAMP(); } while (0)
+#define MK_SYNC() do { MK_STAMP(); target += gridDim.x; mk_grid_sync(a, target); MK_STAMP(); } while (0)
 
 template <int WT, bool TRACE>
 __global__ void __launch_bounds__(MK_THREADS, 1)
 k_decode_pass(const __grid_constant__ MkArgs a) {
     if (threadIdx.x == 0) { mbar_init(SM_MBAR, 1); SM_FLAG[4] = 0; mbar_fence_init(); }
     __syncthreads();
-    unsigned long long seq = a.bar_base;
+    unsigned long long target = a.bar_base;
     int n_stamp = 0;
     const int d = a.d;
     const bool pf_w = a.prefetch & 1;
-    MkGrp G;
-    {   // row groups synchronise on their own when the host says the rows are independent and every matrix stages 16 rows per CTA
-        const int rowb_max = (WT == WT_F16) ? 8 * d : 4 * d;
-        const bool own = a.group_sync && a.n_tok > 16 && 16 * (rowb_max + 16) <= MK_MAXTOK * (MK_ROWB + 16);
-        G.ngrp = own ? (a.n_tok + 15) / 16 : 1;
-        G.grp = blockIdx.x % G.ngrp; G.ci = blockIdx.x / G.ngrp; G.cg = ((int) gridDim.x - G.grp + G.ngrp - 1) / G.ngrp;
-        G.t_base = own ? G.grp * 16 : 0; G.nt = own ? min(16, a.n_tok - G.t_base) : a.n_tok;
-        if (own && a.stagger_clk > 0 && G.grp > 0) {             // start the groups a fraction of a layer apart
-            if (threadIdx.x == 0) { const long long t0 = clock64(), w = (long long) a.stagger_clk * G.grp; while (clock64() - t0 < w) { } }
-            __syncthreads();
-        }
-    }
     MK_STAMP();
-    if (pf_w) mk_prefetch_w(G, a.layers[0].qkv);
+    if (pf_w) mk_prefetch_w(a.layers[0].qkv);
 
-    // 1: LN -> quantised rows of the first layer (whisper.cpp:2536-2543); later layers get theirs from the FC2 phase in front of them
-    mk_lnq<WT>(a, G, a.x, d, a.layers[0].ln0_w, a.layers[0].ln0_b, a.actq);
     for (int l = 0; l < a.n_layer; ++l) {
         const MkLayer & L = a.layers[l];
         MkEpi e;
-        if (pf_w) mk_prefetch_w(G, L.o);
-        if (l == 0) { MK_SYNC(); } else { MK_STAMP(); MK_STAMP(); }
+        // 1: LN -> quantised rows (whisper.cpp:2536-2543)
+        mk_lnq<WT>(a, a.x, d, L.ln0_w, L.ln0_b, a.actq);
+        if (pf_w) mk_prefetch_w(L.o);
+        MK_SYNC();
         // 2: QKV + KV append (2545-2599)
         e = MkEpi(); e.bias = L.qkv_bias; e.scale = L.qkv_scale; e.out = a.qkv; e.kc = L.kc; e.vc = L.vc; e.kv_d = d;
         mk_gemv<WT, false>(a, L.qkv, a.actq, e, (TRACE && l == 1) ? 2048 + 0 : -1);
         MK_SYNC();
         // 3: self-attention (2603-2625) -> quantised rows for the O projection
-        if (pf_w) mk_prefetch_w(G, L.cq);
-        mk_attn_self<WT>(a, G, L);
+        if (pf_w) mk_prefetch_w(L.cq);
+        mk_attn_self<WT>(a, L);
         MK_SYNC();
-        // 4: O + residual (2647-2659), then LN of the finished rows (5) by the last CTA of each row group
-        if (pf_w) mk_prefetch_w(G, L.co);
-        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnc_w; e.ln_b = L.lnc_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
+        // 4: O + residual (2647-2659)
+        if (pf_w) mk_prefetch_w(L.co);
+        e = MkEpi(); e.bias = L.o_bias; e.res = a.x; e.out = a.x;
         mk_gemv<WT, false>(a, L.o, a.actq, e, (TRACE && l == 1) ? 2048 + 8 : -1);
-        MK_STAMP(); MK_STAMP();                                  // (trace slots of the former LN phase)
-        if (pf_w) mk_prefetch_w(G, L.fc1);
+        MK_SYNC();
+        // 5: LN -> quantised rows
+        mk_lnq<WT>(a, a.x, d, L.lnc_w, L.lnc_b, a.actq);
+        if (pf_w) mk_prefetch_w(L.fc1);
         MK_SYNC();
         // 6: cross Q (2661-2681)
         e = MkEpi(); e.bias = L.cq_bias; e.out = a.q2;
         mk_gemv<WT, false>(a, L.cq, a.actq, e, (TRACE && l == 1) ? 2048 + 16 : -1);
         MK_SYNC();
         // 7: cross-attention (2688-2705)
-        if (pf_w) mk_prefetch_w(G, L.fc2);
-        mk_attn_cross<WT>(a, G, L);
+        if (pf_w) mk_prefetch_w(L.fc2);
+        mk_attn_cross<WT>(a, L);
         MK_SYNC();
-        // 8: cross O + residual (2754-2766), then LN (9)
-        e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x; e.ln_w = L.lnm_w; e.ln_b = L.lnm_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt;
+        // 8: cross O + residual (2754-2766)
+        e = MkEpi(); e.bias = L.co_bias; e.res = a.x; e.out = a.x;
         mk_gemv<WT, false>(a, L.co, a.actq, e, (TRACE && l == 1) ? 2048 + 24 : -1);
-        MK_STAMP(); MK_STAMP();
-        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(G, a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(G, a.te); }
         MK_SYNC();
-        // 10: FC1 + GELU (2770-2794); the epilogue writes the quantised rows FC2 consumes
+        // 9: LN -> quantised rows
+        mk_lnq<WT>(a, a.x, d, L.lnm_w, L.lnm_b, a.actq);
+        if (pf_w) { if (l + 1 < a.n_layer) mk_prefetch_w(a.layers[l + 1].qkv); else if (a.want_logits) mk_prefetch_w(a.te); }
+        MK_SYNC();
+        // 10: FC1 + GELU (2770-2794), then the rows are quantised for FC2
         e = MkEpi(); e.bias = L.fc1_bias; e.act = 1; e.qout = a.hq;
         mk_gemv<WT, true>(a, L.fc1, a.actq, e, (TRACE && l == 1) ? 2048 + 32 : -1);
         MK_STAMP(); MK_STAMP();                                  // (trace slot of the former FC1 -> Q8_0 phase)
         MK_SYNC();
-        // 11: FC2 + residual (2797-2806), then the LN in front of the next matrix: next layer's ln0, or the final norm before the logits
+        // 11: FC2 + residual (2797-2806)
         e = MkEpi(); e.bias = L.fc2_bias; e.res = a.x; e.out = a.x;
-        if (l + 1 < a.n_layer) { e.ln_w = a.layers[l + 1].ln0_w; e.ln_b = a.layers[l + 1].ln0_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt; }
-        else if (a.want_logits) { e.ln_w = a.lnf_w; e.ln_b = a.lnf_b; e.ln_dst = a.actq; e.ln_cnt = a.xcnt; }
         mk_gemv<WT, false>(a, L.fc2, a.hq, e, (TRACE && l == 1) ? 2048 + 40 : -1);
         MK_SYNC();
     }
-    if (a.want_logits) {                                         // logits (2811-2827); the final LN came with the last FC2
-        MK_STAMP(); MK_STAMP();
+    if (a.want_logits) {                                         // final LN + logits (2811-2827)
+        mk_lnq<WT>(a, a.x, d, a.lnf_w, a.lnf_b, a.actq);
+        MK_SYNC();
         MkEpi e; e.out = a.logits;
         mk_gemv<WT, false>(a, a.te, a.actq, e);
         MK_STAMP();
@@ -795,7 +720,7 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
 bool mk_cross_head_major() {
     return true;
 }
-int mk_barriers(int n_layer, bool) { return 8 * n_layer + 1; }
+int mk_barriers(int n_layer, bool want_logits) { return 11 * n_layer + (want_logits ? 1 : 0); }
 bool mk_supported(int wtype) { return wtype == WT_F16 || wt_is_block32(wtype); }
 size_t mk_smem_bytes(int, int) { return MK_SMEM; }
 int mk_max_rows() { return MK_MAXTOK; }

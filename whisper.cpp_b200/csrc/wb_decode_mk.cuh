@@ -29,18 +29,14 @@ struct MkArgs {
     float * h;                        // FC1 + GELU output [R][4d]
     uint8_t * actq, * hq;             // quantised rows handed between phases: K = d (>= R*d*2 + R*d/8 bytes) and K = 4d
     float * xpart; int * xcnt;        // cross-attention partials [R*H][16][66] and arrival counters [R*H]
-    unsigned long long * bar;         // barriers: [16*(1+g)] arrival counter of row group g (back to 0 after every barrier), [16*(9+cta)] release flag of each
-                                      // CTA (sequence number of the last barrier it was released from), [8] error flag
-    unsigned long long bar_base;      // sequence number of the last barrier of the launch before (monotonic; the host adds >= mk_barriers())
-    int group_sync;                   // the rows are independent sequences (no row attends to K/V another row writes in this pass): row groups of
-                                      // 16 may synchronise on their own
-    int stagger_clk;                  // with group_sync: group g starts g * stagger_clk SM clocks late
+    unsigned long long * bar;         // grid barrier: [0] arrival counter (monotonic, never reset), [16 + 16*cta] release flag of each CTA
+    unsigned long long bar_base;      // its value when this launch starts
     int * err;                        // set to 1 when a barrier wait times out
     long long * trace;                // optional: phase time stamps of CTA 0 (see MK_STAMP)
     int prefetch;                     // bit0: next-phase weights -> L2, bit1: cross KV -> L2 one phase ahead
 };
 
-// number of barriers one launch passes (host keeps bar_base in step)
+// number of grid barriers one launch passes (host keeps bar_base in step)
 int  mk_barriers(int n_layer, bool want_logits);
 bool mk_supported(int wtype);
 size_t mk_smem_bytes(int wtype, int d);

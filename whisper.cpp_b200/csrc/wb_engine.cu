@@ -67,9 +67,7 @@ bool Engine::init(const Model * model, int cap_windows) {
             set_error("decode: the persistent kernel cannot run on this device/model; set WB200_MEGAKERNEL=0"); return false;
         }
         if (const char * pf = getenv("WB200_MK_PREFETCH")) mk_prefetch = atoi(pf);
-        if (const char * pf = getenv("WB200_MK_GROUPS")) mk_groups = atoi(pf);
-        if (const char * pf = getenv("WB200_MK_STAGGER_US")) mk_stagger_us = atoi(pf);
-        if (use_mk && !mk_bar.alloc(16 * (size_t) (9 + n_sm), true)) return false;
+        if (use_mk && !mk_bar.alloc(32 + 16 * (size_t) n_sm, true)) return false;
         sm_ghz = prop.clockRate * 1e-6;
         if (const char * tp = getenv("WB200_MK_TRACE")) { if (use_mk && *tp) { mk_trace_path = tp; if (!mk_trace.alloc(4096, true)) return false; } }
     }
@@ -471,23 +469,6 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         a.actq = reinterpret_cast<uint8_t *>(dattn.p); a.h = dh.p; a.hq = dhq.p;
         a.xpart = xpart.p; a.xcnt = xcnt.p;
         a.bar = mk_bar.p; a.bar_base = mk_bar_total; a.err = reinterpret_cast<int *>(mk_bar.p + 8); a.prefetch = mk_prefetch; a.trace = mk_trace.p;
-        // Row groups of 16 may run on their own barriers when no row attends to a cell that a row of ANOTHER group writes in this pass
-        // (independent sequences, one token each: the lock-step batch).  Prompt rows of one sequence keep the whole grid in step.
-        a.group_sync = 0; a.stagger_clk = 0;
-        if (mk_groups && n > 16) {
-            if ((int) cell_writer.size() < n_cells) cell_writer.assign(n_cells, 0);
-            const int * h_cell = hints + 2 * R, * h_nkv = hints + 4 * R, * h_idx = hints + 7 * R;
-            bool indep = true;
-            for (int j = 0; j < n; ++j) if (h_cell[j] >= 0 && h_cell[j] < n_cells) cell_writer[h_cell[j]] = j / 16 + 1;
-            for (int j = 0; j < n && indep; ++j)
-                for (int k = 0; k < h_nkv[j]; ++k) {
-                    const int c = h_idx[(size_t) j * ld_idx + k];
-                    if (c >= 0 && c < n_cells && cell_writer[c] && cell_writer[c] != j / 16 + 1) { indep = false; break; }
-                }
-            for (int j = 0; j < n; ++j) if (h_cell[j] >= 0 && h_cell[j] < n_cells) cell_writer[h_cell[j]] = 0;
-            a.group_sync = indep ? 1 : 0;
-            a.stagger_clk = mk_stagger_us * 1900;
-        }
         // algorithmic bytes of one pass: every decoder weight once, the cross K/V of each row, the self K/V each row attends to
         double wbytes = 0.0, flops = 0.0;
         for (int l = 0; l < Lt; ++l) {

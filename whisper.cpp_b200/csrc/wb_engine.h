@@ -76,10 +76,9 @@ struct Engine {
     bool dtw_finish(const std::vector<std::pair<int, int>> & heads, int slot, int n_audio_ctx, std::vector<float> & qk);
     bool use_mk = false;
     int  max_rows = 8;               // rows per decode pass: 64 with the persistent kernel, 8 with the chain
-    int  n_sm = 0, mk_prefetch = 1, mk_groups = 1, mk_stagger_us = 0;      // WB200_MK_PREFETCH / WB200_MK_GROUPS / WB200_MK_STAGGER_US
-    std::vector<int> cell_writer;                                         // scratch of decode_pass_enqueue: row group that writes a cell in this pass, +1
+    int  n_sm = 0, mk_prefetch = 1;
     DevBuf<MkLayer> mk_layers;
-    DevBuf<unsigned long long> mk_bar;   // see MkArgs::bar
+    DevBuf<unsigned long long> mk_bar;   // [0] arrival counter, [8] error flag, [16 + 16*cta] release flags
     unsigned long long mk_bar_total = 0;
     bool mk_build_table();
     // WB200_MK_TRACE=<file>: per-phase clock stamps of CTA 0, averaged over all passes, written when the engine is destroyed

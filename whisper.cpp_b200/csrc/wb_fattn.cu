@@ -13,7 +13,9 @@
 //           O += P_j V_j (8 x tcgen05.mma M128 N64 K16) accumulated in TMEM, l += sum p
 // Knowing m before any exponent is taken removes the online-softmax rescaling of O (no TMEM read-modify-write, no
 // correction warps); the price is recomputing QK^T once: +1/3 tensor work on 14% of the encoder flops.
-// Roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2..5 softmax + epilogue (thread = query row).
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2..9 softmax + epilogue: a query row is shared by two threads (TMEM
+// lane quarter = warp % 4), each takes 64 of the 128 keys of a block -- the phase is bound by the 16 ex2 per clock of the SM, and four
+// warps alone could not keep that pipe busy across the TMEM-load / barrier latencies.
 #include "wb_gemm.cuh"
 #include "wb_ptx.cuh"
 #include "wb_common.h"
@@ -21,10 +23,10 @@
 
 namespace wb {
 
-static constexpr int FA_THREADS = 192;
+static constexpr int FA_THREADS = 320;
 static constexpr int FA_KSTAGES = 3, FA_VSTAGES = 2;
 static constexpr int FA_Q_BYTES = 128 * 128, FA_K_BYTES = 128 * 128, FA_V_BYTES = 64 * 256, FA_P_BYTES = 128 * 256;
-static constexpr int FA_SMEM = FA_Q_BYTES + FA_KSTAGES * FA_K_BYTES + FA_VSTAGES * FA_V_BYTES + 2 * FA_P_BYTES + 1024 + 256;
+static constexpr int FA_SMEM = FA_Q_BYTES + FA_KSTAGES * FA_K_BYTES + FA_VSTAGES * FA_V_BYTES + 2 * FA_P_BYTES + 1024 + 256 + 2 * 128 * 4;
 
 struct FattnParams { int T, n_kb; float scale_log2e; __half * out; int64_t ldo, out_win; };
 
@@ -46,6 +48,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     uint64_t * p_full = bars + 14,  * p_free  = bars + 16;
     uint64_t * q_full = bars + 18,  * o_full  = bars + 19;
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+    float * xch = reinterpret_cast<float *>(bars + 32);          // [2][128]: row maxima / row sums of the two column halves
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, w = blockIdx.z;
@@ -55,7 +58,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < FA_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < FA_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); mbar_init(&p_full[i], 8); mbar_init(&p_free[i], 1); }
         mbar_init(q_full, 1); mbar_init(o_full, 1);
         mbar_fence_init();
     }
@@ -135,6 +138,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     } else {
         // ---------------------------------------------------------------- softmax warps (thread = query row) + epilogue
         const int q = warp & 3;                            // TMEM lane quarter of this warp
+        const int half = (warp - 2) >> 2;                  // which 64 keys of a block (pass 1, 2) / which 32 output dims (epilogue)
         const int row = q * 32 + lane;                     // query row inside the tile
         const uint32_t lane_off = (uint32_t) (q * 32) << 16;
         uint32_t sfull_ph[2] = { 0, 0 }, pfree_ph[2] = { 0, 0 };
@@ -146,7 +150,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             mbar_wait(&s_full[b], sfull_ph[b]); sfull_ph[b] ^= 1;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = half * 2; c < half * 2 + 2; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(tS[b] + lane_off + c * 32, v);
                 tmem_ld_wait();
@@ -157,6 +161,9 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[b]);
         }
+        xch[half * 128 + row] = m;
+        bar_named(1, 256);
+        m = fmaxf(m, xch[(half ^ 1) * 128 + row]);
         const float mc = m * p.scale_log2e;
         float l = 0.0f;
         const int sw = row & 7;
@@ -168,7 +175,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             tc_fence_after();
             uint8_t * prow = sP + b * FA_P_BYTES + row * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = half * 2; c < half * 2 + 2; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(tS[b] + lane_off + c * 32, v);
                 tmem_ld_wait();
@@ -197,13 +204,17 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             if (lane == 0) { mbar_arrive(&s_free[b]); mbar_arrive(&p_full[b]); }
         }
         // epilogue: O / l -> f16 -> global
+        bar_named(1, 256);                                 // everybody has read the maxima
+        xch[half * 128 + row] = l;
+        bar_named(1, 256);
+        l = xch[row] + xch[128 + row];                     // fixed order: both threads of a row get the same sum
         mbar_wait(o_full, 0);
         tc_fence_after();
         const int qg = q0 + row;
         const float inv = 1.0f / l;
         __half * orow = p.out + (int64_t) w * p.out_win + (int64_t) qg * p.ldo + h * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = half;
             uint32_t v[32];
             tmem_ld_32x32(tO + lane_off + c * 32, v);
             tmem_ld_wait();

@@ -9,6 +9,8 @@
 namespace wb {
 
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+// named barrier: the n threads (a multiple of 32) that call it with the same id
+__device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
