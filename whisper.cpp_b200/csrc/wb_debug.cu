@@ -13,7 +13,7 @@ extern "C" {
 // C[n][m] (f32, token-major) = sum_k W[m][k] * X[n][k] ; W given in FILE layout (f16 rows or ggml quant blocks),
 // X given as f32 and rounded to f16 on the way in (as the engine does).  flags bit0: apply gelu; bit1: m-major output;
 // bit2: the persistent double-buffered kernel (quantised weights expanded to f16 once, both operands through TMA); bit3 (with bit2):
-// CTA pairs sharing the activation tile by TMA multicast.
+// CTA pairs sharing the activation tile by TMA multicast, bit4 = f16 output, bit5 = in-place f32 residual (out holds x on entry).
 __attribute__((visibility("default")))
 int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const float * x, const float * bias,
                    float * out, int BN, int flags) {
@@ -54,10 +54,25 @@ int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const fl
     g.ep.out = dout.p; g.ep.out_f16 = 0;
     g.ep.out_mmajor = (flags & 2) ? 1 : 0;
     g.ep.ldo = (flags & 2) ? N : M;
+    DevBuf<__half> dout16;
+    if (flags & 16) {                                            // f16 output (token-major), widened to f32 for the caller
+        if (!dout16.alloc((size_t) M * N)) return -1;
+        g.ep.out = dout16.p; g.ep.out_f16 = 1;
+    }
+    if (flags & 32) {                                            // in-place f32 residual: `out` holds x on entry, x + W a on return
+        WB_CUDA_OKV(cudaMemcpy(dout.p, out, (size_t) M * N * 4, cudaMemcpyHostToDevice), -2);
+        g.ep.res = dout.p; g.ep.ldr = M;
+    }
     cudaError_t e = gemm_launch(g, st);
     if (e != cudaSuccess) { set_error("gemm_launch: %s", cudaGetErrorString(e)); return -6; }
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("gemm sync: %s", cudaGetErrorString(e)); return -7; }
+    if (flags & 16) {
+        std::vector<__half> h((size_t) M * N);
+        WB_CUDA_OKV(cudaMemcpy(h.data(), dout16.p, (size_t) M * N * 2, cudaMemcpyDeviceToHost), -2);
+        for (size_t i = 0; i < h.size(); ++i) out[i] = __half2float(h[i]);
+        return 0;
+    }
     WB_CUDA_OKV(cudaMemcpy(out, dout.p, (size_t) M * N * 4, cudaMemcpyDeviceToHost), -2);
     return 0;
 }

@@ -79,6 +79,67 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmKParams & p, uint32
     const int64_t ooff = (int64_t) b0 * e.out_b0 + (int64_t) b1 * e.out_b1;
     const int64_t roff = (int64_t) b0 * e.res_b0 + (int64_t) b1 * e.res_b1;
     constexpr int CH = BN / 2 / 32;            // 32-column chunks per warp
+    if (e.res && !e.out_mmajor && !e.out_f16 && e.act == 0) {
+        // f32 residual stream (attention-O / FC2: x += W a): the residual values of chunk c+1 are requested before chunk c is drained, so
+        // a warp keeps two chunks (8 KB) in flight -- with one, the 128 KB of a tile took longer to arrive than its main loop runs
+        float * o = reinterpret_cast<float *>(e.out) + ooff;
+        const float * rp = e.res + roff + m;
+        float rn[32];
+        auto fetch = [&](int col) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + col + j;
+                rn[j] = (mval && n < p.N) ? __ldcg(rp + (int64_t) n * e.ldr) : 0.0f;
+            }
+        };
+        fetch(hsel * (BN / 2));
+        const float bs = bias * scl;
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+            const int col = hsel * (BN / 2) + c * 32;
+            if (n0 + col >= p.N) break;        // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) col, v);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = rn[j];
+            if (c + 1 < CH) fetch(col + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + col + j;
+                if (mval && n < p.N) o[(int64_t) (n + e.n_row_off) * e.ldo + m] = fmaf(__uint_as_float(v[j]), scl, bs) + f[j];
+            }
+        }
+        return;
+    }
+    if (e.act == 1 && e.out_f16 && !e.res && !e.out_mmajor && e.hm_rows == 0) {
+        // FC1: GELU with the reference's f16 table semantics, a dozen instructions per value (the generic path below spends about twenty,
+        // which made this epilogue longer than the K = 1280 main loop): see gelu_ref_f16 for the formula and its accuracy
+        __half * o = reinterpret_cast<__half *>(e.out) + ooff;
+        const float bs = bias * scl;
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+            const int col = hsel * (BN / 2) + c * 32;
+            if (n0 + col >= p.N) break;
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) col, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const __half2 h2 = __floats2half2_rn(fmaf(__uint_as_float(v[j]), scl, bs), fmaf(__uint_as_float(v[j + 1]), scl, bs));
+                float2 x = __half22float2(h2);
+                x.x = fmaxf(x.x, -20.0f); x.y = fmaxf(x.y, -20.0f);            // gelu = 0 below -10 either way; keeps exp finite
+                const float e0 = __expf(x.x * fmaf(x.x * x.x, -0.07135481627f, -1.5957691216f));
+                const float e1 = __expf(x.y * fmaf(x.y * x.y, -0.07135481627f, -1.5957691216f));
+                const __half2 g2 = __floats2half2_rn(__fdividef(x.x, 1.0f + e0), __fdividef(x.y, 1.0f + e1));
+                const int n = n0 + col + j;
+                if (mval && n < p.N)     o[(int64_t) (n + e.n_row_off) * e.ldo + m]     = __low2half(g2);
+                if (mval && n + 1 < p.N) o[(int64_t) (n + 1 + e.n_row_off) * e.ldo + m] = __high2half(g2);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int c = 0; c < CH; ++c) {
         const int col = hsel * (BN / 2) + c * 32;
