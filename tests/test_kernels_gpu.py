@@ -155,6 +155,33 @@ def test_attention_decode_kernels(lib):
             assert np.abs(out[t, sl] - want[0]).max() < 1e-4
 
 
+def test_encoder_flash_attention_kernel(lib):
+    """fattn_enc_kernel (wb_fattn.cu) alone against a float64 softmax(Q K^T) V over the 1536 padded keys: 1500 real + 36 all-zero rows that take
+    part in the softmax.  Two windows, ragged last query tile (1500 = 11 x 128 + 92).  Tolerance: the kernel rounds the
+    probabilities to f16 for the tensor core (2^-11 relative each) and the output to f16."""
+    rng = np.random.default_rng(11)
+    T, Tp, H, n_win = 1500, 1536, 3, 2
+    d = H * 64
+    q = (rng.standard_normal((n_win, T, d)) * 1.5).astype(np.float32); k = rng.standard_normal((n_win, T, d)).astype(np.float32)
+    v = rng.standard_normal((n_win, T, d)).astype(np.float32)
+    out = np.empty((n_win, T, d), np.float32)
+    scale = 1.0 / 8.0
+    lib.wb200_dbg_fattn.restype = C.c_int
+    assert lib.wb200_dbg_fattn(_ptr(q), _ptr(k), _ptr(v), T, Tp, H, n_win, C.c_float(scale), _ptr(out)) == 0, lib.wb200_last_error()
+    q16 = q.astype(np.float16).astype(np.float64); k16 = k.astype(np.float16).astype(np.float64); v16 = v.astype(np.float16).astype(np.float64)
+    worst = 0.0
+    for w in range(n_win):
+        for h in range(H):
+            sl = slice(h * 64, h * 64 + 64)
+            s_ = q16[w, :, sl] @ k16[w, :, sl].T * scale                                   # [T][T]
+            s_ = np.concatenate([s_, np.zeros((T, Tp - T))], axis=1)                        # the zero keys score 0
+            p_ = np.exp(s_ - s_.max(axis=1, keepdims=True)); p_ /= p_.sum(axis=1, keepdims=True)
+            want = p_[:, :T] @ v16[w, :, sl]
+            worst = max(worst, float(np.abs(out[w, :, sl] - want).max()))
+    print("encoder attention kernel: worst abs error %.2e" % worst)
+    assert worst < 4e-3
+
+
 def test_whisper_bench_entry_points_measure_the_device(lib):
     """whisper_bench_memcpy_str / whisper_bench_ggml_mul_mat_str (whisper.h:746-753, `whisper-bench -w 1|2`) report device copy bandwidth
     and tcgen05 GEMM throughput"""

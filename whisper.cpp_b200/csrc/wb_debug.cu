@@ -79,6 +79,33 @@ int wb200_dbg_gemm(int wtype, int M, int N, int K, const void * w_file, const fl
 
 
 
+// encoder self-attention kernel alone: q, k, v f32 [n_win][T][H*64] (rounded to f16 on the way in), out f32 [n_win][T][H*64]; keys T..Tp-1 are
+// the all-zero padding rows that take part in the softmax
+__attribute__((visibility("default")))
+int wb200_dbg_fattn(const float * q, const float * k, const float * v, int T, int Tp, int H, int n_win, float scale, float * out) {
+    cudaStream_t st = 0;
+    const int d = H * 64;
+    std::vector<__half> hqk((size_t) n_win * T * 2 * d), hvt((size_t) n_win * d * Tp, __float2half(0.0f));
+    for (int w = 0; w < n_win; ++w)
+        for (int t = 0; t < T; ++t)
+            for (int e = 0; e < d; ++e) {
+                const size_t i = ((size_t) w * T + t) * d + e;
+                hqk[((size_t) w * T + t) * 2 * d + e]     = __float2half_rn(q[i]);
+                hqk[((size_t) w * T + t) * 2 * d + d + e] = __float2half_rn(k[i]);
+                hvt[((size_t) w * d + e) * Tp + t]        = __float2half_rn(v[i]);
+            }
+    DevBuf<__half> dqk, dvt, dout;
+    if (!dqk.alloc(hqk.size()) || !dvt.alloc(hvt.size()) || !dout.alloc((size_t) n_win * T * d)) return -1;
+    WB_CUDA_OKV(cudaMemcpy(dqk.p, hqk.data(), hqk.size() * 2, cudaMemcpyHostToDevice), -2);
+    WB_CUDA_OKV(cudaMemcpy(dvt.p, hvt.data(), hvt.size() * 2, cudaMemcpyHostToDevice), -2);
+    if (!fattn_encoder(dqk.p, 2 * d, d, dvt.p, T, Tp, H, n_win, scale, dout.p, d, st)) return -3;
+    WB_CUDA_OKV(cudaStreamSynchronize(st), -4);
+    std::vector<__half> ho((size_t) n_win * T * d);
+    WB_CUDA_OKV(cudaMemcpy(ho.data(), dout.p, ho.size() * 2, cudaMemcpyDeviceToHost), -2);
+    for (size_t i = 0; i < ho.size(); ++i) out[i] = __half2float(ho[i]);
+    return 0;
+}
+
 // log-mel of a PCM buffer; mel_out [n_mel][n_len]; returns n_len (<0 on error)
 __attribute__((visibility("default")))
 int wb200_dbg_mel(const float * pcm, int n_samples, const float * filters, int n_mel, float * mel_out, int64_t cap) {

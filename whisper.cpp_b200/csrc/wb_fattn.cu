@@ -7,10 +7,14 @@
 // n_ctx are zero-filled by TMA and the V^T buffer keeps zeros in those columns, so they take part in max and sum exactly
 // like in the reference.
 //
-// One CTA = 128 queries (TMEM lanes) of one head.  Two passes over the 12 key blocks of 128:
-//   pass 1  S_j = Q K_j^T (4 x tcgen05.mma M128 N128 K16)  -> row maxima only
+// One CTA = 128 queries (TMEM lanes) of one head.  Two passes over the 24 key blocks of 64:
+//   pass 1  S_j = Q K_j^T (4 x tcgen05.mma M128 N64 K16)  -> row maxima only
 //   pass 2  S_j again, p = exp2((s - m) * scale*log2e) with the FINAL maximum m, P_j -> smem (f16, swizzled K-major),
-//           O += P_j V_j (8 x tcgen05.mma M128 N64 K16) accumulated in TMEM, l += sum p
+//           O += P_j V_j (4 x tcgen05.mma M128 N64 K16) accumulated in TMEM, l += sum p
+// TWO CTAs share an SM (88 KB of shared memory and 256 tensor-memory columns each; blocks of 64 keys make that fit): the kernel is
+// bound by the softmax warps -- 16 ex2 per clock per SM, and chains of TMEM load -> exponent -> smem store -> mbarrier -- and a single
+// CTA per SM left the exponent pipe idle during its first pass, its prologue and its epilogue (measured: 20 us per CTA against 6.4 us
+// of ex2 work).
 // Knowing m before any exponent is taken removes the online-softmax rescaling of O (no TMEM read-modify-write, no
 // correction warps); the price is recomputing QK^T once: +1/3 tensor work on 14% of the encoder flops.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2..9 softmax + epilogue: a query row is shared by two threads (TMEM
@@ -25,14 +29,15 @@ namespace wb {
 
 static constexpr int FA_THREADS = 320;
 static constexpr int FA_KSTAGES = 3, FA_VSTAGES = 2;
-static constexpr int FA_Q_BYTES = 128 * 128, FA_K_BYTES = 128 * 128, FA_V_BYTES = 64 * 256, FA_P_BYTES = 128 * 256;
+static constexpr int FA_KB = 64;                   // keys per block
+static constexpr int FA_Q_BYTES = 128 * 128, FA_K_BYTES = FA_KB * 128, FA_V_BYTES = 64 * FA_KB * 2, FA_P_BYTES = 128 * FA_KB * 2;
 static constexpr int FA_SMEM = FA_Q_BYTES + FA_KSTAGES * FA_K_BYTES + FA_VSTAGES * FA_V_BYTES + 2 * FA_P_BYTES + 1024 + 256 + 2 * 128 * 4;
 
 struct FattnParams { int T, n_kb; float scale_log2e; __half * out; int64_t ldo, out_win; };
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, 2)
 fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV) {
     extern __shared__ uint8_t smem_raw[];
@@ -62,13 +67,13 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
         mbar_init(q_full, 1); mbar_init(o_full, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == 2) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS[2] = { tmem, tmem + 128 };
-    const uint32_t tO = tmem + 256;
+    const uint32_t tS[2] = { tmem, tmem + FA_KB };
+    const uint32_t tO = tmem + 2 * FA_KB;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -80,13 +85,12 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
                 for (int j = 0; j < n_kb; ++j) {
                     mbar_wait(&k_empty[ks], kph ^ 1);
                     mbar_arrive_expect_tx(&k_full[ks], FA_K_BYTES);
-                    tma_load_4d(sK + ks * FA_K_BYTES, &tmK, &k_full[ks], 0, j * 128, h, w);
+                    tma_load_4d(sK + ks * FA_K_BYTES, &tmK, &k_full[ks], 0, j * FA_KB, h, w);
                     if (++ks == FA_KSTAGES) { ks = 0; kph ^= 1; }
                     if (pass == 1) {
                         mbar_wait(&v_empty[vs], vph ^ 1);
                         mbar_arrive_expect_tx(&v_full[vs], FA_V_BYTES);
-                        tma_load_4d(sV + vs * FA_V_BYTES,        &tmV, &v_full[vs], j * 128,      0, h, w);
-                        tma_load_4d(sV + vs * FA_V_BYTES + 8192, &tmV, &v_full[vs], j * 128 + 64, 0, h, w);
+                        tma_load_4d(sV + vs * FA_V_BYTES, &tmV, &v_full[vs], j * FA_KB, 0, h, w);
                         if (++vs == FA_VSTAGES) { vs = 0; vph ^= 1; }
                     }
                 }
@@ -95,7 +99,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            const uint32_t id_qk = umma_idesc_f16(128, 128), id_pv = umma_idesc_f16(128, 64);
+            const uint32_t id_qk = umma_idesc_f16(128, FA_KB), id_pv = umma_idesc_f16(128, 64);
             const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
             mbar_wait(q_full, 0);
             int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0;
@@ -108,9 +112,9 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
                 tc_fence_after();
                 const uint32_t pbase = smem_u32(sP + b * FA_P_BYTES), vbase = smem_u32(sV + vs * FA_V_BYTES);
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const uint64_t ad = umma_desc_sw128(pbase + (s >> 2) * 16384 + (s & 3) * 32);
-                    const uint64_t bd = umma_desc_sw128(vbase + (s >> 2) * 8192  + (s & 3) * 32);
+                for (int s = 0; s < FA_KB / 16; ++s) {
+                    const uint64_t ad = umma_desc_sw128(pbase + s * 32);
+                    const uint64_t bd = umma_desc_sw128(vbase + s * 32);
                     umma_f16_ss(tO, ad, bd, id_pv, (jb | s) ? 1u : 0u);
                 }
                 umma_commit(&p_free[b]);
@@ -138,7 +142,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     } else {
         // ---------------------------------------------------------------- softmax warps (thread = query row) + epilogue
         const int q = warp & 3;                            // TMEM lane quarter of this warp
-        const int half = (warp - 2) >> 2;                  // which 64 keys of a block (pass 1, 2) / which 32 output dims (epilogue)
+        const int half = (warp - 2) >> 2;                  // which 32 keys of a block (pass 1, 2) / which 32 output dims (epilogue)
         const int row = q * 32 + lane;                     // query row inside the tile
         const uint32_t lane_off = (uint32_t) (q * 32) << 16;
         uint32_t sfull_ph[2] = { 0, 0 }, pfree_ph[2] = { 0, 0 };
@@ -149,10 +153,9 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             const int b = it & 1;
             mbar_wait(&s_full[b], sfull_ph[b]); sfull_ph[b] ^= 1;
             tc_fence_after();
-#pragma unroll
-            for (int c = half * 2; c < half * 2 + 2; ++c) {
+            {
                 uint32_t v[32];
-                tmem_ld_32x32(tS[b] + lane_off + c * 32, v);
+                tmem_ld_32x32(tS[b] + lane_off + half * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
@@ -174,8 +177,8 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
             if (j >= 2) { mbar_wait(&p_free[b], pfree_ph[b]); pfree_ph[b] ^= 1; }
             tc_fence_after();
             uint8_t * prow = sP + b * FA_P_BYTES + row * 128;
-#pragma unroll
-            for (int c = half * 2; c < half * 2 + 2; ++c) {
+            {
+                const int c = half;
                 uint32_t v[32];
                 tmem_ld_32x32(tS[b] + lane_off + c * 32, v);
                 tmem_ld_wait();
@@ -190,11 +193,11 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
                     l += pr.x + pr.y;
                     pk[i] = *reinterpret_cast<const uint32_t *>(&hp);
                 }
-                // keys c*32 .. c*32+31 of this block: atom (c >> 1), 16-byte chunks (c & 1)*4 .. +3 of the 128-byte row
-                uint8_t * arow = prow + (c >> 1) * 16384;
+                // keys c*32 .. c*32+31 of this block: 16-byte chunks c*4 .. +3 of the 128-byte row (one swizzle atom)
+                uint8_t * arow = prow;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int chunk = (c & 1) * 4 + u;
+                    const int chunk = c * 4 + u;
                     *reinterpret_cast<uint4 *>(arow + ((chunk ^ sw) << 4)) = make_uint4(pk[4*u], pk[4*u + 1], pk[4*u + 2], pk[4*u + 3]);
                 }
             }
@@ -234,7 +237,7 @@ fattn_enc_kernel(const FattnParams p, const __grid_constant__ CUtensorMap tmQ, c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<512>(tmem);
+    if (warp == 2) tmem_dealloc<256>(tmem);
 }
 
 // Q, K: f16 [n_win][T][ld_qk] with head h at columns h*64 (K at +k_off); Vt: f16 [n_win][H*64][Tp]; out: f16 [n_win*T][ldo]
@@ -242,10 +245,10 @@ bool fattn_encoder(const __half * qk, int ld_qk, int k_off, const __half * vt, i
                    __half * out, int ldo, cudaStream_t st) {
     CUtensorMap tmQ, tmK, tmV;
     if (!make_tmap_f16(&tmQ, qk,         64, T, H, n_win, ld_qk, 64, (uint64_t) T * ld_qk, 128)) return false;
-    if (!make_tmap_f16(&tmK, qk + k_off, 64, T, H, n_win, ld_qk, 64, (uint64_t) T * ld_qk, 128)) return false;
+    if (!make_tmap_f16(&tmK, qk + k_off, 64, T, H, n_win, ld_qk, 64, (uint64_t) T * ld_qk, FA_KB)) return false;
     if (!make_tmap_f16(&tmV, vt, Tp, 64, H, n_win, Tp, (uint64_t) 64 * Tp, (uint64_t) H * 64 * Tp, 64)) return false;
     WB_CUDA_OK(ensure_dyn_smem(reinterpret_cast<const void *>(fattn_enc_kernel), FA_SMEM));
-    FattnParams p; p.T = T; p.n_kb = Tp / 128; p.scale_log2e = scale * 1.4426950408889634f; p.out = out; p.ldo = ldo; p.out_win = (int64_t) T * ldo;
+    FattnParams p; p.T = T; p.n_kb = Tp / FA_KB; p.scale_log2e = scale * 1.4426950408889634f; p.out = out; p.ldo = ldo; p.out_win = (int64_t) T * ldo;
     ProfScope prof(PC_ATTN, st, 0.0, (double) n_win * H * (3.0 * 2 * T * (double) Tp * 64));   // QK twice + PV
     fattn_enc_kernel<<<dim3((T + 127) / 128, H, n_win), FA_THREADS, FA_SMEM, st>>>(p, tmQ, tmK, tmV);
     count_launch();
