@@ -514,7 +514,7 @@ __device__ __forceinline__ float attn_merge(const float * pp, int nw, int dim, f
 // four key groups are requested together, so a row with 200 keys costs a handful of memory round trips instead of one per group.
 template <int WT>
 __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
-    constexpr int WPI = 2, SB = 4;                               // warps per item, key groups whose loads are issued together
+    constexpr int WPI = 2, SB = 2, CV = 16;                      // warps per item, key groups in flight together (double-buffered), cell indices per lane requested at once
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp / WPI, hw = warp % WPI;
     const int d = a.d, H = a.n_head, n_pairs = a.n_tok * H;
     const int kslot = lane >> 2, r = lane & 3;
@@ -525,25 +525,39 @@ __device__ __noinline__ void mk_attn_self(const MkArgs & a, const MkLayer & L) {
         float q[16];
         load_q16(a.qkv + (size_t) t * 3 * d + h * 64, r, q);
         LaneAcc A; lane_init(A);
-        for (int k0 = hw * 8; k0 < nk; k0 += WPI * 8 * SB) {
-            int cell[SB]; KV4 f[SB];
+        // Latency chain of an item: cell indices -> K / V rows -> arithmetic.  The indices of 256 keys (16 per lane) are requested at once,
+        // then the K / V of two key groups at a time, the next two in flight while the current two are used: one round trip for the
+        // indices plus one exposed K / V round trip per item instead of two per 64 keys.  Every lane still meets its keys in ascending order.
+        for (int kb = 0; kb < nk; kb += WPI * 8 * CV) {
+            int cv[CV];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) { const int k = k0 + s * WPI * 8 + kslot; cell[s] = (k < nk) ? __ldg(cells + k) : -1; }
+            for (int i = 0; i < CV; ++i) { const int k = kb + hw * 8 + i * WPI * 8 + kslot; cv[i] = (k < nk) ? __ldg(cells + k) : -1; }
+            KV4 f[2][SB];
+            auto fetch = [&](KV4 (&dst)[SB], int c0, int c1) {
+                const int cc[SB] = { c0, c1 };
 #pragma unroll
-            for (int s = 0; s < SB; ++s) {
-                f[s].k0 = f[s].k1 = f[s].v0 = f[s].v1 = make_uint4(0, 0, 0, 0);
-                if (cell[s] >= 0) {
-                    const size_t off = (size_t) cell[s] * d + h * 64 + r * 8;
-                    const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
-                    f[s].k0 = __ldcg(kp); f[s].k1 = __ldcg(kp + 4); f[s].v0 = __ldcg(vp); f[s].v1 = __ldcg(vp + 4);
+                for (int u = 0; u < SB; ++u) {
+                    dst[u].k0 = dst[u].k1 = dst[u].v0 = dst[u].v1 = make_uint4(0, 0, 0, 0);
+                    if (cc[u] >= 0) {
+                        const size_t off = (size_t) cc[u] * d + h * 64 + r * 8;
+                        const uint4 * kp = reinterpret_cast<const uint4 *>(L.kc + off), * vp = reinterpret_cast<const uint4 *>(L.vc + off);
+                        dst[u].k0 = __ldcg(kp); dst[u].k1 = __ldcg(kp + 4); dst[u].v0 = __ldcg(vp); dst[u].v1 = __ldcg(vp + 4);
+                    }
                 }
-            }
+            };
+            fetch(f[0], cv[0], cv[1]);
 #pragma unroll
-            for (int s = 0; s < SB; ++s) {
-                float sc = dot16(f[s].k0, f[s].k1, q);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-                sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-                if (cell[s] >= 0) lane_update(A, sc, f[s].v0, f[s].v1);
+            for (int g = 0; g < CV / SB; ++g) {
+                const bool more = (g + 1 < CV / SB) && (kb + (g + 1) * SB * WPI * 8 < nk);       // same for both warps of the item
+                if (more) fetch(f[(g + 1) & 1], cv[(2 * g + 2) % CV], cv[(2 * g + 3) % CV]);
+#pragma unroll
+                for (int u = 0; u < SB; ++u) {
+                    float sc = dot16(f[g & 1][u].k0, f[g & 1][u].k1, q);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+                    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+                    if (cv[2 * g + u] >= 0) lane_update(A, sc, f[g & 1][u].v0, f[g & 1][u].v1);
+                }
+                if (!more) break;
             }
         }
         warp_merge(A);
