@@ -200,32 +200,36 @@ __device__ __noinline__ void mk_prefetch_w(const QMat & W) {
 #define MK_FINE(j) do { if (fb >= 0 && blockIdx.x == 0 && threadIdx.x == 0) a.trace[fb + (j)] = clock64(); } while (0)
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void * g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async16_hint(uint32_t saddr, const void * g, uint64_t pol) { asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(saddr), "l"(g), "l"(pol) : "memory"); }
+__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// k-loop of one iteration of mk_gemv for NV valid tile slots (compile-time: predicated slots made the register allocator spill);
-// leaves the split-K partials in SM_RED
-template <int WT, int NV, int TU>
-__device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * wbase, int tile0, int tstep, int nrec, int nb, int SW, int nt, int NH, bool & staged, uint32_t stage_parity, int fb) {
+// k-loop of one iteration of mk_gemv for NV tile slots per warp (compile-time: predicated slots made the register allocator spill);
+// leaves the split-K partials of slots j0 .. j0+NV-1 in SM_RED.  KS warps split K of a slot, UB records per slot are requested together
+// (always 16 / 3: the order in which a warp adds up its blocks is part of the result, and a row must not depend on how many tiles its
+// CTA happens to hold).  Four slots in one call hold 12 records + 32 accumulators per lane and spilled (7.4 us per iteration against
+// 2.4 us for three slots): an iteration with four slots makes two calls of two slots, same partials, no spills.
+template <int WT, int NV, int TU, int KS, int UB>
+__device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * wbase, int tile0, int tstep, int nrec, int nb, int SW, int nt, int NH, bool & staged, uint32_t stage_parity, int fb, int j0) {
     constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
     constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;
-    constexpr int UB = 3;
     constexpr int RLD = 17;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3, ks = warp & (KS - 1);
     float acc[NV][2][4];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
 #pragma unroll
         for (int h = 0; h < 2; ++h) { acc[j][h][0] = acc[j][h][1] = acc[j][h][2] = acc[j][h][3] = 0.0f; }
-    for (int kb = warp; kb < nrec; kb += MK_WARPS * UB) {
+    for (int kb = ks; kb < nrec; kb += KS * UB) {
         uint4 wq[NV][UB]; uint2 wh[NV][UB]; uint32_t wd[NV][UB];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             {
-                const uint8_t * tb = wbase + (size_t) ((tile0 + (j / TU) * tstep) * TU + j % TU) * nrec * REC;
+                const uint8_t * tb = wbase + (size_t) ((tile0 + ((j0 + j) / TU) * tstep) * TU + (j0 + j) % TU) * nrec * REC;
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
-                    const uint8_t * rec = tb + (size_t) min(kb + u * MK_WARPS, nrec - 1) * REC;
+                    const uint8_t * rec = tb + (size_t) min(kb + u * KS, nrec - 1) * REC;
                     if (WT == WT_F16 || WT == WT_Q8_0) wq[j][u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
                     else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[j][u].x = q2.x; wq[j][u].y = q2.y; }
                     if (WT == WT_Q5_0) wh[j][u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
@@ -236,7 +240,7 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
         if (!staged) { mbar_wait(SM_MBAR, stage_parity); staged = true; MK_FINE(1); }     // the rows have landed (this warp's weights are in flight)
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-            const int b = kb + u * MK_WARPS;
+            const int b = kb + u * KS;
             if (b < nrec) {
                 uint32_t bf[2][2]; float dx[2][2];
 #pragma unroll
@@ -295,7 +299,7 @@ __device__ __forceinline__ void mk_gemv_kloop(const MkArgs & a, const uint8_t * 
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) SM_RED[((j * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * RLD + h * 8 + 2 * c + (i & 1)] = acc[j][h][i];
+                for (int i = 0; i < 4; ++i) SM_RED[(((j0 + j) * MK_WARPS + warp) * 16 + g + (i >> 1) * 8) * RLD + h * 8 + 2 * c + (i & 1)] = acc[j][h][i];
         }
 }
 
@@ -356,10 +360,13 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
             const uint8_t * wbase = reinterpret_cast<const uint8_t *>(W.base);
             const int unit0 = ci + u0 * cg;                      // slot j holds tile (unit0 + (j / TU) * cg) * TU + j % TU
             switch (nv) {
-                case 1: if (!PAIR) { mk_gemv_kloop<WT, 1, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break; }
-                case 2: mk_gemv_kloop<WT, 2, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break;
-                case 3: if (!PAIR) { mk_gemv_kloop<WT, 3, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break; }
-                default: mk_gemv_kloop<WT, 4, TU>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb); break;
+                case 1: if (!PAIR) { mk_gemv_kloop<WT, 1, TU, 16, 3>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb, 0); break; }
+                case 2: mk_gemv_kloop<WT, 2, TU, 16, 3>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb, 0); break;
+                case 3: if (!PAIR) { mk_gemv_kloop<WT, 3, TU, 16, 3>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb, 0); break; }
+                default:                                         // four slots: two passes of two (see mk_gemv_kloop)
+                    mk_gemv_kloop<WT, 2, TU, 16, 3>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb, 0);
+                    mk_gemv_kloop<WT, 2, TU, 16, 3>(a, wbase, unit0, cg, nrec, nb, SW, nt, NH, staged, stage_parity, fb, 2);
+                    break;
             }
         }
         if (it == 0) MK_FINE(2);
@@ -411,6 +418,112 @@ __device__ __noinline__ void mk_gemv(const MkArgs & a, const QMat & W, const uin
     }
     if (!staged) mbar_wait(SM_MBAR, stage_parity);               // a CTA without tiles still waits for its copies before the area is reused
     MK_FINE(5);
+}
+
+// Logits (token-embedding matrix, N = n_vocab, K = d): one WARP per 16-row weight tile over the whole K -- no split-K, no reduction through
+// shared memory, no CTA barrier per iteration (the split-K form needs 22 iterations of ~7 us for the 3242 tiles of large-v3: 220 us for a
+// 45.6 MB stream).  A lane requests 8 records of its tile at once; the rows of the CTA's group are staged as in mk_gemv.  A row's result
+// is one accumulator over the blocks in ascending order: independent of the batch.
+template <int WT>
+__device__ __noinline__ void mk_logits_warp(const MkArgs & a, const QMat & W, const uint8_t * x, float * out) {
+    constexpr int REC = (WT == WT_Q4_0) ? 288 : (WT == WT_Q5_0 ? 352 : (WT == WT_Q8_0 ? 544 : 512));
+    constexpr int QSB = (WT == WT_Q8_0) ? 512 : 256;
+    constexpr int RK = (WT == WT_F16) ? 16 : 32;
+    constexpr int UB = 8;
+    const int N = W.N, K = W.K;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    const int n_tiles = (N + 15) >> 4, nrec = K / RK, nb = K >> 5;
+    const int rowb = (WT == WT_F16) ? K * 2 : K, SW = (rowb >> 2) + 4;
+    const int RG = (16 * (rowb + 16) <= MK_MAXTOK * (MK_ROWB + 16)) ? 16 : 8;
+    const int NGc = (a.n_tok + RG - 1) / RG;
+    const int grp = blockIdx.x % NGc, ci = blockIdx.x / NGc, cg = ((int) gridDim.x - grp + NGc - 1) / NGc;
+    const int t_base = grp * RG, nt = min(RG, a.n_tok - t_base), NH = (nt + 7) >> 3;
+    uint32_t stage_parity;
+    {
+        const int ph = SM_FLAG[4];
+        __syncthreads();
+        stage_parity = (uint32_t) ph & 1u;
+        if (tid == 0) {
+            SM_FLAG[4] = ph + 1;
+            mbar_arrive_expect_tx(SM_MBAR, (uint32_t) nt * (uint32_t) (rowb + (WT == WT_F16 ? 0 : nb * 4)));
+        }
+        if (tid < nt) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            bulk_g2s(SM_XQ + tid * SW, x + (size_t) (t_base + tid) * rowb, (uint32_t) rowb, SM_MBAR);
+            if (WT != WT_F16)
+                bulk_g2s(SM_XD + tid * nb, reinterpret_cast<const float *>(x + (size_t) MK_MAXTOK * K) + (size_t) (t_base + tid) * nb, (uint32_t) nb * 4, SM_MBAR);
+        }
+    }
+    bool staged = false;
+    const uint8_t * wbase = reinterpret_cast<const uint8_t *>(W.base);
+    for (int tile = ci * MK_WARPS + warp; tile < n_tiles; tile += cg * MK_WARPS) {
+        float acc[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0f; }
+        const uint8_t * tb = wbase + (size_t) tile * nrec * REC;
+        for (int kb = 0; kb < nrec; kb += UB) {
+            uint4 wq[UB]; uint2 wh[UB]; uint32_t wd[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const uint8_t * rec = tb + (size_t) min(kb + u, nrec - 1) * REC;
+                if (WT == WT_F16 || WT == WT_Q8_0) wq[u] = __ldg(reinterpret_cast<const uint4 *>(rec) + lane);
+                else { const uint2 q2 = __ldg(reinterpret_cast<const uint2 *>(rec) + lane); wq[u].x = q2.x; wq[u].y = q2.y; }
+                if (WT == WT_Q5_0) wh[u] = __ldg(reinterpret_cast<const uint2 *>(rec + QSB) + g);
+                if (WT != WT_F16)  wd[u] = __ldg(reinterpret_cast<const uint32_t *>(rec + QSB + (WT == WT_Q5_0 ? 64 : 0)) + g);
+            }
+            if (!staged) { mbar_wait(SM_MBAR, stage_parity); staged = true; }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int b = kb + u;
+                if (b < nrec) {
+                    uint32_t af[4];
+                    float dw0 = 0.0f, dw1 = 0.0f;
+                    if (WT == WT_F16 || WT == WT_Q8_0) { af[0] = wq[u].x; af[1] = wq[u].y; af[2] = wq[u].z; af[3] = wq[u].w; }
+                    else {
+                        uint32_t lo0 = wq[u].x & 0x0F0F0F0Fu, hi0 = (wq[u].x >> 4) & 0x0F0F0F0Fu, lo1 = wq[u].y & 0x0F0F0F0Fu, hi1 = (wq[u].y >> 4) & 0x0F0F0F0Fu;
+                        if (WT == WT_Q5_0) {
+                            lo0 |= spread4_to_bit4(wh[u].x >> (4 * c)); hi0 |= spread4_to_bit4(wh[u].x >> (16 + 4 * c));
+                            lo1 |= spread4_to_bit4(wh[u].y >> (4 * c)); hi1 |= spread4_to_bit4(wh[u].y >> (16 + 4 * c));
+                            af[0] = __vsub4(lo0, 0x10101010u); af[2] = __vsub4(hi0, 0x10101010u);
+                            af[1] = __vsub4(lo1, 0x10101010u); af[3] = __vsub4(hi1, 0x10101010u);
+                        } else {
+                            af[0] = __vsub4(lo0, 0x08080808u); af[2] = __vsub4(hi0, 0x08080808u);
+                            af[1] = __vsub4(lo1, 0x08080808u); af[3] = __vsub4(hi1, 0x08080808u);
+                        }
+                    }
+                    if (WT != WT_F16) {
+                        dw0 = __half2float(__ushort_as_half((unsigned short) (wd[u] & 0xffffu)));
+                        dw1 = __half2float(__ushort_as_half((unsigned short) (wd[u] >> 16)));
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h < NH) {
+                            const bool ok = h * 8 + g < nt;
+                            const uint32_t b0 = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + c] : 0u, b1 = ok ? SM_XQ[(h * 8 + g) * SW + b * 8 + 4 + c] : 0u;
+                            if (WT == WT_F16) mma_f16_16816(acc[h], af, b0, b1);
+                            else {
+                                const float dx0 = SM_XD[min(h * 8 + 2 * c, nt - 1) * nb + b], dx1 = SM_XD[min(h * 8 + 2 * c + 1, nt - 1) * nb + b];
+                                int dd[4]; mma_s8_16832(dd, af, b0, b1);
+                                acc[h][0] = fmaf(dw0 * dx0, (float) dd[0], acc[h][0]);
+                                acc[h][1] = fmaf(dw0 * dx1, (float) dd[1], acc[h][1]);
+                                acc[h][2] = fmaf(dw1 * dx0, (float) dd[2], acc[h][2]);
+                                acc[h][3] = fmaf(dw1 * dx1, (float) dd[3], acc[h][3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // C fragment: acc[h][i] = weight row g + 8*(i>>1) of the tile, batch row h*8 + 2c + (i&1)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = tile * 16 + g + (i >> 1) * 8, tl = h * 8 + 2 * c + (i & 1);
+                if (tl < nt && row < N) out[(size_t) (t_base + tl) * N + row] = acc[h][i];
+            }
+    }
+    if (!staged) mbar_wait(SM_MBAR, stage_parity);
 }
 
 // ---- attention -----------------------------------------------------------------------------------------------------------
@@ -601,13 +714,33 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) 
     const size_t head_stride = (size_t) a.n_keys * 64;
     const size_t lane_off = (size_t) (warp * 8 + (lane >> 2)) * 64 + (lane & 3) * 8;       // key 8w+s of the chunk, dims {8r.., 32+8r..}
     const uint32_t ring = (uint32_t) __cvta_generic_to_shared(mk_smem) + tid * 16;
+    const float kq_scale = a.kq_scale;
+    // everything the copy path needs in registers (the asm statements are compiler memory barriers: values re-read from the argument
+    // structs after each of them are dependent loads in front of every chunk); the slot of a row is fetched one row ahead
+    const __half * const xk = L.xk, * const xv = L.xv;
+    const int64_t slot_stride = a.slot_stride;
+    const int * const slots = a.slot;
+    const int n_tok = a.n_tok;
+    const bool ef = (a.prefetch & 4) != 0;
+    const uint64_t pol = policy_evict_first();
+    int slot_cur = slots[tl_], slot_nxt = (tl_ + 1 < n_tok) ? slots[tl_ + 1] : 0;
+    size_t pair_off = (size_t) slot_cur * slot_stride + (size_t) hl * head_stride + lane_off;
     auto issue = [&]() {                                           // copy the next chunk (if any) into ring slot il % 4; always commits a group
         if (pl < p1) {
-            const size_t off = (size_t) a.slot[tl_] * a.slot_stride + (size_t) hl * head_stride + (size_t) (jl * MK_XKEYS) * 64 + lane_off;
+            const size_t off = pair_off + (size_t) (jl * MK_XKEYS) * 64;
             const uint32_t sa = ring + (il % MK_RING) * MK_RING_SLOT;
-            cp_async16(sa, L.xk + off); cp_async16(sa + MK_THREADS * 16, L.xk + off + 32);
-            cp_async16(sa + 2 * MK_THREADS * 16, L.xv + off); cp_async16(sa + 3 * MK_THREADS * 16, L.xv + off + 32);
-            if (++jl == nchp) { jl = 0; ++pl; if (++hl == H) { hl = 0; ++tl_; } }
+            if (ef) {                                             // L2 evict-first: 500 MB of K / V per layer would otherwise flush the prefetched weights and the activations
+                cp_async16_hint(sa, xk + off, pol); cp_async16_hint(sa + MK_THREADS * 16, xk + off + 32, pol);
+                cp_async16_hint(sa + 2 * MK_THREADS * 16, xv + off, pol); cp_async16_hint(sa + 3 * MK_THREADS * 16, xv + off + 32, pol);
+            } else {
+                cp_async16(sa, xk + off); cp_async16(sa + MK_THREADS * 16, xk + off + 32);
+                cp_async16(sa + 2 * MK_THREADS * 16, xv + off); cp_async16(sa + 3 * MK_THREADS * 16, xv + off + 32);
+            }
+            if (++jl == nchp) {
+                jl = 0; ++pl;
+                if (++hl == H) { hl = 0; ++tl_; slot_cur = slot_nxt; slot_nxt = (tl_ + 1 < n_tok) ? slots[tl_ + 1] : 0; }
+                pair_off = (size_t) slot_cur * slot_stride + (size_t) hl * head_stride + lane_off;
+            }
         }
         ++il;
         cp_commit();
@@ -632,7 +765,7 @@ __device__ __noinline__ void mk_attn_cross(const MkArgs & a, const MkLayer & L) 
         float sc = dot16s(k0, k1, qsm + buf * 64 + (lane & 3) * 16);
         sc += __shfl_xor_sync(0xffffffffu, sc, 1);
         sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-        lane_update(A, sc * a.kq_scale, v0, v1);
+        lane_update(A, sc * kq_scale, v0, v1);
         if (++j < nchp) continue;
         j = 0;                                                   // last chunk of the pair: merge the CTA and write the row's head
         warp_merge(A);
@@ -725,8 +858,8 @@ k_decode_pass(const __grid_constant__ MkArgs a) {
     if (a.want_logits) {                                         // final LN + logits (2811-2827)
         mk_lnq<WT>(a, a.x, d, a.lnf_w, a.lnf_b, a.actq);
         MK_SYNC();
-        MkEpi e; e.out = a.logits;
-        mk_gemv<WT, false>(a, a.te, a.actq, e);
+        if (a.prefetch & 16) mk_logits_warp<WT>(a, a.te, a.actq, a.logits);
+        else { MkEpi e; e.out = a.logits; mk_gemv<WT, false>(a, a.te, a.actq, e); }
         MK_STAMP();
     }
 }

@@ -34,6 +34,9 @@ struct MkArgs {
     int * err;                        // set to 1 when a barrier wait times out
     long long * trace;                // optional: phase time stamps of CTA 0 (see MK_STAMP)
     int prefetch;                     // bit0: next-phase weights -> L2, bit1: cross KV -> L2 one phase ahead
+    // second generation (wb_decode_mk2.cu) only:
+    int global_sync = 0;              // a row attends to self-KV cells another row GROUP writes in this pass: all groups meet after the KV append
+    int stagger_clk = 0;              // SM cycles between the starts of consecutive row groups
 };
 
 // number of grid barriers one launch passes (host keeps bar_base in step)
@@ -44,5 +47,13 @@ bool mk_cross_head_major();        // cross K/V of a window is expected head-maj
 int  mk_max_rows();                 // rows (sequences x tokens) one launch can take
 // cooperative launch on `st`; grid = number of SMs.  Returns false (with the error set) when the launch is refused.
 bool mk_launch(const MkArgs & a, int wtype, int n_sm, cudaStream_t st);
+
+// ---- second generation (wb_decode_mk2.cu): row groups of 16 walk the layers independently, two CTAs per SM ----
+int  mk2_ctas_per_sm();
+bool mk2_supported(int wtype, int d);
+size_t mk2_smem_bytes();
+size_t mk2_bar_words(int n_sm);     // 64-bit words of MkArgs::bar: [0..127] counters (zeroed by mk2_launch), then 16 per CTA (release flags)
+// cooperative launch on `st`; grid = 2 x number of SMs.  a.bar_base must grow by 4096 per launch.
+bool mk2_launch(const MkArgs & a, int wtype, int n_sm, cudaStream_t st);
 
 } // namespace wb
