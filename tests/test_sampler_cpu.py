@@ -103,4 +103,10 @@ def test_beam_candidates_match_reference(lib, ref, stub):
         for i in range(K):
             assert (a[i].id, a[i].tid) == (b[i].id, b[i].tid), (trial, i)
             assert a[i].p == b[i].p and a[i].plog == b[i].plog and a[i].pt == b[i].pt and a[i].ptsum == b[i].ptsum
+        # the same candidates when the uniforms are taken from the generator BEFORE the decode (what whisper_full does so that the draws
+        # can run on the device): running sums + lower_bound as libstdc++'s discrete_distribution forms them
+        c = (TokenData * K)()
+        assert L.wb200_dbg_sample_topk(path, C.byref(fp), h, len(hist), has_ts, sd, C.c_float(temp), logits.ctypes.data_as(vp), -K, trial, c) == 0
+        for i in range(K):
+            assert (c[i].id, c[i].tid, c[i].p, c[i].plog, c[i].pt, c[i].ptsum) == (b[i].id, b[i].tid, b[i].p, b[i].plog, b[i].pt, b[i].ptsum), (trial, i)
     R.whisper_free(rctx)

@@ -138,7 +138,7 @@ void note_rows(const whisper_context & ctx, whisper_state & st, const int8_t * w
     for (int j = 0; j < n_tokens; ++j) {
         if (!want[j]) continue;
         whisper_state::LogitRow & r = st.lrows[(size_t) j];
-        if (dev) { const SampOut & o = st.samp_out[(size_t) j]; r.mx = o.raw_max; r.sum = o.raw_sum; r.nosp = o.raw_nosp; }
+        if (dev) { const SampOut & o = st.samp_out[(size_t) j * st.samp_stride]; r.mx = o.raw_max; r.sum = o.raw_sum; r.nosp = o.raw_nosp; }
         else if (st.logits.size() >= (size_t) (j + 1) * n) {
             const float * l = st.logits.data() + (size_t) j * n;
             float mx = -INFINITY; for (int i = 0; i < n; ++i) mx = std::max(mx, l[i]);
@@ -202,8 +202,10 @@ bool decode_batch(whisper_context & ctx, whisper_state & st, const int * tokens,
     }
     if (samp) {
         if (!st.eng->set_samp_mask(samp->mask_key, *samp->mask_bits)) return false;
-        st.samp_out.assign(n_tokens, SampOut());
-        if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), nullptr, &samp->cfg, samp->rowinfo, st.samp_out.data())) return false;
+        const int stride = samp->draws ? samp->stride : 1;
+        st.samp_stride = stride;
+        st.samp_out.assign((size_t) n_tokens * stride, SampOut());
+        if (!st.eng->decode(P.rows.data(), n_tokens, P.cells.data(), P.idx.data(), P.ld, P.nkv.data(), nullptr, &samp->cfg, samp->rowinfo, st.samp_out.data(), samp->draws, stride)) return false;
     } else {
         st.samp_out.clear();
         st.logits.resize((size_t) n_tokens * n_vocab);
@@ -434,12 +436,15 @@ void Group::run(std::vector<Req *> & batch) {
         if (ok && all_samp) ok = eng.set_samp_mask(dec[0]->samp->mask_key, *dec[0]->samp->mask_bits);
         if (ok) {
             std::vector<DecToken> rows; std::vector<int> cells, nkv, idx((size_t) total * ld, 0); std::vector<float *> outs;
-            std::vector<int> rowinfo; std::vector<SampOut> souts((size_t) total); std::vector<std::pair<Req *, int>> origin;
+            int stride = 1;                                            // entries per row of the sampler output: the widest request decides
+            if (all_samp) for (Req * q : dec) stride = std::max(stride, q->samp->draws ? q->samp->stride : 1);
+            std::vector<int> rowinfo; std::vector<SampOut> souts((size_t) total * stride); std::vector<std::pair<Req *, int>> origin;
+            std::vector<double> draws; if (stride > 1) draws.assign((size_t) total * stride, 0.0);
             rows.reserve(total);
             // interleave: row k of every request first, so that single-token steps of all members share one pass (<= Engine::max_rows rows)
             // and multi-token prompts advance in lock-step (causal order inside each member is preserved)
             int maxn = 0; for (Req * q : dec) maxn = std::max(maxn, q->n);
-            for (Req * q : dec) { if (all_samp) q->st->samp_out.assign(q->n, SampOut()); else { q->st->samp_out.clear(); q->st->logits.resize((size_t) q->n * n_vocab); } }
+            for (Req * q : dec) { if (all_samp) { q->st->samp_stride = q->samp->draws ? q->samp->stride : 1; q->st->samp_out.assign((size_t) q->n * q->st->samp_stride, SampOut()); } else { q->st->samp_out.clear(); q->st->logits.resize((size_t) q->n * n_vocab); } }
             for (int k = 0; k < maxn; ++k) {
                 for (size_t i = 0; i < dec.size(); ++i) {
                     Req * q = dec[i]; if (k >= q->n) continue;
@@ -448,13 +453,21 @@ void Group::run(std::vector<Req *> & batch) {
                     rows.push_back(P.rows[k]); cells.push_back(P.cells[k]); nkv.push_back(P.nkv[k]);
                     memcpy(idx.data() + r * ld, P.idx.data() + (size_t) k * P.ld, (size_t) P.nkv[k] * sizeof(int));
                     outs.push_back(all_samp ? nullptr : q->st->logits.data() + (size_t) k * n_vocab);
-                    if (all_samp) { rowinfo.push_back(q->samp->rowinfo[2*k]); rowinfo.push_back(q->samp->rowinfo[2*k + 1]); }
+                    if (all_samp) {
+                        const bool has_draws = q->samp->draws != nullptr;
+                        rowinfo.push_back(has_draws ? q->samp->rowinfo[2*k] : (q->samp->rowinfo[2*k] & 0xff)); rowinfo.push_back(q->samp->rowinfo[2*k + 1]);
+                        if (has_draws) memcpy(draws.data() + r * stride, q->samp->draws + (size_t) k * q->samp->stride, (size_t) q->samp->stride * sizeof(double));
+                    }
                     origin.emplace_back(q, k);
                 }
             }
             if (all_samp) {
-                ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), nullptr, &dec[0]->samp->cfg, rowinfo.data(), souts.data());
-                for (int r = 0; r < total; ++r) origin[r].first->st->samp_out[origin[r].second] = souts[r];
+                ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), nullptr, &dec[0]->samp->cfg, rowinfo.data(), souts.data(),
+                                stride > 1 ? draws.data() : nullptr, stride);
+                for (int r = 0; r < total; ++r) {
+                    Req * q = origin[r].first; const int own = q->samp->draws ? q->samp->stride : 1;
+                    for (int j = 0; j < own; ++j) q->st->samp_out[(size_t) origin[r].second * own + j] = souts[(size_t) r * stride + j];
+                }
             } else {
                 ok = eng.decode(rows.data(), total, cells.data(), idx.data(), ld, nkv.data(), outs.data());
             }

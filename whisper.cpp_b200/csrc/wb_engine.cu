@@ -33,6 +33,7 @@ Engine::~Engine() {
     if (hints) cudaFreeHost(hints);
     if (hlogits) cudaFreeHost(hlogits);
     if (hsamp) cudaFreeHost(hsamp);
+    if (hdraws) cudaFreeHost(hdraws);
     for (auto & e : ev) if (e) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
 }
@@ -86,8 +87,9 @@ bool Engine::init(const Model * model, int cap_windows) {
     if (!act_scratch.alloc(8 * act_tok_stride(m->wtype == WT_F32 ? WT_F16 : m->wtype, 4 * d) + 256)) return false;
     if (!set_cells(pad256(hp.n_text_ctx))) return false;
     WB_CUDA_OK(cudaMallocHost(&hlogits, (size_t) max_rows * V * sizeof(float)));
-    WB_CUDA_OK(cudaMallocHost(&hsamp, max_rows * sizeof(SampOut)));
-    if (!dsamp.alloc(max_rows) || !samp_mask.alloc((size_t) (V + 31) / 32, true)) return false;
+    WB_CUDA_OK(cudaMallocHost(&hsamp, (size_t) max_rows * SAMP_MAX_DRAWS * sizeof(SampOut)));
+    WB_CUDA_OK(cudaMallocHost(&hdraws, (size_t) max_rows * SAMP_MAX_DRAWS * sizeof(double)));
+    if (!dsamp.alloc((size_t) max_rows * SAMP_MAX_DRAWS) || !ddraws.alloc((size_t) max_rows * SAMP_MAX_DRAWS) || !samp_mask.alloc((size_t) (V + 31) / 32, true)) return false;
     return true;
 }
 
@@ -552,8 +554,9 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
         if (!use_mk) { if (gemv_v2) gemv2(a, act_scratch.p, st); else gemv(a, st); }      // the persistent kernel already wrote dlogits
         if (samp) {
             SampCfg c = *samp; c.mask = samp_mask.p;
-            greedy_sample(dlogits.p, V, n, d_row, c, dsamp.p, st);
-            WB_CUDA_OK(cudaMemcpyAsync(hsamp, dsamp.p, (size_t) n * sizeof(SampOut), cudaMemcpyDeviceToHost, st));
+            if (draw_stride > 1) WB_CUDA_OK(cudaMemcpyAsync(ddraws.p, hdraws, (size_t) n * draw_stride * sizeof(double), cudaMemcpyHostToDevice, st));
+            greedy_sample(dlogits.p, V, n, d_row, c, dsamp.p, st, draw_stride > 1 ? ddraws.p : nullptr, draw_stride);
+            WB_CUDA_OK(cudaMemcpyAsync(hsamp, dsamp.p, (size_t) n * draw_stride * sizeof(SampOut), cudaMemcpyDeviceToHost, st));
         } else {
             WB_CUDA_OK(cudaMemcpyAsync(hlogits, dlogits.p, (size_t) n * V * 4, cudaMemcpyDeviceToHost, st));
         }
@@ -562,7 +565,7 @@ bool Engine::decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampC
 }
 
 bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
-                    const SampCfg * samp, const int * rowinfo, SampOut * samp_out) {
+                    const SampCfg * samp, const int * rowinfo, SampOut * samp_out, const double * draws, int stride) {
     NvtxRange nvtx("wb200.decode");
     const HParams & hp = m->hp;
     WB_CUDA_OK(cudaSetDevice(m->device));
@@ -586,12 +589,20 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
             memcpy(h_idx + (size_t) j * ld_idx, kv_idx + (size_t) (r0 + j) * ld, (size_t) n_kv[r0 + j] * sizeof(int));
             any_logits |= t.want_logits;
         }
+        draw_stride = (samp && draws && stride > 1) ? std::min(stride, (int) SAMP_MAX_DRAWS) : 1;
+        if (draw_stride > 1) {
+            for (int j = 0; j < n; ++j) memcpy(hdraws + (size_t) j * draw_stride, draws + (size_t) (r0 + j) * stride, (size_t) draw_stride * sizeof(double));
+            for (int j = 0; j < n; ++j) if (((h_row[2*j] >> 8) & 0x7f) > draw_stride) { set_error("decode: a row asks for more draws than the pass carries"); return false; }
+            count_h2d((size_t) n * draw_stride * sizeof(double));
+        } else {
+            for (int j = 0; j < n; ++j) h_row[2*j] &= 0xff;           // no uniforms supplied: greedy picks only
+        }
         count_h2d(((size_t) 7 * R + (size_t) n * ld_idx) * sizeof(int));
-        if (any_logits) count_d2h(samp ? (uint64_t) n * sizeof(SampOut) : (uint64_t) n * V * 4);
+        if (any_logits) count_d2h(samp ? (uint64_t) n * draw_stride * sizeof(SampOut) : (uint64_t) n * V * 4);
 
         // One pass = 8 kernels per text layer.  After the second use of a shape the chain is replayed as a CUDA graph
         // (all per-step values live in `dints`, so kernel arguments never change between steps).
-        uint64_t key = (uint64_t) (n | (any_logits ? 128 : 0) | (samp ? 256 : 0)) | ((uint64_t) n_keys << 10);
+        uint64_t key = (uint64_t) (n | (any_logits ? 128 : 0) | (samp ? 256 : 0)) | ((uint64_t) n_keys << 10) | ((uint64_t) draw_stride << 24);
         if (samp) key |= (uint64_t) ((uint32_t) (samp->token_eot * 31 + samp->token_beg * 17 + samp->token_nosp * 13 + samp->space_id * 7 + samp->max_initial_tid * 3 + samp->no_timestamps * 2 + samp->suppress_blank)) << 32;
         StepGraph * sg = (use_graphs && !use_mk && !prof_enabled() && !dtw_cap.active) ? &graphs[key] : nullptr;
         dtw_cap.row0 = r0;
@@ -621,7 +632,8 @@ bool Engine::decode(const DecToken * rows, int n_rows, const int * cells, const 
         { float ms = 0.0f; cudaEventElapsedTime(&ms, ev[5], ev[6]); counter_add(0, 1); counter_add(1, n); counter_add(2, ms); }
         if (use_mk && mk_trace.p && any_logits) mk_trace_collect(hp.n_text_layer, true);
         if (any_logits && samp && samp_out) {
-            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits) samp_out[r0 + j] = hsamp[j];
+            for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits)
+                for (int q = 0; q < draw_stride; ++q) samp_out[(size_t) (r0 + j) * stride + q] = hsamp[(size_t) j * draw_stride + q];
         } else if (any_logits && logits_out) {
             for (int j = 0; j < n; ++j) if (rows[r0 + j].want_logits && logits_out[r0 + j])
                 memcpy(logits_out[r0 + j], hlogits + (size_t) j * V, (size_t) V * 4);

@@ -91,8 +91,10 @@ struct Engine {
     DevBuf<int>    dints, xcnt;      // packed per-step integers: tokens | pos | cells | slot | n_kv | rowinfo[16] | idx[...]
     DevBuf<uint32_t> samp_mask;      // static suppression bit mask of the on-device sampler
     uint64_t samp_mask_key = 0;
-    DevBuf<SampOut> dsamp;           // [8]
-    SampOut * hsamp = nullptr;       // pinned [8]
+    DevBuf<SampOut> dsamp;           // [max_rows][SAMP_MAX_DRAWS]
+    SampOut * hsamp = nullptr;       // pinned, same shape
+    DevBuf<double> ddraws; double * hdraws = nullptr;   // uniforms of the categorical draws of a pass [max_rows][stride] (device / pinned)
+    int draw_stride = 1;             // entries per row of dsamp / ddraws in the current pass
     int * hints = nullptr;           // pinned mirror of dints
     float * hlogits = nullptr;       // pinned [8][n_vocab]
     int ld_idx = 0;
@@ -124,7 +126,8 @@ struct Engine {
     bool decode_pass_enqueue(int n, bool any_logits, int n_keys, const SampCfg * samp);   // the kernels of one pass (<= max_rows rows) on `st`
     // samp != nullptr: logits stay on the device; the filter + greedy pick run there (rowinfo: 2 ints per row, samp_out: host [n_rows])
     bool decode(const DecToken * rows, int n_rows, const int * cells, const int * kv_idx, int ld, const int * n_kv, float * const * logits_out,
-                const SampCfg * samp = nullptr, const int * rowinfo = nullptr, SampOut * samp_out = nullptr);
+                const SampCfg * samp = nullptr, const int * rowinfo = nullptr, SampOut * samp_out = nullptr,
+                const double * draws = nullptr, int stride = 1);   // draws: [n_rows][stride] uniforms (rows asking for categorical draws, rowinfo bits 8-14); samp_out: [n_rows][stride]
     bool set_samp_mask(uint64_t key, const std::vector<uint32_t> & bits);
 };
 

@@ -2,6 +2,7 @@
 // logits filtering, greedy / temperature / beam sampling, timestamp-driven window advance, fallback ladder, segment
 // emission.  Semantics follow src/whisper.cpp:5947-6053 (defaults), 6156-6667 (filters, samplers, scoring),
 // 6831-7788 (seek loop) and 7813-7941 (parallel); the device work goes through wb::encode_window / wb::decode_batch.
+#include <numeric>
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
@@ -153,6 +154,28 @@ std::vector<whisper_token_data> sample_token_topk(whisper_context & ctx, Decoder
     std::vector<whisper_token_data> out; out.reserve(k);
     for (int i = 0; i < k; ++i) {
         const int id = dist(dec.rng);
+        whisper_token_data t = blank_token();
+        t.id = id; t.tid = tid; t.p = dec.probs[id]; t.plog = dec.logprobs[id]; t.pt = pt; t.ptsum = ptsum;
+        if (t.id >= vocab.token_beg) { t.tid = t.id; t.pt = t.p; }
+        out.push_back(t);
+    }
+    return out;
+}
+
+// the same k draws with the uniforms already taken from dec.rng: std::discrete_distribution (libstdc++) normalises the probabilities by
+// their sum, forms the running sums (the last one forced to 1) and returns lower_bound(cp, u)
+std::vector<whisper_token_data> sample_token_topk_u(whisper_context & ctx, Decoder & dec, int k, const double * u) {
+    const Vocab & vocab = ctx.vocab;
+    whisper_token tid = vocab.token_beg; float pt = 0.0f, ptsum = 0.0f;
+    timestamp_stats(vocab, dec.probs, tid, pt, ptsum);
+    std::vector<double> cp(dec.probs.begin(), dec.probs.end());
+    const double sum = std::accumulate(cp.begin(), cp.end(), 0.0);
+    for (double & v : cp) v /= sum;
+    std::partial_sum(cp.begin(), cp.end(), cp.begin());
+    if (!cp.empty()) cp.back() = 1.0;
+    std::vector<whisper_token_data> out; out.reserve(k);
+    for (int i = 0; i < k; ++i) {
+        const int id = (int) (std::lower_bound(cp.begin(), cp.end(), u[i]) - cp.begin());
         whisper_token_data t = blank_token();
         t.id = id; t.tid = tid; t.p = dec.probs[id]; t.plog = dec.logprobs[id]; t.pt = pt; t.ptsum = ptsum;
         if (t.id >= vocab.token_beg) { t.tid = t.id; t.pt = t.p; }
@@ -602,10 +625,13 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
 
     // on-device logits filter + greedy pick (decode results come back as 32 bytes per sequence instead of n_vocab floats);
     // used whenever the step is a pure argmax: greedy strategy at temperature 0 without a user logits callback
-    const bool dev_samp_ok = params.strategy == WHISPER_SAMPLING_GREEDY && !params.logits_filter_callback && !(params.grammar_rules && params.n_grammar_rules > 0) &&
-                             getenv("WB200_HOST_SAMPLER") == nullptr;
-    std::vector<uint32_t> mask_bits; SampReq sreq; std::vector<int> rowinfo;
-    if (dev_samp_ok) {
+    const bool dev_any_ok = !params.logits_filter_callback && !(params.grammar_rules && params.n_grammar_rules > 0) && getenv("WB200_HOST_SAMPLER") == nullptr;
+    const bool dev_samp_ok = dev_any_ok && params.strategy == WHISPER_SAMPLING_GREEDY;
+    // beam search at temperature 0: filter + the k categorical draws per decoder on the device (k candidates come back instead of n_vocab floats)
+    const bool dev_beam_ok = dev_any_ok && params.strategy == WHISPER_SAMPLING_BEAM_SEARCH && params.beam_search.beam_size >= 1 &&
+                             params.beam_search.beam_size * n_decoders <= SAMP_MAX_DRAWS && getenv("WB200_HOST_BEAM") == nullptr;
+    std::vector<uint32_t> mask_bits; SampReq sreq; std::vector<int> rowinfo; std::vector<double> draws;
+    if (dev_samp_ok || dev_beam_ok) {
         build_static_mask(*ctx, params, mask_bits, sreq.mask_key);
         sreq.mask_bits = &mask_bits;
         make_samp_cfg(*ctx, params, sreq.cfg);
@@ -678,9 +704,22 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 b_tok.assign(prompt.begin(), prompt.end()); b_pos.resize(np); b_seq.assign(np, 0); b_want.assign(np, 0);
                 for (int i = 0; i < np; ++i) b_pos[i] = i;
                 b_want[np - 1] = 1;
-                const bool dev_samp = dev_samp_ok && t_cur < 1e-6f;
-                for (int j = 0; j < n_cur; ++j) state->decoders[j].have_pending = false;
+                const bool dev_beam = dev_beam_ok && t_cur < 1e-6f;
+                const bool dev_samp = (dev_samp_ok && t_cur < 1e-6f) || dev_beam;
+                const int bk = params.beam_search.beam_size;
+                for (int j = 0; j < n_cur; ++j) { Decoder & d = state->decoders[j]; d.have_pending = false; d.have_pending_k = false; d.predrawn.clear(); }
+                sreq.draws = nullptr; sreq.stride = 1;
                 if (dev_samp) { rowinfo.assign((size_t) 2 * np, 0); samp_rowinfo(vocab, params, state->decoders[0], &rowinfo[2 * (np - 1)]); sreq.rowinfo = rowinfo.data(); }
+                if (dev_beam) {      // every decoder draws its k candidates from the distribution of the prompt's last row, each with its own generator (whisper.cpp:7212-7221, 7270-7290)
+                    const int nd = n_cur * bk;
+                    draws.assign((size_t) np * nd, 0.0);
+                    for (int j = 0; j < n_cur; ++j) for (int q = 0; q < bk; ++q) {
+                        const double u = std::generate_canonical<double, std::numeric_limits<double>::digits>(state->decoders[j].rng);
+                        draws[(size_t) (np - 1) * nd + j * bk + q] = u; state->decoders[j].predrawn.push_back(u);
+                    }
+                    rowinfo[2 * (np - 1)] |= nd << 8;
+                    sreq.draws = draws.data(); sreq.stride = nd;
+                }
                 if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), np, dev_samp ? &sreq : nullptr)) { logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -8; }
                 if (params.abort_callback && params.abort_callback(params.abort_callback_user_data)) return -8;
 
@@ -690,8 +729,17 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                 // flagged row 0 left there -- the last single-token step of the previous window, or zeros on a fresh state (p = 1/n_vocab).
                 // row0_nosp() follows exactly that rule on both the host-logits and the device-sampler path.
                 state->no_speech_prob = row0_nosp(*ctx, *state);
-                if (!state->samp_out.empty()) {      // the device already filtered and picked
-                    state->decoders[0].pending = from_samp(state->samp_out[np - 1]);
+                if (!state->samp_out.empty() && dev_beam) {     // the device already filtered and drew: k candidates per decoder
+                    const int nd = n_cur * bk;
+                    for (int j = 0; j < n_cur; ++j) {
+                        Decoder & d = state->decoders[j];
+                        d.pending_k.clear();
+                        for (int q = 0; q < bk; ++q) d.pending_k.push_back(from_samp(state->samp_out[(size_t) (np - 1) * nd + j * bk + q]));
+                        d.have_pending_k = true; d.predrawn.clear();
+                        if (j > 0) state->kv.seq_cp(0, j, -1, -1);
+                    }
+                } else if (!state->samp_out.empty()) {      // the device already filtered and picked
+                    state->decoders[0].pending = from_samp(state->samp_out[(size_t) (np - 1) * state->samp_stride]);
                     state->decoders[0].have_pending = true;
                 }
                 if (state->samp_out.empty()) {
@@ -724,7 +772,11 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                                 else d.sequence.tokens.push_back(sample_token(*ctx, d, t_cur < 1e-6f));
                                 d.sequence.sum_logprobs_all += d.sequence.tokens.back().plog;
                             } else {
-                                const auto toks = sample_token_topk(*ctx, d, params.beam_search.beam_size);
+                                std::vector<whisper_token_data> toks;
+                                if (d.have_pending_k) { toks.swap(d.pending_k); d.have_pending_k = false; }
+                                else if ((int) d.predrawn.size() >= params.beam_search.beam_size) toks = sample_token_topk_u(*ctx, d, params.beam_search.beam_size, d.predrawn.data());
+                                else toks = sample_token_topk(*ctx, d, params.beam_search.beam_size);
+                                d.predrawn.clear();
                                 for (const auto & tk : toks) {
                                     bc_per_dec[j].push_back({ j, d.seek_delta, d.has_ts, d.sequence, d.grammar });
                                     bc_per_dec[j].back().sequence.tokens.push_back(tk);
@@ -804,11 +856,28 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         d.i_batch = (int) b_tok.size();
                         b_tok.push_back(d.sequence.tokens.back().id); b_pos.push_back(n_past); b_seq.push_back(j); b_want.push_back(1);
                     }
-                    const bool dev_samp = dev_samp_ok && t_cur < 1e-6f;
+                    const bool dev_beam = dev_beam_ok && t_cur < 1e-6f && i + 1 < n_max;      // (after the last step nothing is sampled from these logits)
+                    const bool dev_samp = (dev_samp_ok && t_cur < 1e-6f) || dev_beam;
+                    const int bk = params.beam_search.beam_size;
+                    sreq.draws = nullptr; sreq.stride = 1;
                     if (dev_samp) {
                         rowinfo.assign(2 * b_tok.size(), 0);
                         for (int j = 0; j < n_cur; ++j) { const Decoder & d = state->decoders[j]; if (!(d.failed || d.completed)) samp_rowinfo(vocab, params, d, &rowinfo[2 * d.i_batch]); }
                         sreq.rowinfo = rowinfo.data();
+                    }
+                    if (dev_beam) {
+                        draws.assign(b_tok.size() * (size_t) bk, 0.0);
+                        for (int j = 0; j < n_cur; ++j) {
+                            Decoder & d = state->decoders[j];
+                            if (d.failed || d.completed) continue;
+                            d.predrawn.clear();
+                            for (int q = 0; q < bk; ++q) {
+                                const double u = std::generate_canonical<double, std::numeric_limits<double>::digits>(d.rng);
+                                draws[(size_t) d.i_batch * bk + q] = u; d.predrawn.push_back(u);
+                            }
+                            rowinfo[2 * d.i_batch] |= bk << 8;
+                        }
+                        sreq.draws = draws.data(); sreq.stride = bk;
                     }
                     if (!decode_batch(*ctx, *state, b_tok.data(), b_pos.data(), b_seq.data(), b_want.data(), (int) b_tok.size(), dev_samp ? &sreq : nullptr)) {
                         logf(LOG_ERROR, "%s: failed to decode\n", __func__); return -9;
@@ -818,7 +887,11 @@ WB_EXPORT int whisper_full_with_state(struct whisper_context * ctx, struct whisp
                         for (int j = 0; j < n_cur; ++j) {
                             Decoder & d = state->decoders[j];
                             if (d.failed || d.completed) continue;
-                            d.pending = from_samp(state->samp_out[d.i_batch]); d.have_pending = true;
+                            if (dev_beam) {
+                                d.pending_k.clear();
+                                for (int q = 0; q < bk; ++q) d.pending_k.push_back(from_samp(state->samp_out[(size_t) d.i_batch * state->samp_stride + q]));
+                                d.have_pending_k = true; d.predrawn.clear();
+                            } else { d.pending = from_samp(state->samp_out[(size_t) d.i_batch * state->samp_stride]); d.have_pending = true; }
                         }
                         continue;
                     }
@@ -1261,8 +1334,9 @@ WB_EXPORT int wb200_dbg_process_logits_grammar(const char * model_path, const st
 
 // Host-only: the k beam-search candidates (sample_token_topk) for the same inputs, decoder.rng = std::mt19937(seed)
 WB_EXPORT int wb200_dbg_sample_topk(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
-                                    int n_history, int has_ts, int seek_delta, float temperature, const float * logits_in, int k, int seed,
+                                    int n_history, int has_ts, int seek_delta, float temperature, const float * logits_in, int k_in, int seed,
                                     whisper_token_data * out) {
+    const int k = k_in < 0 ? -k_in : k_in;                                    // k < 0: uniforms drawn first, then sample_token_topk_u
     if (!model_path || !params || !logits_in || !out || k <= 0) return -1;
     whisper_context * pc = dbg_vocab_ctx(model_path);
     if (!pc) return -1;
@@ -1274,8 +1348,47 @@ WB_EXPORT int wb200_dbg_sample_topk(const char * model_path, const struct whispe
     st.logits.assign(logits_in, logits_in + ctx.vocab.n_vocab);
     process_logits(ctx, st, dec, *params, temperature);
     dec.rng = std::mt19937(seed);
+    if (k_in < 0) {                                                           // the path whisper_full takes when the uniforms were drawn ahead of the decode
+        std::vector<double> u((size_t) k);
+        for (double & v : u) v = std::generate_canonical<double, std::numeric_limits<double>::digits>(dec.rng);
+        const auto r = sample_token_topk_u(ctx, dec, k, u.data());
+        for (int i = 0; i < k; ++i) out[i] = r[i];
+        return 0;
+    }
     const auto r = sample_token_topk(ctx, dec, k);
     for (int i = 0; i < k; ++i) out[i] = r[i];
+    return 0;
+}
+
+// The ON-DEVICE filter + k categorical draws (k_greedy_sample with draws) on injected logits, uniforms from std::mt19937(seed) as in
+// whisper_full's beam search.  Needs a CUDA device.
+WB_EXPORT int wb200_dbg_draw_sample(const char * model_path, const struct whisper_full_params * params, const whisper_token * history,
+                                    int n_history, int has_ts, int seek_delta, const float * logits_in, int k, int seed, whisper_token_data * out) {
+    if (!model_path || !params || !logits_in || !out || k <= 0 || k > SAMP_MAX_DRAWS) return -1;
+    whisper_context * pc = dbg_vocab_ctx(model_path);
+    if (!pc) return -1;
+    whisper_context & ctx = *pc;
+    const int n = ctx.vocab.n_vocab;
+    Decoder dec;
+    for (int i = 0; i < n_history; ++i) { whisper_token_data td = blank_token(); td.id = history[i]; dec.sequence.tokens.push_back(td); }
+    dec.has_ts = has_ts != 0; dec.seek_delta = seek_delta;
+    std::vector<uint32_t> bits; uint64_t key = 0;
+    build_static_mask(ctx, *params, bits, key);
+    SampCfg cfg; make_samp_cfg(ctx, *params, cfg);
+    int rowinfo[2]; samp_rowinfo(ctx.vocab, *params, dec, rowinfo);
+    rowinfo[0] |= k << 8;
+    std::mt19937 rng(seed);
+    std::vector<double> u((size_t) k);
+    for (double & v : u) v = std::generate_canonical<double, std::numeric_limits<double>::digits>(rng);
+    DevBuf<float> dl; DevBuf<uint32_t> dm; DevBuf<int> dr; DevBuf<SampOut> dout; DevBuf<double> du;
+    if (!dl.alloc(n) || !dm.alloc(bits.size()) || !dr.alloc(2) || !dout.alloc(k) || !du.alloc(k)) return -2;
+    std::vector<SampOut> o((size_t) k);
+    if (cudaMemcpy(dl.p, logits_in, (size_t) n * 4, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dm.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dr.p, rowinfo, sizeof(rowinfo), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(du.p, u.data(), (size_t) k * 8, cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    cfg.mask = dm.p;
+    greedy_sample(dl.p, n, 1, dr.p, cfg, dout.p, nullptr, du.p, k);
+    if (cudaMemcpy(o.data(), dout.p, (size_t) k * sizeof(SampOut), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    for (int i = 0; i < k; ++i) out[i] = from_samp(o[i]);
     return 0;
 }
 

@@ -1149,10 +1149,12 @@ __device__ __forceinline__ PI block_best(PI v, PI * scratch) {
 }
 
 __global__ void __launch_bounds__(1024)
-k_greedy_sample(const float * __restrict__ logits, int V, const int * __restrict__ rowinfo, const SampK c, SampOut * __restrict__ out) {
+k_greedy_sample(const float * __restrict__ logits, int V, const int * __restrict__ rowinfo, const SampK c, SampOut * __restrict__ out,
+                const double * __restrict__ draws, int stride) {
     extern __shared__ uint32_t smask[];
     __shared__ float red[32];
     __shared__ PI redpi[32];
+    __shared__ SampOut srow;
     const int row = blockIdx.x, tid = threadIdx.x;
     const float * l = logits + (int64_t) row * V;
     const int flags = rowinfo[2 * row], tid0 = rowinfo[2 * row + 1];
@@ -1204,14 +1206,76 @@ k_greedy_sample(const float * __restrict__ logits, int V, const int * __restrict
         if (o.id >= c.beg) { o.tid = o.id; o.pt = o.p; }
         o.nosp_raw = expf(l[c.nosp] - (::logf(raw_sum) + raw_max));
         o.raw_max = raw_max; o.raw_sum = raw_sum; o.raw_nosp = l[c.nosp];
-        out[row] = o;
+        out[(int64_t) row * stride] = o;
+        srow = o;
+    }
+    // ---- categorical draws (whisper_sample_token_topk, src/whisper.cpp:6545-6618 = k draws of std::discrete_distribution over probs).
+    // libstdc++ normalises the probabilities by their sum (double), forms the running sums cp[i] (last one forced to 1) and returns
+    // lower_bound(cp, u) for a uniform u in [0, 1): the number of cp[i] < u.  The uniforms come from the host (the decoder's own
+    // mt19937 through std::generate_canonical<double, 53>, the same numbers the reference consumes); here every thread owns a
+    // contiguous slice of the vocabulary, the slices are chained by a scan in double, and each draw is a count.  Only the association
+    // of the double sums differs from the sequential loop (relative 1e-16: a draw changes only if u falls that close to a boundary).
+    const int nd = (flags >> 8) & 0x7f;
+    if (nd > 0) {
+        __shared__ double sc[1024];
+        __shared__ int scnt[64];
+        const int S = (V + blockDim.x - 1) / blockDim.x, i0 = tid * S, i1 = min(V, i0 + S);
+        auto prob = [&](int i) -> float { return (samp_masked(c, smask, i, flags, tid0) || (text_off && i < c.beg)) ? 0.0f : expf(l[i] - lse); };
+        double ls = 0.0;
+        for (int i = i0; i < i1; ++i) ls += (double) prob(i);
+        __syncthreads();
+        sc[tid] = ls;
+        __syncthreads();
+        for (int o = blockDim.x >> 1; o > 0; o >>= 1) { if (tid < o) sc[tid] += sc[tid + o]; __syncthreads(); }
+        const double total = sc[0];
+        __syncthreads();
+        double ln = 0.0;
+        for (int i = i0; i < i1; ++i) ln += (double) prob(i) / total;
+        sc[tid] = ln;
+        __syncthreads();
+        for (int o = 1; o < (int) blockDim.x; o <<= 1) {           // inclusive scan (Hillis-Steele)
+            const double add = tid >= o ? sc[tid - o] : 0.0;
+            __syncthreads();
+            sc[tid] += add;
+            __syncthreads();
+        }
+        const double base = sc[tid] - ln;
+        for (int q0 = 0; q0 < nd; q0 += 8) {
+            if (tid < 64) scnt[tid] = 0;
+            __syncthreads();
+            double u[8]; int cnt[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { u[q] = (q0 + q < nd) ? draws[(int64_t) row * stride + q0 + q] : -1.0; cnt[q] = 0; }
+            double run = base;
+            for (int i = i0; i < i1; ++i) {
+                run += (double) prob(i) / total;
+                if (i != V - 1) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cnt[q] += (run < u[q]) ? 1 : 0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (cnt[q]) atomicAdd(&scnt[q], cnt[q]);
+            __syncthreads();
+            if (tid < 8 && q0 + tid < nd) {
+                const int id = min(scnt[tid], V - 1);
+                SampOut o = srow;                                        // row-level fields (written by thread 0 before the barriers above)
+                o.id = id; o.p = prob(id); o.plog = l[id] - lse;
+                o.tid = best_ts.p > 0.0f ? best_ts.i : c.beg;           // timestamp_stats starts from tid = token_beg in the top-k sampler
+                o.pt = (float) ((double) (best_ts.p > 0.0f ? best_ts.p : 0.0f) / ((double) sts + 1e-10));
+                o.ptsum = sts;
+                if (o.id >= c.beg) { o.tid = o.id; o.pt = o.p; }
+                out[(int64_t) row * stride + q0 + tid] = o;
+            }
+            __syncthreads();
+        }
     }
 }
-void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st) {
+void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st, const double * draws, int stride) {
     SampK c; c.mask = cfg.mask; c.eot = cfg.token_eot; c.beg = cfg.token_beg; c.nosp = cfg.token_nosp; c.space = cfg.space_id;
     c.suppress_blank = cfg.suppress_blank; c.no_ts = cfg.no_timestamps; c.max_init = cfg.max_initial_tid;
     const size_t smem = (size_t) ((V + 31) / 32) * 4;
-    k_greedy_sample<<<n, 1024, smem, st>>>(logits, V, rowinfo, c, out); count_launch();
+    k_greedy_sample<<<n, 1024, smem, st>>>(logits, V, rowinfo, c, out, draws, stride < 1 ? 1 : stride); count_launch();
 }
 
 } // namespace wb

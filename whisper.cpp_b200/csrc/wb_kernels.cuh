@@ -83,7 +83,11 @@ struct SampCfg {                 // uniform for all rows of a pass
 struct SampOut { int id, tid; float p, plog, pt, ptsum, nosp_raw;
                  float raw_max, raw_sum, raw_nosp; };    // unfiltered row: max logit, sum of exp(l - max), logit of the no-speech token
 // rowinfo[2*r] flags: bit0 is_initial, bit1 last token was a timestamp, bit2 penultimate was (or < 2 tokens), bit3 has_ts,
-// bit4 text tokens disabled by max_tokens; rowinfo[2*r+1] = seek_delta/2.  logits: [n][V] f32 on device (not modified).
-void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st);
+// bit4 text tokens disabled by max_tokens, bits 8-14: number of categorical draws wanted for the row (beam search: whisper_sample_token_topk,
+// src/whisper.cpp:6545-6618; 0 = greedy pick only); rowinfo[2*r+1] = seek_delta/2.  logits: [n][V] f32 on device (not modified).
+// out: [n][stride] (entry 0 of a row: the greedy pick, or draw 0 when draws are wanted); draws: [n][stride] uniforms in [0, 1) from the host.
+void greedy_sample(const float * logits, int V, int n, const int * rowinfo, const SampCfg & cfg, SampOut * out, cudaStream_t st,
+                   const double * draws = nullptr, int stride = 1);
+constexpr int SAMP_MAX_DRAWS = 64;
 
 } // namespace wb

@@ -50,6 +50,12 @@ struct Decoder {
     Grammar grammar;                           // GBNF parse state of the tokens generated so far (params.grammar_rules)
     bool have_pending = false;                 // next token already chosen by the on-device sampler
     whisper_token_data pending;
+    // beam search: the k categorical draws of the next step.  The uniforms are taken from `rng` when the decode is submitted (the same
+    // numbers the reference consumes when it samples from those logits); the device returns the drawn tokens (pending_k), or -- when the
+    // pass had to return full logits -- the host sampler uses the same uniforms (predrawn).
+    bool have_pending_k = false;
+    std::vector<whisper_token_data> pending_k;
+    std::vector<double> predrawn;
 };
 
 struct Group;
@@ -82,7 +88,8 @@ struct whisper_state {
     int kv_self_n_dec = 1;
     wb::Decoder decoders[wb::MAX_DECODERS];
     std::vector<float> logits;                 // [n_tokens][n_vocab] of the last decode (rows flagged want_logits are valid)
-    std::vector<wb::SampOut> samp_out;         // per row of the last decode when the on-device sampler was used
+    std::vector<wb::SampOut> samp_out;         // per row of the last decode when the on-device sampler was used: [rows][samp_stride]
+    int samp_stride = 1;
     // What whisper.cpp:7190-7200 reads for the no-speech probability: ROW 0 of the logits buffer, log-sum-exp'ed against the maximum of
     // the WHOLE buffer (whisper_compute_logprobs takes max_element over all n_tokens rows, whisper.cpp:6160).  A decode resizes that
     // buffer to n_tokens rows (new rows are zero-filled) and refreshes only the rows it was asked logits for (whisper.cpp:2957-2963), so
@@ -149,7 +156,8 @@ namespace wb {
 // as a single batched device pass: one batched encoder pass for all windows, one decode launch for all live sequences (weights are read
 // once per step).  A state that runs alone gets a 1-row pass immediately.
 // request for the on-device logits filter + greedy pick of the rows of one decode call
-struct SampReq { SampCfg cfg; uint64_t mask_key = 0; const std::vector<uint32_t> * mask_bits = nullptr; const int * rowinfo = nullptr; };
+struct SampReq { SampCfg cfg; uint64_t mask_key = 0; const std::vector<uint32_t> * mask_bits = nullptr; const int * rowinfo = nullptr;
+                 const double * draws = nullptr; int stride = 1; };   // beam search: [n_rows][stride] uniforms for the categorical draws; samp_out then holds `stride` entries per row
 
 struct Group {
     Engine eng;
