@@ -424,6 +424,11 @@ WB_EXPORT int wb200_full_batch_ex(struct whisper_context * ctx, struct whisper_f
                                   struct whisper_state ** states_out, int flags);
 /* the default state owned by a context created with a *_with_params (non-_no_state) call; NULL otherwise */
 WB_EXPORT struct whisper_state * wb200_ctx_state(struct whisper_context * ctx);
+/* Decode with the self-attention KV cells spelled out by the caller (entry point of the ggml-backend plugin, plugin/ggml_b200_backend.cpp):
+ * row j is stored in cell cells[j] of the state's range and attends to the cells idx[j*ld .. j*ld + nkv[j]); this is the information
+ * whisper_build_graph_decoder puts into kv_head and KQ_mask (reference src/whisper.cpp:2580-2599, 2928-2938).  logits: [n_tokens][n_vocab]. */
+WB_EXPORT int wb200_decode_explicit(struct whisper_context * ctx, struct whisper_state * state, const whisper_token * tokens, const int * pos, int n_tokens,
+                                    const int * cells, const int * idx, int ld, const int * nkv, int n_cells_needed, float * logits);
 /* In-library multi-GPU (environment WB200_DEVICES = "all" | "0,1,.." at whisper_init_from_file*): number of GPUs that hold a replica of
    the weights, and the GPU a state was placed on by whisper_init_state (the one with the fewest states). */
 WB_EXPORT int wb200_n_devices(struct whisper_context * ctx);

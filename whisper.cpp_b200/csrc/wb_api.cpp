@@ -415,6 +415,15 @@ void Group::run(std::vector<Req *> & batch) {
         bool ok = true; int total = 0, ld = 1;
         for (size_t i = 0; i < dec.size(); ++i) {
             Req * q = dec[i];
+            if (q->x_cells) {                                          // explicit cells (ggml-backend plugin): no bookkeeping on this side
+                PreparedDecode & P = preps[i];
+                P.ld = q->x_ld; P.rows.resize(q->n); P.cells.resize(q->n); P.nkv.assign(q->x_nkv, q->x_nkv + q->n); P.idx.assign((size_t) q->n * q->x_ld, 0);
+                for (int j = 0; j < q->n; ++j) {
+                    P.rows[j] = { q->tokens[j], q->pos[j], 0, q->st->slot, q->want[j] != 0 };
+                    P.cells[j] = q->st->cell_off + q->x_cells[j];
+                    for (int c = 0; c < q->x_nkv[j]; ++c) P.idx[(size_t) j * q->x_ld + c] = q->st->cell_off + q->x_idx[(size_t) j * q->x_ld + c];
+                }
+            } else
             ok &= prepare_decode(*q->st, q->tokens, q->pos, q->seq, q->want, q->n, preps[i]);
             total += q->n; ld = std::max(ld, preps[i].ld);
         }
@@ -731,6 +740,23 @@ WB_EXPORT int whisper_decode_with_state(struct whisper_context * ctx, struct whi
     GroupCall gc(st);
     st->kv.seq_rm(0, n_past, -1);
     if (!decode_batch(*ctx, *st, tokens, pos.data(), seq.data(), want.data(), n_tokens)) { logf(LOG_ERROR, "%s: failed to eval\n", __func__); return 1; }
+    return 0;
+}
+// Decode with the self-KV cells spelled out by the caller: row j is written to cell cells[j] of the state's range and attends to
+// idx[j*ld .. j*ld + nkv[j]) (whisper_build_graph_decoder's kv_head and KQ_mask, src/whisper.cpp:2580-2599, 2928-2938).  Entry point of the
+// ggml-backend plugin (plugin/ggml_b200_backend.cpp), whose host keeps the whisper_kv_cache bookkeeping itself.  logits: [n_tokens][n_vocab].
+WB_EXPORT int wb200_decode_explicit(struct whisper_context * ctx, struct whisper_state * st, const whisper_token * tokens, const int * pos, int n_tokens,
+                                    const int * cells, const int * idx, int ld, const int * nkv, int n_cells_needed, float * logits) {
+    if (!ctx || !st || !tokens || !pos || !cells || !idx || !nkv || n_tokens <= 0 || !st->group) return 1;
+    GroupCall gc(st);
+    if (st->kv_self_n_dec < 0 || (int) st->kv.size < n_cells_needed) {
+        if (!st->group->ensure_cells(st, n_cells_needed)) { logf(LOG_ERROR, "%s: KV cache allocation failed: %s\n", __func__, last_error()); return 1; }
+    }
+    std::vector<int8_t> want((size_t) n_tokens, 1);
+    Group::Req r; r.kind = 1; r.ctx = ctx; r.st = st; r.tokens = tokens; r.pos = pos; r.seq = nullptr; r.want = want.data(); r.n = n_tokens;
+    r.x_cells = cells; r.x_idx = idx; r.x_nkv = nkv; r.x_ld = ld;
+    if (!st->group->submit(r)) { logf(LOG_ERROR, "%s: failed to eval: %s\n", __func__, last_error()); return 1; }
+    if (logits) memcpy(logits, st->logits.data(), (size_t) n_tokens * ctx->model.hp.n_vocab * sizeof(float));
     return 0;
 }
 WB_EXPORT int whisper_decode(struct whisper_context * ctx, const whisper_token * tokens, int n_tokens, int n_past, int n_threads) {

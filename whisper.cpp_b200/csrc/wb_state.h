@@ -184,6 +184,7 @@ struct Group {
         int seek = 0, n_ctx = 0;                // encode
         const int * tokens = nullptr, * pos = nullptr, * seq = nullptr; const int8_t * want = nullptr; int n = 0;   // decode
         const SampReq * samp = nullptr;
+        const int * x_cells = nullptr, * x_idx = nullptr, * x_nkv = nullptr; int x_ld = 0;   // explicit self-KV cells / attended lists (relative to the state's range) instead of the KvCells bookkeeping: the ggml-backend plugin passes what the host's KQ_mask says
         bool taken = false;                      // (under mu) some thread took the batch that contains this request
         std::atomic<int> done{0};                // futex word: the member sleeps on its OWN request (no shared mutex to re-acquire on wake-up)
         bool ok = false; int64_t dt_us = 0;
