@@ -82,3 +82,19 @@ def test_reference_cli_on_the_plugin_matches_its_cpu_run(tmp_path, wt, seed, con
         assert cd >= 8
         if conditioned and wt == F16:
             assert td == tg
+
+
+def test_two_host_states_get_two_engine_states(tmp_path):
+    """whisper-cli -p 2 = whisper_full_parallel of the reference: two host states, each with its own kv_cross / kv_self tensors, decode
+    concurrently; the plugin keeps one engine state per host state (keyed by the kv_cross tensor) and the result is the one of the same
+    split on the CPU backend."""
+    if not (os.path.exists(CLI) and os.path.exists(PLUGIN)):
+        pytest.skip("oracle/_ref/whisper-cli-ref or libggml-b200.so not built")
+    model = str(tmp_path / "m.bin")
+    synth.write_model(model, "test-3l.en", F16, seed=3, vocab_from=STUB, scale=lambda n: synth.conditioned(n, 1e-3, 100.0))
+    cpu, _ = _run(model, tmp_path, "cpu2", False, extra=("-p", "2"))
+    gpu, err = _run(model, tmp_path, "b2002", True, extra=("-p", "2"))
+    assert "engine state 2" in err, err[-1500:]
+    tc = [t for s in cpu for t in s[1]]; tg = [t for s in gpu for t in s[1]]
+    print("-p 2: plugin %d tokens in %d segments, CPU %d tokens in %d segments" % (len(tg), len(gpu), len(tc), len(cpu)))
+    assert tg == tc and [s[0] for s in gpu] == [s[0] for s in cpu]

@@ -61,6 +61,23 @@ __device__ __forceinline__ void l2_prefetch(const void * p, uint32_t bytes) {
 // (each on its own 128-byte line), and every other CTA polls only its own flag.
 __device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long target) {
     __syncthreads();
+    if (a.prefetch & 32) {
+        // variant: arrival = a reduction without a return value, and EVERY CTA polls the counter itself -- no dependent chain
+        // "atomic returns -> last arriver writes the flags -> the flags become visible" (one L2 round trip less per barrier)
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(a.bar) : "memory");
+            const long long t0 = clock64();
+            unsigned long long v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.bar) : "memory");
+                if (v >= target) break;
+                if (clock64() - t0 > (6LL << 30)) { *a.err = 1; __threadfence_system(); __trap(); }
+            }
+        }
+        __syncthreads();
+        return;
+    }
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(a.bar, 1ULL);
@@ -69,8 +86,8 @@ __device__ __noinline__ void mk_grid_sync(const MkArgs & a, unsigned long long t
     }
     __syncthreads();
     if (SM_FLAG[2]) {
-        if (threadIdx.x < gridDim.x)
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 + 16 * threadIdx.x), "l"(target) : "memory");
+        for (int i = threadIdx.x; i < (int) gridDim.x; i += MK_THREADS)
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(a.bar + 16 + 16 * i), "l"(target) : "memory");
     } else if (threadIdx.x == 0) {
         const unsigned long long * f = a.bar + 16 + 16 * blockIdx.x;
         const long long t0 = clock64();

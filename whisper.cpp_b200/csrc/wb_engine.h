@@ -76,7 +76,7 @@ struct Engine {
     bool dtw_finish(const std::vector<std::pair<int, int>> & heads, int slot, int n_audio_ctx, std::vector<float> & qk);
     bool use_mk = false;
     int  max_rows = 8;               // rows per decode pass: 64 with the persistent kernel, 8 with the chain
-    int  n_sm = 0, mk_prefetch = 29;     // bit0: next-phase weights -> L2; bit2: K / V streams with L2 evict-first priority; bit3 (generation 2): row groups take turns in the cross-attention; bit4: logits one warp per weight tile
+    int  n_sm = 0, mk_prefetch = 61;     // bit0: next-phase weights -> L2; bit2: K / V streams with L2 evict-first priority; bit3 (generation 2): row groups take turns in the cross-attention; bit4: logits one warp per weight tile
     DevBuf<MkLayer> mk_layers;
     DevBuf<unsigned long long> mk_bar;   // [0] arrival counter, [8] error flag, [16 + 16*cta] release flags
     unsigned long long mk_bar_total = 0;
