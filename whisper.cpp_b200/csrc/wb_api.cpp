@@ -749,7 +749,7 @@ WB_EXPORT int wb200_decode_explicit(struct whisper_context * ctx, struct whisper
                                     const int * cells, const int * idx, int ld, const int * nkv, int n_cells_needed, float * logits) {
     if (!ctx || !st || !tokens || !pos || !cells || !idx || !nkv || n_tokens <= 0 || !st->group) return 1;
     GroupCall gc(st);
-    if (st->kv_self_n_dec < 0 || (int) st->kv.size < n_cells_needed) {
+    if ((int) st->kv.size < n_cells_needed) {                                  // the host's kv_self is larger than this state's cell range so far
         if (!st->group->ensure_cells(st, n_cells_needed)) { logf(LOG_ERROR, "%s: KV cache allocation failed: %s\n", __func__, last_error()); return 1; }
     }
     std::vector<int8_t> want((size_t) n_tokens, 1);
