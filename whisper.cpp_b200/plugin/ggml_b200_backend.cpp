@@ -20,6 +20,9 @@
 // plugin finds among the host's open file descriptors while the host is loading it (or WB200_PLUGIN_MODEL=<path>).
 // libwhisper_b200.so exports the same whisper_* names as the host's own libwhisper, so it is opened with RTLD_LOCAL | RTLD_DEEPBIND and
 // called through function pointers only.
+// Not supported through this seam (the graphs are not executed node by node): a reduced audio_ctx, DTW token timestamps (the decoder
+// graph's aheads_cross_QKs output is not produced; they need flash_attn = false anyway), the VAD graph (runs on the host's CPU backend:
+// whisper_vad builds its own scheduler), models given as memory buffers unless WB200_PLUGIN_MODEL names the file.
 #include <dlfcn.h>
 #include <dirent.h>
 #include <unistd.h>
@@ -54,6 +57,7 @@ struct Api {                                  // libwhisper_b200.so, through dls
     int (*n_vocab)(whisper_context *) = nullptr;
     int (*n_text_state)(whisper_context *) = nullptr;
     int (*n_text_layer)(whisper_context *) = nullptr;
+    int (*n_audio_ctx)(whisper_context *) = nullptr;
     int (*decode_explicit)(whisper_context *, whisper_state *, const whisper_token *, const int *, int, const int *, const int *, int, const int *, int, float *) = nullptr;
     const char * (*last_error)() = nullptr;
 };
@@ -92,6 +96,7 @@ bool load_api() {
     SYM(n_vocab, "whisper_model_n_vocab")
     SYM(n_text_state, "whisper_model_n_text_state")
     SYM(n_text_layer, "whisper_model_n_text_layer")
+    SYM(n_audio_ctx, "whisper_model_n_audio_ctx")
     SYM(decode_explicit, "wb200_decode_explicit")
     SYM(last_error, "wb200_last_error")
 #undef SYM
@@ -254,6 +259,9 @@ ggml_status compute_cross(const ggml_cgraph * gr) {
             g.state_of_cross[kc] = st;
             PLOG("engine state %zu for host kv_cross %p", g.state_of_cross.size(), (const void *) kc);
         } else st = is->second;
+    }
+    if (shape.first != 2 * g.api.n_audio_ctx(g.ctx)) {          // whisper_full_params.audio_ctx / whisper_set_audio_ctx: the engine state would need the same override
+        fprintf(stderr, "ggml-b200: mel window of %d frames: a reduced audio_ctx is not supported through the plugin\n", shape.first); return GGML_STATUS_FAILED;
     }
     // the window of the host (already cut out of the clip and zero-padded, src/whisper.cpp:2389-2411) becomes the engine state's whole mel
     if (g.api.set_mel_with_state(g.ctx, st, mel.data(), shape.first, shape.second) != 0 || g.api.encode_with_state(g.ctx, st, 0, 1) != 0) {
