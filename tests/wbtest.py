@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(ROOT, "whisper.cpp_b200", "libwhisper_b200.so")
+LIB_PATH = os.environ.get("WB200_LIB") or os.path.join(ROOT, "whisper.cpp_b200", "libwhisper_b200.so")      # WB200_LIB: instrumented / A-B builds (scripts/sanitize_host.sh)
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libwhisper_ref.so")
 
 # ggml_type ids (ggml/include/ggml.h:390-405)
