@@ -22,7 +22,8 @@
 // called through function pointers only.
 // Not supported through this seam (the graphs are not executed node by node): a reduced audio_ctx, DTW token timestamps (the decoder
 // graph's aheads_cross_QKs output is not produced; they need flash_attn = false anyway), the VAD graph (runs on the host's CPU backend:
-// whisper_vad builds its own scheduler), models given as memory buffers unless WB200_PLUGIN_MODEL names the file.
+// whisper_vad builds its own scheduler), models given as memory buffers unless WB200_PLUGIN_MODEL names the file, and more than ONE
+// whisper model per process (the engine context is created once, from the first model file seen).
 #include <dlfcn.h>
 #include <dirent.h>
 #include <unistd.h>
